@@ -1,0 +1,241 @@
+/*
+ * bithtm_b200 -- C ABI of the B200 (sm_100a) implementation of the bitHTM
+ * spatial-pooler + temporal-memory timestep.
+ *
+ * The reference (cokwa/bitHTM) has NO FFI: its plugin boundary is duck-typed
+ * Python constructor injection (bithtm/networks.py:14-24, 48-55, 132-144).  The
+ * entry points below are what a ctypes binding of that boundary calls; each one
+ * cites the reference method it replaces.  The Python classes in
+ * bithtm_b200/{networks,projections,regularizations}.py are that binding.
+ *
+ * Conventions
+ *  - The library is STATELESS: every call takes a `bh_ctx` (plain struct of
+ *    sizes, constants and DEVICE pointers owned by the caller).  Nothing is
+ *    allocated per call.  `bh_layout` tells the caller how to carve one arena.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    returns 0 or a negative error (-cudaError or BH_E_*), never throws.
+ *  - Capacity overflows (segments, synapses/segment, matching list, random
+ *    buffer) are recorded in the device status word sc[BH_SC_STATUS] and
+ *    checked lazily by the caller.
+ *  - No CPU fallback exists: without a CUDA device every compute call fails.
+ */
+#ifndef BITHTM_B200_H
+#define BITHTM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BH_ABI_VERSION 1
+#define BH_MT_N 624
+
+/* error codes (negative); CUDA errors are returned as -(1000 + cudaError_t) */
+#define BH_E_BADARG (-1)
+#define BH_E_NODEVICE (-2)
+#define BH_E_UNSUPPORTED (-3)
+
+/* device scalar block: int32 sc[BH_SC_COUNT] */
+enum {
+  BH_SC_STEP = 0,      /* timesteps completed; parity selects ping-pong buffers   */
+  BH_SC_HAVE_PREV,     /* 0 until the first activation (prev distal state None)    */
+  BH_SC_NSEG,          /* segments allocated (reference: len(segment_bundle))      */
+  BH_SC_NSEG_NEXT,     /* staged by learn-select, committed before learn-apply     */
+  BH_SC_M,             /* matching segments of the last activation                 */
+  BH_SC_W0,            /* winner-cell count, buffer 0                              */
+  BH_SC_W1,            /* winner-cell count, buffer 1                              */
+  BH_SC_L0,            /* learning segments chosen among matching ones             */
+  BH_SC_L,             /* rows of the learning list (L0 + recycled + new)          */
+  BH_SC_P,             /* punished segments                                        */
+  BH_SC_NU,            /* winners with no matching segment (unaccounted)           */
+  BH_SC_NR,            /* recycled segments this step                              */
+  BH_SC_STATUS,        /* BH_ST_* bits                                             */
+  BH_SC_MT_POS,        /* MT19937 position inside mt_key (0..624)                  */
+  BH_SC_RAND_FILL,     /* doubles currently in rand_buf for this step              */
+  BH_SC_OFF2,          /* offset of draw #2 (rand(L, W+1)) in rand_buf             */
+  BH_SC_OFF3,          /* offset of draw #3 (rand(M)) in rand_buf                  */
+  BH_SC_INPUT_POS,     /* cursor into the device input ring (bh_step_ring)         */
+  BH_SC_COUNT = 32
+};
+
+/* status bits */
+#define BH_ST_SEG_OVERFLOW 1   /* more segments than seg_capacity                  */
+#define BH_ST_SYN_OVERFLOW 2   /* a segment needed more than syn_capacity slots    */
+#define BH_ST_MATCH_OVERFLOW 4 /* more matching segments than match_capacity       */
+#define BH_ST_LEARN_OVERFLOW 8 /* more learning rows than learn_capacity           */
+#define BH_ST_RAND_OVERFLOW 16 /* a step drew more uniforms than rand_capacity     */
+#define BH_ST_PRI_TIE 32       /* equal priorities straddled a growth cut (the     */
+                               /* reference's np.argsort is undefined there)       */
+
+typedef struct bh_ctx {
+  /* ---- sizes --------------------------------------------------------------- */
+  int32_t input_dim;       /* I                                                    */
+  int32_t input_words;     /* ceil(I / 32)                                         */
+  int32_t mask_stride;     /* uint32 words per connected-mask row, multiple of 4   */
+  int32_t column_dim;      /* C                                                    */
+  int32_t cell_dim;        /* c, 1..32                                             */
+  int32_t active_columns;  /* k                                                    */
+  int32_t seg_capacity;    /* S_cap                                                */
+  int32_t syn_capacity;    /* E_cap: synapse slots per segment, multiple of 32     */
+  int32_t match_capacity;  /* M_cap                                                */
+  int32_t learn_capacity;  /* L_cap                                                */
+  int32_t tm_blocks;       /* NB: CTAs of the ranged TM kernels (<= 1024)          */
+  int32_t sm_count;        /* SMs of the device (grid sizing)                      */
+  int64_t rand_capacity;   /* doubles in rand_buf                                  */
+  int32_t ring_len;        /* rows in input_ring (0 = none)                        */
+  int32_t reserved0;
+
+  /* ---- constants, evaluated on the host with the reference's expressions ----- */
+  double sp_threshold;     /* projections.py:19  permanence >= threshold           */
+  double sp_delta_on;      /* projections.py:24  1.0*(inc+dec)-dec                 */
+  double sp_delta_off;     /* projections.py:24  0.0*(inc+dec)-dec                 */
+  double tm_learn_on;      /* projections.py:102 True *(da-di)+di, learn           */
+  double tm_learn_off;     /*                    False*(da-di)+di, learn           */
+  double tm_punish_on;     /*                    punish                            */
+  double tm_punish_off;
+  float boost_coef;        /* regularizations.py:16  f32(-(intensity/density))     */
+  float duty_momentum;     /* regularizations.py:20  f32(momentum)                 */
+  float duty_increment;    /* regularizations.py:21  f32(1.0 - momentum)           */
+  float tm_perm_initial;   /* projections.py:149 f32(0.21)                         */
+  float tm_perm_threshold; /* projections.py:171 f32(0.5)                          */
+  float epsilon;           /* networks.py:91     f32(1e-8)                         */
+  int32_t tm_learn_can_delete;  /* projections.py:105 min(da,di) < 0               */
+  int32_t tm_punish_can_delete;
+  int32_t seg_activation_threshold;
+  int32_t seg_matching_threshold;
+  int32_t seg_sampling_synapses;
+  int32_t reserved1;
+
+  /* ---- spatial pooler (DenseProjection / ExponentialBoosting / inhibition) --- */
+  double* sp_perm;         /* [C][I] float64 permanence, row-major                 */
+  uint32_t* sp_mask;       /* [C][mask_stride] connected bits (perm >= threshold)  */
+  float* duty;             /* [C]                                                  */
+  int32_t* overlaps;       /* [C]                                                  */
+  double* boosted;         /* [C]                                                  */
+  int32_t* active_cols;    /* [2][k] ping-pong by step parity, reference order     */
+  uint8_t* col_active;     /* [C] 1 for the current active columns                 */
+
+  /* ---- temporal memory: per column (bit b = cell b) and per cell ------------- */
+  uint32_t* col_pred;      /* [C] cell_prediction        networks.py:122           */
+  uint32_t* col_act;       /* [C] cell_activation        networks.py:118-119       */
+  uint32_t* col_win;       /* [C] winner cells of the current step                 */
+  int32_t* cell_nseg;      /* [N] bundle_segments        projections.py:227        */
+  float* cell_maxjit;      /* [N] max_jittered_potential projections.py:236-237    */
+  int32_t* cell_npred;     /* [N] prediction (active segments per cell)  :251      */
+  int32_t* cell_widx;      /* [N] index in the previous winner list or -1          */
+
+  /* ---- segments (rows kept compact: valid synapses are slots [0, count)) ----- */
+  int32_t* seg_owner;      /* [S_cap] segment_bundle     projections.py:226        */
+  int32_t* seg_count;      /* [S_cap] output_edges       projections.py:42         */
+  int32_t* seg_pot;        /* [S_cap] segment_potential  projections.py:246        */
+  int32_t* seg_conn;       /* [S_cap] connected-active count                       */
+  int32_t* syn_cell;       /* [S_cap][E_cap] presynaptic flat cell                 */
+  float* syn_perm;         /* [S_cap][E_cap] float32 permanence                    */
+
+  /* ---- per-step lists ---------------------------------------------------------- */
+  uint32_t* row_pred;      /* [k] prev prediction bits of each active column       */
+  uint32_t* row_act;       /* [k] active cells   (networks.py:115)                 */
+  uint32_t* row_win;       /* [k] winner cells   (networks.py:102)                 */
+  uint32_t* row_unacc;     /* [k] winners without a matching segment               */
+  int32_t* winners;        /* [2][k*c] ordered flat winner cells, ping-pong        */
+  int32_t* unacc;          /* [k*c] ordered unaccounted winners                    */
+  int32_t* m_seg;          /* [M_cap] matching_segment, ascending id               */
+  int32_t* m_conn;         /* [M_cap] matching_segment_activation                  */
+  float* m_jit;            /* [M_cap] matching_segment_jittered_potential          */
+  uint8_t* m_flag;         /* [M_cap] bit0 learn, bit1 punish                      */
+  int32_t* learn_list;     /* [L_cap] learning_segment (projections.py:281 order)  */
+  int32_t* punish_list;    /* [M_cap] punished_segment                             */
+  int32_t* blk;            /* [8][1024] per-CTA counts for ordered compaction      */
+
+  /* ---- randomness: legacy MT19937 stream of np.random, advanced on the device - */
+  uint32_t* mt_key;        /* [624]                                                */
+  double* rand_buf;        /* [rand_capacity] uniforms of the current step         */
+
+  /* ---- scalars, input ring, host staging ---------------------------------------- */
+  int32_t* sc;             /* [BH_SC_COUNT]                                        */
+  uint32_t* input_ring;    /* [ring_len][input_words] packed inputs (bh_step_ring) */
+  uint32_t* input_dev;     /* [input_words] staging for bh_step_host               */
+  uint32_t* input_pinned;  /* HOST pinned [input_words]                            */
+  int32_t* summary_dev;    /* [4 + 4k] step summary (see bh_step_host)             */
+  int32_t* summary_pinned; /* HOST pinned [4 + 4k]                                 */
+} bh_ctx;
+
+/* Arena layout: fills every DEVICE pointer of `ctx` with `base + offset`, given
+ * the sizes already set in ctx.  With base == NULL only returns the byte count.
+ * All sub-buffers are 256-byte aligned.  The caller zero-fills the arena and
+ * then calls bh_init. */
+size_t bh_layout(bh_ctx* ctx, void* base);
+
+/* Set the non-zero initial values (cell_widx = -1, ...).  Arena must be zeroed. */
+int bh_init(const bh_ctx* ctx, void* stream);
+
+int bh_abi_version(void);
+int bh_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- spatial pooler ------------------------------------------------------------- */
+/* Build the connected mask from sp_perm (after uploading the permanence drawn by
+ * DenseProjection.__init__, projections.py:16). */
+int bh_sp_build_mask(const bh_ctx* ctx, void* stream);
+/* Pack a device bool[I] (one byte per bit) into input words. */
+int bh_pack_input(const bh_ctx* ctx, const uint8_t* bool_dev, uint32_t* words_dev, void* stream);
+/* DenseProjection.process (projections.py:18-21) -> ctx->overlaps */
+int bh_sp_overlap(const bh_ctx* ctx, const uint32_t* input_words_dev, void* stream);
+/* ExponentialBoosting.process (regularizations.py:15-17) -> ctx->boosted */
+int bh_boost(const bh_ctx* ctx, void* stream);
+/* GlobalInhibition.process (regularizations.py:28-29) with the canonical rule
+ * (larger first, ties -> lower column, ascending output) -> active_cols[cur] */
+int bh_inhibit(const bh_ctx* ctx, void* stream);
+/* Host-inhibition mode: take an explicit ORDERED active_column list (device). */
+int bh_set_active_columns(const bh_ctx* ctx, const int32_t* cols_dev, void* stream);
+/* DenseProjection.update (projections.py:23-24) on active_cols[cur] */
+int bh_sp_learn(const bh_ctx* ctx, const uint32_t* input_words_dev, void* stream);
+/* ExponentialBoosting.update (regularizations.py:19-21) */
+int bh_duty_update(const bh_ctx* ctx, void* stream);
+/* SpatialPooler.process (networks.py:26-35) = the five calls above */
+int bh_sp_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, void* stream);
+
+/* ---- temporal memory -------------------------------------------------------------- */
+/* networks.py:95-104: bursting + winner cells (consumes rand(k, c)) */
+int bh_tm_select(const bh_ctx* ctx, void* stream);
+/* PredictiveProjection.update (projections.py:257-293) (consumes rand(L, W+1)) */
+int bh_tm_learn(const bh_ctx* ctx, int learning, void* stream);
+/* networks.py:115-128 + PredictiveProjection.process (projections.py:245-255)
+ * (consumes rand(M)); completes the timestep (sc[BH_SC_STEP] += 1) */
+int bh_tm_activate(const bh_ctx* ctx, void* stream);
+/* TemporalMemory.process (networks.py:91-128) = the three calls above */
+int bh_tm_step(const bh_ctx* ctx, int learning, void* stream);
+
+/* ---- whole timestep: HierarchicalTemporalMemory.process (networks.py:146-149) ------ */
+int bh_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, void* stream);
+/* Same, input taken from input_ring[sc[BH_SC_INPUT_POS]++ % ring_len] (no host
+ * involvement; CUDA-graph friendly). */
+int bh_step_ring(const bh_ctx* ctx, int learning, void* stream);
+/* End-to-end call with HOST buffers: packs `input_bool_host` (I bytes), copies it
+ * to the device, runs the step, copies the summary back and synchronises.
+ * summary_host (4 + 4k int32): [0]=step index, [1]=status, [2]=n_segments,
+ * [3]=winner count, then active_column[k], row_pred[k], row_act[k], row_win[k]. */
+int bh_step_host(const bh_ctx* ctx, const uint8_t* input_bool_host, int learning,
+                 int32_t* summary_host, void* stream);
+
+/* ---- CUDA graphs over bh_step_ring -------------------------------------------------- */
+int bh_graph_create(const bh_ctx* ctx, int steps_per_graph, int learning, void* stream, void** graph_exec_out);
+int bh_graph_launch(void* graph_exec, void* stream);
+int bh_graph_destroy(void* graph_exec);
+/* number of kernel launches one bh_step issues (for bench accounting) */
+int bh_step_launches(const bh_ctx* ctx, int learning);
+
+/* ---- randomness ------------------------------------------------------------------------ */
+/* Append `count` float64 uniforms of the MT19937 stream (np.random.random_sample)
+ * to dst_dev and advance the device state (mt_key, sc[BH_SC_MT_POS]). */
+int bh_rng_fill(const bh_ctx* ctx, double* dst_dev, int64_t count, void* stream);
+
+/* ---- test hooks ------------------------------------------------------------------------- */
+/* y[i] = NumPy's float32 SIMD exp(x[i]) (the sequence used by bh_boost). */
+int bh_test_np_expf(const float* x_dev, float* y_dev, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BITHTM_B200_H */

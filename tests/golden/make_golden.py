@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under ``tests/golden/`` from the UNMODIFIED
+reference (cokwa/bitHTM at ``/root/reference``), and check the NumPy oracle
+against it lock-step while doing so.
+
+Run in the build container only (the GPU box has no ``/root/reference``):
+
+    python tests/golden/make_golden.py            # all cases
+    python tests/golden/make_golden.py tiny mid   # selected cases
+
+For every case the reference network is built with a deterministic inhibition
+object injected through the reference's own ``inhibition=`` constructor slot
+(``bithtm/networks.py:16,24``) -- everything else is the
+reference's stock code path.  Inputs come from a private ``default_rng`` so the
+legacy global ``np.random`` stream is consumed only by the network.
+
+Outputs ``<case>.npz``: per-step 8-byte digests (``oracle/digest.py``), learned
+state digests every ``state_every`` steps, and full per-step records for the
+first ``full_steps`` steps (small, for debugging a first divergence).
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from oracle.digest import canonical_from_rows, record_digest, state_digest, step_digest  # noqa: E402
+from oracle.htm_oracle import CanonicalGlobalInhibition, HTMOracle, OracleConfig  # noqa: E402
+
+CASES = {
+    # name: (input_dim, column_dim, cell_dim, active_columns, steps, patterns, density, noise, seed, state_every, full_steps)
+    "tiny": (64, 256, 8, 20, 1500, 12, 0.25, 0.05, 3, 100, 40),
+    "odd": (200, 300, 20, 25, 2000, 25, 0.2, 0.05, 7, 250, 20),
+    "mid": (256, 512, 32, 22, 3000, 40, 0.2, 0.05, 11, 250, 10),
+    "cfg1": (1000, 2048, 32, None, 10000, 100, 0.2, 0.05, 0, 1000, 4),
+    "cfg2": (1024, 2048, 32, None, 10000, 100, 0.2, 0.05, 0, 1000, 4),
+}
+
+
+def make_inputs(input_dim, patterns, density, noise, steps, seed):
+    """example.py:34,52 recipe, but from a private generator."""
+    g = np.random.default_rng(1000 + seed)
+    base = g.random((patterns, input_dim)) < density
+    flips = g.random((steps, input_dim)) < noise
+    idx = np.arange(steps) % patterns
+    return base[idx] ^ flips
+
+
+def reference_record(htm, sp_state, tm_state):
+    c = htm.cell_dim
+    ds = tm_state.distal_state
+    return dict(
+        n_segments=len(htm.temporal_memory.distal_projection.segment_bundle),
+        overlaps=sp_state.overlaps,
+        boosted=sp_state.boosted_overlaps,
+        active_column=sp_state.active_column,
+        bursting=tm_state.active_column_bursting,
+        winner_cell=tm_state.winner_cell[0] * c + tm_state.winner_cell[1],
+        active_cell=tm_state.active_cell[0] * c + tm_state.active_cell[1],
+        matching_segment=ds.matching_segment,
+        matching_activation=ds.matching_segment_activation,
+        matching_jit=ds.matching_segment_jittered_potential,
+    )
+
+
+def reference_state_digest(htm):
+    sp, tm = htm.spatial_pooler, htm.temporal_memory
+    dp = tm.distal_projection
+    proj = dp.segment_projection
+    owner = dp.segment_bundle[:].squeeze(1)
+    edge = proj.output_edge[:]
+    target = proj.get_output_edge_target(edge)
+    canon = canonical_from_rows(owner, np.where(edge == proj.invalid_output_edge, -1, target),
+                                proj.output_permanence[:])
+    return state_digest(sp.proximal_projection.permanence, sp.boosting.duty_cycle,
+                        dp.bundle_segments, canon), canon
+
+
+def run_case(name):
+    import bithtm  # the reference
+
+    I, C, c, k, steps, patterns, density, noise, seed, state_every, full_steps = CASES[name]
+    xs = make_inputs(I, patterns, density, noise, steps, seed)
+
+    np.random.seed(seed)
+    k_eff = k if k is not None else round(C * 0.02)
+    sp = bithtm.SpatialPooler(I, C, k_eff, inhibition=CanonicalGlobalInhibition(k_eff))
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, active_columns=k_eff, spatial_pooler=sp)
+    init_perm = sp.proximal_projection.permanence.copy()
+
+    rs = np.random.RandomState(seed)
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=rs, overlap="packed")
+    assert np.array_equal(orc.permanence, init_perm)
+
+    digests = np.zeros(steps, dtype=np.uint64)
+    draws = np.zeros(steps, dtype=np.int64)
+    state_steps, state_digests = [], []
+    full = {}
+    ties = []
+    t0 = time.time()
+    t_ref = 0.0
+    for t in range(steps):
+        ta = time.perf_counter()
+        sp_state, tm_state = htm.process(xs[t])
+        t_ref += time.perf_counter() - ta
+        ref = reference_record(htm, sp_state, tm_state)
+        rec = orc.step(xs[t])
+        d_ref = step_digest(**ref)
+        d_orc = record_digest(rec)
+        if rec.undefined_tie:
+            ties.append(t)
+        if d_ref != d_orc:
+            for f in ref:
+                a, b = np.asarray(ref[f]).reshape(-1), np.asarray(getattr(rec, f)).reshape(-1)
+                if a.shape != b.shape or not np.array_equal(a, b):
+                    print(f"  step {t}: field {f} differs: ref {a[:8]} ... oracle {b[:8]} ...")
+            raise SystemExit(f"{name}: oracle diverged from the reference at step {t} (ties so far {ties})")
+        digests[t] = d_ref
+        draws[t] = rec.draws
+        if t < full_steps:
+            for f, v in ref.items():
+                full[f"s{t}_{f}"] = np.asarray(v).reshape(-1)
+        if (t + 1) % state_every == 0 or t == steps - 1:
+            sd_ref, _ = reference_state_digest(htm)
+            sd_orc = state_digest(orc.permanence, orc.duty, orc.cell_nseg, orc.canonical_synapses())
+            if sd_ref != sd_orc:
+                raise SystemExit(f"{name}: learned state differs at step {t}")
+            state_steps.append(t)
+            state_digests.append(sd_ref)
+        # the two private/global streams must stay in lock-step
+    assert np.random.get_state()[2] == rs.get_state()[2] and np.array_equal(np.random.get_state()[1], rs.get_state()[1])
+    wall = time.time() - t0
+    out = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(
+        out, config=np.array([I, C, c, k_eff, steps, patterns, seed], dtype=np.int64),
+        density=np.float64(density), noise=np.float64(noise),
+        digests=digests, draws=draws, state_steps=np.array(state_steps, dtype=np.int64),
+        state_digests=np.array(state_digests, dtype=np.uint64), undefined_tie_steps=np.array(ties, dtype=np.int64),
+        n_segments_final=np.int64(rec.n_segments), reference_steps_per_s=np.float64(steps / t_ref), **full)
+    print(f"{name}: {steps} steps ok, S={rec.n_segments}, ties={ties}, ref {steps / t_ref:.1f} steps/s, "
+          f"wall {wall:.1f}s, {os.path.getsize(out) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    for case in (sys.argv[1:] or list(CASES)):
+        run_case(case)
