@@ -1,0 +1,234 @@
+"""Device-side state of one SP+TM network: the ``bh_ctx`` handed to the C ABI and
+the single HBM arena it points into.  PyTorch is used for device memory, pinned
+host memory and the current stream only -- all arithmetic is in the CUDA library.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+_TORCH_DTYPES = None
+
+
+def _torch():
+    import torch
+
+    global _TORCH_DTYPES
+    if _TORCH_DTYPES is None:
+        _TORCH_DTYPES = {"float64": torch.float64, "float32": torch.float32, "int32": torch.int32,
+                         "uint8": torch.uint8}
+    return torch
+
+
+def require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise nat.NativeError("bithtm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Engine:
+    """Owns the arena and the context struct for one network (or one column
+    shard of it)."""
+
+    def __init__(self, input_dim, column_dim, cell_dim, active_columns, *, device=None,
+                 max_segments=None, max_synapses_per_segment=128, match_capacity=None,
+                 learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None):
+        torch = _torch()
+        self.device = require_cuda(device)
+        if not (1 <= cell_dim <= 32):
+            raise NotImplementedError("bithtm_b200 supports 1..32 cells per column (one bit-word per column)")
+        I, Ccol, c, k = int(input_dim), int(column_dim), int(cell_dim), int(active_columns)
+        N = Ccol * c
+        sm, major, minor = C.c_int(0), C.c_int(0), C.c_int(0)
+        nat.check(nat.lib.bh_device_info(self.device.index or 0, C.byref(sm), C.byref(major), C.byref(minor)),
+                  "bh_device_info")
+        self.sm_count = sm.value
+        if max_segments is None:
+            max_segments = min(8 * N, 1 << 22)
+        max_segments = max(int(max_segments), 64)
+        if match_capacity is None:
+            match_capacity = max_segments
+        if learn_capacity is None:
+            learn_capacity = max_segments + k * c
+        if rand_capacity is None:
+            rand_capacity = max(1 << 20, 8 * k * (k + 1)) + k * c + match_capacity
+        if tm_blocks is None:
+            tm_blocks = self.sm_count if max_segments <= (1 << 20) else min(1024, self.sm_count * 6)
+        ctx = nat.BhCtx()
+        ctx.input_dim, ctx.input_words = I, (I + 31) // 32
+        ctx.mask_stride = _round_up(ctx.input_words, 4)
+        ctx.column_dim, ctx.cell_dim, ctx.active_columns = Ccol, c, k
+        ctx.seg_capacity, ctx.syn_capacity = max_segments, _round_up(int(max_synapses_per_segment), 32)
+        ctx.match_capacity, ctx.learn_capacity = int(match_capacity), int(learn_capacity)
+        ctx.tm_blocks, ctx.sm_count = int(tm_blocks), self.sm_count
+        ctx.rand_capacity, ctx.ring_len = int(rand_capacity), int(ring_len)
+        self.ctx = ctx
+        self.I, self.C, self.c, self.k, self.N = I, Ccol, c, k, N
+
+        nbytes = nat.lib.bh_layout(C.byref(ctx), None)
+        self.arena = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        base = self.arena.data_ptr()
+        got = nat.lib.bh_layout(C.byref(ctx), C.c_void_p(base))
+        assert got == nbytes
+        self.arena_bytes = nbytes
+        # typed views into the arena
+        counts = self._counts()
+        self.buf = {}
+        for name, dt in nat.DEVICE_BUFFERS.items():
+            ptr = getattr(ctx, name) or 0
+            n = counts[name]
+            if n == 0:
+                self.buf[name] = torch.empty(0, dtype=_TORCH_DTYPES[dt], device=self.device)
+                continue
+            off = ptr - base
+            item = torch.empty(0, dtype=_TORCH_DTYPES[dt]).element_size()
+            assert 0 <= off and off + n * item <= nbytes, name
+            self.buf[name] = self.arena[off:off + n * item].view(_TORCH_DTYPES[dt])
+        # pinned host staging for bh_step_host
+        self.input_pinned = torch.zeros(ctx.mask_stride, dtype=torch.int32).pin_memory()
+        self.summary_pinned = torch.zeros(nat.summary_ints(k), dtype=torch.int32).pin_memory()
+        ctx.input_pinned = self.input_pinned.data_ptr()
+        ctx.summary_pinned = self.summary_pinned.data_ptr()
+        self._summary_np = self.summary_pinned.numpy()
+        self._summary_out = np.zeros(nat.summary_ints(k), dtype=np.int32)
+        nat.check(nat.lib.bh_init(C.byref(ctx), self.stream), "bh_init")
+        self.epoch = 0  # bumped by every completed step; lazily fetched State fields check it
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _counts(self):
+        x = self.ctx
+        C_, I, c, k = x.column_dim, x.input_dim, x.cell_dim, x.active_columns
+        N, S, E, M = C_ * c, x.seg_capacity, x.syn_capacity, x.match_capacity
+        return {
+            "sp_perm": C_ * I, "sp_mask": C_ * x.mask_stride, "duty": C_, "overlaps": C_, "boosted": C_,
+            "active_cols": 2 * k, "col_active": C_, "col_pred": C_, "col_act": C_, "col_win": C_,
+            "cell_nseg": N, "cell_maxjit": N, "cell_npred": N, "cell_widx": N,
+            "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": S * E, "syn_perm": S * E,
+            "row_pred": k, "row_act": k, "row_win": k, "row_unacc": k, "winners": 2 * k * c, "unacc": k * c,
+            "m_seg": M, "m_conn": M, "m_jit": M, "m_flag": M, "learn_list": x.learn_capacity, "punish_list": M,
+            "blk": 8 * 1024, "mt_key": nat.MT_N, "rand_buf": x.rand_capacity, "sc": nat.SC_COUNT,
+            "input_ring": x.ring_len * x.input_words, "input_dev": x.mask_stride,
+            "summary_dev": nat.summary_ints(k),
+        }
+
+    @property
+    def stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def ref(self):
+        return C.byref(self.ctx)
+
+    def scalars(self) -> np.ndarray:
+        return self.buf["sc"].cpu().numpy()
+
+    def check_status(self, sc=None):
+        st = int(self.scalars()[nat.SC_STATUS] if sc is None else sc)
+        fatal = st & nat.ST_FATAL
+        if fatal:
+            msgs = [m for bit, m in nat.ST_NAMES.items() if fatal & bit]
+            raise nat.NativeError("bithtm_b200 capacity overflow: " + "; ".join(msgs))
+        return st
+
+    # ------------------------------------------------------------------ inputs
+    def pack_input(self, x) -> "torch.Tensor":
+        """bool[I] (numpy, any array-like, or a CUDA tensor) -> packed int32 words on the device."""
+        torch = _torch()
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            if x.dtype == torch.int32 and x.numel() == self.ctx.input_words:
+                return x
+            src = x.to(torch.uint8).contiguous()
+            out = torch.empty(self.ctx.input_words, dtype=torch.int32, device=self.device)
+            nat.check(nat.lib.bh_pack_input(self.ref, src.data_ptr(), out.data_ptr(), self.stream), "bh_pack_input")
+            return out
+        return torch.from_numpy(self.pack_host(x)).to(self.device)
+
+    def pack_host(self, x) -> np.ndarray:
+        xb = np.asarray(x).astype(bool).reshape(-1)
+        if xb.size != self.I:
+            raise ValueError(f"input has {xb.size} bits, expected {self.I}")
+        pad = self.ctx.input_words * 32 - self.I
+        if pad:
+            xb = np.concatenate([xb, np.zeros(pad, dtype=bool)])
+        return np.packbits(xb, bitorder="little").view(np.int32)
+
+    def load_ring(self, inputs):
+        """Upload [T, I] bool inputs into the device input ring (T == ring_len)."""
+        torch = _torch()
+        rows = np.stack([self.pack_host(r) for r in inputs])
+        assert rows.shape[0] == self.ctx.ring_len
+        self.buf["input_ring"].copy_(torch.from_numpy(rows.reshape(-1)).to(self.device))
+        self.buf["sc"][nat.SC_INPUT_POS] = 0
+
+    # ------------------------------------------------------------------ RNG (legacy MT19937 of np.random)
+    def set_rng_state(self, key: np.ndarray, pos: int):
+        torch = _torch()
+        k32 = np.ascontiguousarray(key, dtype=np.uint32).view(np.int32)
+        self.buf["mt_key"].copy_(torch.from_numpy(k32).to(self.device))
+        self.buf["sc"][nat.SC_MT_POS] = int(pos)
+
+    def get_rng_state(self):
+        key = self.buf["mt_key"].cpu().numpy().view(np.uint32).copy()
+        pos = int(self.buf["sc"][nat.SC_MT_POS].item())
+        return key, pos
+
+    def rng_fill(self, count: int) -> np.ndarray:
+        torch = _torch()
+        out = torch.empty(max(count, 1), dtype=torch.float64, device=self.device)
+        nat.check(nat.lib.bh_rng_fill(self.ref, out.data_ptr(), int(count), self.stream), "bh_rng_fill")
+        return out[:count].cpu().numpy()
+
+    # ------------------------------------------------------------------ steps
+    def step_device(self, words, learning=True):
+        nat.check(nat.lib.bh_step(self.ref, words.data_ptr(), int(bool(learning)), self.stream), "bh_step")
+        self.epoch += 1
+
+    def step_host(self, x_bool: np.ndarray, learning=True) -> np.ndarray:
+        xb = np.ascontiguousarray(x_bool, dtype=np.uint8)
+        if xb.size != self.I:
+            raise ValueError(f"input has {xb.size} bits, expected {self.I}")
+        nat.check(nat.lib.bh_step_host(self.ref, xb.ctypes.data, int(bool(learning)),
+                                       self._summary_out.ctypes.data, self.stream), "bh_step_host")
+        self.epoch += 1
+        return self._summary_out
+
+    def summary(self) -> np.ndarray:
+        nat.check(nat.lib.bh_summary(self.ref, self._summary_out.ctypes.data, self.stream), "bh_summary")
+        return self._summary_out
+
+    def graph(self, steps_per_graph: int, learning=True):
+        key = (steps_per_graph, bool(learning))
+        if key not in self._graphs:
+            torch = _torch()
+            handle = C.c_void_p()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                nat.check(nat.lib.bh_graph_create(self.ref, int(steps_per_graph), int(bool(learning)),
+                                                  self.stream, C.byref(handle)), "bh_graph_create")
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graphs[key] = handle
+        return self._graphs[key]
+
+    def launch_graph(self, handle, steps_per_graph: int):
+        nat.check(nat.lib.bh_graph_launch(handle, self.stream), "bh_graph_launch")
+        self.epoch += steps_per_graph
+
+    def __del__(self):
+        try:
+            for h in getattr(self, "_graphs", {}).values():
+                nat.lib.bh_graph_destroy(h)
+        except Exception:
+            pass

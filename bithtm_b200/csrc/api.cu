@@ -1,0 +1,407 @@
+// C ABI of bithtm_b200 (see include/bithtm_b200.h).  Host-side launch code only:
+// the library is stateless, every entry point is a sequence of kernel launches on
+// the caller's stream over the caller's buffers.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "sp_kernels.cuh"
+#include "tm_kernels.cuh"
+
+#define CU_RET(expr)                                   \
+  do {                                                 \
+    cudaError_t e__ = (expr);                          \
+    if (e__ != cudaSuccess) return -(1000 + (int)e__); \
+  } while (0)
+#define LAUNCH_CHECK() CU_RET(cudaGetLastError())
+
+static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------
+namespace {
+struct Carver {
+  char* base;
+  size_t off;
+  template <typename T>
+  void take(T*& ptr, size_t count) {
+    off = (off + 255) & ~size_t(255);
+    ptr = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+  }
+};
+}  // namespace
+
+extern "C" size_t bh_layout(bh_ctx* x, void* base) {
+  Carver cv{reinterpret_cast<char*>(base), 0};
+  const size_t C = x->column_dim, I = x->input_dim, c = x->cell_dim, k = x->active_columns;
+  const size_t N = C * c, S = x->seg_capacity, E = x->syn_capacity, M = x->match_capacity;
+  cv.take(x->sp_perm, C * I);
+  cv.take(x->sp_mask, C * (size_t)x->mask_stride);
+  cv.take(x->duty, C);
+  cv.take(x->overlaps, C);
+  cv.take(x->boosted, C);
+  cv.take(x->active_cols, 2 * k);
+  cv.take(x->col_active, C);
+  cv.take(x->col_pred, C);
+  cv.take(x->col_act, C);
+  cv.take(x->col_win, C);
+  cv.take(x->cell_nseg, N);
+  cv.take(x->cell_maxjit, N);
+  cv.take(x->cell_npred, N);
+  cv.take(x->cell_widx, N);
+  cv.take(x->seg_owner, S);
+  cv.take(x->seg_count, S);
+  cv.take(x->seg_pot, S);
+  cv.take(x->seg_conn, S);
+  cv.take(x->syn_cell, S * E);
+  cv.take(x->syn_perm, S * E);
+  cv.take(x->row_pred, k);
+  cv.take(x->row_act, k);
+  cv.take(x->row_win, k);
+  cv.take(x->row_unacc, k);
+  cv.take(x->winners, 2 * k * c);
+  cv.take(x->unacc, k * c);
+  cv.take(x->m_seg, M);
+  cv.take(x->m_conn, M);
+  cv.take(x->m_jit, M);
+  cv.take(x->m_flag, M);
+  cv.take(x->learn_list, (size_t)x->learn_capacity);
+  cv.take(x->punish_list, M);
+  cv.take(x->blk, (size_t)BLK_ROWS * BH_BLK_STRIDE);
+  cv.take(x->mt_key, (size_t)BH_MT_N);
+  cv.take(x->rand_buf, (size_t)x->rand_capacity);
+  cv.take(x->sc, (size_t)BH_SC_COUNT);
+  cv.take(x->input_ring, (size_t)x->ring_len * x->input_words);
+  cv.take(x->input_dev, (size_t)x->mask_stride);
+  cv.take(x->summary_dev, (size_t)BH_SUMMARY_INTS(k));
+  return (cv.off + 255) & ~size_t(255);
+}
+
+static int check_ctx(const bh_ctx* x) {
+  if (!x) return BH_E_BADARG;
+  if (x->cell_dim < 1 || x->cell_dim > 32) return BH_E_UNSUPPORTED;
+  if (x->input_dim < 1 || x->column_dim < 1 || x->active_columns < 1 || x->active_columns > x->column_dim)
+    return BH_E_BADARG;
+  if (x->input_words != (x->input_dim + 31) / 32 || x->mask_stride % 4 != 0 || x->mask_stride < x->input_words)
+    return BH_E_BADARG;
+  if (x->tm_blocks < 1 || x->tm_blocks > BH_BLK_STRIDE) return BH_E_BADARG;
+  if (x->syn_capacity < 32 || x->syn_capacity % 32 != 0) return BH_E_BADARG;
+  return 0;
+}
+
+extern "C" int bh_abi_version(void) { return BH_ABI_VERSION; }
+extern "C" size_t bh_ctx_size(void) { return sizeof(bh_ctx); }
+
+extern "C" int bh_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return BH_E_NODEVICE;
+  cudaDeviceProp p;
+  CU_RET(cudaGetDeviceProperties(&p, device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return 0;
+}
+
+__global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+extern "C" int bh_init(const bh_ctx* x, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  long long N = (long long)x->column_dim * x->cell_dim;
+  k_fill_i32<<<cdiv(N, 256) < 1184 ? cdiv(N, 256) : 1184, 256, 0, S_(stream)>>>(x->cell_widx, N, -1);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// spatial pooler
+// ------------------------------------------------------------------------------------
+static int overlap_group(const bh_ctx* x) {
+  int vec = x->mask_stride / 4, g = 1;
+  while (g * 2 <= vec && g < 32) g *= 2;
+  return g;
+}
+
+static int sp_grid(const bh_ctx* x, int rows_per_block) {
+  int want = cdiv(x->column_dim, rows_per_block);
+  int cap = (x->sm_count > 0 ? x->sm_count : 148) * 8;
+  return want < cap ? want : cap;
+}
+
+extern "C" int bh_sp_build_mask(const bh_ctx* x, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  long long words = (long long)x->column_dim * x->mask_stride;
+  int grid = cdiv(words, SP_THREADS / 32);
+  int cap = (x->sm_count > 0 ? x->sm_count : 148) * 16;
+  k_sp_build_mask<<<grid < cap ? grid : cap, SP_THREADS, 0, S_(stream)>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bh_pack_input(const bh_ctx* x, const uint8_t* bool_dev, uint32_t* words_dev, void* stream) {
+  k_pack_input<<<cdiv((long long)x->input_words * 32, 256), 256, 0, S_(stream)>>>(*x, bool_dev, words_dev);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool BOOST>
+static int launch_overlap(const bh_ctx* x, const uint32_t* in, cudaStream_t st) {
+  int g = overlap_group(x);
+  int rows_per_block = (SP_THREADS / 32) * (32 / g);
+  size_t smem = (size_t)x->mask_stride * 4;
+  k_sp_overlap<BOOST><<<sp_grid(x, rows_per_block), SP_THREADS, smem, st>>>(*x, in, g);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bh_sp_overlap(const bh_ctx* x, const uint32_t* in, void* stream) {
+  return launch_overlap<false>(x, in, S_(stream));
+}
+
+extern "C" int bh_boost(const bh_ctx* x, void* stream) {
+  k_boost<<<cdiv(x->column_dim, 256), 256, 0, S_(stream)>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bh_inhibit(const bh_ctx* x, void* stream) {
+  k_topk<<<1, TOPK_THREADS, 0, S_(stream)>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bh_set_active_columns(const bh_ctx* x, const int32_t* cols_dev, void* stream) {
+  k_set_active<<<1, 1024, 0, S_(stream)>>>(*x, cols_dev);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bh_sp_learn(const bh_ctx* x, const uint32_t* in, void* stream) {
+  int cap = (x->sm_count > 0 ? x->sm_count : 148) * 8;
+  int grid = x->active_columns < cap ? x->active_columns : cap;
+  k_sp_learn<<<grid, SP_THREADS, 0, S_(stream)>>>(*x, in);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bh_duty_update(const bh_ctx* x, void* stream) {
+  k_duty_update<<<cdiv(x->column_dim, 256), 256, 0, S_(stream)>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int sp_step(const bh_ctx* x, const uint32_t* in, int learning, cudaStream_t st) {
+  int rc;
+  if ((rc = launch_overlap<true>(x, in, st))) return rc;
+  if ((rc = bh_inhibit(x, st))) return rc;
+  if (learning && (rc = bh_sp_learn(x, in, st))) return rc;
+  return bh_duty_update(x, st);
+}
+
+extern "C" int bh_sp_step(const bh_ctx* x, const uint32_t* in, int learning, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  return sp_step(x, in, learning, S_(stream));
+}
+
+__global__ void k_advance_step(const bh_ctx c) { c.sc[BH_SC_STEP] = c.sc[BH_SC_STEP] + 1; }
+
+extern "C" int bh_advance_step(const bh_ctx* x, void* stream) {
+  k_advance_step<<<1, 1, 0, S_(stream)>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// temporal memory
+// ------------------------------------------------------------------------------------
+extern "C" int bh_tm_select(const bh_ctx* x, void* stream) {
+  cudaStream_t st = S_(stream);
+  k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 1, 1);
+  LAUNCH_CHECK();
+  k_tm_select_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  LAUNCH_CHECK();
+  k_tm_select_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int learn_apply_smem(const bh_ctx* x) {
+  long long bits = (long long)x->active_columns * x->cell_dim;
+  return (int)(((bits + 31) / 32) * 4);
+}
+
+extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
+  cudaStream_t st = S_(stream);
+  k_tm_learn_select_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, learning);
+  LAUNCH_CHECK();
+  k_tm_learn_select_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, learning);
+  LAUNCH_CHECK();
+  k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 2, learning);
+  LAUNCH_CHECK();
+  if (learning) {
+    int smem = learn_apply_smem(x);
+    if (smem > 200 * 1024) return BH_E_UNSUPPORTED;
+    if (smem > 40 * 1024)
+      CU_RET(cudaFuncSetAttribute(k_tm_learn_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = (x->sm_count > 0 ? x->sm_count : 148) * 8;
+    k_tm_learn_apply<<<grid, LA_THREADS, smem, st>>>(*x);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int bh_tm_activate(const bh_ctx* x, void* stream) {
+  cudaStream_t st = S_(stream);
+  int k = x->active_columns, kc = k * x->cell_dim;
+  k_tm_post<<<cdiv(kc, 256) < 256 ? cdiv(kc, 256) : 256, 256, 0, st>>>(*x);
+  LAUNCH_CHECK();
+  k_tm_activate_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  LAUNCH_CHECK();
+  k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 3, 1);
+  LAUNCH_CHECK();
+  k_tm_activate_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bh_tm_step(const bh_ctx* x, int learning, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if ((rc = bh_tm_select(x, stream))) return rc;
+  if ((rc = bh_tm_learn(x, learning, stream))) return rc;
+  return bh_tm_activate(x, stream);
+}
+
+// ------------------------------------------------------------------------------------
+// whole step
+// ------------------------------------------------------------------------------------
+extern "C" int bh_step(const bh_ctx* x, const uint32_t* in, int learning, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if ((rc = sp_step(x, in, learning, S_(stream)))) return rc;
+  if ((rc = bh_tm_select(x, stream))) return rc;
+  if ((rc = bh_tm_learn(x, learning, stream))) return rc;
+  return bh_tm_activate(x, stream);
+}
+
+extern "C" int bh_step_launches(const bh_ctx* x, int learning) {
+  (void)x;
+  // overlap+boost, topk, [sp_learn], duty | draw1, select a/b | learn-select a/b, draw2, [apply] |
+  // post, activate a, draw3, activate b
+  return learning ? 15 : 13;
+}
+
+__global__ void k_ring_fetch(const bh_ctx c) {
+  // copy the next ring row to input_dev and advance the cursor (single CTA)
+  int pos = c.sc[BH_SC_INPUT_POS];
+  const uint32_t* src = c.input_ring + (long long)(pos % c.ring_len) * c.input_words;
+  for (int i = threadIdx.x; i < c.input_words; i += blockDim.x) c.input_dev[i] = src[i];
+  __syncthreads();
+  if (threadIdx.x == 0) c.sc[BH_SC_INPUT_POS] = pos + 1;
+}
+
+extern "C" int bh_step_ring(const bh_ctx* x, int learning, void* stream) {
+  if (!x || x->ring_len <= 0) return BH_E_BADARG;
+  k_ring_fetch<<<1, 256, 0, S_(stream)>>>(*x);
+  LAUNCH_CHECK();
+  return bh_step(x, x->input_dev, learning, stream);
+}
+
+extern "C" int bh_step_host(const bh_ctx* x, const uint8_t* input_bool_host, int learning, int32_t* summary_host,
+                            void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (!input_bool_host || !x->input_pinned || !x->summary_pinned) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  // pack on the host: bit i of word i/32 (little-endian bit order)
+  for (int w = 0; w < x->input_words; ++w) {
+    uint32_t bits = 0;
+    int lim = x->input_dim - w * 32;
+    if (lim > 32) lim = 32;
+    const uint8_t* p = input_bool_host + w * 32;
+    for (int b = 0; b < lim; ++b) bits |= (uint32_t)(p[b] != 0) << b;
+    x->input_pinned[w] = bits;
+  }
+  CU_RET(cudaMemcpyAsync(x->input_dev, x->input_pinned, (size_t)x->input_words * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = bh_step(x, x->input_dev, learning, stream))) return rc;
+  return bh_summary(x, summary_host, stream);
+}
+
+extern "C" int bh_summary(const bh_ctx* x, int32_t* summary_host, void* stream) {
+  if (!x || !x->summary_pinned) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  int k = x->active_columns;
+  int n = k > BH_MT_N + 1 ? k : BH_MT_N + 1;
+  k_summary<<<cdiv(n, 256) < 64 ? cdiv(n, 256) : 64, 256, 0, st>>>(*x);
+  LAUNCH_CHECK();
+  size_t bytes = (size_t)BH_SUMMARY_INTS(k) * 4;
+  CU_RET(cudaMemcpyAsync(x->summary_pinned, x->summary_dev, bytes, cudaMemcpyDeviceToHost, st));
+  CU_RET(cudaStreamSynchronize(st));
+  if (summary_host) memcpy(summary_host, x->summary_pinned, bytes);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// CUDA graphs over bh_step_ring
+// ------------------------------------------------------------------------------------
+extern "C" int bh_graph_create(const bh_ctx* x, int steps_per_graph, int learning, void* stream, void** out) {
+  if (!out || steps_per_graph < 1) return BH_E_BADARG;
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  cudaStream_t st = S_(stream);
+  cudaGraph_t graph = nullptr;
+  CU_RET(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  for (int i = 0; i < steps_per_graph && rc == 0; ++i) rc = bh_step_ring(x, learning, stream);
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  *out = exec;
+  return 0;
+}
+
+extern "C" int bh_graph_launch(void* graph_exec, void* stream) {
+  CU_RET(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), S_(stream)));
+  return 0;
+}
+
+extern "C" int bh_graph_destroy(void* graph_exec) {
+  if (graph_exec) CU_RET(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// randomness + test hooks
+// ------------------------------------------------------------------------------------
+extern "C" int bh_rng_fill(const bh_ctx* x, double* dst_dev, int64_t count, void* stream) {
+  if (!x || !dst_dev || count < 0) return BH_E_BADARG;
+  k_rng_fill<<<1, MT_THREADS, 0, S_(stream)>>>(*x, dst_dev, (long long)count);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_test_np_expf(const float* x, float* y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = bh_np_expf(x[i]);
+}
+
+extern "C" int bh_test_np_expf(const float* x_dev, float* y_dev, int64_t n, void* stream) {
+  k_test_np_expf<<<1184, 256, 0, S_(stream)>>>(x_dev, y_dev, (long long)n);
+  LAUNCH_CHECK();
+  return 0;
+}

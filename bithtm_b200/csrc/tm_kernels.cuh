@@ -1,0 +1,598 @@
+// Temporal-memory kernels.  Reference: bithtm/networks.py:91-128 (TemporalMemory.process),
+// bithtm/projections.py:194-293 (PredictiveProjection) on top of :27-192 (SparseProjection).
+//
+// Data layout: a segment is a row of syn_capacity (cell, permanence)
+// slots kept COMPACT -- valid synapses are slots [0, seg_count) -- because every
+// consumer in the reference is a count over the row, so slot order is free.
+// There is no cell->segment forward index: activation is a segment-major scan.
+//
+// Every list whose ORDER the reference defines (winner cells, unaccounted winners,
+// matching segments = index of their jitter draw, learning segments = row of the
+// priority matrix, recycled segment ids) is produced by a two-kernel ordered
+// compaction: kernel A counts per CTA over contiguous ranges, kernel B derives
+// its offset from the per-CTA counts and writes in order.  No atomics decide an
+// order, so results are deterministic and equal to the reference's.
+#pragma once
+
+#include "common.cuh"
+#include "mt19937.cuh"
+
+#define BLK(c, row) ((c).blk + (row)*BH_BLK_STRIDE)
+
+// ---------------------------------------------------------------------------------
+// Random draws.  which = 1: rand(k, c) (networks.py:87); 2: rand(L, W+1)
+// (projections.py:120); 3: rand(M) (projections.py:235).  Single CTA; also the
+// sequence point where data-dependent scalars are committed.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MT_THREADS) k_tm_draw(const bh_ctx c, int which, int learning) {
+  __shared__ uint32_t x[2 * MT_N];
+  __shared__ long long s_count, s_dst;
+  __shared__ int s_red[32];
+  int m_before = 0, m_total = 0;
+  if (which == 3) blk_prefix(BLK(c, BLK_MATCH), 0, c.tm_blocks, s_red, m_before, m_total);
+  if (threadIdx.x == 0) {
+    int* sc = c.sc;
+    const int cur = sc[BH_SC_STEP] & 1;
+    long long count = 0, dst = 0;
+    if (which == 1) {
+      count = (long long)c.active_columns * c.cell_dim;
+      dst = 0;
+      sc[BH_SC_OFF2] = (int)count;
+    } else if (which == 2) {
+      sc[BH_SC_NSEG] = sc[BH_SC_NSEG_NEXT];
+      dst = sc[BH_SC_OFF2];
+      if (learning && sc[BH_SC_HAVE_PREV]) count = (long long)sc[BH_SC_L] * (sc[BH_SC_W0 + (cur ^ 1)] + 1);
+    } else {
+      int M = m_total;
+      if (M > c.match_capacity) {
+        M = c.match_capacity;
+        atomicOr(&sc[BH_SC_STATUS], BH_ST_MATCH_OVERFLOW);
+      }
+      sc[BH_SC_M] = M;
+      count = M;
+      dst = sc[BH_SC_OFF3];
+    }
+    if (dst + count > c.rand_capacity) {
+      atomicOr(&sc[BH_SC_STATUS], BH_ST_RAND_OVERFLOW);
+      count = c.rand_capacity > dst ? c.rand_capacity - dst : 0;
+    }
+    if (which == 2) sc[BH_SC_OFF3] = (int)(dst + count);
+    sc[BH_SC_RAND_FILL] = (int)(dst + count);
+    s_count = count;
+    s_dst = dst;
+  }
+  __syncthreads();
+  mt_fill_block(x, c.mt_key, &c.sc[BH_SC_MT_POS], c.rand_buf + s_dst, s_count);
+}
+
+// Plain stream fill (bh_rng_fill)
+__global__ void __launch_bounds__(MT_THREADS) k_rng_fill(const bh_ctx c, double* dst, long long count) {
+  __shared__ uint32_t x[2 * MT_N];
+  mt_fill_block(x, c.mt_key, &c.sc[BH_SC_MT_POS], dst, count);
+}
+
+// ---------------------------------------------------------------------------------
+// (f) bursting + winner cells, part A: one warp per active column (lane = cell).
+// networks.py:95-104 with evaluate_cell_best_matching (:73-82) and
+// evaluate_cell_least_used (:84-89).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_a(const bh_ctx c) {
+  __shared__ int s_red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int k = c.active_columns, cd = c.cell_dim;
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const bool have_prev = c.sc[BH_SC_HAVE_PREV] != 0;
+  const int* act = c.active_cols + cur * k;
+  const double* rnd = c.rand_buf;  // draw #1 sits at offset 0
+  const Range rg = block_range(k, b, nb);
+  int n_win = 0, n_un = 0;
+  for (int r = rg.begin + warp; r < rg.end; r += BH_TM_WARPS) {
+    const int col = act[r];
+    const uint32_t pred = c.col_pred[col];  // previous step's prediction (networks.py:96)
+    const bool burst = pred == 0u;          // networks.py:97
+    const bool in = lane < cd;
+    const int cell = col * cd + lane;
+    // best matching (networks.py:76-81); float32 arithmetic as in the reference
+    float mj = in ? c.cell_maxjit[cell] : 0.0f;
+    float colmax = warp_max(mj);
+    bool col_matching = have_prev && colmax >= (float)c.seg_matching_threshold;
+    bool best = have_prev && in && fabsf(__fsub_rn(mj, colmax)) < c.epsilon;
+    // least used (networks.py:85-88): f32(f64(count) + u)
+    float x = INFINITY;
+    if (in) x = __double2float_rn(__dadd_rn((double)c.cell_nseg[cell], rnd[(long long)r * cd + lane]));
+    float rowmin = warp_min(x);
+    bool least = in && fabsf(__fsub_rn(x, rowmin)) < c.epsilon;
+    bool predbit = (pred >> lane) & 1u;
+    bool win = in && (predbit || (burst && (col_matching ? best : least)));  // networks.py:102
+    uint32_t wbits = __ballot_sync(BH_FULL, win);
+    // winners no matching segment points at (projections.py:271)
+    uint32_t ubits = __ballot_sync(BH_FULL, win && have_prev && mj < c.epsilon);
+    if (lane == 0) {
+      c.row_pred[r] = pred;
+      c.row_win[r] = wbits;
+      c.row_act[r] = burst ? low_mask(cd) : pred;  // networks.py:115
+      c.row_unacc[r] = ubits;
+      c.col_win[col] = wbits;
+      n_win += __popc(wbits);
+      n_un += __popc(ubits);
+    }
+  }
+  int tw = block_sum(n_win, s_red);
+  int tu = block_sum(n_un, s_red);
+  if (threadIdx.x == 0) {
+    BLK(c, BLK_WIN)[b] = tw;
+    BLK(c, BLK_UNACC)[b] = tu;
+  }
+}
+
+// Part B: ordered winner / unaccounted lists (row order of active_column, cells
+// ascending: np.where on the [k, c] mask, networks.py:103-104).
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_b(const bh_ctx c) {
+  __shared__ int s_red[32];
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int k = c.active_columns, cd = c.cell_dim;
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int* act = c.active_cols + cur * k;
+  const int* prev = c.active_cols + (cur ^ 1) * k;
+  int* wl = c.winners + (long long)cur * k * cd;
+  int w_before, w_total, u_before, u_total;
+  blk_prefix(BLK(c, BLK_WIN), b, nb, s_red, w_before, w_total);
+  blk_prefix(BLK(c, BLK_UNACC), b, nb, s_red, u_before, u_total);
+  const Range rg = block_range(k, b, nb);
+  int wbase = w_before, ubase = u_before;
+  for (int tile = rg.begin; tile < rg.end; tile += BH_TM_THREADS) {
+    const int r = tile + threadIdx.x;
+    const bool ok = r < rg.end;
+    uint32_t wb = ok ? c.row_win[r] : 0u;
+    uint32_t ub = ok ? c.row_unacc[r] : 0u;
+    const int cell0 = ok ? act[r] * cd : 0;
+    int tot;
+    int p = wbase + block_excl_scan(__popc(wb), s_red, tot);
+    wbase += tot;
+    while (wb) {
+      int bit = __ffs(wb) - 1;
+      wb &= wb - 1;
+      wl[p++] = cell0 + bit;
+    }
+    p = ubase + block_excl_scan(__popc(ub), s_red, tot);
+    ubase += tot;
+    while (ub) {
+      int bit = __ffs(ub) - 1;
+      ub &= ub - 1;
+      c.unacc[p++] = cell0 + bit;
+    }
+  }
+  // retire winner words of columns that were active last step but are not now
+  for (int i = b * BH_TM_THREADS + threadIdx.x; i < k; i += nb * BH_TM_THREADS) {
+    int col = prev[i];
+    if (!c.col_active[col]) c.col_win[col] = 0u;
+  }
+  if (b == 0 && threadIdx.x == 0) {
+    c.sc[BH_SC_W0 + cur] = w_total;
+    c.sc[BH_SC_NU] = u_total;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// (f) learning / punished segment selection among the previous matching segments,
+// part A (flags + per-CTA counts).  projections.py:264-269.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_a(const bh_ctx c, int learning) {
+  __shared__ int s_red[32];
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int cd = c.cell_dim;
+  const int M = c.sc[BH_SC_M];
+  const Range rg = block_range(M, b, nb);
+  int nl = 0, np = 0;
+  for (int j = rg.begin + threadIdx.x; j < rg.end; j += BH_TM_THREADS) {
+    uint8_t f = 0;
+    if (learning) {
+      const int s = c.m_seg[j];
+      const int owner = c.seg_owner[s];
+      const int col = owner / cd, bit = owner - col * cd;
+      bool is_winner = (c.col_win[col] >> bit) & 1u;                               // :262
+      bool seg_active = c.m_conn[j] >= c.seg_activation_threshold;                 // :250
+      bool unpredicted = c.cell_npred[owner] == 0;                                 // :266
+      bool best = fabsf(__fsub_rn(c.m_jit[j], c.cell_maxjit[owner])) < c.epsilon;  // :267
+      if (is_winner && (seg_active || (unpredicted && best))) f |= 1;              // :268
+      if (!c.col_active[col]) f |= 2;                                              // :269
+    }
+    c.m_flag[j] = f;
+    nl += f & 1;
+    np += (f >> 1) & 1;
+  }
+  int tl = block_sum(nl, s_red);
+  int tp = block_sum(np, s_red);
+  if (threadIdx.x == 0) {
+    BLK(c, BLK_LEARN)[b] = tl;
+    BLK(c, BLK_PUNISH)[b] = tp;
+  }
+}
+
+// Part B: ordered learning / punished lists; segments for unaccounted winners:
+// recycle the lowest-id segments with fewer than `matching threshold` synapses,
+// then append new ids (projections.py:79-95, 271-281); and the sparse reset of the
+// per-cell results of the previous activation (all their readers ran already).
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_b(const bh_ctx c, int learning) {
+  __shared__ int s_red[32];
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int cd = c.cell_dim;
+  const int M = c.sc[BH_SC_M];
+  const int S = c.sc[BH_SC_NSEG];
+  const int n_u = (learning && c.sc[BH_SC_HAVE_PREV]) ? c.sc[BH_SC_NU] : 0;
+  const int thr = c.seg_matching_threshold;
+  int l_before, L0, p_before, P;
+  blk_prefix(BLK(c, BLK_LEARN), b, nb, s_red, l_before, L0);
+  blk_prefix(BLK(c, BLK_PUNISH), b, nb, s_red, p_before, P);
+  {
+    const Range rg = block_range(M, b, nb);
+    int lbase = l_before, pbase = p_before;
+    for (int tile = rg.begin; tile < rg.end; tile += BH_TM_THREADS) {
+      const int j = tile + threadIdx.x;
+      const bool ok = j < rg.end;
+      const int f = ok ? c.m_flag[j] : 0;
+      const int s = ok ? c.m_seg[j] : 0;
+      int tot;
+      int pos = lbase + block_excl_scan(f & 1, s_red, tot);
+      lbase += tot;
+      if ((f & 1) && pos < c.learn_capacity) c.learn_list[pos] = s;
+      pos = pbase + block_excl_scan((f >> 1) & 1, s_red, tot);
+      pbase += tot;
+      if (f & 2) c.punish_list[pos] = s;
+      if (ok) {
+        const int owner = c.seg_owner[s];
+        c.cell_maxjit[owner] = 0.0f;
+        c.cell_npred[owner] = 0;
+        c.col_pred[owner / cd] = 0u;
+      }
+    }
+  }
+  int n_r = 0, n_new = 0;
+  if (n_u > 0) {
+    int r_before, R;
+    blk_prefix(BLK(c, BLK_RECYC), b, nb, s_red, r_before, R);
+    n_r = n_u < R ? n_u : R;
+    n_new = n_u - n_r;
+    if (S + n_new > c.seg_capacity) {
+      n_new = c.seg_capacity - S;
+      if (b == 0 && threadIdx.x == 0) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_SEG_OVERFLOW);
+    }
+    if (L0 + n_r + n_new > c.learn_capacity && b == 0 && threadIdx.x == 0)
+      atomicOr(&c.sc[BH_SC_STATUS], BH_ST_LEARN_OVERFLOW);
+    if (r_before < n_u) {
+      const Range sr = block_range(S, b, nb);
+      int rbase = r_before;
+      for (int tile = sr.begin; tile < sr.end && rbase < n_u; tile += BH_TM_THREADS) {
+        const int s = tile + threadIdx.x;
+        const bool rec = s < sr.end && c.seg_count[s] < thr;
+        int tot;
+        const int rank = rbase + block_excl_scan(rec ? 1 : 0, s_red, tot);
+        rbase += tot;
+        if (rec && rank < n_u) {
+          const int newo = c.unacc[rank];
+          atomicSub(&c.cell_nseg[c.seg_owner[s]], 1);  // :275-276
+          atomicAdd(&c.cell_nseg[newo], 1);            // :277
+          c.seg_owner[s] = newo;                       // :278
+          c.seg_count[s] = 0;                          // :83-85 (row logically emptied)
+          const int pos = L0 + rank;
+          if (pos < c.learn_capacity) c.learn_list[pos] = s;
+        }
+      }
+    }
+    for (int i = b * BH_TM_THREADS + threadIdx.x; i < n_new; i += nb * BH_TM_THREADS) {
+      const int rank = n_r + i, s = S + i;
+      const int owner = c.unacc[rank];
+      c.seg_owner[s] = owner;  // :280
+      c.seg_count[s] = 0;
+      atomicAdd(&c.cell_nseg[owner], 1);
+      const int pos = L0 + rank;
+      if (pos < c.learn_capacity) c.learn_list[pos] = s;
+    }
+  }
+  if (b == 0 && threadIdx.x == 0) {
+    int L = L0 + n_r + n_new;
+    c.sc[BH_SC_L0] = L0;
+    c.sc[BH_SC_L] = L < c.learn_capacity ? L : c.learn_capacity;
+    c.sc[BH_SC_P] = P;
+    c.sc[BH_SC_NR] = n_r;
+    c.sc[BH_SC_NSEG_NEXT] = S + n_new;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// (f) learning + punishment applied to segment rows.  One CTA per row.
+//  - permanence update in float64, stored as float32, synapses whose float64 sum is
+//    negative are deleted (projections.py:97-109); the row is re-compacted in place;
+//  - growth (learning rows only, projections.py:111-161): n_add = clip(sample -
+//    #synapses to previously active cells, 0, min(sample, W)); priorities are
+//    float32(rand(L, W+1)); previous winners already on the segment are excluded;
+//    the n_add smallest priorities < 1.0 win.  The cut is found by a 4x8-bit radix
+//    select over the float32 bit patterns (positive floats order like uints).
+// ---------------------------------------------------------------------------------
+#define LA_THREADS 128
+
+__global__ void __launch_bounds__(LA_THREADS) k_tm_learn_apply(const bh_ctx c) {
+  extern __shared__ uint32_t s_excl[];  // bitmap over previous-winner indices
+  __shared__ int s_red[32];
+  __shared__ int s_hist[256];
+  __shared__ int s_n, s_nact, s_rem;
+  __shared__ uint32_t s_prefix;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int cd = c.cell_dim, E = c.syn_capacity;
+  const int L = c.sc[BH_SC_L], P = c.sc[BH_SC_P];
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int Wp = c.sc[BH_SC_W0 + (cur ^ 1)];
+  const int* prevw = c.winners + (long long)(cur ^ 1) * c.active_columns * cd;
+  const long long off2 = c.sc[BH_SC_OFF2];
+  const long long rand_fill = c.sc[BH_SC_RAND_FILL];
+  const int sample = c.seg_sampling_synapses;
+  const int excl_words = (Wp + 31) >> 5;
+
+  for (int row = blockIdx.x; row < L + P; row += gridDim.x) {
+    const bool learn = row < L;
+    const int s = learn ? c.learn_list[row] : c.punish_list[row - L];
+    const double d_on = learn ? c.tm_learn_on : c.tm_punish_on;
+    const double d_off = learn ? c.tm_learn_off : c.tm_punish_off;
+    const bool can_delete = learn ? c.tm_learn_can_delete : c.tm_punish_can_delete;
+    int* cells = c.syn_cell + (long long)s * E;
+    float* perms = c.syn_perm + (long long)s * E;
+    if (learn)
+      for (int i = t; i < excl_words; i += LA_THREADS) s_excl[i] = 0u;
+    __syncthreads();
+
+    if (warp == 0) {
+      const int n = c.seg_count[s];
+      int base = 0, n_act = 0;
+      for (int g = 0; g < n; g += 32) {
+        const int slot = g + lane;
+        const bool valid = slot < n;
+        const int cell = valid ? cells[slot] : 0;
+        const float p = valid ? perms[slot] : 0.0f;
+        const bool act = valid && cell_bit(c.col_act, cell, cd);  // previous activation (networks.py:111)
+        const double sum = __dadd_rn((double)p, act ? d_on : d_off);  // :102-103
+        const bool keep = valid && !(can_delete && sum < 0.0);        // :105-108
+        const uint32_t kb = __ballot_sync(BH_FULL, keep);
+        const uint32_t ab = __ballot_sync(BH_FULL, keep && act);
+        const int pos = base + __popc(kb & ((1u << lane) - 1u));
+        if (keep) {
+          cells[pos] = cell;
+          perms[pos] = __double2float_rn(sum);
+          if (learn) {
+            const int wi = c.cell_widx[cell];  // projections.py:117-121
+            if (wi >= 0) atomicOr(&s_excl[wi >> 5], 1u << (wi & 31));
+          }
+        }
+        __syncwarp();
+        base += __popc(kb);
+        n_act += __popc(ab);
+      }
+      if (lane == 0) {
+        s_n = base;
+        s_nact = n_act;
+      }
+    }
+    __syncthreads();
+    const int n = s_n;
+    int cap = sample < Wp ? sample : Wp;
+    int n_add = sample - s_nact;  // projections.py:114-115
+    n_add = n_add < 0 ? 0 : (n_add > cap ? cap : n_add);
+    if (!learn || n_add == 0) {
+      if (t == 0) c.seg_count[s] = n;
+      __syncthreads();
+      continue;
+    }
+    const double* pr = c.rand_buf + off2 + (long long)row * (Wp + 1);  // row of rand(L, W+1)
+    const bool pr_ok = off2 + (long long)(row + 1) * (Wp + 1) <= rand_fill;
+
+    // candidates: previous winners not yet on the segment with priority < 1.0 (:121-123)
+    int nc = 0;
+    for (int w = t; w < Wp; w += LA_THREADS) {
+      bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
+      float pri = pr_ok ? __double2float_rn(pr[w]) : 2.0f;
+      nc += (!ex && pri < 1.0f) ? 1 : 0;
+    }
+    nc = block_sum(nc, s_red);
+    uint32_t cut = 0x3f800000u;  // bits of 1.0f: take every candidate
+    int ties_wanted = 0;
+    if (nc > n_add) {
+      if (t == 0) { s_prefix = 0u; s_rem = n_add; }
+      __syncthreads();
+      for (int pass = 3; pass >= 0; --pass) {
+        for (int i = t; i < 256; i += LA_THREADS) s_hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const int shift = pass * 8;
+        const uint32_t hi_mask = pass == 3 ? 0u : (0xffffffffu << (shift + 8));
+        for (int w = t; w < Wp; w += LA_THREADS) {
+          bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
+          float pri = __double2float_rn(pr[w]);
+          uint32_t bits = __float_as_uint(pri);
+          if (!ex && pri < 1.0f && (bits & hi_mask) == prefix) atomicAdd(&s_hist[(bits >> shift) & 0xff], 1);
+        }
+        __syncthreads();
+        if (t == 0) {
+          int rem = s_rem, d = 0;
+          for (; d < 255; ++d) {
+            if (s_hist[d] >= rem) break;
+            rem -= s_hist[d];
+          }
+          s_rem = rem;
+          s_prefix = prefix | ((uint32_t)d << shift);
+        }
+        __syncthreads();
+      }
+      cut = s_prefix;        // the n_add-th smallest candidate priority
+      ties_wanted = s_rem;   // how many candidates == cut to take (lowest index first)
+    }
+    // ordered append of the chosen winners
+    int base = n, tie_base = 0, tie_total_all = 0;
+    for (int tile = 0; tile < Wp; tile += LA_THREADS) {
+      const int w = tile + t;
+      bool cand = false;
+      uint32_t bits = 0u;
+      if (w < Wp) {
+        bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
+        float pri = pr_ok ? __double2float_rn(pr[w]) : 2.0f;
+        bits = __float_as_uint(pri);
+        cand = !ex && pri < 1.0f;
+      }
+      const bool lt = cand && bits < cut;
+      const bool eq = cand && bits == cut && cut != 0x3f800000u;
+      int tot_eq, tot;
+      const int tie_rank = tie_base + block_excl_scan(eq ? 1 : 0, s_red, tot_eq);
+      const bool take = lt || (eq && tie_rank < ties_wanted);
+      const int pos = base + block_excl_scan(take ? 1 : 0, s_red, tot);
+      if (take) {
+        if (pos < E) {
+          cells[pos] = prevw[w];
+          perms[pos] = c.tm_perm_initial;
+        } else {
+          atomicOr(&c.sc[BH_SC_STATUS], BH_ST_SYN_OVERFLOW);
+        }
+      }
+      base += tot;
+      tie_base += tot_eq;
+      tie_total_all += tot_eq;
+    }
+    if (t == 0) {
+      c.seg_count[s] = base < E ? base : E;
+      if (tie_total_all > ties_wanted && nc > n_add) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_PRI_TIE);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Commit this step's activation and winner index (after learning read the previous
+// ones).  networks.py:118-119; projections.py:117-118 (whole_input_to_winner).
+// ---------------------------------------------------------------------------------
+__global__ void k_tm_post(const bh_ctx c) {
+  const int k = c.active_columns, cd = c.cell_dim;
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int* act = c.active_cols + cur * k;
+  const int* prev = c.active_cols + (cur ^ 1) * k;
+  const int Wc = c.sc[BH_SC_W0 + cur], Wp = c.sc[BH_SC_W0 + (cur ^ 1)];
+  const int* wl_cur = c.winners + (long long)cur * k * cd;
+  const int* wl_prev = c.winners + (long long)(cur ^ 1) * k * cd;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  for (int r = gid; r < k; r += gsz) {
+    c.col_act[act[r]] = c.row_act[r];
+    int pc = prev[r];
+    if (!c.col_active[pc]) c.col_act[pc] = 0u;
+  }
+  for (int i = gid; i < Wc; i += gsz) c.cell_widx[wl_cur[i]] = i;
+  for (int i = gid; i < Wp; i += gsz) {
+    int cell = wl_prev[i];
+    int col = cell / cd;
+    if (!((c.col_win[col] >> (cell - col * cd)) & 1u)) c.cell_widx[cell] = -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// (e) segment activation, part A: one warp per segment scans its synapses against
+// the active-cell bits.  potential = synapses to active cells (projections.py:175-178),
+// connected-active = those with permanence >= threshold (:167-173).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_a(const bh_ctx c) {
+  __shared__ int s_red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int cd = c.cell_dim, E = c.syn_capacity;
+  const int S = c.sc[BH_SC_NSEG];
+  const int thr = c.seg_matching_threshold;
+  const Range rg = block_range(S, b, nb);
+  int nm = 0, nr = 0;
+  for (int s = rg.begin + warp; s < rg.end; s += BH_TM_WARPS) {
+    const int n = c.seg_count[s];
+    const int* cells = c.syn_cell + (long long)s * E;
+    const float* perms = c.syn_perm + (long long)s * E;
+    int pot = 0, conn = 0;
+    for (int slot = lane; slot < n; slot += 32) {
+      const bool a = cell_bit(c.col_act, cells[slot], cd);
+      pot += a ? 1 : 0;
+      conn += (a && perms[slot] >= c.tm_perm_threshold) ? 1 : 0;
+    }
+    pot = warp_sum(pot);
+    conn = warp_sum(conn);
+    if (lane == 0) {
+      c.seg_pot[s] = pot;
+      c.seg_conn[s] = conn;
+      nm += pot >= thr ? 1 : 0;
+      nr += n < thr ? 1 : 0;
+    }
+  }
+  int tm = block_sum(nm, s_red);
+  int tr = block_sum(nr, s_red);
+  if (threadIdx.x == 0) {
+    BLK(c, BLK_MATCH)[b] = tm;
+    BLK(c, BLK_RECYC)[b] = tr;
+  }
+}
+
+// Part B: matching list in ascending segment id (np.where, projections.py:247),
+// jittered potential f32(f64(potential) + u) with the draw indexed by the rank in
+// that list (:234-235), per-cell maximum (:236-237) and active-segment count (:251).
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const bh_ctx c) {
+  __shared__ int s_red[32];
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int cd = c.cell_dim;
+  const int S = c.sc[BH_SC_NSEG];
+  const int thr = c.seg_matching_threshold;
+  const long long off3 = c.sc[BH_SC_OFF3];
+  const long long rand_fill = c.sc[BH_SC_RAND_FILL];
+  int m_before, m_total;
+  blk_prefix(BLK(c, BLK_MATCH), b, nb, s_red, m_before, m_total);
+  const Range rg = block_range(S, b, nb);
+  int base = m_before;
+  for (int tile = rg.begin; tile < rg.end; tile += BH_TM_THREADS) {
+    const int s = tile + threadIdx.x;
+    const bool ok = s < rg.end;
+    const int pot = ok ? c.seg_pot[s] : 0;
+    const bool match = ok && pot >= thr;
+    int tot;
+    const int rank = base + block_excl_scan(match ? 1 : 0, s_red, tot);
+    base += tot;
+    if (match && rank < c.match_capacity) {
+      const int conn = c.seg_conn[s];
+      const double u = (off3 + rank < rand_fill) ? c.rand_buf[off3 + rank] : 0.0;
+      const float jit = __double2float_rn(__dadd_rn((double)pot, u));
+      const int owner = c.seg_owner[s];
+      c.m_seg[rank] = s;
+      c.m_conn[rank] = conn;
+      c.m_jit[rank] = jit;
+      atomicMax(reinterpret_cast<int*>(c.cell_maxjit + owner), __float_as_int(jit));  // jit > 0
+      if (conn >= c.seg_activation_threshold) {
+        atomicAdd(&c.cell_npred[owner], 1);
+        const int col = owner / cd;
+        atomicOr(&c.col_pred[col], 1u << (owner - col * cd));
+      }
+    }
+  }
+  if (b == 0 && threadIdx.x == 0) {
+    c.sc[BH_SC_HAVE_PREV] = 1;
+    c.sc[BH_SC_STEP] = c.sc[BH_SC_STEP] + 1;
+  }
+}
+
+// Step summary for the host (bh_step_host): see include/bithtm_b200.h
+__global__ void k_summary(const bh_ctx c) {
+  const int k = c.active_columns;
+  const int done = c.sc[BH_SC_STEP] - 1;  // the step that just completed
+  const int cur = done & 1;
+  int* out = c.summary_dev;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[0] = done;
+    out[1] = c.sc[BH_SC_STATUS];
+    out[2] = c.sc[BH_SC_NSEG];
+    out[3] = c.sc[BH_SC_W0 + cur];
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+    out[4 + i] = c.active_cols[cur * k + i];
+    out[4 + k + i] = (int)c.row_pred[i];
+    out[4 + 2 * k + i] = (int)c.row_act[i];
+    out[4 + 3 * k + i] = (int)c.row_win[i];
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= BH_MT_N; i += gridDim.x * blockDim.x)
+    out[4 + 4 * k + i] = i < BH_MT_N ? (int)c.mt_key[i] : c.sc[BH_SC_MT_POS];
+}

@@ -1,0 +1,356 @@
+"""Network layer -- device-backed mirrors of ``bithtm/networks.py``:
+``SpatialPooler`` (:7-35), ``TemporalMemory`` (:38-128) and
+``HierarchicalTemporalMemory`` (:131-149) with the same constructor signatures,
+``process`` methods and State attribute names.  Extra keyword-only arguments
+size the device buffers (the reference grows its arrays without bound).
+
+Randomness: the reference draws from the global legacy ``np.random`` stream.
+Here the MT19937 state is advanced on the device; with ``rng_sync="step"``
+(default) the global ``np.random`` state is uploaded before and written back
+after every timestep, so a caller that also uses ``np.random`` (example.py:52)
+sees exactly the reference's stream.  ``rng_sync="lazy"`` uploads once and writes
+back only on :meth:`sync_rng` (no per-step host round trip).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as nat
+from ._engine import Engine
+from .projections import DenseProjection, PredictiveProjection, _Lazy
+from .regularizations import ExponentialBoosting, GlobalInhibition, eng_set_active
+
+
+def _bits(words: np.ndarray, c: int) -> np.ndarray:
+    """uint32 [n] -> bool [n, c] (bit b = cell b)."""
+    w = np.ascontiguousarray(words, dtype=np.uint32).reshape(-1, 1)
+    return ((w >> np.arange(c, dtype=np.uint32)) & np.uint32(1)).astype(bool)
+
+
+class _RngLink:
+    """Keeps the device MT19937 state and the global ``np.random`` state in step."""
+
+    def __init__(self, mode="step"):
+        assert mode in ("step", "lazy")
+        self.mode = mode
+        self._key = None
+        self._pos = None
+        self._seeded = False
+
+    def before(self, eng):
+        if self.mode == "lazy" and self._seeded:
+            return
+        st = np.random.get_state()
+        if self._seeded and st[2] == self._pos and np.array_equal(st[1], self._key):
+            self._tail = st[3:]
+            return
+        eng.set_rng_state(st[1], st[2])
+        self._key, self._pos, self._tail = st[1].copy(), st[2], st[3:]
+        self._seeded = True
+
+    def after(self, eng, summary=None):
+        if self.mode == "lazy":
+            return
+        if summary is None:
+            key, pos = eng.get_rng_state()
+        else:
+            k = eng.k
+            tail = summary[4 + 4 * k:4 + 4 * k + nat.MT_N + 1]
+            key, pos = tail[:nat.MT_N].view(np.uint32).copy(), int(tail[nat.MT_N])
+        np.random.set_state(("MT19937", key, pos) + tuple(self._tail))
+        self._key, self._pos = key, pos
+
+    def sync(self, eng):
+        key, pos = eng.get_rng_state()
+        tail = np.random.get_state()[3:]
+        np.random.set_state(("MT19937", key, pos) + tuple(tail))
+        self._key, self._pos = key, pos
+
+
+class SpatialPooler:
+    """networks.py:7-35."""
+
+    class State(_Lazy):
+        """networks.py:8-12.  ``overlaps`` (int64) and ``boosted_overlaps`` (float64)
+        are fetched from the device on first read."""
+
+        def __init__(self, engine, active_column=None):
+            super().__init__(engine)
+            if active_column is not None:
+                self._cache["active_column"] = active_column
+            # engine.epoch == completed steps == device step counter: parity of the
+            # ping-pong buffer this step's active columns were written to
+            self._parity = engine.epoch & 1
+            self._bh_engine_epoch = (engine, engine.epoch)
+
+        @property
+        def active_column(self):
+            def fetch():
+                eng, cur = self._engine, self._parity
+                return eng.buf["active_cols"][cur * eng.k:(cur + 1) * eng.k].cpu().numpy().astype(np.int64)
+
+            return self._get("active_column", fetch)
+
+        @property
+        def overlaps(self):
+            return self._get("overlaps", lambda: self._engine.buf["overlaps"].cpu().numpy().astype(np.int64))
+
+        @property
+        def boosted_overlaps(self):
+            return self._get("boosted_overlaps", lambda: self._engine.buf["boosted"].cpu().numpy())
+
+    def __init__(self, input_dim, column_dim, active_columns, proximal_projection=None, boosting=None,
+                 inhibition=None, **engine_kwargs):
+        self.input_dim = input_dim
+        self.column_dim = column_dim
+        self.active_columns = active_columns
+        self.proximal_projection = proximal_projection or DenseProjection(input_dim, column_dim)  # :22
+        self.boosting = boosting or ExponentialBoosting(column_dim, active_columns)  # :23
+        self.inhibition = inhibition or GlobalInhibition(active_columns)  # :24
+        if not isinstance(self.proximal_projection, DenseProjection) or not isinstance(self.boosting, ExponentialBoosting):
+            raise TypeError("bithtm_b200.SpatialPooler needs bithtm_b200 DenseProjection / ExponentialBoosting "
+                            "objects (device-backed); only `inhibition` may be an arbitrary host object")
+        self._engine_kwargs = engine_kwargs
+        self._engine = None
+        self._standalone_tm = False
+
+    @property
+    def _native_inhibition(self):
+        return getattr(self.inhibition, "_bh_native", False)
+
+    def _attach(self, engine):
+        self._engine = engine
+        self.proximal_projection._bind(engine)
+        self.boosting._bind(engine)
+        if self._native_inhibition:
+            self.inhibition._bind(engine)
+
+    def _ensure_engine(self):
+        if self._engine is None:
+            kw = dict(max_segments=64, max_synapses_per_segment=32)
+            kw.update(self._engine_kwargs)
+            self._attach(Engine(self.input_dim, self.column_dim, 1, self.active_columns, **kw))
+            self._standalone_tm = True
+        return self._engine
+
+    def process(self, input, learning=True):
+        """networks.py:26-35.  Leaves the active columns on the device for the TM."""
+        eng = self._ensure_engine()
+        self.boosting._bind(eng)
+        words = eng.pack_input(input)
+        if self._native_inhibition:
+            nat.check(nat.lib.bh_sp_step(eng.ref, words.data_ptr(), int(bool(learning)), eng.stream), "bh_sp_step")
+            state = self.State(eng)
+            if self._standalone_tm:
+                self._complete_step(state)
+            return state
+        # host inhibition (any object with .process(boosted) -> ordered active columns)
+        nat.check(nat.lib.bh_sp_overlap(eng.ref, words.data_ptr(), eng.stream), "bh_sp_overlap")
+        nat.check(nat.lib.bh_boost(eng.ref, eng.stream), "bh_boost")
+        boosted = eng.buf["boosted"].cpu().numpy()
+        active_column = np.asarray(self.inhibition.process(boosted))
+        eng_set_active(eng, active_column)
+        if learning:
+            nat.check(nat.lib.bh_sp_learn(eng.ref, words.data_ptr(), eng.stream), "bh_sp_learn")
+        nat.check(nat.lib.bh_duty_update(eng.ref, eng.stream), "bh_duty_update")
+        state = self.State(eng, active_column=active_column)
+        state._cache["boosted_overlaps"] = boosted
+        if self._standalone_tm:
+            self._complete_step(state)
+        return state
+
+    def _complete_step(self, state):
+        """No temporal memory follows: rotate the ping-pong buffers ourselves."""
+        eng = self._engine
+        nat.check(nat.lib.bh_advance_step(eng.ref, eng.stream), "bh_advance_step")
+        eng.epoch += 1
+        state._epoch = eng.epoch
+
+
+class TemporalMemory:
+    """networks.py:38-128."""
+
+    class State(_Lazy):
+        """networks.py:39-46.  Built from the per-step summary (active columns and
+        three bit-words per active column); ``cell_prediction`` and ``distal_state``
+        fields are fetched from the device on first read."""
+
+        def __init__(self, engine, projection, summary, have_winner=True):
+            super().__init__(engine)
+            k, c = engine.k, engine.c
+            s = summary
+            self._c, self._C = c, engine.C
+            self._active_column = s[4:4 + k].astype(np.int64)
+            self._row_pred = s[4 + k:4 + 2 * k].view(np.uint32).copy()
+            self._row_act = s[4 + 2 * k:4 + 3 * k].view(np.uint32).copy()
+            self._row_win = s[4 + 3 * k:4 + 4 * k].view(np.uint32).copy()
+            self._have_winner = have_winner
+            self.n_segments = int(s[2])
+            self.distal_state = PredictiveProjection.State(engine, projection)
+
+        def _cells(self, words):
+            rows, cells = np.nonzero(_bits(words, self._c))
+            return (self._active_column[rows], cells)
+
+        @property
+        def active_cell(self):  # networks.py:116-117
+            return self._get("active_cell", lambda: self._cells(self._row_act))
+
+        @property
+        def winner_cell(self):  # networks.py:103-104
+            if not self._have_winner:
+                return None
+            return self._get("winner_cell", lambda: self._cells(self._row_win))
+
+        @winner_cell.setter
+        def winner_cell(self, value):
+            self._cache["winner_cell"] = value
+
+        @property
+        def active_column_bursting(self):  # networks.py:97, bool [k, 1]
+            return (self._row_pred == 0).reshape(-1, 1)
+
+        @property
+        def cell_activation(self):  # networks.py:118-119, bool [C, c]
+            def build():
+                out = np.zeros((self._C, self._c), dtype=bool)
+                out[self._active_column] = _bits(self._row_act, self._c)
+                return out
+
+            return self._get("cell_activation", build)
+
+        @property
+        def cell_prediction(self):  # networks.py:122, bool [C, c]
+            return self._get("cell_prediction", lambda: _bits(
+                self._engine.buf["col_pred"].cpu().numpy().view(np.uint32), self._c))
+
+        def materialize(self):
+            self.cell_prediction
+            self.distal_state.materialize()
+            return self
+
+    class _EmptyState:
+        """networks.py:59-65."""
+
+        def __init__(self, column_dim, cell_dim):
+            self.active_cell = (np.empty(0, dtype=np.int32), np.empty(0, dtype=np.int32))
+            self.winner_cell = None
+            self.cell_activation = np.zeros((column_dim, cell_dim), dtype=np.bool_)
+            self.cell_prediction = np.zeros((column_dim, cell_dim), dtype=np.bool_)
+            self.active_column_bursting = np.empty(0, dtype=np.bool_)
+            self.distal_state = None
+
+    def __init__(self, column_dim, cell_dim, distal_projection=None, rng_sync="step", **engine_kwargs):
+        self.column_dim = column_dim
+        self.cell_dim = cell_dim
+        self.distal_projection = distal_projection or PredictiveProjection(column_dim * cell_dim)  # :55
+        if not isinstance(self.distal_projection, PredictiveProjection):
+            raise TypeError("bithtm_b200.TemporalMemory needs a bithtm_b200 PredictiveProjection (device-backed)")
+        self._engine_kwargs = engine_kwargs
+        self._engine = None
+        self._rng = _RngLink(rng_sync)
+        self.last_state = self.get_empty_state()  # :57
+
+    def get_empty_state(self):
+        return self._EmptyState(self.column_dim, self.cell_dim)
+
+    def flatten_cell(self, cell):  # networks.py:67-71
+        if cell is None:
+            return None
+        assert len(cell) == 2 and len(cell[0].shape) == 1
+        return cell[0] * self.cell_dim + cell[1]
+
+    def _attach(self, engine, epsilon=1e-8):
+        self._engine = engine
+        self.distal_projection._bind(engine, epsilon)
+
+    def sync_rng(self):
+        """Write the device MT19937 state back into the global np.random."""
+        if self._engine is not None:
+            self._rng.sync(self._engine)
+
+    def _finish(self, summary, have_winner=True):
+        eng = self._engine
+        eng.check_status(summary[1])
+        state = self.State(eng, self.distal_projection, summary, have_winner)
+        self.last_state = state
+        return state
+
+    def process(self, sp_state, prev_state=None, learning=True, return_winner_cell=True, epsilon=1e-8):
+        """networks.py:91-128."""
+        if prev_state is not None and prev_state is not self.last_state:
+            raise NotImplementedError("bithtm_b200.TemporalMemory keeps the previous state on the device; "
+                                      "an explicit prev_state other than last_state is not supported")
+        if not (learning or return_winner_cell):
+            raise NotImplementedError("return_winner_cell=False with learning=False is not implemented yet")
+        active_column = None
+        tag = getattr(sp_state, "_bh_engine_epoch", None)
+        if self._engine is None:
+            if tag is not None:
+                raise RuntimeError("attach SpatialPooler and TemporalMemory through HierarchicalTemporalMemory")
+            active_column = np.asarray(sp_state.active_column)
+            self._attach(Engine(1, self.column_dim, self.cell_dim, len(active_column), **self._engine_kwargs), epsilon)
+        eng = self._engine
+        self.distal_projection._bind(eng, epsilon)
+        on_device = tag is not None and tag[0] is eng and tag[1] == eng.epoch
+        if not on_device:
+            eng_set_active(eng, sp_state.active_column if active_column is None else active_column)
+        self._rng.before(eng)
+        nat.check(nat.lib.bh_tm_step(eng.ref, int(bool(learning)), eng.stream), "bh_tm_step")
+        eng.epoch += 1
+        summary = eng.summary()
+        self._rng.after(eng, summary)
+        return self._finish(summary)
+
+
+class HierarchicalTemporalMemory:
+    """networks.py:131-149."""
+
+    def __init__(self, input_dim, column_dim, cell_dim, active_columns=None, spatial_pooler=None,
+                 temporal_memory=None, rng_sync="step", device=None, **engine_kwargs):
+        if active_columns is None:
+            active_columns = round(column_dim * 0.02)  # :136-137
+        self.input_dim = input_dim
+        self.column_dim = column_dim
+        self.cell_dim = cell_dim
+        self.active_columns = active_columns
+        self.spatial_pooler = spatial_pooler or SpatialPooler(input_dim, column_dim, active_columns)  # :143
+        self.temporal_memory = temporal_memory or TemporalMemory(column_dim, cell_dim, rng_sync=rng_sync)  # :144
+        sp, tm = self.spatial_pooler, self.temporal_memory
+        if not isinstance(sp, SpatialPooler) or not isinstance(tm, TemporalMemory):
+            raise TypeError("bithtm_b200.HierarchicalTemporalMemory composes bithtm_b200 SpatialPooler / "
+                            "TemporalMemory objects")
+        if temporal_memory is None:
+            tm._rng = _RngLink(rng_sync)
+        if sp._engine is not None or tm._engine is not None:
+            raise NotImplementedError("spatial_pooler / temporal_memory were already used stand-alone")
+        self._engine = Engine(input_dim, column_dim, cell_dim, sp.active_columns, device=device, **engine_kwargs)
+        sp._attach(self._engine)
+        tm._attach(self._engine)
+
+    @property
+    def engine(self):
+        return self._engine
+
+    def sync_rng(self):
+        self.temporal_memory.sync_rng()
+
+    def process(self, input, learning=True):
+        """networks.py:146-149.  Host inputs go through ``bh_step_host`` (one H2D of
+        the packed input, the whole step on the device, one D2H of the step summary)."""
+        sp, tm, eng = self.spatial_pooler, self.temporal_memory, self._engine
+        is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
+        if not sp._native_inhibition or not is_host:
+            sp_state = sp.process(input, learning=learning)
+            tm_state = tm.process(sp_state, learning=learning)
+            sp_state._epoch = eng.epoch  # its buffers stay valid until the next step
+            return sp_state, tm_state
+        sp.boosting._bind(eng)
+        tm._rng.before(eng)
+        summary = eng.step_host(np.asarray(input).reshape(-1), learning=learning)
+        tm._rng.after(eng, summary)
+        tm_state = tm._finish(summary)
+        sp_state = sp.State(eng, active_column=tm_state._active_column)
+        sp_state._parity ^= 1  # created after the step completed
+        return sp_state, tm_state

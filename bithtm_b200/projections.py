@@ -1,0 +1,252 @@
+"""Projection plugins -- device-backed mirrors of ``bithtm/projections.py``.
+
+``DenseProjection`` (SP proximal synapses, projections.py:6-24) and
+``PredictiveProjection`` (TM distal segments, projections.py:194-293, built in the
+reference on ``SparseProjection`` :27-192).  Same class names, constructor
+arguments and defaults.  The arithmetic runs in ``libbithtm_b200.so``; these
+classes hold hyper-parameters, evaluate the constants with the reference's own
+Python expressions, and materialise results as NumPy arrays in the reference's
+dtypes when they are read.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as nat
+from .regularizations import eng_set_active
+
+
+class DenseProjection:
+    """projections.py:6-24.  The float64 permanence matrix and its bit-packed
+    connected mask live in HBM; ``permanence`` downloads a copy."""
+
+    def __init__(self, input_dim, output_dim, permanence_mean=0.0, permanence_std=0.1,
+                 permanence_threshold=0.0, permanence_increment=0.03, permanence_decrement=0.015):
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.permanence_threshold = permanence_threshold
+        self.permanence_increment = permanence_increment
+        self.permanence_decrement = permanence_decrement
+        # projections.py:16 -- the identical call, so the global np.random stream is
+        # consumed exactly as the reference consumes it (float64, first consumer).
+        self._host_permanence = np.random.randn(output_dim, input_dim) * permanence_std + permanence_mean
+        self._engine = None
+
+    def _constants(self):
+        both = self.permanence_increment + self.permanence_decrement
+        return dict(
+            sp_threshold=float(self.permanence_threshold),  # :19
+            sp_delta_on=float(1.0 * both - self.permanence_decrement),  # :24 with input bit True
+            sp_delta_off=float(0.0 * both - self.permanence_decrement),  # :24 with input bit False
+        )
+
+    def _bind(self, engine):
+        import torch
+
+        if self._engine is engine:
+            return
+        if self._engine is not None:
+            raise NotImplementedError("this DenseProjection is already attached to another network")
+        if (engine.I, engine.C) != (self.input_dim, self.output_dim):
+            raise ValueError("DenseProjection shape does not match the network")
+        self._engine = engine
+        for k, v in self._constants().items():
+            setattr(engine.ctx, k, v)
+        engine.buf["sp_perm"].copy_(torch.from_numpy(self._host_permanence.reshape(-1)).to(engine.device))
+        self._host_permanence = None
+        nat.check(nat.lib.bh_sp_build_mask(engine.ref, engine.stream), "bh_sp_build_mask")
+
+    def _need_engine(self):
+        if self._engine is None:
+            raise RuntimeError("DenseProjection is not attached to a network yet; construct a "
+                               "bithtm_b200 SpatialPooler with it (proximal_projection=...) first")
+        return self._engine
+
+    @property
+    def permanence(self):
+        if self._engine is None:
+            return self._host_permanence
+        return self._engine.buf["sp_perm"].cpu().numpy().reshape(self.output_dim, self.input_dim)
+
+    def process(self, input_activation):
+        """projections.py:18-21 -> int64 overlaps."""
+        eng = self._need_engine()
+        words = eng.pack_input(input_activation)
+        nat.check(nat.lib.bh_sp_overlap(eng.ref, words.data_ptr(), eng.stream), "bh_sp_overlap")
+        return eng.buf["overlaps"].cpu().numpy().astype(np.int64)
+
+    def update(self, input_activation, learning_output):
+        """projections.py:23-24."""
+        eng = self._need_engine()
+        for k, v in self._constants().items():
+            setattr(eng.ctx, k, v)
+        words = eng.pack_input(input_activation)
+        eng_set_active(eng, learning_output)
+        nat.check(nat.lib.bh_sp_learn(eng.ref, words.data_ptr(), eng.stream), "bh_sp_learn")
+
+
+class _Lazy:
+    """Fetch-on-first-read attribute holder tied to an engine epoch: device
+    buffers are overwritten by the next timestep, so a stale read raises instead
+    of returning another step's data."""
+
+    def __init__(self, engine):
+        self._engine = engine
+        self._epoch = engine.epoch
+        self._cache = {}
+
+    def _get(self, name, fn):
+        if name not in self._cache:
+            if self._engine.epoch != self._epoch:
+                raise RuntimeError(
+                    f"State.{name} was not read before the next timestep ran; its device buffer has been "
+                    "overwritten. Read it (or call .materialize()) right after process().")
+            self._cache[name] = fn()
+        return self._cache[name]
+
+
+class PredictiveProjection:
+    """projections.py:194-293.  Segment store in HBM: compact rows of
+    (presynaptic cell, float32 permanence), per-segment owner cell and count."""
+
+    class State(_Lazy):
+        """projections.py:195-203; every field is fetched from the device on first read."""
+
+        def __init__(self, engine, projection):
+            super().__init__(engine)
+            self._p = projection
+
+        def _scalars(self):
+            return self._get("_sc", self._engine.scalars)
+
+        @property
+        def _S(self):
+            return int(self._scalars()[nat.SC_NSEG])
+
+        @property
+        def _M(self):
+            return int(self._scalars()[nat.SC_M])
+
+        @property
+        def prediction(self):  # :251 float64 count of active segments per cell
+            return self._get("prediction", lambda: self._engine.buf["cell_npred"].cpu().numpy().astype(np.float64))
+
+        @property
+        def segment_potential(self):  # :246 int64 [S]
+            return self._get("segment_potential",
+                             lambda: self._engine.buf["seg_pot"][:self._S].cpu().numpy().astype(np.int64))
+
+        @property
+        def matching_segment(self):  # :247 int64 [M], ascending
+            return self._get("matching_segment",
+                             lambda: self._engine.buf["m_seg"][:self._M].cpu().numpy().astype(np.int64))
+
+        @property
+        def matching_segment_activation(self):  # :249
+            return self._get("matching_segment_activation",
+                             lambda: self._engine.buf["m_conn"][:self._M].cpu().numpy().astype(np.int64))
+
+        @property
+        def matching_segment_active(self):  # :250
+            return self.matching_segment_activation >= self._p.segment_activation_threshold
+
+        @property
+        def max_jittered_potential(self):  # :236-238 float32 [N]
+            return self._get("max_jittered_potential", lambda: self._engine.buf["cell_maxjit"].cpu().numpy())
+
+        @property
+        def matching_segment_jittered_potential(self):  # :234-235 float32 [M]
+            return self._get("matching_segment_jittered_potential",
+                             lambda: self._engine.buf["m_jit"][:self._M].cpu().numpy())
+
+        def materialize(self):
+            for n in ("prediction", "segment_potential", "matching_segment", "matching_segment_activation",
+                      "max_jittered_potential", "matching_segment_jittered_potential"):
+                getattr(self, n)
+            return self
+
+    def __init__(self, output_dim, permanence_initial=0.21, permanence_threshold=0.5, permanence_increment=0.1,
+                 permanence_decrement=0.1, permanence_punishment=0.01, segment_activation_threshold=15,
+                 segment_matching_threshold=15, segment_sampling_synapses=32,
+                 segment_bundle_growth_exponential=True):
+        assert segment_activation_threshold >= segment_matching_threshold  # projections.py:211
+        self.output_dim = output_dim
+        self.permanence_initial = permanence_initial
+        self.permanence_threshold = permanence_threshold
+        self.permanence_increment = permanence_increment
+        self.permanence_decrement = permanence_decrement
+        self.permanence_punishment = permanence_punishment
+        self.segment_activation_threshold = segment_activation_threshold
+        self.segment_matching_threshold = segment_matching_threshold
+        self.segment_sampling_synapses = segment_sampling_synapses
+        self._engine = None
+
+    @staticmethod
+    def _deltas(active_change, inactive_change):
+        # projections.py:102: bool array * float + float -> float64, evaluated per bit value
+        on = (np.array([True]) * (active_change - inactive_change) + inactive_change)[0]
+        off = (np.array([False]) * (active_change - inactive_change) + inactive_change)[0]
+        return float(on), float(off), int(min(active_change, inactive_change) < 0)  # :105
+
+    def _constants(self, epsilon=1e-8):
+        l_on, l_off, l_del = self._deltas(self.permanence_increment, -self.permanence_decrement)  # :287
+        p_on, p_off, p_del = self._deltas(-self.permanence_punishment, 0.0)  # :292
+        return dict(
+            tm_learn_on=l_on, tm_learn_off=l_off, tm_learn_can_delete=l_del,
+            tm_punish_on=p_on, tm_punish_off=p_off, tm_punish_can_delete=p_del,
+            tm_perm_initial=float(np.float32(self.permanence_initial)),  # :149
+            tm_perm_threshold=float(np.float32(self.permanence_threshold)),  # :171
+            epsilon=float(np.float32(epsilon)),
+            seg_activation_threshold=int(self.segment_activation_threshold),
+            seg_matching_threshold=int(self.segment_matching_threshold),
+            seg_sampling_synapses=int(self.segment_sampling_synapses),
+        )
+
+    def _bind(self, engine, epsilon=1e-8):
+        if self._engine is not None and self._engine is not engine:
+            raise NotImplementedError("this PredictiveProjection is already attached to another network")
+        if engine.N != self.output_dim:
+            raise ValueError("PredictiveProjection output_dim does not match column_dim * cell_dim")
+        self._engine = engine
+        for k, v in self._constants(epsilon).items():
+            setattr(engine.ctx, k, v)
+
+    # ---- read-only views of the learned state, in the reference's vocabulary -------
+    @property
+    def bundle_segments(self):  # projections.py:227 int32 [N]
+        if self._engine is None:
+            return np.zeros(self.output_dim, dtype=np.int32)
+        return self._engine.buf["cell_nseg"].cpu().numpy()
+
+    @property
+    def n_segments(self):
+        return 0 if self._engine is None else int(self._engine.scalars()[nat.SC_NSEG])
+
+    @property
+    def segment_bundle(self):  # projections.py:226 int32 [S, 1]
+        S = self.n_segments
+        if S == 0:
+            return np.zeros((0, 1), dtype=np.int32)
+        return self._engine.buf["seg_owner"][:S].cpu().numpy().reshape(S, 1)
+
+    def export_segments(self):
+        """(owner[S], count[S], cells[S, E], perm[S, E]) with free slots = -1 / -1.0 --
+        the row form ``oracle.digest.canonical_from_rows`` and an export shim consume."""
+        S = self.n_segments
+        eng = self._engine
+        E = eng.ctx.syn_capacity
+        owner = eng.buf["seg_owner"][:S].cpu().numpy()
+        count = eng.buf["seg_count"][:S].cpu().numpy()
+        cells = eng.buf["syn_cell"][:S * E].cpu().numpy().reshape(S, E).copy()
+        perm = eng.buf["syn_perm"][:S * E].cpu().numpy().reshape(S, E).copy()
+        free = np.arange(E)[None, :] >= count[:, None]
+        cells[free] = -1
+        perm[free] = -1.0
+        return owner, count, cells, perm
+
+    def process(self, active_input, return_jittered_potential_info=True):
+        raise NotImplementedError("call through bithtm_b200.TemporalMemory.process (the fused device path)")
+
+    def update(self, *args, **kwargs):
+        raise NotImplementedError("call through bithtm_b200.TemporalMemory.process (the fused device path)")

@@ -31,6 +31,7 @@ extern "C" {
 
 #define BH_ABI_VERSION 1
 #define BH_MT_N 624
+#define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 
 /* error codes (negative); CUDA errors are returned as -(1000 + cudaError_t) */
 #define BH_E_BADARG (-1)
@@ -158,8 +159,8 @@ typedef struct bh_ctx {
   uint32_t* input_ring;    /* [ring_len][input_words] packed inputs (bh_step_ring) */
   uint32_t* input_dev;     /* [input_words] staging for bh_step_host               */
   uint32_t* input_pinned;  /* HOST pinned [input_words]                            */
-  int32_t* summary_dev;    /* [4 + 4k] step summary (see bh_step_host)             */
-  int32_t* summary_pinned; /* HOST pinned [4 + 4k]                                 */
+  int32_t* summary_dev;    /* [BH_SUMMARY_INTS(k)] step summary (see bh_step_host) */
+  int32_t* summary_pinned; /* HOST pinned [BH_SUMMARY_INTS(k)]                     */
 } bh_ctx;
 
 /* Arena layout: fills every DEVICE pointer of `ctx` with `base + offset`, given
@@ -172,6 +173,8 @@ size_t bh_layout(bh_ctx* ctx, void* base);
 int bh_init(const bh_ctx* ctx, void* stream);
 
 int bh_abi_version(void);
+/* sizeof(bh_ctx) as compiled, so a binding can verify its struct mirror */
+size_t bh_ctx_size(void);
 int bh_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---- spatial pooler ------------------------------------------------------------- */
@@ -196,6 +199,10 @@ int bh_duty_update(const bh_ctx* ctx, void* stream);
 /* SpatialPooler.process (networks.py:26-35) = the five calls above */
 int bh_sp_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, void* stream);
 
+/* Complete a timestep when no temporal memory follows (stand-alone SpatialPooler):
+ * sc[BH_SC_STEP] += 1 so the ping-pong buffers rotate. */
+int bh_advance_step(const bh_ctx* ctx, void* stream);
+
 /* ---- temporal memory -------------------------------------------------------------- */
 /* networks.py:95-104: bursting + winner cells (consumes rand(k, c)) */
 int bh_tm_select(const bh_ctx* ctx, void* stream);
@@ -214,10 +221,16 @@ int bh_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, vo
 int bh_step_ring(const bh_ctx* ctx, int learning, void* stream);
 /* End-to-end call with HOST buffers: packs `input_bool_host` (I bytes), copies it
  * to the device, runs the step, copies the summary back and synchronises.
- * summary_host (4 + 4k int32): [0]=step index, [1]=status, [2]=n_segments,
- * [3]=winner count, then active_column[k], row_pred[k], row_act[k], row_win[k]. */
+ * summary_host (BH_SUMMARY_INTS(k) int32): [0]=step index, [1]=status, [2]=n_segments,
+ * [3]=winner count, then active_column[k], row_pred[k], row_act[k], row_win[k], then
+ * the MT19937 state after the step (624 key words + position) so the caller can
+ * keep np.random in lock-step. */
 int bh_step_host(const bh_ctx* ctx, const uint8_t* input_bool_host, int learning,
                  int32_t* summary_host, void* stream);
+
+/* Copy the summary of the last completed step to the host and synchronise (used
+ * after bh_tm_step / bh_step when the caller did not go through bh_step_host). */
+int bh_summary(const bh_ctx* ctx, int32_t* summary_host, void* stream);
 
 /* ---- CUDA graphs over bh_step_ring -------------------------------------------------- */
 int bh_graph_create(const bh_ctx* ctx, int steps_per_graph, int learning, void* stream, void** graph_exec_out);

@@ -1,0 +1,123 @@
+"""CPU suite (`-m "not gpu"`): the oracle against the golden traces generated from
+the unmodified reference, the np.exp restatement, and the C-ABI surface."""
+
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import golden_inputs, load_golden, oracle_state_digest
+from oracle.digest import record_digest
+from oracle.htm_oracle import HTMOracle, OracleConfig, canonical_topk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name,steps", [("tiny", None), ("odd", None), ("mid", 1500), ("cfg1", 400), ("cfg2", 400)])
+def test_oracle_matches_reference_golden(name, steps):
+    """Per-step digests and learned-state digests recorded from cokwa/bitHTM
+    (tests/golden/make_golden.py) are reproduced by the oracle."""
+    info = load_golden(name)
+    g = info["g"]
+    steps = info["steps"] if steps is None else steps
+    xs = golden_inputs(info, steps)
+    orc = HTMOracle(OracleConfig(info["I"], info["C"], info["c"], info["k"]),
+                    rng=np.random.RandomState(info["seed"]), overlap="packed")
+    state_at = {int(s): int(d) for s, d in zip(g["state_steps"], g["state_digests"])}
+    for t in range(steps):
+        rec = orc.step(xs[t])
+        assert record_digest(rec) == int(g["digests"][t]), f"{name}: step {t}"
+        assert rec.draws == int(g["draws"][t])
+        if t in state_at:
+            assert oracle_state_digest(orc) == state_at[t], f"{name}: learned state at step {t}"
+
+
+def test_oracle_dense_equals_packed_overlap():
+    cfg = OracleConfig(100, 200, 8, 12)
+    a = HTMOracle(cfg, rng=np.random.RandomState(5), overlap="dense")
+    b = HTMOracle(cfg, rng=np.random.RandomState(5), overlap="packed")
+    g = np.random.default_rng(0)
+    for _ in range(50):
+        x = g.random(100) < 0.3
+        assert record_digest(a.step(x)) == record_digest(b.step(x))
+
+
+def test_canonical_topk_rule():
+    keys = np.array([1.0, 3.0, 3.0, 0.5, 3.0, 2.0])
+    assert canonical_topk(keys, 2).tolist() == [1, 2]
+    assert canonical_topk(keys, 4).tolist() == [1, 2, 4, 5]
+    assert canonical_topk(np.zeros(5), 3).tolist() == [0, 1, 2]
+
+
+def test_np_expf_restatement_matches_numpy():
+    """bithtm_b200/csrc/np_expf.h (the sequence the boost kernel runs) == np.exp on float32."""
+    so = os.path.join(ROOT, "oracle", "_build", "libnpexp.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(so)
+    lib.bh_np_expf_array.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    g = np.random.default_rng(3)
+    x = np.concatenate([
+        -g.random(2_000_000, dtype=np.float32) * np.float32(15.5),
+        np.float32(-14.985366) * np.linspace(0, 1, 100_001, dtype=np.float32),
+        np.array([0.0, -0.0, -1e-30, -15.5, -80.0], dtype=np.float32),
+    ]).astype(np.float32)
+    y = np.empty_like(x)
+    lib.bh_np_expf_array(x.ctypes.data, y.ctypes.data, x.size)
+    assert np.array_equal(np.exp(x).view(np.uint32), y.view(np.uint32))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports every function the
+    header declares; the ctypes struct mirror has the compiled size."""
+    from bithtm_b200 import _native as nat
+
+    header = open(os.path.join(ROOT, "include", "bithtm_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t)\s+(bh_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(nat.lib, name), f"{name} not exported"
+    assert declared == set(nat.EXPORTED), declared ^ set(nat.EXPORTED)
+    assert nat.lib.bh_ctx_size() == ctypes.sizeof(nat.BhCtx)
+    assert nat.lib.bh_abi_version() == 1
+
+
+def test_layout_without_device():
+    """bh_layout(base=NULL) sizes the arena from the context alone (no compute)."""
+    from bithtm_b200 import _native as nat
+
+    ctx = nat.BhCtx()
+    ctx.input_dim, ctx.input_words, ctx.mask_stride = 1024, 32, 32
+    ctx.column_dim, ctx.cell_dim, ctx.active_columns = 2048, 32, 41
+    ctx.seg_capacity, ctx.syn_capacity, ctx.match_capacity, ctx.learn_capacity = 1 << 16, 128, 1 << 16, 1 << 17
+    ctx.tm_blocks, ctx.rand_capacity = 148, 1 << 20
+    n = nat.lib.bh_layout(ctypes.byref(ctx), None)
+    perm_bytes = 2048 * 1024 * 8
+    syn_bytes = (1 << 16) * 128 * 8
+    assert perm_bytes + syn_bytes < n < perm_bytes + syn_bytes + (64 << 20)
+    assert n % 256 == 0
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle."""
+    pkg = os.path.join(ROOT, "bithtm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import bithtm_b200
+    from bithtm_b200 import _native as nat
+
+    with pytest.raises(nat.NativeError):
+        bithtm_b200.HierarchicalTemporalMemory(64, 128, 8, 10)

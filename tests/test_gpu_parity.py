@@ -1,0 +1,282 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the reference-facing
+classes / C ABI, against the NumPy oracle on the same seeded inputs and against
+the golden traces recorded from the unmodified reference.  Bit-exact everywhere.
+"""
+
+import numpy as np
+import pytest
+
+from helpers import (diff_records, golden_inputs, gpu_record, gpu_state_digest, load_golden, oracle_record,
+                     oracle_state_digest, step_digest)
+from oracle.htm_oracle import HTMOracle, OracleConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(I=64, C=128, c=8, k=10, **kw):
+    from bithtm_b200._engine import Engine
+
+    return Engine(I, C, c, k, max_segments=256, **kw)
+
+
+# ------------------------------------------------------------------ building blocks
+def test_device_mt19937_matches_numpy_stream():
+    """bh_rng_fill == np.random.random_sample for any count / position, including
+    odd word positions and block boundaries (networks.py:87, projections.py:120,235)."""
+    eng = _engine()
+    rs = np.random.RandomState(12345)
+    rs.randn(7)  # leave the state mid-block
+    rs.randint(0, 10, size=3)  # odd number of 32-bit words consumed
+    st = rs.get_state()
+    eng.set_rng_state(st[1], st[2])
+    for count in [0, 1, 5, 311, 312, 313, 623, 624, 625, 1, 1000, 4096, 100_003]:
+        got = eng.rng_fill(count)
+        want = rs.random_sample(count)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), f"count {count}"
+    key, pos = eng.get_rng_state()
+    st = rs.get_state()
+    # same continuation: (key, pos) may differ in representation only at pos == 624
+    rs2 = np.random.RandomState()
+    rs2.set_state(("MT19937", key, pos, 0, 0.0))
+    assert np.array_equal(rs2.random_sample(1000), rs.random_sample(1000))
+
+
+def test_device_np_expf_matches_numpy():
+    """The boost kernel's exp == np.exp(float32) bit for bit (regularizations.py:16)."""
+    import ctypes
+
+    import torch
+
+    from bithtm_b200 import _native as nat
+
+    g = np.random.default_rng(7)
+    x = np.concatenate([
+        -g.random(4_000_000, dtype=np.float32) * np.float32(15.5),
+        np.array([0.0, -0.0, -1e-30, -15.5, -14.985366], dtype=np.float32),
+    ]).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nat.check(nat.lib.bh_test_np_expf(xd.data_ptr(), yd.data_ptr(), x.size, st))
+    y = yd.cpu().numpy()
+    assert np.array_equal(np.exp(x).view(np.uint32), y.view(np.uint32))
+
+
+@pytest.mark.parametrize("I,C,k", [(64, 128, 10), (200, 300, 25), (1000, 2048, 41), (1024, 2048, 41), (4100, 512, 20)])
+def test_spatial_pooler_operators(I, C, k):
+    """DenseProjection.process/update, ExponentialBoosting.process/update and
+    GlobalInhibition.process one by one against the oracle (projections.py:18-24,
+    regularizations.py:15-29)."""
+    import bithtm_b200 as bithtm
+
+    seed = 11
+    np.random.seed(seed)
+    sp = bithtm.SpatialPooler(I, C, k)
+    orc = HTMOracle(OracleConfig(I, C, 4, k), rng=np.random.RandomState(seed))
+    assert np.array_equal(sp.proximal_projection.permanence, orc.permanence)
+    g = np.random.default_rng(seed)
+    for t in range(25):
+        x = g.random(I) < 0.2
+        st = sp.process(x, learning=True)
+        ov = orc.sp_overlap(x)
+        bo = orc.sp_boost(ov)
+        ac = orc.sp_inhibit(bo)
+        orc.sp_learn(x, ac)
+        orc.sp_duty_update(ac)
+        assert np.array_equal(st.overlaps, ov), f"overlaps step {t}"
+        assert st.overlaps.dtype == np.int64 and st.boosted_overlaps.dtype == np.float64
+        assert np.array_equal(st.boosted_overlaps.view(np.uint64), bo.view(np.uint64)), f"boosted step {t}"
+        assert np.array_equal(st.active_column, ac), f"active columns step {t}"
+        assert np.array_equal(sp.boosting.duty_cycle.view(np.uint32), orc.duty.view(np.uint32)), f"duty step {t}"
+    assert np.array_equal(sp.proximal_projection.permanence.view(np.uint64), orc.permanence.view(np.uint64))
+    # plugin-granularity calls
+    x = g.random(I) < 0.2
+    assert np.array_equal(sp.proximal_projection.process(x), orc.sp_overlap(x))
+
+
+def test_topk_ties_take_lowest_index():
+    """All-equal keys (zero duty, equal overlaps happen in the first steps): the
+    canonical rule picks the lowest indices, ascending."""
+    import bithtm_b200 as bithtm
+
+    np.random.seed(0)
+    sp = bithtm.SpatialPooler(64, 512, 7)
+    sp._ensure_engine()
+    keys = np.zeros(512)
+    keys[[5, 100, 300]] = 2.0
+    keys[[7, 9, 200, 400, 500]] = 1.0
+    got = sp.inhibition.process(keys)
+    assert got.tolist() == [5, 7, 9, 100, 200, 300, 400]
+
+
+# ------------------------------------------------------------------ lock-step SP+TM
+def _lockstep(name, steps=None, check_every=1, **engine_kw):
+    import bithtm_b200 as bithtm
+
+    info = load_golden(name)
+    g = info["g"]
+    steps = info["steps"] if steps is None else steps
+    xs = golden_inputs(info, steps)
+    np.random.seed(info["seed"])
+    htm = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], **engine_kw)
+    orc = HTMOracle(OracleConfig(info["I"], info["C"], info["c"], info["k"]),
+                    rng=np.random.RandomState(info["seed"]), overlap="packed")
+    state_at = {int(s): int(d) for s, d in zip(g["state_steps"], g["state_digests"])}
+    for t in range(steps):
+        sp_state, tm_state = htm.process(xs[t])
+        rec = orc.step(xs[t])
+        if t % check_every == 0 or t in state_at or t < 50:
+            got, want = gpu_record(htm, sp_state, tm_state), oracle_record(rec)
+            problems = diff_records(got, want)
+            assert not problems, f"{name} step {t}: " + "; ".join(problems) + f"; sc={htm.engine.scalars()[:18]}"
+            assert step_digest(**got) == int(g["digests"][t]), f"{name} step {t}: golden digest"
+        if t in state_at:
+            assert gpu_state_digest(htm) == oracle_state_digest(orc) == state_at[t], f"{name}: learned state, step {t}"
+    # the caller's np.random stream stayed in lock-step with the reference's
+    a, b = np.random.get_state(), orc.rng.get_state()
+    assert np.array_equal(np.random.random_sample(64), orc.rng.random_sample(64)), (a[2], b[2])
+    assert htm.engine.check_status() & ~32 == 0
+    return htm, orc
+
+
+def test_lockstep_tiny():
+    _lockstep("tiny")
+
+
+def test_lockstep_odd_dims():
+    _lockstep("odd")
+
+
+def test_lockstep_mid():
+    _lockstep("mid", check_every=3)
+
+
+def test_lockstep_cfg2_1500_steps():
+    _lockstep("cfg2", steps=1500, check_every=10)
+
+
+def _golden_trace(name, **engine_kw):
+    """Full-length run compared with the digests recorded from the reference."""
+    import bithtm_b200 as bithtm
+
+    info = load_golden(name)
+    g = info["g"]
+    xs = golden_inputs(info)
+    np.random.seed(info["seed"])
+    htm = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], **engine_kw)
+    state_at = {int(s): int(d) for s, d in zip(g["state_steps"], g["state_digests"])}
+    for t in range(info["steps"]):
+        sp_state, tm_state = htm.process(xs[t])
+        d = step_digest(**gpu_record(htm, sp_state, tm_state))
+        assert d == int(g["digests"][t]), f"{name}: step {t} differs from the reference"
+        if t in state_at:
+            assert gpu_state_digest(htm) == state_at[t], f"{name}: learned state at step {t}"
+    assert tm_state.n_segments == int(g["n_segments_final"])
+    assert htm.engine.check_status() & ~32 == 0
+
+
+def test_cfg1_10k_steps_against_reference_trace():
+    """BASELINE configs[0]: example.py defaults, 10 000 steps, bit-exact."""
+    _golden_trace("cfg1")
+
+
+def test_cfg2_10k_steps_against_reference_trace():
+    """BASELINE configs[1]: 2048 columns x 1024 inputs, 10 000 steps, bit-exact."""
+    _golden_trace("cfg2")
+
+
+# ------------------------------------------------------------------ other call paths
+def test_host_inhibition_mode_matches_argpartition_oracle():
+    """Secondary parity mode: any host object in the reference's
+    `inhibition=` slot; here np.argpartition itself, same NumPy on both sides."""
+    import bithtm_b200 as bithtm
+
+    class ArgpartitionInhibition:  # regularizations.py:24-29, verbatim semantics
+        def __init__(self, k):
+            self.k = k
+
+        def process(self, x):
+            return np.argpartition(x, -self.k)[-self.k:]
+
+    I, C, c, k, seed = 128, 256, 16, 20, 4
+    np.random.seed(seed)
+    sp = bithtm.SpatialPooler(I, C, k, inhibition=ArgpartitionInhibition(k))
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp)
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed), inhibition="argpartition")
+    g = np.random.default_rng(seed)
+    base = g.random((10, I)) < 0.25
+    for t in range(400):
+        x = base[t % 10] ^ (g.random(I) < 0.05)
+        sp_state, tm_state = htm.process(x)
+        rec = orc.step(x)
+        problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not problems, f"step {t}: " + "; ".join(problems)
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
+
+
+def test_learning_off_matches_oracle():
+    """learning=False: no permanence/segment updates but duty cycles still move
+    (networks.py:31-33) and winners/jitter are still drawn."""
+    import bithtm_b200 as bithtm
+
+    I, C, c, k, seed = 96, 256, 12, 20, 9
+    np.random.seed(seed)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k)
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    g = np.random.default_rng(seed)
+    base = g.random((8, I)) < 0.25
+    for t in range(300):
+        x = base[t % 8] ^ (g.random(I) < 0.03)
+        learning = not (100 <= t < 200)
+        sp_state, tm_state = htm.process(x, learning=learning)
+        rec = orc.step(x, learning=learning)
+        problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not problems, f"step {t} (learning={learning}): " + "; ".join(problems)
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
+
+
+def test_graph_replay_equals_stepwise():
+    """bh_step_ring under a CUDA graph (the bench's device-resident path) ends in
+    the same learned state as the host-driven path."""
+    import bithtm_b200 as bithtm
+
+    info = load_golden("mid")
+    steps = 500
+    xs = golden_inputs(info, steps)
+    np.random.seed(info["seed"])
+    a = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], rng_sync="lazy")
+    np.random.seed(info["seed"])
+    b = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], rng_sync="lazy",
+                                          ring_len=steps)
+    for t in range(steps):
+        a.process(xs[t])
+    eng = b.engine
+    b.temporal_memory._rng.before(eng)
+    eng.load_ring(xs)
+    per = 20
+    handle = eng.graph(per, learning=True)
+    for _ in range(steps // per):
+        eng.launch_graph(handle, per)
+    import torch
+
+    torch.cuda.synchronize()
+    assert gpu_state_digest(a) == gpu_state_digest(b)
+    assert np.array_equal(a.engine.scalars()[:5], b.engine.scalars()[:5])
+    info_g = info["g"]
+    state_at = {int(s): int(d) for s, d in zip(info_g["state_steps"], info_g["state_digests"])}
+    if steps - 1 in state_at:
+        assert gpu_state_digest(b) == state_at[steps - 1]
+
+
+def test_stale_state_read_raises():
+    import bithtm_b200 as bithtm
+
+    np.random.seed(1)
+    htm = bithtm.HierarchicalTemporalMemory(64, 128, 8, 10)
+    x = np.random.default_rng(0).random(64) < 0.3
+    sp1, tm1 = htm.process(x)
+    sp1.overlaps  # read in time: cached
+    htm.process(x)
+    assert sp1.overlaps is not None
+    with pytest.raises(RuntimeError):
+        tm1.distal_state.prediction
