@@ -204,6 +204,16 @@ class Engine:
         self.epoch += 1
         return self._summary_out
 
+    def profile_step(self, words, learning=True):
+        """One step with a CUDA event after every launch -> [(kernel name, milliseconds)]."""
+        ms = (C.c_float * 48)()
+        names = (C.c_char_p * 48)()
+        n = nat.lib.bh_profile_step(self.ref, words.data_ptr(), int(bool(learning)), self.stream, ms, names, 48)
+        if n < 0:
+            nat.check(n, "bh_profile_step")
+        self.epoch += 1
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
     def summary(self) -> np.ndarray:
         nat.check(nat.lib.bh_summary(self.ref, self._summary_out.ctypes.data, self.stream), "bh_summary")
         return self._summary_out

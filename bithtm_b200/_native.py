@@ -116,6 +116,7 @@ _SIGNATURES = {
     "bh_graph_create": (C.c_int, [_CTXP, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     "bh_graph_launch": (C.c_int, [_P, _P]),
     "bh_graph_destroy": (C.c_int, [_P]),
+    "bh_profile_step": (C.c_int, [_CTXP, _P, C.c_int, _P, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]),
     "bh_step_launches": (C.c_int, [_CTXP, C.c_int]),
     "bh_rng_fill": (C.c_int, [_CTXP, _P, C.c_int64, _P]),
     "bh_test_np_expf": (C.c_int, [_P, _P, C.c_int64, _P]),

@@ -13,7 +13,27 @@
     cudaError_t e__ = (expr);                          \
     if (e__ != cudaSuccess) return -(1000 + (int)e__); \
   } while (0)
-#define LAUNCH_CHECK() CU_RET(cudaGetLastError())
+
+// Optional per-launch CUDA-event timing (bh_profile_step): every kernel launch site
+// ends with LAUNCHED("name"), which records an event on the launching stream.
+#define BH_PROF_MAX 48
+struct ProfileRec {
+  cudaEvent_t ev[BH_PROF_MAX + 1];
+  const char* name[BH_PROF_MAX];
+  int n;
+  cudaStream_t st;
+};
+static thread_local ProfileRec* g_prof = nullptr;
+
+#define LAUNCHED(nm)                                            \
+  do {                                                          \
+    CU_RET(cudaGetLastError());                                 \
+    if (g_prof && g_prof->n < BH_PROF_MAX) {                    \
+      g_prof->name[g_prof->n] = nm;                             \
+      cudaEventRecord(g_prof->ev[++g_prof->n], g_prof->st);     \
+    }                                                           \
+  } while (0)
+#define LAUNCH_CHECK() LAUNCHED("misc")
 
 static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -158,7 +178,7 @@ static int launch_overlap(const bh_ctx* x, const uint32_t* in, cudaStream_t st) 
   int rows_per_block = (SP_THREADS / 32) * (32 / g);
   size_t smem = (size_t)x->mask_stride * 4;
   k_sp_overlap<BOOST><<<sp_grid(x, rows_per_block), SP_THREADS, smem, st>>>(*x, in, g);
-  LAUNCH_CHECK();
+  LAUNCHED(BOOST ? "sp_overlap_boost" : "sp_overlap");
   return 0;
 }
 
@@ -174,7 +194,7 @@ extern "C" int bh_boost(const bh_ctx* x, void* stream) {
 
 extern "C" int bh_inhibit(const bh_ctx* x, void* stream) {
   k_topk<<<1, TOPK_THREADS, 0, S_(stream)>>>(*x);
-  LAUNCH_CHECK();
+  LAUNCHED("topk");
   return 0;
 }
 
@@ -188,13 +208,13 @@ extern "C" int bh_sp_learn(const bh_ctx* x, const uint32_t* in, void* stream) {
   int cap = (x->sm_count > 0 ? x->sm_count : 148) * 8;
   int grid = x->active_columns < cap ? x->active_columns : cap;
   k_sp_learn<<<grid, SP_THREADS, 0, S_(stream)>>>(*x, in);
-  LAUNCH_CHECK();
+  LAUNCHED("sp_learn");
   return 0;
 }
 
 extern "C" int bh_duty_update(const bh_ctx* x, void* stream) {
   k_duty_update<<<cdiv(x->column_dim, 256), 256, 0, S_(stream)>>>(*x);
-  LAUNCH_CHECK();
+  LAUNCHED("duty_update");
   return 0;
 }
 
@@ -226,11 +246,11 @@ extern "C" int bh_advance_step(const bh_ctx* x, void* stream) {
 extern "C" int bh_tm_select(const bh_ctx* x, void* stream) {
   cudaStream_t st = S_(stream);
   k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 1, 1);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_draw1");
   k_tm_select_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_select_a");
   k_tm_select_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_select_b");
   return 0;
 }
 
@@ -242,11 +262,11 @@ static int learn_apply_smem(const bh_ctx* x) {
 extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
   cudaStream_t st = S_(stream);
   k_tm_learn_select_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, learning);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_learn_select_a");
   k_tm_learn_select_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, learning);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_learn_select_b");
   k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 2, learning);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_draw2");
   if (learning) {
     int smem = learn_apply_smem(x);
     if (smem > 200 * 1024) return BH_E_UNSUPPORTED;
@@ -254,7 +274,7 @@ extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
       CU_RET(cudaFuncSetAttribute(k_tm_learn_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = (x->sm_count > 0 ? x->sm_count : 148) * 8;
     k_tm_learn_apply<<<grid, LA_THREADS, smem, st>>>(*x);
-    LAUNCH_CHECK();
+    LAUNCHED("tm_learn_apply");
   }
   return 0;
 }
@@ -263,13 +283,13 @@ extern "C" int bh_tm_activate(const bh_ctx* x, void* stream) {
   cudaStream_t st = S_(stream);
   int k = x->active_columns, kc = k * x->cell_dim;
   k_tm_post<<<cdiv(kc, 256) < 256 ? cdiv(kc, 256) : 256, 256, 0, st>>>(*x);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_post");
   k_tm_activate_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_activate_a");
   k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 3, 1);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_draw3");
   k_tm_activate_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
-  LAUNCH_CHECK();
+  LAUNCHED("tm_activate_b");
   return 0;
 }
 
@@ -312,7 +332,7 @@ __global__ void k_ring_fetch(const bh_ctx c) {
 extern "C" int bh_step_ring(const bh_ctx* x, int learning, void* stream) {
   if (!x || x->ring_len <= 0) return BH_E_BADARG;
   k_ring_fetch<<<1, 256, 0, S_(stream)>>>(*x);
-  LAUNCH_CHECK();
+  LAUNCHED("ring_fetch");
   return bh_step(x, x->input_dev, learning, stream);
 }
 
@@ -348,6 +368,33 @@ extern "C" int bh_summary(const bh_ctx* x, int32_t* summary_host, void* stream) 
   CU_RET(cudaStreamSynchronize(st));
   if (summary_host) memcpy(summary_host, x->summary_pinned, bytes);
   return 0;
+}
+
+// One step with a CUDA event after every launch; per-launch milliseconds and names.
+extern "C" int bh_profile_step(const bh_ctx* x, const uint32_t* in, int learning, void* stream, float* ms_out,
+                               const char** names_out, int max_out) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  ProfileRec rec;
+  rec.n = 0;
+  rec.st = S_(stream);
+  for (int i = 0; i <= BH_PROF_MAX; ++i) CU_RET(cudaEventCreate(&rec.ev[i]));
+  CU_RET(cudaEventRecord(rec.ev[0], rec.st));
+  g_prof = &rec;
+  rc = bh_step(x, in, learning, stream);
+  g_prof = nullptr;
+  cudaError_t e = cudaStreamSynchronize(rec.st);
+  int n = 0;
+  if (rc == 0 && e == cudaSuccess) {
+    for (; n < rec.n && n < max_out; ++n) {
+      cudaEventElapsedTime(&ms_out[n], rec.ev[n], rec.ev[n + 1]);
+      if (names_out) names_out[n] = rec.name[n];
+    }
+  }
+  for (int i = 0; i <= BH_PROF_MAX; ++i) cudaEventDestroy(rec.ev[i]);
+  if (rc) return rc;
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  return n;
 }
 
 // ------------------------------------------------------------------------------------

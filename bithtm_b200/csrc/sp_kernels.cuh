@@ -91,18 +91,45 @@ __global__ void k_boost(const bh_ctx c) {
 // ---------------------------------------------------------------------------------
 // (b) canonical global inhibition: k largest keys, ties -> lower column index,
 // output ascending.  Keys are non-negative doubles, so their bit patterns order
-// like unsigned integers: MSB-first radix select (8 x 8 bits) for the k-th key,
-// then an ordered compaction.  Single CTA of 1024 threads.
+// like unsigned integers.  Single CTA:
+//   1. block min/max -> the leading bits all keys share are skipped;
+//   2. 8-bit MSB-first radix passes (warp-aggregated shared-memory histogram,
+//      warp-parallel bin scan) until the bin holding the k-th key has at most
+//      TOPK_THREADS members (usually one pass);
+//   3. those candidates are ranked by (key desc, index asc) by counting, which
+//      yields the exact k-th (key, index) pair;
+//   4. ordered compaction over the column index.
+// If all 64 bits are consumed and the bin is still larger (many equal keys), the
+// lowest indices among the equal keys are taken by an ordered tie count.
 // regularizations.py:28-29 (np.argpartition's tie-break/order are undefined).
 // ---------------------------------------------------------------------------------
 #define TOPK_THREADS 1024
 
+__device__ __forceinline__ unsigned long long block_reduce_u64(unsigned long long v, bool want_max,
+                                                               unsigned long long* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long n = __shfl_xor_sync(BH_FULL, v, o);
+    v = want_max ? (n > v ? n : v) : (n < v ? n : v);
+  }
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  unsigned long long r = sm[0];
+  for (int i = 1; i < nw; ++i) r = want_max ? (sm[i] > r ? sm[i] : r) : (sm[i] < r ? sm[i] : r);
+  return r;
+}
+
 __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
   __shared__ int hist[256];
   __shared__ int s_scan[32];
-  __shared__ unsigned long long s_prefix;
-  __shared__ int s_remaining;
-  const int t = threadIdx.x;
+  __shared__ unsigned long long s_u64[32];
+  __shared__ unsigned long long cand_key[TOPK_THREADS];
+  __shared__ int cand_idx[TOPK_THREADS];
+  __shared__ int s_bin, s_rem, s_ncand, s_kth_idx;
+  __shared__ unsigned long long s_kth_key;
+  const int t = threadIdx.x, lane = t & 31;
   const int C = c.column_dim, k = c.active_columns;
   const int cur = c.sc[BH_SC_STEP] & 1;
   int* out = c.active_cols + cur * k;
@@ -111,52 +138,138 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
 
   // retire the previous step's column flags
   for (int i = t; i < k; i += TOPK_THREADS) c.col_active[prev[i]] = 0;
-  if (t == 0) { s_prefix = 0ull; s_remaining = k; }
-  __syncthreads();
 
-  for (int pass = 7; pass >= 0; --pass) {
+  // 1. shared leading bits
+  unsigned long long mn = ~0ull, mx = 0ull;
+  for (int j = t; j < C; j += TOPK_THREADS) {
+    unsigned long long key = keys[j];
+    mn = key < mn ? key : mn;
+    mx = key > mx ? key : mx;
+  }
+  mn = block_reduce_u64(mn, false, s_u64);
+  mx = block_reduce_u64(mx, true, s_u64);
+  int consumed = (mn == mx) ? 64 : __clzll((long long)(mn ^ mx));  // bits known equal for all candidates
+  unsigned long long prefix = (consumed == 0) ? 0ull : (consumed == 64 ? mx : (mx >> (64 - consumed)) << (64 - consumed));
+  int rem = k;       // how many still to take from the current candidate set
+  int ncand = C;     // size of the current candidate set (keys matching `prefix` on the consumed bits)
+
+  // 2. radix passes
+  while (consumed < 64 && ncand > TOPK_THREADS) {
+    const int shift = (64 - consumed - 8) > 0 ? (64 - consumed - 8) : 0;
+    const int width = 64 - consumed - shift;  // 1..8 bits
+    const unsigned long long hi_mask = consumed == 0 ? 0ull : (~0ull << (64 - consumed));
     for (int i = t; i < 256; i += TOPK_THREADS) hist[i] = 0;
     __syncthreads();
-    const unsigned long long prefix = s_prefix;
-    const int shift = pass * 8;
-    const unsigned long long hi_mask = pass == 7 ? 0ull : (~0ull << (shift + 8));
-    for (int j = t; j < C; j += TOPK_THREADS) {
-      unsigned long long key = keys[j];
-      if ((key & hi_mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xff)], 1);
+    for (int base = 0; base < C; base += TOPK_THREADS) {
+      const int j = base + t;
+      const unsigned long long key = j < C ? keys[j] : 0ull;
+      const bool in = j < C && (key & hi_mask) == prefix;
+      const int d = (int)((key >> shift) & ((1u << width) - 1u));
+      // warp-aggregated histogram: one shared atomic per distinct digit per warp
+      const unsigned peers = __match_any_sync(BH_FULL, in ? d : -1);
+      if (in && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], __popc(peers));
     }
     __syncthreads();
-    if (t == 0) {
-      int rem = s_remaining, d = 255;
-      for (; d > 0; --d) {
-        if (hist[d] >= rem) break;
-        rem -= hist[d];
+    if (t < 32) {
+      // bins in descending order, 8 per lane: lane 0 owns bins 255..248
+      int local[8], sum = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        local[i] = hist[255 - (lane * 8 + i)];
+        sum += local[i];
       }
-      s_remaining = rem;  // still needed from bin d (d == 0 takes whatever is left)
-      s_prefix = prefix | ((unsigned long long)d << shift);
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(BH_FULL, incl, o);
+        if (lane >= o) incl += n;
+      }
+      const int before = incl - sum;  // keys in bins above this lane's bins
+      const bool mine = before < rem && incl >= rem;
+      if (mine) {
+        int r = rem - before;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (r > 0 && local[i] >= r) {
+            s_bin = 255 - (lane * 8 + i);
+            s_rem = r;
+            s_ncand = local[i];
+            r = -1;
+          } else if (r > 0) {
+            r -= local[i];
+          }
+        }
+      }
     }
+    __syncthreads();
+    prefix |= (unsigned long long)s_bin << shift;
+    rem = s_rem;
+    ncand = s_ncand;
+    consumed += width;
     __syncthreads();
   }
-  const unsigned long long kth = s_prefix;  // value of the k-th largest key
-  const int ties_wanted = s_remaining;      // how many keys == kth to take (lowest index first)
-  __syncthreads();
 
-  // ordered compaction over column index, tiles of 1024
+  // 3. exact k-th (key, index)
+  bool tie_mode = false;           // many identical keys: take the `rem` lowest indices among them
+  unsigned long long kth_key = prefix;
+  int kth_idx = 0x7fffffff;
+  if (ncand > TOPK_THREADS) {
+    tie_mode = true;               // consumed == 64: every candidate equals prefix
+  } else {
+    const unsigned long long hi_mask = consumed == 0 ? 0ull : (consumed == 64 ? ~0ull : (~0ull << (64 - consumed)));
+    if (t == 0) s_ncand = 0;
+    __syncthreads();
+    for (int j = t; j < C; j += TOPK_THREADS) {
+      const unsigned long long key = keys[j];
+      if ((key & hi_mask) == prefix) {
+        const int p = atomicAdd(&s_ncand, 1);
+        cand_key[p] = key;
+        cand_idx[p] = j;
+      }
+    }
+    __syncthreads();
+    const int n = s_ncand;
+    if (t < n) {
+      const unsigned long long mk = cand_key[t];
+      const int mi = cand_idx[t];
+      int ahead = 0;
+      for (int i = 0; i < n; ++i) {
+        const unsigned long long ok = cand_key[i];
+        ahead += (ok > mk || (ok == mk && cand_idx[i] < mi)) ? 1 : 0;
+      }
+      if (ahead == rem - 1) {
+        s_kth_key = mk;
+        s_kth_idx = mi;
+      }
+    }
+    __syncthreads();
+    kth_key = s_kth_key;
+    kth_idx = s_kth_idx;
+  }
+
+  // 4. ordered compaction over column index
   int base_sel = 0, base_tie = 0;
   for (int tile = 0; tile < C; tile += TOPK_THREADS) {
-    int j = tile + t;
-    unsigned long long key = j < C ? keys[j] : 0ull;
-    bool gt = j < C && key > kth;
-    bool eq = j < C && key == kth;
-    int tie_total, sel_total;
-    int tie_rank = base_tie + block_excl_scan(eq ? 1 : 0, s_scan, tie_total);
-    bool take = gt || (eq && tie_rank < ties_wanted);
-    int pos = base_sel + block_excl_scan(take ? 1 : 0, s_scan, sel_total);
+    const int j = tile + t;
+    const unsigned long long key = j < C ? keys[j] : 0ull;
+    const bool gt = j < C && key > kth_key;
+    const bool eq = j < C && key == kth_key;
+    bool take;
+    if (tie_mode) {
+      int tie_total;
+      const int tie_rank = base_tie + block_excl_scan(eq ? 1 : 0, s_scan, tie_total);
+      base_tie += tie_total;
+      take = gt || (eq && tie_rank < rem);
+    } else {
+      take = gt || (eq && j <= kth_idx);
+    }
+    int sel_total;
+    const int pos = base_sel + block_excl_scan(take ? 1 : 0, s_scan, sel_total);
     if (take && pos < k) {
       out[pos] = j;
       c.col_active[j] = 1;
     }
     base_sel += sel_total;
-    base_tie += tie_total;
   }
 }
 

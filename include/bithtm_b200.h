@@ -236,6 +236,11 @@ int bh_summary(const bh_ctx* ctx, int32_t* summary_host, void* stream);
 int bh_graph_create(const bh_ctx* ctx, int steps_per_graph, int learning, void* stream, void** graph_exec_out);
 int bh_graph_launch(void* graph_exec, void* stream);
 int bh_graph_destroy(void* graph_exec);
+/* One bh_step with a CUDA event recorded on `stream` after every kernel launch.
+ * Returns the number of launches n (>= 0) and fills ms_out[0..n) / names_out[0..n)
+ * (static strings); synchronises the stream. */
+int bh_profile_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, void* stream,
+                    float* ms_out, const char** names_out, int max_out);
 /* number of kernel launches one bh_step issues (for bench accounting) */
 int bh_step_launches(const bh_ctx* ctx, int learning);
 
