@@ -153,7 +153,19 @@ def algorithmic_bytes(cfg, name, sc_stats):
         "tm_learn_apply": 16 * L * 40 + 8 * L * (W + 1),          # learning rows RMW + their priority rows
         "tm_draw2": 8 * L * (W + 1),
     }
+    # the fused kernel moves the whole step (SP + TM algorithmic bytes)
+    sp = C * I / 8 + I / 8 + 16 * k * I + k * I / 8 + 28 * C
+    tm = 8 * syn + 16 * L * 40 + 4 * (C * c) / 8 + 8 * (k * c + L * (W + 1) + M)
+    table["step_fused_cluster"] = table["step_fused_grid"] = sp + tm
     return table.get(name)
+
+
+def nat_launches(eng):
+    """Kernel launches one device-resident step issues (fused: 1; per-stage: 15 + ring fetch)."""
+    from bithtm_b200 import _native as nat
+
+    n = nat.lib.bh_step_launches(eng.ref, 1)
+    return n if eng.ctx.fused_mode else n + 1
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -178,7 +190,7 @@ def ours(args):
         np.random.seed(seed)
         return bithtm.HierarchicalTemporalMemory(cfg["input_dim"], cfg["column_dim"], cfg["cell_dim"],
                                                  cfg["active_columns"], rng_sync=rng_sync, ring_len=ring_len,
-                                                 max_segments=1 << 17)
+                                                 max_segments=1 << 17, fused=args.fused, fused_ctas=args.fused_ctas)
 
     xs = make_inputs(cfg, total, seed)
 
@@ -188,6 +200,10 @@ def ours(args):
     htm.temporal_memory._rng.before(eng)  # upload np.random's MT19937 state once
     eng.load_ring(xs)
     graph1 = eng.graph(1, learning=True)
+    launches = nat_launches(eng)
+    exec_mode = {0: "one kernel per stage (15 launches/step)",
+                 1: f"whole step in one kernel on a thread-block cluster of {eng.ctx.fused_ctas} CTAs",
+                 2: f"whole step in one cooperative kernel, {eng.ctx.fused_ctas} CTAs"}[eng.ctx.fused_mode]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     for _ in range(W):
         eng.launch_graph(graph1, 1)
@@ -287,12 +303,13 @@ def ours(args):
     if rank == 0:
         from bithtm_b200 import _native as nat
 
-        launches_per_step = nat.lib.bh_step_launches(None, 1) + 1  # + ring fetch
+        launches_per_step = launches
         line = {
             "metric": METRIC, "value": world * K / dev_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 permanence / f32 / u32 bit-words", "data": "synthetic",
             "config": {"workload": workload_name(cfg), "parallelism": f"{world} independent network(s), 1 per GPU",
+                       "execution": exec_mode,
                        "l2": "flushed before every timed step (256 MiB write); per-step CUDA events summed",
                        "inputs": "device-resident ring, one CUDA graph launch per step"},
             "l2_resident": {"value": world * 1e3 / warm_ms_per_step, "unit": UNIT, "ms_per_step": warm_ms_per_step,
@@ -315,6 +332,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fused", default="auto", choices=["auto", "cluster", "grid", "off"],
+                    help="execution mode of the step (default: one kernel on a thread-block cluster at this size)")
+    ap.add_argument("--fused-ctas", type=int, default=None, help="CTAs of the fused kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -43,7 +43,8 @@ class Engine:
 
     def __init__(self, input_dim, column_dim, cell_dim, active_columns, *, device=None,
                  max_segments=None, max_synapses_per_segment=128, match_capacity=None,
-                 learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None):
+                 learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
+                 fused="auto", fused_ctas=None):
         torch = _torch()
         self.device = require_cuda(device)
         if not (1 <= cell_dim <= 32):
@@ -73,6 +74,14 @@ class Engine:
         ctx.match_capacity, ctx.learn_capacity = int(match_capacity), int(learn_capacity)
         ctx.tm_blocks, ctx.sm_count = int(tm_blocks), self.sm_count
         ctx.rand_capacity, ctx.ring_len = int(rand_capacity), int(ring_len)
+        # whole step as one kernel: on one thread-block cluster while the step is
+        # latency-bound (mask <= 8 MiB), else on a cooperative grid with one CTA per SM
+        if fused == "auto":
+            fused = "cluster" if Ccol * ctx.mask_stride * 4 <= (8 << 20) else "grid"
+        ctx.fused_mode = {"off": 0, "cluster": 1, "grid": 2}[fused]
+        if fused_ctas is None:
+            fused_ctas = 16 if fused == "cluster" else self.sm_count
+        ctx.fused_ctas = int(fused_ctas)
         self.ctx = ctx
         self.I, self.C, self.c, self.k, self.N = I, Ccol, c, k, N
 
@@ -110,7 +119,7 @@ class Engine:
     def _counts(self):
         x = self.ctx
         C_, I, c, k = x.column_dim, x.input_dim, x.cell_dim, x.active_columns
-        N, S, E, M = C_ * c, x.seg_capacity, x.syn_capacity, x.match_capacity
+        N, S, E, M = C_ * 32, x.seg_capacity, x.syn_capacity, x.match_capacity  # device cell id = col*32+cell
         return {
             "sp_perm": C_ * I, "sp_mask": C_ * x.mask_stride, "duty": C_, "overlaps": C_, "boosted": C_,
             "active_cols": 2 * k, "col_active": C_, "col_pred": C_, "col_act": C_, "col_win": C_,
@@ -130,6 +139,16 @@ class Engine:
     @property
     def ref(self):
         return C.byref(self.ctx)
+
+    # device cell ids are column * 32 + cell; the reference's flat ids are column * c + cell
+    def cells_to_flat(self, dev_ids: np.ndarray) -> np.ndarray:
+        d = np.asarray(dev_ids).astype(np.int64)
+        return (d >> 5) * self.c + (d & 31)
+
+    def per_cell(self, name: str) -> np.ndarray:
+        """A per-cell device array as the reference's flat [C * c] array."""
+        a = self.buf[name].cpu().numpy().reshape(self.C, 32)[:, :self.c]
+        return np.ascontiguousarray(a).reshape(-1)
 
     def scalars(self) -> np.ndarray:
         return self.buf["sc"].cpu().numpy()

@@ -17,7 +17,7 @@ MT_N = 624
 
 # device scalar block indices (enum in the header)
 (SC_STEP, SC_HAVE_PREV, SC_NSEG, SC_NSEG_NEXT, SC_M, SC_W0, SC_W1, SC_L0, SC_L, SC_P, SC_NU, SC_NR,
- SC_STATUS, SC_MT_POS, SC_RAND_FILL, SC_OFF2, SC_OFF3, SC_INPUT_POS) = range(18)
+ SC_STATUS, SC_MT_POS, SC_RAND_FILL, SC_OFF2, SC_OFF3, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN) = range(20)
 SC_COUNT = 32
 
 ST_SEG_OVERFLOW, ST_SYN_OVERFLOW, ST_MATCH_OVERFLOW, ST_LEARN_OVERFLOW, ST_RAND_OVERFLOW, ST_PRI_TIE = 1, 2, 4, 8, 16, 32
@@ -48,7 +48,7 @@ class BhCtx(C.Structure):
         ("column_dim", C.c_int32), ("cell_dim", C.c_int32), ("active_columns", C.c_int32),
         ("seg_capacity", C.c_int32), ("syn_capacity", C.c_int32), ("match_capacity", C.c_int32),
         ("learn_capacity", C.c_int32), ("tm_blocks", C.c_int32), ("sm_count", C.c_int32),
-        ("rand_capacity", C.c_int64), ("ring_len", C.c_int32), ("reserved0", C.c_int32),
+        ("rand_capacity", C.c_int64), ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
         ("sp_threshold", C.c_double), ("sp_delta_on", C.c_double), ("sp_delta_off", C.c_double),
         ("tm_learn_on", C.c_double), ("tm_learn_off", C.c_double),
         ("tm_punish_on", C.c_double), ("tm_punish_off", C.c_double),
@@ -56,7 +56,7 @@ class BhCtx(C.Structure):
         ("tm_perm_initial", C.c_float), ("tm_perm_threshold", C.c_float), ("epsilon", C.c_float),
         ("tm_learn_can_delete", C.c_int32), ("tm_punish_can_delete", C.c_int32),
         ("seg_activation_threshold", C.c_int32), ("seg_matching_threshold", C.c_int32),
-        ("seg_sampling_synapses", C.c_int32), ("reserved1", C.c_int32),
+        ("seg_sampling_synapses", C.c_int32), ("fused_ctas", C.c_int32),
         # device pointers
         ("sp_perm", _P), ("sp_mask", _P), ("duty", _P), ("overlaps", _P), ("boosted", _P),
         ("active_cols", _P), ("col_active", _P),

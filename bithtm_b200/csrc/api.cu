@@ -7,6 +7,7 @@
 
 #include "sp_kernels.cuh"
 #include "tm_kernels.cuh"
+#include "fused.cuh"
 
 #define CU_RET(expr)                                   \
   do {                                                 \
@@ -57,7 +58,7 @@ struct Carver {
 extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   Carver cv{reinterpret_cast<char*>(base), 0};
   const size_t C = x->column_dim, I = x->input_dim, c = x->cell_dim, k = x->active_columns;
-  const size_t N = C * c, S = x->seg_capacity, E = x->syn_capacity, M = x->match_capacity;
+  const size_t N = C * 32 /* device cell id = column * 32 + cell */, S = x->seg_capacity, E = x->syn_capacity, M = x->match_capacity;
   cv.take(x->sp_perm, C * I);
   cv.take(x->sp_mask, C * (size_t)x->mask_stride);
   cv.take(x->duty, C);
@@ -134,7 +135,7 @@ __global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
 extern "C" int bh_init(const bh_ctx* x, void* stream) {
   int rc = check_ctx(x);
   if (rc) return rc;
-  long long N = (long long)x->column_dim * x->cell_dim;
+  long long N = (long long)x->column_dim * 32;
   k_fill_i32<<<cdiv(N, 256) < 1184 ? cdiv(N, 256) : 1184, 256, 0, S_(stream)>>>(x->cell_widx, N, -1);
   LAUNCH_CHECK();
   return 0;
@@ -143,7 +144,7 @@ extern "C" int bh_init(const bh_ctx* x, void* stream) {
 // ------------------------------------------------------------------------------------
 // spatial pooler
 // ------------------------------------------------------------------------------------
-static int overlap_group(const bh_ctx* x) {
+static int overlap_group_host(const bh_ctx* x) {
   int vec = x->mask_stride / 4, g = 1;
   while (g * 2 <= vec && g < 32) g *= 2;
   return g;
@@ -174,10 +175,10 @@ extern "C" int bh_pack_input(const bh_ctx* x, const uint8_t* bool_dev, uint32_t*
 
 template <bool BOOST>
 static int launch_overlap(const bh_ctx* x, const uint32_t* in, cudaStream_t st) {
-  int g = overlap_group(x);
+  int g = overlap_group_host(x);
   int rows_per_block = (SP_THREADS / 32) * (32 / g);
   size_t smem = (size_t)x->mask_stride * 4;
-  k_sp_overlap<BOOST><<<sp_grid(x, rows_per_block), SP_THREADS, smem, st>>>(*x, in, g);
+  k_sp_overlap<BOOST><<<sp_grid(x, rows_per_block), SP_THREADS, smem, st>>>(*x, in);
   LAUNCHED(BOOST ? "sp_overlap_boost" : "sp_overlap");
   return 0;
 }
@@ -232,7 +233,7 @@ extern "C" int bh_sp_step(const bh_ctx* x, const uint32_t* in, int learning, voi
   return sp_step(x, in, learning, S_(stream));
 }
 
-__global__ void k_advance_step(const bh_ctx c) { c.sc[BH_SC_STEP] = c.sc[BH_SC_STEP] + 1; }
+__global__ void k_advance_step(const __grid_constant__ bh_ctx c) { c.sc[BH_SC_STEP] = c.sc[BH_SC_STEP] + 1; }
 
 extern "C" int bh_advance_step(const bh_ctx* x, void* stream) {
   k_advance_step<<<1, 1, 0, S_(stream)>>>(*x);
@@ -272,7 +273,7 @@ extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
     if (smem > 200 * 1024) return BH_E_UNSUPPORTED;
     if (smem > 40 * 1024)
       CU_RET(cudaFuncSetAttribute(k_tm_learn_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int grid = (x->sm_count > 0 ? x->sm_count : 148) * 8;
+    int grid = (x->sm_count > 0 ? x->sm_count : 148) * 2;
     k_tm_learn_apply<<<grid, LA_THREADS, smem, st>>>(*x);
     LAUNCHED("tm_learn_apply");
   }
@@ -304,9 +305,65 @@ extern "C" int bh_tm_step(const bh_ctx* x, int learning, void* stream) {
 // ------------------------------------------------------------------------------------
 // whole step
 // ------------------------------------------------------------------------------------
+static int fused_smem(const bh_ctx* x) {
+  int a = x->mask_stride * 4, b = learn_apply_smem(x);
+  return a > b ? a : b;
+}
+
+// One-time function attributes (per process): non-portable cluster sizes, dynamic smem.
+static int prepare_fused(int mode) {
+  static bool done[3] = {false, false, false};
+  if (mode < 1 || mode > 2) return BH_E_BADARG;
+  if (done[mode]) return 0;
+  if (mode == 1) {
+    CU_RET(cudaFuncSetAttribute(k_step_fused<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CU_RET(cudaFuncSetAttribute(k_step_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  } else {
+    CU_RET(cudaFuncSetAttribute(k_step_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  }
+  done[mode] = true;
+  return 0;
+}
+
+// One launch of the fused kernel: n_steps consecutive steps (input_fixed == NULL ->
+// inputs from the device ring), optionally followed by the host summary.
+static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_steps, int learning, int want_summary,
+                        cudaStream_t st) {
+  const int nb = x->fused_ctas;
+  if (nb < 1) return BH_E_BADARG;
+  const int smem = fused_smem(x);
+  if (smem > 160 * 1024) return BH_E_UNSUPPORTED;
+  int prc = prepare_fused(x->fused_mode);
+  if (prc) return prc;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(nb);
+  cfg.blockDim = dim3(FUSED_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (x->fused_mode == 1) {
+    if (nb > 16) return BH_E_BADARG;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nb;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    CU_RET(cudaLaunchKernelEx(&cfg, k_step_fused<1>, *x, input_fixed, n_steps, learning, want_summary));
+  } else {
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    CU_RET(cudaLaunchKernelEx(&cfg, k_step_fused<2>, *x, input_fixed, n_steps, learning, want_summary));
+  }
+  LAUNCHED(x->fused_mode == 1 ? "step_fused_cluster" : "step_fused_grid");
+  return 0;
+}
+
 extern "C" int bh_step(const bh_ctx* x, const uint32_t* in, int learning, void* stream) {
   int rc = check_ctx(x);
   if (rc) return rc;
+  if (x->fused_mode) return launch_fused(x, in, 1, learning, 0, S_(stream));
   if ((rc = sp_step(x, in, learning, S_(stream)))) return rc;
   if ((rc = bh_tm_select(x, stream))) return rc;
   if ((rc = bh_tm_learn(x, learning, stream))) return rc;
@@ -314,13 +371,13 @@ extern "C" int bh_step(const bh_ctx* x, const uint32_t* in, int learning, void* 
 }
 
 extern "C" int bh_step_launches(const bh_ctx* x, int learning) {
-  (void)x;
+  if (x && x->fused_mode) return 1;
   // overlap+boost, topk, [sp_learn], duty | draw1, select a/b | learn-select a/b, draw2, [apply] |
   // post, activate a, draw3, activate b
   return learning ? 15 : 13;
 }
 
-__global__ void k_ring_fetch(const bh_ctx c) {
+__global__ void k_ring_fetch(const __grid_constant__ bh_ctx c) {
   // copy the next ring row to input_dev and advance the cursor (single CTA)
   int pos = c.sc[BH_SC_INPUT_POS];
   const uint32_t* src = c.input_ring + (long long)(pos % c.ring_len) * c.input_words;
@@ -331,6 +388,10 @@ __global__ void k_ring_fetch(const bh_ctx c) {
 
 extern "C" int bh_step_ring(const bh_ctx* x, int learning, void* stream) {
   if (!x || x->ring_len <= 0) return BH_E_BADARG;
+  if (x->fused_mode) {
+    int rc = check_ctx(x);
+    return rc ? rc : launch_fused(x, nullptr, 1, learning, 0, S_(stream));
+  }
   k_ring_fetch<<<1, 256, 0, S_(stream)>>>(*x);
   LAUNCHED("ring_fetch");
   return bh_step(x, x->input_dev, learning, stream);
@@ -352,6 +413,15 @@ extern "C" int bh_step_host(const bh_ctx* x, const uint8_t* input_bool_host, int
     x->input_pinned[w] = bits;
   }
   CU_RET(cudaMemcpyAsync(x->input_dev, x->input_pinned, (size_t)x->input_words * 4, cudaMemcpyHostToDevice, st));
+  if (x->fused_mode) {
+    // one kernel: the step and the summary gather
+    if ((rc = launch_fused(x, x->input_dev, 1, learning, 1, st))) return rc;
+    size_t bytes = (size_t)BH_SUMMARY_INTS(x->active_columns) * 4;
+    CU_RET(cudaMemcpyAsync(x->summary_pinned, x->summary_dev, bytes, cudaMemcpyDeviceToHost, st));
+    CU_RET(cudaStreamSynchronize(st));
+    if (summary_host) memcpy(summary_host, x->summary_pinned, bytes);
+    return 0;
+  }
   if ((rc = bh_step(x, x->input_dev, learning, stream))) return rc;
   return bh_summary(x, summary_host, stream);
 }
@@ -406,8 +476,13 @@ extern "C" int bh_graph_create(const bh_ctx* x, int steps_per_graph, int learnin
   if (rc) return rc;
   cudaStream_t st = S_(stream);
   cudaGraph_t graph = nullptr;
+  if (x->fused_mode && (rc = prepare_fused(x->fused_mode))) return rc;  // not inside the capture
   CU_RET(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  for (int i = 0; i < steps_per_graph && rc == 0; ++i) rc = bh_step_ring(x, learning, stream);
+  if (x->fused_mode) {
+    rc = launch_fused(x, nullptr, steps_per_graph, learning, 0, st);  // all steps in one launch
+  } else {
+    for (int i = 0; i < steps_per_graph && rc == 0; ++i) rc = bh_step_ring(x, learning, stream);
+  }
   cudaError_t e = cudaStreamEndCapture(st, &graph);
   if (rc) {
     if (graph) cudaGraphDestroy(graph);

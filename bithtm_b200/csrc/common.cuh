@@ -1,4 +1,11 @@
 // Shared device helpers for the bithtm_b200 kernels (sm_100a).
+//
+// Every stage of the timestep is a `__device__` phase function `ph_*(ctx, b, nb, ...)`
+// executed by CTA `b` of `nb` cooperating CTAs with blockDim.x threads each.  The
+// same phase code runs (i) as its own kernel behind the fine-grained C entry points
+// and (ii) inside the fused step kernel, where phases are separated by a cluster
+// barrier (small networks) or a grid barrier (large ones).  Buffers written during a
+// step are never read through the non-coherent path (no __ldg / ld.global.nc).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -7,12 +14,13 @@
 #include "../../include/bithtm_b200.h"
 
 #define BH_FULL 0xffffffffu
-#define BH_TM_THREADS 256            // block size of the ranged TM kernels
-#define BH_TM_WARPS (BH_TM_THREADS / 32)
-#define BH_BLK_STRIDE 1024           // ints per row of ctx.blk
+#define BH_TM_THREADS 256  // block size of the stand-alone ranged TM kernels
+#define BH_BLK_STRIDE 1024  // ints per row of ctx.blk
+#define BH_MAX_WARPS 32
 
 // rows of ctx.blk (per-CTA counts used for ordered, deterministic compaction)
 enum { BLK_WIN = 0, BLK_UNACC, BLK_LEARN, BLK_PUNISH, BLK_MATCH, BLK_RECYC, BLK_ROWS = 8 };
+#define BLK(c, row) ((c).blk + (row)*BH_BLK_STRIDE)
 
 struct Range {
   int begin, end;
@@ -45,22 +53,22 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
-// Block-wide sum; every thread gets the total.  `sm` holds >= 32 ints.
-__device__ __forceinline__ int block_sum(int v, int* sm) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+// Block-wide sum; every thread gets the total.  `sm` holds >= 32 ints.  The
+// cross-warp stage is a redundant warp shuffle reduction in every warp (small code,
+// no third barrier).
+__device__ __noinline__ int block_sum(int v, int* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   v = warp_sum(v);
   __syncthreads();  // protect sm from a previous use
   if (lane == 0) sm[w] = v;
   __syncthreads();
-  int t = 0;
-  for (int i = 0; i < nw; ++i) t += sm[i];
-  return t;
+  return warp_sum(lane < nw ? sm[lane] : 0);
 }
 
 // Block-wide exclusive prefix of a per-thread count (thread order); `total`
 // receives the block sum.  `sm` holds >= 32 ints.  All threads must call.
-__device__ __forceinline__ int block_excl_scan(int v, int* sm, int& total) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+__device__ __noinline__ int block_excl_scan(int v, int* sm, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   int inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -70,20 +78,23 @@ __device__ __forceinline__ int block_excl_scan(int v, int* sm, int& total) {
   __syncthreads();
   if (lane == 31) sm[w] = inc;
   __syncthreads();
-  int off = 0, tot = 0;
-  for (int i = 0; i < nw; ++i) {
-    int s = sm[i];
-    if (i < w) off += s;
-    tot += s;
+  int ws = lane < nw ? sm[lane] : 0;  // per-warp sums, scanned redundantly by every warp
+  int winc = ws;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(BH_FULL, winc, o);
+    if (lane >= o) winc += n;
   }
-  total = tot;
+  total = __shfl_sync(BH_FULL, winc, 31);
+  const int off = __shfl_sync(BH_FULL, winc - ws, w);
   return off + inc - v;
 }
 
 // Sum of counts[0..b) and of counts[0..nb) (nb <= 1024), computed by the whole
 // block.  `sm` holds >= 32 ints.
-__device__ __forceinline__ void blk_prefix(const int* counts, int b, int nb, int* sm, int& before, int& total) {
+__device__ __noinline__ void blk_prefix(const int* counts, int b, int nb, int* sm, int& before, int& total) {
   int pre = 0, all = 0;
+  #pragma unroll 1
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
     int v = counts[i];
     all += v;
@@ -93,9 +104,42 @@ __device__ __forceinline__ void blk_prefix(const int* counts, int b, int nb, int
   total = block_sum(all, sm);
 }
 
-__device__ __forceinline__ bool cell_bit(const uint32_t* col_words, int cell, int c) {
-  int col = cell / c;
-  return (__ldg(col_words + col) >> (cell - col * c)) & 1u;
+// device cell id = column * 32 + cell-in-column (c <= 32)
+__device__ __forceinline__ bool cell_bit(const uint32_t* col_words, int cell) {
+  return (col_words[cell >> 5] >> (cell & 31)) & 1u;
 }
 
 __device__ __forceinline__ uint32_t low_mask(int c) { return c >= 32 ? 0xffffffffu : ((1u << c) - 1u); }
+
+// ------------------------------------------------------------------------------------
+// barriers between phases of the fused step kernel
+// ------------------------------------------------------------------------------------
+// All CTAs of the (single) thread-block cluster; release/acquire at cluster scope
+// makes global-memory writes of earlier phases visible (and invalidates L1).
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// All CTAs of a cooperative (co-resident) grid: self-resetting counter + generation
+// word in global memory.  `bar[0]` = arrivals, `bar[1]` = generation.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n_ctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int gen;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+    __threadfence();
+    unsigned int prev = atomicAdd(bar, 1u);
+    if (prev == n_ctas - 1) {
+      bar[0] = 0u;
+      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
+    } else {
+      unsigned int now;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory");
+      } while (now == gen);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}

@@ -1,0 +1,108 @@
+// The whole SP+TM timestep (HierarchicalTemporalMemory.process, networks.py:146-149)
+// as ONE kernel: the phase functions of sp_kernels.cuh / tm_kernels.cuh separated by
+// barriers.  MODE 1: the grid is a single thread-block cluster (hardware
+// barrier.cluster, for networks whose step is latency-bound); MODE 2: a cooperative
+// grid with one CTA per SM and a global-memory barrier (HBM-bound sizes).
+// One launch can run several consecutive steps from the device input ring.
+#pragma once
+
+#include "sp_kernels.cuh"
+#include "tm_kernels.cuh"
+
+#define FUSED_THREADS 1024
+
+template <int MODE>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+    k_step_fused(const __grid_constant__ bh_ctx c, const uint32_t* input_fixed, int n_steps, int learning, int want_summary) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int nw = nb > 1 ? nb - 1 : 1;  // CTAs running the ranged TM phases
+  const bool worker = b < nw;
+  const bool rng = b == nb - 1;        // CTA producing the random draws
+  unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
+#define BH_SYNC()                          \
+  do {                                     \
+    if (MODE == 1) cluster_barrier();      \
+    else grid_barrier(bar, (unsigned)nb);  \
+  } while (0)
+
+  // phase timestamps of the last step (CTA 0): ctx.blk row 7, as 64-bit globaltimer ns
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE);
+  int stamp_i = 0;
+#define BH_STAMP()                                                            \
+  do {                                                                        \
+    if (b == 0 && threadIdx.x == 0) {                                         \
+      unsigned long long t_;                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                  \
+      stamps[stamp_i] = t_;                                                   \
+    }                                                                         \
+    ++stamp_i;                                                                \
+  } while (0)
+  const int pos0 = c.sc[BH_SC_INPUT_POS];
+  for (int step = 0; step < n_steps; ++step) {
+    const uint32_t* input =
+        input_fixed ? input_fixed : c.input_ring + (long long)((pos0 + step) % c.ring_len) * c.input_words;
+    stamp_i = 0;
+    BH_STAMP();
+    // P0: overlap + boost on all CTAs; draw #1 (rand(k, c)) on the rng CTA
+    if (rng) ph_draw(c, 1, 1, nw);
+    if (nb == 1) ph_overlap<true>(c, input, s_dyn, 0, 1);
+    else if (!rng) ph_overlap<true>(c, input, s_dyn, b, nb - 1);  // the rng CTA is busy drawing
+    BH_SYNC();
+    BH_STAMP();
+    // P1: global inhibition (one CTA)
+    if (b == 0) ph_topk(c);
+    BH_SYNC();
+    BH_STAMP();
+    // P2: SP learning + duty cycles; bursting / winner bits per active column
+    if (learning) ph_sp_learn(c, input, b, nb);
+    ph_duty(c, b, nb);
+    if (worker) ph_select_a(c, b, nw);
+    BH_SYNC();
+    BH_STAMP();
+    // P3: ordered winner lists; learning / punished flags among previous matching segments
+    if (worker) {
+      ph_select_b(c, b, nw);
+      ph_learn_select_a(c, learning, b, nw);
+    }
+    BH_SYNC();
+    BH_STAMP();
+    // P4: learning lists, recycled / new segments; draw #2 (rand(L, W+1)) on the rng CTA
+    if (rng) ph_draw(c, 2, learning, nw);
+    if (worker) ph_learn_select_b(c, learning, b, nw);
+    BH_SYNC();
+    BH_STAMP();
+    // P5: permanence updates, deletion, growth
+    if (learning) ph_learn_apply(c, s_dyn, b, nb);
+    BH_SYNC();
+    BH_STAMP();
+    // P6: commit activation bit-words, winner index, segment count
+    ph_post(c, b, nb);
+    BH_SYNC();
+    BH_STAMP();
+#ifdef BH_ICACHE_EXPERIMENT
+    ph_post(c, b, nb);  // idempotent: second run with warm instruction cache
+    BH_SYNC();
+    BH_STAMP();
+    ph_post(c, b, nb);
+    BH_SYNC();
+    BH_STAMP();
+#endif
+    // P7: segment potentials
+    if (worker) ph_activate_a(c, b, nw);
+    BH_SYNC();
+    BH_STAMP();
+    // P8: draw #3 (rand(M))
+    if (rng) ph_draw(c, 3, 1, nw);
+    BH_SYNC();
+    BH_STAMP();
+    // P9: matching list, jitter, predictions; completes the step
+    if (worker) ph_activate_b(c, b, nw);
+    BH_SYNC();
+    BH_STAMP();
+  }
+  if (want_summary) ph_summary(c, b, nb);
+  if (!input_fixed && b == 0 && threadIdx.x == 0) c.sc[BH_SC_INPUT_POS] = pos0 + n_steps;
+#undef BH_SYNC
+#undef BH_STAMP
+}

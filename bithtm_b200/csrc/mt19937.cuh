@@ -32,7 +32,7 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 }
 
 // x[0..624) holds the current state block; writes the next block to x[624..1248).
-// Called by all MT_THREADS threads of the CTA.
+// Called by all threads of the CTA (blockDim.x >= 256).
 __device__ __forceinline__ void mt_next_block(uint32_t* x) {
   const int t = threadIdx.x;
   if (t < MT_N - MT_M) x[MT_N + t] = x[t + MT_M] ^ mt_twist(x[t], x[t + 1]);
@@ -51,10 +51,11 @@ __device__ __forceinline__ void mt_next_block(uint32_t* x) {
 }
 
 // Emit `count` doubles to out[0..count) continuing the stream at (key, *pos_io).
-// Whole CTA (MT_THREADS threads); x is shared memory of 2*MT_N words.
-__device__ void mt_fill_block(uint32_t* x, uint32_t* key, int* pos_io, double* out, long long count) {
-  const int t = threadIdx.x;
-  for (int i = t; i < MT_N; i += MT_THREADS) x[i] = key[i];
+// Whole CTA (blockDim.x >= 256 threads); x is shared memory of 2*MT_N words.
+__device__ __noinline__ void mt_fill_block(uint32_t* x, uint32_t* key, int* pos_io, double* out, long long count) {
+  const int t = threadIdx.x, NT = blockDim.x;
+  #pragma unroll 1
+  for (int i = t; i < MT_N; i += NT) x[i] = key[i];
   int p = *pos_io;
   __syncthreads();
   long long done = 0;
@@ -65,20 +66,23 @@ __device__ void mt_fill_block(uint32_t* x, uint32_t* key, int* pos_io, double* o
     int avail = (gen ? 2 * MT_N : MT_N) - p;
     long long pairs = avail / 2;
     if (pairs > count - done) pairs = count - done;
-    for (int q = t; q < pairs; q += MT_THREADS) {
+    #pragma unroll 1
+    for (int q = t; q < pairs; q += NT) {
       uint32_t a = mt_temper(x[p + 2 * q]) >> 5;
       uint32_t b = mt_temper(x[p + 2 * q + 1]) >> 6;
-      out[done + q] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+      out[done + q] = ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
     }
     p += 2 * (int)pairs;
     done += pairs;
     __syncthreads();
     if (gen) {  // then p > 624: the new block becomes the current one
-      for (int i = t; i < MT_N; i += MT_THREADS) x[i] = x[MT_N + i];  // disjoint halves
+      #pragma unroll 1
+      for (int i = t; i < MT_N; i += NT) x[i] = x[MT_N + i];  // disjoint halves
       p -= MT_N;
       __syncthreads();
     }
   }
-  for (int i = t; i < MT_N; i += MT_THREADS) key[i] = x[i];
+  #pragma unroll 1
+  for (int i = t; i < MT_N; i += NT) key[i] = x[i];
   if (t == 0) *pos_io = p;
 }

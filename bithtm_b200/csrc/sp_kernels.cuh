@@ -1,4 +1,4 @@
-// Spatial-pooler kernels: overlap (bit-packed popcount GEMV), boosting, canonical
+// Spatial-pooler phases: overlap (bit-packed popcount GEMV), boosting, canonical
 // top-k inhibition, float64 permanence learning with mask re-pack, duty-cycle EMA.
 // Reference: bithtm/projections.py:6-24, bithtm/regularizations.py:4-29,
 // bithtm/networks.py:26-35.
@@ -12,7 +12,7 @@
 // ---------------------------------------------------------------------------------
 // Connected mask from the float64 permanence (one warp per 32 consecutive inputs).
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SP_THREADS) k_sp_build_mask(const bh_ctx c) {
+__global__ void __launch_bounds__(SP_THREADS) k_sp_build_mask(const __grid_constant__ bh_ctx c) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = SP_THREADS / 32;
   const long long n_words = (long long)c.column_dim * c.mask_stride;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_build_mask(const bh_ctx c) {
 }
 
 // bool bytes -> packed words
-__global__ void k_pack_input(const bh_ctx c, const uint8_t* __restrict__ src, uint32_t* __restrict__ dst) {
+__global__ void k_pack_input(const __grid_constant__ bh_ctx c, const uint8_t* __restrict__ src, uint32_t* __restrict__ dst) {
   const int lane = threadIdx.x & 31;
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= c.input_words) return;
@@ -41,31 +41,41 @@ __global__ void k_pack_input(const bh_ctx c, const uint8_t* __restrict__ src, ui
 
 // ---------------------------------------------------------------------------------
 // (a) overlap + (c) boost.  G lanes cooperate on one mask row with 128-bit loads
-// (G = min(32, mask_stride/4) rounded to a power of two), so a warp covers 32/G
-// rows and every load instruction is a full coalesced 16 B per lane.
+// (G = largest power of two <= min(32, mask_stride/4)), so a warp covers 32/G rows
+// and every load instruction is a full coalesced 16 B per lane.  `s_in` = dynamic
+// shared memory of mask_stride words (16-byte aligned).
 // projections.py:18-21, regularizations.py:15-17.
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ int overlap_group(int mask_stride) {
+  int vec = mask_stride / 4, g = 1;
+  while (g * 2 <= vec && g < 32) g *= 2;
+  return g;
+}
+
 template <bool BOOST>
-__global__ void __launch_bounds__(SP_THREADS) k_sp_overlap(const bh_ctx c, const uint32_t* __restrict__ input,
-                                                          int group) {
-  extern __shared__ __align__(16) uint32_t s_in[];  // mask_stride words (zero padded)
+__device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* input, uint32_t* s_in, int b, int nb) {
+  #pragma unroll 1
   for (int i = threadIdx.x; i < c.mask_stride; i += blockDim.x) s_in[i] = i < c.input_words ? input[i] : 0u;
   __syncthreads();
+  const int group = overlap_group(c.mask_stride);
   const int lane = threadIdx.x & 31;
-  const int sub = lane % group;               // lane within its row group
+  const int sub = lane % group;  // lane within its row group
   const int rows_per_warp = 32 / group;
-  const int warp_global = blockIdx.x * (SP_THREADS / 32) + (threadIdx.x >> 5);
-  const int n_warps = gridDim.x * (SP_THREADS / 32);
+  const int warps = blockDim.x >> 5;
+  const int warp_global = b * warps + (threadIdx.x >> 5);
+  const int n_warps = nb * warps;
   const int vec_per_row = c.mask_stride / 4;
-  const uint4* __restrict__ mask4 = reinterpret_cast<const uint4*>(c.sp_mask);
+  const uint4* mask4 = reinterpret_cast<const uint4*>(c.sp_mask);
   const uint4* s_in4 = reinterpret_cast<const uint4*>(s_in);
+  #pragma unroll 1
   for (int base = warp_global * rows_per_warp; base < c.column_dim; base += n_warps * rows_per_warp) {
     int row = base + lane / group;
     int acc = 0;
     if (row < c.column_dim) {
       const uint4* mrow = mask4 + (long long)row * vec_per_row;
+      #pragma unroll 1
       for (int v = sub; v < vec_per_row; v += group) {
-        uint4 m = __ldg(mrow + v);
+        uint4 m = mrow[v];
         uint4 x = s_in4[v];
         acc += __popc(m.x & x.x) + __popc(m.y & x.y) + __popc(m.z & x.z) + __popc(m.w & x.w);
       }
@@ -81,7 +91,13 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_overlap(const bh_ctx c, const
   }
 }
 
-__global__ void k_boost(const bh_ctx c) {
+template <bool BOOST>
+__global__ void __launch_bounds__(SP_THREADS) k_sp_overlap(const __grid_constant__ bh_ctx c, const uint32_t* input) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  ph_overlap<BOOST>(c, input, s_dyn, blockIdx.x, gridDim.x);
+}
+
+__global__ void k_boost(const __grid_constant__ bh_ctx c) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= c.column_dim) return;
   float f = bh_np_expf(__fmul_rn(c.boost_coef, c.duty[j]));
@@ -91,11 +107,11 @@ __global__ void k_boost(const bh_ctx c) {
 // ---------------------------------------------------------------------------------
 // (b) canonical global inhibition: k largest keys, ties -> lower column index,
 // output ascending.  Keys are non-negative doubles, so their bit patterns order
-// like unsigned integers.  Single CTA:
+// like unsigned integers.  Single CTA (any block size that is a multiple of 32):
 //   1. block min/max -> the leading bits all keys share are skipped;
 //   2. 8-bit MSB-first radix passes (warp-aggregated shared-memory histogram,
 //      warp-parallel bin scan) until the bin holding the k-th key has at most
-//      TOPK_THREADS members (usually one pass);
+//      blockDim.x members (usually one pass);
 //   3. those candidates are ranked by (key desc, index asc) by counting, which
 //      yields the exact k-th (key, index) pair;
 //   4. ordered compaction over the column index.
@@ -105,7 +121,7 @@ __global__ void k_boost(const bh_ctx c) {
 // ---------------------------------------------------------------------------------
 #define TOPK_THREADS 1024
 
-__device__ __forceinline__ unsigned long long block_reduce_u64(unsigned long long v, bool want_max,
+__device__ __noinline__ unsigned long long block_reduce_u64(unsigned long long v, bool want_max,
                                                                unsigned long long* sm) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
@@ -116,12 +132,16 @@ __device__ __forceinline__ unsigned long long block_reduce_u64(unsigned long lon
   __syncthreads();
   if (lane == 0) sm[w] = v;
   __syncthreads();
-  unsigned long long r = sm[0];
-  for (int i = 1; i < nw; ++i) r = want_max ? (sm[i] > r ? sm[i] : r) : (sm[i] < r ? sm[i] : r);
+  unsigned long long r = sm[lane < nw ? lane : 0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long n = __shfl_xor_sync(BH_FULL, r, o);
+    r = want_max ? (n > r ? n : r) : (n < r ? n : r);
+  }
   return r;
 }
 
-__global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
+__device__ void ph_topk(const bh_ctx& c) {
   __shared__ int hist[256];
   __shared__ int s_scan[32];
   __shared__ unsigned long long s_u64[32];
@@ -129,7 +149,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
   __shared__ int cand_idx[TOPK_THREADS];
   __shared__ int s_bin, s_rem, s_ncand, s_kth_idx;
   __shared__ unsigned long long s_kth_key;
-  const int t = threadIdx.x, lane = t & 31;
+  const int t = threadIdx.x, lane = t & 31, NT = blockDim.x;
   const int C = c.column_dim, k = c.active_columns;
   const int cur = c.sc[BH_SC_STEP] & 1;
   int* out = c.active_cols + cur * k;
@@ -137,30 +157,35 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
   const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(c.boosted);
 
   // retire the previous step's column flags
-  for (int i = t; i < k; i += TOPK_THREADS) c.col_active[prev[i]] = 0;
+  #pragma unroll 1
+  for (int i = t; i < k; i += NT) c.col_active[prev[i]] = 0;
 
   // 1. shared leading bits
   unsigned long long mn = ~0ull, mx = 0ull;
-  for (int j = t; j < C; j += TOPK_THREADS) {
+  #pragma unroll 1
+  for (int j = t; j < C; j += NT) {
     unsigned long long key = keys[j];
     mn = key < mn ? key : mn;
     mx = key > mx ? key : mx;
   }
   mn = block_reduce_u64(mn, false, s_u64);
   mx = block_reduce_u64(mx, true, s_u64);
-  int consumed = (mn == mx) ? 64 : __clzll((long long)(mn ^ mx));  // bits known equal for all candidates
-  unsigned long long prefix = (consumed == 0) ? 0ull : (consumed == 64 ? mx : (mx >> (64 - consumed)) << (64 - consumed));
-  int rem = k;       // how many still to take from the current candidate set
-  int ncand = C;     // size of the current candidate set (keys matching `prefix` on the consumed bits)
+  int consumed = (mn == mx) ? 64 : __clzll((long long)(mn ^ mx));  // leading bits equal for all candidates
+  unsigned long long prefix =
+      (consumed == 0) ? 0ull : (consumed == 64 ? mx : (mx >> (64 - consumed)) << (64 - consumed));
+  int rem = k;    // how many still to take from the current candidate set
+  int ncand = C;  // size of the current candidate set (keys matching `prefix` on the consumed bits)
 
   // 2. radix passes
-  while (consumed < 64 && ncand > TOPK_THREADS) {
+  while (consumed < 64 && ncand > NT) {
     const int shift = (64 - consumed - 8) > 0 ? (64 - consumed - 8) : 0;
     const int width = 64 - consumed - shift;  // 1..8 bits
     const unsigned long long hi_mask = consumed == 0 ? 0ull : (~0ull << (64 - consumed));
-    for (int i = t; i < 256; i += TOPK_THREADS) hist[i] = 0;
+    #pragma unroll 1
+    for (int i = t; i < 256; i += NT) hist[i] = 0;
     __syncthreads();
-    for (int base = 0; base < C; base += TOPK_THREADS) {
+    #pragma unroll 1
+    for (int base = 0; base < C; base += NT) {
       const int j = base + t;
       const unsigned long long key = j < C ? keys[j] : 0ull;
       const bool in = j < C && (key & hi_mask) == prefix;
@@ -185,8 +210,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
         if (lane >= o) incl += n;
       }
       const int before = incl - sum;  // keys in bins above this lane's bins
-      const bool mine = before < rem && incl >= rem;
-      if (mine) {
+      if (before < rem && incl >= rem) {
         int r = rem - before;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -210,16 +234,17 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
   }
 
   // 3. exact k-th (key, index)
-  bool tie_mode = false;           // many identical keys: take the `rem` lowest indices among them
+  bool tie_mode = false;  // many identical keys: take the `rem` lowest indices among them
   unsigned long long kth_key = prefix;
   int kth_idx = 0x7fffffff;
-  if (ncand > TOPK_THREADS) {
-    tie_mode = true;               // consumed == 64: every candidate equals prefix
+  if (ncand > NT) {
+    tie_mode = true;  // consumed == 64: every candidate equals prefix
   } else {
     const unsigned long long hi_mask = consumed == 0 ? 0ull : (consumed == 64 ? ~0ull : (~0ull << (64 - consumed)));
     if (t == 0) s_ncand = 0;
     __syncthreads();
-    for (int j = t; j < C; j += TOPK_THREADS) {
+    #pragma unroll 1
+    for (int j = t; j < C; j += NT) {
       const unsigned long long key = keys[j];
       if ((key & hi_mask) == prefix) {
         const int p = atomicAdd(&s_ncand, 1);
@@ -233,6 +258,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
       const unsigned long long mk = cand_key[t];
       const int mi = cand_idx[t];
       int ahead = 0;
+#pragma unroll 2
       for (int i = 0; i < n; ++i) {
         const unsigned long long ok = cand_key[i];
         ahead += (ok > mk || (ok == mk && cand_idx[i] < mi)) ? 1 : 0;
@@ -249,7 +275,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
 
   // 4. ordered compaction over column index
   int base_sel = 0, base_tie = 0;
-  for (int tile = 0; tile < C; tile += TOPK_THREADS) {
+  #pragma unroll 1
+  for (int tile = 0; tile < C; tile += NT) {
     const int j = tile + t;
     const unsigned long long key = j < C ? keys[j] : 0ull;
     const bool gt = j < C && key > kth_key;
@@ -273,17 +300,21 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const bh_ctx c) {
   }
 }
 
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk(const __grid_constant__ bh_ctx c) { ph_topk(c); }
+
 // host-inhibition mode: adopt an explicit ordered list
-__global__ void k_set_active(const bh_ctx c, const int32_t* __restrict__ cols) {
+__global__ void k_set_active(const __grid_constant__ bh_ctx c, const int32_t* __restrict__ cols) {
   const int k = c.active_columns;
   const int cur = c.sc[BH_SC_STEP] & 1;
   int* out = c.active_cols + cur * k;
   const int* prev = c.active_cols + (cur ^ 1) * k;
+  #pragma unroll 1
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     c.col_active[prev[i]] = 0;
     c.col_active[out[i]] = 0;  // in case bh_inhibit already ran this step
   }
   __syncthreads();
+  #pragma unroll 1
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     int j = cols[i];
     out[i] = j;
@@ -298,18 +329,20 @@ __global__ void k_set_active(const bh_ctx c, const int32_t* __restrict__ cols) {
 // 256-byte permanence segment is coalesced and the ballot is the mask word.
 // projections.py:23-24.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SP_THREADS) k_sp_learn(const bh_ctx c, const uint32_t* __restrict__ input) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void ph_sp_learn(const bh_ctx& c, const uint32_t* input, int b, int nb) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int k = c.active_columns;
   const int cur = c.sc[BH_SC_STEP] & 1;
   const int* act = c.active_cols + cur * k;
-  for (int r = blockIdx.x; r < k; r += gridDim.x) {
+  #pragma unroll 1
+  for (int r = b; r < k; r += nb) {
     const int col = act[r];
     double* prow = c.sp_perm + (long long)col * c.input_dim;
     uint32_t* mrow = c.sp_mask + (long long)col * c.mask_stride;
-    for (int w = warp; w < c.input_words; w += SP_THREADS / 32) {
+    #pragma unroll 1
+    for (int w = warp; w < c.input_words; w += warps) {
       int i = w * 32 + lane;
-      uint32_t xin = __ldg(input + w);
+      uint32_t xin = input[w];
       bool on = false;
       if (i < c.input_dim) {
         double p = __dadd_rn(prow[i], ((xin >> lane) & 1u) ? c.sp_delta_on : c.sp_delta_off);
@@ -322,12 +355,19 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_learn(const bh_ctx c, const u
   }
 }
 
+__global__ void __launch_bounds__(SP_THREADS) k_sp_learn(const __grid_constant__ bh_ctx c, const uint32_t* input) {
+  ph_sp_learn(c, input, blockIdx.x, gridDim.x);
+}
+
 // (c) duty-cycle EMA: two separately rounded float32 operations.
 // regularizations.py:19-21; runs even when learning is off (networks.py:33).
-__global__ void k_duty_update(const bh_ctx c) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= c.column_dim) return;
-  float d = __fmul_rn(c.duty[j], c.duty_momentum);
-  if (c.col_active[j]) d = __fadd_rn(d, c.duty_increment);
-  c.duty[j] = d;
+__device__ __forceinline__ void ph_duty(const bh_ctx& c, int b, int nb) {
+  #pragma unroll 1
+  for (int j = b * blockDim.x + threadIdx.x; j < c.column_dim; j += nb * blockDim.x) {
+    float d = __fmul_rn(c.duty[j], c.duty_momentum);
+    if (c.col_active[j]) d = __fadd_rn(d, c.duty_increment);
+    c.duty[j] = d;
+  }
 }
+
+__global__ void k_duty_update(const __grid_constant__ bh_ctx c) { ph_duty(c, blockIdx.x, gridDim.x); }

@@ -1,4 +1,4 @@
-// Temporal-memory kernels.  Reference: bithtm/networks.py:91-128 (TemporalMemory.process),
+// Temporal-memory phases.  Reference: bithtm/networks.py:91-128 (TemporalMemory.process),
 // bithtm/projections.py:194-293 (PredictiveProjection) on top of :27-192 (SparseProjection).
 //
 // Data layout: a segment is a row of syn_capacity (cell, permanence)
@@ -8,28 +8,61 @@
 //
 // Every list whose ORDER the reference defines (winner cells, unaccounted winners,
 // matching segments = index of their jitter draw, learning segments = row of the
-// priority matrix, recycled segment ids) is produced by a two-kernel ordered
-// compaction: kernel A counts per CTA over contiguous ranges, kernel B derives
-// its offset from the per-CTA counts and writes in order.  No atomics decide an
-// order, so results are deterministic and equal to the reference's.
+// priority matrix, recycled segment ids) is produced by a two-phase ordered
+// compaction: phase A counts per CTA over contiguous ranges, phase B derives its
+// offset from the per-CTA counts and writes in order.  No atomics decide an order,
+// so results are deterministic and equal to the reference's.
+//
+// Cells are addressed on the device as column * 32 + cell (c <= 32), so column and
+// bit come from a shift and a mask; the host converts at the export boundary.
+//
+// Phase functions take (ctx, b, nb): CTA b of nb cooperating CTAs, any block size
+// that is a multiple of 32 (>= 256 for the draw phase).
 #pragma once
 
 #include "common.cuh"
 #include "mt19937.cuh"
 
-#define BLK(c, row) ((c).blk + (row)*BH_BLK_STRIDE)
+// Totals of the learning bookkeeping, derived identically by every CTA from the
+// per-CTA counts written by ph_learn_select_a (projections.py:264-281).
+struct LearnTotals {
+  int L0, P, n_u, n_r, n_new, L;
+  int l_before, p_before, r_before;
+  bool seg_overflow, learn_overflow;
+};
+
+__device__ __forceinline__ LearnTotals learn_totals(const bh_ctx& c, int learning, int b, int nb, int* s_red) {
+  LearnTotals t;
+  blk_prefix(BLK(c, BLK_LEARN), b, nb, s_red, t.l_before, t.L0);
+  blk_prefix(BLK(c, BLK_PUNISH), b, nb, s_red, t.p_before, t.P);
+  int R;
+  blk_prefix(BLK(c, BLK_RECYC), b, nb, s_red, t.r_before, R);
+  const int S = c.sc[BH_SC_NSEG];
+  t.n_u = (learning && c.sc[BH_SC_HAVE_PREV]) ? c.sc[BH_SC_NU] : 0;
+  t.n_r = t.n_u < R ? t.n_u : R;  // projections.py:80-81: recycle first
+  t.n_new = t.n_u - t.n_r;        // :90-94: then append
+  t.seg_overflow = S + t.n_new > c.seg_capacity;
+  if (t.seg_overflow) t.n_new = c.seg_capacity - S;
+  t.L = t.L0 + t.n_r + t.n_new;
+  t.learn_overflow = t.L > c.learn_capacity;
+  if (t.learn_overflow) t.L = c.learn_capacity;
+  return t;
+}
 
 // ---------------------------------------------------------------------------------
 // Random draws.  which = 1: rand(k, c) (networks.py:87); 2: rand(L, W+1)
-// (projections.py:120); 3: rand(M) (projections.py:235).  Single CTA; also the
-// sequence point where data-dependent scalars are committed.
+// (projections.py:120); 3: rand(M) (projections.py:235).  One CTA.  `nw` is the
+// number of CTAs that ran the ranged phases (for the per-CTA count arrays).
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MT_THREADS) k_tm_draw(const bh_ctx c, int which, int learning) {
+__device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, int nw) {
   __shared__ uint32_t x[2 * MT_N];
   __shared__ long long s_count, s_dst;
   __shared__ int s_red[32];
   int m_before = 0, m_total = 0;
-  if (which == 3) blk_prefix(BLK(c, BLK_MATCH), 0, c.tm_blocks, s_red, m_before, m_total);
+  LearnTotals lt;
+  lt.L = 0;
+  if (which == 3) blk_prefix(BLK(c, BLK_MATCH), 0, nw, s_red, m_before, m_total);
+  if (which == 2) lt = learn_totals(c, learning, 0, nw, s_red);
   if (threadIdx.x == 0) {
     int* sc = c.sc;
     const int cur = sc[BH_SC_STEP] & 1;
@@ -39,9 +72,8 @@ __global__ void __launch_bounds__(MT_THREADS) k_tm_draw(const bh_ctx c, int whic
       dst = 0;
       sc[BH_SC_OFF2] = (int)count;
     } else if (which == 2) {
-      sc[BH_SC_NSEG] = sc[BH_SC_NSEG_NEXT];
       dst = sc[BH_SC_OFF2];
-      if (learning && sc[BH_SC_HAVE_PREV]) count = (long long)sc[BH_SC_L] * (sc[BH_SC_W0 + (cur ^ 1)] + 1);
+      if (learning && sc[BH_SC_HAVE_PREV]) count = (long long)lt.L * (sc[BH_SC_W0 + (cur ^ 1)] + 1);
     } else {
       int M = m_total;
       if (M > c.match_capacity) {
@@ -63,36 +95,43 @@ __global__ void __launch_bounds__(MT_THREADS) k_tm_draw(const bh_ctx c, int whic
   }
   __syncthreads();
   mt_fill_block(x, c.mt_key, &c.sc[BH_SC_MT_POS], c.rand_buf + s_dst, s_count);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MT_THREADS) k_tm_draw(const __grid_constant__ bh_ctx c, int which, int learning) {
+  ph_draw(c, which, learning, c.tm_blocks);
 }
 
 // Plain stream fill (bh_rng_fill)
-__global__ void __launch_bounds__(MT_THREADS) k_rng_fill(const bh_ctx c, double* dst, long long count) {
+__global__ void __launch_bounds__(MT_THREADS) k_rng_fill(const __grid_constant__ bh_ctx c, double* dst, long long count) {
   __shared__ uint32_t x[2 * MT_N];
   mt_fill_block(x, c.mt_key, &c.sc[BH_SC_MT_POS], dst, count);
 }
 
 // ---------------------------------------------------------------------------------
-// (f) bursting + winner cells, part A: one warp per active column (lane = cell).
+// (f) bursting + winner cells, phase A: one warp per active column (lane = cell).
 // networks.py:95-104 with evaluate_cell_best_matching (:73-82) and
-// evaluate_cell_least_used (:84-89).
+// evaluate_cell_least_used (:84-89).  Also retires the winner words of columns that
+// were active last step but are not now.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_a(const bh_ctx c) {
+__device__ void ph_select_a(const bh_ctx& c, int b, int nb) {
   __shared__ int s_red[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x, nb = gridDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int k = c.active_columns, cd = c.cell_dim;
   const int cur = c.sc[BH_SC_STEP] & 1;
   const bool have_prev = c.sc[BH_SC_HAVE_PREV] != 0;
   const int* act = c.active_cols + cur * k;
+  const int* prev = c.active_cols + (cur ^ 1) * k;
   const double* rnd = c.rand_buf;  // draw #1 sits at offset 0
   const Range rg = block_range(k, b, nb);
   int n_win = 0, n_un = 0;
-  for (int r = rg.begin + warp; r < rg.end; r += BH_TM_WARPS) {
+  #pragma unroll 1
+  for (int r = rg.begin + warp; r < rg.end; r += warps) {
     const int col = act[r];
     const uint32_t pred = c.col_pred[col];  // previous step's prediction (networks.py:96)
     const bool burst = pred == 0u;          // networks.py:97
     const bool in = lane < cd;
-    const int cell = col * cd + lane;
+    const int cell = col * 32 + lane;
     // best matching (networks.py:76-81); float32 arithmetic as in the reference
     float mj = in ? c.cell_maxjit[cell] : 0.0f;
     float colmax = warp_max(mj);
@@ -118,6 +157,11 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_a(const bh_ctx c) {
       n_un += __popc(ubits);
     }
   }
+  #pragma unroll 1
+  for (int i = b * blockDim.x + threadIdx.x; i < k; i += nb * blockDim.x) {
+    int col = prev[i];
+    if (!c.col_active[col]) c.col_win[col] = 0u;
+  }
   int tw = block_sum(n_win, s_red);
   int tu = block_sum(n_un, s_red);
   if (threadIdx.x == 0) {
@@ -126,27 +170,26 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_a(const bh_ctx c) {
   }
 }
 
-// Part B: ordered winner / unaccounted lists (row order of active_column, cells
+// Phase B: ordered winner / unaccounted lists (row order of active_column, cells
 // ascending: np.where on the [k, c] mask, networks.py:103-104).
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_b(const bh_ctx c) {
+__device__ void ph_select_b(const bh_ctx& c, int b, int nb) {
   __shared__ int s_red[32];
-  const int b = blockIdx.x, nb = gridDim.x;
-  const int k = c.active_columns, cd = c.cell_dim;
+  const int k = c.active_columns, cd = c.cell_dim, NT = blockDim.x;
   const int cur = c.sc[BH_SC_STEP] & 1;
   const int* act = c.active_cols + cur * k;
-  const int* prev = c.active_cols + (cur ^ 1) * k;
   int* wl = c.winners + (long long)cur * k * cd;
   int w_before, w_total, u_before, u_total;
   blk_prefix(BLK(c, BLK_WIN), b, nb, s_red, w_before, w_total);
   blk_prefix(BLK(c, BLK_UNACC), b, nb, s_red, u_before, u_total);
   const Range rg = block_range(k, b, nb);
   int wbase = w_before, ubase = u_before;
-  for (int tile = rg.begin; tile < rg.end; tile += BH_TM_THREADS) {
+  #pragma unroll 1
+  for (int tile = rg.begin; tile < rg.end; tile += NT) {
     const int r = tile + threadIdx.x;
     const bool ok = r < rg.end;
     uint32_t wb = ok ? c.row_win[r] : 0u;
     uint32_t ub = ok ? c.row_unacc[r] : 0u;
-    const int cell0 = ok ? act[r] * cd : 0;
+    const int cell0 = ok ? act[r] * 32 : 0;
     int tot;
     int p = wbase + block_excl_scan(__popc(wb), s_red, tot);
     wbase += tot;
@@ -163,11 +206,6 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_b(const bh_ctx c) {
       c.unacc[p++] = cell0 + bit;
     }
   }
-  // retire winner words of columns that were active last step but are not now
-  for (int i = b * BH_TM_THREADS + threadIdx.x; i < k; i += nb * BH_TM_THREADS) {
-    int col = prev[i];
-    if (!c.col_active[col]) c.col_win[col] = 0u;
-  }
   if (b == 0 && threadIdx.x == 0) {
     c.sc[BH_SC_W0 + cur] = w_total;
     c.sc[BH_SC_NU] = u_total;
@@ -176,21 +214,22 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_b(const bh_ctx c) {
 
 // ---------------------------------------------------------------------------------
 // (f) learning / punished segment selection among the previous matching segments,
-// part A (flags + per-CTA counts).  projections.py:264-269.
+// phase A (flags + per-CTA counts, projections.py:264-269), plus the per-CTA count
+// of recyclable segments (fewer than `matching threshold` synapses, :80).
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_a(const bh_ctx c, int learning) {
+__device__ void ph_learn_select_a(const bh_ctx& c, int learning, int b, int nb) {
   __shared__ int s_red[32];
-  const int b = blockIdx.x, nb = gridDim.x;
-  const int cd = c.cell_dim;
+  const int NT = blockDim.x;
   const int M = c.sc[BH_SC_M];
   const Range rg = block_range(M, b, nb);
-  int nl = 0, np = 0;
-  for (int j = rg.begin + threadIdx.x; j < rg.end; j += BH_TM_THREADS) {
+  int nl = 0, np = 0, nr = 0;
+  #pragma unroll 1
+  for (int j = rg.begin + threadIdx.x; j < rg.end; j += NT) {
     uint8_t f = 0;
     if (learning) {
       const int s = c.m_seg[j];
       const int owner = c.seg_owner[s];
-      const int col = owner / cd, bit = owner - col * cd;
+      const int col = owner >> 5, bit = owner & 31;
       bool is_winner = (c.col_win[col] >> bit) & 1u;                               // :262
       bool seg_active = c.m_conn[j] >= c.seg_activation_threshold;                 // :250
       bool unpredicted = c.cell_npred[owner] == 0;                                 // :266
@@ -202,33 +241,38 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_a(const bh_ct
     nl += f & 1;
     np += (f >> 1) & 1;
   }
+  if (learning && c.sc[BH_SC_HAVE_PREV]) {
+    const int S = c.sc[BH_SC_NSEG], thr = c.seg_matching_threshold;
+    const Range sr = block_range(S, b, nb);
+    #pragma unroll 1
+    for (int s = sr.begin + threadIdx.x; s < sr.end; s += NT) nr += c.seg_count[s] < thr ? 1 : 0;
+  }
   int tl = block_sum(nl, s_red);
   int tp = block_sum(np, s_red);
+  int tr = block_sum(nr, s_red);
   if (threadIdx.x == 0) {
     BLK(c, BLK_LEARN)[b] = tl;
     BLK(c, BLK_PUNISH)[b] = tp;
+    BLK(c, BLK_RECYC)[b] = tr;
   }
 }
 
-// Part B: ordered learning / punished lists; segments for unaccounted winners:
-// recycle the lowest-id segments with fewer than `matching threshold` synapses,
-// then append new ids (projections.py:79-95, 271-281); and the sparse reset of the
-// per-cell results of the previous activation (all their readers ran already).
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_b(const bh_ctx c, int learning) {
+// Phase B: ordered learning / punished lists; segments for unaccounted winners:
+// recycle the lowest-id short segments, then append new ids (projections.py:79-95,
+// 271-281); and the sparse reset of the per-cell results of the previous activation
+// (all their readers ran already).
+__device__ void ph_learn_select_b(const bh_ctx& c, int learning, int b, int nb) {
   __shared__ int s_red[32];
-  const int b = blockIdx.x, nb = gridDim.x;
-  const int cd = c.cell_dim;
+  const int NT = blockDim.x;
   const int M = c.sc[BH_SC_M];
   const int S = c.sc[BH_SC_NSEG];
-  const int n_u = (learning && c.sc[BH_SC_HAVE_PREV]) ? c.sc[BH_SC_NU] : 0;
   const int thr = c.seg_matching_threshold;
-  int l_before, L0, p_before, P;
-  blk_prefix(BLK(c, BLK_LEARN), b, nb, s_red, l_before, L0);
-  blk_prefix(BLK(c, BLK_PUNISH), b, nb, s_red, p_before, P);
+  const LearnTotals lt = learn_totals(c, learning, b, nb, s_red);
   {
     const Range rg = block_range(M, b, nb);
-    int lbase = l_before, pbase = p_before;
-    for (int tile = rg.begin; tile < rg.end; tile += BH_TM_THREADS) {
+    int lbase = lt.l_before, pbase = lt.p_before;
+    #pragma unroll 1
+    for (int tile = rg.begin; tile < rg.end; tile += NT) {
       const int j = tile + threadIdx.x;
       const bool ok = j < rg.end;
       const int f = ok ? c.m_flag[j] : 0;
@@ -244,81 +288,175 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_b(const bh_ct
         const int owner = c.seg_owner[s];
         c.cell_maxjit[owner] = 0.0f;
         c.cell_npred[owner] = 0;
-        c.col_pred[owner / cd] = 0u;
+        c.col_pred[owner >> 5] = 0u;
       }
     }
   }
-  int n_r = 0, n_new = 0;
-  if (n_u > 0) {
-    int r_before, R;
-    blk_prefix(BLK(c, BLK_RECYC), b, nb, s_red, r_before, R);
-    n_r = n_u < R ? n_u : R;
-    n_new = n_u - n_r;
-    if (S + n_new > c.seg_capacity) {
-      n_new = c.seg_capacity - S;
-      if (b == 0 && threadIdx.x == 0) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_SEG_OVERFLOW);
-    }
-    if (L0 + n_r + n_new > c.learn_capacity && b == 0 && threadIdx.x == 0)
-      atomicOr(&c.sc[BH_SC_STATUS], BH_ST_LEARN_OVERFLOW);
-    if (r_before < n_u) {
+  if (lt.n_u > 0) {
+    if (lt.r_before < lt.n_u) {
       const Range sr = block_range(S, b, nb);
-      int rbase = r_before;
-      for (int tile = sr.begin; tile < sr.end && rbase < n_u; tile += BH_TM_THREADS) {
+      int rbase = lt.r_before;
+      #pragma unroll 1
+      for (int tile = sr.begin; tile < sr.end && rbase < lt.n_u; tile += NT) {
         const int s = tile + threadIdx.x;
         const bool rec = s < sr.end && c.seg_count[s] < thr;
         int tot;
         const int rank = rbase + block_excl_scan(rec ? 1 : 0, s_red, tot);
         rbase += tot;
-        if (rec && rank < n_u) {
+        if (rec && rank < lt.n_u) {
           const int newo = c.unacc[rank];
           atomicSub(&c.cell_nseg[c.seg_owner[s]], 1);  // :275-276
           atomicAdd(&c.cell_nseg[newo], 1);            // :277
           c.seg_owner[s] = newo;                       // :278
           c.seg_count[s] = 0;                          // :83-85 (row logically emptied)
-          const int pos = L0 + rank;
+          const int pos = lt.L0 + rank;
           if (pos < c.learn_capacity) c.learn_list[pos] = s;
         }
       }
     }
-    for (int i = b * BH_TM_THREADS + threadIdx.x; i < n_new; i += nb * BH_TM_THREADS) {
-      const int rank = n_r + i, s = S + i;
+    #pragma unroll 1
+    for (int i = b * NT + threadIdx.x; i < lt.n_new; i += nb * NT) {
+      const int rank = lt.n_r + i, s = S + i;
       const int owner = c.unacc[rank];
       c.seg_owner[s] = owner;  // :280
       c.seg_count[s] = 0;
       atomicAdd(&c.cell_nseg[owner], 1);
-      const int pos = L0 + rank;
+      const int pos = lt.L0 + rank;
       if (pos < c.learn_capacity) c.learn_list[pos] = s;
     }
   }
   if (b == 0 && threadIdx.x == 0) {
-    int L = L0 + n_r + n_new;
-    c.sc[BH_SC_L0] = L0;
-    c.sc[BH_SC_L] = L < c.learn_capacity ? L : c.learn_capacity;
-    c.sc[BH_SC_P] = P;
-    c.sc[BH_SC_NR] = n_r;
-    c.sc[BH_SC_NSEG_NEXT] = S + n_new;
+    c.sc[BH_SC_L0] = lt.L0;
+    c.sc[BH_SC_L] = lt.L;
+    c.sc[BH_SC_P] = lt.P;
+    c.sc[BH_SC_NR] = lt.n_r;
+    c.sc[BH_SC_NSEG_NEXT] = S + lt.n_new;
+    if (lt.seg_overflow) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_SEG_OVERFLOW);
+    if (lt.learn_overflow) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_LEARN_OVERFLOW);
   }
 }
 
 // ---------------------------------------------------------------------------------
-// (f) learning + punishment applied to segment rows.  One CTA per row.
-//  - permanence update in float64, stored as float32, synapses whose float64 sum is
-//    negative are deleted (projections.py:97-109); the row is re-compacted in place;
-//  - growth (learning rows only, projections.py:111-161): n_add = clip(sample -
-//    #synapses to previously active cells, 0, min(sample, W)); priorities are
-//    float32(rand(L, W+1)); previous winners already on the segment are excluded;
-//    the n_add smallest priorities < 1.0 win.  The cut is found by a 4x8-bit radix
-//    select over the float32 bit patterns (positive floats order like uints).
+// (f) learning + punishment applied to segment rows.
+//  Stage 1, one warp per row: permanence update in float64, stored as float32;
+//  synapses whose float64 sum is negative are deleted (projections.py:97-109) and the
+//  row is re-compacted in place.
+//  Stage 2, one CTA per learning row that must grow (projections.py:111-161):
+//  n_add = clip(sample - #synapses to previously active cells, 0, min(sample, W));
+//  priorities are float32(rand(L, W+1)); previous winners already on the segment are
+//  excluded (bitmap in shared memory); the n_add smallest priorities < 1.0 win.  The
+//  cut is found by a 4x8-bit radix select over the float32 bit patterns (positive
+//  floats order like unsigned ints); ties at the cut -> lower winner index and the
+//  PRI_TIE status bit (np.argsort is undefined there).
+//  `s_excl` = dynamic shared memory, ceil(k*c/32) words.
 // ---------------------------------------------------------------------------------
-#define LA_THREADS 128
+__device__ void grow_row(const bh_ctx& c, int row, int s, int n, int n_add, int Wp, const int* prevw, long long off2,
+                         bool pr_ok, uint32_t* s_excl, int* s_red, int* s_hist, int* s_rem, uint32_t* s_prefix) {
+  const int t = threadIdx.x, NT = blockDim.x, E = c.syn_capacity;
+  int* cells = c.syn_cell + (long long)s * E;
+  float* perms = c.syn_perm + (long long)s * E;
+  const int excl_words = (Wp + 31) >> 5;
+  #pragma unroll 1
+  for (int i = t; i < excl_words; i += NT) s_excl[i] = 0u;
+  __syncthreads();
+  #pragma unroll 1
+  for (int slot = t; slot < n; slot += NT) {  // projections.py:117-121
+    const int wi = c.cell_widx[cells[slot]];
+    if (wi >= 0) atomicOr(&s_excl[wi >> 5], 1u << (wi & 31));
+  }
+  __syncthreads();
+  const double* pr = c.rand_buf + off2 + (long long)row * (Wp + 1);  // row of rand(L, W+1)
+  // candidates: previous winners not yet on the segment with priority < 1.0 (:121-123)
+  int nc = 0;
+  #pragma unroll 1
+  for (int w = t; w < Wp; w += NT) {
+    bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
+    float pri = pr_ok ? __double2float_rn(pr[w]) : 2.0f;
+    nc += (!ex && pri < 1.0f) ? 1 : 0;
+  }
+  nc = block_sum(nc, s_red);
+  uint32_t cut = 0x3f800000u;  // bits of 1.0f: take every candidate
+  int ties_wanted = 0;
+  if (nc > n_add) {
+    if (t == 0) {
+      *s_prefix = 0u;
+      *s_rem = n_add;
+    }
+    __syncthreads();
+    for (int pass = 3; pass >= 0; --pass) {
+      #pragma unroll 1
+      for (int i = t; i < 256; i += NT) s_hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = *s_prefix;
+      const int shift = pass * 8;
+      const uint32_t hi_mask = pass == 3 ? 0u : (0xffffffffu << (shift + 8));
+      #pragma unroll 1
+      for (int w = t; w < Wp; w += NT) {
+        bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
+        float pri = __double2float_rn(pr[w]);
+        uint32_t bits = __float_as_uint(pri);
+        if (!ex && pri < 1.0f && (bits & hi_mask) == prefix) atomicAdd(&s_hist[(bits >> shift) & 0xff], 1);
+      }
+      __syncthreads();
+      if (t == 0) {
+        int rem = *s_rem, d = 0;
+        for (; d < 255; ++d) {
+          if (s_hist[d] >= rem) break;
+          rem -= s_hist[d];
+        }
+        *s_rem = rem;
+        *s_prefix = prefix | ((uint32_t)d << shift);
+      }
+      __syncthreads();
+    }
+    cut = *s_prefix;       // the n_add-th smallest candidate priority
+    ties_wanted = *s_rem;  // how many candidates == cut to take (lowest index first)
+  }
+  // ordered append of the chosen winners
+  int base = n, tie_base = 0;
+  #pragma unroll 1
+  for (int tile = 0; tile < Wp; tile += NT) {
+    const int w = tile + t;
+    bool cand = false;
+    uint32_t bits = 0u;
+    if (w < Wp) {
+      bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
+      float pri = pr_ok ? __double2float_rn(pr[w]) : 2.0f;
+      bits = __float_as_uint(pri);
+      cand = !ex && pri < 1.0f;
+    }
+    const bool lt = cand && bits < cut;
+    const bool eq = cand && bits == cut && cut != 0x3f800000u;
+    int tot_eq, tot;
+    const int tie_rank = tie_base + block_excl_scan(eq ? 1 : 0, s_red, tot_eq);
+    const bool take = lt || (eq && tie_rank < ties_wanted);
+    const int pos = base + block_excl_scan(take ? 1 : 0, s_red, tot);
+    if (take) {
+      if (pos < E) {
+        cells[pos] = prevw[w];
+        perms[pos] = c.tm_perm_initial;  // :149
+      } else {
+        atomicOr(&c.sc[BH_SC_STATUS], BH_ST_SYN_OVERFLOW);
+      }
+    }
+    base += tot;
+    tie_base += tot_eq;
+  }
+  if (t == 0) {
+    c.seg_count[s] = base < E ? base : E;  // :161
+    if (nc > n_add && tie_base > ties_wanted) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_PRI_TIE);
+  }
+  __syncthreads();
+}
 
-__global__ void __launch_bounds__(LA_THREADS) k_tm_learn_apply(const bh_ctx c) {
-  extern __shared__ uint32_t s_excl[];  // bitmap over previous-winner indices
+__device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb) {
   __shared__ int s_red[32];
   __shared__ int s_hist[256];
-  __shared__ int s_n, s_nact, s_rem;
+  __shared__ int s_rem;
   __shared__ uint32_t s_prefix;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ int s_ngrow;
+  __shared__ int s_grow_row[BH_MAX_WARPS], s_grow_n[BH_MAX_WARPS], s_grow_add[BH_MAX_WARPS];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, warps = blockDim.x >> 5;
   const int cd = c.cell_dim, E = c.syn_capacity;
   const int L = c.sc[BH_SC_L], P = c.sc[BH_SC_P];
   const int cur = c.sc[BH_SC_STEP] & 1;
@@ -327,147 +465,80 @@ __global__ void __launch_bounds__(LA_THREADS) k_tm_learn_apply(const bh_ctx c) {
   const long long off2 = c.sc[BH_SC_OFF2];
   const long long rand_fill = c.sc[BH_SC_RAND_FILL];
   const int sample = c.seg_sampling_synapses;
-  const int excl_words = (Wp + 31) >> 5;
+  const int cap = sample < Wp ? sample : Wp;
 
-  for (int row = blockIdx.x; row < L + P; row += gridDim.x) {
-    const bool learn = row < L;
-    const int s = learn ? c.learn_list[row] : c.punish_list[row - L];
-    const double d_on = learn ? c.tm_learn_on : c.tm_punish_on;
-    const double d_off = learn ? c.tm_learn_off : c.tm_punish_off;
-    const bool can_delete = learn ? c.tm_learn_can_delete : c.tm_punish_can_delete;
-    int* cells = c.syn_cell + (long long)s * E;
-    float* perms = c.syn_perm + (long long)s * E;
-    if (learn)
-      for (int i = t; i < excl_words; i += LA_THREADS) s_excl[i] = 0u;
+  #pragma unroll 1
+  for (int base_row = 0; base_row < L + P; base_row += nb * warps) {
+    if (t == 0) s_ngrow = 0;
     __syncthreads();
-
-    if (warp == 0) {
+    // ---- stage 1: one warp per row (rows interleaved over CTAs) -------------------
+    const int row = base_row + warp * nb + b;
+    if (row < L + P) {
+      const bool learn = row < L;
+      const int s = learn ? c.learn_list[row] : c.punish_list[row - L];
+      const double d_on = learn ? c.tm_learn_on : c.tm_punish_on;
+      const double d_off = learn ? c.tm_learn_off : c.tm_punish_off;
+      const bool can_delete = learn ? c.tm_learn_can_delete : c.tm_punish_can_delete;
+      int* cells = c.syn_cell + (long long)s * E;
+      float* perms = c.syn_perm + (long long)s * E;
       const int n = c.seg_count[s];
-      int base = 0, n_act = 0;
+      int kept = 0, n_act = 0;
+      #pragma unroll 1
       for (int g = 0; g < n; g += 32) {
         const int slot = g + lane;
         const bool valid = slot < n;
         const int cell = valid ? cells[slot] : 0;
         const float p = valid ? perms[slot] : 0.0f;
-        const bool act = valid && cell_bit(c.col_act, cell, cd);  // previous activation (networks.py:111)
+        const bool act = valid && cell_bit(c.col_act, cell);          // previous activation (networks.py:111)
         const double sum = __dadd_rn((double)p, act ? d_on : d_off);  // :102-103
         const bool keep = valid && !(can_delete && sum < 0.0);        // :105-108
         const uint32_t kb = __ballot_sync(BH_FULL, keep);
         const uint32_t ab = __ballot_sync(BH_FULL, keep && act);
-        const int pos = base + __popc(kb & ((1u << lane) - 1u));
+        const int pos = kept + __popc(kb & ((1u << lane) - 1u));
         if (keep) {
           cells[pos] = cell;
           perms[pos] = __double2float_rn(sum);
-          if (learn) {
-            const int wi = c.cell_widx[cell];  // projections.py:117-121
-            if (wi >= 0) atomicOr(&s_excl[wi >> 5], 1u << (wi & 31));
-          }
         }
         __syncwarp();
-        base += __popc(kb);
+        kept += __popc(kb);
         n_act += __popc(ab);
       }
       if (lane == 0) {
-        s_n = base;
-        s_nact = n_act;
+        c.seg_count[s] = kept;
+        int n_add = sample - n_act;  // projections.py:114-115
+        n_add = n_add < 0 ? 0 : (n_add > cap ? cap : n_add);
+        if (learn && n_add > 0) {
+          const int g = atomicAdd(&s_ngrow, 1);
+          s_grow_row[g] = row;
+          s_grow_n[g] = kept;
+          s_grow_add[g] = n_add;
+        }
       }
     }
     __syncthreads();
-    const int n = s_n;
-    int cap = sample < Wp ? sample : Wp;
-    int n_add = sample - s_nact;  // projections.py:114-115
-    n_add = n_add < 0 ? 0 : (n_add > cap ? cap : n_add);
-    if (!learn || n_add == 0) {
-      if (t == 0) c.seg_count[s] = n;
-      __syncthreads();
-      continue;
-    }
-    const double* pr = c.rand_buf + off2 + (long long)row * (Wp + 1);  // row of rand(L, W+1)
-    const bool pr_ok = off2 + (long long)(row + 1) * (Wp + 1) <= rand_fill;
-
-    // candidates: previous winners not yet on the segment with priority < 1.0 (:121-123)
-    int nc = 0;
-    for (int w = t; w < Wp; w += LA_THREADS) {
-      bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
-      float pri = pr_ok ? __double2float_rn(pr[w]) : 2.0f;
-      nc += (!ex && pri < 1.0f) ? 1 : 0;
-    }
-    nc = block_sum(nc, s_red);
-    uint32_t cut = 0x3f800000u;  // bits of 1.0f: take every candidate
-    int ties_wanted = 0;
-    if (nc > n_add) {
-      if (t == 0) { s_prefix = 0u; s_rem = n_add; }
-      __syncthreads();
-      for (int pass = 3; pass >= 0; --pass) {
-        for (int i = t; i < 256; i += LA_THREADS) s_hist[i] = 0;
-        __syncthreads();
-        const uint32_t prefix = s_prefix;
-        const int shift = pass * 8;
-        const uint32_t hi_mask = pass == 3 ? 0u : (0xffffffffu << (shift + 8));
-        for (int w = t; w < Wp; w += LA_THREADS) {
-          bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
-          float pri = __double2float_rn(pr[w]);
-          uint32_t bits = __float_as_uint(pri);
-          if (!ex && pri < 1.0f && (bits & hi_mask) == prefix) atomicAdd(&s_hist[(bits >> shift) & 0xff], 1);
-        }
-        __syncthreads();
-        if (t == 0) {
-          int rem = s_rem, d = 0;
-          for (; d < 255; ++d) {
-            if (s_hist[d] >= rem) break;
-            rem -= s_hist[d];
-          }
-          s_rem = rem;
-          s_prefix = prefix | ((uint32_t)d << shift);
-        }
-        __syncthreads();
-      }
-      cut = s_prefix;        // the n_add-th smallest candidate priority
-      ties_wanted = s_rem;   // how many candidates == cut to take (lowest index first)
-    }
-    // ordered append of the chosen winners
-    int base = n, tie_base = 0, tie_total_all = 0;
-    for (int tile = 0; tile < Wp; tile += LA_THREADS) {
-      const int w = tile + t;
-      bool cand = false;
-      uint32_t bits = 0u;
-      if (w < Wp) {
-        bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
-        float pri = pr_ok ? __double2float_rn(pr[w]) : 2.0f;
-        bits = __float_as_uint(pri);
-        cand = !ex && pri < 1.0f;
-      }
-      const bool lt = cand && bits < cut;
-      const bool eq = cand && bits == cut && cut != 0x3f800000u;
-      int tot_eq, tot;
-      const int tie_rank = tie_base + block_excl_scan(eq ? 1 : 0, s_red, tot_eq);
-      const bool take = lt || (eq && tie_rank < ties_wanted);
-      const int pos = base + block_excl_scan(take ? 1 : 0, s_red, tot);
-      if (take) {
-        if (pos < E) {
-          cells[pos] = prevw[w];
-          perms[pos] = c.tm_perm_initial;
-        } else {
-          atomicOr(&c.sc[BH_SC_STATUS], BH_ST_SYN_OVERFLOW);
-        }
-      }
-      base += tot;
-      tie_base += tot_eq;
-      tie_total_all += tot_eq;
-    }
-    if (t == 0) {
-      c.seg_count[s] = base < E ? base : E;
-      if (tie_total_all > ties_wanted && nc > n_add) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_PRI_TIE);
+    // ---- stage 2: the whole CTA grows the rows its warps flagged ------------------
+    const int ng = s_ngrow;
+    for (int g = 0; g < ng; ++g) {
+      const int grow = s_grow_row[g];
+      const bool pr_ok = off2 + (long long)(grow + 1) * (Wp + 1) <= rand_fill;
+      grow_row(c, grow, c.learn_list[grow], s_grow_n[g], s_grow_add[g], Wp, prevw, off2, pr_ok, s_excl, s_red,
+               s_hist, &s_rem, &s_prefix);
     }
     __syncthreads();
   }
 }
 
+#define LA_THREADS 256
+__global__ void __launch_bounds__(LA_THREADS) k_tm_learn_apply(const __grid_constant__ bh_ctx c) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  ph_learn_apply(c, s_dyn, blockIdx.x, gridDim.x);
+}
+
 // ---------------------------------------------------------------------------------
 // Commit this step's activation and winner index (after learning read the previous
-// ones).  networks.py:118-119; projections.py:117-118 (whole_input_to_winner).
+// ones) and the segment count.  networks.py:118-119; projections.py:117-118.
 // ---------------------------------------------------------------------------------
-__global__ void k_tm_post(const bh_ctx c) {
+__device__ void ph_post(const bh_ctx& c, int b, int nb) {
   const int k = c.active_columns, cd = c.cell_dim;
   const int cur = c.sc[BH_SC_STEP] & 1;
   const int* act = c.active_cols + cur * k;
@@ -475,68 +546,102 @@ __global__ void k_tm_post(const bh_ctx c) {
   const int Wc = c.sc[BH_SC_W0 + cur], Wp = c.sc[BH_SC_W0 + (cur ^ 1)];
   const int* wl_cur = c.winners + (long long)cur * k * cd;
   const int* wl_prev = c.winners + (long long)(cur ^ 1) * k * cd;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  const int gid = b * blockDim.x + threadIdx.x, gsz = nb * blockDim.x;
+  #pragma unroll 1
   for (int r = gid; r < k; r += gsz) {
     c.col_act[act[r]] = c.row_act[r];
     int pc = prev[r];
     if (!c.col_active[pc]) c.col_act[pc] = 0u;
   }
+  #pragma unroll 1
   for (int i = gid; i < Wc; i += gsz) c.cell_widx[wl_cur[i]] = i;
+  #pragma unroll 1
   for (int i = gid; i < Wp; i += gsz) {
     int cell = wl_prev[i];
-    int col = cell / cd;
-    if (!((c.col_win[col] >> (cell - col * cd)) & 1u)) c.cell_widx[cell] = -1;
+    if (!((c.col_win[cell >> 5] >> (cell & 31)) & 1u)) c.cell_widx[cell] = -1;
   }
+  if (gid == 0) c.sc[BH_SC_NSEG] = c.sc[BH_SC_NSEG_NEXT];
 }
 
 // ---------------------------------------------------------------------------------
-// (e) segment activation, part A: one warp per segment scans its synapses against
-// the active-cell bits.  potential = synapses to active cells (projections.py:175-178),
-// connected-active = those with permanence >= threshold (:167-173).
+// (e) segment activation, phase A: one warp per segment scans its synapses against
+// the active-cell bit-words.  potential = synapses to active cells
+// (projections.py:175-178), connected-active = those with permanence >= threshold
+// (:167-173).
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_a(const bh_ctx c) {
+#define ACT_BATCH 4  // segments per warp iteration, 64 slots each: 16 independent loads in flight per lane
+__device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
   __shared__ int s_red[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x, nb = gridDim.x;
-  const int cd = c.cell_dim, E = c.syn_capacity;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int E = c.syn_capacity;
   const int S = c.sc[BH_SC_NSEG];
   const int thr = c.seg_matching_threshold;
+  const float pthr = c.tm_perm_threshold;
+  const uint32_t* col_act = c.col_act;
   const Range rg = block_range(S, b, nb);
-  int nm = 0, nr = 0;
-  for (int s = rg.begin + warp; s < rg.end; s += BH_TM_WARPS) {
-    const int n = c.seg_count[s];
-    const int* cells = c.syn_cell + (long long)s * E;
-    const float* perms = c.syn_perm + (long long)s * E;
-    int pot = 0, conn = 0;
-    for (int slot = lane; slot < n; slot += 32) {
-      const bool a = cell_bit(c.col_act, cells[slot], cd);
-      pot += a ? 1 : 0;
-      conn += (a && perms[slot] >= c.tm_perm_threshold) ? 1 : 0;
+  int nm = 0;
+#pragma unroll 1
+  for (int s0 = rg.begin + warp * ACT_BATCH; s0 < rg.end; s0 += warps * ACT_BATCH) {
+    // counts of the batch with one load, then slots [0, 64) of every row at once
+    const int my_n = (lane < ACT_BATCH && s0 + lane < rg.end) ? c.seg_count[s0 + lane] : 0;
+    int n[ACT_BATCH], cell[ACT_BATCH][2];
+    float perm[ACT_BATCH][2];
+#pragma unroll
+    for (int j = 0; j < ACT_BATCH; ++j) {
+      n[j] = __shfl_sync(BH_FULL, my_n, j);
+      const long long base = (long long)(s0 + j) * E + lane;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool v = lane + 32 * h < n[j];
+        cell[j][h] = v ? c.syn_cell[base + 32 * h] : 0;
+        perm[j][h] = v ? c.syn_perm[base + 32 * h] : 0.0f;
+      }
     }
-    pot = warp_sum(pot);
-    conn = warp_sum(conn);
-    if (lane == 0) {
-      c.seg_pot[s] = pot;
-      c.seg_conn[s] = conn;
-      nm += pot >= thr ? 1 : 0;
-      nr += n < thr ? 1 : 0;
+    uint32_t word[ACT_BATCH][2];
+#pragma unroll
+    for (int j = 0; j < ACT_BATCH; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) word[j][h] = lane + 32 * h < n[j] ? col_act[cell[j][h] >> 5] : 0u;
+#pragma unroll
+    for (int j = 0; j < ACT_BATCH; ++j) {
+      int pot = 0, conn = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool a = lane + 32 * h < n[j] && ((word[j][h] >> (cell[j][h] & 31)) & 1u);
+        pot += __popc(__ballot_sync(BH_FULL, a));
+        conn += __popc(__ballot_sync(BH_FULL, a && perm[j][h] >= pthr));
+      }
+      if (n[j] > 64) {  // rows longer than two warp-widths
+        const int s = s0 + j;
+#pragma unroll 1
+        for (int g = 64; g < n[j]; g += 32) {
+          const int slot = g + lane;
+          const bool v = slot < n[j];
+          const int cl = v ? c.syn_cell[(long long)s * E + slot] : 0;
+          const float pm = v ? c.syn_perm[(long long)s * E + slot] : 0.0f;
+          const bool a2 = v && cell_bit(col_act, cl);
+          pot += __popc(__ballot_sync(BH_FULL, a2));
+          conn += __popc(__ballot_sync(BH_FULL, a2 && pm >= pthr));
+        }
+      }
+      if (lane == 0 && s0 + j < rg.end) {
+        c.seg_pot[s0 + j] = pot;
+        c.seg_conn[s0 + j] = conn;
+        nm += pot >= thr ? 1 : 0;
+      }
     }
   }
   int tm = block_sum(nm, s_red);
-  int tr = block_sum(nr, s_red);
-  if (threadIdx.x == 0) {
-    BLK(c, BLK_MATCH)[b] = tm;
-    BLK(c, BLK_RECYC)[b] = tr;
-  }
+  if (threadIdx.x == 0) BLK(c, BLK_MATCH)[b] = tm;
 }
 
-// Part B: matching list in ascending segment id (np.where, projections.py:247),
+// Phase B: matching list in ascending segment id (np.where, projections.py:247),
 // jittered potential f32(f64(potential) + u) with the draw indexed by the rank in
 // that list (:234-235), per-cell maximum (:236-237) and active-segment count (:251).
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const bh_ctx c) {
+// CTA 0 completes the timestep.
+__device__ void ph_activate_b(const bh_ctx& c, int b, int nb) {
   __shared__ int s_red[32];
-  const int b = blockIdx.x, nb = gridDim.x;
-  const int cd = c.cell_dim;
+  const int NT = blockDim.x;
   const int S = c.sc[BH_SC_NSEG];
   const int thr = c.seg_matching_threshold;
   const long long off3 = c.sc[BH_SC_OFF3];
@@ -545,7 +650,8 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const bh_ctx c)
   blk_prefix(BLK(c, BLK_MATCH), b, nb, s_red, m_before, m_total);
   const Range rg = block_range(S, b, nb);
   int base = m_before;
-  for (int tile = rg.begin; tile < rg.end; tile += BH_TM_THREADS) {
+  #pragma unroll 1
+  for (int tile = rg.begin; tile < rg.end; tile += NT) {
     const int s = tile + threadIdx.x;
     const bool ok = s < rg.end;
     const int pot = ok ? c.seg_pot[s] : 0;
@@ -564,8 +670,7 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const bh_ctx c)
       atomicMax(reinterpret_cast<int*>(c.cell_maxjit + owner), __float_as_int(jit));  // jit > 0
       if (conn >= c.seg_activation_threshold) {
         atomicAdd(&c.cell_npred[owner], 1);
-        const int col = owner / cd;
-        atomicOr(&c.col_pred[col], 1u << (owner - col * cd));
+        atomicOr(&c.col_pred[owner >> 5], 1u << (owner & 31));
       }
     }
   }
@@ -575,24 +680,44 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const bh_ctx c)
   }
 }
 
+// ---------------------------------------------------------------------------------
+// stand-alone kernels (fine-grained C entry points)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_a(const __grid_constant__ bh_ctx c) { ph_select_a(c, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_b(const __grid_constant__ bh_ctx c) { ph_select_b(c, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_a(const __grid_constant__ bh_ctx c, int learning) {
+  ph_learn_select_a(c, learning, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_b(const __grid_constant__ bh_ctx c, int learning) {
+  ph_learn_select_b(c, learning, blockIdx.x, gridDim.x);
+}
+__global__ void k_tm_post(const __grid_constant__ bh_ctx c) { ph_post(c, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_a(const __grid_constant__ bh_ctx c) { ph_activate_a(c, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const __grid_constant__ bh_ctx c) { ph_activate_b(c, blockIdx.x, gridDim.x); }
+
 // Step summary for the host (bh_step_host): see include/bithtm_b200.h
-__global__ void k_summary(const bh_ctx c) {
+__device__ void ph_summary(const bh_ctx& c, int b, int nb) {
   const int k = c.active_columns;
   const int done = c.sc[BH_SC_STEP] - 1;  // the step that just completed
   const int cur = done & 1;
   int* out = c.summary_dev;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  const int gid = b * blockDim.x + threadIdx.x, gsz = nb * blockDim.x;
+  if (gid == 0) {
     out[0] = done;
     out[1] = c.sc[BH_SC_STATUS];
     out[2] = c.sc[BH_SC_NSEG];
     out[3] = c.sc[BH_SC_W0 + cur];
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+  #pragma unroll 1
+  for (int i = gid; i < k; i += gsz) {
     out[4 + i] = c.active_cols[cur * k + i];
     out[4 + k + i] = (int)c.row_pred[i];
     out[4 + 2 * k + i] = (int)c.row_act[i];
     out[4 + 3 * k + i] = (int)c.row_win[i];
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= BH_MT_N; i += gridDim.x * blockDim.x)
+  #pragma unroll 1
+  for (int i = gid; i <= BH_MT_N; i += gsz)
     out[4 + 4 * k + i] = i < BH_MT_N ? (int)c.mt_key[i] : c.sc[BH_SC_MT_POS];
 }
+
+__global__ void k_summary(const __grid_constant__ bh_ctx c) { ph_summary(c, blockIdx.x, gridDim.x); }

@@ -130,7 +130,7 @@ class PredictiveProjection:
 
         @property
         def prediction(self):  # :251 float64 count of active segments per cell
-            return self._get("prediction", lambda: self._engine.buf["cell_npred"].cpu().numpy().astype(np.float64))
+            return self._get("prediction", lambda: self._engine.per_cell("cell_npred").astype(np.float64))
 
         @property
         def segment_potential(self):  # :246 int64 [S]
@@ -153,7 +153,7 @@ class PredictiveProjection:
 
         @property
         def max_jittered_potential(self):  # :236-238 float32 [N]
-            return self._get("max_jittered_potential", lambda: self._engine.buf["cell_maxjit"].cpu().numpy())
+            return self._get("max_jittered_potential", lambda: self._engine.per_cell("cell_maxjit"))
 
         @property
         def matching_segment_jittered_potential(self):  # :234-235 float32 [M]
@@ -217,7 +217,7 @@ class PredictiveProjection:
     def bundle_segments(self):  # projections.py:227 int32 [N]
         if self._engine is None:
             return np.zeros(self.output_dim, dtype=np.int32)
-        return self._engine.buf["cell_nseg"].cpu().numpy()
+        return self._engine.per_cell("cell_nseg")
 
     @property
     def n_segments(self):
@@ -228,7 +228,8 @@ class PredictiveProjection:
         S = self.n_segments
         if S == 0:
             return np.zeros((0, 1), dtype=np.int32)
-        return self._engine.buf["seg_owner"][:S].cpu().numpy().reshape(S, 1)
+        eng = self._engine
+        return eng.cells_to_flat(eng.buf["seg_owner"][:S].cpu().numpy()).astype(np.int32).reshape(S, 1)
 
     def export_segments(self):
         """(owner[S], count[S], cells[S, E], perm[S, E]) with free slots = -1 / -1.0 --
@@ -236,9 +237,9 @@ class PredictiveProjection:
         S = self.n_segments
         eng = self._engine
         E = eng.ctx.syn_capacity
-        owner = eng.buf["seg_owner"][:S].cpu().numpy()
+        owner = eng.cells_to_flat(eng.buf["seg_owner"][:S].cpu().numpy())
         count = eng.buf["seg_count"][:S].cpu().numpy()
-        cells = eng.buf["syn_cell"][:S * E].cpu().numpy().reshape(S, E).copy()
+        cells = eng.cells_to_flat(eng.buf["syn_cell"][:S * E].cpu().numpy()).reshape(S, E)
         perm = eng.buf["syn_perm"][:S * E].cpu().numpy().reshape(S, E).copy()
         free = np.arange(E)[None, :] >= count[:, None]
         cells[free] = -1

@@ -58,6 +58,8 @@ enum {
   BH_SC_OFF2,          /* offset of draw #2 (rand(L, W+1)) in rand_buf             */
   BH_SC_OFF3,          /* offset of draw #3 (rand(M)) in rand_buf                  */
   BH_SC_INPUT_POS,     /* cursor into the device input ring (bh_step_ring)         */
+  BH_SC_BAR_COUNT,     /* grid barrier of the fused kernel: arrivals               */
+  BH_SC_BAR_GEN,       /*                                   generation             */
   BH_SC_COUNT = 32
 };
 
@@ -86,7 +88,8 @@ typedef struct bh_ctx {
   int32_t sm_count;        /* SMs of the device (grid sizing)                      */
   int64_t rand_capacity;   /* doubles in rand_buf                                  */
   int32_t ring_len;        /* rows in input_ring (0 = none)                        */
-  int32_t reserved0;
+  int32_t fused_mode;      /* bh_step*: 0 = one kernel per stage, 1 = one kernel on a  */
+                           /* thread-block cluster, 2 = one cooperative-grid kernel   */
 
   /* ---- constants, evaluated on the host with the reference's expressions ----- */
   double sp_threshold;     /* projections.py:19  permanence >= threshold           */
@@ -107,7 +110,7 @@ typedef struct bh_ctx {
   int32_t seg_activation_threshold;
   int32_t seg_matching_threshold;
   int32_t seg_sampling_synapses;
-  int32_t reserved1;
+  int32_t fused_ctas;      /* CTAs of the fused kernel (cluster size <= 16, or grid)  */
 
   /* ---- spatial pooler (DenseProjection / ExponentialBoosting / inhibition) --- */
   double* sp_perm;         /* [C][I] float64 permanence, row-major                 */
@@ -118,21 +121,22 @@ typedef struct bh_ctx {
   int32_t* active_cols;    /* [2][k] ping-pong by step parity, reference order     */
   uint8_t* col_active;     /* [C] 1 for the current active columns                 */
 
-  /* ---- temporal memory: per column (bit b = cell b) and per cell ------------- */
+  /* ---- temporal memory: per column (bit b = cell b) and per cell.  Cells are    */
+  /* addressed on the device as column * 32 + cell; N32 = 32 * C.                  */
   uint32_t* col_pred;      /* [C] cell_prediction        networks.py:122           */
   uint32_t* col_act;       /* [C] cell_activation        networks.py:118-119       */
   uint32_t* col_win;       /* [C] winner cells of the current step                 */
-  int32_t* cell_nseg;      /* [N] bundle_segments        projections.py:227        */
-  float* cell_maxjit;      /* [N] max_jittered_potential projections.py:236-237    */
-  int32_t* cell_npred;     /* [N] prediction (active segments per cell)  :251      */
-  int32_t* cell_widx;      /* [N] index in the previous winner list or -1          */
+  int32_t* cell_nseg;      /* [N32] bundle_segments        projections.py:227        */
+  float* cell_maxjit;      /* [N32] max_jittered_potential projections.py:236-237    */
+  int32_t* cell_npred;     /* [N32] prediction (active segments per cell)  :251      */
+  int32_t* cell_widx;      /* [N32] index in the previous winner list or -1          */
 
   /* ---- segments (rows kept compact: valid synapses are slots [0, count)) ----- */
   int32_t* seg_owner;      /* [S_cap] segment_bundle     projections.py:226        */
   int32_t* seg_count;      /* [S_cap] output_edges       projections.py:42         */
   int32_t* seg_pot;        /* [S_cap] segment_potential  projections.py:246        */
   int32_t* seg_conn;       /* [S_cap] connected-active count                       */
-  int32_t* syn_cell;       /* [S_cap][E_cap] presynaptic flat cell                 */
+  int32_t* syn_cell;       /* [S_cap][E_cap] presynaptic cell (column * 32 + cell) */
   float* syn_perm;         /* [S_cap][E_cap] float32 permanence                    */
 
   /* ---- per-step lists ---------------------------------------------------------- */

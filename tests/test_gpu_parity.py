@@ -139,20 +139,26 @@ def _lockstep(name, steps=None, check_every=1, **engine_kw):
     return htm, orc
 
 
-def test_lockstep_tiny():
-    _lockstep("tiny")
+@pytest.mark.parametrize("fused,ctas", [("cluster", 8), ("cluster", 1), ("cluster", 3), ("cluster", 16),
+                                        ("grid", None), ("grid", 5), ("off", None)])
+def test_lockstep_tiny(fused, ctas):
+    """Every execution mode of the step: one kernel on a thread-block cluster of
+    1..16 CTAs, one cooperative-grid kernel, or one kernel per stage."""
+    _lockstep("tiny", fused=fused, fused_ctas=ctas)
 
 
-def test_lockstep_odd_dims():
-    _lockstep("odd")
+@pytest.mark.parametrize("fused", ["cluster", "grid", "off"])
+def test_lockstep_odd_dims(fused):
+    _lockstep("odd", fused=fused)
 
 
 def test_lockstep_mid():
     _lockstep("mid", check_every=3)
 
 
-def test_lockstep_cfg2_1500_steps():
-    _lockstep("cfg2", steps=1500, check_every=10)
+@pytest.mark.parametrize("fused", ["cluster", "grid", "off"])
+def test_lockstep_cfg2_1500_steps(fused):
+    _lockstep("cfg2", steps=1500, check_every=10, fused=fused)
 
 
 def _golden_trace(name, **engine_kw):
@@ -235,7 +241,8 @@ def test_learning_off_matches_oracle():
     assert gpu_state_digest(htm) == oracle_state_digest(orc)
 
 
-def test_graph_replay_equals_stepwise():
+@pytest.mark.parametrize("fused", ["cluster", "off"])
+def test_graph_replay_equals_stepwise(fused):
     """bh_step_ring under a CUDA graph (the bench's device-resident path) ends in
     the same learned state as the host-driven path."""
     import bithtm_b200 as bithtm
@@ -247,7 +254,7 @@ def test_graph_replay_equals_stepwise():
     a = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], rng_sync="lazy")
     np.random.seed(info["seed"])
     b = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], rng_sync="lazy",
-                                          ring_len=steps)
+                                          ring_len=steps, fused=fused)
     for t in range(steps):
         a.process(xs[t])
     eng = b.engine
