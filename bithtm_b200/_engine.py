@@ -44,7 +44,10 @@ class Engine:
     def __init__(self, input_dim, column_dim, cell_dim, active_columns, *, device=None,
                  max_segments=None, max_synapses_per_segment=128, match_capacity=None,
                  learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
-                 fused="auto", fused_ctas=None):
+                 fused="auto", fused_ctas=None, column_shard=None):
+        """``column_shard=(rank, world)``: this engine owns columns
+        [rank*C/world, (rank+1)*C/world) of the spatial pooler (permanence, mask, duty
+        cycles); the temporal memory is replicated."""
         torch = _torch()
         self.device = require_cuda(device)
         if not (1 <= cell_dim <= 32):
@@ -70,6 +73,17 @@ class Engine:
         ctx.input_dim, ctx.input_words = I, (I + 31) // 32
         ctx.mask_stride = _round_up(ctx.input_words, 4)
         ctx.column_dim, ctx.cell_dim, ctx.active_columns = Ccol, c, k
+        if column_shard is None:
+            self.shard_rank, self.shard_world = 0, 1
+        else:
+            self.shard_rank, self.shard_world = int(column_shard[0]), int(column_shard[1])
+            if Ccol % self.shard_world:
+                raise ValueError("column_dim must be divisible by the number of column shards")
+            fused = "off"  # the all-gather sits between kernels
+        ctx.col_local = Ccol // self.shard_world
+        ctx.col_lo = self.shard_rank * ctx.col_local
+        self.C_local, self.col_lo = ctx.col_local, ctx.col_lo
+        self.k_local = min(k, ctx.col_local)
         ctx.seg_capacity, ctx.syn_capacity = max_segments, _round_up(int(max_synapses_per_segment), 32)
         ctx.match_capacity, ctx.learn_capacity = int(match_capacity), int(learn_capacity)
         ctx.tm_blocks, ctx.sm_count = int(tm_blocks), self.sm_count
@@ -119,9 +133,10 @@ class Engine:
     def _counts(self):
         x = self.ctx
         C_, I, c, k = x.column_dim, x.input_dim, x.cell_dim, x.active_columns
+        CL = x.col_local
         N, S, E, M = C_ * 32, x.seg_capacity, x.syn_capacity, x.match_capacity  # device cell id = col*32+cell
         return {
-            "sp_perm": C_ * I, "sp_mask": C_ * x.mask_stride, "duty": C_, "overlaps": C_, "boosted": C_,
+            "sp_perm": CL * I, "sp_mask": CL * x.mask_stride, "duty": CL, "overlaps": CL, "boosted": CL,
             "active_cols": 2 * k, "col_active": C_, "col_pred": C_, "col_act": C_, "col_win": C_,
             "cell_nseg": N, "cell_maxjit": N, "cell_npred": N, "cell_widx": N,
             "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": S * E, "syn_perm": S * E,

@@ -48,7 +48,8 @@ class BhCtx(C.Structure):
         ("column_dim", C.c_int32), ("cell_dim", C.c_int32), ("active_columns", C.c_int32),
         ("seg_capacity", C.c_int32), ("syn_capacity", C.c_int32), ("match_capacity", C.c_int32),
         ("learn_capacity", C.c_int32), ("tm_blocks", C.c_int32), ("sm_count", C.c_int32),
-        ("rand_capacity", C.c_int64), ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
+        ("rand_capacity", C.c_int64), ("col_lo", C.c_int32), ("col_local", C.c_int32),
+        ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
         ("sp_threshold", C.c_double), ("sp_delta_on", C.c_double), ("sp_delta_off", C.c_double),
         ("tm_learn_on", C.c_double), ("tm_learn_off", C.c_double),
         ("tm_punish_on", C.c_double), ("tm_punish_off", C.c_double),
@@ -104,6 +105,8 @@ _SIGNATURES = {
     "bh_sp_learn": (C.c_int, [_CTXP, _P, _P]),
     "bh_duty_update": (C.c_int, [_CTXP, _P]),
     "bh_sp_step": (C.c_int, [_CTXP, _P, C.c_int, _P]),
+    "bh_sp_shard_local": (C.c_int, [_CTXP, _P, _P, _P, _P]),
+    "bh_sp_shard_finish": (C.c_int, [_CTXP, _P, _P, _P, C.c_int, C.c_int, _P]),
     "bh_advance_step": (C.c_int, [_CTXP, _P]),
     "bh_tm_select": (C.c_int, [_CTXP, _P]),
     "bh_tm_learn": (C.c_int, [_CTXP, C.c_int, _P]),

@@ -1,0 +1,50 @@
+"""Column sharding of the spatial pooler across ranks.
+
+Each rank owns a contiguous range of columns (permanence rows, mask rows, duty
+cycles).  Per timestep there is ONE exchange: every rank contributes its best
+``min(k, C/world)`` candidates as (float64 key, int32 global column) pairs in
+ascending column order; after an all-gather in rank order the concatenation is in
+ascending column order too, so the canonical rule (larger key first, ties -> lower
+column) can be applied to it on every rank identically.  The temporal memory is
+replicated: every rank computes it from the same active-column list and the same
+MT19937 stream, so no second exchange is needed and results are bit-identical to the
+single-GPU run by construction.
+"""
+
+from __future__ import annotations
+
+
+def gather_candidates(keys, cols, group=None):
+    """All-gather (keys[k_loc] float64, cols[k_loc] int32) in rank order.  Works on
+    CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    out_keys = torch.empty(world * keys.numel(), dtype=keys.dtype, device=keys.device)
+    out_cols = torch.empty(world * cols.numel(), dtype=cols.dtype, device=cols.device)
+    if keys.is_cuda:
+        dist.all_gather_into_tensor(out_keys, keys, group=group)
+        dist.all_gather_into_tensor(out_cols, cols, group=group)
+    else:  # gloo has no all_gather_into_tensor on every build: use list form
+        ks = [torch.empty_like(keys) for _ in range(world)]
+        cs = [torch.empty_like(cols) for _ in range(world)]
+        dist.all_gather(ks, keys, group=group)
+        dist.all_gather(cs, cols, group=group)
+        out_keys, out_cols = torch.cat(ks), torch.cat(cs)
+    return out_keys, out_cols
+
+
+def gather_columns(local, group=None):
+    """All-gather a per-column array (this rank's slice) into the full [C] array."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if local.is_cuda:
+        out = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    return torch.cat(parts)

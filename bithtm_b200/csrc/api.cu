@@ -59,11 +59,12 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   Carver cv{reinterpret_cast<char*>(base), 0};
   const size_t C = x->column_dim, I = x->input_dim, c = x->cell_dim, k = x->active_columns;
   const size_t N = C * 32 /* device cell id = column * 32 + cell */, S = x->seg_capacity, E = x->syn_capacity, M = x->match_capacity;
-  cv.take(x->sp_perm, C * I);
-  cv.take(x->sp_mask, C * (size_t)x->mask_stride);
-  cv.take(x->duty, C);
-  cv.take(x->overlaps, C);
-  cv.take(x->boosted, C);
+  const size_t CL = x->col_local;  // columns owned by this rank (== C when not sharded)
+  cv.take(x->sp_perm, CL * I);
+  cv.take(x->sp_mask, CL * (size_t)x->mask_stride);
+  cv.take(x->duty, CL);
+  cv.take(x->overlaps, CL);
+  cv.take(x->boosted, CL);
   cv.take(x->active_cols, 2 * k);
   cv.take(x->col_active, C);
   cv.take(x->col_pred, C);
@@ -109,6 +110,8 @@ static int check_ctx(const bh_ctx* x) {
   if (x->input_words != (x->input_dim + 31) / 32 || x->mask_stride % 4 != 0 || x->mask_stride < x->input_words)
     return BH_E_BADARG;
   if (x->tm_blocks < 1 || x->tm_blocks > BH_BLK_STRIDE) return BH_E_BADARG;
+  if (x->col_local < 1 || x->col_lo < 0 || x->col_lo + x->col_local > x->column_dim) return BH_E_BADARG;
+  if (x->col_local != x->column_dim && x->fused_mode) return BH_E_UNSUPPORTED;  // sharded: per-stage kernels
   if (x->syn_capacity < 32 || x->syn_capacity % 32 != 0) return BH_E_BADARG;
   return 0;
 }
@@ -151,7 +154,7 @@ static int overlap_group_host(const bh_ctx* x) {
 }
 
 static int sp_grid(const bh_ctx* x, int rows_per_block) {
-  int want = cdiv(x->column_dim, rows_per_block);
+  int want = cdiv(x->col_local, rows_per_block);
   int cap = (x->sm_count > 0 ? x->sm_count : 148) * 8;
   return want < cap ? want : cap;
 }
@@ -159,7 +162,7 @@ static int sp_grid(const bh_ctx* x, int rows_per_block) {
 extern "C" int bh_sp_build_mask(const bh_ctx* x, void* stream) {
   int rc = check_ctx(x);
   if (rc) return rc;
-  long long words = (long long)x->column_dim * x->mask_stride;
+  long long words = (long long)x->col_local * x->mask_stride;
   int grid = cdiv(words, SP_THREADS / 32);
   int cap = (x->sm_count > 0 ? x->sm_count : 148) * 16;
   k_sp_build_mask<<<grid < cap ? grid : cap, SP_THREADS, 0, S_(stream)>>>(*x);
@@ -188,7 +191,7 @@ extern "C" int bh_sp_overlap(const bh_ctx* x, const uint32_t* in, void* stream) 
 }
 
 extern "C" int bh_boost(const bh_ctx* x, void* stream) {
-  k_boost<<<cdiv(x->column_dim, 256), 256, 0, S_(stream)>>>(*x);
+  k_boost<<<cdiv(x->col_local, 256), 256, 0, S_(stream)>>>(*x);
   LAUNCH_CHECK();
   return 0;
 }
@@ -214,7 +217,7 @@ extern "C" int bh_sp_learn(const bh_ctx* x, const uint32_t* in, void* stream) {
 }
 
 extern "C" int bh_duty_update(const bh_ctx* x, void* stream) {
-  k_duty_update<<<cdiv(x->column_dim, 256), 256, 0, S_(stream)>>>(*x);
+  k_duty_update<<<cdiv(x->col_local, 256), 256, 0, S_(stream)>>>(*x);
   LAUNCHED("duty_update");
   return 0;
 }
@@ -223,6 +226,34 @@ static int sp_step(const bh_ctx* x, const uint32_t* in, int learning, cudaStream
   int rc;
   if ((rc = launch_overlap<true>(x, in, st))) return rc;
   if ((rc = bh_inhibit(x, st))) return rc;
+  if (learning && (rc = bh_sp_learn(x, in, st))) return rc;
+  return bh_duty_update(x, st);
+}
+
+// ---- column shard: exchange 1 (top-k candidates) ---------------------------------------
+extern "C" int bh_sp_shard_local(const bh_ctx* x, const uint32_t* in, double* cand_keys, int32_t* cand_cols,
+                                 void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (!cand_keys || !cand_cols) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  if ((rc = launch_overlap<true>(x, in, st))) return rc;
+  // scratch for the selected local positions: the (not yet used) current active-column buffer
+  int* scratch = x->row_unacc ? reinterpret_cast<int*>(x->row_unacc) : nullptr;
+  if (!scratch) return BH_E_BADARG;
+  k_topk_shard_local<<<1, TOPK_THREADS, 0, st>>>(*x, scratch, cand_keys, cand_cols);
+  LAUNCHED("topk_shard_local");
+  return 0;
+}
+
+extern "C" int bh_sp_shard_finish(const bh_ctx* x, const uint32_t* in, const double* cand_keys,
+                                  const int32_t* cand_cols, int n, int learning, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (!cand_keys || !cand_cols || n < x->active_columns) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  k_topk_shard_merge<<<1, TOPK_THREADS, 0, st>>>(*x, cand_keys, cand_cols, n);
+  LAUNCHED("topk_shard_merge");
   if (learning && (rc = bh_sp_learn(x, in, st))) return rc;
   return bh_duty_update(x, st);
 }

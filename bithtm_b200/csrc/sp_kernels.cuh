@@ -15,7 +15,7 @@
 __global__ void __launch_bounds__(SP_THREADS) k_sp_build_mask(const __grid_constant__ bh_ctx c) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = SP_THREADS / 32;
-  const long long n_words = (long long)c.column_dim * c.mask_stride;
+  const long long n_words = (long long)c.col_local * c.mask_stride;
   for (long long w = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < n_words;
        w += (long long)gridDim.x * warps_per_block) {
     int row = (int)(w / c.mask_stride);
@@ -67,21 +67,32 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
   const int vec_per_row = c.mask_stride / 4;
   const uint4* mask4 = reinterpret_cast<const uint4*>(c.sp_mask);
   const uint4* s_in4 = reinterpret_cast<const uint4*>(s_in);
-  #pragma unroll 1
-  for (int base = warp_global * rows_per_warp; base < c.column_dim; base += n_warps * rows_per_warp) {
+  const int n_rows = c.col_local;  // this rank's columns (all of them when not sharded)
+#pragma unroll 1
+  for (int base = warp_global * rows_per_warp; base < n_rows; base += n_warps * rows_per_warp) {
     int row = base + lane / group;
     int acc = 0;
-    if (row < c.column_dim) {
+    if (row < n_rows) {
       const uint4* mrow = mask4 + (long long)row * vec_per_row;
-      #pragma unroll 1
-      for (int v = sub; v < vec_per_row; v += group) {
-        uint4 m = mrow[v];
-        uint4 x = s_in4[v];
+      int v = sub;
+#pragma unroll 1
+      for (; v + 3 * group < vec_per_row; v += 4 * group) {  // 4 independent 16-byte loads in flight
+        const uint4 m0 = mrow[v], m1 = mrow[v + group], m2 = mrow[v + 2 * group], m3 = mrow[v + 3 * group];
+        const uint4 x0 = s_in4[v], x1 = s_in4[v + group], x2 = s_in4[v + 2 * group], x3 = s_in4[v + 3 * group];
+        acc += __popc(m0.x & x0.x) + __popc(m0.y & x0.y) + __popc(m0.z & x0.z) + __popc(m0.w & x0.w);
+        acc += __popc(m1.x & x1.x) + __popc(m1.y & x1.y) + __popc(m1.z & x1.z) + __popc(m1.w & x1.w);
+        acc += __popc(m2.x & x2.x) + __popc(m2.y & x2.y) + __popc(m2.z & x2.z) + __popc(m2.w & x2.w);
+        acc += __popc(m3.x & x3.x) + __popc(m3.y & x3.y) + __popc(m3.z & x3.z) + __popc(m3.w & x3.w);
+      }
+#pragma unroll 1
+      for (; v < vec_per_row; v += group) {
+        const uint4 m = mrow[v];
+        const uint4 x = s_in4[v];
         acc += __popc(m.x & x.x) + __popc(m.y & x.y) + __popc(m.z & x.z) + __popc(m.w & x.w);
       }
     }
     for (int o = group >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(BH_FULL, acc, o);
-    if (sub == 0 && row < c.column_dim) {
+    if (sub == 0 && row < n_rows) {
       c.overlaps[row] = acc;
       if (BOOST) {
         float f = bh_np_expf(__fmul_rn(c.boost_coef, c.duty[row]));
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_overlap(const __grid_constant
 
 __global__ void k_boost(const __grid_constant__ bh_ctx c) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= c.column_dim) return;
+  if (j >= c.col_local) return;
   float f = bh_np_expf(__fmul_rn(c.boost_coef, c.duty[j]));
   c.boosted[j] = __dmul_rn((double)f, (double)c.overlaps[j]);
 }
@@ -141,7 +152,10 @@ __device__ __noinline__ unsigned long long block_reduce_u64(unsigned long long v
   return r;
 }
 
-__device__ void ph_topk(const bh_ctx& c) {
+// keys[0..n): select the k largest (ties -> lower position); positions ascending are
+// written as out[i] = map ? map[pos] : pos, and flags[that value] = 1 when flags != null.
+__device__ void topk_core(const unsigned long long* keys, const int C, const int k, int* out, const int* map,
+                          uint8_t* flags) {
   __shared__ int hist[256];
   __shared__ int s_scan[32];
   __shared__ unsigned long long s_u64[32];
@@ -150,15 +164,6 @@ __device__ void ph_topk(const bh_ctx& c) {
   __shared__ int s_bin, s_rem, s_ncand, s_kth_idx;
   __shared__ unsigned long long s_kth_key;
   const int t = threadIdx.x, lane = t & 31, NT = blockDim.x;
-  const int C = c.column_dim, k = c.active_columns;
-  const int cur = c.sc[BH_SC_STEP] & 1;
-  int* out = c.active_cols + cur * k;
-  const int* prev = c.active_cols + (cur ^ 1) * k;
-  const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(c.boosted);
-
-  // retire the previous step's column flags
-  #pragma unroll 1
-  for (int i = t; i < k; i += NT) c.col_active[prev[i]] = 0;
 
   // 1. shared leading bits
   unsigned long long mn = ~0ull, mx = 0ull;
@@ -293,14 +298,56 @@ __device__ void ph_topk(const bh_ctx& c) {
     int sel_total;
     const int pos = base_sel + block_excl_scan(take ? 1 : 0, s_scan, sel_total);
     if (take && pos < k) {
-      out[pos] = j;
-      c.col_active[j] = 1;
+      const int col = map ? map[j] : j;
+      out[pos] = col;
+      if (flags) flags[col] = 1;
     }
     base_sel += sel_total;
   }
 }
 
+// retire the previous step's column flags (single CTA, before the new ones are set)
+__device__ __forceinline__ void retire_prev_flags(const bh_ctx& c) {
+  const int k = c.active_columns;
+  const int* prev = c.active_cols + ((c.sc[BH_SC_STEP] & 1) ^ 1) * k;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < k; i += blockDim.x) c.col_active[prev[i]] = 0;
+  __syncthreads();
+}
+
+// GlobalInhibition.process on this rank's keys = all columns (not sharded)
+__device__ void ph_topk(const bh_ctx& c) {
+  retire_prev_flags(c);
+  const int k = c.active_columns;
+  topk_core(reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, k,
+            c.active_cols + (c.sc[BH_SC_STEP] & 1) * k, nullptr, c.col_active);
+}
+
 __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const __grid_constant__ bh_ctx c) { ph_topk(c); }
+
+// Column shard, exchange 1: this shard's best min(k, col_local) candidates as (key,
+// global column) pairs in ascending column order.  `scratch` holds k_loc ints.
+__global__ void __launch_bounds__(TOPK_THREADS)
+    k_topk_shard_local(const __grid_constant__ bh_ctx c, int* scratch, double* cand_keys, int32_t* cand_cols) {
+  const int k_loc = c.active_columns < c.col_local ? c.active_columns : c.col_local;
+  topk_core(reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr);
+  __syncthreads();
+  for (int i = threadIdx.x; i < k_loc; i += blockDim.x) {
+    const int pos = scratch[i];
+    cand_keys[i] = c.boosted[pos];
+    cand_cols[i] = c.col_lo + pos;
+  }
+}
+
+// Global top-k among the gathered candidates (rank order = ascending column, so the
+// position tie-break is the column tie-break); identical on every rank.
+__global__ void __launch_bounds__(TOPK_THREADS)
+    k_topk_shard_merge(const __grid_constant__ bh_ctx c, const double* cand_keys, const int32_t* cand_cols, int n) {
+  retire_prev_flags(c);
+  const int k = c.active_columns;
+  topk_core(reinterpret_cast<const unsigned long long*>(cand_keys), n, k, c.active_cols + (c.sc[BH_SC_STEP] & 1) * k,
+            cand_cols, c.col_active);
+}
 
 // host-inhibition mode: adopt an explicit ordered list
 __global__ void k_set_active(const __grid_constant__ bh_ctx c, const int32_t* __restrict__ cols) {
@@ -331,26 +378,38 @@ __global__ void k_set_active(const __grid_constant__ bh_ctx c, const int32_t* __
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void ph_sp_learn(const bh_ctx& c, const uint32_t* input, int b, int nb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  const int k = c.active_columns;
+  const int k = c.active_columns, I = c.input_dim, words = c.input_words;
   const int cur = c.sc[BH_SC_STEP] & 1;
   const int* act = c.active_cols + cur * k;
-  #pragma unroll 1
+  const double d_on = c.sp_delta_on, d_off = c.sp_delta_off, thr = c.sp_threshold;
+#pragma unroll 1
   for (int r = b; r < k; r += nb) {
-    const int col = act[r];
-    double* prow = c.sp_perm + (long long)col * c.input_dim;
+    const int col = act[r] - c.col_lo;  // local row; columns of other shards are skipped
+    if (col < 0 || col >= c.col_local) continue;
+    double* prow = c.sp_perm + (long long)col * I;
     uint32_t* mrow = c.sp_mask + (long long)col * c.mask_stride;
-    #pragma unroll 1
-    for (int w = warp; w < c.input_words; w += warps) {
-      int i = w * 32 + lane;
-      uint32_t xin = input[w];
-      bool on = false;
-      if (i < c.input_dim) {
-        double p = __dadd_rn(prow[i], ((xin >> lane) & 1u) ? c.sp_delta_on : c.sp_delta_off);
-        prow[i] = p;
-        on = p >= c.sp_threshold;
+#pragma unroll 1
+    for (int w0 = warp * 4; w0 < words; w0 += warps * 4) {  // 4 x 256 B of permanence in flight per warp
+      double p[4];
+      uint32_t xin[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int w = w0 + j, i = w * 32 + lane;
+        xin[j] = w < words ? input[w] : 0u;
+        p[j] = (w < words && i < I) ? prow[i] : -1.0;
       }
-      uint32_t bits = __ballot_sync(BH_FULL, on);
-      if (lane == 0) mrow[w] = bits;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int w = w0 + j, i = w * 32 + lane;
+        bool on = false;
+        if (w < words && i < I) {
+          const double q = __dadd_rn(p[j], ((xin[j] >> lane) & 1u) ? d_on : d_off);
+          prow[i] = q;
+          on = q >= thr;
+        }
+        const uint32_t bits = __ballot_sync(BH_FULL, on);
+        if (lane == 0 && w < words) mrow[w] = bits;
+      }
     }
   }
 }
@@ -363,9 +422,9 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_learn(const __grid_constant__
 // regularizations.py:19-21; runs even when learning is off (networks.py:33).
 __device__ __forceinline__ void ph_duty(const bh_ctx& c, int b, int nb) {
   #pragma unroll 1
-  for (int j = b * blockDim.x + threadIdx.x; j < c.column_dim; j += nb * blockDim.x) {
+  for (int j = b * blockDim.x + threadIdx.x; j < c.col_local; j += nb * blockDim.x) {
     float d = __fmul_rn(c.duty[j], c.duty_momentum);
-    if (c.col_active[j]) d = __fadd_rn(d, c.duty_increment);
+    if (c.col_active[c.col_lo + j]) d = __fadd_rn(d, c.duty_increment);
     c.duty[j] = d;
   }
 }

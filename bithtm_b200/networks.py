@@ -83,6 +83,7 @@ class SpatialPooler:
             # ping-pong buffer this step's active columns were written to
             self._parity = engine.epoch & 1
             self._bh_engine_epoch = (engine, engine.epoch)
+            self._group = None
 
         @property
         def active_column(self):
@@ -92,13 +93,21 @@ class SpatialPooler:
 
             return self._get("active_column", fetch)
 
+        def _columns(self, name):
+            eng = self._engine
+            if eng.shard_world > 1:  # COLLECTIVE: every rank must read this field
+                from ._shard import gather_columns
+
+                return gather_columns(eng.buf[name], self._group).cpu().numpy()
+            return eng.buf[name].cpu().numpy()
+
         @property
         def overlaps(self):
-            return self._get("overlaps", lambda: self._engine.buf["overlaps"].cpu().numpy().astype(np.int64))
+            return self._get("overlaps", lambda: self._columns("overlaps").astype(np.int64))
 
         @property
         def boosted_overlaps(self):
-            return self._get("boosted_overlaps", lambda: self._engine.buf["boosted"].cpu().numpy())
+            return self._get("boosted_overlaps", lambda: self._columns("boosted"))
 
     def __init__(self, input_dim, column_dim, active_columns, proximal_projection=None, boosting=None,
                  inhibition=None, **engine_kwargs):
@@ -114,6 +123,7 @@ class SpatialPooler:
         self._engine_kwargs = engine_kwargs
         self._engine = None
         self._standalone_tm = False
+        self._group = None  # torch.distributed group of the column shards
 
     @property
     def _native_inhibition(self):
@@ -134,11 +144,36 @@ class SpatialPooler:
             self._standalone_tm = True
         return self._engine
 
+    def _process_sharded(self, eng, words, learning):
+        """Column-sharded SP step: local overlap/boost + local candidates, one all-gather,
+        identical global selection on every rank, local learning (see _shard.py)."""
+        import torch
+
+        from ._shard import gather_candidates
+
+        if not self._native_inhibition:
+            raise NotImplementedError("column sharding needs the built-in GlobalInhibition (canonical rule)")
+        k_loc = eng.k_local
+        keys = torch.empty(k_loc, dtype=torch.float64, device=eng.device)
+        cols = torch.empty(k_loc, dtype=torch.int32, device=eng.device)
+        nat.check(nat.lib.bh_sp_shard_local(eng.ref, words.data_ptr(), keys.data_ptr(), cols.data_ptr(), eng.stream),
+                  "bh_sp_shard_local")
+        all_keys, all_cols = gather_candidates(keys, cols, self._group)
+        nat.check(nat.lib.bh_sp_shard_finish(eng.ref, words.data_ptr(), all_keys.data_ptr(), all_cols.data_ptr(),
+                                             int(all_keys.numel()), int(bool(learning)), eng.stream),
+                  "bh_sp_shard_finish")
+        return self.State(eng)
+
     def process(self, input, learning=True):
         """networks.py:26-35.  Leaves the active columns on the device for the TM."""
         eng = self._ensure_engine()
         self.boosting._bind(eng)
         words = eng.pack_input(input)
+        if eng.shard_world > 1:
+            state = self._process_sharded(eng, words, learning)
+            if self._standalone_tm:
+                self._complete_step(state)
+            return state
         if self._native_inhibition:
             nat.check(nat.lib.bh_sp_step(eng.ref, words.data_ptr(), int(bool(learning)), eng.stream), "bh_sp_step")
             state = self.State(eng)
@@ -308,7 +343,13 @@ class HierarchicalTemporalMemory:
     """networks.py:131-149."""
 
     def __init__(self, input_dim, column_dim, cell_dim, active_columns=None, spatial_pooler=None,
-                 temporal_memory=None, rng_sync="step", device=None, **engine_kwargs):
+                 temporal_memory=None, rng_sync="step", device=None, column_shard=None, process_group=None,
+                 **engine_kwargs):
+        """Extensions (keyword-only in spirit): ``column_shard=True`` shards the spatial
+        pooler's columns over the ranks of ``process_group`` (default: the world group of an
+        initialised torch.distributed; every rank must construct the network after the same
+        ``np.random.seed`` and feed the same inputs).  Other keyword arguments size the
+        device buffers (see ``Engine``)."""
         if active_columns is None:
             active_columns = round(column_dim * 0.02)  # :136-137
         self.input_dim = input_dim
@@ -325,7 +366,17 @@ class HierarchicalTemporalMemory:
             tm._rng = _RngLink(rng_sync)
         if sp._engine is not None or tm._engine is not None:
             raise NotImplementedError("spatial_pooler / temporal_memory were already used stand-alone")
-        self._engine = Engine(input_dim, column_dim, cell_dim, sp.active_columns, device=device, **engine_kwargs)
+        shard = None
+        if column_shard:
+            import torch.distributed as dist
+
+            if column_shard is True:
+                shard = (dist.get_rank(process_group), dist.get_world_size(process_group))
+            else:
+                shard = tuple(column_shard)
+            sp._group = process_group
+        self._engine = Engine(input_dim, column_dim, cell_dim, sp.active_columns, device=device,
+                              column_shard=shard, **engine_kwargs)
         sp._attach(self._engine)
         tm._attach(self._engine)
 
@@ -341,8 +392,9 @@ class HierarchicalTemporalMemory:
         the packed input, the whole step on the device, one D2H of the step summary)."""
         sp, tm, eng = self.spatial_pooler, self.temporal_memory, self._engine
         is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
-        if not sp._native_inhibition or not is_host:
+        if not sp._native_inhibition or not is_host or eng.shard_world > 1:
             sp_state = sp.process(input, learning=learning)
+            sp_state._group = sp._group
             tm_state = tm.process(sp_state, learning=learning)
             sp_state._epoch = eng.epoch  # its buffers stay valid until the next step
             return sp_state, tm_state

@@ -22,7 +22,12 @@ class DenseProjection:
     connected mask live in HBM; ``permanence`` downloads a copy."""
 
     def __init__(self, input_dim, output_dim, permanence_mean=0.0, permanence_std=0.1,
-                 permanence_threshold=0.0, permanence_increment=0.03, permanence_decrement=0.015):
+                 permanence_threshold=0.0, permanence_increment=0.03, permanence_decrement=0.015,
+                 *, permanence=None):
+        """``permanence`` (extension, keyword-only): a ready [output_dim, input_dim] float64
+        matrix (NumPy array or CUDA tensor) to use instead of drawing one -- e.g. a matrix
+        drawn on the device for sizes where the host draw (8 GiB at 65536 x 16384) is the
+        bottleneck.  When given, the global np.random stream is NOT consumed."""
         self.input_dim = input_dim
         self.output_dim = output_dim
         self.permanence_threshold = permanence_threshold
@@ -30,7 +35,13 @@ class DenseProjection:
         self.permanence_decrement = permanence_decrement
         # projections.py:16 -- the identical call, so the global np.random stream is
         # consumed exactly as the reference consumes it (float64, first consumer).
-        self._host_permanence = np.random.randn(output_dim, input_dim) * permanence_std + permanence_mean
+        if permanence is None:
+            self._host_permanence = np.random.randn(output_dim, input_dim) * permanence_std + permanence_mean
+        else:
+            if permanence.shape[1] != input_dim or permanence.shape[0] > output_dim:
+                raise ValueError("permanence must have shape (output_dim, input_dim) "
+                                 "(or this rank's rows of it when column-sharded)")
+            self._host_permanence = permanence
         self._engine = None
 
     def _constants(self):
@@ -53,7 +64,16 @@ class DenseProjection:
         self._engine = engine
         for k, v in self._constants().items():
             setattr(engine.ctx, k, v)
-        engine.buf["sp_perm"].copy_(torch.from_numpy(self._host_permanence.reshape(-1)).to(engine.device))
+        src = self._host_permanence
+        if engine.shard_world > 1 and src.shape[0] == self.output_dim:
+            src = src[engine.col_lo:engine.col_lo + engine.C_local]  # this rank's rows
+        if tuple(src.shape) != (engine.C_local, self.input_dim):
+            raise ValueError("permanence rows do not match this rank's column shard")
+        if isinstance(src, torch.Tensor):
+            engine.buf["sp_perm"].copy_(src.reshape(-1).to(device=engine.device, dtype=torch.float64))
+        else:
+            engine.buf["sp_perm"].copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64).reshape(-1))
+                                        .to(engine.device))
         self._host_permanence = None
         nat.check(nat.lib.bh_sp_build_mask(engine.ref, engine.stream), "bh_sp_build_mask")
 
@@ -67,7 +87,8 @@ class DenseProjection:
     def permanence(self):
         if self._engine is None:
             return self._host_permanence
-        return self._engine.buf["sp_perm"].cpu().numpy().reshape(self.output_dim, self.input_dim)
+        eng = self._engine  # column-sharded: this rank's rows
+        return eng.buf["sp_perm"].cpu().numpy().reshape(eng.C_local, self.input_dim)
 
     def process(self, input_activation):
         """projections.py:18-21 -> int64 overlaps."""

@@ -87,6 +87,9 @@ typedef struct bh_ctx {
   int32_t tm_blocks;       /* NB: CTAs of the ranged TM kernels (<= 1024)          */
   int32_t sm_count;        /* SMs of the device (grid sizing)                      */
   int64_t rand_capacity;   /* doubles in rand_buf                                  */
+  int32_t col_lo;          /* column shard: first global column owned by this rank  */
+  int32_t col_local;       /* columns owned (C when not sharded); the SP buffers    */
+                           /* sp_perm/sp_mask/duty/overlaps/boosted are local-sized */
   int32_t ring_len;        /* rows in input_ring (0 = none)                        */
   int32_t fused_mode;      /* bh_step*: 0 = one kernel per stage, 1 = one kernel on a  */
                            /* thread-block cluster, 2 = one cooperative-grid kernel   */
@@ -202,6 +205,20 @@ int bh_sp_learn(const bh_ctx* ctx, const uint32_t* input_words_dev, void* stream
 int bh_duty_update(const bh_ctx* ctx, void* stream);
 /* SpatialPooler.process (networks.py:26-35) = the five calls above */
 int bh_sp_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, void* stream);
+
+/* ---- column-sharded spatial pooler (exchange 1) -----------------------
+ * Each rank owns columns [col_lo, col_lo + col_local): their permanence rows, mask rows
+ * and duty cycles.  bh_sp_shard_local computes the local overlaps / boosted keys and
+ * this shard's best min(k, col_local) candidates (canonical order) as (key, global
+ * column) pairs, ascending column.  The caller all-gathers the pairs in rank order
+ * (NCCL) and passes the n = world * min(k, col_local) gathered pairs to
+ * bh_sp_shard_finish, which selects the global top-k on every rank identically, then
+ * learns / updates duty cycles for the local columns.  The temporal memory that
+ * follows is replicated. */
+int bh_sp_shard_local(const bh_ctx* ctx, const uint32_t* input_words_dev, double* cand_keys_out,
+                      int32_t* cand_cols_out, void* stream);
+int bh_sp_shard_finish(const bh_ctx* ctx, const uint32_t* input_words_dev, const double* cand_keys,
+                       const int32_t* cand_cols, int n, int learning, void* stream);
 
 /* Complete a timestep when no temporal memory follows (stand-alone SpatialPooler):
  * sc[BH_SC_STEP] += 1 so the ping-pong buffers rotate. */

@@ -92,6 +92,7 @@ def test_layout_without_device():
     ctx = nat.BhCtx()
     ctx.input_dim, ctx.input_words, ctx.mask_stride = 1024, 32, 32
     ctx.column_dim, ctx.cell_dim, ctx.active_columns = 2048, 32, 41
+    ctx.col_lo, ctx.col_local = 0, 2048
     ctx.seg_capacity, ctx.syn_capacity, ctx.match_capacity, ctx.learn_capacity = 1 << 16, 128, 1 << 16, 1 << 17
     ctx.tm_blocks, ctx.rand_capacity = 148, 1 << 20
     n = nat.lib.bh_layout(ctypes.byref(ctx), None)

@@ -1,0 +1,199 @@
+"""Multi-rank path: the top-k candidate exchange on CPU with gloo
+(world_size 2, runs anywhere) and the full column-sharded SP + replicated TM on two
+GPUs with NCCL (skipped without 2 GPUs)."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _init(rank, world, port, backend):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+
+
+# ----------------------------------------------------------------------------- CPU / gloo
+def _gloo_worker(rank, world, port, result):
+    import torch
+    import torch.distributed as dist
+
+    _init(rank, world, port, "gloo")
+    from bithtm_b200._shard import gather_candidates, gather_columns
+    from oracle.htm_oracle import canonical_topk
+
+    g = np.random.default_rng(5)
+    ok = True
+    for trial in range(40):
+        C, k = 64 * world, int(g.integers(1, 40))
+        # few distinct values -> many ties, also across the shard boundary
+        keys = g.integers(0, 6 if trial % 2 else 1000, size=C).astype(np.float64)
+        lo, hi = rank * C // world, (rank + 1) * C // world
+        k_loc = min(k, hi - lo)
+        local = canonical_topk(keys[lo:hi], k_loc)  # ascending local positions
+        ck, cc = gather_candidates(torch.from_numpy(keys[lo:hi][local]), torch.from_numpy((lo + local).astype(np.int32)))
+        ck, cc = ck.numpy(), cc.numpy()
+        assert np.all(np.diff(cc) > 0), "gathered candidates must be in ascending column order"
+        sel = cc[canonical_topk(ck, k)]  # position tie-break == column tie-break
+        ok &= np.array_equal(sel, canonical_topk(keys, k))
+        full = gather_columns(torch.from_numpy(keys[lo:hi])).numpy()
+        ok &= np.array_equal(full, keys)
+    flag = torch.tensor([int(ok)])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        result.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+def test_candidate_exchange_gloo_world2():
+    """Per-shard top-min(k, C/world) candidates, gathered in rank order and selected with
+    the position tie-break, equal the global canonical top-k (ties included)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    result = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, result)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert result.get(timeout=10) == 1
+
+
+# ----------------------------------------------------------------------------- 2 GPUs / NCCL
+def _nccl_worker(rank, world, port, result, name, steps):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    _init(rank, world, port, "nccl")
+    import bithtm_b200 as bithtm
+    from helpers import golden_inputs, gpu_record, load_golden, step_digest
+    from oracle.digest import canonical_from_rows, state_digest
+
+    info = load_golden(name)
+    g = info["g"]
+    xs = golden_inputs(info, steps)
+    np.random.seed(info["seed"])
+    htm = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], column_shard=True)
+    state_at = {int(s): int(d) for s, d in zip(g["state_steps"], g["state_digests"])}
+    bad = None
+    for t in range(steps):
+        sp_state, tm_state = htm.process(xs[t])
+        d = step_digest(**gpu_record(htm, sp_state, tm_state))  # overlaps/boosted reads are collectives
+        if d != int(g["digests"][t]) and bad is None:
+            bad = f"rank {rank}: step {t} differs from the reference trace"
+        if t in state_at:
+            sp, tm = htm.spatial_pooler, htm.temporal_memory
+            perm = [None] * world
+            duty = [None] * world
+            dist.all_gather_object(perm, sp.proximal_projection.permanence)
+            dist.all_gather_object(duty, sp.boosting.duty_cycle)
+            owner, count, cells, pm = tm.distal_projection.export_segments()
+            sd = state_digest(np.concatenate(perm), np.concatenate(duty), tm.distal_projection.bundle_segments,
+                              canonical_from_rows(owner, cells, pm))
+            if sd != state_at[t] and bad is None:
+                bad = f"rank {rank}: learned state differs at step {t}"
+    flag = torch.tensor([0 if bad else 1], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if bad:
+        print(bad, flush=True)
+    if rank == 0:
+        result.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,steps", [("mid", 500), ("tiny", 300)])
+def test_column_sharded_two_gpus_match_reference_trace(name, steps):
+    """Column-sharded SP (NCCL all-gather of candidates) + replicated TM on 2 GPUs:
+    every rank reproduces the single-network reference trace bit for bit."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    result = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, result, name, steps)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    assert result.get(timeout=10) == 1
+
+
+@pytest.mark.gpu
+def test_column_shard_single_process_emulation():
+    """The shard entry points on ONE GPU: two engines own one half of the columns
+    each; their candidates are concatenated by hand (what the all-gather does)."""
+    import torch
+
+    import bithtm_b200 as bithtm
+    from bithtm_b200 import _native as nat
+    from helpers import golden_inputs, load_golden
+    from oracle.htm_oracle import HTMOracle, OracleConfig
+
+    info = load_golden("mid")
+    I, C, c, k, seed = info["I"], info["C"], info["c"], info["k"], info["seed"]
+    xs = golden_inputs(info, 120)
+    shards = []
+    for r in range(2):
+        np.random.seed(seed)
+        shards.append(bithtm.HierarchicalTemporalMemory(I, C, c, k, column_shard=(r, 2), rng_sync="lazy"))
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    for t in range(120):
+        rec = orc.step(xs[t])
+        cand = []
+        for h in shards:
+            eng = h.engine
+            h.spatial_pooler.boosting._bind(eng)
+            words = eng.pack_input(xs[t])
+            keys = torch.empty(eng.k_local, dtype=torch.float64, device="cuda")
+            cols = torch.empty(eng.k_local, dtype=torch.int32, device="cuda")
+            nat.check(nat.lib.bh_sp_shard_local(eng.ref, words.data_ptr(), keys.data_ptr(), cols.data_ptr(), eng.stream))
+            cand.append((words, keys, cols))
+        all_keys = torch.cat([x[1] for x in cand])
+        all_cols = torch.cat([x[2] for x in cand])
+        for h, (words, _, _) in zip(shards, cand):
+            eng = h.engine
+            nat.check(nat.lib.bh_sp_shard_finish(eng.ref, words.data_ptr(), all_keys.data_ptr(), all_cols.data_ptr(),
+                                                 int(all_keys.numel()), 1, eng.stream))
+            tm = h.temporal_memory
+            tm._rng.before(eng)
+            nat.check(nat.lib.bh_tm_step(eng.ref, 1, eng.stream))
+            eng.epoch += 1
+            summary = eng.summary()
+            st = tm._finish(summary)
+            assert np.array_equal(st._active_column, rec.active_column), f"step {t}"
+            wc = st.winner_cell[0] * c + st.winner_cell[1]
+            assert np.array_equal(wc, rec.winner_cell), f"step {t}"
+            assert st.n_segments == rec.n_segments
+        ov = np.concatenate([h.engine.buf["overlaps"].cpu().numpy() for h in shards])
+        assert np.array_equal(ov, rec.overlaps)
+    perm = np.concatenate([h.spatial_pooler.proximal_projection.permanence for h in shards])
+    assert np.array_equal(perm.view(np.uint64), orc.permanence.view(np.uint64))
