@@ -50,6 +50,9 @@ class Engine:
         cycles); the temporal memory is replicated."""
         torch = _torch()
         self.device = require_cuda(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (
+            lambda i: torch.cuda.current_stream(i).cuda_stream)
         if not (1 <= cell_dim <= 32):
             raise NotImplementedError("bithtm_b200 supports 1..32 cells per column (one bit-word per column)")
         I, Ccol, c, k = int(input_dim), int(column_dim), int(cell_dim), int(active_columns)
@@ -128,6 +131,7 @@ class Engine:
         nat.check(nat.lib.bh_init(C.byref(ctx), self.stream), "bh_init")
         self.epoch = 0  # bumped by every completed step; lazily fetched State fields check it
         self._graphs = {}
+        self.host_graph = True  # bh_step_host as one CUDA graph launch (constants are frozen at capture)
 
     # ------------------------------------------------------------------ plumbing
     def _counts(self):
@@ -149,7 +153,8 @@ class Engine:
 
     @property
     def stream(self):
-        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+        """torch's current stream on this device, as a raw cudaStream_t."""
+        return C.c_void_p(self._raw_stream(self._dev_index))
 
     @property
     def ref(self):
@@ -233,8 +238,26 @@ class Engine:
         xb = np.ascontiguousarray(x_bool, dtype=np.uint8)
         if xb.size != self.I:
             raise ValueError(f"input has {xb.size} bits, expected {self.I}")
-        nat.check(nat.lib.bh_step_host(self.ref, xb.ctypes.data, int(bool(learning)),
-                                       self._summary_out.ctypes.data, self.stream), "bh_step_host")
+        learning = bool(learning)
+        key = ("host", learning, bytes(self.ctx))  # kernel arguments are frozen in the graph
+        handle = self._graphs.get(key)
+        if handle is None and self.host_graph:
+            # one CUDA graph = H2D copy node, the step, D2H copy node (captured on a side stream)
+            torch = _torch()
+            handle = C.c_void_p()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                nat.check(nat.lib.bh_host_graph_create(self.ref, int(learning), self.stream, C.byref(handle)),
+                          "bh_host_graph_create")
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graphs[key] = handle
+        if handle is not None:
+            nat.check(nat.lib.bh_step_host_graph(self.ref, handle, xb.ctypes.data, self._summary_out.ctypes.data,
+                                                 self.stream), "bh_step_host_graph")
+        else:
+            nat.check(nat.lib.bh_step_host(self.ref, xb.ctypes.data, int(learning),
+                                           self._summary_out.ctypes.data, self.stream), "bh_step_host")
         self.epoch += 1
         return self._summary_out
 

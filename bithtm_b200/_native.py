@@ -115,6 +115,8 @@ _SIGNATURES = {
     "bh_step": (C.c_int, [_CTXP, _P, C.c_int, _P]),
     "bh_step_ring": (C.c_int, [_CTXP, C.c_int, _P]),
     "bh_step_host": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
+    "bh_host_graph_create": (C.c_int, [_CTXP, C.c_int, _P, C.POINTER(_P)]),
+    "bh_step_host_graph": (C.c_int, [_CTXP, _P, _P, _P, _P]),
     "bh_summary": (C.c_int, [_CTXP, _P, _P]),
     "bh_graph_create": (C.c_int, [_CTXP, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     "bh_graph_launch": (C.c_int, [_P, _P]),

@@ -428,13 +428,8 @@ extern "C" int bh_step_ring(const bh_ctx* x, int learning, void* stream) {
   return bh_step(x, x->input_dev, learning, stream);
 }
 
-extern "C" int bh_step_host(const bh_ctx* x, const uint8_t* input_bool_host, int learning, int32_t* summary_host,
-                            void* stream) {
-  int rc = check_ctx(x);
-  if (rc) return rc;
-  if (!input_bool_host || !x->input_pinned || !x->summary_pinned) return BH_E_BADARG;
-  cudaStream_t st = S_(stream);
-  // pack on the host: bit i of word i/32 (little-endian bit order)
+// pack bool bytes on the host: bit i of word i/32 (little-endian bit order)
+static void pack_host(const bh_ctx* x, const uint8_t* input_bool_host) {
   for (int w = 0; w < x->input_words; ++w) {
     uint32_t bits = 0;
     int lim = x->input_dim - w * 32;
@@ -443,18 +438,71 @@ extern "C" int bh_step_host(const bh_ctx* x, const uint8_t* input_bool_host, int
     for (int b = 0; b < lim; ++b) bits |= (uint32_t)(p[b] != 0) << b;
     x->input_pinned[w] = bits;
   }
+}
+
+static int step_host_enqueue(const bh_ctx* x, int learning, cudaStream_t st) {
+  int rc;
   CU_RET(cudaMemcpyAsync(x->input_dev, x->input_pinned, (size_t)x->input_words * 4, cudaMemcpyHostToDevice, st));
   if (x->fused_mode) {
-    // one kernel: the step and the summary gather
-    if ((rc = launch_fused(x, x->input_dev, 1, learning, 1, st))) return rc;
-    size_t bytes = (size_t)BH_SUMMARY_INTS(x->active_columns) * 4;
-    CU_RET(cudaMemcpyAsync(x->summary_pinned, x->summary_dev, bytes, cudaMemcpyDeviceToHost, st));
-    CU_RET(cudaStreamSynchronize(st));
-    if (summary_host) memcpy(summary_host, x->summary_pinned, bytes);
-    return 0;
+    if ((rc = launch_fused(x, x->input_dev, 1, learning, 1, st))) return rc;  // step + summary gather
+  } else {
+    if ((rc = bh_step(x, x->input_dev, learning, st))) return rc;
+    int k = x->active_columns;
+    int n = k > BH_MT_N + 1 ? k : BH_MT_N + 1;
+    k_summary<<<cdiv(n, 256) < 64 ? cdiv(n, 256) : 64, 256, 0, st>>>(*x);
+    LAUNCHED("summary");
   }
-  if ((rc = bh_step(x, x->input_dev, learning, stream))) return rc;
-  return bh_summary(x, summary_host, stream);
+  CU_RET(cudaMemcpyAsync(x->summary_pinned, x->summary_dev, (size_t)BH_SUMMARY_INTS(x->active_columns) * 4,
+                         cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+extern "C" int bh_host_graph_create(const bh_ctx* x, int learning, void* stream, void** out) {
+  if (!out) return BH_E_BADARG;
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (!x->input_pinned || !x->summary_pinned) return BH_E_BADARG;
+  if (x->fused_mode && (rc = prepare_fused(x->fused_mode))) return rc;
+  cudaStream_t st = S_(stream);
+  cudaGraph_t graph = nullptr;
+  CU_RET(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  rc = step_host_enqueue(x, learning, st);
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  *out = exec;
+  return 0;
+}
+
+extern "C" int bh_step_host_graph(const bh_ctx* x, void* graph_exec, const uint8_t* input_bool_host,
+                                  int32_t* summary_host, void* stream) {
+  if (!x || !graph_exec || !input_bool_host) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  pack_host(x, input_bool_host);
+  CU_RET(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), st));
+  CU_RET(cudaStreamSynchronize(st));
+  if (summary_host) memcpy(summary_host, x->summary_pinned, (size_t)BH_SUMMARY_INTS(x->active_columns) * 4);
+  return 0;
+}
+
+extern "C" int bh_step_host(const bh_ctx* x, const uint8_t* input_bool_host, int learning, int32_t* summary_host,
+                            void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (!input_bool_host || !x->input_pinned || !x->summary_pinned) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  pack_host(x, input_bool_host);
+  if ((rc = step_host_enqueue(x, learning, st))) return rc;
+  CU_RET(cudaStreamSynchronize(st));
+  if (summary_host) memcpy(summary_host, x->summary_pinned, (size_t)BH_SUMMARY_INTS(x->active_columns) * 4);
+  return 0;
 }
 
 extern "C" int bh_summary(const bh_ctx* x, int32_t* summary_host, void* stream) {

@@ -16,7 +16,7 @@
 
 #define MT_N 624
 #define MT_M 397
-#define MT_THREADS 256
+#define MT_THREADS 1024
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v) {
   uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
@@ -50,39 +50,61 @@ __device__ __forceinline__ void mt_next_block(uint32_t* x) {
   __syncthreads();
 }
 
+#define MT_RING 2048  // shared-memory ring of stream words (power of two >= 1078 + 623)
+
 // Emit `count` doubles to out[0..count) continuing the stream at (key, *pos_io).
-// Whole CTA (blockDim.x >= 256 threads); x is shared memory of 2*MT_N words.
+// Whole CTA (blockDim.x >= 256 threads); x is shared memory of MT_RING words.
+//
+// The stream is kept as a ring of raw words indexed by absolute position.  After one
+// classic block (to have 1078 words of history) it is extended 623 words per barrier
+// with the recurrence expanded three times,
+//     x[n] = x[n-681] ^ f(n-1078) ^ f(n-851) ^ f(n-624),  f(m) = twist(x[m], x[m+1]),
+// whose operands all precede a 623-word wave.  Any 624 consecutive stream words are a
+// valid np.random key, so the final state is the last 624 words generated plus the
+// offset of the first unconsumed one.
 __device__ __noinline__ void mt_fill_block(uint32_t* x, uint32_t* key, int* pos_io, double* out, long long count) {
   const int t = threadIdx.x, NT = blockDim.x;
-  #pragma unroll 1
+  const unsigned M = MT_RING - 1;
+#pragma unroll 1
   for (int i = t; i < MT_N; i += NT) x[i] = key[i];
-  int p = *pos_io;
+  const long long p = *pos_io;           // absolute index of the first unconsumed word
+  const long long need_end = p + 2 * count;
+  long long G = MT_N;                    // words available: [0, G)
+  long long done = 0;                    // doubles emitted so far
   __syncthreads();
-  long long done = 0;
-  while (done < count) {
-    long long need_words = 2 * (count - done);
-    bool gen = (long long)p + need_words > MT_N;
-    if (gen) mt_next_block(x);
-    int avail = (gen ? 2 * MT_N : MT_N) - p;
-    long long pairs = avail / 2;
-    if (pairs > count - done) pairs = count - done;
-    #pragma unroll 1
-    for (int q = t; q < pairs; q += NT) {
-      uint32_t a = mt_temper(x[p + 2 * q]) >> 5;
-      uint32_t b = mt_temper(x[p + 2 * q + 1]) >> 6;
-      out[done + q] = ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
-    }
-    p += 2 * (int)pairs;
-    done += pairs;
-    __syncthreads();
-    if (gen) {  // then p > 624: the new block becomes the current one
-      #pragma unroll 1
-      for (int i = t; i < MT_N; i += NT) x[i] = x[MT_N + i];  // disjoint halves
-      p -= MT_N;
-      __syncthreads();
-    }
+#define MT_EMIT()                                                                          \
+  do {                                                                                     \
+    long long upto_ = G > p ? (G - p) / 2 : 0;                                             \
+    if (upto_ > count) upto_ = count;                                                      \
+    _Pragma("unroll 1") for (long long q = done + t; q < upto_; q += NT) {                 \
+      const unsigned w_ = (unsigned)(p + 2 * q);                                           \
+      const uint32_t a_ = mt_temper(x[w_ & M]) >> 5, b_ = mt_temper(x[(w_ + 1) & M]) >> 6; \
+      out[q] = ((double)a_ * 67108864.0 + (double)b_) * (1.0 / 9007199254740992.0);        \
+    }                                                                                      \
+    done = upto_ > done ? upto_ : done;                                                    \
+  } while (0)
+  MT_EMIT();
+  if (need_end > G) {  // classic regeneration of one block: words [624, 1248)
+    mt_next_block(x);
+    G = 2 * MT_N;
+    MT_EMIT();
   }
-  #pragma unroll 1
-  for (int i = t; i < MT_N; i += NT) key[i] = x[i];
-  if (t == 0) *pos_io = p;
+#pragma unroll 1
+  while (need_end > G) {  // 623 independent words per barrier
+#pragma unroll 1
+    for (int i = t; i < MT_N - 1; i += NT) {
+      const unsigned n = (unsigned)G + i;
+      x[n & M] = x[(n - 681) & M] ^ mt_twist(x[(n - 1078) & M], x[(n - 1077) & M]) ^
+                 mt_twist(x[(n - 851) & M], x[(n - 850) & M]) ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
+    }
+    __syncthreads();
+    G += MT_N - 1;
+    MT_EMIT();
+  }
+#undef MT_EMIT
+  __syncthreads();
+  const long long start = G - MT_N;
+#pragma unroll 1
+  for (int i = t; i < MT_N; i += NT) key[i] = x[(unsigned)(start + i) & M];
+  if (t == 0) *pos_io = (int)(need_end - start);
 }

@@ -55,7 +55,7 @@ __device__ __forceinline__ LearnTotals learn_totals(const bh_ctx& c, int learnin
 // number of CTAs that ran the ranged phases (for the per-CTA count arrays).
 // ---------------------------------------------------------------------------------
 __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, int nw) {
-  __shared__ uint32_t x[2 * MT_N];
+  __shared__ uint32_t x[MT_RING];
   __shared__ long long s_count, s_dst;
   __shared__ int s_red[32];
   int m_before = 0, m_total = 0;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_tm_draw(const __grid_constant__ 
 
 // Plain stream fill (bh_rng_fill)
 __global__ void __launch_bounds__(MT_THREADS) k_rng_fill(const __grid_constant__ bh_ctx c, double* dst, long long count) {
-  __shared__ uint32_t x[2 * MT_N];
+  __shared__ uint32_t x[MT_RING];
   mt_fill_block(x, c.mt_key, &c.sc[BH_SC_MT_POS], dst, count);
 }
 

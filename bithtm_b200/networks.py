@@ -29,24 +29,35 @@ def _bits(words: np.ndarray, c: int) -> np.ndarray:
 
 
 class _RngLink:
-    """Keeps the device MT19937 state and the global ``np.random`` state in step."""
+    """Keeps the device MT19937 state and the global ``np.random`` state in step.
+
+    np.random.get_state()/set_state() cost ~40 us each, so the legacy global
+    RandomState's raw state (624 key words + position, numpy/random/src/mt19937) is
+    read and written in place through the address NumPy publishes for that purpose
+    (``BitGenerator.ctypes.state_address``).  The Gaussian cache of the legacy
+    generator is never touched, exactly as rand() does not touch it."""
 
     def __init__(self, mode="step"):
         assert mode in ("step", "lazy")
         self.mode = mode
-        self._key = None
-        self._pos = None
         self._seeded = False
+        import ctypes
+
+        addr = np.random.mtrand._rand._bit_generator.ctypes.state_address
+        self._live_key = np.ctypeslib.as_array((ctypes.c_uint32 * nat.MT_N).from_address(addr))
+        self._live_pos = ctypes.c_int.from_address(addr + 4 * nat.MT_N)
+        self._key = np.zeros(nat.MT_N, dtype=np.uint32)  # what the device continues from
+        self._pos = -1
 
     def before(self, eng):
         if self.mode == "lazy" and self._seeded:
             return
-        st = np.random.get_state()
-        if self._seeded and st[2] == self._pos and np.array_equal(st[1], self._key):
-            self._tail = st[3:]
-            return
-        eng.set_rng_state(st[1], st[2])
-        self._key, self._pos, self._tail = st[1].copy(), st[2], st[3:]
+        pos = self._live_pos.value
+        if self._seeded and pos == self._pos and np.array_equal(self._live_key, self._key):
+            return  # nobody drew from np.random since our last write-back
+        self._key[:] = self._live_key
+        self._pos = pos
+        eng.set_rng_state(self._key, pos)
         self._seeded = True
 
     def after(self, eng, summary=None):
@@ -57,15 +68,18 @@ class _RngLink:
         else:
             k = eng.k
             tail = summary[4 + 4 * k:4 + 4 * k + nat.MT_N + 1]
-            key, pos = tail[:nat.MT_N].view(np.uint32).copy(), int(tail[nat.MT_N])
-        np.random.set_state(("MT19937", key, pos) + tuple(self._tail))
-        self._key, self._pos = key, pos
+            key, pos = tail[:nat.MT_N].view(np.uint32), int(tail[nat.MT_N])
+        self._key[:] = key
+        self._pos = pos
+        self._live_key[:] = key
+        self._live_pos.value = pos
 
     def sync(self, eng):
         key, pos = eng.get_rng_state()
-        tail = np.random.get_state()[3:]
-        np.random.set_state(("MT19937", key, pos) + tuple(tail))
-        self._key, self._pos = key, pos
+        self._key[:] = key
+        self._pos = pos
+        self._live_key[:] = key
+        self._live_pos.value = pos
 
 
 class SpatialPooler:

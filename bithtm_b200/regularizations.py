@@ -32,9 +32,13 @@ class ExponentialBoosting:
         )
 
     def _bind(self, engine):
+        key = (self.intensity, self.density, self.momentum, id(engine))
+        if getattr(self, "_bound_key", None) == key:
+            return  # constants unchanged since the last call
         self._engine = engine
         for k, v in self._constants().items():
             setattr(engine.ctx, k, v)
+        self._bound_key = key
 
     def _need_engine(self):
         if self._engine is None:

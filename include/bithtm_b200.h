@@ -249,6 +249,14 @@ int bh_step_ring(const bh_ctx* ctx, int learning, void* stream);
 int bh_step_host(const bh_ctx* ctx, const uint8_t* input_bool_host, int learning,
                  int32_t* summary_host, void* stream);
 
+/* The same end-to-end step as ONE CUDA graph launch (H2D copy node from
+ * ctx->input_pinned, the step, the summary gather, D2H copy node into
+ * ctx->summary_pinned).  bh_host_graph_create captures it once per (ctx, learning);
+ * bh_step_host_graph packs the input, launches and synchronises. */
+int bh_host_graph_create(const bh_ctx* ctx, int learning, void* stream, void** graph_exec_out);
+int bh_step_host_graph(const bh_ctx* ctx, void* graph_exec, const uint8_t* input_bool_host,
+                       int32_t* summary_host, void* stream);
+
 /* Copy the summary of the last completed step to the host and synchronise (used
  * after bh_tm_step / bh_step when the caller did not go through bh_step_host). */
 int bh_summary(const bh_ctx* ctx, int32_t* summary_host, void* stream);
