@@ -146,7 +146,7 @@ class Engine:
             "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": S * E, "syn_perm": S * E,
             "row_pred": k, "row_act": k, "row_win": k, "row_unacc": k, "winners": 2 * k * c, "unacc": k * c,
             "m_seg": M, "m_conn": M, "m_jit": M, "m_flag": M, "learn_list": x.learn_capacity, "punish_list": M,
-            "blk": 8 * 1024, "mt_key": nat.MT_N, "rand_buf": x.rand_capacity, "sc": nat.SC_COUNT,
+            "blk": 8 * 1024, "topk_ws": 8192, "mt_key": nat.MT_N, "rand_buf": x.rand_capacity, "sc": nat.SC_COUNT,
             "input_ring": x.ring_len * x.input_words, "input_dev": x.mask_stride,
             "summary_dev": nat.summary_ints(k),
         }

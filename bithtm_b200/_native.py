@@ -68,7 +68,7 @@ class BhCtx(C.Structure):
         ("row_pred", _P), ("row_act", _P), ("row_win", _P), ("row_unacc", _P),
         ("winners", _P), ("unacc", _P),
         ("m_seg", _P), ("m_conn", _P), ("m_jit", _P), ("m_flag", _P),
-        ("learn_list", _P), ("punish_list", _P), ("blk", _P),
+        ("learn_list", _P), ("punish_list", _P), ("blk", _P), ("topk_ws", _P),
         ("mt_key", _P), ("rand_buf", _P),
         ("sc", _P), ("input_ring", _P), ("input_dev", _P), ("input_pinned", _P),
         ("summary_dev", _P), ("summary_pinned", _P),
@@ -84,7 +84,7 @@ DEVICE_BUFFERS = {
     "syn_cell": "int32", "syn_perm": "float32",
     "row_pred": "int32", "row_act": "int32", "row_win": "int32", "row_unacc": "int32",
     "winners": "int32", "unacc": "int32", "m_seg": "int32", "m_conn": "int32", "m_jit": "float32",
-    "m_flag": "uint8", "learn_list": "int32", "punish_list": "int32", "blk": "int32",
+    "m_flag": "uint8", "learn_list": "int32", "punish_list": "int32", "blk": "int32", "topk_ws": "int32",
     "mt_key": "int32", "rand_buf": "float64", "sc": "int32", "input_ring": "int32", "input_dev": "int32",
     "summary_dev": "int32",
 }

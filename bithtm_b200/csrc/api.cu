@@ -93,6 +93,7 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->learn_list, (size_t)x->learn_capacity);
   cv.take(x->punish_list, M);
   cv.take(x->blk, (size_t)BLK_ROWS * BH_BLK_STRIDE);
+  cv.take(x->topk_ws, (size_t)BH_TOPK_WS_INTS);
   cv.take(x->mt_key, (size_t)BH_MT_N);
   cv.take(x->rand_buf, (size_t)x->rand_capacity);
   cv.take(x->sc, (size_t)BH_SC_COUNT);
@@ -196,7 +197,32 @@ extern "C" int bh_boost(const bh_ctx* x, void* stream) {
   return 0;
 }
 
+// cooperative launch of a <<<sm_count, TOPK_THREADS>>> kernel taking (ctx, extra args...)
+template <typename... Args>
+static int launch_coop(void (*kern)(const bh_ctx, Args...), const bh_ctx* x, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(x->sm_count > 0 ? x->sm_count : 148);
+  cfg.blockDim = dim3(TOPK_THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_RET(cudaLaunchKernelEx(&cfg, kern, *x, args...));
+  return 0;
+}
+
+#define BH_TOPK_MULTI_MIN 16384  // columns from which the grid-wide top-k pays for its barriers
+
 extern "C" int bh_inhibit(const bh_ctx* x, void* stream) {
+  if (x->column_dim >= BH_TOPK_MULTI_MIN) {
+    int rc = launch_coop(k_topk_multi, x, S_(stream));
+    if (rc) return rc;
+    LAUNCHED("topk_multi");
+    return 0;
+  }
   k_topk<<<1, TOPK_THREADS, 0, S_(stream)>>>(*x);
   LAUNCHED("topk");
   return 0;
@@ -241,7 +267,11 @@ extern "C" int bh_sp_shard_local(const bh_ctx* x, const uint32_t* in, double* ca
   // scratch for the selected local positions: the (not yet used) current active-column buffer
   int* scratch = x->row_unacc ? reinterpret_cast<int*>(x->row_unacc) : nullptr;
   if (!scratch) return BH_E_BADARG;
-  k_topk_shard_local<<<1, TOPK_THREADS, 0, st>>>(*x, scratch, cand_keys, cand_cols);
+  if (x->col_local >= BH_TOPK_MULTI_MIN) {
+    if ((rc = launch_coop(k_topk_shard_local_multi, x, st, scratch, cand_keys, cand_cols))) return rc;
+  } else {
+    k_topk_shard_local<<<1, TOPK_THREADS, 0, st>>>(*x, scratch, cand_keys, cand_cols);
+  }
   LAUNCHED("topk_shard_local");
   return 0;
 }

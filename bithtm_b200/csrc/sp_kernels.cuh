@@ -349,6 +349,234 @@ __global__ void __launch_bounds__(TOPK_THREADS)
             cand_cols, c.col_active);
 }
 
+// ---------------------------------------------------------------------------------
+// (b) for large column counts: the same selection on a cooperative grid of nb CTAs
+// (grid barriers between stages).  Workspace `ws` (ctx.topk_ws, zero between calls):
+//   u64[0] = max key, u64[1] = max ~key (=> min), u64[2] = k-th key, u64[3..3+1024) =
+//   candidate keys; then ints: [0] cand count, [1] k-th index, [2] tie mode, [3] rem,
+//   [8..8+8*256) per-pass histograms, [.. +1024) candidate indices, [.. +1024) per-CTA
+//   tie counts.  Per-CTA selected counts use ctx.blk row 6.
+// ---------------------------------------------------------------------------------
+#define TKW_U64_CAND 4
+#define TKW_INT_BASE ((TKW_U64_CAND + TOPK_THREADS) * 2)
+#define TKW_HIST 8
+#define TKW_CIDX (TKW_HIST + 8 * 256)
+#define TKW_TIES (TKW_CIDX + TOPK_THREADS)
+#define TKW_INTS (TKW_INT_BASE + TKW_TIES + BH_BLK_STRIDE)
+#define BLK_TOPK 6
+
+__device__ void topk_multi(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
+                           const int* map, uint8_t* flags, int b, int nb, unsigned int* bar) {
+  __shared__ int hist[256];
+  __shared__ int s_scan[32];
+  __shared__ unsigned long long s_u64[32];
+  __shared__ int s_bin, s_rem, s_ncand;
+  unsigned long long* w64 = reinterpret_cast<unsigned long long*>(c.topk_ws);
+  int* wi = c.topk_ws + TKW_INT_BASE;
+  const int t = threadIdx.x, lane = t & 31, NT = blockDim.x;
+  const Range rg = block_range(n, b, nb);
+
+  // stage 1: global min / max
+  unsigned long long mn = ~0ull, mx = 0ull;
+#pragma unroll 1
+  for (int j = rg.begin + t; j < rg.end; j += NT) {
+    const unsigned long long key = keys[j];
+    mn = key < mn ? key : mn;
+    mx = key > mx ? key : mx;
+  }
+  mn = block_reduce_u64(mn, false, s_u64);
+  mx = block_reduce_u64(mx, true, s_u64);
+  if (t == 0 && rg.begin < rg.end) {
+    atomicMax(&w64[0], mx);
+    atomicMax(&w64[1], ~mn);
+  }
+  grid_barrier(bar, nb);
+  mx = w64[0];
+  mn = ~w64[1];
+  int consumed = (mn == mx) ? 64 : __clzll((long long)(mn ^ mx));
+  unsigned long long prefix =
+      (consumed == 0) ? 0ull : (consumed == 64 ? mx : (mx >> (64 - consumed)) << (64 - consumed));
+  int rem = k, ncand = n, pass = 0;
+
+  // stage 2: radix passes over global histograms until <= TOPK_THREADS candidates remain
+#pragma unroll 1
+  while (consumed < 64 && ncand > TOPK_THREADS && pass < 8) {
+    const int shift = (64 - consumed - 8) > 0 ? (64 - consumed - 8) : 0;
+    const int width = 64 - consumed - shift;
+    const unsigned long long hi_mask = consumed == 0 ? 0ull : (~0ull << (64 - consumed));
+    int* ghist = wi + TKW_HIST + pass * 256;
+#pragma unroll 1
+    for (int i = t; i < 256; i += NT) hist[i] = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int base = rg.begin; base < rg.end; base += NT) {
+      const int j = base + t;
+      const unsigned long long key = j < rg.end ? keys[j] : 0ull;
+      const bool in = j < rg.end && (key & hi_mask) == prefix;
+      const int d = (int)((key >> shift) & ((1u << width) - 1u));
+      const unsigned peers = __match_any_sync(BH_FULL, in ? d : -1);
+      if (in && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], __popc(peers));
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = t; i < 256; i += NT)
+      if (hist[i]) atomicAdd(&ghist[i], hist[i]);
+    grid_barrier(bar, nb);
+    if (t < 32) {
+      int local[8], sum = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        local[i] = ghist[255 - (lane * 8 + i)];
+        sum += local[i];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(BH_FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int before = incl - sum;
+      if (before < rem && incl >= rem) {
+        int r = rem - before;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (r > 0 && local[i] >= r) {
+            s_bin = 255 - (lane * 8 + i);
+            s_rem = r;
+            s_ncand = local[i];
+            r = -1;
+          } else if (r > 0) {
+            r -= local[i];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (unsigned long long)s_bin << shift;
+    rem = s_rem;
+    ncand = s_ncand;
+    consumed += width;
+    ++pass;
+    __syncthreads();
+  }
+
+  // stage 3: gather the candidates (unordered), rank them in CTA 0
+  const bool tie_mode = ncand > TOPK_THREADS;  // > 1024 identical keys at the cut
+  if (!tie_mode) {
+    const unsigned long long hi_mask = consumed == 0 ? 0ull : (consumed == 64 ? ~0ull : (~0ull << (64 - consumed)));
+#pragma unroll 1
+    for (int j = rg.begin + t; j < rg.end; j += NT) {
+      const unsigned long long key = keys[j];
+      if ((key & hi_mask) == prefix) {
+        const int p = atomicAdd(&wi[0], 1);
+        w64[TKW_U64_CAND + p] = key;
+        wi[TKW_CIDX + p] = j;
+      }
+    }
+  }
+  grid_barrier(bar, nb);
+  if (!tie_mode && b == 0) {
+    const int nc = wi[0];
+    if (t < nc) {
+      const unsigned long long mk = w64[TKW_U64_CAND + t];
+      const int mi = wi[TKW_CIDX + t];
+      int ahead = 0;
+#pragma unroll 2
+      for (int i = 0; i < nc; ++i) {
+        const unsigned long long ok = w64[TKW_U64_CAND + i];
+        ahead += (ok > mk || (ok == mk && wi[TKW_CIDX + i] < mi)) ? 1 : 0;
+      }
+      if (ahead == rem - 1) {
+        w64[2] = mk;
+        wi[1] = mi;
+      }
+    }
+  }
+  if (tie_mode && b == 0 && t == 0) {
+    w64[2] = prefix;
+    wi[1] = 0x7fffffff;
+  }
+  grid_barrier(bar, nb);
+  const unsigned long long kth_key = w64[2];
+  const int kth_idx = wi[1];
+
+  // stage 4: per-CTA counts over contiguous ranges, then the ordered write
+  int n_sel = 0, n_tie = 0;
+#pragma unroll 1
+  for (int j = rg.begin + t; j < rg.end; j += NT) {
+    const unsigned long long key = keys[j];
+    n_tie += key == kth_key ? 1 : 0;
+    n_sel += (key > kth_key || (!tie_mode && key == kth_key && j <= kth_idx)) ? 1 : 0;
+  }
+  n_sel = block_sum(n_sel, s_scan);
+  n_tie = block_sum(n_tie, s_scan);
+  if (t == 0) {
+    BLK(c, BLK_TOPK)[b] = n_sel;
+    wi[TKW_TIES + b] = n_tie;
+  }
+  grid_barrier(bar, nb);
+  int tie_before = 0, tie_all = 0, gt_before = 0, gt_all = 0;
+  blk_prefix(BLK(c, BLK_TOPK), b, nb, s_scan, gt_before, gt_all);
+  if (tie_mode) blk_prefix(wi + TKW_TIES, b, nb, s_scan, tie_before, tie_all);
+  // in tie mode the selected set = all keys > kth plus the first `rem` equal keys by index;
+  // the output position of an element is (#greater before it) + (#taken ties before it)
+  int base_sel = gt_before + (tie_mode ? (tie_before < rem ? tie_before : rem) : 0), base_tie = tie_before;
+#pragma unroll 1
+  for (int tile = rg.begin; tile < rg.end; tile += NT) {
+    const int j = tile + t;
+    const unsigned long long key = j < rg.end ? keys[j] : 0ull;
+    const bool gt = j < rg.end && key > kth_key;
+    const bool eq = j < rg.end && key == kth_key;
+    bool take;
+    if (tie_mode) {
+      int tie_total;
+      const int tie_rank = base_tie + block_excl_scan(eq ? 1 : 0, s_scan, tie_total);
+      base_tie += tie_total;
+      take = gt || (eq && tie_rank < rem);
+    } else {
+      take = gt || (eq && j <= kth_idx);
+    }
+    int sel_total;
+    const int pos = base_sel + block_excl_scan(take ? 1 : 0, s_scan, sel_total);
+    if (take && pos < k) {
+      const int col = map ? map[j] : j;
+      out[pos] = col;
+      if (flags) flags[col] = 1;
+    }
+    base_sel += sel_total;
+  }
+  // leave the workspace zeroed for the next call (all readers are past the last barrier)
+  grid_barrier(bar, nb);
+  if (b == 0) {
+#pragma unroll 1
+    for (int i = t; i < TKW_HIST + 8 * 256; i += NT) wi[i] = 0;
+    if (t < 3) w64[t] = 0ull;
+  }
+}
+
+// stand-alone cooperative kernels built on topk_multi (grid = one CTA per SM)
+__global__ void __launch_bounds__(TOPK_THREADS, 1) k_topk_multi(const __grid_constant__ bh_ctx c) {
+  unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
+  if (blockIdx.x == 0) retire_prev_flags(c);
+  const int k = c.active_columns;
+  topk_multi(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, k,
+             c.active_cols + (c.sc[BH_SC_STEP] & 1) * k, nullptr, c.col_active, blockIdx.x, gridDim.x, bar);
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS, 1)
+    k_topk_shard_local_multi(const __grid_constant__ bh_ctx c, int* scratch, double* cand_keys, int32_t* cand_cols) {
+  unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
+  const int k_loc = c.active_columns < c.col_local ? c.active_columns : c.col_local;
+  topk_multi(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
+             blockIdx.x, gridDim.x, bar);
+  grid_barrier(bar, gridDim.x);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k_loc; i += gridDim.x * blockDim.x) {
+    const int pos = scratch[i];
+    cand_keys[i] = c.boosted[pos];
+    cand_cols[i] = c.col_lo + pos;
+  }
+}
+
 // host-inhibition mode: adopt an explicit ordered list
 __global__ void k_set_active(const __grid_constant__ bh_ctx c, const int32_t* __restrict__ cols) {
   const int k = c.active_columns;

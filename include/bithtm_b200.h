@@ -32,6 +32,7 @@ extern "C" {
 #define BH_ABI_VERSION 1
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
+#define BH_TOPK_WS_INTS 8192
 
 /* error codes (negative); CUDA errors are returned as -(1000 + cudaError_t) */
 #define BH_E_BADARG (-1)
@@ -156,6 +157,7 @@ typedef struct bh_ctx {
   int32_t* learn_list;     /* [L_cap] learning_segment (projections.py:281 order)  */
   int32_t* punish_list;    /* [M_cap] punished_segment                             */
   int32_t* blk;            /* [8][1024] per-CTA counts for ordered compaction      */
+  int32_t* topk_ws;        /* [BH_TOPK_WS_INTS] workspace of the multi-CTA top-k   */
 
   /* ---- randomness: legacy MT19937 stream of np.random, advanced on the device - */
   uint32_t* mt_key;        /* [624]                                                */

@@ -62,7 +62,8 @@ def test_device_np_expf_matches_numpy():
     assert np.array_equal(np.exp(x).view(np.uint32), y.view(np.uint32))
 
 
-@pytest.mark.parametrize("I,C,k", [(64, 128, 10), (200, 300, 25), (1000, 2048, 41), (1024, 2048, 41), (4100, 512, 20)])
+@pytest.mark.parametrize("I,C,k", [(64, 128, 10), (200, 300, 25), (1000, 2048, 41), (1024, 2048, 41), (4100, 512, 20),
+                                   (96, 20480, 410)])  # the last one takes the grid-wide top-k
 def test_spatial_pooler_operators(I, C, k):
     """DenseProjection.process/update, ExponentialBoosting.process/update and
     GlobalInhibition.process one by one against the oracle (projections.py:18-24,
@@ -109,6 +110,25 @@ def test_topk_ties_take_lowest_index():
     assert got.tolist() == [5, 7, 9, 100, 200, 300, 400]
 
 
+def test_topk_grid_wide_ties():
+    """Grid-wide top-k (>= 16384 columns): more than 1024 identical keys at the cut
+    (tie mode) and a mixed case, lowest column index first."""
+    import bithtm_b200 as bithtm
+
+    np.random.seed(0)
+    C, k = 20480, 2000
+    sp = bithtm.SpatialPooler(64, C, k)
+    sp._ensure_engine()
+    from oracle.htm_oracle import canonical_topk
+
+    g = np.random.default_rng(1)
+    cases = [np.zeros(C), np.where(g.random(C) < 0.05, 3.0, 1.0), g.integers(0, 50, C).astype(np.float64),
+             g.random(C) * 100]
+    for keys in cases:
+        got = sp.inhibition.process(keys)
+        assert np.array_equal(got, canonical_topk(keys, k))
+
+
 # ------------------------------------------------------------------ lock-step SP+TM
 def _lockstep(name, steps=None, check_every=1, **engine_kw):
     import bithtm_b200 as bithtm
@@ -150,6 +170,25 @@ def test_lockstep_tiny(fused, ctas):
 @pytest.mark.parametrize("fused", ["cluster", "grid", "off"])
 def test_lockstep_odd_dims(fused):
     _lockstep("odd", fused=fused)
+
+
+def test_lockstep_many_columns_grid_kernel():
+    """16384 columns: the cooperative-grid fused kernel with the grid-wide top-k."""
+    import bithtm_b200 as bithtm
+
+    I, C, c, k, seed = 256, 16384, 4, 328, 21
+    np.random.seed(seed)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused="grid")
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed), overlap="packed")
+    g = np.random.default_rng(seed)
+    base = g.random((5, I)) < 0.2
+    for t in range(40):
+        x = base[t % 5] ^ (g.random(I) < 0.05)
+        sp_state, tm_state = htm.process(x)
+        rec = orc.step(x)
+        problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not problems, f"step {t}: " + "; ".join(problems)
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
 
 
 def test_lockstep_mid():
