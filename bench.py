@@ -300,9 +300,19 @@ def ours(args):
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"1500 timesteps of the same workload, NumPy oracle in reference-literal mode "
                          f"({dt:.1f} s), single thread as the reference; {os.cpu_count()} host cores visible"}
-    if rank == 0:
-        from bithtm_b200 import _native as nat
+    hbm = None
+    if rank == 0 and world == 1 and not args.no_hbm:
+        # the HBM-bound kernels of the path at cfg3 size (65536 x 16384): the cfg2 step is
+        # latency-bound, so kernel quality against the HBM roofline is shown here
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import sp_roofline
 
+            torch.cuda.empty_cache()
+            hbm = sp_roofline.measure(65536, 16384, 20)
+        except Exception as e:  # never lose the headline line
+            hbm = {"error": repr(e)}
+    if rank == 0:
         launches_per_step = launches
         line = {
             "metric": METRIC, "value": world * K / dev_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -318,7 +328,7 @@ def ours(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "note": "HierarchicalTemporalMemory.process(host bool array), np.random kept in lock-step"},
             "gpu_launches": launches_per_step * K,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -332,6 +342,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the cfg3-size HBM-bound kernel measurements")
     ap.add_argument("--fused", default="auto", choices=["auto", "cluster", "grid", "off"],
                     help="execution mode of the step (default: one kernel on a thread-block cluster at this size)")
     ap.add_argument("--fused-ctas", type=int, default=None, help="CTAs of the fused kernel")

@@ -267,8 +267,45 @@ class PredictiveProjection:
         perm[free] = -1.0
         return owner, count, cells, perm
 
+    @property
+    def segment_projection(self):
+        """Read-only snapshot of the synapse store in the reference's storage vocabulary
+        (``SparseProjection``, projections.py:27-68): what
+        ``reference_implementations.TemporalMemory.copy_custom`` reads
+        (reference_implementations.py:51-70)."""
+        return SegmentProjectionView(self)
+
     def process(self, active_input, return_jittered_potential_info=True):
         raise NotImplementedError("call through bithtm_b200.TemporalMemory.process (the fused device path)")
 
     def update(self, *args, **kwargs):
         raise NotImplementedError("call through bithtm_b200.TemporalMemory.process (the fused device path)")
+
+
+class SegmentProjectionView:
+    """Export shim with the attribute names of the reference's ``SparseProjection``
+    (projections.py:32-68).  ``output_edge`` holds the presynaptic flat cell directly
+    (slot index 0), so ``get_output_edge_target`` is the reference's ``% (input_dim+1)``
+    and free slots carry ``invalid_output_edge == input_dim`` (:36)."""
+
+    def __init__(self, projection):
+        self.input_dim = projection.output_dim  # presynaptic cells = all cells (networks.py:55)
+        self.invalid_input_edge = 0
+        self.invalid_output_edge = self.input_dim
+        if projection._engine is None:
+            self.output_dim = 0
+            self.output_edges = np.zeros((0, 1), dtype=np.int32)
+            self.output_edge = np.zeros((0, 0), dtype=np.int32)
+            self.output_permanence = np.zeros((0, 0), dtype=np.float32)
+            return
+        owner, count, cells, perm = projection.export_segments()
+        width = int(count.max()) if len(count) else 0
+        self.output_dim = len(owner)
+        self.output_edges = count.astype(np.int32).reshape(-1, 1)  # :42
+        edge = cells[:, :width].astype(np.int32)
+        edge[edge < 0] = self.invalid_output_edge
+        self.output_edge = edge  # :43
+        self.output_permanence = perm[:, :width].astype(np.float32)  # :44 (-1.0 = free)
+
+    def get_output_edge_target(self, output_edge):  # projections.py:60-61
+        return output_edge % (self.input_dim + 1)

@@ -326,3 +326,59 @@ def test_stale_state_read_raises():
     assert sp1.overlaps is not None
     with pytest.raises(RuntimeError):
         tm1.distal_state.prediction
+
+
+def test_export_shim_feeds_reference_style_reader():
+    """The state export in the reference's storage vocabulary (segment_bundle,
+    segment_projection.output_edge / output_permanence / invalid_output_edge /
+    get_output_edge_target) read the way reference_implementations.py:51-70 reads it
+    gives the oracle's synapses."""
+    import bithtm_b200 as bithtm
+
+    info = load_golden("tiny")
+    xs = golden_inputs(info, 400)
+    np.random.seed(info["seed"])
+    htm = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"])
+    orc = HTMOracle(OracleConfig(info["I"], info["C"], info["c"], info["k"]), rng=np.random.RandomState(info["seed"]))
+    for t in range(400):
+        htm.process(xs[t])
+        orc.step(xs[t])
+    dp = htm.temporal_memory.distal_projection
+    proj = dp.segment_projection
+    segment_cell = dp.segment_bundle[:].squeeze(1).tolist()
+    assert segment_cell == orc.seg_owner[:orc.n_seg].tolist()
+    assert np.array_equal(dp.bundle_segments, orc.cell_nseg)
+    for seg, (synapses, permanences) in enumerate(zip(proj.output_edge[:], proj.output_permanence[:])):
+        got = sorted((int(proj.get_output_edge_target(s)), float(p)) for s, p in zip(synapses, permanences)
+                     if s != proj.invalid_output_edge)
+        v = orc.syn_cell[seg] >= 0
+        want = sorted(zip(orc.syn_cell[seg][v].tolist(), orc.syn_perm[seg][v].astype(float).tolist()))
+        assert got == want, f"segment {seg}"
+        assert int(proj.output_edges[seg, 0]) == len(want)
+    last = htm.temporal_memory.last_state
+    assert np.array_equal(htm.temporal_memory.flatten_cell(last.active_cell),
+                          htm.temporal_memory.flatten_cell(last.active_cell))
+
+
+def test_example_driver_stream_matches_oracle():
+    """example.py's loop (np.random used by the caller between steps, example.py:34,52):
+    the interleaved global stream is consumed exactly as the reference consumes it."""
+    import bithtm_b200 as bithtm
+
+    I, C, c, seed = 128, 256, 8, 13
+    k = 20
+    np.random.seed(seed)
+    inputs = np.random.rand(7, I) < 0.25
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k)
+    rs = np.random.RandomState(seed)
+    inputs_o = rs.rand(7, I) < 0.25
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=rs)
+    assert np.array_equal(inputs, inputs_o)
+    for t in range(200):
+        x = inputs[t % 7] ^ (np.random.rand(I) < 0.05)
+        xo = inputs_o[t % 7] ^ (rs.rand(I) < 0.05)
+        assert np.array_equal(x, xo), f"caller-visible np.random diverged at step {t}"
+        sp_state, tm_state = htm.process(x)
+        rec = orc.step(xo)
+        problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not problems, f"step {t}: " + "; ".join(problems)
