@@ -103,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
                  str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -111,12 +111,18 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        if os.path.getsize(self.path) == 0:  # the loop never got to print: one synchronous sample
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=20).stdout
+                open(self.path, "w").write(out)
+            except Exception:
+                pass
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in open(self.path):
@@ -205,15 +211,16 @@ def ours(args):
                  1: f"whole step in one kernel on a thread-block cluster of {eng.ctx.fused_ctas} CTAs",
                  2: f"whole step in one cooperative kernel, {eng.ctx.fused_ctas} CTAs"}[eng.ctx.fused_mode]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi needs a moment to start: sample from the warm-up on (same load)
     for _ in range(W):
+        flush.fill_(1)
         eng.launch_graph(graph1, 1)
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
     for a, b in ev:
         flush.fill_(1)  # evict L2 so the step streams its state from HBM
         a.record()

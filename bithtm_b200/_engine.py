@@ -6,6 +6,7 @@ host memory and the current stream only -- all arithmetic is in the CUDA library
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -20,7 +21,7 @@ def _torch():
     global _TORCH_DTYPES
     if _TORCH_DTYPES is None:
         _TORCH_DTYPES = {"float64": torch.float64, "float32": torch.float32, "int32": torch.int32,
-                         "uint8": torch.uint8}
+                         "uint8": torch.uint8, "int64": torch.int64}
     return torch
 
 
@@ -44,7 +45,7 @@ class Engine:
     def __init__(self, input_dim, column_dim, cell_dim, active_columns, *, device=None,
                  max_segments=None, max_synapses_per_segment=128, match_capacity=None,
                  learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
-                 fused="auto", fused_ctas=None, column_shard=None):
+                 fused="auto", fused_ctas=None, column_shard=None, parallel_rng="auto"):
         """``column_shard=(rank, world)``: this engine owns columns
         [rank*C/world, (rank+1)*C/world) of the spatial pooler (permanence, mask, duty
         cycles); the temporal memory is replicated."""
@@ -68,8 +69,8 @@ class Engine:
             match_capacity = max_segments
         if learn_capacity is None:
             learn_capacity = max_segments + k * c
-        if rand_capacity is None:
-            rand_capacity = max(1 << 20, 8 * k * (k + 1)) + k * c + match_capacity
+        if rand_capacity is None:  # float64 draws one step may take: rand(k, c) + rand(L, W+1) + rand(M)
+            rand_capacity = max(1 << 18, 2 * k * (k + 1) + k * c + min(match_capacity, 4 * k * c))
         if tm_blocks is None:
             tm_blocks = self.sm_count if max_segments <= (1 << 20) else min(1024, self.sm_count * 6)
         ctx = nat.BhCtx()
@@ -90,7 +91,19 @@ class Engine:
         ctx.seg_capacity, ctx.syn_capacity = max_segments, _round_up(int(max_synapses_per_segment), 32)
         ctx.match_capacity, ctx.learn_capacity = int(match_capacity), int(learn_capacity)
         ctx.tm_blocks, ctx.sm_count = int(tm_blocks), self.sm_count
-        ctx.rand_capacity, ctx.ring_len = int(rand_capacity), int(ring_len)
+        # the stream ring holds raw MT19937 words (2 per double); a step may use a quarter of it
+        ring_words = 1 << 20
+        while ring_words < 8 * int(rand_capacity):
+            ring_words <<= 1
+        ctx.rng_ring_words, ctx.ring_len = ring_words, int(ring_len)
+        # many-CTA stream production (jump-ahead polynomials) once a step draws enough words
+        from . import _mtjump
+
+        typical = 2 * (k * (k + 1) + 2 * k * c)
+        if parallel_rng == "auto":
+            parallel_rng = typical >= 8 * _mtjump.CHUNK_WORDS
+        ctx.jump_polys = (3 * ring_words // 4) // _mtjump.CHUNK_WORDS + 2 if parallel_rng else 0
+        ctx.rng_lookahead = min(2 * (k * c + 4 * k) + 2 * nat.MT_N, ring_words // 8) if parallel_rng else 0
         # whole step as one kernel: on one thread-block cluster while the step is
         # latency-bound (mask <= 8 MiB), else on a cooperative grid with one CTA per SM
         if fused == "auto":
@@ -128,6 +141,9 @@ class Engine:
         ctx.summary_pinned = self.summary_pinned.data_ptr()
         self._summary_np = self.summary_pinned.numpy()
         self._summary_out = np.zeros(nat.summary_ints(k), dtype=np.int32)
+        if ctx.jump_polys:
+            tab = _mtjump.jump_table(ctx.jump_polys, cache_dir=os.path.dirname(nat.LIB_PATH))
+            self.buf["mt_jump"].copy_(torch.from_numpy(tab.view(np.int32).reshape(-1)).to(self.device))
         nat.check(nat.lib.bh_init(C.byref(ctx), self.stream), "bh_init")
         self.epoch = 0  # bumped by every completed step; lazily fetched State fields check it
         self._graphs = {}
@@ -146,7 +162,8 @@ class Engine:
             "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": S * E, "syn_perm": S * E,
             "row_pred": k, "row_act": k, "row_win": k, "row_unacc": k, "winners": 2 * k * c, "unacc": k * c,
             "m_seg": M, "m_conn": M, "m_jit": M, "m_flag": M, "learn_list": x.learn_capacity, "punish_list": M,
-            "blk": 8 * 1024, "topk_ws": 8192, "mt_key": nat.MT_N, "rand_buf": x.rand_capacity, "sc": nat.SC_COUNT,
+            "blk": 8 * 1024, "topk_ws": 8192, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
+            "rng64": nat.R_COUNT, "sc": nat.SC_COUNT,
             "input_ring": x.ring_len * x.input_words, "input_dev": x.mask_stride,
             "summary_dev": nat.summary_ints(k),
         }
@@ -217,8 +234,10 @@ class Engine:
         k32 = np.ascontiguousarray(key, dtype=np.uint32).view(np.int32)
         self.buf["mt_key"].copy_(torch.from_numpy(k32).to(self.device))
         self.buf["sc"][nat.SC_MT_POS] = int(pos)
+        nat.check(nat.lib.bh_rng_import(self.ref, self.stream), "bh_rng_import")
 
     def get_rng_state(self):
+        nat.check(nat.lib.bh_rng_export(self.ref, self.stream), "bh_rng_export")
         key = self.buf["mt_key"].cpu().numpy().view(np.uint32).copy()
         pos = int(self.buf["sc"][nat.SC_MT_POS].item())
         return key, pos

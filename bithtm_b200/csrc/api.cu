@@ -95,7 +95,9 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->blk, (size_t)BLK_ROWS * BH_BLK_STRIDE);
   cv.take(x->topk_ws, (size_t)BH_TOPK_WS_INTS);
   cv.take(x->mt_key, (size_t)BH_MT_N);
-  cv.take(x->rand_buf, (size_t)x->rand_capacity);
+  cv.take(x->rng_ring, (size_t)x->rng_ring_words);
+  cv.take(x->mt_jump, (size_t)x->jump_polys * BH_MT_N);
+  cv.take(x->rng64, (size_t)R_COUNT);
   cv.take(x->sc, (size_t)BH_SC_COUNT);
   cv.take(x->input_ring, (size_t)x->ring_len * x->input_words);
   cv.take(x->input_dev, (size_t)x->mask_stride);
@@ -114,6 +116,8 @@ static int check_ctx(const bh_ctx* x) {
   if (x->col_local < 1 || x->col_lo < 0 || x->col_lo + x->col_local > x->column_dim) return BH_E_BADARG;
   if (x->col_local != x->column_dim && x->fused_mode) return BH_E_UNSUPPORTED;  // sharded: per-stage kernels
   if (x->syn_capacity < 32 || x->syn_capacity % 32 != 0) return BH_E_BADARG;
+  if (x->rng_ring_words < (1 << 20) || (x->rng_ring_words & (x->rng_ring_words - 1))) return BH_E_BADARG;
+  if (x->jump_polys < 0 || x->rng_lookahead < 0) return BH_E_BADARG;
   return 0;
 }
 
@@ -141,6 +145,8 @@ extern "C" int bh_init(const bh_ctx* x, void* stream) {
   if (rc) return rc;
   long long N = (long long)x->column_dim * 32;
   k_fill_i32<<<cdiv(N, 256) < 1184 ? cdiv(N, 256) : 1184, 256, 0, S_(stream)>>>(x->cell_widx, N, -1);
+  LAUNCH_CHECK();
+  k_rng_import<<<1, 256, 0, S_(stream)>>>(*x);  // a defined (all-zero key) stream until the caller imports one
   LAUNCH_CHECK();
   return 0;
 }
@@ -321,6 +327,15 @@ static int learn_apply_smem(const bh_ctx* x) {
   return (int)(((bits + 31) / 32) * 4);
 }
 
+static int prepare_chunks() {
+  static bool done = false;
+  if (!done) {
+    CU_RET(cudaFuncSetAttribute(k_rng_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, RNG_CHUNK_SMEM));
+    done = true;
+  }
+  return 0;
+}
+
 extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
   cudaStream_t st = S_(stream);
   k_tm_learn_select_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, learning);
@@ -329,6 +344,13 @@ extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
   LAUNCHED("tm_learn_select_b");
   k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 2, learning);
   LAUNCHED("tm_draw2");
+  if (x->jump_polys > 0) {  // the chunks of the plan draw #2 may have left
+    int prc = prepare_chunks();
+    if (prc) return prc;
+    int cap = (x->sm_count > 0 ? x->sm_count : 148);
+    k_rng_chunks<<<x->jump_polys < cap ? x->jump_polys : cap, MT_THREADS, RNG_CHUNK_SMEM, st>>>(*x);
+    LAUNCHED("rng_chunks");
+  }
   if (learning) {
     int smem = learn_apply_smem(x);
     if (smem > 200 * 1024) return BH_E_UNSUPPORTED;
@@ -368,7 +390,9 @@ extern "C" int bh_tm_step(const bh_ctx* x, int learning, void* stream) {
 // ------------------------------------------------------------------------------------
 static int fused_smem(const bh_ctx* x) {
   int a = x->mask_stride * 4, b = learn_apply_smem(x);
-  return a > b ? a : b;
+  int m = a > b ? a : b;
+  if (x->fused_mode == 2 && x->jump_polys > 0 && m < RNG_CHUNK_SMEM) m = RNG_CHUNK_SMEM;
+  return m;
 }
 
 // One-time function attributes (per process): non-portable cluster sizes, dynamic smem.
@@ -433,9 +457,9 @@ extern "C" int bh_step(const bh_ctx* x, const uint32_t* in, int learning, void* 
 
 extern "C" int bh_step_launches(const bh_ctx* x, int learning) {
   if (x && x->fused_mode) return 1;
-  // overlap+boost, topk, [sp_learn], duty | draw1, select a/b | learn-select a/b, draw2, [apply] |
+  // overlap+boost, topk, [sp_learn], duty | draw1, select a/b | learn-select a/b, draw2, [chunks], [apply] |
   // post, activate a, draw3, activate b
-  return learning ? 15 : 13;
+  return (learning ? 15 : 13) + (x && x->jump_polys > 0 ? 1 : 0);
 }
 
 __global__ void k_ring_fetch(const __grid_constant__ bh_ctx c) {
@@ -619,9 +643,36 @@ extern "C" int bh_graph_destroy(void* graph_exec) {
 // ------------------------------------------------------------------------------------
 // randomness + test hooks
 // ------------------------------------------------------------------------------------
+extern "C" int bh_rng_import(const bh_ctx* x, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  k_rng_import<<<1, 256, 0, S_(stream)>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bh_rng_export(const bh_ctx* x, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  k_rng_export<<<1, 256, 0, S_(stream)>>>(*x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int bh_rng_fill(const bh_ctx* x, double* dst_dev, int64_t count, void* stream) {
-  if (!x || !dst_dev || count < 0) return BH_E_BADARG;
-  k_rng_fill<<<1, MT_THREADS, 0, S_(stream)>>>(*x, dst_dev, (long long)count);
+  if (!x || !dst_dev || count < 0 || count > x->rng_ring_words / 4) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  k_rng_fill_draw<<<1, MT_THREADS, 0, st>>>(*x, (long long)count);
+  LAUNCH_CHECK();
+  if (x->jump_polys > 0) {
+    int prc = prepare_chunks();
+    if (prc) return prc;
+    int cap = (x->sm_count > 0 ? x->sm_count : 148);
+    k_rng_chunks<<<x->jump_polys < cap ? x->jump_polys : cap, MT_THREADS, RNG_CHUNK_SMEM, st>>>(*x);
+    LAUNCH_CHECK();
+  }
+  int grid = cdiv(count > 0 ? count : 1, 256);
+  k_rng_fill_copy<<<grid < 1184 ? grid : 1184, 256, 0, st>>>(*x, dst_dev);
   LAUNCH_CHECK();
   return 0;
 }

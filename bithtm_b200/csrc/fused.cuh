@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (rng) ph_draw(c, 2, learning, nw);
     if (worker) ph_learn_select_b(c, learning, b, nw);
     BH_SYNC();
+    if (MODE == 2 && c.jump_polys > 0) {  // stream words draw #2 planned for many CTAs (mt19937.cuh)
+      ph_rng_chunks(c, s_dyn, b, nb);
+      BH_SYNC();
+    }
     BH_STAMP();
     // P5: permanence updates, deletion, growth
     if (learning) ph_learn_apply(c, s_dyn, b, nb);

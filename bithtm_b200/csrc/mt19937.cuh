@@ -1,15 +1,30 @@
 // Device-side MT19937 producing np.random's legacy float64 stream.
 //
-// The reference draws every random number from the global legacy np.random
-// stream (networks.py:87, projections.py:120,235).  How many are drawn per step
-// (L*(W+1), M) is decided on the device, so the generator lives on the device:
-// the host uploads np.random.get_state() (624 words + position) and can read it
-// back at any time, which keeps the caller's np.random in lock-step.
+// The reference draws every random number from the global legacy np.random stream
+// (networks.py:87, projections.py:120,235).  How many are drawn per step (L*(W+1), M)
+// is decided on the device, but the stream itself does not depend on the data, so the
+// generator is a PRODUCER that appends raw (untempered) stream words to a ring in
+// global memory, and the draws are CONSUMERS that take a range of it:
 //
-// One CTA regenerates the 624-word state in three dependency waves
-// (227 + 227 + 170 words: x[n] = x[n-227] ^ twist(x[n-624], x[n-623])) and emits
-// random_sample() doubles: (a >> 5) * 2^26 + (b >> 6)) / 2^53 from two tempered
-// words.
+//   rng_ring[a & (rng_ring_words-1)] = stream word with absolute index a
+//   rng64[R_PRODUCED] = words [.., PRODUCED) are in the ring
+//   rng64[R_CURSOR]   = first word no draw has taken yet
+//
+// Absolute index 0 is key[0] of the last state the host imported (bh_rng_import).  A
+// random_sample() double is built from two consecutive tempered words.  Any 624
+// consecutive stream words plus an offset are a valid np.random state, which is how
+// the state at the cursor is exported back (ph_rng_export / the step summary).
+//
+// Producers.
+//  * serial (one CTA): after two classic 227-word waves (x[n] = x[n-227] ^
+//    twist(x[n-624], x[n-623])) the recurrence expanded three times,
+//        x[n] = x[n-681] ^ f(n-1078) ^ f(n-851) ^ f(n-624),  f(m) = twist(x[m], x[m+1]),
+//    gives 623 independent words per barrier.
+//  * parallel (any number of CTAs): chunk p of RNG_CHUNK words starts at
+//    PLAN_BASE + p * RNG_CHUNK.  Its first 624 words are obtained from the RNG_WINDOW
+//    words before PLAN_BASE with the jump polynomial g_p = t^(RNG_WINDOW + p*RNG_CHUNK)
+//    mod phi(t) (bithtm_b200/_mtjump.py): x[m + D] = XOR_{i: g[i]=1} x[m + i]; the rest of
+//    the chunk follows with the serial recurrence inside the CTA.
 #pragma once
 
 #include "common.cuh"
@@ -17,6 +32,27 @@
 #define MT_N 624
 #define MT_M 397
 #define MT_THREADS 1024
+#define MT_RING 2048          // shared-memory ring of stream words (power of two >= 1078 + 623)
+#define RNG_WINDOW 20560      // 19937 + 623 words determine any 624 later consecutive words
+#define RNG_CHUNK 24920       // 40 * 623
+#define RNG_WIN_PAD 20608     // window words staged in shared memory (32*623 + 4*155 + 36, rounded)
+#define RNG_PAR_MIN (3 * RNG_CHUNK)  // deficits below this are produced serially
+#define RNG_CHUNK_SMEM ((RNG_WIN_PAD + MT_RING + MT_N) * 4)
+
+// rng64 slots
+enum {
+  R_PRODUCED = 0,
+  R_CURSOR,
+  R_OFF1,         // absolute word index of draw #1 (rand(k, c)) of the current step
+  R_OFF2,         // draw #2 (rand(L, W+1))
+  R_OFF3,         // draw #3 (rand(M))
+  R_N2,           // doubles actually drawn for #2 / #3 (after capacity clamping)
+  R_N3,
+  R_PLAN_BASE,    // parallel production plan: chunks [0, PLAN_CHUNKS) start at PLAN_BASE
+  R_PLAN_CHUNKS,
+  R_STEP_BASE,    // cursor at the first draw of the current step
+  R_COUNT = 16
+};
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v) {
   uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
@@ -31,80 +67,219 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-// x[0..624) holds the current state block; writes the next block to x[624..1248).
-// Called by all threads of the CTA (blockDim.x >= 256).
-__device__ __forceinline__ void mt_next_block(uint32_t* x) {
-  const int t = threadIdx.x;
-  if (t < MT_N - MT_M) x[MT_N + t] = x[t + MT_M] ^ mt_twist(x[t], x[t + 1]);
-  __syncthreads();
-  {
-    int kk = (MT_N - MT_M) + t;  // 227 .. 453
-    if (t < MT_N - MT_M) x[MT_N + kk] = x[MT_N + kk - (MT_N - MT_M)] ^ mt_twist(x[kk], x[kk + 1]);
+__device__ __forceinline__ uint32_t rng_word(const bh_ctx& c, long long a) {
+  return c.rng_ring[(unsigned long long)a & (unsigned long long)(c.rng_ring_words - 1)];
+}
+
+// random_sample(): the double made of stream words a and a + 1
+__device__ __forceinline__ double rng_uniform(const bh_ctx& c, long long a) {
+  const uint32_t hi = mt_temper(rng_word(c, a)) >> 5, lo = mt_temper(rng_word(c, a + 1)) >> 6;
+  return ((double)hi * 67108864.0 + (double)lo) * (1.0 / 9007199254740992.0);
+}
+
+// Extend the stream inside one CTA.  x = shared ring holding words [lo, G) at x[a & 2047]
+// (G - lo >= 624); generates up to at least `target` in whole waves and returns the new
+// G.  Words with absolute index in [store_lo, store_hi) are also written to the global
+// ring.  All threads call; ends with a barrier.
+__device__ __noinline__ long long mt_generate(const bh_ctx& c, uint32_t* x, long long lo, long long G, long long target,
+                                              long long store_lo, long long store_hi) {
+  const int t = threadIdx.x, NT = blockDim.x;
+  const unsigned M = MT_RING - 1;
+  const unsigned long long gm = (unsigned long long)(c.rng_ring_words - 1);
+#pragma unroll 1
+  while (G < target) {
+    // the expanded form needs 1078 words of history that were themselves generated
+    const bool wide = (G - lo >= 1078) && (G >= 1078 + MT_N);
+    const int width = wide ? MT_N - 1 : MT_N - MT_M;
+#pragma unroll 1
+    for (int i = t; i < width; i += NT) {
+      const long long a = G + i;
+      const unsigned n = (unsigned)a;
+      uint32_t v;
+      if (wide)
+        v = x[(n - 681) & M] ^ mt_twist(x[(n - 1078) & M], x[(n - 1077) & M]) ^
+            mt_twist(x[(n - 851) & M], x[(n - 850) & M]) ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
+      else
+        v = x[(n - 227) & M] ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
+      x[n & M] = v;
+      if (a >= store_lo && a < store_hi) c.rng_ring[(unsigned long long)a & gm] = v;
+    }
+    __syncthreads();
+    G += width;
   }
+  return G;
+}
+
+// Serial producer (one CTA): make sure words [.., target) are in the ring.
+__device__ __noinline__ void rng_produce_serial(const bh_ctx& c, uint32_t* x, long long target) {
+  const int t = threadIdx.x, NT = blockDim.x;
   __syncthreads();
-  {
-    int kk = 2 * (MT_N - MT_M) + t;  // 454 .. 623
-    if (kk < MT_N - 1) x[MT_N + kk] = x[MT_N + kk - (MT_N - MT_M)] ^ mt_twist(x[kk], x[kk + 1]);
-    if (kk == MT_N - 1) x[MT_N + kk] = x[MT_N + kk - (MT_N - MT_M)] ^ mt_twist(x[kk], x[MT_N]);
-  }
+  const long long G0 = c.rng64[R_PRODUCED];
+  if (G0 >= target) return;
+  const long long hist = G0 < 1078 + MT_N ? G0 : 1078 + MT_N;
+  const long long lo = G0 - hist;
+#pragma unroll 1
+  for (long long a = lo + t; a < G0; a += NT) x[(unsigned)a & (MT_RING - 1)] = rng_word(c, a);
+  __syncthreads();
+  const long long G = mt_generate(c, x, lo, G0, target, G0, 0x7fffffffffffffffLL);
+  if (t == 0) c.rng64[R_PRODUCED] = G;
   __syncthreads();
 }
 
-#define MT_RING 2048  // shared-memory ring of stream words (power of two >= 1078 + 623)
-
-// Emit `count` doubles to out[0..count) continuing the stream at (key, *pos_io).
-// Whole CTA (blockDim.x >= 256 threads); x is shared memory of MT_RING words.
-//
-// The stream is kept as a ring of raw words indexed by absolute position.  After one
-// classic block (to have 1078 words of history) it is extended 623 words per barrier
-// with the recurrence expanded three times,
-//     x[n] = x[n-681] ^ f(n-1078) ^ f(n-851) ^ f(n-624),  f(m) = twist(x[m], x[m+1]),
-// whose operands all precede a 623-word wave.  Any 624 consecutive stream words are a
-// valid np.random key, so the final state is the last 624 words generated plus the
-// offset of the first unconsumed one.
-__device__ __noinline__ void mt_fill_block(uint32_t* x, uint32_t* key, int* pos_io, double* out, long long count) {
+// Parallel producer: chunk p of the current plan (whole CTA, blockDim.x >= 960).
+// smem: RNG_CHUNK_SMEM bytes.
+__device__ __noinline__ void rng_chunk(const bh_ctx& c, uint32_t* smem, int p) {
+  uint32_t* s_win = smem;                    // [RNG_WIN_PAD]
+  uint32_t* x = smem + RNG_WIN_PAD;          // [MT_RING]
+  uint32_t* s_out = x + MT_RING;             // [MT_N]
   const int t = threadIdx.x, NT = blockDim.x;
-  const unsigned M = MT_RING - 1;
+  const long long base = c.rng64[R_PLAN_BASE];
+  const long long cb = base + (long long)p * RNG_CHUNK;
 #pragma unroll 1
-  for (int i = t; i < MT_N; i += NT) x[i] = key[i];
-  const long long p = *pos_io;           // absolute index of the first unconsumed word
-  const long long need_end = p + 2 * count;
-  long long G = MT_N;                    // words available: [0, G)
-  long long done = 0;                    // doubles emitted so far
+  for (int i = t; i < RNG_WIN_PAD; i += NT) s_win[i] = i < RNG_WINDOW ? rng_word(c, base - RNG_WINDOW + i) : 0u;
+#pragma unroll 1
+  for (int i = t; i < MT_N; i += NT) s_out[i] = 0u;
   __syncthreads();
-#define MT_EMIT()                                                                          \
-  do {                                                                                     \
-    long long upto_ = G > p ? (G - p) / 2 : 0;                                             \
-    if (upto_ > count) upto_ = count;                                                      \
-    _Pragma("unroll 1") for (long long q = done + t; q < upto_; q += NT) {                 \
-      const unsigned w_ = (unsigned)(p + 2 * q);                                           \
-      const uint32_t a_ = mt_temper(x[w_ & M]) >> 5, b_ = mt_temper(x[(w_ + 1) & M]) >> 6; \
-      out[q] = ((double)a_ * 67108864.0 + (double)b_) * (1.0 / 9007199254740992.0);        \
-    }                                                                                      \
-    done = upto_ > done ? upto_ : done;                                                    \
-  } while (0)
-  MT_EMIT();
-  if (need_end > G) {  // classic regeneration of one block: words [624, 1248)
-    mt_next_block(x);
-    G = 2 * MT_N;
-    MT_EMIT();
-  }
+  // out[j] = XOR_{i : g[i]} win[i + j].  6 groups of 156 threads split the 624 words of
+  // g; thread q of a group keeps outputs 4q..4q+3 and slides a register window over win.
+  if (t < 936) {
+    const int grp = t / 156, q = t - grp * 156;
+    const uint32_t* gp = c.mt_jump + (long long)p * MT_N;
+    uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
 #pragma unroll 1
-  while (need_end > G) {  // 623 independent words per barrier
-#pragma unroll 1
-    for (int i = t; i < MT_N - 1; i += NT) {
-      const unsigned n = (unsigned)G + i;
-      x[n & M] = x[(n - 681) & M] ^ mt_twist(x[(n - 1078) & M], x[(n - 1077) & M]) ^
-                 mt_twist(x[(n - 851) & M], x[(n - 850) & M]) ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
+    for (int wi = grp * 104; wi < grp * 104 + 104; ++wi) {
+      const uint32_t gw = __ldg(gp + wi);
+      if (gw == 0u) continue;
+      const uint4* wp = reinterpret_cast<const uint4*>(s_win + 32 * wi + 4 * q);
+      uint32_t r[36];
+#pragma unroll
+      for (int m = 0; m < 9; ++m) {
+        const uint4 v = wp[m];
+        r[4 * m] = v.x;
+        r[4 * m + 1] = v.y;
+        r[4 * m + 2] = v.z;
+        r[4 * m + 3] = v.w;
+      }
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        if (gw & (1u << b)) {
+          a0 ^= r[b];
+          a1 ^= r[b + 1];
+          a2 ^= r[b + 2];
+          a3 ^= r[b + 3];
+        }
+      }
     }
-    __syncthreads();
-    G += MT_N - 1;
-    MT_EMIT();
+    atomicXor(&s_out[4 * q], a0);
+    atomicXor(&s_out[4 * q + 1], a1);
+    atomicXor(&s_out[4 * q + 2], a2);
+    atomicXor(&s_out[4 * q + 3], a3);
   }
-#undef MT_EMIT
   __syncthreads();
-  const long long start = G - MT_N;
+  const unsigned long long gm = (unsigned long long)(c.rng_ring_words - 1);
 #pragma unroll 1
-  for (int i = t; i < MT_N; i += NT) key[i] = x[(unsigned)(start + i) & M];
-  if (t == 0) *pos_io = (int)(need_end - start);
+  for (int j = t; j < MT_N; j += NT) {
+    const uint32_t v = s_out[j];
+    x[(unsigned)(cb + j) & (MT_RING - 1)] = v;
+    c.rng_ring[(unsigned long long)(cb + j) & gm] = v;
+  }
+  __syncthreads();
+  mt_generate(c, x, cb, cb + MT_N, cb + RNG_CHUNK, cb + MT_N, cb + RNG_CHUNK);
+}
+
+// All CTAs: run the chunks of the pending plan (b of nb).  The plan is committed
+// (PRODUCED advanced) by the next rng_commit_plan on the drawing CTA.
+__device__ __forceinline__ void ph_rng_chunks(const bh_ctx& c, uint32_t* smem, int b, int nb) {
+  const int n = (int)c.rng64[R_PLAN_CHUNKS];
+#pragma unroll 1
+  for (int p = b; p < n; p += nb) {
+    rng_chunk(c, smem, p);
+    __syncthreads();
+  }
+}
+
+// Single thread of the drawing CTA: fold a finished parallel plan into PRODUCED.
+__device__ __forceinline__ void rng_commit_plan(const bh_ctx& c) {
+  const long long n = c.rng64[R_PLAN_CHUNKS];
+  if (n > 0) {
+    c.rng64[R_PRODUCED] = c.rng64[R_PLAN_BASE] + n * RNG_CHUNK;
+    c.rng64[R_PLAN_CHUNKS] = 0;
+  }
+}
+
+// Largest number of doubles a draw starting at `cursor` may take so that the words of the
+// current step (from step_base on), the jump window and one round of chunks fit the ring.
+__device__ __forceinline__ long long rng_room(const bh_ctx& c, long long step_base, long long cursor) {
+  const long long cap = c.rng_ring_words / 2 - (cursor - step_base);
+  return cap > 0 ? cap / 2 : 0;
+}
+
+// One CTA.  Take `count` doubles at the cursor (thread 0 publishes *off_slot / *n_slot) and
+// make sure they -- plus `lookahead` more words -- are produced, serially when the
+// deficit is small, else by planning chunks for ph_rng_chunks (which must run next).
+// `x` = MT_RING words of shared memory.  Returns through shared state only.
+__device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long count, int off_slot, int n_slot,
+                                      bool first_of_step, long long lookahead, bool may_plan) {
+  __shared__ long long s_serial_target;
+  if (threadIdx.x == 0) {
+    long long* r = c.rng64;
+    rng_commit_plan(c);
+    const long long cur = r[R_CURSOR];
+    if (first_of_step) r[R_STEP_BASE] = cur;
+    const long long room = rng_room(c, r[R_STEP_BASE], cur);
+    if (count > room) {
+      count = room;
+      atomicOr(&c.sc[BH_SC_STATUS], BH_ST_RAND_OVERFLOW);
+    }
+    r[off_slot] = cur;
+    if (n_slot >= 0) r[n_slot] = count;
+    const long long end = cur + 2 * count;
+    r[R_CURSOR] = end;
+    long long la = lookahead;
+    if (la > c.rng_ring_words / 4) la = c.rng_ring_words / 4;
+    const long long target = end + la + MT_N;  // keep 624 words past the cursor for state export
+    long long produced = r[R_PRODUCED];
+    long long serial_target = target;
+    if (may_plan && c.jump_polys > 0 && target - produced > RNG_PAR_MIN) {
+      // the window must consist of generated words (absolute index >= 1)
+      const long long need = produced < 1 + RNG_WINDOW ? 1 + RNG_WINDOW : produced;
+      long long chunks = (target - need + RNG_CHUNK - 1) / RNG_CHUNK;
+      if (chunks > c.jump_polys) chunks = c.jump_polys;  // the rest is produced serially by later draws
+      if (chunks > 0) {
+        serial_target = need;
+        r[R_PLAN_BASE] = need;  // == PRODUCED after the serial part below
+        r[R_PLAN_CHUNKS] = chunks;
+      }
+    }
+    s_serial_target = serial_target;
+  }
+  __syncthreads();
+  rng_produce_serial(c, x, s_serial_target);
+  if (threadIdx.x == 0 && c.rng64[R_PLAN_CHUNKS] > 0) c.rng64[R_PLAN_BASE] = c.rng64[R_PRODUCED];
+  __syncthreads();
+}
+
+// Host state -> ring (single CTA): key = words [0, 624), cursor = pos.
+__device__ __forceinline__ void ph_rng_import(const bh_ctx& c) {
+#pragma unroll 1
+  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) c.rng_ring[i] = c.mt_key[i];
+  if (threadIdx.x == 0) {
+    long long* r = c.rng64;
+    r[R_PRODUCED] = MT_N;
+    r[R_CURSOR] = c.sc[BH_SC_MT_POS];
+    r[R_PLAN_CHUNKS] = 0;
+    r[R_STEP_BASE] = c.sc[BH_SC_MT_POS];
+  }
+}
+
+// State at the cursor as (624 key words, pos): out[i] = key word i, out[624] = pos.
+// Threads gid of gsz cooperate; requires PRODUCED >= CURSOR and PRODUCED >= 624 (always
+// true after an import) and no uncommitted plan covering the cursor.
+__device__ __forceinline__ void rng_export(const bh_ctx& c, int* out, int gid, int gsz) {
+  const long long n = c.rng64[R_PLAN_CHUNKS];
+  const long long produced = n > 0 ? c.rng64[R_PLAN_BASE] + n * RNG_CHUNK : c.rng64[R_PRODUCED];
+  const long long cur = c.rng64[R_CURSOR];
+  const long long start = cur < produced - MT_N ? cur : produced - MT_N;
+#pragma unroll 1
+  for (int i = gid; i <= MT_N; i += gsz) out[i] = i < MT_N ? (int)rng_word(c, start + i) : (int)(cur - start);
 }

@@ -51,12 +51,14 @@ __device__ __forceinline__ LearnTotals learn_totals(const bh_ctx& c, int learnin
 
 // ---------------------------------------------------------------------------------
 // Random draws.  which = 1: rand(k, c) (networks.py:87); 2: rand(L, W+1)
-// (projections.py:120); 3: rand(M) (projections.py:235).  One CTA.  `nw` is the
-// number of CTAs that ran the ranged phases (for the per-CTA count arrays).
+// (projections.py:120); 3: rand(M) (projections.py:235).  One CTA takes the range of
+// the stream (mt19937.cuh); `nw` is the number of CTAs that ran the ranged phases
+// (for the per-CTA count arrays).  Draw #2 may leave a parallel production plan that
+// ph_rng_chunks (all CTAs) must run before the values are read.
 // ---------------------------------------------------------------------------------
 __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, int nw) {
   __shared__ uint32_t x[MT_RING];
-  __shared__ long long s_count, s_dst;
+  __shared__ long long s_count;
   __shared__ int s_red[32];
   int m_before = 0, m_total = 0;
   LearnTotals lt;
@@ -66,13 +68,10 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
   if (threadIdx.x == 0) {
     int* sc = c.sc;
     const int cur = sc[BH_SC_STEP] & 1;
-    long long count = 0, dst = 0;
+    long long count = 0;
     if (which == 1) {
       count = (long long)c.active_columns * c.cell_dim;
-      dst = 0;
-      sc[BH_SC_OFF2] = (int)count;
     } else if (which == 2) {
-      dst = sc[BH_SC_OFF2];
       if (learning && sc[BH_SC_HAVE_PREV]) count = (long long)lt.L * (sc[BH_SC_W0 + (cur ^ 1)] + 1);
     } else {
       int M = m_total;
@@ -82,30 +81,48 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
       }
       sc[BH_SC_M] = M;
       count = M;
-      dst = sc[BH_SC_OFF3];
     }
-    if (dst + count > c.rand_capacity) {
-      atomicOr(&sc[BH_SC_STATUS], BH_ST_RAND_OVERFLOW);
-      count = c.rand_capacity > dst ? c.rand_capacity - dst : 0;
-    }
-    if (which == 2) sc[BH_SC_OFF3] = (int)(dst + count);
-    sc[BH_SC_RAND_FILL] = (int)(dst + count);
     s_count = count;
-    s_dst = dst;
   }
   __syncthreads();
-  mt_fill_block(x, c.mt_key, &c.sc[BH_SC_MT_POS], c.rand_buf + s_dst, s_count);
-  __syncthreads();
+  if (which == 1) rng_draw(c, x, s_count, R_OFF1, -1, true, 0, false);
+  else if (which == 2) rng_draw(c, x, s_count, R_OFF2, R_N2, false, c.rng_lookahead, true);
+  else rng_draw(c, x, s_count, R_OFF3, R_N3, false, 0, false);
 }
 
 __global__ void __launch_bounds__(MT_THREADS) k_tm_draw(const __grid_constant__ bh_ctx c, int which, int learning) {
   ph_draw(c, which, learning, c.tm_blocks);
 }
 
-// Plain stream fill (bh_rng_fill)
-__global__ void __launch_bounds__(MT_THREADS) k_rng_fill(const __grid_constant__ bh_ctx c, double* dst, long long count) {
+// chunks of the production plan draw #2 may have left (no-op without one)
+__global__ void __launch_bounds__(MT_THREADS, 1) k_rng_chunks(const __grid_constant__ bh_ctx c) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  ph_rng_chunks(c, s_dyn, blockIdx.x, gridDim.x);
+}
+
+// bh_rng_fill: take `count` doubles at the cursor (one CTA; may leave a plan for
+// k_rng_chunks), then convert them (any grid).
+__global__ void __launch_bounds__(MT_THREADS) k_rng_fill_draw(const __grid_constant__ bh_ctx c, long long count) {
   __shared__ uint32_t x[MT_RING];
-  mt_fill_block(x, c.mt_key, &c.sc[BH_SC_MT_POS], dst, count);
+  rng_draw(c, x, count, R_OFF1, R_N2, true, 0, true);
+}
+
+__global__ void k_rng_fill_copy(const __grid_constant__ bh_ctx c, double* dst) {
+  const long long off = c.rng64[R_OFF1], n = c.rng64[R_N2];
+#pragma unroll 1
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+    dst[q] = rng_uniform(c, off + 2 * q);
+}
+
+__global__ void k_rng_import(const __grid_constant__ bh_ctx c) { ph_rng_import(c); }
+
+__global__ void k_rng_export(const __grid_constant__ bh_ctx c) {
+  __shared__ int s_out[MT_N + 1];
+  rng_export(c, s_out, threadIdx.x, blockDim.x);
+  __syncthreads();
+#pragma unroll 1
+  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) c.mt_key[i] = (uint32_t)s_out[i];
+  if (threadIdx.x == 0) c.sc[BH_SC_MT_POS] = s_out[MT_N];
 }
 
 // ---------------------------------------------------------------------------------
@@ -122,7 +139,7 @@ __device__ void ph_select_a(const bh_ctx& c, int b, int nb) {
   const bool have_prev = c.sc[BH_SC_HAVE_PREV] != 0;
   const int* act = c.active_cols + cur * k;
   const int* prev = c.active_cols + (cur ^ 1) * k;
-  const double* rnd = c.rand_buf;  // draw #1 sits at offset 0
+  const long long off1 = c.rng64[R_OFF1];  // draw #1: rand(k, c), row-major
   const Range rg = block_range(k, b, nb);
   int n_win = 0, n_un = 0;
   #pragma unroll 1
@@ -139,7 +156,7 @@ __device__ void ph_select_a(const bh_ctx& c, int b, int nb) {
     bool best = have_prev && in && fabsf(__fsub_rn(mj, colmax)) < c.epsilon;
     // least used (networks.py:85-88): f32(f64(count) + u)
     float x = INFINITY;
-    if (in) x = __double2float_rn(__dadd_rn((double)c.cell_nseg[cell], rnd[(long long)r * cd + lane]));
+    if (in) x = __double2float_rn(__dadd_rn((double)c.cell_nseg[cell], rng_uniform(c, off1 + 2 * ((long long)r * cd + lane))));
     float rowmin = warp_min(x);
     bool least = in && fabsf(__fsub_rn(x, rowmin)) < c.epsilon;
     bool predbit = (pred >> lane) & 1u;
@@ -365,13 +382,13 @@ __device__ void grow_row(const bh_ctx& c, int row, int s, int n, int n_add, int 
     if (wi >= 0) atomicOr(&s_excl[wi >> 5], 1u << (wi & 31));
   }
   __syncthreads();
-  const double* pr = c.rand_buf + off2 + (long long)row * (Wp + 1);  // row of rand(L, W+1)
+  const long long pr = off2 + 2 * (long long)row * (Wp + 1);  // stream index of this row of rand(L, W+1)
   // candidates: previous winners not yet on the segment with priority < 1.0 (:121-123)
   int nc = 0;
   #pragma unroll 1
   for (int w = t; w < Wp; w += NT) {
     bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
-    float pri = pr_ok ? __double2float_rn(pr[w]) : 2.0f;
+    float pri = pr_ok ? __double2float_rn(rng_uniform(c, pr + 2 * w)) : 2.0f;
     nc += (!ex && pri < 1.0f) ? 1 : 0;
   }
   nc = block_sum(nc, s_red);
@@ -393,7 +410,7 @@ __device__ void grow_row(const bh_ctx& c, int row, int s, int n, int n_add, int 
       #pragma unroll 1
       for (int w = t; w < Wp; w += NT) {
         bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
-        float pri = __double2float_rn(pr[w]);
+        float pri = __double2float_rn(rng_uniform(c, pr + 2 * w));
         uint32_t bits = __float_as_uint(pri);
         if (!ex && pri < 1.0f && (bits & hi_mask) == prefix) atomicAdd(&s_hist[(bits >> shift) & 0xff], 1);
       }
@@ -421,7 +438,7 @@ __device__ void grow_row(const bh_ctx& c, int row, int s, int n, int n_add, int 
     uint32_t bits = 0u;
     if (w < Wp) {
       bool ex = (s_excl[w >> 5] >> (w & 31)) & 1u;
-      float pri = pr_ok ? __double2float_rn(pr[w]) : 2.0f;
+      float pri = pr_ok ? __double2float_rn(rng_uniform(c, pr + 2 * w)) : 2.0f;
       bits = __float_as_uint(pri);
       cand = !ex && pri < 1.0f;
     }
@@ -462,8 +479,8 @@ __device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb)
   const int cur = c.sc[BH_SC_STEP] & 1;
   const int Wp = c.sc[BH_SC_W0 + (cur ^ 1)];
   const int* prevw = c.winners + (long long)(cur ^ 1) * c.active_columns * cd;
-  const long long off2 = c.sc[BH_SC_OFF2];
-  const long long rand_fill = c.sc[BH_SC_RAND_FILL];
+  const long long off2 = c.rng64[R_OFF2];
+  const long long n2 = c.rng64[R_N2];  // doubles draw #2 obtained (capacity-clamped)
   const int sample = c.seg_sampling_synapses;
   const int cap = sample < Wp ? sample : Wp;
 
@@ -520,7 +537,7 @@ __device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb)
     const int ng = s_ngrow;
     for (int g = 0; g < ng; ++g) {
       const int grow = s_grow_row[g];
-      const bool pr_ok = off2 + (long long)(grow + 1) * (Wp + 1) <= rand_fill;
+      const bool pr_ok = (long long)(grow + 1) * (Wp + 1) <= n2;
       grow_row(c, grow, c.learn_list[grow], s_grow_n[g], s_grow_add[g], Wp, prevw, off2, pr_ok, s_excl, s_red,
                s_hist, &s_rem, &s_prefix);
     }
@@ -644,8 +661,8 @@ __device__ void ph_activate_b(const bh_ctx& c, int b, int nb) {
   const int NT = blockDim.x;
   const int S = c.sc[BH_SC_NSEG];
   const int thr = c.seg_matching_threshold;
-  const long long off3 = c.sc[BH_SC_OFF3];
-  const long long rand_fill = c.sc[BH_SC_RAND_FILL];
+  const long long off3 = c.rng64[R_OFF3];
+  const long long n3 = c.rng64[R_N3];
   int m_before, m_total;
   blk_prefix(BLK(c, BLK_MATCH), b, nb, s_red, m_before, m_total);
   const Range rg = block_range(S, b, nb);
@@ -661,7 +678,7 @@ __device__ void ph_activate_b(const bh_ctx& c, int b, int nb) {
     base += tot;
     if (match && rank < c.match_capacity) {
       const int conn = c.seg_conn[s];
-      const double u = (off3 + rank < rand_fill) ? c.rand_buf[off3 + rank] : 0.0;
+      const double u = rank < n3 ? rng_uniform(c, off3 + 2 * rank) : 0.0;
       const float jit = __double2float_rn(__dadd_rn((double)pot, u));
       const int owner = c.seg_owner[s];
       c.m_seg[rank] = s;
@@ -715,9 +732,7 @@ __device__ void ph_summary(const bh_ctx& c, int b, int nb) {
     out[4 + 2 * k + i] = (int)c.row_act[i];
     out[4 + 3 * k + i] = (int)c.row_win[i];
   }
-  #pragma unroll 1
-  for (int i = gid; i <= BH_MT_N; i += gsz)
-    out[4 + 4 * k + i] = i < BH_MT_N ? (int)c.mt_key[i] : c.sc[BH_SC_MT_POS];
+  rng_export(c, out + 4 + 4 * k, gid, gsz);  // MT19937 state at the stream cursor
 }
 
 __global__ void k_summary(const __grid_constant__ bh_ctx c) { ph_summary(c, blockIdx.x, gridDim.x); }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 1
+#define BH_ABI_VERSION 2
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 8192
@@ -54,10 +54,11 @@ enum {
   BH_SC_NU,            /* winners with no matching segment (unaccounted)           */
   BH_SC_NR,            /* recycled segments this step                              */
   BH_SC_STATUS,        /* BH_ST_* bits                                             */
-  BH_SC_MT_POS,        /* MT19937 position inside mt_key (0..624)                  */
-  BH_SC_RAND_FILL,     /* doubles currently in rand_buf for this step              */
-  BH_SC_OFF2,          /* offset of draw #2 (rand(L, W+1)) in rand_buf             */
-  BH_SC_OFF3,          /* offset of draw #3 (rand(M)) in rand_buf                  */
+  BH_SC_MT_POS,        /* position inside mt_key (0..624) of an imported/exported   */
+                       /* MT19937 state (bh_rng_import / bh_rng_export)             */
+  BH_SC_RESERVED0,
+  BH_SC_RESERVED1,
+  BH_SC_RESERVED2,
   BH_SC_INPUT_POS,     /* cursor into the device input ring (bh_step_ring)         */
   BH_SC_BAR_COUNT,     /* grid barrier of the fused kernel: arrivals               */
   BH_SC_BAR_GEN,       /*                                   generation             */
@@ -69,7 +70,7 @@ enum {
 #define BH_ST_SYN_OVERFLOW 2   /* a segment needed more than syn_capacity slots    */
 #define BH_ST_MATCH_OVERFLOW 4 /* more matching segments than match_capacity       */
 #define BH_ST_LEARN_OVERFLOW 8 /* more learning rows than learn_capacity           */
-#define BH_ST_RAND_OVERFLOW 16 /* a step drew more uniforms than rand_capacity     */
+#define BH_ST_RAND_OVERFLOW 16 /* a step drew more uniforms than the stream ring holds */
 #define BH_ST_PRI_TIE 32       /* equal priorities straddled a growth cut (the     */
                                /* reference's np.argsort is undefined there)       */
 
@@ -87,13 +88,17 @@ typedef struct bh_ctx {
   int32_t learn_capacity;  /* L_cap                                                */
   int32_t tm_blocks;       /* NB: CTAs of the ranged TM kernels (<= 1024)          */
   int32_t sm_count;        /* SMs of the device (grid sizing)                      */
-  int64_t rand_capacity;   /* doubles in rand_buf                                  */
+  int64_t rng_ring_words;  /* words in rng_ring: a power of two >= 2^20; one step may   */
+                           /* draw at most rng_ring_words / 4 doubles                  */
   int32_t col_lo;          /* column shard: first global column owned by this rank  */
   int32_t col_local;       /* columns owned (C when not sharded); the SP buffers    */
                            /* sp_perm/sp_mask/duty/overlaps/boosted are local-sized */
   int32_t ring_len;        /* rows in input_ring (0 = none)                        */
   int32_t fused_mode;      /* bh_step*: 0 = one kernel per stage, 1 = one kernel on a  */
                            /* thread-block cluster, 2 = one cooperative-grid kernel   */
+  int32_t jump_polys;      /* rows of mt_jump (0 = the stream is produced by one CTA)  */
+  int32_t rng_lookahead;   /* stream words draw #2 produces beyond its own need (the   */
+                           /* following rand(M) and next step's rand(k, c))            */
 
   /* ---- constants, evaluated on the host with the reference's expressions ----- */
   double sp_threshold;     /* projections.py:19  permanence >= threshold           */
@@ -159,9 +164,12 @@ typedef struct bh_ctx {
   int32_t* blk;            /* [8][1024] per-CTA counts for ordered compaction      */
   int32_t* topk_ws;        /* [BH_TOPK_WS_INTS] workspace of the multi-CTA top-k   */
 
-  /* ---- randomness: legacy MT19937 stream of np.random, advanced on the device - */
-  uint32_t* mt_key;        /* [624]                                                */
-  double* rand_buf;        /* [rand_capacity] uniforms of the current step         */
+  /* ---- randomness: legacy MT19937 stream of np.random, produced on the device -- */
+  uint32_t* mt_key;        /* [624] staging of an imported / exported state         */
+  uint32_t* rng_ring;      /* [rng_ring_words] raw stream words by absolute index   */
+  uint32_t* mt_jump;       /* [jump_polys][624] jump polynomials (caller-filled,    */
+                           /* bithtm_b200/_mtjump.py) for multi-CTA production      */
+  long long* rng64;        /* [16] producer / consumer cursors (csrc/mt19937.cuh)   */
 
   /* ---- scalars, input ring, host staging ---------------------------------------- */
   int32_t* sc;             /* [BH_SC_COUNT]                                        */
@@ -276,8 +284,13 @@ int bh_profile_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int lear
 int bh_step_launches(const bh_ctx* ctx, int learning);
 
 /* ---- randomness ------------------------------------------------------------------------ */
-/* Append `count` float64 uniforms of the MT19937 stream (np.random.random_sample)
- * to dst_dev and advance the device state (mt_key, sc[BH_SC_MT_POS]). */
+/* Adopt the MT19937 state the caller wrote to ctx->mt_key / sc[BH_SC_MT_POS]
+ * (np.random.get_state()): the device stream continues from it. */
+int bh_rng_import(const bh_ctx* ctx, void* stream);
+/* Write the state at the device's stream cursor to ctx->mt_key / sc[BH_SC_MT_POS]. */
+int bh_rng_export(const bh_ctx* ctx, void* stream);
+/* Take the next `count` float64 uniforms of the stream (np.random.random_sample)
+ * into dst_dev; count <= rng_ring_words / 4. */
 int bh_rng_fill(const bh_ctx* ctx, double* dst_dev, int64_t count, void* stream);
 
 /* ---- test hooks ------------------------------------------------------------------------- */

@@ -82,7 +82,7 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(nat.lib, name), f"{name} not exported"
     assert declared == set(nat.EXPORTED), declared ^ set(nat.EXPORTED)
     assert nat.lib.bh_ctx_size() == ctypes.sizeof(nat.BhCtx)
-    assert nat.lib.bh_abi_version() == 1
+    assert nat.lib.bh_abi_version() == nat.ABI_VERSION
 
 
 def test_layout_without_device():
@@ -94,7 +94,7 @@ def test_layout_without_device():
     ctx.column_dim, ctx.cell_dim, ctx.active_columns = 2048, 32, 41
     ctx.col_lo, ctx.col_local = 0, 2048
     ctx.seg_capacity, ctx.syn_capacity, ctx.match_capacity, ctx.learn_capacity = 1 << 16, 128, 1 << 16, 1 << 17
-    ctx.tm_blocks, ctx.rand_capacity = 148, 1 << 20
+    ctx.tm_blocks, ctx.rng_ring_words = 148, 1 << 20
     n = nat.lib.bh_layout(ctypes.byref(ctx), None)
     perm_bytes = 2048 * 1024 * 8
     syn_bytes = (1 << 16) * 128 * 8
@@ -122,3 +122,25 @@ def test_no_gpu_fails_loudly():
 
     with pytest.raises(nat.NativeError):
         bithtm_b200.HierarchicalTemporalMemory(64, 128, 8, 10)
+
+
+def test_mt19937_jump_polynomials():
+    """The characteristic polynomial and the jump polynomials the device generator uses
+    (bithtm_b200/_mtjump.py) reproduce a simulated MT19937 stream."""
+    from bithtm_b200 import _mtjump
+
+    assert len(_mtjump.PHI) == 135 and _mtjump.PHI[-1] == 19937
+    assert _mtjump.self_check(seed=11, polys=3)
+    key = np.random.RandomState(4).get_state()[1]
+    x = _mtjump.raw_stream(key.astype(np.uint32), 3 * 624)
+    bg = np.random.MT19937()
+    bg.state = {"bit_generator": "MT19937", "state": {"key": key, "pos": 624}}
+    raw = bg.random_raw(1248).astype(np.uint32)
+
+    def temper(y):
+        y = y ^ (y >> np.uint32(11))
+        y = y ^ ((y << np.uint32(7)) & np.uint32(0x9D2C5680))
+        y = y ^ ((y << np.uint32(15)) & np.uint32(0xEFC60000))
+        return y ^ (y >> np.uint32(18))
+
+    assert np.array_equal(temper(x[624:624 + 1248]), raw)

@@ -41,6 +41,31 @@ def test_device_mt19937_matches_numpy_stream():
     assert np.array_equal(rs2.random_sample(1000), rs.random_sample(1000))
 
 
+def test_device_mt19937_parallel_production_matches_numpy_stream():
+    """Many-CTA production (jump-ahead polynomials, csrc/mt19937.cuh rng_chunk) yields the
+    same stream as the serial generator and as NumPy, from a fresh state (window not yet
+    generated), mid-stream, with odd word offsets, and exports the same state."""
+    eng = _engine(parallel_rng=True, rand_capacity=1 << 21)
+    assert eng.ctx.jump_polys > 0
+    rs = np.random.RandomState(777)
+    rs.randint(0, 10, size=1)  # odd word position
+    st = rs.get_state()
+    eng.set_rng_state(st[1], st[2])
+    for count in [600_000, 3, 40_000, 1_000_001, 0, 150_000, 2_000_000, 12]:
+        got = eng.rng_fill(count)
+        want = rs.random_sample(count)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), f"count {count}"
+    key, pos = eng.get_rng_state()
+    rs2 = np.random.RandomState()
+    rs2.set_state(("MT19937", key, pos, 0, 0.0))
+    assert np.array_equal(rs2.random_sample(1000), rs.random_sample(1000))
+    # re-import mid-way: the ring restarts from the 624-word key
+    st = rs.get_state()
+    eng.set_rng_state(st[1], st[2])
+    got = eng.rng_fill(300_000)
+    assert np.array_equal(got.view(np.uint64), rs.random_sample(300_000).view(np.uint64))
+
+
 def test_device_np_expf_matches_numpy():
     """The boost kernel's exp == np.exp(float32) bit for bit (regularizations.py:16)."""
     import ctypes
