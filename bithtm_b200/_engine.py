@@ -45,10 +45,15 @@ class Engine:
     def __init__(self, input_dim, column_dim, cell_dim, active_columns, *, device=None,
                  max_segments=None, max_synapses_per_segment=128, match_capacity=None,
                  learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
-                 fused="auto", fused_ctas=None, column_shard=None, parallel_rng="auto"):
+                 fused="auto", fused_ctas=None, column_shard=None, parallel_rng="auto", segment_shard=None,
+                 exchange_match_capacity=None, exchange_recycle_capacity=None):
         """``column_shard=(rank, world)``: this engine owns columns
         [rank*C/world, (rank+1)*C/world) of the spatial pooler (permanence, mask, duty
-        cycles); the temporal memory is replicated."""
+        cycles).  ``segment_shard=(rank, world)``: it holds the synapse rows of the
+        segments whose 64-id block is dealt to ``rank`` (the per-cell state and the
+        temporal-memory bookkeeping are replicated; one exchange per step, see
+        ``include/bithtm_b200.h``).  Without ``segment_shard`` the temporal memory is
+        replicated whole."""
         torch = _torch()
         self.device = require_cuda(device)
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -84,6 +89,15 @@ class Engine:
             if Ccol % self.shard_world:
                 raise ValueError("column_dim must be divisible by the number of column shards")
             fused = "off"  # the all-gather sits between kernels
+        if segment_shard is None:
+            self.seg_rank, self.seg_world = 0, 1
+        else:
+            self.seg_rank, self.seg_world = int(segment_shard[0]), int(segment_shard[1])
+            fused = "off"  # the exchange sits between kernels
+        ctx.seg_rank, ctx.seg_world = self.seg_rank, self.seg_world
+        if self.seg_world > 1:
+            ctx.xm_cap = int(exchange_match_capacity or min(int(match_capacity), 8 * k + 1024))
+            ctx.xr_cap = int(exchange_recycle_capacity or (2 * k + 64))
         ctx.col_local = Ccol // self.shard_world
         ctx.col_lo = self.shard_rank * ctx.col_local
         self.C_local, self.col_lo = ctx.col_local, ctx.col_lo
@@ -145,6 +159,10 @@ class Engine:
             tab = _mtjump.jump_table(ctx.jump_polys, cache_dir=os.path.dirname(nat.LIB_PATH))
             self.buf["mt_jump"].copy_(torch.from_numpy(tab.view(np.int32).reshape(-1)).to(self.device))
         nat.check(nat.lib.bh_init(C.byref(ctx), self.stream), "bh_init")
+        if self.seg_world > 1:  # this rank's exchange record / the gathered records of all ranks
+            n = int(nat.lib.bh_tm_shard_xch_ints(C.byref(ctx)))
+            self.xch_send = torch.zeros(n, dtype=torch.int32, device=self.device)
+            self.xch_recv = torch.zeros(n * self.seg_world, dtype=torch.int32, device=self.device)
         self.epoch = 0  # bumped by every completed step; lazily fetched State fields check it
         self._graphs = {}
         self.host_graph = True  # bh_step_host as one CUDA graph launch (constants are frozen at capture)
@@ -155,14 +173,17 @@ class Engine:
         C_, I, c, k = x.column_dim, x.input_dim, x.cell_dim, x.active_columns
         CL = x.col_local
         N, S, E, M = C_ * 32, x.seg_capacity, x.syn_capacity, x.match_capacity  # device cell id = col*32+cell
+        W = max(1, x.seg_world)
+        rows = S if W == 1 else ((S + 63) // 64 + W - 1) // W * 64  # locally held synapse rows
+        self.seg_rows = rows
         return {
             "sp_perm": CL * I, "sp_mask": CL * x.mask_stride, "duty": CL, "overlaps": CL, "boosted": CL,
             "active_cols": 2 * k, "col_active": C_, "col_pred": C_, "col_act": C_, "col_win": C_,
             "cell_nseg": N, "cell_maxjit": N, "cell_npred": N, "cell_widx": N,
-            "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": S * E, "syn_perm": S * E,
+            "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": rows * E, "syn_perm": rows * E,
             "row_pred": k, "row_act": k, "row_win": k, "row_unacc": k, "winners": 2 * k * c, "unacc": k * c,
             "m_seg": M, "m_conn": M, "m_jit": M, "m_flag": M, "learn_list": x.learn_capacity, "punish_list": M,
-            "blk": 8 * 1024, "topk_ws": 8192, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
+            "recyc_list": W * x.xr_cap if W > 1 else 0, "blk": 8 * 1024, "topk_ws": 8192, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
             "rng64": nat.R_COUNT, "sc": nat.SC_COUNT,
             "input_ring": x.ring_len * x.input_words, "input_dev": x.mask_stride,
             "summary_dev": nat.summary_ints(k),
@@ -186,6 +207,24 @@ class Engine:
         """A per-cell device array as the reference's flat [C * c] array."""
         a = self.buf[name].cpu().numpy().reshape(self.C, 32)[:, :self.c]
         return np.ascontiguousarray(a).reshape(-1)
+
+    # ------------------------------------------------------------------ segment shards
+    def held_segment_ids(self, S: int) -> np.ndarray:
+        """Ids < S of the segments whose synapse rows this rank stores, ascending (= local row order)."""
+        ids = np.arange(S, dtype=np.int64)
+        if self.seg_world > 1:
+            ids = ids[(ids >> 6) % self.seg_world == self.seg_rank]
+        return ids
+
+    def tm_shard_pre(self, learning=True):
+        nat.check(nat.lib.bh_tm_shard_pre(self.ref, int(bool(learning)), self.xch_send.data_ptr(), self.stream),
+                  "bh_tm_shard_pre")
+        return self.xch_send
+
+    def tm_shard_post(self, gathered):
+        assert gathered.numel() == self.xch_recv.numel() and gathered.dtype == self.xch_recv.dtype
+        nat.check(nat.lib.bh_tm_shard_post(self.ref, gathered.data_ptr(), self.stream), "bh_tm_shard_post")
+        self.epoch += 1
 
     def scalars(self) -> np.ndarray:
         return self.buf["sc"].cpu().numpy()

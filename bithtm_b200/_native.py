@@ -14,24 +14,28 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libbithtm_b200.so")
 
 MT_N = 624
-ABI_VERSION = 2
+ABI_VERSION = 3
 R_COUNT = 16  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)
 (SC_STEP, SC_HAVE_PREV, SC_NSEG, SC_NSEG_NEXT, SC_M, SC_W0, SC_W1, SC_L0, SC_L, SC_P, SC_NU, SC_NR,
- SC_STATUS, SC_MT_POS, SC_RESERVED0, SC_RESERVED1, SC_RESERVED2, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN) = range(20)
+ SC_STATUS, SC_MT_POS, SC_X_MATCH, SC_X_RECYC_AVAIL, SC_X_RECYC_TOTAL, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN) = range(20)
 SC_COUNT = 32
 
 ST_SEG_OVERFLOW, ST_SYN_OVERFLOW, ST_MATCH_OVERFLOW, ST_LEARN_OVERFLOW, ST_RAND_OVERFLOW, ST_PRI_TIE = 1, 2, 4, 8, 16, 32
+ST_XCH_OVERFLOW = 64
 ST_NAMES = {
     ST_SEG_OVERFLOW: "segment capacity exceeded (max_segments)",
     ST_SYN_OVERFLOW: "synapse slots per segment exceeded (max_synapses_per_segment)",
     ST_MATCH_OVERFLOW: "matching-segment list capacity exceeded",
     ST_LEARN_OVERFLOW: "learning-segment list capacity exceeded",
     ST_RAND_OVERFLOW: "a step drew more random numbers than the stream ring holds (rng_ring_words / 4 doubles)",
+    ST_XCH_OVERFLOW: "segment shards: more matching / recyclable segments on a rank than the exchange carries "
+                     "(exchange_match_capacity / exchange_recycle_capacity)",
     ST_PRI_TIE: "equal growth priorities straddled a selection cut (reference-undefined tie)",
 }
-ST_FATAL = ST_SEG_OVERFLOW | ST_SYN_OVERFLOW | ST_MATCH_OVERFLOW | ST_LEARN_OVERFLOW | ST_RAND_OVERFLOW
+ST_FATAL = (ST_SEG_OVERFLOW | ST_SYN_OVERFLOW | ST_MATCH_OVERFLOW | ST_LEARN_OVERFLOW | ST_RAND_OVERFLOW
+            | ST_XCH_OVERFLOW)
 
 
 def summary_ints(k: int) -> int:
@@ -51,7 +55,9 @@ class BhCtx(C.Structure):
         ("seg_capacity", C.c_int32), ("syn_capacity", C.c_int32), ("match_capacity", C.c_int32),
         ("learn_capacity", C.c_int32), ("tm_blocks", C.c_int32), ("sm_count", C.c_int32),
         ("rng_ring_words", C.c_int64), ("col_lo", C.c_int32), ("col_local", C.c_int32),
-        ("ring_len", C.c_int32), ("fused_mode", C.c_int32), ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32),
+        ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
+        ("seg_rank", C.c_int32), ("seg_world", C.c_int32), ("xm_cap", C.c_int32), ("xr_cap", C.c_int32),
+        ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32),
         ("sp_threshold", C.c_double), ("sp_delta_on", C.c_double), ("sp_delta_off", C.c_double),
         ("tm_learn_on", C.c_double), ("tm_learn_off", C.c_double),
         ("tm_punish_on", C.c_double), ("tm_punish_off", C.c_double),
@@ -70,7 +76,7 @@ class BhCtx(C.Structure):
         ("row_pred", _P), ("row_act", _P), ("row_win", _P), ("row_unacc", _P),
         ("winners", _P), ("unacc", _P),
         ("m_seg", _P), ("m_conn", _P), ("m_jit", _P), ("m_flag", _P),
-        ("learn_list", _P), ("punish_list", _P), ("blk", _P), ("topk_ws", _P),
+        ("learn_list", _P), ("punish_list", _P), ("recyc_list", _P), ("blk", _P), ("topk_ws", _P),
         ("mt_key", _P), ("rng_ring", _P), ("mt_jump", _P), ("rng64", _P),
         ("sc", _P), ("input_ring", _P), ("input_dev", _P), ("input_pinned", _P),
         ("summary_dev", _P), ("summary_pinned", _P),
@@ -86,7 +92,7 @@ DEVICE_BUFFERS = {
     "syn_cell": "int32", "syn_perm": "float32",
     "row_pred": "int32", "row_act": "int32", "row_win": "int32", "row_unacc": "int32",
     "winners": "int32", "unacc": "int32", "m_seg": "int32", "m_conn": "int32", "m_jit": "float32",
-    "m_flag": "uint8", "learn_list": "int32", "punish_list": "int32", "blk": "int32", "topk_ws": "int32",
+    "m_flag": "uint8", "learn_list": "int32", "punish_list": "int32", "recyc_list": "int32", "blk": "int32", "topk_ws": "int32",
     "mt_key": "int32", "rng_ring": "int32", "mt_jump": "int32", "rng64": "int64", "sc": "int32", "input_ring": "int32", "input_dev": "int32",
     "summary_dev": "int32",
 }
@@ -109,6 +115,9 @@ _SIGNATURES = {
     "bh_sp_step": (C.c_int, [_CTXP, _P, C.c_int, _P]),
     "bh_sp_shard_local": (C.c_int, [_CTXP, _P, _P, _P, _P]),
     "bh_sp_shard_finish": (C.c_int, [_CTXP, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "bh_tm_shard_xch_ints": (C.c_size_t, [_CTXP]),
+    "bh_tm_shard_pre": (C.c_int, [_CTXP, C.c_int, _P, _P]),
+    "bh_tm_shard_post": (C.c_int, [_CTXP, _P, _P]),
     "bh_advance_step": (C.c_int, [_CTXP, _P]),
     "bh_tm_select": (C.c_int, [_CTXP, _P]),
     "bh_tm_learn": (C.c_int, [_CTXP, C.c_int, _P]),

@@ -9,6 +9,11 @@ column) can be applied to it on every rank identically.  The temporal memory is
 replicated: every rank computes it from the same active-column list and the same
 MT19937 stream, so no second exchange is needed and results are bit-identical to the
 single-GPU run by construction.
+
+Segment sharding of the temporal memory (``segment_shard``) distributes the synapse
+rows -- the HBM-heavy part -- by segment id and adds ONE more exchange per timestep:
+``gather_records`` all-gathers each rank's fixed-size record of matching segments and
+lowest recyclable segment ids (see ``include/bithtm_b200.h``).
 """
 
 from __future__ import annotations
@@ -48,3 +53,29 @@ def gather_columns(local, group=None):
     parts = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(parts, local.contiguous(), group=group)
     return torch.cat(parts)
+
+
+def gather_records(send, recv, group=None):
+    """All-gather the per-rank exchange records (int32, equal sizes) in rank order into
+    ``recv``.  CUDA tensors (NCCL) or CPU tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    assert recv.numel() == world * send.numel()
+    if send.is_cuda:
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send, group=group)
+        recv.copy_(torch.cat(parts))
+    return recv
+
+
+def merge_segment_parts(parts):
+    """Per-rank (ids, count, cells, perm) of the held segments -> arrays ordered by segment id."""
+    import numpy as np
+
+    ids = np.concatenate([p[0] for p in parts])
+    order = np.argsort(ids, kind="stable")
+    return tuple(np.concatenate([p[i] for p in parts])[order] for i in range(1, 4))

@@ -8,6 +8,7 @@
 #include "sp_kernels.cuh"
 #include "tm_kernels.cuh"
 #include "fused.cuh"
+#include "tm_shard.cuh"
 
 #define CU_RET(expr)                                   \
   do {                                                 \
@@ -78,8 +79,11 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->seg_count, S);
   cv.take(x->seg_pot, S);
   cv.take(x->seg_conn, S);
-  cv.take(x->syn_cell, S * E);
-  cv.take(x->syn_perm, S * E);
+  // segment shards: rows of the 64-id blocks dealt to this rank (round-robin)
+  const size_t W = x->seg_world > 1 ? x->seg_world : 1;
+  const size_t rows = W > 1 ? ((S + 63) / 64 + W - 1) / W * 64 : S;
+  cv.take(x->syn_cell, rows * E);
+  cv.take(x->syn_perm, rows * E);
   cv.take(x->row_pred, k);
   cv.take(x->row_act, k);
   cv.take(x->row_win, k);
@@ -92,6 +96,7 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->m_flag, M);
   cv.take(x->learn_list, (size_t)x->learn_capacity);
   cv.take(x->punish_list, M);
+  cv.take(x->recyc_list, W > 1 ? W * (size_t)x->xr_cap : 0);
   cv.take(x->blk, (size_t)BLK_ROWS * BH_BLK_STRIDE);
   cv.take(x->topk_ws, (size_t)BH_TOPK_WS_INTS);
   cv.take(x->mt_key, (size_t)BH_MT_N);
@@ -118,6 +123,10 @@ static int check_ctx(const bh_ctx* x) {
   if (x->syn_capacity < 32 || x->syn_capacity % 32 != 0) return BH_E_BADARG;
   if (x->rng_ring_words < (1 << 20) || (x->rng_ring_words & (x->rng_ring_words - 1))) return BH_E_BADARG;
   if (x->jump_polys < 0 || x->rng_lookahead < 0) return BH_E_BADARG;
+  if (x->seg_world > 1) {
+    if (x->seg_rank < 0 || x->seg_rank >= x->seg_world || x->xm_cap < 1 || x->xr_cap < 1) return BH_E_BADARG;
+    if (x->fused_mode) return BH_E_UNSUPPORTED;  // the exchange sits between kernels
+  }
   return 0;
 }
 
@@ -364,6 +373,7 @@ extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
 }
 
 extern "C" int bh_tm_activate(const bh_ctx* x, void* stream) {
+  if (x->seg_world > 1) return BH_E_UNSUPPORTED;  // use bh_tm_shard_pre / bh_tm_shard_post
   cudaStream_t st = S_(stream);
   int k = x->active_columns, kc = k * x->cell_dim;
   k_tm_post<<<cdiv(kc, 256) < 256 ? cdiv(kc, 256) : 256, 256, 0, st>>>(*x);
@@ -374,6 +384,45 @@ extern "C" int bh_tm_activate(const bh_ctx* x, void* stream) {
   LAUNCHED("tm_draw3");
   k_tm_activate_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
   LAUNCHED("tm_activate_b");
+  return 0;
+}
+
+// ---- segment shards: exchange 2 ----------------------------------------------------------
+extern "C" size_t bh_tm_shard_xch_ints(const bh_ctx* x) { return x ? (size_t)xch_ints(*x) : 0; }
+
+static int tm_post_and_scan(const bh_ctx* x, cudaStream_t st) {
+  int k = x->active_columns, kc = k * x->cell_dim;
+  k_tm_post<<<cdiv(kc, 256) < 256 ? cdiv(kc, 256) : 256, 256, 0, st>>>(*x);
+  LAUNCHED("tm_post");
+  k_tm_activate_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  LAUNCHED("tm_activate_a");
+  return 0;
+}
+
+extern "C" int bh_tm_shard_pre(const bh_ctx* x, int learning, int32_t* send_dev, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (x->seg_world <= 1 || !send_dev) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  if ((rc = bh_tm_select(x, stream))) return rc;
+  if ((rc = bh_tm_learn(x, learning, stream))) return rc;
+  if ((rc = tm_post_and_scan(x, st))) return rc;
+  k_tm_shard_pack<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, send_dev);
+  LAUNCHED("tm_shard_pack");
+  return 0;
+}
+
+extern "C" int bh_tm_shard_post(const bh_ctx* x, const int32_t* recv_dev, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (x->seg_world <= 1 || !recv_dev) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  k_tm_shard_merge<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, recv_dev);
+  LAUNCHED("tm_shard_merge");
+  k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 3, 1);
+  LAUNCHED("tm_draw3");
+  k_tm_activate_finish<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  LAUNCHED("tm_activate_finish");
   return 0;
 }
 

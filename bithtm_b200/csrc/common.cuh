@@ -109,6 +109,25 @@ __device__ __forceinline__ bool cell_bit(const uint32_t* col_words, int cell) {
   return (col_words[cell >> 5] >> (cell & 31)) & 1u;
 }
 
+// ------------------------------------------------------------------------------------
+// segment shards: ids are dealt to ranks in blocks of 64 (block b -> rank b % world);
+// a rank stores the synapse rows of its segments compactly, in ascending id order.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool seg_held(const bh_ctx& c, int s) {
+  return c.seg_world <= 1 || ((s >> 6) % c.seg_world) == c.seg_rank;
+}
+__device__ __forceinline__ int seg_row(const bh_ctx& c, int s) {  // local row of a held segment
+  return c.seg_world <= 1 ? s : ((((s >> 6) / c.seg_world) << 6) | (s & 63));
+}
+__device__ __forceinline__ int seg_gid(const bh_ctx& c, int row) {  // segment id of a local row
+  return c.seg_world <= 1 ? row : ((((row >> 6) * c.seg_world + c.seg_rank) << 6) | (row & 63));
+}
+__device__ __forceinline__ int seg_local_count(const bh_ctx& c, int S) {  // held ids below S
+  if (c.seg_world <= 1) return S;
+  const int nblk = S >> 6, rem = S & 63, q = nblk / c.seg_world, r = nblk % c.seg_world;
+  return (q + (c.seg_rank < r ? 1 : 0)) * 64 + (c.seg_rank == r ? rem : 0);
+}
+
 __device__ __forceinline__ uint32_t low_mask(int c) { return c >= 32 ? 0xffffffffu : ((1u << c) - 1u); }
 
 // ------------------------------------------------------------------------------------

@@ -37,6 +37,10 @@ __device__ __forceinline__ LearnTotals learn_totals(const bh_ctx& c, int learnin
   blk_prefix(BLK(c, BLK_PUNISH), b, nb, s_red, t.p_before, t.P);
   int R;
   blk_prefix(BLK(c, BLK_RECYC), b, nb, s_red, t.r_before, R);
+  if (c.seg_world > 1) {  // segment shards: candidates come merged from the exchange (tm_shard.cuh)
+    R = c.sc[BH_SC_X_RECYC_AVAIL];
+    t.r_before = 0;
+  }
   const int S = c.sc[BH_SC_NSEG];
   t.n_u = (learning && c.sc[BH_SC_HAVE_PREV]) ? c.sc[BH_SC_NU] : 0;
   t.n_r = t.n_u < R ? t.n_u : R;  // projections.py:80-81: recycle first
@@ -74,7 +78,7 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
     } else if (which == 2) {
       if (learning && sc[BH_SC_HAVE_PREV]) count = (long long)lt.L * (sc[BH_SC_W0 + (cur ^ 1)] + 1);
     } else {
-      int M = m_total;
+      int M = c.seg_world > 1 ? sc[BH_SC_X_MATCH] : m_total;
       if (M > c.match_capacity) {
         M = c.match_capacity;
         atomicOr(&sc[BH_SC_STATUS], BH_ST_MATCH_OVERFLOW);
@@ -258,7 +262,7 @@ __device__ void ph_learn_select_a(const bh_ctx& c, int learning, int b, int nb) 
     nl += f & 1;
     np += (f >> 1) & 1;
   }
-  if (learning && c.sc[BH_SC_HAVE_PREV]) {
+  if (learning && c.sc[BH_SC_HAVE_PREV] && c.seg_world <= 1) {
     const int S = c.sc[BH_SC_NSEG], thr = c.seg_matching_threshold;
     const Range sr = block_range(S, b, nb);
     #pragma unroll 1
@@ -309,8 +313,24 @@ __device__ void ph_learn_select_b(const bh_ctx& c, int learning, int b, int nb) 
       }
     }
   }
+  if (lt.n_u > 0 && c.seg_world > 1) {
+    // segment shards: the merged ascending list of recyclable ids (every rank identically)
+    #pragma unroll 1
+    for (int i = b * NT + threadIdx.x; i < lt.n_r; i += nb * NT) {
+      const int s = c.recyc_list[i], newo = c.unacc[i];
+      atomicSub(&c.cell_nseg[c.seg_owner[s]], 1);
+      atomicAdd(&c.cell_nseg[newo], 1);
+      c.seg_owner[s] = newo;
+      c.seg_count[s] = 0;
+      const int pos = lt.L0 + i;
+      if (pos < c.learn_capacity) c.learn_list[pos] = s;
+    }
+    if (b == 0 && threadIdx.x == 0 && lt.n_u > c.sc[BH_SC_X_RECYC_AVAIL] &&
+        c.sc[BH_SC_X_RECYC_TOTAL] > c.sc[BH_SC_X_RECYC_AVAIL])
+      atomicOr(&c.sc[BH_SC_STATUS], BH_ST_XCH_OVERFLOW);  // a rank had more candidates than it could send
+  }
   if (lt.n_u > 0) {
-    if (lt.r_before < lt.n_u) {
+    if (lt.r_before < lt.n_u && c.seg_world <= 1) {
       const Range sr = block_range(S, b, nb);
       int rbase = lt.r_before;
       #pragma unroll 1
@@ -370,8 +390,8 @@ __device__ void ph_learn_select_b(const bh_ctx& c, int learning, int b, int nb) 
 __device__ void grow_row(const bh_ctx& c, int row, int s, int n, int n_add, int Wp, const int* prevw, long long off2,
                          bool pr_ok, uint32_t* s_excl, int* s_red, int* s_hist, int* s_rem, uint32_t* s_prefix) {
   const int t = threadIdx.x, NT = blockDim.x, E = c.syn_capacity;
-  int* cells = c.syn_cell + (long long)s * E;
-  float* perms = c.syn_perm + (long long)s * E;
+  int* cells = c.syn_cell + (long long)seg_row(c, s) * E;
+  float* perms = c.syn_perm + (long long)seg_row(c, s) * E;
   const int excl_words = (Wp + 31) >> 5;
   #pragma unroll 1
   for (int i = t; i < excl_words; i += NT) s_excl[i] = 0u;
@@ -490,14 +510,15 @@ __device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb)
     __syncthreads();
     // ---- stage 1: one warp per row (rows interleaved over CTAs) -------------------
     const int row = base_row + warp * nb + b;
-    if (row < L + P) {
+    const int s_row = row < L + P ? (row < L ? c.learn_list[row] : c.punish_list[row - L]) : 0;
+    if (row < L + P && seg_held(c, s_row)) {  // segment shards: only the rows stored here
       const bool learn = row < L;
-      const int s = learn ? c.learn_list[row] : c.punish_list[row - L];
+      const int s = s_row;
       const double d_on = learn ? c.tm_learn_on : c.tm_punish_on;
       const double d_off = learn ? c.tm_learn_off : c.tm_punish_off;
       const bool can_delete = learn ? c.tm_learn_can_delete : c.tm_punish_can_delete;
-      int* cells = c.syn_cell + (long long)s * E;
-      float* perms = c.syn_perm + (long long)s * E;
+      int* cells = c.syn_cell + (long long)seg_row(c, s) * E;
+      float* perms = c.syn_perm + (long long)seg_row(c, s) * E;
       const int n = c.seg_count[s];
       int kept = 0, n_act = 0;
       #pragma unroll 1
@@ -595,12 +616,13 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
   const int thr = c.seg_matching_threshold;
   const float pthr = c.tm_perm_threshold;
   const uint32_t* col_act = c.col_act;
-  const Range rg = block_range(S, b, nb);
-  int nm = 0;
+  const Range rg = block_range(seg_local_count(c, S), b, nb);  // local rows (== segment ids when not sharded)
+  int nm = 0, nrec = 0;
 #pragma unroll 1
   for (int s0 = rg.begin + warp * ACT_BATCH; s0 < rg.end; s0 += warps * ACT_BATCH) {
     // counts of the batch with one load, then slots [0, 64) of every row at once
-    const int my_n = (lane < ACT_BATCH && s0 + lane < rg.end) ? c.seg_count[s0 + lane] : 0;
+    const int my_n = (lane < ACT_BATCH && s0 + lane < rg.end) ? c.seg_count[seg_gid(c, s0 + lane)] : 0;
+    if (lane < ACT_BATCH && s0 + lane < rg.end && my_n < thr) ++nrec;  // recyclable (projections.py:80)
     int n[ACT_BATCH], cell[ACT_BATCH][2];
     float perm[ACT_BATCH][2];
 #pragma unroll
@@ -642,14 +664,19 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
         }
       }
       if (lane == 0 && s0 + j < rg.end) {
-        c.seg_pot[s0 + j] = pot;
-        c.seg_conn[s0 + j] = conn;
+        const int sid = seg_gid(c, s0 + j);
+        c.seg_pot[sid] = pot;
+        c.seg_conn[sid] = conn;
         nm += pot >= thr ? 1 : 0;
       }
     }
   }
   int tm = block_sum(nm, s_red);
   if (threadIdx.x == 0) BLK(c, BLK_MATCH)[b] = tm;
+  if (c.seg_world > 1) {  // segment shards: per-CTA count of recyclable local rows for ph_shard_pack
+    int tr = block_sum(nrec, s_red);
+    if (threadIdx.x == 0) BLK(c, BLK_RECYC)[b] = tr;
+  }
 }
 
 // Phase B: matching list in ascending segment id (np.where, projections.py:247),

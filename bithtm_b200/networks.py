@@ -346,8 +346,14 @@ class TemporalMemory:
         if not on_device:
             eng_set_active(eng, sp_state.active_column if active_column is None else active_column)
         self._rng.before(eng)
-        nat.check(nat.lib.bh_tm_step(eng.ref, int(bool(learning)), eng.stream), "bh_tm_step")
-        eng.epoch += 1
+        if eng.seg_world > 1:  # segment shards: local scan, ONE all-gather, merge (see _shard.py)
+            from ._shard import gather_records
+
+            send = eng.tm_shard_pre(learning)
+            eng.tm_shard_post(gather_records(send, eng.xch_recv, self.distal_projection._group))
+        else:
+            nat.check(nat.lib.bh_tm_step(eng.ref, int(bool(learning)), eng.stream), "bh_tm_step")
+            eng.epoch += 1
         summary = eng.summary()
         self._rng.after(eng, summary)
         return self._finish(summary)
@@ -358,12 +364,14 @@ class HierarchicalTemporalMemory:
 
     def __init__(self, input_dim, column_dim, cell_dim, active_columns=None, spatial_pooler=None,
                  temporal_memory=None, rng_sync="step", device=None, column_shard=None, process_group=None,
-                 **engine_kwargs):
-        """Extensions (keyword-only in spirit): ``column_shard=True`` shards the spatial
-        pooler's columns over the ranks of ``process_group`` (default: the world group of an
-        initialised torch.distributed; every rank must construct the network after the same
-        ``np.random.seed`` and feed the same inputs).  Other keyword arguments size the
-        device buffers (see ``Engine``)."""
+                 segment_shard=None, **engine_kwargs):
+        """Extensions (keyword-only in spirit): ``column_shard=True`` shards the network over
+        the ranks of ``process_group`` (default: the world group of an initialised
+        torch.distributed; every rank must construct the network after the same
+        ``np.random.seed`` and feed the same inputs): the spatial pooler by column and --
+        unless ``segment_shard=False`` -- the temporal memory's synapse rows by segment id.
+        ``(rank, world)`` tuples select a shard explicitly (single-process tests).  Other
+        keyword arguments size the device buffers (see ``Engine``)."""
         if active_columns is None:
             active_columns = round(column_dim * 0.02)  # :136-137
         self.input_dim = input_dim
@@ -389,8 +397,16 @@ class HierarchicalTemporalMemory:
             else:
                 shard = tuple(column_shard)
             sp._group = process_group
+        if segment_shard is None:
+            segment_shard = shard is not None
+        if segment_shard is True:
+            segment_shard = shard
+        seg = tuple(segment_shard) if segment_shard else None
+        if seg is not None and seg[1] <= 1:
+            seg = None
+        tm.distal_projection._group = process_group
         self._engine = Engine(input_dim, column_dim, cell_dim, sp.active_columns, device=device,
-                              column_shard=shard, **engine_kwargs)
+                              column_shard=shard, segment_shard=seg, **engine_kwargs)
         sp._attach(self._engine)
         tm._attach(self._engine)
 
@@ -406,7 +422,7 @@ class HierarchicalTemporalMemory:
         the packed input, the whole step on the device, one D2H of the step summary)."""
         sp, tm, eng = self.spatial_pooler, self.temporal_memory, self._engine
         is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
-        if not sp._native_inhibition or not is_host or eng.shard_world > 1:
+        if not sp._native_inhibition or not is_host or eng.shard_world > 1 or eng.seg_world > 1:
             sp_state = sp.process(input, learning=learning)
             sp_state._group = sp._group
             tm_state = tm.process(sp_state, learning=learning)

@@ -155,8 +155,22 @@ class PredictiveProjection:
 
         @property
         def segment_potential(self):  # :246 int64 [S]
-            return self._get("segment_potential",
-                             lambda: self._engine.buf["seg_pot"][:self._S].cpu().numpy().astype(np.int64))
+            def fetch():
+                eng = self._engine
+                pot = eng.buf["seg_pot"][:self._S].cpu().numpy().astype(np.int64)
+                if eng.seg_world > 1:  # COLLECTIVE: each rank scanned only the segments it stores
+                    import torch
+                    import torch.distributed as dist
+
+                    held = np.zeros(self._S, dtype=np.int64)
+                    ids = eng.held_segment_ids(self._S)
+                    held[ids] = pot[ids]
+                    t = torch.from_numpy(held).to(eng.device)
+                    dist.all_reduce(t, group=self._p._group)
+                    pot = t.cpu().numpy()
+                return pot
+
+            return self._get("segment_potential", fetch)
 
         @property
         def matching_segment(self):  # :247 int64 [M], ascending
@@ -202,6 +216,7 @@ class PredictiveProjection:
         self.segment_matching_threshold = segment_matching_threshold
         self.segment_sampling_synapses = segment_sampling_synapses
         self._engine = None
+        self._group = None  # torch.distributed group of the segment shards
 
     @staticmethod
     def _deltas(active_change, inactive_change):
@@ -252,19 +267,41 @@ class PredictiveProjection:
         eng = self._engine
         return eng.cells_to_flat(eng.buf["seg_owner"][:S].cpu().numpy()).astype(np.int32).reshape(S, 1)
 
-    def export_segments(self):
-        """(owner[S], count[S], cells[S, E], perm[S, E]) with free slots = -1 / -1.0 --
-        the row form ``oracle.digest.canonical_from_rows`` and an export shim consume."""
+    def export_local_segments(self):
+        """(ids, count, cells, perm) of the segments whose synapse rows THIS rank stores
+        (all of them when not segment-sharded), ids ascending."""
         S = self.n_segments
         eng = self._engine
         E = eng.ctx.syn_capacity
-        owner = eng.cells_to_flat(eng.buf["seg_owner"][:S].cpu().numpy())
-        count = eng.buf["seg_count"][:S].cpu().numpy()
-        cells = eng.cells_to_flat(eng.buf["syn_cell"][:S * E].cpu().numpy()).reshape(S, E)
-        perm = eng.buf["syn_perm"][:S * E].cpu().numpy().reshape(S, E).copy()
+        ids = eng.held_segment_ids(S)
+        n = len(ids)
+        count = eng.buf["seg_count"][:S].cpu().numpy()[ids]
+        cells = eng.cells_to_flat(eng.buf["syn_cell"][:n * E].cpu().numpy()).reshape(n, E)
+        perm = eng.buf["syn_perm"][:n * E].cpu().numpy().reshape(n, E).copy()
         free = np.arange(E)[None, :] >= count[:, None]
         cells[free] = -1
         perm[free] = -1.0
+        return ids, count, cells, perm
+
+    def export_segments(self, parts=None):
+        """(owner[S], count[S], cells[S, E], perm[S, E]) with free slots = -1 / -1.0 --
+        the row form ``oracle.digest.canonical_from_rows`` and an export shim consume.
+        Segment-sharded: a COLLECTIVE (every rank contributes its rows), unless the
+        per-rank ``export_local_segments()`` results are passed as ``parts``."""
+        S = self.n_segments
+        eng = self._engine
+        owner = eng.cells_to_flat(eng.buf["seg_owner"][:S].cpu().numpy())
+        if eng.seg_world == 1:
+            _, count, cells, perm = self.export_local_segments()
+            return owner, count, cells, perm
+        from ._shard import merge_segment_parts
+
+        if parts is None:
+            import torch.distributed as dist
+
+            parts = [None] * eng.seg_world
+            dist.all_gather_object(parts, self.export_local_segments(), group=self._group)
+        count, cells, perm = merge_segment_parts(parts)
         return owner, count, cells, perm
 
     @property

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 2
+#define BH_ABI_VERSION 3
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 8192
@@ -56,9 +56,9 @@ enum {
   BH_SC_STATUS,        /* BH_ST_* bits                                             */
   BH_SC_MT_POS,        /* position inside mt_key (0..624) of an imported/exported   */
                        /* MT19937 state (bh_rng_import / bh_rng_export)             */
-  BH_SC_RESERVED0,
-  BH_SC_RESERVED1,
-  BH_SC_RESERVED2,
+  BH_SC_X_MATCH,       /* segment shards: matching segments over all ranks (merged)  */
+  BH_SC_X_RECYC_AVAIL, /* recyclable segment ids received (merged, ascending)       */
+  BH_SC_X_RECYC_TOTAL, /* recyclable segments over all ranks (true count)           */
   BH_SC_INPUT_POS,     /* cursor into the device input ring (bh_step_ring)         */
   BH_SC_BAR_COUNT,     /* grid barrier of the fused kernel: arrivals               */
   BH_SC_BAR_GEN,       /*                                   generation             */
@@ -73,6 +73,8 @@ enum {
 #define BH_ST_RAND_OVERFLOW 16 /* a step drew more uniforms than the stream ring holds */
 #define BH_ST_PRI_TIE 32       /* equal priorities straddled a growth cut (the     */
                                /* reference's np.argsort is undefined there)       */
+#define BH_ST_XCH_OVERFLOW 64  /* segment shards: a rank had more matching or      */
+                               /* recyclable segments than the exchange carries    */
 
 typedef struct bh_ctx {
   /* ---- sizes --------------------------------------------------------------- */
@@ -96,6 +98,11 @@ typedef struct bh_ctx {
   int32_t ring_len;        /* rows in input_ring (0 = none)                        */
   int32_t fused_mode;      /* bh_step*: 0 = one kernel per stage, 1 = one kernel on a  */
                            /* thread-block cluster, 2 = one cooperative-grid kernel   */
+  int32_t seg_rank;        /* segment shard: this rank holds the synapse rows of the   */
+  int32_t seg_world;       /* segments whose 64-id block b has b % seg_world ==       */
+                           /* seg_rank (1 = all); syn_cell/syn_perm hold local rows   */
+  int32_t xm_cap;          /* exchange capacity per rank: matching segments           */
+  int32_t xr_cap;          /*                             recyclable segment ids      */
   int32_t jump_polys;      /* rows of mt_jump (0 = the stream is produced by one CTA)  */
   int32_t rng_lookahead;   /* stream words draw #2 produces beyond its own need (the   */
                            /* following rand(M) and next step's rand(k, c))            */
@@ -145,8 +152,9 @@ typedef struct bh_ctx {
   int32_t* seg_count;      /* [S_cap] output_edges       projections.py:42         */
   int32_t* seg_pot;        /* [S_cap] segment_potential  projections.py:246        */
   int32_t* seg_conn;       /* [S_cap] connected-active count                       */
-  int32_t* syn_cell;       /* [S_cap][E_cap] presynaptic cell (column * 32 + cell) */
-  float* syn_perm;         /* [S_cap][E_cap] float32 permanence                    */
+  int32_t* syn_cell;       /* [rows][E_cap] presynaptic cell (column * 32 + cell);  */
+  float* syn_perm;         /* [rows][E_cap] float32 permanence; rows = S_cap, or    */
+                           /* the locally held share of it (segment shards)         */
 
   /* ---- per-step lists ---------------------------------------------------------- */
   uint32_t* row_pred;      /* [k] prev prediction bits of each active column       */
@@ -161,6 +169,7 @@ typedef struct bh_ctx {
   uint8_t* m_flag;         /* [M_cap] bit0 learn, bit1 punish                      */
   int32_t* learn_list;     /* [L_cap] learning_segment (projections.py:281 order)  */
   int32_t* punish_list;    /* [M_cap] punished_segment                             */
+  int32_t* recyc_list;     /* [seg_world * xr_cap] segment shards: merged recyclable ids */
   int32_t* blk;            /* [8][1024] per-CTA counts for ordered compaction      */
   int32_t* topk_ws;        /* [BH_TOPK_WS_INTS] workspace of the multi-CTA top-k   */
 
@@ -229,6 +238,28 @@ int bh_sp_shard_local(const bh_ctx* ctx, const uint32_t* input_words_dev, double
                       int32_t* cand_cols_out, void* stream);
 int bh_sp_shard_finish(const bh_ctx* ctx, const uint32_t* input_words_dev, const double* cand_keys,
                        const int32_t* cand_cols, int n, int learning, void* stream);
+
+/* ---- segment-sharded temporal memory (exchange 2) ------------------------
+ * The synapse rows are distributed over seg_world ranks by segment id (blocks of 64 ids,
+ * round-robin); the small per-cell / per-column state and the segment owners are
+ * replicated, so bursting, winner selection and the learning bookkeeping run
+ * identically on every rank from the same inputs and the same MT19937 stream.  Per
+ * timestep ONE exchange is needed: after the segment scan each rank contributes its
+ * matching segments (id, potential, connected-active count; ascending id) and its
+ * lowest recyclable segment ids; the caller all-gathers these fixed-size records in rank
+ * order and every rank merges them into the global ascending lists the reference's
+ * orderings are defined on (projections.py:80-81, 235, 247, 281).
+ *
+ * bh_tm_shard_xch_ints: int32 per rank record.  Record layout: [0] matching count,
+ * [1] recyclable ids sent, [2] recyclable count (true), [3] status bits; id[xm_cap],
+ * potential[xm_cap], connected[xm_cap]; recyclable id[xr_cap].
+ * bh_tm_shard_pre : networks.py:95-119 + learning + the local segment scan; fills
+ *                   send_dev with this rank's record.
+ * bh_tm_shard_post: merges the seg_world gathered records (recv_dev, rank order), draws
+ *                   rand(M), computes jitter / predictions; completes the timestep. */
+size_t bh_tm_shard_xch_ints(const bh_ctx* ctx);
+int bh_tm_shard_pre(const bh_ctx* ctx, int learning, int32_t* send_dev, void* stream);
+int bh_tm_shard_post(const bh_ctx* ctx, const int32_t* recv_dev, void* stream);
 
 /* Complete a timestep when no temporal memory follows (stand-alone SpatialPooler):
  * sc[BH_SC_STEP] += 1 so the ping-pong buffers rotate. */

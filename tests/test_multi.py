@@ -38,7 +38,7 @@ def _gloo_worker(rank, world, port, result):
     import torch.distributed as dist
 
     _init(rank, world, port, "gloo")
-    from bithtm_b200._shard import gather_candidates, gather_columns
+    from bithtm_b200._shard import gather_candidates, gather_columns, gather_records
     from oracle.htm_oracle import canonical_topk
 
     g = np.random.default_rng(5)
@@ -57,6 +57,10 @@ def _gloo_worker(rank, world, port, result):
         ok &= np.array_equal(sel, canonical_topk(keys, k))
         full = gather_columns(torch.from_numpy(keys[lo:hi])).numpy()
         ok &= np.array_equal(full, keys)
+        # exchange 2: fixed-size int32 records, delivered in rank order
+        send = torch.full((7 + trial,), rank * 1000 + trial, dtype=torch.int32)
+        recv = gather_records(send, torch.zeros(world * send.numel(), dtype=torch.int32)).numpy()
+        ok &= np.array_equal(recv, np.repeat(np.arange(world) * 1000 + trial, send.numel()))
     flag = torch.tensor([int(ok)])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -164,7 +168,8 @@ def test_column_shard_single_process_emulation():
     shards = []
     for r in range(2):
         np.random.seed(seed)
-        shards.append(bithtm.HierarchicalTemporalMemory(I, C, c, k, column_shard=(r, 2), rng_sync="lazy"))
+        shards.append(bithtm.HierarchicalTemporalMemory(I, C, c, k, column_shard=(r, 2), rng_sync="lazy",
+                                                        segment_shard=False))  # replicated temporal memory
     orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
     for t in range(120):
         rec = orc.step(xs[t])
@@ -197,3 +202,98 @@ def test_column_shard_single_process_emulation():
         assert np.array_equal(ov, rec.overlaps)
     perm = np.concatenate([h.spatial_pooler.proximal_projection.permanence for h in shards])
     assert np.array_equal(perm.view(np.uint64), orc.permanence.view(np.uint64))
+
+
+# ----------------------------------------------------------------------------- segment shards, one GPU
+def _emulated_shards(info, world, **kw):
+    import bithtm_b200 as bithtm
+
+    shards = []
+    for r in range(world):
+        np.random.seed(info["seed"])
+        shards.append(bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"],
+                                                        column_shard=(r, world), rng_sync="lazy", **kw))
+    return shards
+
+
+def _emulated_step(shards, x, learning=True):
+    """One timestep of `world` shards living in ONE process: the two all-gathers are
+    torch.cat of the per-shard buffers (exactly what NCCL delivers, rank order)."""
+    import torch
+
+    from bithtm_b200 import _native as nat
+
+    cand = []
+    for h in shards:
+        eng = h.engine
+        h.spatial_pooler.boosting._bind(eng)
+        words = eng.pack_input(x)
+        keys = torch.empty(eng.k_local, dtype=torch.float64, device="cuda")
+        cols = torch.empty(eng.k_local, dtype=torch.int32, device="cuda")
+        nat.check(nat.lib.bh_sp_shard_local(eng.ref, words.data_ptr(), keys.data_ptr(), cols.data_ptr(), eng.stream))
+        cand.append((words, keys, cols))
+    all_keys = torch.cat([c[1] for c in cand])
+    all_cols = torch.cat([c[2] for c in cand])
+    for h, (words, _, _) in zip(shards, cand):
+        eng = h.engine
+        nat.check(nat.lib.bh_sp_shard_finish(eng.ref, words.data_ptr(), all_keys.data_ptr(), all_cols.data_ptr(),
+                                             int(all_keys.numel()), int(learning), eng.stream))
+        h.temporal_memory._rng.before(eng)
+    records = torch.cat([h.engine.tm_shard_pre(learning) for h in shards])  # exchange 2
+    states = []
+    for h in shards:
+        eng = h.engine
+        eng.tm_shard_post(records)
+        states.append(h.temporal_memory._finish(eng.summary()))
+    return states
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,world,steps", [("tiny", 2, 600), ("tiny", 4, 400), ("odd", 3, 750), ("mid", 2, 1100),
+                                              ("mid", 4, 950)])
+def test_segment_shards_single_process_emulation(name, world, steps):
+    """Column-sharded SP + segment-sharded TM, every shard in one process: each shard
+    reproduces the oracle's step records (winner/active cells, matching segments with
+    their jitter draws, segment counts) and together they hold the oracle's learned
+    state, including segments recycled across shards."""
+    import bithtm_b200 as bithtm  # noqa: F401
+    from bithtm_b200 import _native as nat
+    from helpers import golden_inputs, load_golden
+    from oracle.digest import canonical_from_rows, state_digest
+    from oracle.htm_oracle import HTMOracle, OracleConfig
+
+    info = load_golden(name)
+    I, C, c, k, seed = info["I"], info["C"], info["c"], info["k"], info["seed"]
+    xs = golden_inputs(info, steps)
+    shards = _emulated_shards(info, world)
+    assert all(h.engine.seg_world == world for h in shards)
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    recycled = 0
+    for t in range(steps):
+        rec = orc.step(xs[t])
+        states = _emulated_step(shards, xs[t])
+        for r, (h, st) in enumerate(zip(shards, states)):
+            where = f"step {t} shard {r}"
+            ds = st.distal_state
+            assert np.array_equal(st._active_column, rec.active_column), where
+            assert np.array_equal(st.winner_cell[0] * c + st.winner_cell[1], rec.winner_cell), where
+            assert np.array_equal(st.active_cell[0] * c + st.active_cell[1], rec.active_cell), where
+            assert st.n_segments == rec.n_segments, where
+            assert np.array_equal(ds.matching_segment, rec.matching_segment), where
+            assert np.array_equal(ds.matching_segment_activation, rec.matching_activation), where
+            assert np.array_equal(ds.matching_segment_jittered_potential.view(np.uint32),
+                                  np.asarray(rec.matching_jit, dtype=np.float32).view(np.uint32)), where
+        recycled += int(shards[0].engine.scalars()[nat.SC_NR])
+    # learned state: SP rows by column shard, synapse rows by segment shard
+    perm = np.concatenate([h.spatial_pooler.proximal_projection.permanence for h in shards])
+    duty = np.concatenate([h.spatial_pooler.boosting.duty_cycle for h in shards])
+    parts = [h.temporal_memory.distal_projection.export_local_segments() for h in shards]
+    for h in shards:
+        proj = h.temporal_memory.distal_projection
+        owner, count, cells, pm = proj.export_segments(parts=parts)
+        got = state_digest(perm, duty, proj.bundle_segments, canonical_from_rows(owner, cells, pm))
+        want = state_digest(orc.permanence, orc.duty, orc.cell_nseg, orc.canonical_synapses())
+        assert got == want
+    assert sum(len(p[0]) for p in parts) == orc.n_seg
+    if True:
+        assert recycled > 0, "the run never recycled a segment: the cross-shard path was not exercised"
