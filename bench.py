@@ -146,24 +146,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ roofline
-def algorithmic_bytes(cfg, name, sc_stats):
-    """Algorithmic bytes one launch of kernel `name` must move."""
-    C, I, k, c = cfg["column_dim"], cfg["input_dim"], cfg["active_columns"], cfg["cell_dim"]
-    S, syn, M, L, W = (sc_stats[n] for n in ("S", "synapses", "M", "L", "W"))
-    table = {
-        "sp_overlap_boost": C * I / 8 + I / 8 + 16 * C,          # mask + input + duty read, overlaps/boosted write
-        "topk": 8 * C + 4 * k,                                    # keys once + the k winners
-        "sp_learn": 16 * k * I + k * I / 8 + I / 8,               # fp64 RMW of k rows + their mask rows
-        "duty_update": 9 * C,
-        "tm_activate_a": 8 * syn + 12 * S,                        # every live synapse (cell+perm) once
-        "tm_learn_apply": 16 * L * 40 + 8 * L * (W + 1),          # learning rows RMW + their priority rows
-        "tm_draw2": 8 * L * (W + 1),
-    }
-    # the fused kernel moves the whole step (SURVEY.md 8d: SP + TM algorithmic bytes)
-    sp = C * I / 8 + I / 8 + 16 * k * I + k * I / 8 + 28 * C
-    tm = 8 * syn + 16 * L * 40 + 4 * (C * c) / 8 + 8 * (k * c + L * (W + 1) + M)
-    table["step_fused_cluster"] = table["step_fused_grid"] = sp + tm
-    return table.get(name)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from cfg3_kernels import algorithmic_bytes, network_stats  # noqa: E402  (shared with tools/cfg3_kernels.py)
 
 
 def nat_launches(eng):
@@ -256,11 +240,7 @@ def ours(args):
         flush.fill_(1)
         for name, ms in eng.profile_step(words, learning=True):
             prof[name] = prof.get(name, 0.0) + ms / n_prof
-    S = int(eng.scalars()[2])
-    counts = eng.buf["seg_count"][:S].cpu().numpy()
-    sc_now = eng.scalars()
-    stats = dict(S=S, synapses=int(counts.sum()), M=int(sc_now[4]), L=int(sc_now[8]),
-                 W=int(sc_now[5 + ((int(sc_now[0]) - 1) & 1)]))
+    stats = network_stats(eng)
     dominant = max(prof, key=prof.get)
     peaks = {}
     try:
@@ -312,11 +292,10 @@ def ours(args):
         # the HBM-bound kernels of the path at cfg3 size (65536 x 16384): the cfg2 step is
         # latency-bound, so kernel quality against the HBM roofline is shown here
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import sp_roofline
+            import cfg3_kernels
 
             torch.cuda.empty_cache()
-            hbm = sp_roofline.measure(65536, 16384, 20)
+            hbm = cfg3_kernels.measure(65536, 16384, 250, 20)
         except Exception as e:  # never lose the headline line
             hbm = {"error": repr(e)}
     if rank == 0:

@@ -105,19 +105,27 @@ class Engine:
         ctx.seg_capacity, ctx.syn_capacity = max_segments, _round_up(int(max_synapses_per_segment), 32)
         ctx.match_capacity, ctx.learn_capacity = int(match_capacity), int(learn_capacity)
         ctx.tm_blocks, ctx.sm_count = int(tm_blocks), self.sm_count
-        # the stream ring holds raw MT19937 words (2 per double); a step may use a quarter of it
-        ring_words = 1 << 20
-        while ring_words < 8 * int(rand_capacity):
-            ring_words <<= 1
-        ctx.rng_ring_words, ctx.ring_len = ring_words, int(ring_len)
-        # many-CTA stream production (jump-ahead polynomials) once a step draws enough words
+        # the stream ring holds raw MT19937 words (2 per float64 draw)
         from . import _mtjump
 
+        step_words = max(4 * int(rand_capacity), 1 << 18)  # most words one step may draw (2x margin)
         typical = 2 * (k * (k + 1) + 2 * k * c)
-        if parallel_rng == "auto":
+        if parallel_rng == "auto":  # many-CTA stream production once a step draws enough words
             parallel_rng = typical >= 8 * _mtjump.CHUNK_WORDS
-        ctx.jump_polys = (3 * ring_words // 4) // _mtjump.CHUNK_WORDS + 2 if parallel_rng else 0
-        ctx.rng_lookahead = min(2 * (k * c + 4 * k) + 2 * nat.MT_N, ring_words // 8) if parallel_rng else 0
+        need = 2 * step_words
+        if parallel_rng:
+            # history for the sparse chunk start (csrc/mt19937.cuh): 19937 << s words, where 623 << s
+            # covers one step's production
+            depth = _mtjump.DEGREE
+            while depth // _mtjump.DEGREE * _mtjump.MAX_SHIFT <= typical + 2 * _mtjump.CHUNK_WORDS:
+                depth *= 2
+            need = max(need, depth + 2 * step_words)
+        ring_words = 1 << 20
+        while ring_words < need:
+            ring_words <<= 1
+        ctx.rng_ring_words, ctx.rng_step_words, ctx.ring_len = ring_words, step_words, int(ring_len)
+        ctx.jump_polys = (step_words + step_words // 2) // _mtjump.CHUNK_WORDS + 3 if parallel_rng else 0
+        ctx.rng_lookahead = min(2 * (k * c + 4 * k) + 2 * nat.MT_N, step_words // 2) if parallel_rng else 0
         # whole step as one kernel: on one thread-block cluster while the step is
         # latency-bound (mask <= 8 MiB), else on a cooperative grid with one CTA per SM
         if fused == "auto":

@@ -82,14 +82,21 @@ def jump_table(n_polys: int, cache_dir: str | None = None) -> np.ndarray:
     n_polys = int(n_polys)
     path = None
     if cache_dir:
-        path = os.path.join(cache_dir, f"mtjump_w{WINDOW_WORDS}_j{CHUNK_WORDS}_n{n_polys}.npy")
-        if os.path.exists(path):
-            try:
-                tab = np.load(path)
-                if tab.shape == (n_polys, MT_N) and tab.dtype == np.uint32:
-                    return tab
-            except Exception:
-                pass
+        prefix = f"mtjump_w{WINDOW_WORDS}_j{CHUNK_WORDS}_n"
+        path = os.path.join(cache_dir, f"{prefix}{n_polys}.npy")
+        try:  # any cached table with at least n_polys rows will do (row p does not depend on the count)
+            cached = sorted((int(f[len(prefix):-4]), f) for f in os.listdir(cache_dir)
+                            if f.startswith(prefix) and f.endswith(".npy") and f[len(prefix):-4].isdigit())
+        except OSError:
+            cached = []
+        for n, f in cached:
+            if n >= n_polys:
+                try:
+                    tab = np.load(os.path.join(cache_dir, f))
+                    if tab.shape == (n, MT_N) and tab.dtype == np.uint32:
+                        return np.ascontiguousarray(tab[:n_polys])
+                except Exception:
+                    pass
     tab = np.zeros((n_polys, MT_N), dtype=np.uint32)
     g = power_of_t(WINDOW_WORDS)
     for p in range(n_polys):

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libbithtm_b200.so")
 
 MT_N = 624
-ABI_VERSION = 3
+ABI_VERSION = 4
 R_COUNT = 16  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)
@@ -29,7 +29,7 @@ ST_NAMES = {
     ST_SYN_OVERFLOW: "synapse slots per segment exceeded (max_synapses_per_segment)",
     ST_MATCH_OVERFLOW: "matching-segment list capacity exceeded",
     ST_LEARN_OVERFLOW: "learning-segment list capacity exceeded",
-    ST_RAND_OVERFLOW: "a step drew more random numbers than the stream ring holds (rng_ring_words / 4 doubles)",
+    ST_RAND_OVERFLOW: "a step drew more random numbers than provisioned (rand_capacity)",
     ST_XCH_OVERFLOW: "segment shards: more matching / recyclable segments on a rank than the exchange carries "
                      "(exchange_match_capacity / exchange_recycle_capacity)",
     ST_PRI_TIE: "equal growth priorities straddled a selection cut (reference-undefined tie)",
@@ -54,7 +54,7 @@ class BhCtx(C.Structure):
         ("column_dim", C.c_int32), ("cell_dim", C.c_int32), ("active_columns", C.c_int32),
         ("seg_capacity", C.c_int32), ("syn_capacity", C.c_int32), ("match_capacity", C.c_int32),
         ("learn_capacity", C.c_int32), ("tm_blocks", C.c_int32), ("sm_count", C.c_int32),
-        ("rng_ring_words", C.c_int64), ("col_lo", C.c_int32), ("col_local", C.c_int32),
+        ("rng_ring_words", C.c_int64), ("rng_step_words", C.c_int64), ("col_lo", C.c_int32), ("col_local", C.c_int32),
         ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
         ("seg_rank", C.c_int32), ("seg_world", C.c_int32), ("xm_cap", C.c_int32), ("xr_cap", C.c_int32),
         ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32),

@@ -122,6 +122,10 @@ static int check_ctx(const bh_ctx* x) {
   if (x->col_local != x->column_dim && x->fused_mode) return BH_E_UNSUPPORTED;  // sharded: per-stage kernels
   if (x->syn_capacity < 32 || x->syn_capacity % 32 != 0) return BH_E_BADARG;
   if (x->rng_ring_words < (1 << 20) || (x->rng_ring_words & (x->rng_ring_words - 1))) return BH_E_BADARG;
+  if (x->rng_step_words < 2 * BH_MT_N || 2 * x->rng_step_words > x->rng_ring_words) return BH_E_BADARG;
+  // one round of chunks must cover a whole step (plus lookahead) when the stream is produced by many CTAs
+  if (x->jump_polys > 0 && (long long)x->jump_polys * RNG_CHUNK < x->rng_step_words + x->rng_step_words / 2 + RNG_CHUNK)
+    return BH_E_BADARG;
   if (x->jump_polys < 0 || x->rng_lookahead < 0) return BH_E_BADARG;
   if (x->seg_world > 1) {
     if (x->seg_rank < 0 || x->seg_rank >= x->seg_world || x->xm_cap < 1 || x->xr_cap < 1) return BH_E_BADARG;
@@ -709,7 +713,7 @@ extern "C" int bh_rng_export(const bh_ctx* x, void* stream) {
 }
 
 extern "C" int bh_rng_fill(const bh_ctx* x, double* dst_dev, int64_t count, void* stream) {
-  if (!x || !dst_dev || count < 0 || count > x->rng_ring_words / 4) return BH_E_BADARG;
+  if (!x || !dst_dev || count < 0 || 2 * count > x->rng_step_words) return BH_E_BADARG;
   cudaStream_t st = S_(stream);
   k_rng_fill_draw<<<1, MT_THREADS, 0, st>>>(*x, (long long)count);
   LAUNCH_CHECK();

@@ -25,6 +25,11 @@
 //    words before PLAN_BASE with the jump polynomial g_p = t^(RNG_WINDOW + p*RNG_CHUNK)
 //    mod phi(t) (bithtm_b200/_mtjump.py): x[m + D] = XOR_{i: g[i]=1} x[m + i]; the rest of
 //    the chunk follows with the serial recurrence inside the CTA.
+//    Once the ring holds enough history the jump is replaced by the sparse recurrence of
+//    phi(t)^(2^s) = sum over phi's 135 exponents e of t^(e << s):
+//        x[n] = XOR_{e in PHI, e < 19937} x[n - (19937 << s) + (e << s)],
+//    whose nearest operand lies 623 << s words back, i.e. before PLAN_BASE for a large
+//    enough s: 134 coalesced loads per word instead of ~10^4 shared-memory XORs.
 #pragma once
 
 #include "common.cuh"
@@ -38,6 +43,19 @@
 #define RNG_WIN_PAD 20608     // window words staged in shared memory (32*623 + 4*155 + 36, rounded)
 #define RNG_PAR_MIN (3 * RNG_CHUNK)  // deficits below this are produced serially
 #define RNG_CHUNK_SMEM ((RNG_WIN_PAD + MT_RING + MT_N) * 4)
+
+// exponents below 19937 of the characteristic polynomial of MT19937 (bithtm_b200/_mtjump.py: PHI)
+#define RNG_PHI_LOW 134
+__constant__ int c_phi_low[RNG_PHI_LOW] = {
+    0, 1189, 1416, 1585, 1643, 1870, 2493, 2773, 3000, 3227, 3454, 3681, 3908, 4135, 4362, 4753, 5661, 6337, 6569,
+    7129, 7477, 7525, 7583, 7752, 7979, 8206, 9505, 9901, 9969, 10128, 10693, 10761, 10920, 11089, 11147, 11157,
+    11215, 11321, 11374, 11384, 11485, 11611, 11712, 11717, 11838, 11881, 11944, 11997, 12277, 12335, 12393, 12504,
+    12509, 12620, 12673, 12731, 12736, 12789, 12905, 12958, 12963, 13137, 13185, 13190, 13243, 13301, 13412, 13528,
+    13533, 13639, 13697, 13760, 13813, 13866, 14093, 14151, 14209, 14320, 14325, 14436, 14547, 14552, 14605, 14721,
+    14774, 14779, 14953, 15001, 15006, 15059, 15117, 15228, 15344, 15349, 15455, 15513, 15576, 15629, 15682, 15909,
+    15967, 16025, 16136, 16141, 16252, 16363, 16368, 16421, 16537, 16590, 16595, 16817, 16822, 16875, 16933, 17044,
+    17160, 17271, 17329, 17445, 17498, 17725, 17783, 17841, 17952, 18068, 18179, 18237, 18406, 18633, 18691, 18860,
+    19087, 19314};
 
 // rng64 slots
 enum {
@@ -135,14 +153,40 @@ __device__ __noinline__ void rng_chunk(const bh_ctx& c, uint32_t* smem, int p) {
   const int t = threadIdx.x, NT = blockDim.x;
   const long long base = c.rng64[R_PLAN_BASE];
   const long long cb = base + (long long)p * RNG_CHUNK;
+  // sparse start: smallest s whose nearest operand (623 << s words back) precedes PLAN_BASE;
+  // usable when the farthest one (19937 << s back) is still in the ring and was generated
+  int sh = 0;
+  while ((623LL << sh) <= (long long)p * RNG_CHUNK + MT_N) ++sh;
+  const long long depth = 19937LL << sh;
+  const long long plan_end = base + c.rng64[R_PLAN_CHUNKS] * RNG_CHUNK;  // slots below plan_end - ring are reused
+  const long long lowest = plan_end - c.rng_ring_words > 1 ? plan_end - c.rng_ring_words : 1;
+  const bool sparse = cb - depth >= lowest;
+  if (sparse) {
 #pragma unroll 1
-  for (int i = t; i < RNG_WIN_PAD; i += NT) s_win[i] = i < RNG_WINDOW ? rng_word(c, base - RNG_WINDOW + i) : 0u;
+    for (int j = t; j < MT_N; j += NT) {
+      const long long a0 = cb + j - depth;
+      uint32_t v = 0u;
 #pragma unroll 1
-  for (int i = t; i < MT_N; i += NT) s_out[i] = 0u;
+      for (int e0 = 0; e0 < RNG_PHI_LOW; e0 += 16) {  // 16 independent loads in flight per thread
+        uint32_t w[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          w[u] = e0 + u < RNG_PHI_LOW ? rng_word(c, a0 + ((long long)c_phi_low[e0 + u] << sh)) : 0u;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v ^= w[u];
+      }
+      s_out[j] = v;
+    }
+  } else {
+#pragma unroll 1
+    for (int i = t; i < RNG_WIN_PAD; i += NT) s_win[i] = i < RNG_WINDOW ? rng_word(c, base - RNG_WINDOW + i) : 0u;
+#pragma unroll 1
+    for (int i = t; i < MT_N; i += NT) s_out[i] = 0u;
+  }
   __syncthreads();
   // out[j] = XOR_{i : g[i]} win[i + j].  6 groups of 156 threads split the 624 words of
   // g; thread q of a group keeps outputs 4q..4q+3 and slides a register window over win.
-  if (t < 936) {
+  if (!sparse && t < 936) {
     const int grp = t / 156, q = t - grp * 156;
     const uint32_t* gp = c.mt_jump + (long long)p * MT_N;
     uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
@@ -207,10 +251,10 @@ __device__ __forceinline__ void rng_commit_plan(const bh_ctx& c) {
   }
 }
 
-// Largest number of doubles a draw starting at `cursor` may take so that the words of the
-// current step (from step_base on), the jump window and one round of chunks fit the ring.
+// Largest number of doubles a draw starting at `cursor` may take: a step (from step_base
+// on) may use rng_step_words words, which the caller sized the ring and the jump table for.
 __device__ __forceinline__ long long rng_room(const bh_ctx& c, long long step_base, long long cursor) {
-  const long long cap = c.rng_ring_words / 2 - (cursor - step_base);
+  const long long cap = c.rng_step_words - (cursor - step_base);
   return cap > 0 ? cap / 2 : 0;
 }
 
@@ -236,7 +280,7 @@ __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long co
     const long long end = cur + 2 * count;
     r[R_CURSOR] = end;
     long long la = lookahead;
-    if (la > c.rng_ring_words / 4) la = c.rng_ring_words / 4;
+    if (la > c.rng_step_words / 2) la = c.rng_step_words / 2;
     const long long target = end + la + MT_N;  // keep 624 words past the cursor for state export
     long long produced = r[R_PRODUCED];
     long long serial_target = target;

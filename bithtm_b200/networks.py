@@ -326,8 +326,10 @@ class TemporalMemory:
         self.last_state = state
         return state
 
-    def process(self, sp_state, prev_state=None, learning=True, return_winner_cell=True, epsilon=1e-8):
-        """networks.py:91-128."""
+    def process(self, sp_state, prev_state=None, learning=True, return_winner_cell=True, epsilon=1e-8,
+                return_state=True):
+        """networks.py:91-128.  ``return_state=False`` (extension) enqueues the step without
+        reading anything back (no host synchronisation; needs ``rng_sync="lazy"``)."""
         if prev_state is not None and prev_state is not self.last_state:
             raise NotImplementedError("bithtm_b200.TemporalMemory keeps the previous state on the device; "
                                       "an explicit prev_state other than last_state is not supported")
@@ -354,6 +356,11 @@ class TemporalMemory:
         else:
             nat.check(nat.lib.bh_tm_step(eng.ref, int(bool(learning)), eng.stream), "bh_tm_step")
             eng.epoch += 1
+        if not return_state:
+            if self._rng.mode != "lazy":
+                raise ValueError('return_state=False needs rng_sync="lazy" (no per-step read-back)')
+            self.last_state = None
+            return None
         summary = eng.summary()
         self._rng.after(eng, summary)
         return self._finish(summary)
@@ -417,15 +424,19 @@ class HierarchicalTemporalMemory:
     def sync_rng(self):
         self.temporal_memory.sync_rng()
 
-    def process(self, input, learning=True):
+    def process(self, input, learning=True, return_state=True):
         """networks.py:146-149.  Host inputs go through ``bh_step_host`` (one H2D of
-        the packed input, the whole step on the device, one D2H of the step summary)."""
+        the packed input, the whole step on the device, one D2H of the step summary).
+        ``return_state=False`` (extension; device inputs, ``rng_sync="lazy"``) only enqueues
+        the step: nothing is read back and the host does not wait."""
         sp, tm, eng = self.spatial_pooler, self.temporal_memory, self._engine
         is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
-        if not sp._native_inhibition or not is_host or eng.shard_world > 1 or eng.seg_world > 1:
+        if not sp._native_inhibition or not is_host or eng.shard_world > 1 or eng.seg_world > 1 or not return_state:
             sp_state = sp.process(input, learning=learning)
             sp_state._group = sp._group
-            tm_state = tm.process(sp_state, learning=learning)
+            tm_state = tm.process(sp_state, learning=learning, return_state=return_state)
+            if not return_state:
+                return None
             sp_state._epoch = eng.epoch  # its buffers stay valid until the next step
             return sp_state, tm_state
         sp.boosting._bind(eng)

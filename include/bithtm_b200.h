@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 3
+#define BH_ABI_VERSION 4
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 8192
@@ -90,8 +90,9 @@ typedef struct bh_ctx {
   int32_t learn_capacity;  /* L_cap                                                */
   int32_t tm_blocks;       /* NB: CTAs of the ranged TM kernels (<= 1024)          */
   int32_t sm_count;        /* SMs of the device (grid sizing)                      */
-  int64_t rng_ring_words;  /* words in rng_ring: a power of two >= 2^20; one step may   */
-                           /* draw at most rng_ring_words / 4 doubles                  */
+  int64_t rng_ring_words;  /* words in rng_ring: a power of two >= 2^20 and              */
+                           /* >= 2 * rng_step_words                                     */
+  int64_t rng_step_words;  /* most stream words (2 per float64) one timestep may draw  */
   int32_t col_lo;          /* column shard: first global column owned by this rank  */
   int32_t col_local;       /* columns owned (C when not sharded); the SP buffers    */
                            /* sp_perm/sp_mask/duty/overlaps/boosted are local-sized */
@@ -321,7 +322,7 @@ int bh_rng_import(const bh_ctx* ctx, void* stream);
 /* Write the state at the device's stream cursor to ctx->mt_key / sc[BH_SC_MT_POS]. */
 int bh_rng_export(const bh_ctx* ctx, void* stream);
 /* Take the next `count` float64 uniforms of the stream (np.random.random_sample)
- * into dst_dev; count <= rng_ring_words / 4. */
+ * into dst_dev; 2 * count <= rng_step_words. */
 int bh_rng_fill(const bh_ctx* ctx, double* dst_dev, int64_t count, void* stream);
 
 /* ---- test hooks ------------------------------------------------------------------------- */

@@ -94,7 +94,7 @@ def test_layout_without_device():
     ctx.column_dim, ctx.cell_dim, ctx.active_columns = 2048, 32, 41
     ctx.col_lo, ctx.col_local = 0, 2048
     ctx.seg_capacity, ctx.syn_capacity, ctx.match_capacity, ctx.learn_capacity = 1 << 16, 128, 1 << 16, 1 << 17
-    ctx.tm_blocks, ctx.rng_ring_words = 148, 1 << 20
+    ctx.tm_blocks, ctx.rng_ring_words, ctx.rng_step_words = 148, 1 << 20, 1 << 18
     n = nat.lib.bh_layout(ctypes.byref(ctx), None)
     perm_bytes = 2048 * 1024 * 8
     syn_bytes = (1 << 16) * 128 * 8

@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""cfg3 (65536 columns x 16384 inputs, 32 cells, k=1311) as ONE network sharded over the
+ranks of a torchrun job: spatial pooler by column, temporal memory by segment id, two
+NCCL all-gathers per timestep.  Permanence rows are drawn on each device (performance
+run; parity of the sharded path is tests/test_multi.py).
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/cfg3_sharded.py [steps] [C] [I]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+import bithtm_b200 as bithtm
+from bithtm_b200.projections import DenseProjection
+
+
+def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    C = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+    I = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c, k = 32, round(C * 0.02)
+    patterns = 50
+    g = np.random.default_rng(0)
+    base = g.random((patterns, I)) < 0.2
+    xs = base[np.arange(steps) % patterns] ^ (g.random((steps, I)) < 0.05)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+    perm = torch.randn(C // world, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
+    np.random.seed(0)
+    sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy",
+                                            column_shard=True if world > 1 else None,
+                                            max_segments=1 << 21, max_synapses_per_segment=64,
+                                            fused="off" if world > 1 else "off")
+    del perm
+    sp.proximal_projection._host_permanence = None
+    torch.cuda.empty_cache()
+    eng = htm.engine
+    htm.temporal_memory._rng.before(eng)
+    words = [eng.pack_input(x) for x in xs[:patterns * 2]]
+    torch.cuda.synchronize()
+    times = []
+    chunk = 50
+    for t0 in range(0, steps, chunk):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for t in range(t0, min(t0 + chunk, steps)):
+            htm.process(words[t % len(words)], return_state=False)
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / chunk], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        times.append(float(ms))
+        sc = eng.scalars()
+        if rank == 0:
+            print(f"step {t0 + chunk}: {times[-1]:.3f} ms/step  S={sc[2]} M={sc[4]} L={sc[8]} status={sc[12]}", flush=True)
+    eng.check_status()
+    if rank == 0:
+        print(json.dumps({"workload": f"cfg3 sharded: {C} columns x {I} inputs, k={k}", "n_gpus": world,
+                          "ms_per_step": times[-1], "steps_per_s": 1e3 / times[-1],
+                          "exchanges_per_step": 2 if world > 1 else 0}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
