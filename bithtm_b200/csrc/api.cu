@@ -593,7 +593,16 @@ extern "C" int bh_step_host_graph(const bh_ctx* x, void* graph_exec, const uint8
   if (!x || !graph_exec || !input_bool_host) return BH_E_BADARG;
   cudaStream_t st = S_(stream);
   pack_host(x, input_bool_host);
+  // The D2H node rewrites summary_pinned[0] (the finished step's index, >= 0): spin on it instead of
+  // sleeping in the driver (saves the wake-up latency of a ~50 us step), then synchronise for real.
+  volatile int32_t* flag = x->summary_pinned;
+  flag[0] = -1;
   CU_RET(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), st));
+  for (long spins = 0; flag[0] == -1 && spins < 4000000; ++spins) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
   CU_RET(cudaStreamSynchronize(st));
   if (summary_host) memcpy(summary_host, x->summary_pinned, (size_t)BH_SUMMARY_INTS(x->active_columns) * 4);
   return 0;

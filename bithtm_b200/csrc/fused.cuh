@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     } else if (b == 0) {
       ph_topk(c);
     }
+    if (rng && nb > 1) ph_rng_speculate(c);  // idle here: produce the stream words this step will draw
     BH_SYNC();
     BH_STAMP();
     // P2: SP learning + duty cycles; bursting / winner bits per active column
@@ -102,12 +103,24 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (worker) ph_activate_a(c, b, nw);
     BH_SYNC();
     BH_STAMP();
-    // P8: draw #3 (rand(M))
-    if (rng) ph_draw(c, 3, 1, nw);
-    BH_SYNC();
+    // P8: draw #3 (rand(M)) -- a phase of its own only when the words draw #2 left produced do not
+    // cover it (every CTA takes the same decision from barrier-published values)
+    bool ready3;
+    {
+      __shared__ int s_red3[32];
+      int mb, mt;
+      blk_prefix(BLK(c, BLK_MATCH), 0, nw, s_red3, mb, mt);
+      ready3 = (long long)(mt < c.match_capacity ? mt : c.match_capacity) <= c.rng64[R_READY3];
+      __syncthreads();
+    }
+    if (!ready3) {
+      if (rng) ph_draw(c, 3, 1, nw);
+      BH_SYNC();
+    }
     BH_STAMP();
     // P9: matching list, jitter, predictions; completes the step
-    if (worker) ph_activate_b(c, b, nw);
+    if (ready3 && rng) ph_draw3_ready(c, nw);
+    if (worker) ph_activate_b(c, b, nw, ready3);
     BH_SYNC();
     BH_STAMP();
   }

@@ -69,6 +69,8 @@ enum {
   R_PLAN_BASE,    // parallel production plan: chunks [0, PLAN_CHUNKS) start at PLAN_BASE
   R_PLAN_CHUNKS,
   R_STEP_BASE,    // cursor at the first draw of the current step
+  R_READY3,       // published with draw #2: doubles draw #3 can take from words already produced
+  R_EST,          // stream words a step is expected to draw (previous step + margin): speculation target
   R_COUNT = 16
 };
 
@@ -263,7 +265,8 @@ __device__ __forceinline__ long long rng_room(const bh_ctx& c, long long step_ba
 // deficit is small, else by planning chunks for ph_rng_chunks (which must run next).
 // `x` = MT_RING words of shared memory.  Returns through shared state only.
 __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long count, int off_slot, int n_slot,
-                                      bool first_of_step, long long lookahead, bool may_plan) {
+                                      bool first_of_step, long long lookahead, bool may_plan,
+                                      bool publish_next = false) {
   __shared__ long long s_serial_target;
   if (threadIdx.x == 0) {
     long long* r = c.rng64;
@@ -299,8 +302,48 @@ __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long co
   }
   __syncthreads();
   rng_produce_serial(c, x, s_serial_target);
-  if (threadIdx.x == 0 && c.rng64[R_PLAN_CHUNKS] > 0) c.rng64[R_PLAN_BASE] = c.rng64[R_PRODUCED];
+  if (threadIdx.x == 0) {
+    long long* r = c.rng64;
+    if (r[R_PLAN_CHUNKS] > 0) r[R_PLAN_BASE] = r[R_PRODUCED];
+    if (publish_next) {
+      // draw #3 follows directly in the stream: where it starts, and how many doubles of it are covered
+      // by words that exist once this draw (and its chunks) are done -- lets the fused kernel skip the
+      // draw-#3 phase and its barrier (fused.cuh)
+      const long long end = r[R_CURSOR];
+      const long long produced = r[R_PLAN_CHUNKS] > 0 ? r[R_PLAN_BASE] + r[R_PLAN_CHUNKS] * RNG_CHUNK : r[R_PRODUCED];
+      long long ready = (produced - end - MT_N) / 2;
+      const long long room = rng_room(c, r[R_STEP_BASE], end);
+      if (ready > room) ready = room;
+      r[R_OFF3] = end;
+      r[R_READY3] = ready > 0 ? ready : 0;
+    }
+  }
   __syncthreads();
+}
+
+// Thread 0 of the drawing CTA, after the last draw of a step: what the next step is expected to need.
+__device__ __forceinline__ void rng_finish_step(const bh_ctx& c) {
+  long long* r = c.rng64;
+  const long long used = r[R_CURSOR] - r[R_STEP_BASE];
+  long long est = used + used / 4 + 2 * (long long)c.active_columns * c.cell_dim + 2 * MT_N;
+  if (est > c.rng_step_words / 2) est = c.rng_step_words / 2;
+  r[R_EST] = est;
+}
+
+// Draw #3 when R_READY3 covers it: bookkeeping only (thread 0 of the drawing CTA).
+__device__ __forceinline__ void rng_draw3_commit(const bh_ctx& c, long long count) {
+  long long* r = c.rng64;
+  r[R_N3] = count;
+  r[R_CURSOR] = r[R_OFF3] + 2 * count;
+  rng_finish_step(c);
+}
+
+// One CTA, while it has nothing else to do: produce the words the current step is expected to
+// draw (serial producer; with many-CTA production the draws plan their own chunks).
+__device__ __noinline__ void ph_rng_speculate(const bh_ctx& c) {
+  __shared__ uint32_t x[MT_RING];
+  if (c.jump_polys > 0) return;
+  rng_produce_serial(c, x, c.rng64[R_STEP_BASE] + c.rng64[R_EST]);
 }
 
 // Host state -> ring (single CTA): key = words [0, 624), cursor = pos.

@@ -90,8 +90,28 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
   }
   __syncthreads();
   if (which == 1) rng_draw(c, x, s_count, R_OFF1, -1, true, 0, false);
-  else if (which == 2) rng_draw(c, x, s_count, R_OFF2, R_N2, false, c.rng_lookahead, true);
-  else rng_draw(c, x, s_count, R_OFF3, R_N3, false, 0, false);
+  else if (which == 2) rng_draw(c, x, s_count, R_OFF2, R_N2, false, c.rng_lookahead, true, true);
+  else {
+    rng_draw(c, x, s_count, R_OFF3, R_N3, false, 0, false);
+    if (threadIdx.x == 0) rng_finish_step(c);
+  }
+}
+
+// Draw #3 without production, when the words exist already (count <= R_READY3, decided
+// identically by every CTA): the drawing CTA only does the bookkeeping.
+__device__ __noinline__ void ph_draw3_ready(const bh_ctx& c, int nw) {
+  __shared__ int s_red[32];
+  int m_before, m_total;
+  blk_prefix(BLK(c, BLK_MATCH), 0, nw, s_red, m_before, m_total);
+  if (threadIdx.x == 0) {
+    int M = c.seg_world > 1 ? c.sc[BH_SC_X_MATCH] : m_total;
+    if (M > c.match_capacity) {
+      M = c.match_capacity;
+      atomicOr(&c.sc[BH_SC_STATUS], BH_ST_MATCH_OVERFLOW);
+    }
+    c.sc[BH_SC_M] = M;
+    rng_draw3_commit(c, M);
+  }
 }
 
 __global__ void __launch_bounds__(MT_THREADS) k_tm_draw(const __grid_constant__ bh_ctx c, int which, int learning) {
@@ -620,22 +640,25 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
   int nm = 0, nrec = 0;
 #pragma unroll 1
   for (int s0 = rg.begin + warp * ACT_BATCH; s0 < rg.end; s0 += warps * ACT_BATCH) {
-    // counts of the batch with one load, then slots [0, 64) of every row at once
+    // the counts of the batch and slots [0, 64) of every row are fetched TOGETHER (free slots hold
+    // stale but valid cell ids and are masked afterwards): two dependent round trips per batch
+    // instead of three
     const int my_n = (lane < ACT_BATCH && s0 + lane < rg.end) ? c.seg_count[seg_gid(c, s0 + lane)] : 0;
-    if (lane < ACT_BATCH && s0 + lane < rg.end && my_n < thr) ++nrec;  // recyclable (projections.py:80)
     int n[ACT_BATCH], cell[ACT_BATCH][2];
     float perm[ACT_BATCH][2];
 #pragma unroll
     for (int j = 0; j < ACT_BATCH; ++j) {
-      n[j] = __shfl_sync(BH_FULL, my_n, j);
       const long long base = (long long)(s0 + j) * E + lane;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const bool v = lane + 32 * h < n[j];
+        const bool v = s0 + j < rg.end && lane + 32 * h < E;
         cell[j][h] = v ? c.syn_cell[base + 32 * h] : 0;
         perm[j][h] = v ? c.syn_perm[base + 32 * h] : 0.0f;
       }
     }
+    if (lane < ACT_BATCH && s0 + lane < rg.end && my_n < thr) ++nrec;  // recyclable (projections.py:80)
+#pragma unroll
+    for (int j = 0; j < ACT_BATCH; ++j) n[j] = __shfl_sync(BH_FULL, my_n, j);
     uint32_t word[ACT_BATCH][2];
 #pragma unroll
     for (int j = 0; j < ACT_BATCH; ++j)
@@ -683,15 +706,16 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
 // jittered potential f32(f64(potential) + u) with the draw indexed by the rank in
 // that list (:234-235), per-cell maximum (:236-237) and active-segment count (:251).
 // CTA 0 completes the timestep.
-__device__ void ph_activate_b(const bh_ctx& c, int b, int nb) {
+// `ready`: draw #3 was not run as a phase (fused.cuh); its count is the clamped list length.
+__device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false) {
   __shared__ int s_red[32];
   const int NT = blockDim.x;
   const int S = c.sc[BH_SC_NSEG];
   const int thr = c.seg_matching_threshold;
   const long long off3 = c.rng64[R_OFF3];
-  const long long n3 = c.rng64[R_N3];
   int m_before, m_total;
   blk_prefix(BLK(c, BLK_MATCH), b, nb, s_red, m_before, m_total);
+  const long long n3 = ready ? (m_total < c.match_capacity ? m_total : c.match_capacity) : c.rng64[R_N3];
   const Range rg = block_range(S, b, nb);
   int base = m_before;
   #pragma unroll 1
