@@ -311,6 +311,18 @@ def ours(args):
             hbm = cfg3_kernels.measure(65536, 16384, 250, 20)
         except Exception as e:  # never lose the headline line
             hbm = {"error": repr(e)}
+    batched = None
+    if rank == 0 and world == 1 and not args.no_hbm:
+        # independent streams side by side on the one GPU (BASELINE configs[3]): aggregate throughput
+        try:
+            import stream_batch
+
+            torch.cuda.empty_cache()
+            batched = stream_batch.measure(128, 4, 400, 200)
+            batched["note"] = ("128 independent cfg2 networks, one 4-CTA cluster kernel each, one CUDA graph of 50 "
+                               "steps x 128 launches; L2-resident")
+        except Exception as e:
+            batched = {"error": repr(e)}
     if rank == 0:
         launches_per_step = launches
         line = {
@@ -327,7 +339,8 @@ def ours(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "note": "HierarchicalTemporalMemory.process(host bool array), np.random kept in lock-step"},
             "gpu_launches": launches_per_step * K,
-            "roofline": roofline, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "roofline_hbm_kernels": hbm, "streams_batched": batched, "cpu_baseline": cpu,
+            "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

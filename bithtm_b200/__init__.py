@@ -10,11 +10,12 @@ The arithmetic runs in hand-written CUDA kernels (``csrc/``) behind a C ABI
 (``include/bithtm_b200.h``); there is no CPU fallback.
 """
 
-from . import networks, projections, regularizations  # noqa: F401
+from . import batch, networks, projections, regularizations  # noqa: F401
 
 SpatialPooler = networks.SpatialPooler
 TemporalMemory = networks.TemporalMemory
 HierarchicalTemporalMemory = networks.HierarchicalTemporalMemory
+StreamBatch = batch.StreamBatch  # extension: independent streams side by side on one GPU
 
-__all__ = ["SpatialPooler", "TemporalMemory", "HierarchicalTemporalMemory", "networks", "projections",
-           "regularizations"]
+__all__ = ["SpatialPooler", "TemporalMemory", "HierarchicalTemporalMemory", "StreamBatch", "networks",
+           "projections", "regularizations", "batch"]

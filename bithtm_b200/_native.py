@@ -130,6 +130,7 @@ _SIGNATURES = {
     "bh_step_host_graph": (C.c_int, [_CTXP, _P, _P, _P, _P]),
     "bh_summary": (C.c_int, [_CTXP, _P, _P]),
     "bh_graph_create": (C.c_int, [_CTXP, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "bh_batch_graph_create": (C.c_int, [C.POINTER(_CTXP), C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     "bh_graph_launch": (C.c_int, [_P, _P]),
     "bh_graph_destroy": (C.c_int, [_P]),
     "bh_profile_step": (C.c_int, [_CTXP, _P, C.c_int, _P, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]),

@@ -692,6 +692,55 @@ extern "C" int bh_graph_create(const bh_ctx* x, int steps_per_graph, int learnin
   return 0;
 }
 
+// n independent networks in one graph: fork from `stream` onto side streams, one fused launch per
+// network, join.  The side streams exist only during the capture.
+extern "C" int bh_batch_graph_create(const bh_ctx* const* ctxs, int n, int steps_per_graph, int learning,
+                                     void* stream, void** out) {
+  if (!out || !ctxs || n < 1 || steps_per_graph < 1) return BH_E_BADARG;
+  for (int i = 0; i < n; ++i) {
+    int rc = check_ctx(ctxs[i]);
+    if (rc) return rc;
+    if (!ctxs[i]->fused_mode || ctxs[i]->ring_len <= 0) return BH_E_UNSUPPORTED;
+    if ((rc = prepare_fused(ctxs[i]->fused_mode))) return rc;
+  }
+  cudaStream_t st = S_(stream);
+  const int NS = n < 32 ? n : 32;
+  cudaStream_t side[32];
+  cudaEvent_t fork, join[32];
+  for (int i = 0; i < NS; ++i) {
+    CU_RET(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+    CU_RET(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+  }
+  CU_RET(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  cudaGraph_t graph = nullptr;
+  int rc = 0;
+  CU_RET(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  cudaError_t e = cudaEventRecord(fork, st);
+  for (int i = 0; i < NS && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(side[i], fork, 0);
+  for (int i = 0; i < n && rc == 0 && e == cudaSuccess; ++i)
+    rc = launch_fused(ctxs[i], nullptr, steps_per_graph, learning, 0, side[i % NS]);
+  for (int i = 0; i < NS && e == cudaSuccess; ++i) {
+    e = cudaEventRecord(join[i], side[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join[i], 0);
+  }
+  cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+  for (int i = 0; i < NS; ++i) {
+    cudaStreamDestroy(side[i]);
+    cudaEventDestroy(join[i]);
+  }
+  cudaEventDestroy(fork);
+  if (rc || e != cudaSuccess || e2 != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc ? rc : -(1000 + (int)(e != cudaSuccess ? e : e2));
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  *out = exec;
+  return 0;
+}
+
 extern "C" int bh_graph_launch(void* graph_exec, void* stream) {
   CU_RET(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), S_(stream)));
   return 0;

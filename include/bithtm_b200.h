@@ -307,6 +307,13 @@ int bh_summary(const bh_ctx* ctx, int32_t* summary_host, void* stream);
 int bh_graph_create(const bh_ctx* ctx, int steps_per_graph, int learning, void* stream, void** graph_exec_out);
 int bh_graph_launch(void* graph_exec, void* stream);
 int bh_graph_destroy(void* graph_exec);
+/* Independent streams: ONE graph that advances n independent networks
+ * (ctxs[i], each with its own arena and device input ring, fused_mode != 0) by
+ * steps_per_graph timesteps, with no dependency between them, so their kernels run
+ * side by side on the SMs a single small network leaves idle.  Launch with
+ * bh_graph_launch, free with bh_graph_destroy. */
+int bh_batch_graph_create(const bh_ctx* const* ctxs, int n, int steps_per_graph, int learning, void* stream,
+                          void** graph_exec_out);
 /* One bh_step with a CUDA event recorded on `stream` after every kernel launch.
  * Returns the number of launches n (>= 0) and fills ms_out[0..n) / names_out[0..n)
  * (static strings); synchronises the stream. */

@@ -6,8 +6,8 @@ the golden traces recorded from the unmodified reference.  Bit-exact everywhere.
 import numpy as np
 import pytest
 
-from helpers import (diff_records, golden_inputs, gpu_record, gpu_state_digest, load_golden, oracle_record,
-                     oracle_state_digest, step_digest)
+from helpers import (diff_records, golden_inputs, gpu_record, gpu_state_digest, load_golden, make_inputs,
+                     oracle_record, oracle_state_digest, step_digest)
 from oracle.htm_oracle import HTMOracle, OracleConfig
 
 pytestmark = pytest.mark.gpu
@@ -407,3 +407,39 @@ def test_example_driver_stream_matches_oracle():
         rec = orc.step(xo)
         problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
         assert not problems, f"step {t}: " + "; ".join(problems)
+
+
+@pytest.mark.gpu
+def test_stream_batch_equals_streams_stepped_alone():
+    """Independent streams advanced side by side by one CUDA graph (StreamBatch, cfg4's
+    mode) end in exactly the state each reaches when stepped alone."""
+    import bithtm_b200 as bithtm
+
+    info = load_golden("tiny")
+    I, C, c, k = info["I"], info["C"], info["c"], info["k"]
+    steps, B = 120, 5
+    seeds = [info["seed"] + 17 * i for i in range(B)]
+    inputs = [make_inputs(I, info["patterns"], info["density"], info["noise"], steps, s) for s in seeds]
+
+    def build(seed):
+        np.random.seed(seed)
+        return bithtm.HierarchicalTemporalMemory(I, C, c, k, rng_sync="lazy", ring_len=steps, max_segments=1 << 12,
+                                                 fused="cluster", fused_ctas=4)
+
+    alone = []
+    for s, xs in zip(seeds, inputs):
+        h = build(s)
+        eng = h.engine
+        h.temporal_memory._rng.before(eng)
+        eng.load_ring(xs)
+        eng.launch_graph(eng.graph(steps, learning=True), steps)
+        alone.append(gpu_state_digest(h))
+    nets = [build(s) for s in seeds]
+    batch = bithtm.StreamBatch(nets)
+    batch.load_inputs(inputs)
+    for _ in range(4):
+        batch.run(steps // 4)
+    batch.check_status()
+    assert [gpu_state_digest(h) for h in nets] == alone
+    # and they really are different streams
+    assert len(set(alone)) == B
