@@ -88,14 +88,16 @@ class Engine:
             self.shard_rank, self.shard_world = int(column_shard[0]), int(column_shard[1])
             if Ccol % self.shard_world:
                 raise ValueError("column_dim must be divisible by the number of column shards")
-            fused = "off"  # the all-gather sits between kernels
+            if fused != "shard":
+                fused = "off"  # the all-gather sits between kernels
         if segment_shard is None:
             self.seg_rank, self.seg_world = 0, 1
         else:
             self.seg_rank, self.seg_world = int(segment_shard[0]), int(segment_shard[1])
-            fused = "off"  # the exchange sits between kernels
+            if fused != "shard":
+                fused = "off"  # the exchange sits between kernels
         ctx.seg_rank, ctx.seg_world = self.seg_rank, self.seg_world
-        if self.seg_world > 1:
+        if self.seg_world > 1 or fused == "shard":
             ctx.xm_cap = int(exchange_match_capacity or min(int(match_capacity), 8 * k + 1024))
             ctx.xr_cap = int(exchange_recycle_capacity or (2 * k + 64))
         ctx.col_local = Ccol // self.shard_world
@@ -130,7 +132,7 @@ class Engine:
         # latency-bound (mask <= 8 MiB), else on a cooperative grid with one CTA per SM
         if fused == "auto":
             fused = "cluster" if Ccol * ctx.mask_stride * 4 <= (8 << 20) else "grid"
-        ctx.fused_mode = {"off": 0, "cluster": 1, "grid": 2}[fused]
+        ctx.fused_mode = {"off": 0, "cluster": 1, "grid": 2, "shard": 3}[fused]
         if fused_ctas is None:
             fused_ctas = 16 if fused == "cluster" else self.sm_count
         ctx.fused_ctas = int(fused_ctas)
@@ -191,7 +193,11 @@ class Engine:
             "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": rows * E, "syn_perm": rows * E,
             "row_pred": k, "row_act": k, "row_win": k, "row_unacc": k, "winners": 2 * k * c, "unacc": k * c,
             "m_seg": M, "m_conn": M, "m_jit": M, "m_flag": M, "learn_list": x.learn_capacity, "punish_list": M,
-            "recyc_list": W * x.xr_cap if W > 1 else 0, "blk": 8 * 1024, "topk_ws": 8192, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
+            "recyc_list": W * x.xr_cap if W > 1 else 0,
+            "x_send": max((3 * min(k, CL) + 3) // 4 * 4, (4 + 3 * x.xm_cap + x.xr_cap + 3) // 4 * 4)
+            if x.fused_mode == 3 else 0,
+            "xk_keys": W * min(k, CL) if x.fused_mode == 3 else 0,
+            "xk_cols": W * min(k, CL) if x.fused_mode == 3 else 0, "blk": 8 * 1024, "topk_ws": 8192, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
             "rng64": nat.R_COUNT, "sc": nat.SC_COUNT,
             "input_ring": x.ring_len * x.input_words, "input_dev": x.mask_stride,
             "summary_dev": nat.summary_ints(k),
@@ -223,6 +229,19 @@ class Engine:
         if self.seg_world > 1:
             ids = ids[(ids >> 6) % self.seg_world == self.seg_rank]
         return ids
+
+    # fused sharded step (fused="shard"): every rank's exchange region must be visible to its peers
+    def exchange_region_ints(self) -> int:
+        return int(nat.lib.bh_xch_region_ints(self.ref))
+
+    def set_exchange_regions(self, pointers, keepalive=None):
+        """pointers[r] = device address of rank r's (zero-filled) exchange region as mapped into THIS
+        process; pointers[own rank] is the local one."""
+        world = max(1, self.seg_world)
+        assert len(pointers) == world <= nat.MAX_RANKS
+        for r, p in enumerate(pointers):
+            self.ctx.xpeer[r] = int(p)
+        self._xch_keepalive = keepalive
 
     def tm_shard_pre(self, learning=True):
         nat.check(nat.lib.bh_tm_shard_pre(self.ref, int(bool(learning)), self.xch_send.data_ptr(), self.stream),

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libbithtm_b200.so")
 
 MT_N = 624
-ABI_VERSION = 4
+ABI_VERSION = 5
 R_COUNT = 16  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)
@@ -24,6 +24,8 @@ SC_COUNT = 32
 
 ST_SEG_OVERFLOW, ST_SYN_OVERFLOW, ST_MATCH_OVERFLOW, ST_LEARN_OVERFLOW, ST_RAND_OVERFLOW, ST_PRI_TIE = 1, 2, 4, 8, 16, 32
 ST_XCH_OVERFLOW = 64
+ST_XCH_TIMEOUT = 128
+MAX_RANKS = 8
 ST_NAMES = {
     ST_SEG_OVERFLOW: "segment capacity exceeded (max_segments)",
     ST_SYN_OVERFLOW: "synapse slots per segment exceeded (max_synapses_per_segment)",
@@ -32,10 +34,11 @@ ST_NAMES = {
     ST_RAND_OVERFLOW: "a step drew more random numbers than provisioned (rand_capacity)",
     ST_XCH_OVERFLOW: "segment shards: more matching / recyclable segments on a rank than the exchange carries "
                      "(exchange_match_capacity / exchange_recycle_capacity)",
+    ST_XCH_TIMEOUT: "fused sharded step: a peer rank's record never arrived (peer not running the same step?)",
     ST_PRI_TIE: "equal growth priorities straddled a selection cut (reference-undefined tie)",
 }
 ST_FATAL = (ST_SEG_OVERFLOW | ST_SYN_OVERFLOW | ST_MATCH_OVERFLOW | ST_LEARN_OVERFLOW | ST_RAND_OVERFLOW
-            | ST_XCH_OVERFLOW)
+            | ST_XCH_OVERFLOW | ST_XCH_TIMEOUT)
 
 
 def summary_ints(k: int) -> int:
@@ -76,8 +79,10 @@ class BhCtx(C.Structure):
         ("row_pred", _P), ("row_act", _P), ("row_win", _P), ("row_unacc", _P),
         ("winners", _P), ("unacc", _P),
         ("m_seg", _P), ("m_conn", _P), ("m_jit", _P), ("m_flag", _P),
-        ("learn_list", _P), ("punish_list", _P), ("recyc_list", _P), ("blk", _P), ("topk_ws", _P),
+        ("learn_list", _P), ("punish_list", _P), ("recyc_list", _P),
+        ("x_send", _P), ("xk_keys", _P), ("xk_cols", _P), ("blk", _P), ("topk_ws", _P),
         ("mt_key", _P), ("rng_ring", _P), ("mt_jump", _P), ("rng64", _P),
+        ("xpeer", _P * 8),
         ("sc", _P), ("input_ring", _P), ("input_dev", _P), ("input_pinned", _P),
         ("summary_dev", _P), ("summary_pinned", _P),
     ]
@@ -92,7 +97,8 @@ DEVICE_BUFFERS = {
     "syn_cell": "int32", "syn_perm": "float32",
     "row_pred": "int32", "row_act": "int32", "row_win": "int32", "row_unacc": "int32",
     "winners": "int32", "unacc": "int32", "m_seg": "int32", "m_conn": "int32", "m_jit": "float32",
-    "m_flag": "uint8", "learn_list": "int32", "punish_list": "int32", "recyc_list": "int32", "blk": "int32", "topk_ws": "int32",
+    "m_flag": "uint8", "learn_list": "int32", "punish_list": "int32", "recyc_list": "int32",
+    "x_send": "int32", "xk_keys": "float64", "xk_cols": "int32", "blk": "int32", "topk_ws": "int32",
     "mt_key": "int32", "rng_ring": "int32", "mt_jump": "int32", "rng64": "int64", "sc": "int32", "input_ring": "int32", "input_dev": "int32",
     "summary_dev": "int32",
 }
@@ -116,6 +122,7 @@ _SIGNATURES = {
     "bh_sp_shard_local": (C.c_int, [_CTXP, _P, _P, _P, _P]),
     "bh_sp_shard_finish": (C.c_int, [_CTXP, _P, _P, _P, C.c_int, C.c_int, _P]),
     "bh_tm_shard_xch_ints": (C.c_size_t, [_CTXP]),
+    "bh_xch_region_ints": (C.c_size_t, [_CTXP]),
     "bh_tm_shard_pre": (C.c_int, [_CTXP, C.c_int, _P, _P]),
     "bh_tm_shard_post": (C.c_int, [_CTXP, _P, _P]),
     "bh_advance_step": (C.c_int, [_CTXP, _P]),

@@ -79,3 +79,46 @@ def merge_segment_parts(parts):
     ids = np.concatenate([p[0] for p in parts])
     order = np.argsort(ids, kind="stable")
     return tuple(np.concatenate([p[i] for p in parts])[order] for i in range(1, 4))
+
+
+def map_exchange_regions(engine, group=None):
+    """Allocate this rank's exchange region of the fused sharded step in memory the peer GPUs
+    can store into over NVLink, exchange the mappings, and hand all bases to the engine.
+    Symmetric memory (torch.distributed._symmetric_memory) when it works, else CUDA IPC
+    handles passed through the process group."""
+    import torch
+    import torch.distributed as dist
+
+    n = engine.exchange_region_ints()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    assert world == engine.seg_world and rank == engine.seg_rank
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        t = symm_mem.empty(n, dtype=torch.int32, device=engine.device)
+        t.zero_()
+        torch.cuda.synchronize(engine.device)
+        handle = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        keep = (t, handle)
+        how = "symmetric memory"
+    except Exception:
+        t = torch.zeros(n, dtype=torch.int32, device=engine.device)
+        torch.cuda.synchronize(engine.device)
+        mine = t.untyped_storage()._share_cuda_()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        opened, ptrs = [], []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(t.data_ptr())
+            else:
+                st = torch.UntypedStorage._new_shared_cuda(*handles[r])
+                opened.append(st)
+                ptrs.append(st.data_ptr())
+        keep = (t, opened)
+        how = "CUDA IPC"
+    dist.barrier(group=group)
+    engine.set_exchange_regions(ptrs, keepalive=keep)
+    return how

@@ -9,6 +9,7 @@
 #include "tm_kernels.cuh"
 #include "fused.cuh"
 #include "tm_shard.cuh"
+#include "shard_fused.cuh"
 
 #define CU_RET(expr)                                   \
   do {                                                 \
@@ -97,6 +98,16 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->learn_list, (size_t)x->learn_capacity);
   cv.take(x->punish_list, M);
   cv.take(x->recyc_list, W > 1 ? W * (size_t)x->xr_cap : 0);
+  if (x->fused_mode == 3) {  // fused sharded step: record staging and the gathered top-k candidates
+    const size_t n1 = (size_t)xch_n1(*x), n4 = (size_t)xch_n4(*x);
+    cv.take(x->x_send, n1 > n4 ? n1 : n4);
+    cv.take(x->xk_keys, W * (size_t)xch_k_loc(*x));
+    cv.take(x->xk_cols, W * (size_t)xch_k_loc(*x));
+  } else {
+    x->x_send = nullptr;
+    x->xk_keys = nullptr;
+    x->xk_cols = nullptr;
+  }
   cv.take(x->blk, (size_t)BLK_ROWS * BH_BLK_STRIDE);
   cv.take(x->topk_ws, (size_t)BH_TOPK_WS_INTS);
   cv.take(x->mt_key, (size_t)BH_MT_N);
@@ -119,7 +130,13 @@ static int check_ctx(const bh_ctx* x) {
     return BH_E_BADARG;
   if (x->tm_blocks < 1 || x->tm_blocks > BH_BLK_STRIDE) return BH_E_BADARG;
   if (x->col_local < 1 || x->col_lo < 0 || x->col_lo + x->col_local > x->column_dim) return BH_E_BADARG;
-  if (x->col_local != x->column_dim && x->fused_mode) return BH_E_UNSUPPORTED;  // sharded: per-stage kernels
+  if (x->fused_mode < 0 || x->fused_mode > 3) return BH_E_BADARG;
+  if (x->col_local != x->column_dim && x->fused_mode && x->fused_mode != 3) return BH_E_UNSUPPORTED;
+  if (x->fused_mode == 3) {  // one kernel per shard, exchanges in-kernel: SP by column and TM by segment, same ranks
+    const int W = x->seg_world > 1 ? x->seg_world : 1;
+    if (W > BH_MAX_RANKS || x->xm_cap < 1 || x->xr_cap < 1) return BH_E_BADARG;
+    if ((long long)x->col_local * W != x->column_dim || x->col_lo != x->seg_rank * x->col_local) return BH_E_BADARG;
+  }
   if (x->syn_capacity < 32 || x->syn_capacity % 32 != 0) return BH_E_BADARG;
   if (x->rng_ring_words < (1 << 20) || (x->rng_ring_words & (x->rng_ring_words - 1))) return BH_E_BADARG;
   if (x->rng_step_words < 2 * BH_MT_N || 2 * x->rng_step_words > x->rng_ring_words) return BH_E_BADARG;
@@ -129,7 +146,7 @@ static int check_ctx(const bh_ctx* x) {
   if (x->jump_polys < 0 || x->rng_lookahead < 0) return BH_E_BADARG;
   if (x->seg_world > 1) {
     if (x->seg_rank < 0 || x->seg_rank >= x->seg_world || x->xm_cap < 1 || x->xr_cap < 1) return BH_E_BADARG;
-    if (x->fused_mode) return BH_E_UNSUPPORTED;  // the exchange sits between kernels
+    if (x->fused_mode && x->fused_mode != 3) return BH_E_UNSUPPORTED;  // the exchange sits between kernels
   }
   return 0;
 }
@@ -393,6 +410,7 @@ extern "C" int bh_tm_activate(const bh_ctx* x, void* stream) {
 
 // ---- segment shards: exchange 2 ----------------------------------------------------------
 extern "C" size_t bh_tm_shard_xch_ints(const bh_ctx* x) { return x ? (size_t)xch_ints(*x) : 0; }
+extern "C" size_t bh_xch_region_ints(const bh_ctx* x) { return x ? (size_t)xch_region_ints(*x) : 0; }
 
 static int tm_post_and_scan(const bh_ctx* x, cudaStream_t st) {
   int k = x->active_columns, kc = k * x->cell_dim;
@@ -444,20 +462,22 @@ extern "C" int bh_tm_step(const bh_ctx* x, int learning, void* stream) {
 static int fused_smem(const bh_ctx* x) {
   int a = x->mask_stride * 4, b = learn_apply_smem(x);
   int m = a > b ? a : b;
-  if (x->fused_mode == 2 && x->jump_polys > 0 && m < RNG_CHUNK_SMEM) m = RNG_CHUNK_SMEM;
+  if (x->fused_mode >= 2 && x->jump_polys > 0 && m < RNG_CHUNK_SMEM) m = RNG_CHUNK_SMEM;
   return m;
 }
 
 // One-time function attributes (per process): non-portable cluster sizes, dynamic smem.
 static int prepare_fused(int mode) {
-  static bool done[3] = {false, false, false};
-  if (mode < 1 || mode > 2) return BH_E_BADARG;
+  static bool done[4] = {false, false, false, false};
+  if (mode < 1 || mode > 3) return BH_E_BADARG;
   if (done[mode]) return 0;
   if (mode == 1) {
     CU_RET(cudaFuncSetAttribute(k_step_fused<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CU_RET(cudaFuncSetAttribute(k_step_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  } else {
+  } else if (mode == 2) {
     CU_RET(cudaFuncSetAttribute(k_step_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  } else {
+    CU_RET(cudaFuncSetAttribute(k_step_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
   done[mode] = true;
   return 0;
@@ -489,12 +509,19 @@ static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_step
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     CU_RET(cudaLaunchKernelEx(&cfg, k_step_fused<1>, *x, input_fixed, n_steps, learning, want_summary));
-  } else {
+  } else if (x->fused_mode == 2) {
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     CU_RET(cudaLaunchKernelEx(&cfg, k_step_fused<2>, *x, input_fixed, n_steps, learning, want_summary));
+  } else {
+    const int W = x->seg_world > 1 ? x->seg_world : 1;
+    for (int r = 0; r < W; ++r)
+      if (!x->xpeer[r]) return BH_E_BADARG;
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    CU_RET(cudaLaunchKernelEx(&cfg, k_step_shard, *x, input_fixed, n_steps, learning, want_summary));
   }
-  LAUNCHED(x->fused_mode == 1 ? "step_fused_cluster" : "step_fused_grid");
+  LAUNCHED(x->fused_mode == 1 ? "step_fused_cluster" : (x->fused_mode == 2 ? "step_fused_grid" : "step_shard"));
   return 0;
 }
 

@@ -1,0 +1,187 @@
+// One network sharded over several GPUs, the whole timestep of a shard as ONE
+// cooperative kernel: the phases of fused.cuh with the two exchanges of SURVEY.md 8e
+// done INSIDE the kernel over NVLink peer memory -- each rank stores its record
+// straight into every peer's receive buffer, publishes a sequence number with a
+// system-scope release store and waits for the peers' numbers -- instead of returning to
+// the host for an NCCL all-gather.  The same phase functions run behind
+// bh_sp_shard_* / bh_tm_shard_* with NCCL (tm_shard.cuh, sp_kernels.cuh).
+//
+// Exchange region of a rank (int32 units; identical layout on every rank; ctx.xpeer[p]
+// = base of rank p's region, mapped into this process):
+//   flags [2][8]               kind 0 = top-k candidates, 1 = segment records; entry s =
+//                              sequence number (step + 1) of the last record from rank s
+//   cand  [2 parity][G][n1]    n1 = 3 * k_loc rounded up to 4: k_loc float64 keys, k_loc columns
+//   segs  [2 parity][G][n4]    n4 = bh_tm_shard_xch_ints rounded up to 4
+// Records are double-buffered by step parity: a rank can be at most one exchange ahead
+// of a peer, because finishing an exchange needs every peer's record of that exchange.
+#pragma once
+
+#include "fused.cuh"
+#include "tm_shard.cuh"
+
+#define XCH_FLAG_INTS 16
+#define XCH_TIMEOUT_CYCLES 6000000000LL  // ~3 s at 2 GHz: a peer that never answers sets BH_ST_XCH_TIMEOUT
+
+__host__ __device__ __forceinline__ int xch_k_loc(const bh_ctx& c) {
+  return c.active_columns < c.col_local ? c.active_columns : c.col_local;
+}
+__host__ __device__ __forceinline__ long long xch_n1(const bh_ctx& c) { return (3LL * xch_k_loc(c) + 3) & ~3LL; }
+__host__ __device__ __forceinline__ long long xch_n4(const bh_ctx& c) { return (xch_ints(c) + 3) & ~3LL; }
+__host__ __device__ __forceinline__ long long xch_region_ints(const bh_ctx& c) {
+  return XCH_FLAG_INTS + 2LL * c.seg_world * (xch_n1(c) + xch_n4(c));
+}
+// this rank's receive area of exchange `kind` for the current step parity: record of rank s at + s * n
+__device__ __forceinline__ long long xch_recv_off(const bh_ctx& c, int kind, int par) {
+  const long long G = c.seg_world;
+  return XCH_FLAG_INTS + (kind == 0 ? (long long)par * G * xch_n1(c) : 2 * G * xch_n1(c) + (long long)par * G * xch_n4(c));
+}
+
+// All CTAs of the cooperative grid: deliver send[0..n) (n a multiple of 4, 16-byte aligned,
+// complete and visible grid-wide) to every rank's receive area and wait for all ranks'.
+__device__ void xch_exchange(const bh_ctx& c, int kind, const int* send, long long n, int b, int nb, unsigned int* bar) {
+  const int G = c.seg_world, me = c.seg_rank;
+  const int step = c.sc[BH_SC_STEP];
+  const int seq = step + 1;
+  const long long off = xch_recv_off(c, kind, step & 1) + (long long)me * n;
+  const int4* src = reinterpret_cast<const int4*>(send);
+  const long long n4 = n >> 2;
+  const long long gid = (long long)b * blockDim.x + threadIdx.x, gsz = (long long)nb * blockDim.x;
+#pragma unroll 1
+  for (int p = 0; p < G; ++p) {
+    int4* dst = reinterpret_cast<int4*>(c.xpeer[p] + off);
+#pragma unroll 1
+    for (long long i = gid; i < n4; i += gsz) dst[i] = src[i];
+  }
+  __threadfence_system();
+  grid_barrier(bar, nb);
+  if (b == 0 && threadIdx.x < G) {
+    const int s = threadIdx.x;
+    int* peer_flag = c.xpeer[s] + kind * 8 + me;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flag), "r"(seq) : "memory");
+    const int* my_flag = c.xpeer[me] + kind * 8 + s;
+    const long long t0 = clock64();
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(my_flag) : "memory");
+      if (v < seq && clock64() - t0 > XCH_TIMEOUT_CYCLES) {
+        atomicOr(&c.sc[BH_SC_STATUS], BH_ST_XCH_TIMEOUT);
+        break;
+      }
+    } while (v < seq);
+  }
+  grid_barrier(bar, nb);
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+    k_step_shard(const __grid_constant__ bh_ctx c, const uint32_t* input_fixed, int n_steps, int learning, int want_summary) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int nw = nb > 1 ? nb - 1 : 1;
+  const bool worker = b < nw;
+  const bool rng = b == nb - 1;
+  unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
+#define BH_SYNC() grid_barrier(bar, (unsigned)nb)
+  const int G = c.seg_world, me = c.seg_rank;
+  const int k = c.active_columns, k_loc = xch_k_loc(c);
+  const long long n1 = xch_n1(c), n4 = xch_n4(c);
+  int* region = c.xpeer[me];
+  const long long gid = (long long)b * blockDim.x + threadIdx.x, gsz = (long long)nb * blockDim.x;
+  const int pos0 = c.sc[BH_SC_INPUT_POS];
+  for (int step = 0; step < n_steps; ++step) {
+    const uint32_t* input =
+        input_fixed ? input_fixed : c.input_ring + (long long)((pos0 + step) % c.ring_len) * c.input_words;
+    const int par = c.sc[BH_SC_STEP] & 1;
+    // P0: overlap + boost of the local columns; draw #1 on the rng CTA
+    if (rng) ph_draw(c, 1, 1, nw);
+    if (nb == 1) ph_overlap<true>(c, input, s_dyn, 0, 1);
+    else if (!rng) ph_overlap<true>(c, input, s_dyn, b, nb - 1);
+    BH_SYNC();
+    // P1: this shard's best k_loc candidates -> record -> exchange 1 -> global top-k on every rank
+    int* scratch = reinterpret_cast<int*>(c.row_unacc);  // not in use yet this step
+    if (c.col_local >= 16384) {
+      topk_multi(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
+                 b, nb, bar);
+    } else if (b == 0) {
+      topk_core(reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr);
+    }
+    BH_SYNC();
+    {
+      double* rk = reinterpret_cast<double*>(c.x_send);
+      int* rc = c.x_send + 2 * k_loc;
+#pragma unroll 1
+      for (long long i = gid; i < k_loc; i += gsz) {
+        const int pos = scratch[i];
+        rk[i] = c.boosted[pos];
+        rc[i] = c.col_lo + pos;
+      }
+    }
+    BH_SYNC();
+    xch_exchange(c, 0, c.x_send, n1, b, nb, bar);
+    {
+      const int* recv = region + xch_recv_off(c, 0, par);
+#pragma unroll 1
+      for (long long i = gid; i < (long long)G * k_loc; i += gsz) {
+        const int s = (int)(i / k_loc), j = (int)(i - (long long)s * k_loc);
+        const int* rec = recv + s * n1;
+        const int lo = __ldcv(rec + 2 * j), hi = __ldcv(rec + 2 * j + 1);
+        c.xk_keys[i] = __hiloint2double(hi, lo);
+        c.xk_cols[i] = __ldcv(rec + 2 * k_loc + j);
+      }
+    }
+    BH_SYNC();
+    if ((long long)G * k_loc >= 16384) {
+      if (b == 0) retire_prev_flags(c);
+      topk_multi(c, reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k,
+                 c.active_cols + par * k, c.xk_cols, c.col_active, b, nb, bar);
+    } else if (b == 0) {
+      retire_prev_flags(c);
+      topk_core(reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k, c.active_cols + par * k, c.xk_cols,
+                c.col_active);
+    }
+    if (rng && nb > 1) ph_rng_speculate(c);
+    BH_SYNC();
+    // P2..P7 as in fused.cuh; learning and the segment scan touch only what this rank stores
+    if (learning) ph_sp_learn(c, input, b, nb);
+    ph_duty(c, b, nb);
+    if (worker) ph_select_a(c, b, nw);
+    BH_SYNC();
+    if (worker) {
+      ph_select_b(c, b, nw);
+      ph_learn_select_a(c, learning, b, nw);
+    }
+    BH_SYNC();
+    if (rng) ph_draw(c, 2, learning, nw);
+    if (worker) ph_learn_select_b(c, learning, b, nw);
+    BH_SYNC();
+    if (c.jump_polys > 0) {
+      ph_rng_chunks(c, s_dyn, b, nb);
+      BH_SYNC();
+    }
+    if (learning) ph_learn_apply(c, s_dyn, b, nb);
+    BH_SYNC();
+    ph_post(c, b, nb);
+    BH_SYNC();
+    if (worker) ph_activate_a(c, b, nw);
+    BH_SYNC();
+    // P8: this rank's record of matching / recyclable segments -> exchange 2 -> merged global lists
+    if (worker) ph_shard_pack(c, c.x_send, b, nw);
+    BH_SYNC();
+    xch_exchange(c, 1, c.x_send, n4, b, nb, bar);
+    ph_shard_merge(c, region + xch_recv_off(c, 1, par), b, nb, (int)n4);
+    BH_SYNC();
+    // P9: draw #3 (a phase of its own only when not covered, see fused.cuh), jitter, predictions
+    const int M = c.sc[BH_SC_X_MATCH] < c.match_capacity ? c.sc[BH_SC_X_MATCH] : c.match_capacity;
+    const bool ready3 = (long long)M <= c.rng64[R_READY3];
+    if (!ready3) {
+      if (rng) ph_draw(c, 3, 1, nw);
+      BH_SYNC();
+    } else if (rng) {
+      ph_draw3_ready(c, nw);
+    }
+    if (worker) ph_activate_finish(c, b, nw, ready3);
+    BH_SYNC();
+  }
+  if (want_summary) ph_summary(c, b, nb);
+  if (!input_fixed && b == 0 && threadIdx.x == 0) c.sc[BH_SC_INPUT_POS] = pos0 + n_steps;
+#undef BH_SYNC
+}

@@ -21,9 +21,9 @@ struct XchRecord {  // views into one rank's record of bh_tm_shard_xch_ints() in
 
 __host__ __device__ __forceinline__ long long xch_ints(const bh_ctx& c) { return 4 + 3LL * c.xm_cap + c.xr_cap; }
 
-__device__ __forceinline__ XchRecord xch_record(const bh_ctx& c, int* base, int rank) {
+__device__ __forceinline__ XchRecord xch_record(const bh_ctx& c, int* base, int rank, long long stride = 0) {
   XchRecord r;
-  r.hdr = base + rank * xch_ints(c);
+  r.hdr = base + rank * (stride ? stride : xch_ints(c));
   r.id = r.hdr + 4;
   r.pot = r.id + c.xm_cap;
   r.conn = r.pot + c.xm_cap;
@@ -74,12 +74,13 @@ __device__ void ph_shard_pack(const bh_ctx& c, int* send, int b, int nb) {
   }
 }
 
-// entries of list[0..n) (ascending) smaller than key
+// entries of list[0..n) (ascending) smaller than key.  Gathered records may have been written
+// by a peer GPU (shard_fused.cuh): they are read with ld.cv, never through L1.
 __device__ __forceinline__ int lower_count(const int* list, int n, int key) {
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (list[mid] < key) lo = mid + 1;
+    if (__ldcv(list + mid) < key) lo = mid + 1;
     else hi = mid;
   }
   return lo;
@@ -87,23 +88,23 @@ __device__ __forceinline__ int lower_count(const int* list, int n, int key) {
 
 // Merge the seg_world gathered records (rank order) into the global ascending lists:
 // m_seg / m_conn (+ seg_pot / seg_conn of those segments) and recyc_list.
-__device__ void ph_shard_merge(const bh_ctx& c, const int* recv, int b, int nb) {
+__device__ void ph_shard_merge(const bh_ctx& c, const int* recv, int b, int nb, long long stride = 0) {
   int* base = const_cast<int*>(recv);
   const int G = c.seg_world;
   const int gid0 = b * blockDim.x + threadIdx.x, gsz = nb * blockDim.x;
 #pragma unroll 1
   for (long long idx = gid0; idx < (long long)G * c.xm_cap; idx += gsz) {
     const int g = (int)(idx / c.xm_cap), j = (int)(idx - (long long)g * c.xm_cap);
-    const XchRecord me = xch_record(c, base, g);
-    if (j >= me.hdr[0]) continue;
-    const int s = me.id[j];
+    const XchRecord me = xch_record(c, base, g, stride);
+    if (j >= __ldcv(me.hdr)) continue;
+    const int s = __ldcv(me.id + j);
     int pos = j;
     for (int o = 0; o < G; ++o)
       if (o != g) {
-        const XchRecord other = xch_record(c, base, o);
-        pos += lower_count(other.id, other.hdr[0], s);
+        const XchRecord other = xch_record(c, base, o, stride);
+        pos += lower_count(other.id, __ldcv(other.hdr), s);
       }
-    const int pot = me.pot[j], conn = me.conn[j];
+    const int pot = __ldcv(me.pot + j), conn = __ldcv(me.conn + j);
     c.seg_pot[s] = pot;  // every rank knows the potentials of the matching segments
     c.seg_conn[s] = conn;
     if (pos < c.match_capacity) {
@@ -114,25 +115,25 @@ __device__ void ph_shard_merge(const bh_ctx& c, const int* recv, int b, int nb) 
 #pragma unroll 1
   for (long long idx = gid0; idx < (long long)G * c.xr_cap; idx += gsz) {
     const int g = (int)(idx / c.xr_cap), j = (int)(idx - (long long)g * c.xr_cap);
-    const XchRecord me = xch_record(c, base, g);
-    if (j >= me.hdr[1]) continue;
-    const int s = me.recyc[j];
+    const XchRecord me = xch_record(c, base, g, stride);
+    if (j >= __ldcv(me.hdr + 1)) continue;
+    const int s = __ldcv(me.recyc + j);
     int pos = j;
     for (int o = 0; o < G; ++o)
       if (o != g) {
-        const XchRecord other = xch_record(c, base, o);
-        pos += lower_count(other.recyc, other.hdr[1], s);
+        const XchRecord other = xch_record(c, base, o, stride);
+        pos += lower_count(other.recyc, __ldcv(other.hdr + 1), s);
       }
     c.recyc_list[pos] = s;
   }
   if (gid0 == 0) {
     int m = 0, ra = 0, rt = 0, st = 0;
     for (int g = 0; g < G; ++g) {
-      const XchRecord r = xch_record(c, base, g);
-      m += r.hdr[0];
-      ra += r.hdr[1];
-      rt += r.hdr[2];
-      st |= r.hdr[3];
+      const XchRecord r = xch_record(c, base, g, stride);
+      m += __ldcv(r.hdr);
+      ra += __ldcv(r.hdr + 1);
+      rt += __ldcv(r.hdr + 2);
+      st |= __ldcv(r.hdr + 3);
     }
     c.sc[BH_SC_X_MATCH] = m;
     c.sc[BH_SC_X_RECYC_AVAIL] = ra;
@@ -144,9 +145,11 @@ __device__ void ph_shard_merge(const bh_ctx& c, const int* recv, int b, int nb) 
 // After the merge and draw #3: jittered potential by rank in the global matching list
 // (projections.py:234-235), per-cell maximum (:236-237), active-segment count (:251).
 // Every rank computes all of it (the per-cell state is replicated).  Completes the step.
-__device__ void ph_activate_finish(const bh_ctx& c, int b, int nb) {
-  const int M = c.sc[BH_SC_M];
-  const long long off3 = c.rng64[R_OFF3], n3 = c.rng64[R_N3];
+// `ready`: draw #3 was bookkeeping only and may still be running on the drawing CTA.
+__device__ void ph_activate_finish(const bh_ctx& c, int b, int nb, bool ready = false) {
+  const int mx = c.sc[BH_SC_X_MATCH] < c.match_capacity ? c.sc[BH_SC_X_MATCH] : c.match_capacity;
+  const int M = ready ? mx : c.sc[BH_SC_M];
+  const long long off3 = c.rng64[R_OFF3], n3 = ready ? (long long)mx : c.rng64[R_N3];
 #pragma unroll 1
   for (int j = b * blockDim.x + threadIdx.x; j < M; j += nb * blockDim.x) {
     const int s = c.m_seg[j];

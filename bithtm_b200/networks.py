@@ -416,6 +416,18 @@ class HierarchicalTemporalMemory:
                               column_shard=shard, segment_shard=seg, **engine_kwargs)
         sp._attach(self._engine)
         tm._attach(self._engine)
+        if self._engine.ctx.fused_mode == 3:  # one kernel per shard, exchanges over peer memory
+            import torch
+
+            eng = self._engine
+            if eng.seg_world > 1 and column_shard is True:
+                from ._shard import map_exchange_regions
+
+                self.exchange_transport = map_exchange_regions(eng, process_group)
+            elif eng.seg_world <= 1:  # a single shard exchanges with itself
+                region = torch.zeros(eng.exchange_region_ints(), dtype=torch.int32, device=eng.device)
+                eng.set_exchange_regions([region.data_ptr()], keepalive=region)
+            # explicit (rank, world) tuples: the caller wires the regions (single-process tests)
 
     @property
     def engine(self):
@@ -431,6 +443,25 @@ class HierarchicalTemporalMemory:
         the step: nothing is read back and the host does not wait."""
         sp, tm, eng = self.spatial_pooler, self.temporal_memory, self._engine
         is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
+        if eng.ctx.fused_mode == 3:  # the shard's whole step is one kernel (exchanges inside)
+            if not sp._native_inhibition:
+                raise NotImplementedError('fused="shard" needs the built-in GlobalInhibition')
+            sp.boosting._bind(eng)
+            words = eng.pack_input(input)
+            tm._rng.before(eng)
+            eng.step_device(words, learning=learning)
+            if not return_state:
+                if tm._rng.mode != "lazy":
+                    raise ValueError('return_state=False needs rng_sync="lazy" (no per-step read-back)')
+                tm.last_state = None
+                return None
+            summary = eng.summary()
+            tm._rng.after(eng, summary)
+            tm_state = tm._finish(summary)
+            sp_state = sp.State(eng, active_column=tm_state._active_column)
+            sp_state._parity ^= 1
+            sp_state._group = sp._group
+            return sp_state, tm_state
         if not sp._native_inhibition or not is_host or eng.shard_world > 1 or eng.seg_world > 1 or not return_state:
             sp_state = sp.process(input, learning=learning)
             sp_state._group = sp._group

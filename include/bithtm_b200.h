@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 4
+#define BH_ABI_VERSION 5
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 8192
@@ -75,6 +75,8 @@ enum {
                                /* reference's np.argsort is undefined there)       */
 #define BH_ST_XCH_OVERFLOW 64  /* segment shards: a rank had more matching or      */
                                /* recyclable segments than the exchange carries    */
+#define BH_ST_XCH_TIMEOUT 128  /* fused sharded step: a peer's record never arrived */
+#define BH_MAX_RANKS 8
 
 typedef struct bh_ctx {
   /* ---- sizes --------------------------------------------------------------- */
@@ -98,7 +100,9 @@ typedef struct bh_ctx {
                            /* sp_perm/sp_mask/duty/overlaps/boosted are local-sized */
   int32_t ring_len;        /* rows in input_ring (0 = none)                        */
   int32_t fused_mode;      /* bh_step*: 0 = one kernel per stage, 1 = one kernel on a  */
-                           /* thread-block cluster, 2 = one cooperative-grid kernel   */
+                           /* thread-block cluster, 2 = one cooperative-grid kernel,  */
+                           /* 3 = one cooperative-grid kernel per SHARD with the two  */
+                           /* exchanges done in-kernel over peer memory (xpeer)       */
   int32_t seg_rank;        /* segment shard: this rank holds the synapse rows of the   */
   int32_t seg_world;       /* segments whose 64-id block b has b % seg_world ==       */
                            /* seg_rank (1 = all); syn_cell/syn_perm hold local rows   */
@@ -171,6 +175,9 @@ typedef struct bh_ctx {
   int32_t* learn_list;     /* [L_cap] learning_segment (projections.py:281 order)  */
   int32_t* punish_list;    /* [M_cap] punished_segment                             */
   int32_t* recyc_list;     /* [seg_world * xr_cap] segment shards: merged recyclable ids */
+  int32_t* x_send;         /* [max record] this rank's exchange record (fused_mode 3)    */
+  double* xk_keys;         /* [seg_world * k_loc] gathered top-k candidate keys          */
+  int32_t* xk_cols;        /* [seg_world * k_loc] and their global columns               */
   int32_t* blk;            /* [8][1024] per-CTA counts for ordered compaction      */
   int32_t* topk_ws;        /* [BH_TOPK_WS_INTS] workspace of the multi-CTA top-k   */
 
@@ -180,6 +187,10 @@ typedef struct bh_ctx {
   uint32_t* mt_jump;       /* [jump_polys][624] jump polynomials (caller-filled,    */
                            /* bithtm_b200/_mtjump.py) for multi-CTA production      */
   long long* rng64;        /* [16] producer / consumer cursors (csrc/mt19937.cuh)   */
+
+  /* ---- fused sharded step: exchange regions of all ranks, mapped into this process ---- */
+  int32_t* xpeer[BH_MAX_RANKS]; /* xpeer[r] = base of rank r's region of bh_xch_region_ints() */
+                           /* int32 (zero-filled by the caller; xpeer[seg_rank] is local)  */
 
   /* ---- scalars, input ring, host staging ---------------------------------------- */
   int32_t* sc;             /* [BH_SC_COUNT]                                        */
@@ -259,6 +270,11 @@ int bh_sp_shard_finish(const bh_ctx* ctx, const uint32_t* input_words_dev, const
  * bh_tm_shard_post: merges the seg_world gathered records (recv_dev, rank order), draws
  *                   rand(M), computes jitter / predictions; completes the timestep. */
 size_t bh_tm_shard_xch_ints(const bh_ctx* ctx);
+/* fused_mode 3: size (int32) of one rank's exchange region.  Every rank allocates one in
+ * memory its peers can map (CUDA IPC / symmetric memory), zero-fills it and passes all
+ * bases in ctx->xpeer; bh_step / bh_step_ring / bh_graph_* then run the shard's whole
+ * timestep as one kernel that exchanges the two records over NVLink itself. */
+size_t bh_xch_region_ints(const bh_ctx* ctx);
 int bh_tm_shard_pre(const bh_ctx* ctx, int learning, int32_t* send_dev, void* stream);
 int bh_tm_shard_post(const bh_ctx* ctx, const int32_t* recv_dev, void* stream);
 

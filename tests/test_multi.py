@@ -297,3 +297,83 @@ def test_segment_shards_single_process_emulation(name, world, steps):
     assert sum(len(p[0]) for p in parts) == orc.n_seg
     if True:
         assert recycled > 0, "the run never recycled a segment: the cross-shard path was not exercised"
+
+
+# ----------------------------------------------------------------------------- fused sharded step
+@pytest.mark.gpu
+def test_fused_shard_kernel_single_shard_matches_oracle():
+    """fused="shard" with ONE shard: the sharded phase sequence (candidate record, segment
+    record, merge) and the in-kernel exchange protocol run against the rank's own region;
+    results must equal the oracle's like every other execution mode."""
+    import bithtm_b200 as bithtm
+    from helpers import diff_records, golden_inputs, gpu_record, gpu_state_digest, load_golden, oracle_record, \
+        oracle_state_digest
+    from oracle.htm_oracle import HTMOracle, OracleConfig
+
+    info = load_golden("mid")
+    I, C, c, k, seed = info["I"], info["C"], info["c"], info["k"], info["seed"]
+    steps = 1000
+    xs = golden_inputs(info, steps)
+    np.random.seed(seed)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused="shard", fused_ctas=12)
+    assert htm.engine.ctx.fused_mode == 3
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    for t in range(steps):
+        rec = orc.step(xs[t])
+        sp_state, tm_state = htm.process(xs[t])
+        d = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not d, f"step {t}: {d}"
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,world,steps", [("tiny", 2, 600), ("mid", 2, 1100), ("odd", 3, 750), ("mid", 4, 950)])
+def test_fused_shard_kernels_concurrent_on_one_gpu(name, world, steps):
+    """`world` shards as `world` cooperative kernels running CONCURRENTLY on one GPU (one
+    stream each), exchanging their records through each other's regions exactly as they do
+    across GPUs over NVLink.  Every shard must reproduce the oracle."""
+    import torch
+
+    import bithtm_b200 as bithtm
+    from bithtm_b200 import _native as nat
+    from helpers import golden_inputs, load_golden
+    from oracle.digest import canonical_from_rows, state_digest
+    from oracle.htm_oracle import HTMOracle, OracleConfig
+
+    info = load_golden(name)
+    I, C, c, k, seed = info["I"], info["C"], info["c"], info["k"], info["seed"]
+    xs = golden_inputs(info, steps)
+    shards = _emulated_shards(info, world, fused="shard", fused_ctas=8)
+    regions = [torch.zeros(h.engine.exchange_region_ints(), dtype=torch.int32, device="cuda") for h in shards]
+    for h in shards:
+        h.engine.set_exchange_regions([r.data_ptr() for r in regions], keepalive=regions)
+        h.temporal_memory._rng.before(h.engine)
+    streams = [torch.cuda.Stream() for _ in shards]
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    torch.cuda.synchronize()
+    for t in range(steps):
+        rec = orc.step(xs[t])
+        words = shards[0].engine.pack_input(xs[t])
+        torch.cuda.synchronize()
+        for h, st in zip(shards, streams):
+            with torch.cuda.stream(st):
+                h.process(words, return_state=False)
+        torch.cuda.synchronize()
+        for r, h in enumerate(shards):
+            eng = h.engine
+            st = h.temporal_memory._finish(eng.summary())
+            where = f"step {t} shard {r}"
+            ds = st.distal_state
+            assert np.array_equal(st._active_column, rec.active_column), where
+            assert np.array_equal(st.winner_cell[0] * c + st.winner_cell[1], rec.winner_cell), where
+            assert st.n_segments == rec.n_segments, where
+            assert np.array_equal(ds.matching_segment, rec.matching_segment), where
+            assert np.array_equal(ds.matching_segment_jittered_potential.view(np.uint32),
+                                  np.asarray(rec.matching_jit, dtype=np.float32).view(np.uint32)), where
+    perm = np.concatenate([h.spatial_pooler.proximal_projection.permanence for h in shards])
+    duty = np.concatenate([h.spatial_pooler.boosting.duty_cycle for h in shards])
+    parts = [h.temporal_memory.distal_projection.export_local_segments() for h in shards]
+    proj = shards[-1].temporal_memory.distal_projection
+    owner, count, cells, pm = proj.export_segments(parts=parts)
+    got = state_digest(perm, duty, proj.bundle_segments, canonical_from_rows(owner, cells, pm))
+    assert got == state_digest(orc.permanence, orc.duty, orc.cell_nseg, orc.canonical_synapses())
