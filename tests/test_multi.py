@@ -86,7 +86,7 @@ def test_candidate_exchange_gloo_world2():
 
 
 # ----------------------------------------------------------------------------- 2 GPUs / NCCL
-def _nccl_worker(rank, world, port, result, name, steps):
+def _nccl_worker(rank, world, port, result, name, steps, fused="off"):
     import torch
     import torch.distributed as dist
 
@@ -100,7 +100,8 @@ def _nccl_worker(rank, world, port, result, name, steps):
     g = info["g"]
     xs = golden_inputs(info, steps)
     np.random.seed(info["seed"])
-    htm = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], column_shard=True)
+    kw = dict(fused="shard", fused_ctas=32) if fused == "shard" else {}
+    htm = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], column_shard=True, **kw)
     state_at = {int(s): int(d) for s, d in zip(g["state_steps"], g["state_digests"])}
     bad = None
     for t in range(steps):
@@ -129,10 +130,11 @@ def _nccl_worker(rank, world, port, result, name, steps):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,steps", [("mid", 500), ("tiny", 300)])
-def test_column_sharded_two_gpus_match_reference_trace(name, steps):
-    """Column-sharded SP (NCCL all-gather of candidates) + replicated TM on 2 GPUs:
-    every rank reproduces the single-network reference trace bit for bit."""
+@pytest.mark.parametrize("name,steps,fused", [("mid", 1000, "off"), ("tiny", 400, "off"), ("mid", 1000, "shard")])
+def test_column_sharded_two_gpus_match_reference_trace(name, steps, fused):
+    """Column-sharded SP + segment-sharded TM on 2 GPUs -- per-stage kernels with NCCL
+    all-gathers ("off"), or one kernel per shard exchanging over NVLink peer memory
+    ("shard") -- every rank reproduces the single-network reference trace bit for bit."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -142,7 +144,7 @@ def test_column_sharded_two_gpus_match_reference_trace(name, steps):
     ctx = mp.get_context("spawn")
     result = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, result, name, steps)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, result, name, steps, fused)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

@@ -4,7 +4,10 @@ ranks of a torchrun job: spatial pooler by column, temporal memory by segment id
 NCCL all-gathers per timestep.  Permanence rows are drawn on each device (performance
 run; parity of the sharded path is tests/test_multi.py).
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/cfg3_sharded.py [steps] [C] [I]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/cfg3_sharded.py [steps] [C] [I] [mode]
+
+mode = "nccl" (default: per-stage kernels, NCCL all-gathers issued by the host) or "fused" (one cooperative
+kernel per shard and per 50 steps, exchanges in-kernel over NVLink peer memory).
 """
 import json
 import os
@@ -24,6 +27,7 @@ def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     C = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
     I = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
+    mode = sys.argv[4] if len(sys.argv) > 4 else "nccl"
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -39,27 +43,37 @@ def main():
     perm = torch.randn(C // world, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
     np.random.seed(0)
     sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
+    chunk = 50
     htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy",
                                             column_shard=True if world > 1 else None,
                                             max_segments=1 << 21, max_synapses_per_segment=64,
-                                            fused="off" if world > 1 else "off")
+                                            fused="shard" if mode == "fused" else "off",
+                                            ring_len=2 * patterns if mode == "fused" else 0)
     del perm
     sp.proximal_projection._host_permanence = None
     torch.cuda.empty_cache()
     eng = htm.engine
     htm.temporal_memory._rng.before(eng)
     words = [eng.pack_input(x) for x in xs[:patterns * 2]]
+    graph = None
+    if mode == "fused":
+        eng.load_ring(xs[:patterns * 2])
+        graph = eng.graph(chunk, learning=True)
+        if rank == 0:
+            print("exchange transport:", getattr(htm, "exchange_transport", "local"), flush=True)
     torch.cuda.synchronize()
     times = []
-    chunk = 50
     for t0 in range(0, steps, chunk):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for t in range(t0, min(t0 + chunk, steps)):
-            htm.process(words[t % len(words)], return_state=False)
+        if graph is not None:
+            eng.launch_graph(graph, chunk)
+        else:
+            for t in range(t0, min(t0 + chunk, steps)):
+                htm.process(words[t % len(words)], return_state=False)
         b.record()
         torch.cuda.synchronize()
         ms = torch.tensor([a.elapsed_time(b) / chunk], device="cuda")
@@ -73,7 +87,7 @@ def main():
     if rank == 0:
         print(json.dumps({"workload": f"cfg3 sharded: {C} columns x {I} inputs, k={k}", "n_gpus": world,
                           "ms_per_step": times[-1], "steps_per_s": 1e3 / times[-1],
-                          "exchanges_per_step": 2 if world > 1 else 0}))
+                          "exchanges_per_step": 2 if world > 1 else 0, "mode": mode}))
     if world > 1:
         dist.destroy_process_group()
 
