@@ -197,7 +197,7 @@ class Engine:
             "x_send": max((3 * min(k, CL) + 3) // 4 * 4, (4 + 3 * x.xm_cap + x.xr_cap + 3) // 4 * 4)
             if x.fused_mode == 3 else 0,
             "xk_keys": W * min(k, CL) if x.fused_mode == 3 else 0,
-            "xk_cols": W * min(k, CL) if x.fused_mode == 3 else 0, "blk": 8 * 1024, "topk_ws": 8192, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
+            "xk_cols": W * min(k, CL) if x.fused_mode == 3 else 0, "blk": 8 * 1024, "topk_ws": 81920, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
             "rng64": nat.R_COUNT, "sc": nat.SC_COUNT,
             "input_ring": x.ring_len * x.input_words, "input_dev": x.mask_stride,
             "summary_dev": nat.summary_ints(k),

@@ -36,10 +36,15 @@ class StreamBatch:
         self.engines = engines
         self._graphs = {}
 
-    def load_inputs(self, inputs):
-        """inputs[i]: bool [ring_len, input_dim] for stream i (uploaded into its device ring)."""
-        for h, e, x in zip(self.networks, self.engines, inputs):
-            h.temporal_memory._rng.before(e)  # adopt np.random's state once (lazy mode)
+    def load_inputs(self, inputs, rng_states=None):
+        """inputs[i]: bool [ring_len, input_dim] for stream i (uploaded into its device ring).
+        rng_states[i]: the ``np.random.get_state()`` tuple stream i continues from (default: the
+        global np.random state at this call, for every stream)."""
+        for i, (h, e, x) in enumerate(zip(self.networks, self.engines, inputs)):
+            if rng_states is not None:
+                h.temporal_memory._rng.adopt(e, rng_states[i])
+            else:
+                h.temporal_memory._rng.before(e)  # adopt np.random's state once (lazy mode)
             e.load_ring(x)
 
     def _graph(self, steps, learning):

@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     // P1: global inhibition (one CTA)
     if (MODE == 2 && c.column_dim >= 16384) {  // grid-wide selection (its own barriers inside)
       if (b == 0) retire_prev_flags(c);
-      topk_multi(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, c.active_columns,
-                 c.active_cols + (c.sc[BH_SC_STEP] & 1) * c.active_columns, nullptr, c.col_active, b, nb, bar);
+      topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, c.active_columns,
+                c.active_cols + (c.sc[BH_SC_STEP] & 1) * c.active_columns, nullptr, c.col_active, b, nb, bar);
     } else if (b == 0) {
       ph_topk(c);
     }

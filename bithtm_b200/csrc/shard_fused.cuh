@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     // P1: this shard's best k_loc candidates -> record -> exchange 1 -> global top-k on every rank
     int* scratch = reinterpret_cast<int*>(c.row_unacc);  // not in use yet this step
     if (c.col_local >= 16384) {
-      topk_multi(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
-                 b, nb, bar);
+      topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
+                b, nb, bar);
     } else if (b == 0) {
       topk_core(reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr);
     }
@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_SYNC();
     if ((long long)G * k_loc >= 16384) {
       if (b == 0) retire_prev_flags(c);
-      topk_multi(c, reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k,
-                 c.active_cols + par * k, c.xk_cols, c.col_active, b, nb, bar);
+      topk_grid(c, reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k,
+                c.active_cols + par * k, c.xk_cols, c.col_active, b, nb, bar);
     } else if (b == 0) {
       retire_prev_flags(c);
       topk_core(reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k, c.active_cols + par * k, c.xk_cols,

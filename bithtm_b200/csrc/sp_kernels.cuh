@@ -9,6 +9,37 @@
 
 #define SP_THREADS 256
 
+// workspace of topk_grid inside ctx.topk_ws (ints; after the 8192 ints of topk_multi)
+#define TK2_BASE 8192
+#define TK2_VALID 4        // 1 when u64[0] = max key, u64[1] = ~min key were published by ph_overlap<true>
+#define TK2_CALL 5         // call counter: parity selects one of two histogram / candidate buffers
+#define TK2_PAR0 16
+#define TK2_PSIZE 3344     // per parity: ghist[256], count (+7 pad), cand_idx[1024], cand_key u64[1024]
+#define TK2_TAB (TK2_PAR0 + 2 * TK2_PSIZE)  // [256 CTAs][256]: keys of a CTA's range with a larger digit
+#define TK2_MAX_CTAS 256
+#define TK2_INTS (TK2_TAB + TK2_MAX_CTAS * 256)
+
+__device__ __noinline__ unsigned long long block_reduce_u64(unsigned long long v, bool want_max,
+                                                               unsigned long long* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long n = __shfl_xor_sync(BH_FULL, v, o);
+    v = want_max ? (n > v ? n : v) : (n < v ? n : v);
+  }
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  unsigned long long r = sm[lane < nw ? lane : 0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long n = __shfl_xor_sync(BH_FULL, r, o);
+    r = want_max ? (n > r ? n : r) : (n < r ? n : r);
+  }
+  return r;
+}
+
+
 // ---------------------------------------------------------------------------------
 // Connected mask from the float64 permanence (one warp per 32 consecutive inputs).
 // ---------------------------------------------------------------------------------
@@ -68,6 +99,7 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
   const uint4* mask4 = reinterpret_cast<const uint4*>(c.sp_mask);
   const uint4* s_in4 = reinterpret_cast<const uint4*>(s_in);
   const int n_rows = c.col_local;  // this rank's columns (all of them when not sharded)
+  unsigned long long key_min = ~0ull, key_max = 0ull;  // of the boosted keys this thread wrote (for topk_grid)
 #pragma unroll 1
   for (int base = warp_global * rows_per_warp; base < n_rows; base += n_warps * rows_per_warp) {
     int row = base + lane / group;
@@ -96,8 +128,23 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
       c.overlaps[row] = acc;
       if (BOOST) {
         float f = bh_np_expf(__fmul_rn(c.boost_coef, c.duty[row]));
-        c.boosted[row] = __dmul_rn((double)f, (double)acc);
+        const double bo = __dmul_rn((double)f, (double)acc);
+        c.boosted[row] = bo;
+        const unsigned long long key = (unsigned long long)__double_as_longlong(bo);
+        key_min = key < key_min ? key : key_min;
+        key_max = key > key_max ? key : key_max;
       }
+    }
+  }
+  if (BOOST) {  // range of the keys, for the grid-wide top-k that follows (saves it a pass and a barrier)
+    __shared__ unsigned long long s_mm[32];
+    key_min = block_reduce_u64(key_min, false, s_mm);
+    key_max = block_reduce_u64(key_max, true, s_mm);
+    if (threadIdx.x == 0) {
+      unsigned long long* w64 = reinterpret_cast<unsigned long long*>(c.topk_ws + TK2_BASE);
+      atomicMax(&w64[0], key_max);
+      atomicMax(&w64[1], ~key_min);
+      c.topk_ws[TK2_BASE + TK2_VALID] = 1;
     }
   }
 }
@@ -131,26 +178,6 @@ __global__ void k_boost(const __grid_constant__ bh_ctx c) {
 // regularizations.py:28-29 (np.argpartition's tie-break/order are undefined).
 // ---------------------------------------------------------------------------------
 #define TOPK_THREADS 1024
-
-__device__ __noinline__ unsigned long long block_reduce_u64(unsigned long long v, bool want_max,
-                                                               unsigned long long* sm) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long n = __shfl_xor_sync(BH_FULL, v, o);
-    v = want_max ? (n > v ? n : v) : (n < v ? n : v);
-  }
-  __syncthreads();
-  if (lane == 0) sm[w] = v;
-  __syncthreads();
-  unsigned long long r = sm[lane < nw ? lane : 0];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long n = __shfl_xor_sync(BH_FULL, r, o);
-    r = want_max ? (n > r ? n : r) : (n < r ? n : r);
-  }
-  return r;
-}
 
 // keys[0..n): select the k largest (ties -> lower position); positions ascending are
 // written as out[i] = map ? map[pos] : pos, and flags[that value] = 1 when flags != null.
@@ -554,21 +581,249 @@ __device__ void topk_multi(const bh_ctx& c, const unsigned long long* keys, cons
   }
 }
 
+// ---------------------------------------------------------------------------------
+// (b) grid-wide selection with TWO grid barriers (topk_multi needs seven): the key range
+// comes from the producer (ph_overlap<true>), one 8-bit histogram pass finds the bin of
+// the k-th key, every CTA publishes how many of its keys lie in higher bins, the bin's
+// members (<= 1024) are gathered, and then every CTA -- redundantly, from the same data
+// -- ranks them, derives the exact k-th (key, index) and its own output offset.  Falls
+// back to topk_multi for degenerate inputs (all keys equal, > 1024 keys in the bin).
+// Workspace: ctx.topk_ws + TK2_BASE (see the TK2_* layout above).
+// ---------------------------------------------------------------------------------
+__device__ void topk_grid(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
+                          const int* map, uint8_t* flags, int b, int nb, unsigned int* bar) {
+  __shared__ int hist[256];
+  __shared__ int s_scan[32];
+  __shared__ unsigned long long s_u64[32];
+  __shared__ unsigned long long cand_key[TOPK_THREADS];
+  __shared__ int cand_idx[TOPK_THREADS];
+  __shared__ int s_bin, s_rem, s_ncand, s_kth_idx;
+  __shared__ unsigned long long s_kth_key;
+  int* ws = c.topk_ws + TK2_BASE;
+  unsigned long long* w64 = reinterpret_cast<unsigned long long*>(ws);
+  const int t = threadIdx.x, lane = t & 31, NT = blockDim.x;
+  const Range rg = block_range(n, b, nb);
+  const bool valid = ws[TK2_VALID] != 0;
+  const int par = ws[TK2_CALL] & 1;
+#ifdef BH_TOPK_STAMPS
+  unsigned long long* tk_stamps = reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE) + 40;
+  int tk_i = 0;
+#define TK_STAMP()                                              \
+  do {                                                          \
+    if (b == 0 && t == 0) {                                     \
+      unsigned long long t_;                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));    \
+      tk_stamps[tk_i] = t_;                                     \
+    }                                                           \
+    ++tk_i;                                                     \
+  } while (0)
+#else
+#define TK_STAMP() do {} while (0)
+#endif
+  TK_STAMP();
+  if (nb > TK2_MAX_CTAS) {
+    topk_multi(c, keys, n, k, out, map, flags, b, nb, bar);
+    return;
+  }
+  if (!valid) {  // nobody published the key range: one extra pass and barrier
+    unsigned long long mn = ~0ull, mx = 0ull;
+#pragma unroll 1
+    for (int j = rg.begin + t; j < rg.end; j += NT) {
+      const unsigned long long key = keys[j];
+      mn = key < mn ? key : mn;
+      mx = key > mx ? key : mx;
+    }
+    mn = block_reduce_u64(mn, false, s_u64);
+    mx = block_reduce_u64(mx, true, s_u64);
+    if (t == 0 && rg.begin < rg.end) {
+      atomicMax(&w64[0], mx);
+      atomicMax(&w64[1], ~mn);
+    }
+    grid_barrier(bar, nb);
+  }
+  const unsigned long long mx = w64[0], mn = ~w64[1];
+  const int consumed = (mn == mx) ? 64 : __clzll((long long)(mn ^ mx));
+  const int shift = (64 - consumed - 8) > 0 ? (64 - consumed - 8) : 0;
+  const int width = 64 - consumed - shift;
+  const unsigned dmask = (1u << width) - 1u;
+  int* ghist = ws + TK2_PAR0 + par * TK2_PSIZE;
+  int* gcount = ghist + 256;
+  int* gidx = ghist + 264;
+  unsigned long long* gkey = reinterpret_cast<unsigned long long*>(ghist + 264 + TOPK_THREADS);
+  int* tab = ws + TK2_TAB;
+  const bool degenerate = consumed == 64;  // all keys equal (uniform over the grid)
+
+  // stage 1: local histogram -> global histogram + this CTA's "keys in higher bins" table
+  if (!degenerate) {
+#pragma unroll 1
+    for (int i = t; i < 256; i += NT) hist[i] = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int base = rg.begin; base < rg.end; base += NT) {
+      const int j = base + t;
+      const bool in = j < rg.end;
+      const int d = in ? (int)((keys[j] >> shift) & dmask) : -1;
+      const unsigned peers = __match_any_sync(BH_FULL, d);
+      if (in && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], __popc(peers));
+    }
+    __syncthreads();
+    if (t < 256) {  // global histogram; suffix sums of the local one (8 warps: shuffle scan + warp totals)
+      const int h = hist[t];
+      if (h) atomicAdd(&ghist[t], h);
+      int incl = h;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_down_sync(BH_FULL, incl, o);
+        if (lane + o < 32) incl += v;
+      }
+      if (lane == 0) s_scan[t >> 5] = incl;  // total of bins [32w, 32w + 32)
+      hist[t] = incl - h;                    // bins of the same warp above t
+    }
+    __syncthreads();
+    if (t < 256) {
+      int above = hist[t];
+      for (int w = (t >> 5) + 1; w < 8; ++w) above += s_scan[w];
+      tab[b * 256 + t] = above;
+    }
+  }
+  TK_STAMP();
+  grid_barrier(bar, nb);
+  TK_STAMP();
+  // stage 2: the bin of the k-th key (every CTA, from the same global histogram); gather its members
+  if (!degenerate && t < 32) {
+    int local[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      local[i] = ghist[255 - (lane * 8 + i)];
+      sum += local[i];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(BH_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int before = incl - sum;
+    if (before < k && incl >= k) {
+      int r = k - before;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (r > 0 && local[i] >= r) {
+          s_bin = 255 - (lane * 8 + i);
+          s_rem = r;
+          s_ncand = local[i];
+          r = -1;
+        } else if (r > 0) {
+          r -= local[i];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const bool fallback = degenerate || s_ncand > TOPK_THREADS;  // uniform over the grid
+  const int bin = s_bin, rem = s_rem;
+  if (!fallback) {
+#pragma unroll 1
+    for (int j = rg.begin + t; j < rg.end; j += NT) {
+      const unsigned long long key = keys[j];
+      if ((int)((key >> shift) & dmask) == bin) {
+        const int p = atomicAdd(gcount, 1);
+        gkey[p] = key;
+        gidx[p] = j;
+      }
+    }
+  }
+  TK_STAMP();
+  grid_barrier(bar, nb);
+  TK_STAMP();
+  if (b == 0) {  // leave the OTHER buffer and the key range clean for the next call; advance the parity
+    int* oh = ws + TK2_PAR0 + (par ^ 1) * TK2_PSIZE;
+#pragma unroll 1
+    for (int i = t; i < 264; i += NT) oh[i] = 0;
+    if (t == 0) {
+      w64[0] = 0ull;
+      w64[1] = 0ull;
+      ws[TK2_VALID] = 0;
+      ws[TK2_CALL] = par ^ 1;
+    }
+  }
+  if (fallback) {  // degenerate input: the general algorithm (own workspace)
+    topk_multi(c, keys, n, k, out, map, flags, b, nb, bar);
+    return;
+  }
+  // stage 3 (every CTA): exact k-th (key, index); own output offset; ordered write
+  const int nc = *gcount;
+#pragma unroll 1
+  for (int i = t; i < nc; i += NT) {
+    cand_key[i] = gkey[i];
+    cand_idx[i] = gidx[i];
+  }
+  __syncthreads();
+  if (t < nc) {
+    const unsigned long long mk = cand_key[t];
+    const int mi = cand_idx[t];
+    int ahead = 0;
+#pragma unroll 2
+    for (int i = 0; i < nc; ++i) {
+      const unsigned long long ok = cand_key[i];
+      ahead += (ok > mk || (ok == mk && cand_idx[i] < mi)) ? 1 : 0;
+    }
+    if (ahead == rem - 1) {
+      s_kth_key = mk;
+      s_kth_idx = mi;
+    }
+  }
+  __syncthreads();
+  const unsigned long long kth_key = s_kth_key;
+  const int kth_idx = s_kth_idx;
+  TK_STAMP();
+  int before = 0;
+  if (t < nc) {  // selected members of the bin that precede this CTA's range
+    const unsigned long long mk = cand_key[t];
+    const int mi = cand_idx[t];
+    before = (mi < rg.begin && (mk > kth_key || (mk == kth_key && mi <= kth_idx))) ? 1 : 0;
+  }
+#pragma unroll 1
+  for (int i = t; i < b; i += NT) before += tab[i * 256 + bin];  // keys of earlier ranges in higher bins
+  int base_sel = block_sum(before, s_scan);
+#pragma unroll 1
+  for (int tile = rg.begin; tile < rg.end; tile += NT) {
+    const int j = tile + t;
+    const unsigned long long key = j < rg.end ? keys[j] : 0ull;
+    const bool take = j < rg.end && (key > kth_key || (key == kth_key && j <= kth_idx));
+    int sel_total;
+    const int pos = base_sel + block_excl_scan(take ? 1 : 0, s_scan, sel_total);
+    if (take && pos < k) {
+      const int col = map ? map[j] : j;
+      out[pos] = col;
+      if (flags) flags[col] = 1;
+    }
+    base_sel += sel_total;
+  }
+  TK_STAMP();
+  if (b == 0 && t == 0) {
+#ifdef BH_TOPK_STAMPS
+    tk_stamps[15] = (unsigned long long)nc | ((unsigned long long)valid << 32);
+#endif
+  }
+#undef TK_STAMP
+}
+
 // stand-alone cooperative kernels built on topk_multi (grid = one CTA per SM)
 __global__ void __launch_bounds__(TOPK_THREADS, 1) k_topk_multi(const __grid_constant__ bh_ctx c) {
   unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
   if (blockIdx.x == 0) retire_prev_flags(c);
   const int k = c.active_columns;
-  topk_multi(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, k,
-             c.active_cols + (c.sc[BH_SC_STEP] & 1) * k, nullptr, c.col_active, blockIdx.x, gridDim.x, bar);
+  topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, k,
+            c.active_cols + (c.sc[BH_SC_STEP] & 1) * k, nullptr, c.col_active, blockIdx.x, gridDim.x, bar);
 }
 
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
     k_topk_shard_local_multi(const __grid_constant__ bh_ctx c, int* scratch, double* cand_keys, int32_t* cand_cols) {
   unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
   const int k_loc = c.active_columns < c.col_local ? c.active_columns : c.col_local;
-  topk_multi(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
-             blockIdx.x, gridDim.x, bar);
+  topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
+            blockIdx.x, gridDim.x, bar);
   grid_barrier(bar, gridDim.x);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k_loc; i += gridDim.x * blockDim.x) {
     const int pos = scratch[i];

@@ -60,6 +60,14 @@ class _RngLink:
         eng.set_rng_state(self._key, pos)
         self._seeded = True
 
+    def adopt(self, eng, state):
+        """Continue the device stream from an explicit ``np.random.get_state()`` tuple."""
+        key, pos = np.asarray(state[1], dtype=np.uint32), int(state[2])
+        self._key[:] = key
+        self._pos = pos
+        eng.set_rng_state(self._key, pos)
+        self._seeded = True
+
     def after(self, eng, summary=None):
         if self.mode == "lazy":
             return

@@ -32,7 +32,7 @@ extern "C" {
 #define BH_ABI_VERSION 5
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
-#define BH_TOPK_WS_INTS 8192
+#define BH_TOPK_WS_INTS 81920
 
 /* error codes (negative); CUDA errors are returned as -(1000 + cudaError_t) */
 #define BH_E_BADARG (-1)

@@ -423,20 +423,22 @@ def test_stream_batch_equals_streams_stepped_alone():
 
     def build(seed):
         np.random.seed(seed)
-        return bithtm.HierarchicalTemporalMemory(I, C, c, k, rng_sync="lazy", ring_len=steps, max_segments=1 << 12,
-                                                 fused="cluster", fused_ctas=4)
+        h = bithtm.HierarchicalTemporalMemory(I, C, c, k, rng_sync="lazy", ring_len=steps, max_segments=1 << 12,
+                                              fused="cluster", fused_ctas=4)
+        return h, np.random.get_state()  # every stream continues from its own state
 
     alone = []
     for s, xs in zip(seeds, inputs):
-        h = build(s)
+        h, state = build(s)
         eng = h.engine
-        h.temporal_memory._rng.before(eng)
+        h.temporal_memory._rng.adopt(eng, state)
         eng.load_ring(xs)
         eng.launch_graph(eng.graph(steps, learning=True), steps)
         alone.append(gpu_state_digest(h))
-    nets = [build(s) for s in seeds]
+    built = [build(s) for s in seeds]
+    nets = [h for h, _ in built]
     batch = bithtm.StreamBatch(nets)
-    batch.load_inputs(inputs)
+    batch.load_inputs(inputs, rng_states=[st for _, st in built])
     for _ in range(4):
         batch.run(steps // 4)
     batch.check_status()

@@ -62,6 +62,10 @@ def main():
     print(f"last 50 steps: {np.mean(times[-50:]):.3f} ms/step -> {1e3 / np.mean(times[-50:]):.1f} steps/s")
     for name, v in zip(PHASES, acc):
         print(f"  {name:32s} {v / 1e3:9.2f} us")
+    if os.environ.get("BH_TOPK_STAMPS"):  # library built with -DBH_TOPK_STAMPS: stages of topk_grid (last step)
+        st = eng.buf["blk"][7 * 1024 + 80:7 * 1024 + 80 + 32].cpu().numpy().view(np.uint64)
+        print("  topk_grid stages (ns):", np.diff(st[:7].astype(np.int64)).tolist(), "candidates", int(st[15] & 0xffffffff),
+              "range published", int(st[15] >> 32))
 
 
 if __name__ == "__main__":
