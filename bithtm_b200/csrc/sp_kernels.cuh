@@ -136,11 +136,14 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
       }
     }
   }
-  if (BOOST) {  // range of the keys, for the grid-wide top-k that follows (saves it a pass and a barrier)
-    __shared__ unsigned long long s_mm[32];
-    key_min = block_reduce_u64(key_min, false, s_mm);
-    key_max = block_reduce_u64(key_max, true, s_mm);
-    if (threadIdx.x == 0) {
+  if (BOOST) {  // range of the keys, for the top-k that follows (saves it a pass): one red per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(BH_FULL, key_min, o), z = __shfl_xor_sync(BH_FULL, key_max, o);
+      key_min = a < key_min ? a : key_min;
+      key_max = z > key_max ? z : key_max;
+    }
+    if (lane == 0 && key_max >= key_min) {
       unsigned long long* w64 = reinterpret_cast<unsigned long long*>(c.topk_ws + TK2_BASE);
       atomicMax(&w64[0], key_max);
       atomicMax(&w64[1], ~key_min);
@@ -179,15 +182,28 @@ __global__ void k_boost(const __grid_constant__ bh_ctx c) {
 // ---------------------------------------------------------------------------------
 #define TOPK_THREADS 1024
 
+// Shared-memory scratch of the top-k variants (one instance per kernel: they never run at
+// the same time inside a CTA).
+struct TopkScratch {
+  unsigned long long cand_key[TOPK_THREADS];
+  int cand_idx[TOPK_THREADS];
+  int hist[2048];
+};
+__device__ __forceinline__ TopkScratch& topk_scratch() {
+  __shared__ TopkScratch s;
+  return s;
+}
+
 // keys[0..n): select the k largest (ties -> lower position); positions ascending are
 // written as out[i] = map ? map[pos] : pos, and flags[that value] = 1 when flags != null.
-__device__ void topk_core(const unsigned long long* keys, const int C, const int k, int* out, const int* map,
+__device__ __noinline__ void topk_core(const unsigned long long* keys, const int C, const int k, int* out, const int* map,
                           uint8_t* flags) {
-  __shared__ int hist[256];
+  TopkScratch& sm = topk_scratch();
+  int* hist = sm.hist;
+  unsigned long long* cand_key = sm.cand_key;
+  int* cand_idx = sm.cand_idx;
   __shared__ int s_scan[32];
   __shared__ unsigned long long s_u64[32];
-  __shared__ unsigned long long cand_key[TOPK_THREADS];
-  __shared__ int cand_idx[TOPK_THREADS];
   __shared__ int s_bin, s_rem, s_ncand, s_kth_idx;
   __shared__ unsigned long long s_kth_key;
   const int t = threadIdx.x, lane = t & 31, NT = blockDim.x;
@@ -333,6 +349,145 @@ __device__ void topk_core(const unsigned long long* keys, const int C, const int
   }
 }
 
+// ---------------------------------------------------------------------------------
+// (b) for small column counts (C <= 4 keys per thread, one CTA): the same canonical
+// selection with every key held in registers.  One 11-bit histogram pass over the bits
+// below the keys' common prefix finds the bin of the k-th key (a handful of members at
+// these sizes), its members are ranked by counting, and the ordered compaction is a
+// single block scan because thread order is index order.  The key range comes from the
+// producer (ph_overlap<true>, ctx.topk_ws) when `ws` says so.  Falls back to topk_core.
+// ---------------------------------------------------------------------------------
+#define TOPK_SMALL_KPT 4
+__device__ __noinline__ void topk_small(const unsigned long long* keys, const int C, const int k, int* out, const int* map,
+                           uint8_t* flags, int* ws) {
+  TopkScratch& sm = topk_scratch();
+  int* hist = sm.hist;
+  unsigned long long* cand_key = sm.cand_key;
+  int* cand_idx = sm.cand_idx;
+  __shared__ int s_scan[32];
+  __shared__ unsigned long long s_u64[32];
+  __shared__ int s_bin, s_rem, s_ncand, s_kth_idx, s_cnt;
+  __shared__ unsigned long long s_kth_key;
+  const int t = threadIdx.x, NT = blockDim.x;
+  const int kpt = (C + NT - 1) / NT;  // keys per thread, <= TOPK_SMALL_KPT (caller checks)
+  unsigned long long key[TOPK_SMALL_KPT];
+  unsigned long long mn = ~0ull, mx = 0ull;
+#pragma unroll
+  for (int i = 0; i < TOPK_SMALL_KPT; ++i) {
+    const int j = t * kpt + i;
+    const bool in = i < kpt && j < C;
+    key[i] = in ? keys[j] : 0ull;
+    if (in) {
+      mn = key[i] < mn ? key[i] : mn;
+      mx = key[i] > mx ? key[i] : mx;
+    }
+  }
+  unsigned long long* w64 = reinterpret_cast<unsigned long long*>(ws);
+  if (ws && ws[TK2_VALID]) {  // published by the overlap phase; consumed (reset) here
+    mx = w64[0];
+    mn = ~w64[1];
+    __syncthreads();
+    if (t == 0) {
+      w64[0] = 0ull;
+      w64[1] = 0ull;
+      ws[TK2_VALID] = 0;
+    }
+  } else {
+    mn = block_reduce_u64(mn, false, s_u64);
+    mx = block_reduce_u64(mx, true, s_u64);
+  }
+  const int consumed = (mn == mx) ? 64 : __clzll((long long)(mn ^ mx));
+  if (consumed == 64) {  // all keys equal: the general algorithm handles the tie rule
+    topk_core(keys, C, k, out, map, flags);
+    return;
+  }
+  const int shift = (64 - consumed - 11) > 0 ? (64 - consumed - 11) : 0;
+  const int width = 64 - consumed - shift;
+  const unsigned dmask = (1u << width) - 1u;
+#pragma unroll 1
+  for (int i = t; i < 2048; i += NT) hist[i] = 0;
+  if (t == 0) s_cnt = 0;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < TOPK_SMALL_KPT; ++i)
+    if (i < kpt && t * kpt + i < C) atomicAdd(&hist[(int)((key[i] >> shift) & dmask)], 1);
+  __syncthreads();
+  {  // bins in descending order, 2048 / NT per thread; ordered block scan finds the bin of the k-th key
+    const int per = (2048 + NT - 1) / NT;
+    int sum = 0;
+    for (int i = 0; i < per; ++i) {
+      const int bin = 2047 - (t * per + i);
+      sum += bin >= 0 ? hist[bin] : 0;
+    }
+    int total;
+    const int before = block_excl_scan(sum, s_scan, total);
+    if (before < k && before + sum >= k) {
+      int r = k - before;
+      for (int i = 0; i < per; ++i) {
+        const int bin = 2047 - (t * per + i);
+        const int h = bin >= 0 ? hist[bin] : 0;
+        if (r > 0 && h >= r) {
+          s_bin = bin;
+          s_rem = r;
+          s_ncand = h;
+          r = -1;
+        } else if (r > 0) {
+          r -= h;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (s_ncand > 256) {
+    topk_core(keys, C, k, out, map, flags);
+    return;
+  }
+  const int bin = s_bin, rem = s_rem;
+#pragma unroll
+  for (int i = 0; i < TOPK_SMALL_KPT; ++i)
+    if (i < kpt && t * kpt + i < C && (int)((key[i] >> shift) & dmask) == bin) {
+      const int p = atomicAdd(&s_cnt, 1);
+      cand_key[p] = key[i];
+      cand_idx[p] = t * kpt + i;
+    }
+  __syncthreads();
+  const int nc = s_cnt;
+  if (t < nc) {
+    const unsigned long long mk = cand_key[t];
+    const int mi = cand_idx[t];
+    int ahead = 0;
+    for (int i = 0; i < nc; ++i) {
+      const unsigned long long ok = cand_key[i];
+      ahead += (ok > mk || (ok == mk && cand_idx[i] < mi)) ? 1 : 0;
+    }
+    if (ahead == rem - 1) {
+      s_kth_key = mk;
+      s_kth_idx = mi;
+    }
+  }
+  __syncthreads();
+  const unsigned long long kth_key = s_kth_key;
+  const int kth_idx = s_kth_idx;
+  int n_take = 0;
+  bool take[TOPK_SMALL_KPT];
+#pragma unroll
+  for (int i = 0; i < TOPK_SMALL_KPT; ++i) {
+    const int j = t * kpt + i;
+    take[i] = i < kpt && j < C && (key[i] > kth_key || (key[i] == kth_key && j <= kth_idx));
+    n_take += take[i] ? 1 : 0;
+  }
+  int total;
+  int pos = block_excl_scan(n_take, s_scan, total);
+#pragma unroll
+  for (int i = 0; i < TOPK_SMALL_KPT; ++i)
+    if (take[i] && pos < k) {
+      const int j = t * kpt + i;
+      const int col = map ? map[j] : j;
+      out[pos++] = col;
+      if (flags) flags[col] = 1;
+    }
+}
+
 // retire the previous step's column flags (single CTA, before the new ones are set)
 __device__ __forceinline__ void retire_prev_flags(const bh_ctx& c) {
   const int k = c.active_columns;
@@ -346,8 +501,12 @@ __device__ __forceinline__ void retire_prev_flags(const bh_ctx& c) {
 __device__ void ph_topk(const bh_ctx& c) {
   retire_prev_flags(c);
   const int k = c.active_columns;
-  topk_core(reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, k,
-            c.active_cols + (c.sc[BH_SC_STEP] & 1) * k, nullptr, c.col_active);
+  if (c.column_dim <= TOPK_SMALL_KPT * (int)blockDim.x)
+    topk_small(reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, k,
+               c.active_cols + (c.sc[BH_SC_STEP] & 1) * k, nullptr, c.col_active, c.topk_ws + TK2_BASE);
+  else
+    topk_core(reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, k,
+              c.active_cols + (c.sc[BH_SC_STEP] & 1) * k, nullptr, c.col_active);
 }
 
 __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const __grid_constant__ bh_ctx c) { ph_topk(c); }
@@ -392,9 +551,9 @@ __global__ void __launch_bounds__(TOPK_THREADS)
 #define TKW_INTS (TKW_INT_BASE + TKW_TIES + BH_BLK_STRIDE)
 #define BLK_TOPK 6
 
-__device__ void topk_multi(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
+__device__ __noinline__ void topk_multi(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
                            const int* map, uint8_t* flags, int b, int nb, unsigned int* bar) {
-  __shared__ int hist[256];
+  int* hist = topk_scratch().hist;
   __shared__ int s_scan[32];
   __shared__ unsigned long long s_u64[32];
   __shared__ int s_bin, s_rem, s_ncand;
@@ -590,13 +749,14 @@ __device__ void topk_multi(const bh_ctx& c, const unsigned long long* keys, cons
 // back to topk_multi for degenerate inputs (all keys equal, > 1024 keys in the bin).
 // Workspace: ctx.topk_ws + TK2_BASE (see the TK2_* layout above).
 // ---------------------------------------------------------------------------------
-__device__ void topk_grid(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
+__device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
                           const int* map, uint8_t* flags, int b, int nb, unsigned int* bar) {
-  __shared__ int hist[256];
+  TopkScratch& sm = topk_scratch();
+  int* hist = sm.hist;
+  unsigned long long* cand_key = sm.cand_key;
+  int* cand_idx = sm.cand_idx;
   __shared__ int s_scan[32];
   __shared__ unsigned long long s_u64[32];
-  __shared__ unsigned long long cand_key[TOPK_THREADS];
-  __shared__ int cand_idx[TOPK_THREADS];
   __shared__ int s_bin, s_rem, s_ncand, s_kth_idx;
   __shared__ unsigned long long s_kth_key;
   int* ws = c.topk_ws + TK2_BASE;
