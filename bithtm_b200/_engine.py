@@ -160,7 +160,7 @@ class Engine:
             self.buf[name] = self.arena[off:off + n * item].view(_TORCH_DTYPES[dt])
         # pinned host staging for bh_step_host
         self.input_pinned = torch.zeros(ctx.mask_stride, dtype=torch.int32).pin_memory()
-        self.summary_pinned = torch.zeros(nat.summary_ints(k), dtype=torch.int32).pin_memory()
+        self.summary_pinned = torch.zeros(nat.summary_ints(k) + 4, dtype=torch.int32).pin_memory()
         ctx.input_pinned = self.input_pinned.data_ptr()
         ctx.summary_pinned = self.summary_pinned.data_ptr()
         self._summary_np = self.summary_pinned.numpy()

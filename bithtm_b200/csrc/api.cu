@@ -596,11 +596,18 @@ extern "C" int bh_host_graph_create(const bh_ctx* x, int learning, void* stream,
   int rc = check_ctx(x);
   if (rc) return rc;
   if (!x->input_pinned || !x->summary_pinned) return BH_E_BADARG;
+  const bool zero_copy = x->fused_mode == 1 || x->fused_mode == 2;
   if (x->fused_mode && (rc = prepare_fused(x->fused_mode))) return rc;
   cudaStream_t st = S_(stream);
   cudaGraph_t graph = nullptr;
   CU_RET(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  rc = step_host_enqueue(x, learning, st);
+  if (zero_copy) {  // the kernel alone: pinned host input in, pinned host summary + flag out
+    bh_ctx y = *x;
+    y.summary_dev = x->summary_pinned;
+    rc = launch_fused(&y, x->input_pinned, 1, learning, 2, st);
+  } else {
+    rc = step_host_enqueue(x, learning, st);
+  }
   cudaError_t e = cudaStreamEndCapture(st, &graph);
   if (rc) {
     if (graph) cudaGraphDestroy(graph);
@@ -620,17 +627,19 @@ extern "C" int bh_step_host_graph(const bh_ctx* x, void* graph_exec, const uint8
   if (!x || !graph_exec || !input_bool_host) return BH_E_BADARG;
   cudaStream_t st = S_(stream);
   pack_host(x, input_bool_host);
-  // The D2H node rewrites summary_pinned[0] (the finished step's index, >= 0): spin on it instead of
-  // sleeping in the driver (saves the wake-up latency of a ~50 us step), then synchronise for real.
-  volatile int32_t* flag = x->summary_pinned;
+  const bool zero_copy = x->fused_mode == 1 || x->fused_mode == 2;
+  // Spin on host memory the device writes last -- the kernel's completion flag (zero-copy step) or
+  // word 0 of the summary the D2H node delivers -- instead of sleeping in the driver.
+  volatile int32_t* flag = zero_copy ? x->summary_pinned + BH_SUMMARY_INTS(x->active_columns) : x->summary_pinned;
   flag[0] = -1;
   CU_RET(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), st));
-  for (long spins = 0; flag[0] == -1 && spins < 4000000; ++spins) {
+  long spins = 0;
+  for (; flag[0] == -1 && spins < 40000000; ++spins) {
 #if defined(__x86_64__)
     __builtin_ia32_pause();
 #endif
   }
-  CU_RET(cudaStreamSynchronize(st));
+  if (!zero_copy || flag[0] == -1) CU_RET(cudaStreamSynchronize(st));  // copy nodes / a kernel that faulted
   if (summary_host) memcpy(summary_host, x->summary_pinned, (size_t)BH_SUMMARY_INTS(x->active_columns) * 4);
   return 0;
 }

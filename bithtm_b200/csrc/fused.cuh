@@ -39,6 +39,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     ++stamp_i;                                                                \
   } while (0)
   const int pos0 = c.sc[BH_SC_INPUT_POS];
+  // want_summary == 2: zero-copy host step -- `input_fixed` is pinned HOST memory (read over PCIe once
+  // per CTA in P0 and staged into input_dev for the learning phase) and summary_dev is pinned HOST
+  // memory too, completed by a flag word the host spins on
+  const bool zero_copy = want_summary == 2;
   for (int step = 0; step < n_steps; ++step) {
     const uint32_t* input =
         input_fixed ? input_fixed : c.input_ring + (long long)((pos0 + step) % c.ring_len) * c.input_words;
@@ -48,6 +52,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (rng) ph_draw(c, 1, 1, nw);
     if (nb == 1) ph_overlap<true>(c, input, s_dyn, 0, 1);
     else if (!rng) ph_overlap<true>(c, input, s_dyn, b, nb - 1);  // the rng CTA is busy drawing
+    if (zero_copy) {
+      if (b == 0)  // s_dyn holds the input words (ph_overlap staged them)
+        for (int i = threadIdx.x; i < c.input_words; i += blockDim.x) c.input_dev[i] = s_dyn[i];
+      input = c.input_dev;
+    }
     BH_SYNC();
     BH_STAMP();
     // P1: global inhibition (one CTA)
@@ -125,6 +134,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_STAMP();
   }
   if (want_summary) ph_summary(c, b, nb);
+  if (zero_copy) {  // every CTA's summary words are on their way to host memory; then the flag
+    __threadfence_system();
+    BH_SYNC();
+    if (b == 0 && threadIdx.x == 0) {
+      volatile int* flag = c.summary_dev + BH_SUMMARY_INTS(c.active_columns);
+      *flag = c.sc[BH_SC_STEP];  // completed steps, >= 1
+      __threadfence_system();
+    }
+  }
   if (!input_fixed && b == 0 && threadIdx.x == 0) c.sc[BH_SC_INPUT_POS] = pos0 + n_steps;
 #undef BH_SYNC
 #undef BH_STAMP

@@ -198,7 +198,8 @@ typedef struct bh_ctx {
   uint32_t* input_dev;     /* [input_words] staging for bh_step_host               */
   uint32_t* input_pinned;  /* HOST pinned [input_words]                            */
   int32_t* summary_dev;    /* [BH_SUMMARY_INTS(k)] step summary (see bh_step_host) */
-  int32_t* summary_pinned; /* HOST pinned [BH_SUMMARY_INTS(k)]                     */
+  int32_t* summary_pinned; /* HOST pinned [BH_SUMMARY_INTS(k) + 4]; the extra words  */
+                           /* are the completion flag of the zero-copy host step   */
 } bh_ctx;
 
 /* Arena layout: fills every DEVICE pointer of `ctx` with `base + offset`, given
@@ -307,10 +308,14 @@ int bh_step_ring(const bh_ctx* ctx, int learning, void* stream);
 int bh_step_host(const bh_ctx* ctx, const uint8_t* input_bool_host, int learning,
                  int32_t* summary_host, void* stream);
 
-/* The same end-to-end step as ONE CUDA graph launch (H2D copy node from
- * ctx->input_pinned, the step, the summary gather, D2H copy node into
- * ctx->summary_pinned).  bh_host_graph_create captures it once per (ctx, learning);
- * bh_step_host_graph packs the input, launches and synchronises. */
+/* The same end-to-end step as ONE CUDA graph launch.  With a fused step kernel the
+ * graph is that kernel alone: it reads the packed input straight from ctx->input_pinned
+ * and stores the summary straight into ctx->summary_pinned over PCIe (the pinned buffers
+ * must be device-accessible, as cudaHostAlloc memory is), followed by a completion flag
+ * the host spins on -- no copy nodes, no driver synchronisation on the critical path.
+ * Without a fused kernel: H2D copy node, the per-stage kernels, D2H copy node.
+ * bh_host_graph_create captures it once per (ctx, learning); bh_step_host_graph packs the
+ * input, launches and waits. */
 int bh_host_graph_create(const bh_ctx* ctx, int learning, void* stream, void** graph_exec_out);
 int bh_step_host_graph(const bh_ctx* ctx, void* graph_exec, const uint8_t* input_bool_host,
                        int32_t* summary_host, void* stream);
