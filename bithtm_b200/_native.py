@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libbithtm_b200.so")
+LIB_PATH = os.environ.get("BITHTM_B200_LIB") or os.path.join(_HERE, "_lib", "libbithtm_b200.so")  # env: A/B builds
 
 MT_N = 624
 ABI_VERSION = 5

@@ -85,8 +85,10 @@ __device__ __forceinline__ int overlap_group(int mask_stride) {
 
 template <bool BOOST>
 __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* input, uint32_t* s_in, int b, int nb) {
+  __shared__ unsigned long long s_range[2];  // max key, max ~key of this CTA
   #pragma unroll 1
   for (int i = threadIdx.x; i < c.mask_stride; i += blockDim.x) s_in[i] = i < c.input_words ? input[i] : 0u;
+  if (threadIdx.x < 2) s_range[threadIdx.x] = 0ull;
   __syncthreads();
   const int group = overlap_group(c.mask_stride);
   const int lane = threadIdx.x & 31;
@@ -100,43 +102,79 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
   const uint4* s_in4 = reinterpret_cast<const uint4*>(s_in);
   const int n_rows = c.col_local;  // this rank's columns (all of them when not sharded)
   unsigned long long key_min = ~0ull, key_max = 0ull;  // of the boosted keys this thread wrote (for topk_grid)
-#pragma unroll 1
-  for (int base = warp_global * rows_per_warp; base < n_rows; base += n_warps * rows_per_warp) {
-    int row = base + lane / group;
-    int acc = 0;
-    if (row < n_rows) {
-      const uint4* mrow = mask4 + (long long)row * vec_per_row;
-      int v = sub;
-#pragma unroll 1
-      for (; v + 3 * group < vec_per_row; v += 4 * group) {  // 4 independent 16-byte loads in flight
-        const uint4 m0 = mrow[v], m1 = mrow[v + group], m2 = mrow[v + 2 * group], m3 = mrow[v + 3 * group];
-        const uint4 x0 = s_in4[v], x1 = s_in4[v + group], x2 = s_in4[v + 2 * group], x3 = s_in4[v + 3 * group];
-        acc += __popc(m0.x & x0.x) + __popc(m0.y & x0.y) + __popc(m0.z & x0.z) + __popc(m0.w & x0.w);
-        acc += __popc(m1.x & x1.x) + __popc(m1.y & x1.y) + __popc(m1.z & x1.z) + __popc(m1.w & x1.w);
-        acc += __popc(m2.x & x2.x) + __popc(m2.y & x2.y) + __popc(m2.z & x2.z) + __popc(m2.w & x2.w);
-        acc += __popc(m3.x & x3.x) + __popc(m3.y & x3.y) + __popc(m3.z & x3.z) + __popc(m3.w & x3.w);
-      }
-#pragma unroll 1
-      for (; v < vec_per_row; v += group) {
-        const uint4 m = mrow[v];
-        const uint4 x = s_in4[v];
-        acc += __popc(m.x & x.x) + __popc(m.y & x.y) + __popc(m.z & x.z) + __popc(m.w & x.w);
-      }
+  // per-row epilogue: overlap count, boosted key (NumPy-exact exp, exact float64 product), key range
+  auto finish = [&](int row, int acc) {
+    c.overlaps[row] = acc;
+    if (BOOST) {
+      float f = bh_np_expf(__fmul_rn(c.boost_coef, c.duty[row]));
+      const double bo = __dmul_rn((double)f, (double)acc);
+      c.boosted[row] = bo;
+      const unsigned long long key = (unsigned long long)__double_as_longlong(bo);
+      key_min = key < key_min ? key : key_min;
+      key_max = key > key_max ? key : key_max;
     }
-    for (int o = group >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(BH_FULL, acc, o);
-    if (sub == 0 && row < n_rows) {
-      c.overlaps[row] = acc;
-      if (BOOST) {
-        float f = bh_np_expf(__fmul_rn(c.boost_coef, c.duty[row]));
-        const double bo = __dmul_rn((double)f, (double)acc);
-        c.boosted[row] = bo;
-        const unsigned long long key = (unsigned long long)__double_as_longlong(bo);
-        key_min = key < key_min ? key : key_min;
-        key_max = key > key_max ? key : key_max;
+  };
+  auto popc4 = [](const uint4& m, const uint4& x) {
+    return __popc(m.x & x.x) + __popc(m.y & x.y) + __popc(m.z & x.z) + __popc(m.w & x.w);
+  };
+  const int stride_rows = n_warps * rows_per_warp;
+  if (vec_per_row == 4 * group) {
+    // every lane owns exactly four 16-byte vectors of a row (HBM-bound sizes): software pipeline --
+    // the next row's four loads are issued before the current row is reduced, so a warp always has
+    // loads in flight
+    int base = warp_global * rows_per_warp;
+    int row = base + lane / group;
+    uint4 cur[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (row < n_rows) {
+      const uint4* mrow = mask4 + (long long)row * vec_per_row + sub;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = mrow[j * group];
+    }
+#pragma unroll 1
+    while (base < n_rows) {
+      const int nbase = base + stride_rows, nrow = nbase + lane / group;
+      uint4 nxt[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nxt[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (nrow < n_rows) {
+        const uint4* mrow = mask4 + (long long)nrow * vec_per_row + sub;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nxt[j] = mrow[j * group];
       }
+      int acc = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc += popc4(cur[j], s_in4[sub + j * group]);
+      for (int o = group >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(BH_FULL, acc, o);
+      if (sub == 0 && row < n_rows) finish(row, acc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      base = nbase;
+      row = nrow;
+    }
+  } else {
+#pragma unroll 1
+    for (int base = warp_global * rows_per_warp; base < n_rows; base += stride_rows) {
+      int row = base + lane / group;
+      int acc = 0;
+      if (row < n_rows) {
+        const uint4* mrow = mask4 + (long long)row * vec_per_row;
+        int v = sub;
+#pragma unroll 1
+        for (; v + 3 * group < vec_per_row; v += 4 * group) {  // 4 independent 16-byte loads in flight
+          const uint4 m0 = mrow[v], m1 = mrow[v + group], m2 = mrow[v + 2 * group], m3 = mrow[v + 3 * group];
+          acc += popc4(m0, s_in4[v]) + popc4(m1, s_in4[v + group]) + popc4(m2, s_in4[v + 2 * group]) +
+                 popc4(m3, s_in4[v + 3 * group]);
+        }
+#pragma unroll 1
+        for (; v < vec_per_row; v += group) acc += popc4(mrow[v], s_in4[v]);
+      }
+      for (int o = group >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(BH_FULL, acc, o);
+      if (sub == 0 && row < n_rows) finish(row, acc);
     }
   }
-  if (BOOST) {  // range of the keys, for the top-k that follows (saves it a pass): one red per warp
+  if (BOOST) {  // range of the keys, for the top-k that follows (saves it a pass): warp -> CTA -> one red per CTA
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const unsigned long long a = __shfl_xor_sync(BH_FULL, key_min, o), z = __shfl_xor_sync(BH_FULL, key_max, o);
@@ -144,9 +182,14 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
       key_max = z > key_max ? z : key_max;
     }
     if (lane == 0 && key_max >= key_min) {
+      atomicMax(&s_range[0], key_max);
+      atomicMax(&s_range[1], ~key_min);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (s_range[0] | s_range[1])) {
       unsigned long long* w64 = reinterpret_cast<unsigned long long*>(c.topk_ws + TK2_BASE);
-      atomicMax(&w64[0], key_max);
-      atomicMax(&w64[1], ~key_min);
+      atomicMax(&w64[0], s_range[0]);
+      atomicMax(&w64[1], s_range[1]);
       c.topk_ws[TK2_BASE + TK2_VALID] = 1;
     }
   }
