@@ -138,7 +138,9 @@ static int check_ctx(const bh_ctx* x) {
     if ((long long)x->col_local * W != x->column_dim || x->col_lo != x->seg_rank * x->col_local) return BH_E_BADARG;
   }
   if (x->syn_capacity < 32 || x->syn_capacity % 32 != 0) return BH_E_BADARG;
-  if (x->rng_ring_words < (1 << 20) || (x->rng_ring_words & (x->rng_ring_words - 1))) return BH_E_BADARG;
+  if (x->rng_ring_words < (1 << 20) || x->rng_ring_words > (1LL << 31) ||
+      (x->rng_ring_words & (x->rng_ring_words - 1)))
+    return BH_E_BADARG;
   if (x->rng_step_words < 2 * BH_MT_N || 2 * x->rng_step_words > x->rng_ring_words) return BH_E_BADARG;
   // one round of chunks must cover a whole step (plus lookahead) when the stream is produced by many CTAs
   if (x->jump_polys > 0 && (long long)x->jump_polys * RNG_CHUNK < x->rng_step_words + x->rng_step_words / 2 + RNG_CHUNK)

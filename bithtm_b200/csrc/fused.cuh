@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (rng) ph_draw(c, 2, learning, nw);
     if (worker) ph_learn_select_b(c, learning, b, nw);
     BH_SYNC();
-    if (MODE == 2 && c.jump_polys > 0) {  // stream words draw #2 planned for many CTAs (mt19937.cuh)
+    BH_STAMP();
+    // P4b: the stream words draw #2 planned for many CTAs (mt19937.cuh)
+    if (MODE == 2 && c.jump_polys > 0) {
       ph_rng_chunks(c, s_dyn, b, nb);
       BH_SYNC();
     }

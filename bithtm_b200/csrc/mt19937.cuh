@@ -105,27 +105,59 @@ __device__ __noinline__ long long mt_generate(const bh_ctx& c, uint32_t* x, long
                                               long long store_lo, long long store_hi) {
   const int t = threadIdx.x, NT = blockDim.x;
   const unsigned M = MT_RING - 1;
-  const unsigned long long gm = (unsigned long long)(c.rng_ring_words - 1);
+  const unsigned gm = (unsigned)(c.rng_ring_words - 1);  // ring_words <= 2^31 words (checked by the host layer)
+  uint32_t* ring = c.rng_ring;
+  // narrow waves (the plain recurrence, 227 words) until 1078 generated words of history exist
 #pragma unroll 1
-  while (G < target) {
-    // the expanded form needs 1078 words of history that were themselves generated
-    const bool wide = (G - lo >= 1078) && (G >= 1078 + MT_N);
-    const int width = wide ? MT_N - 1 : MT_N - MT_M;
+  while (G < target && !((G - lo >= 1078) && (G >= 1078 + MT_N))) {
 #pragma unroll 1
-    for (int i = t; i < width; i += NT) {
+    for (int i = t; i < MT_N - MT_M; i += NT) {
       const long long a = G + i;
       const unsigned n = (unsigned)a;
-      uint32_t v;
-      if (wide)
-        v = x[(n - 681) & M] ^ mt_twist(x[(n - 1078) & M], x[(n - 1077) & M]) ^
-            mt_twist(x[(n - 851) & M], x[(n - 850) & M]) ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
-      else
-        v = x[(n - 227) & M] ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
+      const uint32_t v = x[(n - 227) & M] ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
       x[n & M] = v;
-      if (a >= store_lo && a < store_hi) c.rng_ring[(unsigned long long)a & gm] = v;
+      if (a >= store_lo && a < store_hi) ring[n & gm] = v;
     }
     __syncthreads();
-    G += width;
+    G += MT_N - MT_M;
+  }
+  // wide waves: 623 independent words per barrier; all index arithmetic in 32 bits
+  if (G < target) {
+    const long long waves = (target - G + (MT_N - 2)) / (MT_N - 1);
+    // store window relative to G, clamped to 32 bits
+    const long long rel_lo = store_lo - G, rel_hi = store_hi - G;
+    const unsigned s_lo = rel_lo < 0 ? 0u : (rel_lo > 0x7fffffffLL ? 0x7fffffffu : (unsigned)rel_lo);
+    const unsigned s_hi = rel_hi < 0 ? 0u : (rel_hi > 0x7fffffffLL ? 0x7fffffffu : (unsigned)rel_hi);
+    const unsigned g0 = (unsigned)G;
+    unsigned off = (unsigned)t;  // offset of this thread's word from G
+    if (NT >= MT_N - 1) {
+#pragma unroll 1
+      for (long long w = 0; w < waves; ++w) {
+        if (t < MT_N - 1) {
+          const unsigned n = g0 + off;
+          const uint32_t v = x[(n - 681) & M] ^ mt_twist(x[(n - 1078) & M], x[(n - 1077) & M]) ^
+                             mt_twist(x[(n - 851) & M], x[(n - 850) & M]) ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
+          x[n & M] = v;
+          if (off >= s_lo && off < s_hi) ring[n & gm] = v;
+        }
+        off += MT_N - 1;
+        __syncthreads();
+      }
+    } else {
+#pragma unroll 1
+      for (long long w = 0; w < waves; ++w) {
+#pragma unroll 1
+        for (int i = t; i < MT_N - 1; i += NT) {
+          const unsigned o2 = (unsigned)(w * (MT_N - 1)) + i, n = g0 + o2;
+          const uint32_t v = x[(n - 681) & M] ^ mt_twist(x[(n - 1078) & M], x[(n - 1077) & M]) ^
+                             mt_twist(x[(n - 851) & M], x[(n - 850) & M]) ^ mt_twist(x[(n - 624) & M], x[(n - 623) & M]);
+          x[n & M] = v;
+          if (o2 >= s_lo && o2 < s_hi) ring[n & gm] = v;
+        }
+        __syncthreads();
+      }
+    }
+    G += waves * (MT_N - 1);
   }
   return G;
 }
@@ -160,6 +192,13 @@ __device__ __noinline__ void rng_chunk(const bh_ctx& c, uint32_t* smem, int p) {
   int sh = 0;
   while ((623LL << sh) <= (long long)p * RNG_CHUNK + MT_N) ++sh;
   const long long depth = 19937LL << sh;
+#ifdef BH_TOPK_STAMPS
+  if (blockIdx.x == 0 && t == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE)[59] = t_;
+  }
+#endif
   const long long plan_end = base + c.rng64[R_PLAN_CHUNKS] * RNG_CHUNK;  // slots below plan_end - ring are reused
   const long long lowest = plan_end - c.rng_ring_words > 1 ? plan_end - c.rng_ring_words : 1;
   const bool sparse = cb - depth >= lowest;
@@ -169,13 +208,13 @@ __device__ __noinline__ void rng_chunk(const bh_ctx& c, uint32_t* smem, int p) {
       const long long a0 = cb + j - depth;
       uint32_t v = 0u;
 #pragma unroll 1
-      for (int e0 = 0; e0 < RNG_PHI_LOW; e0 += 16) {  // 16 independent loads in flight per thread
-        uint32_t w[16];
+      for (int e0 = 0; e0 < RNG_PHI_LOW; e0 += 32) {  // 32 independent loads in flight per thread
+        uint32_t w[32];
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
+        for (int u = 0; u < 32; ++u)
           w[u] = e0 + u < RNG_PHI_LOW ? rng_word(c, a0 + ((long long)c_phi_low[e0 + u] << sh)) : 0u;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v ^= w[u];
+        for (int u = 0; u < 32; ++u) v ^= w[u];
       }
       s_out[j] = v;
     }
@@ -186,6 +225,13 @@ __device__ __noinline__ void rng_chunk(const bh_ctx& c, uint32_t* smem, int p) {
     for (int i = t; i < MT_N; i += NT) s_out[i] = 0u;
   }
   __syncthreads();
+#ifdef BH_TOPK_STAMPS
+  if (blockIdx.x == 0 && t == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE)[60] = t_;
+  }
+#endif
   // out[j] = XOR_{i : g[i]} win[i + j].  6 groups of 156 threads split the 624 words of
   // g; thread q of a group keeps outputs 4q..4q+3 and slides a register window over win.
   if (!sparse && t < 936) {
@@ -231,6 +277,13 @@ __device__ __noinline__ void rng_chunk(const bh_ctx& c, uint32_t* smem, int p) {
   }
   __syncthreads();
   mt_generate(c, x, cb, cb + MT_N, cb + RNG_CHUNK, cb + MT_N, cb + RNG_CHUNK);
+#ifdef BH_TOPK_STAMPS
+  if (blockIdx.x == 0 && t == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE)[61] = t_;
+  }
+#endif
 }
 
 // All CTAs: run the chunks of the pending plan (b of nb).  The plan is committed

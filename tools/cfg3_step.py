@@ -18,7 +18,7 @@ import bithtm_b200 as bithtm
 from bithtm_b200.projections import DenseProjection
 
 PHASES = ["P0 overlap+draw1", "P1 topk", "P2 sp_learn+duty+select_a", "P3 select_b+learn_select_a",
-          "P4 learn_select_b+draw2", "P5 learn_apply", "P6 post", "P7 activate_a", "P8 draw3", "P9 activate_b"]
+          "P4 learn_select_b+draw2", "P4b rng chunks", "P5 learn_apply", "P6 post", "P7 activate_a", "P8 draw3", "P9 activate_b"]
 
 
 def main():
@@ -66,6 +66,8 @@ def main():
         st = eng.buf["blk"][7 * 1024 + 80:7 * 1024 + 80 + 32].cpu().numpy().view(np.uint64)
         print("  topk_grid stages (ns):", np.diff(st[:7].astype(np.int64)).tolist(), "candidates", int(st[15] & 0xffffffff),
               "range published", int(st[15] >> 32))
+        rs = eng.buf["blk"][7 * 1024 + 118:7 * 1024 + 124].cpu().numpy().view(np.uint64).astype(np.int64)
+        print("  rng_chunk CTA 0 (ns): start", int(rs[1] - rs[0]), "generate", int(rs[2] - rs[1]))
 
 
 if __name__ == "__main__":

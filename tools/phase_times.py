@@ -13,9 +13,9 @@ import bithtm_b200 as bithtm
 from bench import CFG2, make_inputs
 
 PHASES = ["P0 overlap+draw1", "P1 topk", "P2 sp_learn+duty+select_a", "P3 select_b+learn_select_a",
-          "P4 learn_select_b+draw2", "P5 learn_apply", "P6 post", "P7 activate_a", "P8 draw3", "P9 activate_b"]
+          "P4 learn_select_b+draw2", "P4b rng chunks", "P5 learn_apply", "P6 post", "P7 activate_a", "P8 draw3", "P9 activate_b"]
 if os.environ.get("BH_ICACHE_EXPERIMENT"):
-    PHASES[7:7] = ["P6' post again (warm I$)", "P6'' post again"]
+    PHASES[8:8] = ["P6' post again (warm I$)", "P6'' post again"]
 
 
 def main():
