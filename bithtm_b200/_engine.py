@@ -173,6 +173,7 @@ class Engine:
             n = int(nat.lib.bh_tm_shard_xch_ints(C.byref(ctx)))
             self.xch_send = torch.zeros(n, dtype=torch.int32, device=self.device)
             self.xch_recv = torch.zeros(n * self.seg_world, dtype=torch.int32, device=self.device)
+        self.tm_deferred = False  # the last step left a deferred jitter draw / no winner cells (networks.py)
         self.epoch = 0  # bumped by every completed step; lazily fetched State fields check it
         self._graphs = {}
         self.host_graph = True  # bh_step_host as one CUDA graph launch (constants are frozen at capture)

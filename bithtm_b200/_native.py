@@ -14,12 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BITHTM_B200_LIB") or os.path.join(_HERE, "_lib", "libbithtm_b200.so")  # env: A/B builds
 
 MT_N = 624
-ABI_VERSION = 5
+ABI_VERSION = 6
 R_COUNT = 16  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)
 (SC_STEP, SC_HAVE_PREV, SC_NSEG, SC_NSEG_NEXT, SC_M, SC_W0, SC_W1, SC_L0, SC_L, SC_P, SC_NU, SC_NR,
- SC_STATUS, SC_MT_POS, SC_X_MATCH, SC_X_RECYC_AVAIL, SC_X_RECYC_TOTAL, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN) = range(20)
+ SC_STATUS, SC_MT_POS, SC_X_MATCH, SC_X_RECYC_AVAIL, SC_X_RECYC_TOTAL, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN,
+ SC_JIT_PENDING, SC_WNONE0, SC_WNONE1) = range(23)
 SC_COUNT = 32
 
 ST_SEG_OVERFLOW, ST_SYN_OVERFLOW, ST_MATCH_OVERFLOW, ST_LEARN_OVERFLOW, ST_RAND_OVERFLOW, ST_PRI_TIE = 1, 2, 4, 8, 16, 32
@@ -130,6 +131,7 @@ _SIGNATURES = {
     "bh_tm_learn": (C.c_int, [_CTXP, C.c_int, _P]),
     "bh_tm_activate": (C.c_int, [_CTXP, _P]),
     "bh_tm_step": (C.c_int, [_CTXP, C.c_int, _P]),
+    "bh_tm_step_ex": (C.c_int, [_CTXP, C.c_int, C.c_int, C.c_int, _P]),
     "bh_step": (C.c_int, [_CTXP, _P, C.c_int, _P]),
     "bh_step_ring": (C.c_int, [_CTXP, C.c_int, _P]),
     "bh_step_host": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),

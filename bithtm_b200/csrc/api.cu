@@ -343,16 +343,23 @@ extern "C" int bh_advance_step(const bh_ctx* x, void* stream) {
 // ------------------------------------------------------------------------------------
 // temporal memory
 // ------------------------------------------------------------------------------------
-extern "C" int bh_tm_select(const bh_ctx* x, void* stream) {
-  cudaStream_t st = S_(stream);
-  k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 1, 1);
-  LAUNCHED("tm_draw1");
-  k_tm_select_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+static int tm_post_and_scan(const bh_ctx* x, cudaStream_t st);
+
+static int tm_select(const bh_ctx* x, int want, cudaStream_t st) {
+  if (want) {
+    k_tm_fill_jitter<<<1, MT_THREADS, 0, st>>>(*x);  // no-op unless the last activation deferred its draw
+    LAUNCHED("tm_fill_jitter");
+    k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 1, 1);
+    LAUNCHED("tm_draw1");
+  }
+  k_tm_select_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, want);
   LAUNCHED("tm_select_a");
-  k_tm_select_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  k_tm_select_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, want);
   LAUNCHED("tm_select_b");
   return 0;
 }
+
+extern "C" int bh_tm_select(const bh_ctx* x, void* stream) { return tm_select(x, 1, S_(stream)); }
 
 static int learn_apply_smem(const bh_ctx* x) {
   long long bits = (long long)x->active_columns * x->cell_dim;
@@ -405,7 +412,21 @@ extern "C" int bh_tm_activate(const bh_ctx* x, void* stream) {
   LAUNCHED("tm_activate_a");
   k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 3, 1);
   LAUNCHED("tm_draw3");
-  k_tm_activate_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  k_tm_activate_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, 1);
+  LAUNCHED("tm_activate_b");
+  return 0;
+}
+
+extern "C" int bh_tm_step_ex(const bh_ctx* x, int learning, int want_winner, int want_jitter, void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (x->seg_world > 1) return BH_E_UNSUPPORTED;
+  cudaStream_t st = S_(stream);
+  if ((rc = tm_select(x, (learning || want_winner) ? 1 : 0, st))) return rc;
+  if ((rc = bh_tm_learn(x, learning, stream))) return rc;
+  if (want_jitter) return bh_tm_activate(x, stream);
+  if ((rc = tm_post_and_scan(x, st))) return rc;
+  k_tm_activate_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, 0);
   LAUNCHED("tm_activate_b");
   return 0;
 }

@@ -76,7 +76,9 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
     if (which == 1) {
       count = (long long)c.active_columns * c.cell_dim;
     } else if (which == 2) {
-      if (learning && sc[BH_SC_HAVE_PREV]) count = (long long)lt.L * (sc[BH_SC_W0 + (cur ^ 1)] + 1);
+      // projections.py:191: no growth (and no draw) when the previous step had no winner cells at all
+      if (learning && sc[BH_SC_HAVE_PREV] && !sc[BH_SC_WNONE0 + (cur ^ 1)])
+        count = (long long)lt.L * (sc[BH_SC_W0 + (cur ^ 1)] + 1);
     } else {
       int M = c.seg_world > 1 ? sc[BH_SC_X_MATCH] : m_total;
       if (M > c.match_capacity) {
@@ -155,7 +157,9 @@ __global__ void k_rng_export(const __grid_constant__ bh_ctx c) {
 // evaluate_cell_least_used (:84-89).  Also retires the winner words of columns that
 // were active last step but are not now.
 // ---------------------------------------------------------------------------------
-__device__ void ph_select_a(const bh_ctx& c, int b, int nb) {
+// `want` = learning or return_winner_cell (networks.py:99): without it no winner cells are formed
+// and rand(k, c) is not drawn.
+__device__ void ph_select_a(const bh_ctx& c, int b, int nb, bool want = true) {
   __shared__ int s_red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int k = c.active_columns, cd = c.cell_dim;
@@ -180,11 +184,12 @@ __device__ void ph_select_a(const bh_ctx& c, int b, int nb) {
     bool best = have_prev && in && fabsf(__fsub_rn(mj, colmax)) < c.epsilon;
     // least used (networks.py:85-88): f32(f64(count) + u)
     float x = INFINITY;
-    if (in) x = __double2float_rn(__dadd_rn((double)c.cell_nseg[cell], rng_uniform(c, off1 + 2 * ((long long)r * cd + lane))));
+    if (in && want)
+      x = __double2float_rn(__dadd_rn((double)c.cell_nseg[cell], rng_uniform(c, off1 + 2 * ((long long)r * cd + lane))));
     float rowmin = warp_min(x);
     bool least = in && fabsf(__fsub_rn(x, rowmin)) < c.epsilon;
     bool predbit = (pred >> lane) & 1u;
-    bool win = in && (predbit || (burst && (col_matching ? best : least)));  // networks.py:102
+    bool win = want && in && (predbit || (burst && (col_matching ? best : least)));  // networks.py:102
     uint32_t wbits = __ballot_sync(BH_FULL, win);
     // winners no matching segment points at (projections.py:271)
     uint32_t ubits = __ballot_sync(BH_FULL, win && have_prev && mj < c.epsilon);
@@ -213,7 +218,7 @@ __device__ void ph_select_a(const bh_ctx& c, int b, int nb) {
 
 // Phase B: ordered winner / unaccounted lists (row order of active_column, cells
 // ascending: np.where on the [k, c] mask, networks.py:103-104).
-__device__ void ph_select_b(const bh_ctx& c, int b, int nb) {
+__device__ void ph_select_b(const bh_ctx& c, int b, int nb, bool want = true) {
   __shared__ int s_red[32];
   const int k = c.active_columns, cd = c.cell_dim, NT = blockDim.x;
   const int cur = c.sc[BH_SC_STEP] & 1;
@@ -250,6 +255,7 @@ __device__ void ph_select_b(const bh_ctx& c, int b, int nb) {
   if (b == 0 && threadIdx.x == 0) {
     c.sc[BH_SC_W0 + cur] = w_total;
     c.sc[BH_SC_NU] = u_total;
+    c.sc[BH_SC_WNONE0 + cur] = want ? 0 : 1;  // winner_cell is None (networks.py:125)
   }
 }
 
@@ -707,7 +713,9 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
 // that list (:234-235), per-cell maximum (:236-237) and active-segment count (:251).
 // CTA 0 completes the timestep.
 // `ready`: draw #3 was not run as a phase (fused.cuh); its count is the clamped list length.
-__device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false) {
+// `want_jitter` = return_winner_cell (networks.py:121): without it the jitter (and its draw) is left
+// to a later step (ph_fill_jitter); this phase then also publishes M.
+__device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false, bool want_jitter = true) {
   __shared__ int s_red[32];
   const int NT = blockDim.x;
   const int S = c.sc[BH_SC_NSEG];
@@ -729,13 +737,15 @@ __device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false
     base += tot;
     if (match && rank < c.match_capacity) {
       const int conn = c.seg_conn[s];
-      const double u = rank < n3 ? rng_uniform(c, off3 + 2 * rank) : 0.0;
-      const float jit = __double2float_rn(__dadd_rn((double)pot, u));
       const int owner = c.seg_owner[s];
       c.m_seg[rank] = s;
       c.m_conn[rank] = conn;
-      c.m_jit[rank] = jit;
-      atomicMax(reinterpret_cast<int*>(c.cell_maxjit + owner), __float_as_int(jit));  // jit > 0
+      if (want_jitter) {
+        const double u = rank < n3 ? rng_uniform(c, off3 + 2 * rank) : 0.0;
+        const float jit = __double2float_rn(__dadd_rn((double)pot, u));
+        c.m_jit[rank] = jit;
+        atomicMax(reinterpret_cast<int*>(c.cell_maxjit + owner), __float_as_int(jit));  // jit > 0
+      }
       if (conn >= c.seg_activation_threshold) {
         atomicAdd(&c.cell_npred[owner], 1);
         atomicOr(&c.col_pred[owner >> 5], 1u << (owner & 31));
@@ -745,14 +755,45 @@ __device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false
   if (b == 0 && threadIdx.x == 0) {
     c.sc[BH_SC_HAVE_PREV] = 1;
     c.sc[BH_SC_STEP] = c.sc[BH_SC_STEP] + 1;
+    c.sc[BH_SC_JIT_PENDING] = want_jitter ? 0 : 1;
+    if (!want_jitter) {
+      if (m_total > c.match_capacity) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_MATCH_OVERFLOW);
+      c.sc[BH_SC_M] = m_total < c.match_capacity ? m_total : c.match_capacity;
+    }
   }
 }
+
+// The deferred jitter of the previous activation (projections.py:229-239 reached through
+// get_jittered_potential_info, networks.py:76): rand(M) drawn now, before this step's rand(k, c).
+// One CTA; no-op unless BH_SC_JIT_PENDING.
+__device__ void ph_fill_jitter(const bh_ctx& c) {
+  __shared__ uint32_t x[MT_RING];
+  if (!c.sc[BH_SC_JIT_PENDING] || !c.sc[BH_SC_HAVE_PREV]) return;
+  const int M = c.sc[BH_SC_M];
+  rng_draw(c, x, M, R_OFF3, R_N3, true, 0, false);
+  const long long off3 = c.rng64[R_OFF3], n3 = c.rng64[R_N3];
+#pragma unroll 1
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const int s = c.m_seg[j];
+    const double u = j < n3 ? rng_uniform(c, off3 + 2 * j) : 0.0;
+    const float jit = __double2float_rn(__dadd_rn((double)c.seg_pot[s], u));
+    c.m_jit[j] = jit;
+    atomicMax(reinterpret_cast<int*>(c.cell_maxjit + c.seg_owner[s]), __float_as_int(jit));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) c.sc[BH_SC_JIT_PENDING] = 0;
+}
+__global__ void __launch_bounds__(MT_THREADS) k_tm_fill_jitter(const __grid_constant__ bh_ctx c) { ph_fill_jitter(c); }
 
 // ---------------------------------------------------------------------------------
 // stand-alone kernels (fine-grained C entry points)
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_a(const __grid_constant__ bh_ctx c) { ph_select_a(c, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_b(const __grid_constant__ bh_ctx c) { ph_select_b(c, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_a(const __grid_constant__ bh_ctx c, int want) {
+  ph_select_a(c, blockIdx.x, gridDim.x, want != 0);
+}
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_select_b(const __grid_constant__ bh_ctx c, int want) {
+  ph_select_b(c, blockIdx.x, gridDim.x, want != 0);
+}
 __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_a(const __grid_constant__ bh_ctx c, int learning) {
   ph_learn_select_a(c, learning, blockIdx.x, gridDim.x);
 }
@@ -761,7 +802,9 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_learn_select_b(const __gri
 }
 __global__ void k_tm_post(const __grid_constant__ bh_ctx c) { ph_post(c, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_a(const __grid_constant__ bh_ctx c) { ph_activate_a(c, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const __grid_constant__ bh_ctx c) { ph_activate_b(c, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const __grid_constant__ bh_ctx c, int want_jitter) {
+  ph_activate_b(c, blockIdx.x, gridDim.x, false, want_jitter != 0);
+}
 
 // Step summary for the host (bh_step_host): see include/bithtm_b200.h
 __device__ void ph_summary(const bh_ctx& c, int b, int nb) {

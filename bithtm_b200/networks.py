@@ -233,7 +233,7 @@ class TemporalMemory:
         three bit-words per active column); ``cell_prediction`` and ``distal_state``
         fields are fetched from the device on first read."""
 
-        def __init__(self, engine, projection, summary, have_winner=True):
+        def __init__(self, engine, projection, summary, have_winner=True, have_jitter=True):
             super().__init__(engine)
             k, c = engine.k, engine.c
             s = summary
@@ -244,7 +244,7 @@ class TemporalMemory:
             self._row_win = s[4 + 3 * k:4 + 4 * k].view(np.uint32).copy()
             self._have_winner = have_winner
             self.n_segments = int(s[2])
-            self.distal_state = PredictiveProjection.State(engine, projection)
+            self.distal_state = PredictiveProjection.State(engine, projection, have_jitter)
 
         def _cells(self, words):
             rows, cells = np.nonzero(_bits(words, self._c))
@@ -327,10 +327,10 @@ class TemporalMemory:
         if self._engine is not None:
             self._rng.sync(self._engine)
 
-    def _finish(self, summary, have_winner=True):
+    def _finish(self, summary, have_winner=True, have_jitter=True):
         eng = self._engine
         eng.check_status(summary[1])
-        state = self.State(eng, self.distal_projection, summary, have_winner)
+        state = self.State(eng, self.distal_projection, summary, have_winner, have_jitter)
         self.last_state = state
         return state
 
@@ -341,8 +341,7 @@ class TemporalMemory:
         if prev_state is not None and prev_state is not self.last_state:
             raise NotImplementedError("bithtm_b200.TemporalMemory keeps the previous state on the device; "
                                       "an explicit prev_state other than last_state is not supported")
-        if not (learning or return_winner_cell):
-            raise NotImplementedError("return_winner_cell=False with learning=False is not implemented yet")
+        want = bool(learning or return_winner_cell)  # networks.py:99
         active_column = None
         tag = getattr(sp_state, "_bh_engine_epoch", None)
         if self._engine is None:
@@ -359,11 +358,17 @@ class TemporalMemory:
         if eng.seg_world > 1:  # segment shards: local scan, ONE all-gather, merge (see _shard.py)
             from ._shard import gather_records
 
+            if not return_winner_cell:
+                raise NotImplementedError("segment shards support the default return_winner_cell=True only")
             send = eng.tm_shard_pre(learning)
             eng.tm_shard_post(gather_records(send, eng.xch_recv, self.distal_projection._group))
         else:
-            nat.check(nat.lib.bh_tm_step(eng.ref, int(bool(learning)), eng.stream), "bh_tm_step")
+            nat.check(nat.lib.bh_tm_step_ex(eng.ref, int(bool(learning)), int(bool(return_winner_cell)),
+                                            int(bool(return_winner_cell)), eng.stream), "bh_tm_step_ex")
             eng.epoch += 1
+        # a step without winner cells / without the jitter draw leaves state only the per-stage kernels
+        # interpret (deferred rand(M), "winner_cell is None"): the next step must take this path too
+        eng.tm_deferred = not bool(return_winner_cell)
         if not return_state:
             if self._rng.mode != "lazy":
                 raise ValueError('return_state=False needs rng_sync="lazy" (no per-step read-back)')
@@ -371,7 +376,7 @@ class TemporalMemory:
             return None
         summary = eng.summary()
         self._rng.after(eng, summary)
-        return self._finish(summary)
+        return self._finish(summary, have_winner=want, have_jitter=bool(return_winner_cell))
 
 
 class HierarchicalTemporalMemory:
@@ -444,16 +449,20 @@ class HierarchicalTemporalMemory:
     def sync_rng(self):
         self.temporal_memory.sync_rng()
 
-    def process(self, input, learning=True, return_state=True):
-        """networks.py:146-149.  Host inputs go through ``bh_step_host`` (one H2D of
+    def process(self, input, learning=True, return_state=True, return_winner_cell=True):
+        """networks.py:146-149 (``return_winner_cell`` -- an extension here -- is passed on to
+        ``TemporalMemory.process``; with ``learning=False`` it gives the inference-only step).  Host inputs go through ``bh_step_host`` (one H2D of
         the packed input, the whole step on the device, one D2H of the step summary).
         ``return_state=False`` (extension; device inputs, ``rng_sync="lazy"``) only enqueues
         the step: nothing is read back and the host does not wait."""
         sp, tm, eng = self.spatial_pooler, self.temporal_memory, self._engine
         is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
+        staged = not return_winner_cell or eng.tm_deferred  # needs the per-stage kernels (bh_tm_step_ex)
         if eng.ctx.fused_mode == 3:  # the shard's whole step is one kernel (exchanges inside)
             if not sp._native_inhibition:
                 raise NotImplementedError('fused="shard" needs the built-in GlobalInhibition')
+            if staged:
+                raise NotImplementedError('fused="shard" supports the default return_winner_cell=True only')
             sp.boosting._bind(eng)
             words = eng.pack_input(input)
             tm._rng.before(eng)
@@ -470,10 +479,12 @@ class HierarchicalTemporalMemory:
             sp_state._parity ^= 1
             sp_state._group = sp._group
             return sp_state, tm_state
-        if not sp._native_inhibition or not is_host or eng.shard_world > 1 or eng.seg_world > 1 or not return_state:
+        if (not sp._native_inhibition or not is_host or eng.shard_world > 1 or eng.seg_world > 1 or not return_state
+                or staged):
             sp_state = sp.process(input, learning=learning)
             sp_state._group = sp._group
-            tm_state = tm.process(sp_state, learning=learning, return_state=return_state)
+            tm_state = tm.process(sp_state, learning=learning, return_state=return_state,
+                                  return_winner_cell=return_winner_cell)
             if not return_state:
                 return None
             sp_state._epoch = eng.epoch  # its buffers stay valid until the next step

@@ -134,9 +134,10 @@ class PredictiveProjection:
     class State(_Lazy):
         """projections.py:195-203; every field is fetched from the device on first read."""
 
-        def __init__(self, engine, projection):
+        def __init__(self, engine, projection, have_jitter=True):
             super().__init__(engine)
             self._p = projection
+            self._have_jitter = have_jitter  # False: return_jittered_potential_info=False (projections.py:253)
 
         def _scalars(self):
             return self._get("_sc", self._engine.scalars)
@@ -187,11 +188,15 @@ class PredictiveProjection:
             return self.matching_segment_activation >= self._p.segment_activation_threshold
 
         @property
-        def max_jittered_potential(self):  # :236-238 float32 [N]
+        def max_jittered_potential(self):  # :236-238 float32 [N]; None until drawn (projections.py:196-203)
+            if not self._have_jitter:
+                return None
             return self._get("max_jittered_potential", lambda: self._engine.per_cell("cell_maxjit"))
 
         @property
         def matching_segment_jittered_potential(self):  # :234-235 float32 [M]
+            if not self._have_jitter:
+                return None
             return self._get("matching_segment_jittered_potential",
                              lambda: self._engine.buf["m_jit"][:self._M].cpu().numpy())
 

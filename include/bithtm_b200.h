@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 5
+#define BH_ABI_VERSION 6
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 81920
@@ -62,6 +62,11 @@ enum {
   BH_SC_INPUT_POS,     /* cursor into the device input ring (bh_step_ring)         */
   BH_SC_BAR_COUNT,     /* grid barrier of the fused kernel: arrivals               */
   BH_SC_BAR_GEN,       /*                                   generation             */
+  BH_SC_JIT_PENDING,   /* the last activation did not draw its jitter (rand(M)); a  */
+                       /* later step that needs it draws it first (projections.py:  */
+                       /* 229-243 run lazily from networks.py:76)                   */
+  BH_SC_WNONE0,        /* winner_cell of buffer 0 / 1 is None (a step with neither  */
+  BH_SC_WNONE1,        /* learning nor return_winner_cell): no growth, no rand(L,W+1) */
   BH_SC_COUNT = 32
 };
 
@@ -293,6 +298,12 @@ int bh_tm_learn(const bh_ctx* ctx, int learning, void* stream);
 int bh_tm_activate(const bh_ctx* ctx, void* stream);
 /* TemporalMemory.process (networks.py:91-128) = the three calls above */
 int bh_tm_step(const bh_ctx* ctx, int learning, void* stream);
+/* The same with TemporalMemory.process's return_winner_cell flag (networks.py:91):
+ * want_winner = 0 with learning = 0 is the inference-only step (no winner cells, no random
+ * draw at all); want_jitter = return_winner_cell (networks.py:121): when 0 the rand(M) draw of
+ * the activation is deferred to the next step that needs it, exactly as the reference's lazy
+ * fill_jittered_potential_info does.  Per-stage kernels; not for segment shards. */
+int bh_tm_step_ex(const bh_ctx* ctx, int learning, int want_winner, int want_jitter, void* stream);
 
 /* ---- whole timestep: HierarchicalTemporalMemory.process (networks.py:146-149) ------ */
 int bh_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, void* stream);

@@ -301,13 +301,30 @@ class HTMOracle:
             self.seg_count[s] += len(chosen)  # :161
         return tie, L * (W + 1)
 
-    def tm_select(self, active_column):
-        """networks.py:95-104: bursting columns and winner cells."""
+    def _fill_jitter(self):
+        """projections.py:229-239, run lazily (networks.py:76 -> projections.py:241-243) when the
+        previous activation was asked not to draw it (return_jittered_potential_info=False)."""
+        if not getattr(self, "jit_pending", False):
+            return 0
+        u = self.rng.random_sample(len(self.m_seg))  # :235
+        jit = (self.seg_potential[self.m_seg].astype(F64) + u).astype(F32)
+        self.max_jit = np.zeros(self.N, dtype=F32)
+        np.maximum.at(self.max_jit, self.seg_owner[self.m_seg], jit)  # :236-237
+        self.m_jit = jit
+        self.jit_pending = False
+        return len(self.m_seg)
+
+    def tm_select(self, active_column, want=True):
+        """networks.py:95-104: bursting columns and winner cells (`want` = learning or
+        return_winner_cell, networks.py:99)."""
         cfg, c = self.cfg, self.c
         eps = F32(cfg.epsilon)
         acp = self.cell_prediction[active_column]
         burst = ~acp.any(axis=1)
         k = len(active_column)
+        if not want:
+            return acp, burst, None, 0
+        filled = self._fill_jitter() if self.have_prev else 0
         if self.have_prev:  # networks.py:73-82
             mj = self.max_jit.reshape(self.C, c)[active_column]
             colmax = mj.max(axis=1, keepdims=True)
@@ -323,7 +340,7 @@ class HTMOracle:
         win = acp | (burst[:, None] & np.where(col_matching, best, least))
         rows, cells = np.nonzero(win)
         winners = active_column[rows] * c + cells
-        return acp, burst, winners.astype(np.int64), k * c
+        return acp, burst, winners.astype(np.int64), filled + k * c
 
     def tm_learn(self, active_column, winners):
         """projections.py:257-293."""
@@ -370,8 +387,8 @@ class HTMOracle:
         self._update_rows(punish, prev_active_flat, self.d_punish)  # :290-293
         return learn, punish, tie, draws
 
-    def tm_activate(self, active_flat_mask):
-        """projections.py:245-255 + :229-239."""
+    def tm_activate(self, active_flat_mask, want_jitter=True):
+        """projections.py:245-255 + :229-239 (the jitter only when asked, networks.py:121)."""
         cfg = self.cfg
         S = self.n_seg
         cells = self.syn_cell[:S]
@@ -383,6 +400,15 @@ class HTMOracle:
         owner = self.seg_owner[matching]
         active = conn >= cfg.segment_activation_threshold  # :250
         self.npred = np.bincount(owner, weights=active, minlength=self.N).astype(np.int64)  # :251
+        if not want_jitter:  # the draw is deferred until (and unless) somebody needs it
+            self.m_seg, self.m_act, self.m_jit = matching.astype(np.int64), conn.astype(np.int64), None
+            self.max_jit = np.zeros(self.N, dtype=F32)
+            self.seg_potential = potential
+            self.cell_prediction = (self.npred > 0).reshape(self.C, self.c)
+            self.have_prev = True
+            self.jit_pending = True
+            return 0
+        self.jit_pending = False
         u = self.rng.random_sample(len(matching))  # :235
         jit = (potential[matching].astype(F64) + u).astype(F32)
         self.max_jit = np.zeros(self.N, dtype=F32)
@@ -394,9 +420,10 @@ class HTMOracle:
         return len(matching)
 
     # ------------------------------------------------------------------ full step
-    def step(self, x, learning=True, active_column=None) -> StepRecord:
+    def step(self, x, learning=True, active_column=None, return_winner_cell=True) -> StepRecord:
         """One ``HierarchicalTemporalMemory.process`` (networks.py:146-149).
-        ``active_column`` overrides inhibition (host-inhibition parity mode)."""
+        ``active_column`` overrides inhibition (host-inhibition parity mode);
+        ``return_winner_cell`` is ``TemporalMemory.process``'s flag (networks.py:91)."""
         x = np.asarray(x, dtype=bool)
         overlaps = self.sp_overlap(x)
         boosted = self.sp_boost(overlaps)
@@ -407,7 +434,7 @@ class HTMOracle:
             self.sp_learn(x, active_column)
         self.sp_duty_update(active_column)  # networks.py:33: always
 
-        acp, burst, winners, d1 = self.tm_select(active_column)
+        acp, burst, winners, d1 = self.tm_select(active_column, want=learning or return_winner_cell)
         learn = punish = np.zeros(0, dtype=np.int64)
         tie, d2 = False, 0
         if learning:
@@ -417,14 +444,15 @@ class HTMOracle:
         active_cell = (active_column[rows] * self.c + cells).astype(np.int64)
         activation = np.zeros((self.C, self.c), dtype=bool)
         activation[active_column] = act_rows  # networks.py:118-119
-        d3 = self.tm_activate(activation.reshape(-1))
+        d3 = self.tm_activate(activation.reshape(-1), want_jitter=return_winner_cell)
         self.cell_activation = activation
         self.prev_winners = winners
         return StepRecord(
             overlaps=overlaps, boosted=boosted, active_column=active_column, bursting=burst,
-            winner_cell=winners, active_cell=active_cell, learning_segment=learn,
-            punished_segment=punish, n_segments=self.n_seg, matching_segment=self.m_seg,
-            matching_activation=self.m_act, matching_jit=self.m_jit, draws=d1 + d2 + d3,
+            winner_cell=winners if winners is not None else np.zeros(0, dtype=np.int64), active_cell=active_cell,
+            learning_segment=learn, punished_segment=punish, n_segments=self.n_seg, matching_segment=self.m_seg,
+            matching_activation=self.m_act,
+            matching_jit=self.m_jit if self.m_jit is not None else np.zeros(0, dtype=F32), draws=d1 + d2 + d3,
             undefined_tie=tie,
         )
 

@@ -42,7 +42,21 @@ CASES = {
     "mid": (256, 512, 32, 22, 3000, 40, 0.2, 0.05, 11, 250, 10),
     "cfg1": (1000, 2048, 32, None, 10000, 100, 0.2, 0.05, 0, 1000, 4),
     "cfg2": (1024, 2048, 32, None, 10000, 100, 0.2, 0.05, 0, 1000, 4),
+    # every step draws its (learning, return_winner_cell) flags (networks.py:91) from `mode_schedule`
+    "mixed": (64, 256, 8, 20, 1200, 12, 0.25, 0.05, 5, 100, 0),
 }
+
+
+def mode_schedule(steps, seed):
+    """Per-step (learning, return_winner_cell): mostly the default (True, True), with runs of
+    inference-only steps, learning without the jitter draw, and winners without learning."""
+    g = np.random.default_rng(77 + seed)
+    r = g.random(steps)
+    learning = (r < 0.6) | ((r >= 0.75) & (r < 0.87))
+    winner = (r < 0.6) | (r >= 0.87)
+    learning[:30] = True  # let some segments form first
+    winner[:30] = True
+    return learning, winner
 
 
 def make_inputs(input_dim, patterns, density, noise, steps, seed):
@@ -57,17 +71,19 @@ def make_inputs(input_dim, patterns, density, noise, steps, seed):
 def reference_record(htm, sp_state, tm_state):
     c = htm.cell_dim
     ds = tm_state.distal_state
+    wc = tm_state.winner_cell  # None when neither learning nor return_winner_cell (networks.py:99,125)
+    jit = ds.matching_segment_jittered_potential  # None until somebody needs it (projections.py:229-243)
     return dict(
         n_segments=len(htm.temporal_memory.distal_projection.segment_bundle),
         overlaps=sp_state.overlaps,
         boosted=sp_state.boosted_overlaps,
         active_column=sp_state.active_column,
         bursting=tm_state.active_column_bursting,
-        winner_cell=tm_state.winner_cell[0] * c + tm_state.winner_cell[1],
+        winner_cell=wc[0] * c + wc[1] if wc is not None else np.zeros(0, dtype=np.int64),
         active_cell=tm_state.active_cell[0] * c + tm_state.active_cell[1],
         matching_segment=ds.matching_segment,
         matching_activation=ds.matching_segment_activation,
-        matching_jit=ds.matching_segment_jittered_potential,
+        matching_jit=jit if jit is not None else np.zeros(0, dtype=np.float32),
     )
 
 
@@ -100,6 +116,8 @@ def run_case(name):
     orc = HTMOracle(OracleConfig(I, C, c, k), rng=rs, overlap="packed")
     assert np.array_equal(orc.permanence, init_perm)
 
+    learn_flags, winner_flags = (mode_schedule(steps, seed) if name == "mixed"
+                                 else (np.ones(steps, dtype=bool), np.ones(steps, dtype=bool)))
     digests = np.zeros(steps, dtype=np.uint64)
     draws = np.zeros(steps, dtype=np.int64)
     state_steps, state_digests = [], []
@@ -109,10 +127,15 @@ def run_case(name):
     t_ref = 0.0
     for t in range(steps):
         ta = time.perf_counter()
-        sp_state, tm_state = htm.process(xs[t])
+        lf, wf = bool(learn_flags[t]), bool(winner_flags[t])
+        if name == "mixed":  # HierarchicalTemporalMemory.process (networks.py:146-149) with the TM flag exposed
+            sp_state = htm.spatial_pooler.process(xs[t], learning=lf)
+            tm_state = htm.temporal_memory.process(sp_state, learning=lf, return_winner_cell=wf)
+        else:
+            sp_state, tm_state = htm.process(xs[t])
         t_ref += time.perf_counter() - ta
         ref = reference_record(htm, sp_state, tm_state)
-        rec = orc.step(xs[t])
+        rec = orc.step(xs[t], learning=lf, return_winner_cell=wf)
         d_ref = step_digest(**ref)
         d_orc = record_digest(rec)
         if rec.undefined_tie:
@@ -141,8 +164,8 @@ def run_case(name):
     out = os.path.join(HERE, f"{name}.npz")
     np.savez_compressed(
         out, config=np.array([I, C, c, k_eff, steps, patterns, seed], dtype=np.int64),
-        density=np.float64(density), noise=np.float64(noise),
-        digests=digests, draws=draws, state_steps=np.array(state_steps, dtype=np.int64),
+        density=np.float64(density), noise=np.float64(noise), learning_flags=learn_flags,
+        winner_flags=winner_flags, digests=digests, draws=draws, state_steps=np.array(state_steps, dtype=np.int64),
         state_digests=np.array(state_digests, dtype=np.uint64), undefined_tie_steps=np.array(ties, dtype=np.int64),
         n_segments_final=np.int64(rec.n_segments), reference_steps_per_s=np.float64(steps / t_ref), **full)
     print(f"{name}: {steps} steps ok, S={rec.n_segments}, ties={ties}, ref {steps / t_ref:.1f} steps/s, "

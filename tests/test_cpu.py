@@ -35,6 +35,28 @@ def test_oracle_matches_reference_golden(name, steps):
             assert oracle_state_digest(orc) == state_at[t], f"{name}: learned state at step {t}"
 
 
+def test_oracle_matches_reference_golden_mixed_modes():
+    """A trace in which every step has its own (learning, return_winner_cell) flags
+    (TemporalMemory.process, networks.py:91-128): inference-only steps draw nothing, the
+    jitter draw is deferred until a later step needs it, growth is skipped after a step
+    without winner cells."""
+    info = load_golden("mixed")
+    g = info["g"]
+    xs = golden_inputs(info, info["steps"])
+    orc = HTMOracle(OracleConfig(info["I"], info["C"], info["c"], info["k"]),
+                    rng=np.random.RandomState(info["seed"]), overlap="packed")
+    state_at = {int(s): int(d) for s, d in zip(g["state_steps"], g["state_digests"])}
+    flags = list(zip(g["learning_flags"], g["winner_flags"]))
+    assert len({(bool(a), bool(b)) for a, b in flags}) == 4
+    for t in range(info["steps"]):
+        lf, wf = bool(flags[t][0]), bool(flags[t][1])
+        rec = orc.step(xs[t], learning=lf, return_winner_cell=wf)
+        assert record_digest(rec) == int(g["digests"][t]), f"step {t}"
+        assert rec.draws == int(g["draws"][t])
+        if t in state_at:
+            assert oracle_state_digest(orc) == state_at[t], f"learned state at step {t}"
+
+
 def test_oracle_dense_equals_packed_overlap():
     cfg = OracleConfig(100, 200, 8, 12)
     a = HTMOracle(cfg, rng=np.random.RandomState(5), overlap="dense")

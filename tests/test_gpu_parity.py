@@ -445,3 +445,48 @@ def test_stream_batch_equals_streams_stepped_alone():
     assert [gpu_state_digest(h) for h in nets] == alone
     # and they really are different streams
     assert len(set(alone)) == B
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", ["cluster", "off"])
+def test_mixed_learning_and_winner_flags_match_reference_trace(fused):
+    """Per-step (learning, return_winner_cell) flags of TemporalMemory.process (networks.py:91):
+    inference-only steps draw nothing, the jitter draw is deferred until a later step needs
+    it, no growth after a step without winner cells -- against the trace recorded from the
+    unmodified reference (tests/golden/mixed.npz), through HierarchicalTemporalMemory.process
+    (which falls back from the fused kernel to the per-stage kernels when it has to)."""
+    import bithtm_b200 as bithtm
+
+    info = load_golden("mixed")
+    g = info["g"]
+    I, C, c, k, seed, steps = info["I"], info["C"], info["c"], info["k"], info["seed"], info["steps"]
+    xs = golden_inputs(info, steps)
+    np.random.seed(seed)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused=fused)
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    state_at = {int(s): int(d) for s, d in zip(g["state_steps"], g["state_digests"])}
+    for t in range(steps):
+        lf, wf = bool(g["learning_flags"][t]), bool(g["winner_flags"][t])
+        rec = orc.step(xs[t], learning=lf, return_winner_cell=wf)
+        sp_state, tm_state = htm.process(xs[t], learning=lf, return_winner_cell=wf)
+        ds = tm_state.distal_state
+        wc = tm_state.winner_cell
+        assert (wc is None) == (not (lf or wf))
+        assert (ds.matching_segment_jittered_potential is None) == (not wf)
+        got = dict(
+            n_segments=tm_state.n_segments, overlaps=sp_state.overlaps, boosted=sp_state.boosted_overlaps,
+            active_column=sp_state.active_column, bursting=tm_state.active_column_bursting,
+            winner_cell=wc[0] * c + wc[1] if wc is not None else np.zeros(0, dtype=np.int64),
+            active_cell=tm_state.active_cell[0] * c + tm_state.active_cell[1],
+            matching_segment=ds.matching_segment, matching_activation=ds.matching_segment_activation,
+            matching_jit=ds.matching_segment_jittered_potential if wf else np.zeros(0, dtype=np.float32))
+        d = diff_records(got, oracle_record(rec))
+        assert not d, f"step {t} (learning={lf}, return_winner_cell={wf}): {d}"
+        assert step_digest(**got) == int(g["digests"][t]), f"step {t}: differs from the reference trace"
+        if t in state_at:
+            assert gpu_state_digest(htm) == state_at[t], f"learned state at step {t}"
+    # the caller's np.random ends where the reference's does
+    rs = np.random.RandomState(seed)
+    rs.randn(C, I)
+    rs.random_sample(int(np.sum(g["draws"])))
+    assert np.array_equal(np.random.random_sample(2000), rs.random_sample(2000))  # same continuation
