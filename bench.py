@@ -93,7 +93,7 @@ def reference_arm(args):
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index):
         self.index = index
@@ -108,7 +108,13 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Start of the region whose samples count (the sampler itself is started early: nvidia-smi
+        takes a few hundred ms to come up)."""
+        self.t_mark = time.time()
+
     def stop(self):
+        self.t_stop = time.time()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -123,18 +129,32 @@ class ClockSampler:
                 open(self.path, "w").write(out)
             except Exception:
                 pass
+        import datetime
+
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in open(self.path):
             f = [p.strip() for p in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
+                row = (float(f[1]), float(f[2]), f[5:9])
             except ValueError:
                 continue
-            for name, v in zip(names, f[5:9]):
+            ts = None
+            if len(f) > 9:
+                try:
+                    ts = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    ts = None
+            rows.append((ts, row))
+        t0 = getattr(self, "t_mark", None)
+        inside = [r for ts, r in rows if ts is not None and t0 is not None and t0 - 0.05 <= ts <= self.t_stop + 0.05]
+        for a, b, flags in (inside or [r for _, r in rows]):
+            sm.append(a)
+            smax.append(b)
+            for name, v in zip(names, flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         try:
@@ -192,6 +212,8 @@ def ours(args):
                                                  max_segments=1 << 17, fused=args.fused, fused_ctas=args.fused_ctas)
 
     xs = make_inputs(cfg, total, seed)
+    sampler = ClockSampler(local)
+    sampler.start()  # early: nvidia-smi takes a few hundred ms to deliver its first sample
 
     # ---------------- device-resident arm: inputs in an HBM ring, one CUDA graph per step
     htm = build(total, "lazy")
@@ -204,8 +226,7 @@ def ours(args):
                  1: f"whole step in one kernel on a thread-block cluster of {eng.ctx.fused_ctas} CTAs",
                  2: f"whole step in one cooperative kernel, {eng.ctx.fused_ctas} CTAs"}[eng.ctx.fused_mode]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    sampler = ClockSampler(local)
-    sampler.start()  # nvidia-smi needs a moment to start: sample from the warm-up on (same load)
+    sampler.mark()  # clocks are reported from the warm-up on (same load as the timed region)
     for _ in range(W):
         flush.fill_(1)
         eng.launch_graph(graph1, 1)
@@ -311,6 +332,17 @@ def ours(args):
             hbm = cfg3_kernels.measure(65536, 16384, 250, 20)
         except Exception as e:  # never lose the headline line
             hbm = {"error": repr(e)}
+    sharded = None
+    if world > 1 and not args.no_hbm:
+        # the multi-GPU path of ONE network: cfg3 sharded over all ranks, SP by column, TM by
+        # segment id, one cooperative kernel per shard with in-kernel exchanges over NVLink peer memory
+        try:
+            import cfg3_sharded
+
+            torch.cuda.empty_cache()
+            sharded = cfg3_sharded.measure(300, 65536, 16384, "fused")
+        except Exception as e:  # never lose the headline line
+            sharded = {"error": repr(e)}
     batched = None
     if rank == 0 and world == 1 and not args.no_hbm:
         # independent streams side by side on the one GPU (BASELINE configs[3]): aggregate throughput
@@ -339,7 +371,8 @@ def ours(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "note": "HierarchicalTemporalMemory.process(host bool array), np.random kept in lock-step"},
             "gpu_launches": launches_per_step * K,
-            "roofline": roofline, "roofline_hbm_kernels": hbm, "streams_batched": batched, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_hbm_kernels": hbm, "streams_batched": batched, "sharded_cfg3": sharded,
+            "cpu_baseline": cpu,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

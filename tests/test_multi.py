@@ -379,3 +379,72 @@ def test_fused_shard_kernels_concurrent_on_one_gpu(name, world, steps):
     owner, count, cells, pm = proj.export_segments(parts=parts)
     got = state_digest(perm, duty, proj.bundle_segments, canonical_from_rows(owner, cells, pm))
     assert got == state_digest(orc.permanence, orc.duty, orc.cell_nseg, orc.canonical_synapses())
+
+
+@pytest.mark.gpu
+def test_sharded_equals_unsharded_at_scale():
+    """No oracle at this size (validate sharded == unsharded): 32768
+    columns x 4096 inputs, many-CTA random-stream production and the grid-wide top-k active.
+    One network as a single cooperative kernel vs the same network as two shard kernels
+    running concurrently and exchanging through each other's regions."""
+    import torch
+
+    import bithtm_b200 as bithtm
+    from bithtm_b200.projections import DenseProjection
+    from oracle.digest import canonical_from_rows, state_digest
+
+    I, C, c, k, steps, world = 4096, 32768, 32, 655, 160, 2
+    g = np.random.default_rng(3)
+    base = g.random((20, I)) < 0.2
+    xs = base[np.arange(steps) % 20] ^ (g.random((steps, I)) < 0.05)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(99)
+    perm = torch.randn(C, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
+    kw = dict(rng_sync="lazy", max_segments=1 << 18, max_synapses_per_segment=64)
+
+    def build(**extra):
+        np.random.seed(4)
+        rows = perm
+        if "column_shard" in extra:
+            r, w = extra["column_shard"]
+            rows = perm[r * C // w:(r + 1) * C // w]
+        sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=rows))
+        return bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, **kw, **extra)
+
+    whole = build(fused="grid")
+    assert whole.engine.ctx.jump_polys > 0
+    shards = [build(column_shard=(r, world), fused="shard", fused_ctas=60) for r in range(world)]
+    regions = [torch.zeros(h.engine.exchange_region_ints(), dtype=torch.int32, device="cuda") for h in shards]
+    for h in shards + [whole]:
+        h.temporal_memory._rng.before(h.engine)
+    for h in shards:
+        h.engine.set_exchange_regions([r.data_ptr() for r in regions], keepalive=regions)
+    streams = [torch.cuda.Stream() for _ in shards]
+    for t in range(steps):
+        words = whole.engine.pack_input(xs[t])
+        whole.process(words, return_state=False)
+        torch.cuda.synchronize()
+        for h, st in zip(shards, streams):
+            with torch.cuda.stream(st):
+                h.process(words, return_state=False)
+        torch.cuda.synchronize()
+        if t % 20 == 19 or t == steps - 1:
+            ref = whole.engine.summary().copy()
+            for r, h in enumerate(shards):
+                got = h.engine.summary()
+                n = 4 + 4 * k  # step, status, segments, winners, active columns, row words (not the RNG key form)
+                assert np.array_equal(got[:n], ref[:n]), f"step {t} shard {r}"
+    for h in shards + [whole]:
+        h.engine.check_status()
+    proj = whole.temporal_memory.distal_projection
+    owner, count, cells, pm = proj.export_segments()
+    want = state_digest(whole.spatial_pooler.proximal_projection.permanence, whole.spatial_pooler.boosting.duty_cycle,
+                        proj.bundle_segments, canonical_from_rows(owner, cells, pm))
+    parts = [h.temporal_memory.distal_projection.export_local_segments() for h in shards]
+    sproj = shards[0].temporal_memory.distal_projection
+    owner, count, cells, pm = sproj.export_segments(parts=parts)
+    got = state_digest(np.concatenate([h.spatial_pooler.proximal_projection.permanence for h in shards]),
+                       np.concatenate([h.spatial_pooler.boosting.duty_cycle for h in shards]),
+                       sproj.bundle_segments, canonical_from_rows(owner, cells, pm))
+    assert got == want
+    assert int(whole.engine.scalars()[2]) > 5000  # segments were learned

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """cfg3 (65536 columns x 16384 inputs, 32 cells, k=1311) as ONE network sharded over the
 ranks of a torchrun job: spatial pooler by column, temporal memory by segment id, two
-NCCL all-gathers per timestep.  Permanence rows are drawn on each device (performance
-run; parity of the sharded path is tests/test_multi.py).
+exchanges per timestep.  Permanence rows are drawn on each device (performance run; parity
+of the sharded path is tests/test_multi.py).
 
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/cfg3_sharded.py [steps] [C] [I] [mode]
 
-mode = "nccl" (default: per-stage kernels, NCCL all-gathers issued by the host) or "fused" (one cooperative
-kernel per shard and per 50 steps, exchanges in-kernel over NVLink peer memory).
+mode = "fused" (default: one cooperative kernel per shard and per 50 steps, exchanges in-kernel
+over NVLink peer memory) or "nccl" (per-stage kernels, NCCL all-gathers issued by the host).
 """
 import json
 import os
@@ -16,34 +16,29 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
-import torch.distributed as dist
-
-import bithtm_b200 as bithtm
-from bithtm_b200.projections import DenseProjection
 
 
-def main():
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    C = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
-    I = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
-    mode = sys.argv[4] if len(sys.argv) > 4 else "nccl"
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def measure(steps=300, C=65536, I=16384, mode="fused", verbose=False):
+    """Every rank of the (already initialised, when world > 1) process group calls this; returns
+    the result dict on every rank (times are the max over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    import bithtm_b200 as bithtm
+    from bithtm_b200.projections import DenseProjection
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
     c, k = 32, round(C * 0.02)
-    patterns = 50
+    patterns, chunk = 50, 50
     g = np.random.default_rng(0)
     base = g.random((patterns, I)) < 0.2
-    xs = base[np.arange(steps) % patterns] ^ (g.random((steps, I)) < 0.05)
+    xs = base[np.arange(2 * patterns) % patterns] ^ (g.random((2 * patterns, I)) < 0.05)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + rank)
     perm = torch.randn(C // world, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
     np.random.seed(0)
     sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
-    chunk = 50
     htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy",
                                             column_shard=True if world > 1 else None,
                                             max_segments=1 << 21, max_synapses_per_segment=64,
@@ -54,13 +49,11 @@ def main():
     torch.cuda.empty_cache()
     eng = htm.engine
     htm.temporal_memory._rng.before(eng)
-    words = [eng.pack_input(x) for x in xs[:patterns * 2]]
+    words = [eng.pack_input(x) for x in xs]
     graph = None
     if mode == "fused":
-        eng.load_ring(xs[:patterns * 2])
+        eng.load_ring(xs)
         graph = eng.graph(chunk, learning=True)
-        if rank == 0:
-            print("exchange transport:", getattr(htm, "exchange_transport", "local"), flush=True)
     torch.cuda.synchronize()
     times = []
     for t0 in range(0, steps, chunk):
@@ -80,14 +73,37 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         times.append(float(ms))
-        sc = eng.scalars()
-        if rank == 0:
-            print(f"step {t0 + chunk}: {times[-1]:.3f} ms/step  S={sc[2]} M={sc[4]} L={sc[8]} status={sc[12]}", flush=True)
+        if verbose and rank == 0:
+            sc = eng.scalars()
+            print(f"step {t0 + chunk}: {times[-1]:.3f} ms/step  S={sc[2]} M={sc[4]} L={sc[8]} status={sc[12]}",
+                  flush=True)
     eng.check_status()
-    if rank == 0:
-        print(json.dumps({"workload": f"cfg3 sharded: {C} columns x {I} inputs, k={k}", "n_gpus": world,
-                          "ms_per_step": times[-1], "steps_per_s": 1e3 / times[-1],
-                          "exchanges_per_step": 2 if world > 1 else 0, "mode": mode}))
+    out = {"workload": f"cfg3 as ONE network: {C} columns x {I} inputs, k={k}, sharded over {world} GPU(s)",
+           "n_gpus": world, "ms_per_step": times[-1], "steps_per_s": 1e3 / times[-1], "mode": mode,
+           "exchanges_per_step": 2 if world > 1 else 0,
+           "transport": getattr(htm, "exchange_transport", "local") if mode == "fused" else "NCCL all-gather",
+           "steps": steps}
+    del htm, eng, sp
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    C = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+    I = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
+    mode = sys.argv[4] if len(sys.argv) > 4 else "fused"
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = measure(steps, C, I, mode, verbose=True)
+    if int(os.environ.get("RANK", 0)) == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
