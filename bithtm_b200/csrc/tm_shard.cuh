@@ -65,7 +65,8 @@ __device__ void ph_shard_pack(const bh_ctx& c, int* send, int b, int nb) {
     if (rec_ok && pos < c.xr_cap) rec.recyc[pos] = s;
   }
   if (b == 0 && threadIdx.x == 0) {
-    int st = 0;
+    // every rank learns of any rank's overflow / tie note through the record (one exchange later)
+    int st = c.sc[BH_SC_STATUS];
     if (m_total > c.xm_cap) st |= BH_ST_XCH_OVERFLOW;
     rec.hdr[0] = m_total < c.xm_cap ? m_total : c.xm_cap;
     rec.hdr[1] = r_total < c.xr_cap ? r_total : c.xr_cap;

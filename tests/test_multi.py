@@ -390,6 +390,7 @@ def test_sharded_equals_unsharded_at_scale():
     import torch
 
     import bithtm_b200 as bithtm
+    from bithtm_b200 import _native as nat
     from bithtm_b200.projections import DenseProjection
     from oracle.digest import canonical_from_rows, state_digest
 
@@ -400,7 +401,7 @@ def test_sharded_equals_unsharded_at_scale():
     gen = torch.Generator(device="cuda")
     gen.manual_seed(99)
     perm = torch.randn(C, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
-    kw = dict(rng_sync="lazy", max_segments=1 << 18, max_synapses_per_segment=64)
+    kw = dict(rng_sync="lazy", max_segments=1 << 18, max_synapses_per_segment=128)
 
     def build(**extra):
         np.random.seed(4)
@@ -431,9 +432,15 @@ def test_sharded_equals_unsharded_at_scale():
         if t % 20 == 19 or t == steps - 1:
             ref = whole.engine.summary().copy()
             for r, h in enumerate(shards):
-                got = h.engine.summary()
+                got = h.engine.summary().copy()
                 n = 4 + 4 * k  # step, status, segments, winners, active columns, row words (not the RNG key form)
-                assert np.array_equal(got[:n], ref[:n]), f"step {t} shard {r}"
+                # the status word is per rank (notes raised by the rank that stores a row reach the others
+                # with the next exchange): compared at the end
+                got[1] = 0
+                want = ref[:n].copy()
+                want[1] = 0
+                bad = np.flatnonzero(got[:n] != want)
+                assert bad.size == 0, f"step {t} shard {r}: summary words {bad[:8]} differ: {got[bad[:8]]} vs {want[bad[:8]]}"
     for h in shards + [whole]:
         h.engine.check_status()
     proj = whole.temporal_memory.distal_projection
