@@ -344,15 +344,24 @@ def ours(args):
         except Exception as e:  # never lose the headline line
             sharded = {"error": repr(e)}
     batched = None
-    if rank == 0 and world == 1 and not args.no_hbm:
-        # independent streams side by side on the one GPU (BASELINE configs[3]): aggregate throughput
+    if not args.no_hbm:
+        # independent streams side by side on every GPU (BASELINE configs[3]: 1024 streams over 8 GPUs = 128 per
+        # GPU, partitioned trivially): aggregate throughput, max-over-ranks time
         try:
             import stream_batch
 
             torch.cuda.empty_cache()
-            batched = stream_batch.measure(128, 4, 400, 200)
-            batched["note"] = ("128 independent cfg2 networks, one 4-CTA cluster kernel each, one CUDA graph of 50 "
-                               "steps x 128 launches; L2-resident")
+            if world > 1:
+                dist.barrier()
+            batched = stream_batch.measure(128, 4, 400, 200, seed0=1000 * rank)
+            if world > 1:
+                ms = torch.tensor([batched["ms"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                batched["ms"] = float(ms)
+                batched["streams"] *= world
+                batched["aggregate_steps_per_s"] = batched["streams"] * batched["steps_per_stream"] / (batched["ms"] * 1e-3)
+            batched["note"] = (f"{128 * world} independent cfg2 networks, 128 per GPU, one 4-CTA cluster kernel each, one "
+                               "CUDA graph of 50 steps x 128 launches per GPU; L2-resident; no collective")
         except Exception as e:
             batched = {"error": repr(e)}
     if rank == 0:

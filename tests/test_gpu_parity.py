@@ -490,3 +490,56 @@ def test_mixed_learning_and_winner_flags_match_reference_trace(fused):
     rs.randn(C, I)
     rs.random_sample(int(np.sum(g["draws"])))
     assert np.array_equal(np.random.random_sample(2000), rs.random_sample(2000))  # same continuation
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", ["cluster", "grid", "off"])
+def test_degenerate_inputs_match_oracle(fused):
+    """Empty input (every overlap 0: the whole top-k is one tie, lowest columns win), full
+    input, and the same input repeated -- interleaved with ordinary ones."""
+    import bithtm_b200 as bithtm
+
+    I, C, c, k, seed = 96, 320, 16, 12, 21
+    g = np.random.default_rng(5)
+    xs = []
+    for t in range(160):
+        r = t % 8
+        if r == 3:
+            xs.append(np.zeros(I, dtype=bool))
+        elif r == 6:
+            xs.append(np.ones(I, dtype=bool))
+        elif r == 7:
+            xs.append(xs[-2].copy())
+        else:
+            xs.append(g.random(I) < 0.25)
+    np.random.seed(seed)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused=fused, fused_ctas=5 if fused != "off" else None)
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    for t, x in enumerate(xs):
+        rec = orc.step(x)
+        sp_state, tm_state = htm.process(x)
+        d = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not d, f"step {t}: {d}"
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
+
+
+@pytest.mark.gpu
+def test_capacity_overflow_raises():
+    """The reference grows its arrays without bound; here an exhausted capacity raises and names it."""
+    import bithtm_b200 as bithtm
+    from bithtm_b200 import _native as nat
+
+    info = load_golden("tiny")
+    xs = golden_inputs(info, 200)
+    np.random.seed(info["seed"])
+    htm = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], max_segments=64)
+    with pytest.raises(nat.NativeError, match="max_segments"):
+        for t in range(200):
+            htm.process(xs[t])
+    np.random.seed(info["seed"])
+    htm = bithtm.HierarchicalTemporalMemory(info["I"], info["C"], info["c"], info["k"], max_synapses_per_segment=32,
+                                            max_segments=4096)
+    # 32 slots hold a freshly grown segment exactly; later growth on top of surviving synapses does not fit
+    with pytest.raises(nat.NativeError, match="max_synapses_per_segment"):
+        for t in range(1500):
+            htm.process(xs[t % 200])

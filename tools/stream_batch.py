@@ -13,7 +13,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def measure(B=64, ctas=16, steps=400, warm=200):
+def measure(B=64, ctas=16, steps=400, warm=200, seed0=0):
     import torch
 
     import bithtm_b200 as bithtm
@@ -23,11 +23,11 @@ def measure(B=64, ctas=16, steps=400, warm=200):
     total = warm + steps
     nets, inputs = [], []
     for i in range(B):
-        np.random.seed(i)
+        np.random.seed(seed0 + i)
         nets.append(bithtm.HierarchicalTemporalMemory(cfg["input_dim"], cfg["column_dim"], cfg["cell_dim"],
                                                       cfg["active_columns"], rng_sync="lazy", ring_len=total,
                                                       max_segments=1 << 15, fused="cluster", fused_ctas=ctas))
-        inputs.append(make_inputs(cfg, total, i))
+        inputs.append(make_inputs(cfg, total, seed0 + i))
     batch = bithtm.StreamBatch(nets)
     batch.load_inputs(inputs)
     per = 50
