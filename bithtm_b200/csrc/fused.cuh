@@ -19,6 +19,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
   const int nw = nb > 1 ? nb - 1 : 1;  // CTAs running the ranged TM phases
   const bool worker = b < nw;
   const bool rng = b == nb - 1;        // CTA producing the random draws
+  // Small networks (cluster mode): independent pieces of a phase run on DIFFERENT CTAs instead of one after
+  // the other on all of them -- CTAs [0, nsel) form the winner lists while the others learn the SP rows
+  // (P2) and flag the learning segments (P3), so a phase costs its longest chain of dependent L2 round
+  // trips, not their sum.  Partitions: select (b, nsel); learn-select (b - nl0, nlrn); scan (b, nw).
+  const bool split = MODE == 1 && nw >= 8;
+  const int nsel = split ? 4 : nw;
+  const int nl0 = split ? nsel : 0;
+  const int nlrn = nw - nl0;
   unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
 #define BH_SYNC()                          \
   do {                                     \
@@ -71,21 +79,28 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_SYNC();
     BH_STAMP();
     // P2: SP learning + duty cycles; bursting / winner bits per active column
-    if (learning) ph_sp_learn(c, input, b, nb);
-    ph_duty(c, b, nb);
-    if (worker) ph_select_a(c, b, nw);
-    BH_SYNC();
-    BH_STAMP();
-    // P3: ordered winner lists; learning / punished flags among previous matching segments
-    if (worker) {
-      ph_select_b(c, b, nw);
-      ph_learn_select_a(c, learning, b, nw);
+    if (split) {
+      if (b < nsel) {
+        ph_select_a(c, b, nsel);
+      } else {
+        if (learning) ph_sp_learn<true>(c, input, b - nsel, nb - nsel);
+        ph_duty(c, b - nsel, nb - nsel);
+      }
+    } else {
+      if (learning) ph_sp_learn<MODE == 1>(c, input, b, nb);
+      ph_duty(c, b, nb);
+      if (worker) ph_select_a(c, b, nw);
     }
     BH_SYNC();
     BH_STAMP();
+    // P3: ordered winner lists; learning / punished flags among previous matching segments
+    if (b < nsel) ph_select_b(c, b, nsel);
+    if (b >= nl0 && worker) ph_learn_select_a(c, learning, b - nl0, nlrn);
+    BH_SYNC();
+    BH_STAMP();
     // P4: learning lists, recycled / new segments; draw #2 (rand(L, W+1)) on the rng CTA
-    if (rng) ph_draw(c, 2, learning, nw);
-    if (worker) ph_learn_select_b(c, learning, b, nw);
+    if (rng) ph_draw(c, 2, learning, nlrn);
+    if (b >= nl0 && worker) ph_learn_select_b(c, learning, b - nl0, nlrn);
     BH_SYNC();
     BH_STAMP();
     // P4b: the stream words draw #2 planned for many CTAs (mt19937.cuh)

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (rng && nb > 1) ph_rng_speculate(c);
     BH_SYNC();
     // P2..P7 as in fused.cuh; learning and the segment scan touch only what this rank stores
-    if (learning) ph_sp_learn(c, input, b, nb);
+    if (learning) ph_sp_learn<false>(c, input, b, nb);
     ph_duty(c, b, nb);
     if (worker) ph_select_a(c, b, nw);
     BH_SYNC();

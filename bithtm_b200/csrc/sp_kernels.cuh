@@ -1062,7 +1062,7 @@ __global__ void k_set_active(const __grid_constant__ bh_ctx c, const int32_t* __
 // 256-byte permanence segment is coalesced and the ballot is the mask word.
 // projections.py:23-24.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void ph_sp_learn(const bh_ctx& c, const uint32_t* input, int b, int nb) {
+__device__ __forceinline__ void sp_learn_wide(const bh_ctx& c, const uint32_t* input, int b, int nb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int k = c.active_columns, I = c.input_dim, words = c.input_words;
   const int cur = c.sc[BH_SC_STEP] & 1;
@@ -1100,8 +1100,57 @@ __device__ __forceinline__ void ph_sp_learn(const bh_ctx& c, const uint32_t* inp
   }
 }
 
+// Short rows (a warp covers 4 x 32 inputs per iteration, so a row needs only a few warps): the warps of
+// a CTA form teams that work on different rows at the same time.
+__device__ __forceinline__ void sp_learn_grouped(const bh_ctx& c, const uint32_t* input, int b, int nb) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int k = c.active_columns, I = c.input_dim, words = c.input_words;
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int* act = c.active_cols + cur * k;
+  const double d_on = c.sp_delta_on, d_off = c.sp_delta_off, thr = c.sp_threshold;
+  const int wpr = (words + 3) / 4;  // warps that have work on one row
+  const int groups = warps / wpr, grp = warp / wpr, wig = warp - grp * wpr;
+  if (grp >= groups) return;  // leftover warps
+#pragma unroll 1
+  for (int r = b * groups + grp; r < k; r += nb * groups) {
+    const int col = act[r] - c.col_lo;  // local row; columns of other shards are skipped
+    if (col < 0 || col >= c.col_local) continue;
+    double* prow = c.sp_perm + (long long)col * I;
+    uint32_t* mrow = c.sp_mask + (long long)col * c.mask_stride;
+    const int w0 = wig * 4;
+    double p[4];
+    uint32_t xin[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int w = w0 + j, i = w * 32 + lane;
+      xin[j] = w < words ? input[w] : 0u;
+      p[j] = (w < words && i < I) ? prow[i] : -1.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int w = w0 + j, i = w * 32 + lane;
+      bool on = false;
+      if (w < words && i < I) {
+        const double q = __dadd_rn(p[j], ((xin[j] >> lane) & 1u) ? d_on : d_off);
+        prow[i] = q;
+        on = q >= thr;
+      }
+      const uint32_t bits = __ballot_sync(BH_FULL, on);
+      if (lane == 0 && w < words) mrow[w] = bits;
+    }
+  }
+}
+
+// SHORT_ROWS: also compile the team variant (kernels that serve small networks); the HBM-bound grid
+// kernel keeps only the wide loop (the extra code costs it registers and 5 us per step at cfg3).
+template <bool SHORT_ROWS = true>
+__device__ __forceinline__ void ph_sp_learn(const bh_ctx& c, const uint32_t* input, int b, int nb) {
+  if (SHORT_ROWS && (c.input_words + 3) / 4 * 2 <= (int)(blockDim.x >> 5)) sp_learn_grouped(c, input, b, nb);
+  else sp_learn_wide(c, input, b, nb);
+}
+
 __global__ void __launch_bounds__(SP_THREADS) k_sp_learn(const __grid_constant__ bh_ctx c, const uint32_t* input) {
-  ph_sp_learn(c, input, blockIdx.x, gridDim.x);
+  ph_sp_learn<true>(c, input, blockIdx.x, gridDim.x);
 }
 
 // (c) duty-cycle EMA: two separately rounded float32 operations.
