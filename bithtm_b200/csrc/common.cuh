@@ -65,6 +65,25 @@ __device__ __noinline__ int block_sum(int v, int* sm) {
   return warp_sum(lane < nw ? sm[lane] : 0);
 }
 
+// Three block-wide sums with one pair of barriers; thread 0's results are valid (all threads' are).
+// `sm` holds >= 96 ints.
+__device__ __noinline__ void block_sum3(int& a, int& b, int& c, int* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  c = warp_sum(c);
+  __syncthreads();  // protect sm from a previous use
+  if (lane == 0) {
+    sm[w] = a;
+    sm[32 + w] = b;
+    sm[64 + w] = c;
+  }
+  __syncthreads();
+  a = warp_sum(lane < nw ? sm[lane] : 0);
+  b = warp_sum(lane < nw ? sm[32 + lane] : 0);
+  c = warp_sum(lane < nw ? sm[64 + lane] : 0);
+}
+
 // Block-wide exclusive prefix of a per-thread count (thread order); `total`
 // receives the block sum.  `sm` holds >= 32 ints.  All threads must call.
 __device__ __noinline__ int block_excl_scan(int v, int* sm, int& total) {
@@ -102,6 +121,41 @@ __device__ __noinline__ void blk_prefix(const int* counts, int b, int nb, int* s
   }
   before = block_sum(pre, sm);
   total = block_sum(all, sm);
+}
+
+// The same for three count arrays at once (one pass, one pair of barriers).  `sm` holds >= 192 ints.
+__device__ __noinline__ void blk_prefix3(const int* c0, const int* c1, const int* c2, int b, int nb, int* sm,
+                                         int (&before)[3], int (&total)[3]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int v[6] = {0, 0, 0, 0, 0, 0};
+  #pragma unroll 1
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    const int a0 = c0[i], a1 = c1[i], a2 = c2[i];
+    v[1] += a0;
+    v[3] += a1;
+    v[5] += a2;
+    if (i < b) {
+      v[0] += a0;
+      v[2] += a1;
+      v[4] += a2;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) v[j] = warp_sum(v[j]);
+  __syncthreads();  // protect sm from a previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sm[j * 32 + w] = v[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 6; ++j) v[j] = warp_sum(lane < nw ? sm[j * 32 + lane] : 0);
+  before[0] = v[0];
+  total[0] = v[1];
+  before[1] = v[2];
+  total[1] = v[3];
+  before[2] = v[4];
+  total[2] = v[5];
 }
 
 // device cell id = column * 32 + cell-in-column (c <= 32)

@@ -33,10 +33,15 @@ struct LearnTotals {
 
 __device__ __forceinline__ LearnTotals learn_totals(const bh_ctx& c, int learning, int b, int nb, int* s_red) {
   LearnTotals t;
-  blk_prefix(BLK(c, BLK_LEARN), b, nb, s_red, t.l_before, t.L0);
-  blk_prefix(BLK(c, BLK_PUNISH), b, nb, s_red, t.p_before, t.P);
-  int R;
-  blk_prefix(BLK(c, BLK_RECYC), b, nb, s_red, t.r_before, R);
+  __shared__ int s_red6[192];
+  int before[3], total[3];
+  blk_prefix3(BLK(c, BLK_LEARN), BLK(c, BLK_PUNISH), BLK(c, BLK_RECYC), b, nb, s_red6, before, total);
+  t.l_before = before[0];
+  t.L0 = total[0];
+  t.p_before = before[1];
+  t.P = total[1];
+  t.r_before = before[2];
+  int R = total[2];
   if (c.seg_world > 1) {  // segment shards: candidates come merged from the exchange (tm_shard.cuh)
     R = c.sc[BH_SC_X_RECYC_AVAIL];
     t.r_before = 0;
@@ -294,13 +299,12 @@ __device__ void ph_learn_select_a(const bh_ctx& c, int learning, int b, int nb) 
     #pragma unroll 1
     for (int s = sr.begin + threadIdx.x; s < sr.end; s += NT) nr += c.seg_count[s] < thr ? 1 : 0;
   }
-  int tl = block_sum(nl, s_red);
-  int tp = block_sum(np, s_red);
-  int tr = block_sum(nr, s_red);
+  __shared__ int s_red3[96];
+  block_sum3(nl, np, nr, s_red3);
   if (threadIdx.x == 0) {
-    BLK(c, BLK_LEARN)[b] = tl;
-    BLK(c, BLK_PUNISH)[b] = tp;
-    BLK(c, BLK_RECYC)[b] = tr;
+    BLK(c, BLK_LEARN)[b] = nl;
+    BLK(c, BLK_PUNISH)[b] = np;
+    BLK(c, BLK_RECYC)[b] = nr;
   }
 }
 
