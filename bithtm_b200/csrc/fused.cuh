@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     } else if (b == 0) {
       ph_topk(c);
     }
-    if (rng && nb > 1) ph_rng_speculate(c);  // idle here: produce the stream words this step will draw
+    if (rng && nb > 1) ph_rng_speculate(c, 2);  // idle here: produce half of the stream words this step will draw
     BH_SYNC();
     BH_STAMP();
     // P2: SP learning + duty cycles; bursting / winner bits per active column
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     // P3: ordered winner lists; learning / punished flags among previous matching segments
     if (b < nsel) ph_select_b(c, b, nsel);
     if (b >= nl0 && worker) ph_learn_select_a(c, learning, b - nl0, nlrn);
+    if (rng && nb > 1) ph_rng_speculate(c, 1);  // idle here too: the other half
     BH_SYNC();
     BH_STAMP();
     // P4: learning lists, recycled / new segments; draw #2 (rand(L, W+1)) on the rng CTA
@@ -125,18 +126,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_SYNC();
     BH_STAMP();
 #endif
-    // P7: segment potentials
+    // P7: segment potentials; the drawing CTA is idle for the whole scan: it produces the stream words of
+    // the rest of this step and of the next one (the P1 / P3 calls then only top up)
     if (worker) ph_activate_a(c, b, nw);
+    if (rng && nb > 1) ph_rng_speculate(c, 1, true);
     BH_SYNC();
     BH_STAMP();
     // P8: draw #3 (rand(M)) -- a phase of its own only when the words draw #2 left produced do not
     // cover it (every CTA takes the same decision from barrier-published values)
     bool ready3;
+    int m_before, m_total;  // this CTA's offset in the matching list and its length (reused by P9)
     {
       __shared__ int s_red3[32];
-      int mb, mt;
-      blk_prefix(BLK(c, BLK_MATCH), 0, nw, s_red3, mb, mt);
-      ready3 = (long long)(mt < c.match_capacity ? mt : c.match_capacity) <= c.rng64[R_READY3];
+      blk_prefix(BLK(c, BLK_MATCH), worker ? b : 0, nw, s_red3, m_before, m_total);
+      ready3 = (long long)(m_total < c.match_capacity ? m_total : c.match_capacity) <= c.rng64[R_READY3];
       __syncthreads();
     }
     if (!ready3) {
@@ -145,8 +148,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     }
     BH_STAMP();
     // P9: matching list, jitter, predictions; completes the step
-    if (ready3 && rng) ph_draw3_ready(c, nw);
-    if (worker) ph_activate_b(c, b, nw, ready3);
+    if (ready3 && rng) ph_draw3_ready(c, nw, m_total);
+    if (worker) ph_activate_b(c, b, nw, ready3, true, m_before, m_total);
     BH_SYNC();
     BH_STAMP();
   }

@@ -393,10 +393,11 @@ __device__ __forceinline__ void rng_draw3_commit(const bh_ctx& c, long long coun
 
 // One CTA, while it has nothing else to do: produce the words the current step is expected to
 // draw (serial producer; with many-CTA production the draws plan their own chunks).
-__device__ __noinline__ void ph_rng_speculate(const bh_ctx& c) {
+// `ahead`: count from the cursor (the rest of this step and the next one) instead of the step's start.
+__device__ __noinline__ void ph_rng_speculate(const bh_ctx& c, int divisor = 1, bool ahead = false) {
   __shared__ uint32_t x[MT_RING];
   if (c.jump_polys > 0) return;
-  rng_produce_serial(c, x, c.rng64[R_STEP_BASE] + c.rng64[R_EST]);
+  rng_produce_serial(c, x, c.rng64[ahead ? R_CURSOR : R_STEP_BASE] + c.rng64[R_EST] / divisor);
 }
 
 // Host state -> ring (single CTA): key = words [0, 624), cursor = pos.

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       topk_core(reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k, c.active_cols + par * k, c.xk_cols,
                 c.col_active);
     }
-    if (rng && nb > 1) ph_rng_speculate(c);
+    if (rng && nb > 1) ph_rng_speculate(c, 1);
     BH_SYNC();
     // P2..P7 as in fused.cuh; learning and the segment scan touch only what this rank stores
     if (learning) ph_sp_learn<false>(c, input, b, nb);

@@ -106,10 +106,10 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
 
 // Draw #3 without production, when the words exist already (count <= R_READY3, decided
 // identically by every CTA): the drawing CTA only does the bookkeeping.
-__device__ __noinline__ void ph_draw3_ready(const bh_ctx& c, int nw) {
+__device__ __noinline__ void ph_draw3_ready(const bh_ctx& c, int nw, int pre_total = -1) {
   __shared__ int s_red[32];
-  int m_before, m_total;
-  blk_prefix(BLK(c, BLK_MATCH), 0, nw, s_red, m_before, m_total);
+  int m_before, m_total = pre_total;
+  if (pre_total < 0) blk_prefix(BLK(c, BLK_MATCH), 0, nw, s_red, m_before, m_total);
   if (threadIdx.x == 0) {
     int M = c.seg_world > 1 ? c.sc[BH_SC_X_MATCH] : m_total;
     if (M > c.match_capacity) {
@@ -270,7 +270,6 @@ __device__ void ph_select_b(const bh_ctx& c, int b, int nb, bool want = true) {
 // of recyclable segments (fewer than `matching threshold` synapses, :80).
 // ---------------------------------------------------------------------------------
 __device__ void ph_learn_select_a(const bh_ctx& c, int learning, int b, int nb) {
-  __shared__ int s_red[32];
   const int NT = blockDim.x;
   const int M = c.sc[BH_SC_M];
   const Range rg = block_range(M, b, nb);
@@ -637,7 +636,7 @@ __device__ void ph_post(const bh_ctx& c, int b, int nb) {
 // (projections.py:175-178), connected-active = those with permanence >= threshold
 // (:167-173).
 // ---------------------------------------------------------------------------------
-#define ACT_BATCH 4  // segments per warp iteration, 64 slots each: 16 independent loads in flight per lane
+#define ACT_BATCH 5  // segments per warp iteration, 64 slots each: 20 independent loads in flight per lane
 __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
   __shared__ int s_red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -719,14 +718,15 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
 // `ready`: draw #3 was not run as a phase (fused.cuh); its count is the clamped list length.
 // `want_jitter` = return_winner_cell (networks.py:121): without it the jitter (and its draw) is left
 // to a later step (ph_fill_jitter); this phase then also publishes M.
-__device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false, bool want_jitter = true) {
+__device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false, bool want_jitter = true,
+                              int pre_before = -1, int pre_total = -1) {
   __shared__ int s_red[32];
   const int NT = blockDim.x;
   const int S = c.sc[BH_SC_NSEG];
   const int thr = c.seg_matching_threshold;
   const long long off3 = c.rng64[R_OFF3];
-  int m_before, m_total;
-  blk_prefix(BLK(c, BLK_MATCH), b, nb, s_red, m_before, m_total);
+  int m_before = pre_before, m_total = pre_total;
+  if (pre_total < 0) blk_prefix(BLK(c, BLK_MATCH), b, nb, s_red, m_before, m_total);  // else: the caller did
   const long long n3 = ready ? (m_total < c.match_capacity ? m_total : c.match_capacity) : c.rng64[R_N3];
   const Range rg = block_range(S, b, nb);
   int base = m_before;
