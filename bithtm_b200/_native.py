@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BITHTM_B200_LIB") or os.path.join(_HERE, "_lib", "libbithtm_b200.so")  # env: A/B builds
 
 MT_N = 624
-ABI_VERSION = 6
+ABI_VERSION = 7
 R_COUNT = 16  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)
@@ -114,6 +114,7 @@ _SIGNATURES = {
     "bh_sp_build_mask": (C.c_int, [_CTXP, _P]),
     "bh_pack_input": (C.c_int, [_CTXP, _P, _P, _P]),
     "bh_sp_overlap": (C.c_int, [_CTXP, _P, _P]),
+    "bh_sp_overlap_batched": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
     "bh_boost": (C.c_int, [_CTXP, _P]),
     "bh_inhibit": (C.c_int, [_CTXP, _P]),
     "bh_set_active_columns": (C.c_int, [_CTXP, _P, _P]),

@@ -201,6 +201,30 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_overlap(const __grid_constant
   ph_overlap<BOOST>(c, input, s_dyn, blockIdx.x, gridDim.x);
 }
 
+// ---------------------------------------------------------------------------------
+// (a') overlaps of many input vectors against the one connected mask: a 32 x 32 tile of
+// (input, column) pairs per CTA, mask and input words staged in shared memory 32 words at
+// a time (+1 padding: conflict-free), output coalesced along the columns.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_sp_overlap_batched(const __grid_constant__ bh_ctx c, const uint32_t* __restrict__ inputs,
+                                                            int n_inputs, int32_t* __restrict__ out) {
+  __shared__ uint32_t s_m[32][33], s_x[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // tx: column in tile, ty: input in tile
+  const int col0 = blockIdx.x * 32, in0 = blockIdx.y * 32;
+  int acc = 0;
+  for (int w0 = 0; w0 < c.input_words; w0 += 32) {
+    const int w = w0 + tx;
+    const int col = col0 + ty, inp = in0 + ty;
+    s_m[ty][tx] = (col < c.col_local && w < c.input_words) ? c.sp_mask[(long long)col * c.mask_stride + w] : 0u;
+    s_x[ty][tx] = (inp < n_inputs && w < c.input_words) ? inputs[(long long)inp * c.input_words + w] : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += __popc(s_m[tx][j] & s_x[ty][j]);
+    __syncthreads();
+  }
+  if (col0 + tx < c.col_local && in0 + ty < n_inputs) out[(long long)(in0 + ty) * c.col_local + col0 + tx] = acc;
+}
+
 __global__ void k_boost(const __grid_constant__ bh_ctx c) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= c.col_local) return;

@@ -97,6 +97,30 @@ class DenseProjection:
         nat.check(nat.lib.bh_sp_overlap(eng.ref, words.data_ptr(), eng.stream), "bh_sp_overlap")
         return eng.buf["overlaps"].cpu().numpy().astype(np.int64)
 
+    def process_batch(self, input_activations):
+        """Extension: ``process`` (projections.py:18-21) for a batch of inputs [B, input_dim] against
+        this one projection -> int64 overlaps [B, output_dim] (a CUDA tensor in, a CUDA tensor out
+        when given one).  Column-sharded: this rank's columns."""
+        import torch
+
+        eng = self._need_engine()
+        is_cuda = isinstance(input_activations, torch.Tensor) and input_activations.is_cuda
+        x = input_activations if is_cuda else torch.from_numpy(np.ascontiguousarray(input_activations)).to(eng.device)
+        x = x.reshape(-1, self.input_dim).to(torch.bool)
+        B, words = x.shape[0], eng.ctx.input_words
+        pad = words * 32 - self.input_dim
+        if pad:
+            x = torch.cat([x, torch.zeros(B, pad, dtype=torch.bool, device=eng.device)], dim=1)
+        # pack 32 bools per word, bit i of word i // 32 (little-endian bit order, as everywhere)
+        weights = (1 << torch.arange(32, device=eng.device, dtype=torch.int64))
+        packed = (x.view(B, words, 32).to(torch.int64) * weights).sum(dim=2)
+        packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32).contiguous()
+        out = torch.empty(B, eng.C_local, dtype=torch.int32, device=eng.device)
+        nat.check(nat.lib.bh_sp_overlap_batched(eng.ref, packed.data_ptr(), B, out.data_ptr(), eng.stream),
+                  "bh_sp_overlap_batched")
+        out = out.to(torch.int64)
+        return out if is_cuda else out.cpu().numpy()
+
     def update(self, input_activation, learning_output):
         """projections.py:23-24."""
         eng = self._need_engine()

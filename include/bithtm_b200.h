@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 6
+#define BH_ABI_VERSION 7
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 81920
@@ -229,6 +229,13 @@ int bh_sp_build_mask(const bh_ctx* ctx, void* stream);
 int bh_pack_input(const bh_ctx* ctx, const uint8_t* bool_dev, uint32_t* words_dev, void* stream);
 /* DenseProjection.process (projections.py:18-21) -> ctx->overlaps */
 int bh_sp_overlap(const bh_ctx* ctx, const uint32_t* input_words_dev, void* stream);
+/* DenseProjection.process for n_inputs input vectors against the ONE connected mask of this
+ * network (a loop of projections.py:18-21 over inputs that share the projection, e.g. inference
+ * over many streams with SP learning off): inputs_dev [n_inputs][input_words] packed words,
+ * overlaps_out [n_inputs][col_local] int32.  Bit-packed AND + popcount; the result write
+ * (4 * n_inputs * C bytes) bounds it, which is why no tensor-core contraction is used. */
+int bh_sp_overlap_batched(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
+                          void* stream);
 /* ExponentialBoosting.process (regularizations.py:15-17) -> ctx->boosted */
 int bh_boost(const bh_ctx* ctx, void* stream);
 /* GlobalInhibition.process (regularizations.py:28-29) with the canonical rule

@@ -543,3 +543,25 @@ def test_capacity_overflow_raises():
     with pytest.raises(nat.NativeError, match="max_synapses_per_segment"):
         for t in range(1500):
             htm.process(xs[t % 200])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("I,C,B", [(1024, 2048, 300), (200, 300, 33), (4100, 512, 64)])
+def test_batched_overlap_equals_loop_of_process(I, C, B):
+    """DenseProjection.process_batch == a loop of DenseProjection.process (projections.py:18-21)
+    == the dense float64 comparison of the oracle."""
+    import bithtm_b200 as bithtm
+
+    np.random.seed(9)
+    proj = bithtm.projections.DenseProjection(I, C)
+    perm = proj.permanence.copy()
+    sp = bithtm.SpatialPooler(I, C, max(1, round(0.02 * C)), proximal_projection=proj)
+    sp._ensure_engine()
+    g = np.random.default_rng(2)
+    xs = g.random((B, I)) < 0.3
+    got = proj.process_batch(xs)
+    want = ((perm >= 0.0)[None, :, :] & xs[:, None, :]).sum(axis=2) if B * C * I < 3e8 else None
+    if want is None:
+        want = np.stack([((perm >= 0.0) & x).sum(axis=1) for x in xs])
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+    assert np.array_equal(proj.process(xs[5]), want[5])
