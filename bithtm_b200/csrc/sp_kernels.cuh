@@ -118,40 +118,45 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
     return __popc(m.x & x.x) + __popc(m.y & x.y) + __popc(m.z & x.z) + __popc(m.w & x.w);
   };
   const int stride_rows = n_warps * rows_per_warp;
-  if (vec_per_row == 4 * group) {
-    // every lane owns exactly four 16-byte vectors of a row (HBM-bound sizes): software pipeline --
-    // the next row's four loads are issued before the current row is reduced, so a warp always has
-    // loads in flight
-    int base = warp_global * rows_per_warp;
-    int row = base + lane / group;
-    uint4 cur[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) cur[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < n_rows) {
-      const uint4* mrow = mask4 + (long long)row * vec_per_row + sub;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = mrow[j * group];
-    }
+  if (vec_per_row == 4 * group && group == 32) {
+    // Long rows (HBM-bound sizes): every lane owns exactly four 16-byte vectors of a row.  A warp takes
+    // R consecutive rows at a time: the next row's four loads are issued before the current row is
+    // reduced (software pipeline), and the per-row epilogue (exp, boost, stores, key range) runs once
+    // per R rows with lane i finishing row i instead of once per row on a single lane.
+    int R = 1;
+    while (R < 32 && (long long)2 * R * n_warps <= n_rows) R *= 2;
+    const int n_groups = (n_rows + R - 1) / R;
 #pragma unroll 1
-    while (base < n_rows) {
-      const int nbase = base + stride_rows, nrow = nbase + lane / group;
-      uint4 nxt[4];
+    for (int g = warp_global; g < n_groups; g += n_warps) {
+      const int row0 = g * R;
+      const int rows_here = n_rows - row0 < R ? n_rows - row0 : R;
+      int my_acc = 0;
+      uint4 cur[4];
+      {
+        const uint4* mrow = mask4 + (long long)row0 * vec_per_row + lane;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) nxt[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (nrow < n_rows) {
-        const uint4* mrow = mask4 + (long long)nrow * vec_per_row + sub;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) nxt[j] = mrow[j * group];
+        for (int j = 0; j < 4; ++j) cur[j] = mrow[j * 32];
       }
-      int acc = 0;
+#pragma unroll 1
+      for (int i = 0; i < rows_here; ++i) {
+        uint4 nxt[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc += popc4(cur[j], s_in4[sub + j * group]);
-      for (int o = group >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(BH_FULL, acc, o);
-      if (sub == 0 && row < n_rows) finish(row, acc);
+        for (int j = 0; j < 4; ++j) nxt[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (i + 1 < rows_here) {
+          const uint4* mrow = mask4 + (long long)(row0 + i + 1) * vec_per_row + lane;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
-      base = nbase;
-      row = nrow;
+          for (int j = 0; j < 4; ++j) nxt[j] = mrow[j * 32];
+        }
+        int acc = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc += popc4(cur[j], s_in4[lane + j * 32]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(BH_FULL, acc, o);
+        if (lane == i) my_acc = acc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      }
+      if (lane < rows_here) finish(row0 + lane, my_acc);
     }
   } else {
 #pragma unroll 1
