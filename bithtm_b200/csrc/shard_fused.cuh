@@ -52,13 +52,17 @@ __device__ void xch_exchange(const bh_ctx& c, int kind, const int* send, long lo
 #pragma unroll 1
     for (long long i = gid; i < n4; i += gsz) dst[i] = src[i];
   }
-  __threadfence_system();
+  // one system-scope fence per CTA (its threads' stores are ordered before it by the block barrier), one
+  // grid barrier, then the sequence numbers; every CTA polls the local flags itself (no second barrier)
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
   grid_barrier(bar, nb);
   if (b == 0 && threadIdx.x < G) {
-    const int s = threadIdx.x;
-    int* peer_flag = c.xpeer[s] + kind * 8 + me;
+    int* peer_flag = c.xpeer[threadIdx.x] + kind * 8 + me;
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flag), "r"(seq) : "memory");
-    const int* my_flag = c.xpeer[me] + kind * 8 + s;
+  }
+  if (threadIdx.x < G) {
+    const int* my_flag = c.xpeer[me] + kind * 8 + threadIdx.x;
     const long long t0 = clock64();
     int v;
     do {
@@ -69,7 +73,7 @@ __device__ void xch_exchange(const bh_ctx& c, int kind, const int* send, long lo
       }
     } while (v < seq);
   }
-  grid_barrier(bar, nb);
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
@@ -81,6 +85,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
   const bool rng = b == nb - 1;
   unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
 #define BH_SYNC() grid_barrier(bar, (unsigned)nb)
+  // phase timestamps of the last step (CTA 0): ctx.blk row 7, as 64-bit globaltimer ns (tools/cfg3_sharded.py)
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE);
+  int stamp_i = 0;
+#define BH_STAMP()                                                            \
+  do {                                                                        \
+    if (b == 0 && threadIdx.x == 0) {                                         \
+      unsigned long long t_;                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                  \
+      stamps[stamp_i] = t_;                                                   \
+    }                                                                         \
+    ++stamp_i;                                                                \
+  } while (0)
   const int G = c.seg_world, me = c.seg_rank;
   const int k = c.active_columns, k_loc = xch_k_loc(c);
   const long long n1 = xch_n1(c), n4 = xch_n4(c);
@@ -91,11 +107,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     const uint32_t* input =
         input_fixed ? input_fixed : c.input_ring + (long long)((pos0 + step) % c.ring_len) * c.input_words;
     const int par = c.sc[BH_SC_STEP] & 1;
+    stamp_i = 0;
+    BH_STAMP();
     // P0: overlap + boost of the local columns; draw #1 on the rng CTA
     if (rng) ph_draw(c, 1, 1, nw);
     if (nb == 1) ph_overlap<true>(c, input, s_dyn, 0, 1);
     else if (!rng) ph_overlap<true>(c, input, s_dyn, b, nb - 1);
     BH_SYNC();
+    BH_STAMP();  // 1: overlap
     // P1: this shard's best k_loc candidates -> record -> exchange 1 -> global top-k on every rank
     int* scratch = reinterpret_cast<int*>(c.row_unacc);  // not in use yet this step
     if (c.col_local >= 16384) {
@@ -105,6 +124,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       topk_core(reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr);
     }
     BH_SYNC();
+    BH_STAMP();  // 2: local top-k
     {
       double* rk = reinterpret_cast<double*>(c.x_send);
       int* rc = c.x_send + 2 * k_loc;
@@ -116,7 +136,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       }
     }
     BH_SYNC();
+    BH_STAMP();  // 3: record
     xch_exchange(c, 0, c.x_send, n1, b, nb, bar);
+    BH_STAMP();  // 3: exchange 1
     {
       const int* recv = region + xch_recv_off(c, 0, par);
 #pragma unroll 1
@@ -140,35 +162,45 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     }
     if (rng && nb > 1) ph_rng_speculate(c, 1);
     BH_SYNC();
+    BH_STAMP();  // 4: unpack + global top-k
     // P2..P7 as in fused.cuh; learning and the segment scan touch only what this rank stores
     if (learning) ph_sp_learn<false>(c, input, b, nb);
     ph_duty(c, b, nb);
     if (worker) ph_select_a(c, b, nw);
     BH_SYNC();
+    BH_STAMP();  // 5: SP learn + duty + winner bits
     if (worker) {
       ph_select_b(c, b, nw);
       ph_learn_select_a(c, learning, b, nw);
     }
     BH_SYNC();
+    BH_STAMP();  // 6: lists + learning flags
     if (rng) ph_draw(c, 2, learning, nw);
     if (worker) ph_learn_select_b(c, learning, b, nw);
     BH_SYNC();
+    BH_STAMP();  // 7: learning lists + draw 2
     if (c.jump_polys > 0) {
       ph_rng_chunks(c, s_dyn, b, nb);
       BH_SYNC();
     }
+    BH_STAMP();  // 8: stream chunks
     if (learning) ph_learn_apply(c, s_dyn, b, nb);
     BH_SYNC();
     ph_post(c, b, nb);
     BH_SYNC();
+    BH_STAMP();  // 9: learn + post
     if (worker) ph_activate_a(c, b, nw);
     BH_SYNC();
+    BH_STAMP();  // 10: segment scan
     // P8: this rank's record of matching / recyclable segments -> exchange 2 -> merged global lists
     if (worker) ph_shard_pack(c, c.x_send, b, nw);
     BH_SYNC();
+    BH_STAMP();  // 11: record
     xch_exchange(c, 1, c.x_send, n4, b, nb, bar);
+    BH_STAMP();  // 12: exchange 2
     ph_shard_merge(c, region + xch_recv_off(c, 1, par), b, nb, (int)n4);
     BH_SYNC();
+    BH_STAMP();  // 13: merge
     // P9: draw #3 (a phase of its own only when not covered, see fused.cuh), jitter, predictions
     const int M = c.sc[BH_SC_X_MATCH] < c.match_capacity ? c.sc[BH_SC_X_MATCH] : c.match_capacity;
     const bool ready3 = (long long)M <= c.rng64[R_READY3];
@@ -180,8 +212,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     }
     if (worker) ph_activate_finish(c, b, nw, ready3);
     BH_SYNC();
+    BH_STAMP();  // 14: draw 3 + jitter + predictions
   }
   if (want_summary) ph_summary(c, b, nb);
   if (!input_fixed && b == 0 && threadIdx.x == 0) c.sc[BH_SC_INPUT_POS] = pos0 + n_steps;
 #undef BH_SYNC
+#undef BH_STAMP
 }

@@ -14,10 +14,11 @@
 #define TK2_VALID 4        // 1 when u64[0] = max key, u64[1] = ~min key were published by ph_overlap<true>
 #define TK2_CALL 5         // call counter: parity selects one of two histogram / candidate buffers
 #define TK2_PAR0 16
-#define TK2_PSIZE 3344     // per parity: ghist[256], count (+7 pad), cand_idx[1024], cand_key u64[1024]
-#define TK2_TAB (TK2_PAR0 + 2 * TK2_PSIZE)  // [256 CTAs][256]: keys of a CTA's range with a larger digit
+#define TK2_BINS 2048      // 11-bit digit below the keys' common prefix
+#define TK2_PSIZE 5136     // per parity: ghist[2048], count (+7 pad), cand_idx[1024], cand_key u64[1024]
+#define TK2_TAB (TK2_PAR0 + 2 * TK2_PSIZE)  // [256 CTAs]: keys of a CTA's range in bins above the k-th key's
 #define TK2_MAX_CTAS 256
-#define TK2_INTS (TK2_TAB + TK2_MAX_CTAS * 256)
+#define TK2_INTS (TK2_TAB + TK2_MAX_CTAS)
 
 __device__ __noinline__ unsigned long long block_reduce_u64(unsigned long long v, bool want_max,
                                                                unsigned long long* sm) {
@@ -833,7 +834,7 @@ __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long
   __shared__ unsigned long long s_kth_key;
   int* ws = c.topk_ws + TK2_BASE;
   unsigned long long* w64 = reinterpret_cast<unsigned long long*>(ws);
-  const int t = threadIdx.x, lane = t & 31, NT = blockDim.x;
+  const int t = threadIdx.x, NT = blockDim.x;
   const Range rg = block_range(n, b, nb);
   const bool valid = ws[TK2_VALID] != 0;
   const int par = ws[TK2_CALL] & 1;
@@ -875,78 +876,56 @@ __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long
   }
   const unsigned long long mx = w64[0], mn = ~w64[1];
   const int consumed = (mn == mx) ? 64 : __clzll((long long)(mn ^ mx));
-  const int shift = (64 - consumed - 8) > 0 ? (64 - consumed - 8) : 0;
+  const int shift = (64 - consumed - 11) > 0 ? (64 - consumed - 11) : 0;
   const int width = 64 - consumed - shift;
   const unsigned dmask = (1u << width) - 1u;
   int* ghist = ws + TK2_PAR0 + par * TK2_PSIZE;
-  int* gcount = ghist + 256;
-  int* gidx = ghist + 264;
-  unsigned long long* gkey = reinterpret_cast<unsigned long long*>(ghist + 264 + TOPK_THREADS);
+  int* gcount = ghist + TK2_BINS;
+  int* gidx = ghist + TK2_BINS + 8;
+  unsigned long long* gkey = reinterpret_cast<unsigned long long*>(ghist + TK2_BINS + 8 + TOPK_THREADS);
   int* tab = ws + TK2_TAB;
   const bool degenerate = consumed == 64;  // all keys equal (uniform over the grid)
 
-  // stage 1: local histogram -> global histogram + this CTA's "keys in higher bins" table
+  // stage 1: local histogram (kept in shared memory for stage 2) -> global histogram
   if (!degenerate) {
 #pragma unroll 1
-    for (int i = t; i < 256; i += NT) hist[i] = 0;
+    for (int i = t; i < TK2_BINS; i += NT) hist[i] = 0;
     __syncthreads();
 #pragma unroll 1
-    for (int base = rg.begin; base < rg.end; base += NT) {
-      const int j = base + t;
-      const bool in = j < rg.end;
-      const int d = in ? (int)((keys[j] >> shift) & dmask) : -1;
-      const unsigned peers = __match_any_sync(BH_FULL, d);
-      if (in && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], __popc(peers));
-    }
+    for (int j = rg.begin + t; j < rg.end; j += NT) atomicAdd(&hist[(int)((keys[j] >> shift) & dmask)], 1);
     __syncthreads();
-    if (t < 256) {  // global histogram; suffix sums of the local one (8 warps: shuffle scan + warp totals)
-      const int h = hist[t];
-      if (h) atomicAdd(&ghist[t], h);
-      int incl = h;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_down_sync(BH_FULL, incl, o);
-        if (lane + o < 32) incl += v;
-      }
-      if (lane == 0) s_scan[t >> 5] = incl;  // total of bins [32w, 32w + 32)
-      hist[t] = incl - h;                    // bins of the same warp above t
-    }
-    __syncthreads();
-    if (t < 256) {
-      int above = hist[t];
-      for (int w = (t >> 5) + 1; w < 8; ++w) above += s_scan[w];
-      tab[b * 256 + t] = above;
+#pragma unroll 1
+    for (int i = t; i < TK2_BINS; i += NT) {
+      const int h = hist[i];
+      if (h) atomicAdd(&ghist[i], h);
     }
   }
   TK_STAMP();
   grid_barrier(bar, nb);
   TK_STAMP();
-  // stage 2: the bin of the k-th key (every CTA, from the same global histogram); gather its members
-  if (!degenerate && t < 32) {
-    int local[8], sum = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      local[i] = ghist[255 - (lane * 8 + i)];
-      sum += local[i];
+  // stage 2: the bin of the k-th key (every CTA, from the same global histogram: bins in descending
+  // order, an ordered block scan); this CTA's keys in higher bins; gather the bin's members
+  if (!degenerate) {
+    const int per = (TK2_BINS + NT - 1) / NT;
+    int sum = 0;
+    for (int i = 0; i < per; ++i) {
+      const int bin = TK2_BINS - 1 - (t * per + i);
+      sum += bin >= 0 ? ghist[bin] : 0;
     }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(BH_FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int before = incl - sum;
-    if (before < k && incl >= k) {
+    int total;
+    const int before = block_excl_scan(sum, s_scan, total);
+    if (before < k && before + sum >= k) {
       int r = k - before;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (r > 0 && local[i] >= r) {
-          s_bin = 255 - (lane * 8 + i);
+      for (int i = 0; i < per; ++i) {
+        const int bin = TK2_BINS - 1 - (t * per + i);
+        const int h = bin >= 0 ? ghist[bin] : 0;
+        if (r > 0 && h >= r) {
+          s_bin = bin;
           s_rem = r;
-          s_ncand = local[i];
+          s_ncand = h;
           r = -1;
         } else if (r > 0) {
-          r -= local[i];
+          r -= h;
         }
       }
     }
@@ -955,6 +934,11 @@ __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long
   const bool fallback = degenerate || s_ncand > TOPK_THREADS;  // uniform over the grid
   const int bin = s_bin, rem = s_rem;
   if (!fallback) {
+    int above = 0;  // this CTA's keys in bins above `bin` (its local histogram is still in shared memory)
+#pragma unroll 1
+    for (int i = bin + 1 + t; i < TK2_BINS; i += NT) above += hist[i];
+    above = block_sum(above, s_scan);
+    if (t == 0) tab[b] = above;
 #pragma unroll 1
     for (int j = rg.begin + t; j < rg.end; j += NT) {
       const unsigned long long key = keys[j];
@@ -971,7 +955,7 @@ __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long
   if (b == 0) {  // leave the OTHER buffer and the key range clean for the next call; advance the parity
     int* oh = ws + TK2_PAR0 + (par ^ 1) * TK2_PSIZE;
 #pragma unroll 1
-    for (int i = t; i < 264; i += NT) oh[i] = 0;
+    for (int i = t; i < TK2_BINS + 8; i += NT) oh[i] = 0;
     if (t == 0) {
       w64[0] = 0ull;
       w64[1] = 0ull;
@@ -1016,7 +1000,7 @@ __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long
     before = (mi < rg.begin && (mk > kth_key || (mk == kth_key && mi <= kth_idx))) ? 1 : 0;
   }
 #pragma unroll 1
-  for (int i = t; i < b; i += NT) before += tab[i * 256 + bin];  // keys of earlier ranges in higher bins
+  for (int i = t; i < b; i += NT) before += tab[i];  // keys of earlier ranges in higher bins
   int base_sel = block_sum(before, s_scan);
 #pragma unroll 1
   for (int tile = rg.begin; tile < rg.end; tile += NT) {

@@ -78,11 +78,25 @@ def measure(steps=300, C=65536, I=16384, mode="fused", verbose=False):
             print(f"step {t0 + chunk}: {times[-1]:.3f} ms/step  S={sc[2]} M={sc[4]} L={sc[8]} status={sc[12]}",
                   flush=True)
     eng.check_status()
+    phases = None
+    if mode == "fused":
+        names = ["overlap", "local top-k", "candidate record", "exchange 1", "unpack + global top-k", "SP learn + winner bits",
+                 "lists + learning flags", "learning lists + draw 2", "stream chunks", "learn + post", "segment scan",
+                 "record", "exchange 2", "merge", "draw 3 + jitter + predictions"]
+        st = eng.buf["blk"][7 * 1024:7 * 1024 + 2 * (len(names) + 1)].cpu().numpy().view(np.uint64).astype(np.float64)
+        phases = {n: round(float(v) / 1e3, 2) for n, v in zip(names, np.diff(st))}
+        if verbose and rank == 0:
+            for n, v in phases.items():
+                print(f"  {n:32s} {v:8.2f} us")
+            if os.environ.get("BH_TOPK_STAMPS"):  # library built with -DBH_TOPK_STAMPS
+                tk = eng.buf["blk"][7 * 1024 + 80:7 * 1024 + 80 + 32].cpu().numpy().view(np.uint64)
+                print("  topk_grid stages of the LAST call (ns):", np.diff(tk[:7].astype(np.int64)).tolist(),
+                      "candidates", int(tk[15] & 0xffffffff), "range published", int(tk[15] >> 32))
     out = {"workload": f"cfg3 as ONE network: {C} columns x {I} inputs, k={k}, sharded over {world} GPU(s)",
            "n_gpus": world, "ms_per_step": times[-1], "steps_per_s": 1e3 / times[-1], "mode": mode,
            "exchanges_per_step": 2 if world > 1 else 0,
            "transport": getattr(htm, "exchange_transport", "local") if mode == "fused" else "NCCL all-gather",
-           "steps": steps}
+           "steps": steps, "phase_us_rank0_last_step": phases}
     del htm, eng, sp
     torch.cuda.empty_cache()
     return out
