@@ -20,6 +20,10 @@
 #include "tm_shard.cuh"
 
 #define XCH_FLAG_INTS 16
+// from this many keys the grid-wide selection (two grid barriers) beats one CTA -- much earlier than in the
+// unsharded kernels, because a shard selects min(k, C/G) of only C/G keys and the merge k of G*min(k, C/G):
+// large fractions, for which the single-CTA radix select degenerates
+#define XCH_TOPK_GRID_MIN 4096
 #define XCH_TIMEOUT_CYCLES 6000000000LL  // ~3 s at 2 GHz: a peer that never answers sets BH_ST_XCH_TIMEOUT
 
 __host__ __device__ __forceinline__ int xch_k_loc(const bh_ctx& c) {
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_STAMP();  // 1: overlap
     // P1: this shard's best k_loc candidates -> record -> exchange 1 -> global top-k on every rank
     int* scratch = reinterpret_cast<int*>(c.row_unacc);  // not in use yet this step
-    if (c.col_local >= 16384) {
+    if (c.col_local >= XCH_TOPK_GRID_MIN) {
       topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
                 b, nb, bar);
     } else if (b == 0) {
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       }
     }
     BH_SYNC();
-    if ((long long)G * k_loc >= 16384) {
+    if ((long long)G * k_loc >= XCH_TOPK_GRID_MIN) {
       if (b == 0) retire_prev_flags(c);
       topk_grid(c, reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k,
                 c.active_cols + par * k, c.xk_cols, c.col_active, b, nb, bar);
