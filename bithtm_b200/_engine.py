@@ -165,6 +165,7 @@ class Engine:
         ctx.summary_pinned = self.summary_pinned.data_ptr()
         self._summary_np = self.summary_pinned.numpy()
         self._summary_out = np.zeros(nat.summary_ints(k), dtype=np.int32)
+        self._summary_out_ptr = self._summary_out.ctypes.data  # (ndarray.ctypes builds an object per access)
         if ctx.jump_polys:
             tab = _mtjump.jump_table(ctx.jump_polys, cache_dir=os.path.dirname(nat.LIB_PATH))
             self.buf["mt_jump"].copy_(torch.from_numpy(tab.view(np.int32).reshape(-1)).to(self.device))
@@ -321,7 +322,9 @@ class Engine:
         self.epoch += 1
 
     def step_host(self, x_bool: np.ndarray, learning=True) -> np.ndarray:
-        xb = np.ascontiguousarray(x_bool, dtype=np.uint8)
+        xb = x_bool
+        if not (isinstance(xb, np.ndarray) and xb.dtype == np.bool_ and xb.flags.c_contiguous):
+            xb = np.ascontiguousarray(x_bool, dtype=np.bool_)  # one byte per bit, 0/1: what bh_step_host reads
         if xb.size != self.I:
             raise ValueError(f"input has {xb.size} bits, expected {self.I}")
         learning = bool(learning)
@@ -339,11 +342,11 @@ class Engine:
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graphs[key] = handle
         if handle is not None:
-            nat.check(nat.lib.bh_step_host_graph(self.ref, handle, xb.ctypes.data, self._summary_out.ctypes.data,
-                                                 self.stream), "bh_step_host_graph")
+            nat.check(nat.lib.bh_step_host_graph(self.ref, handle, xb.__array_interface__["data"][0],
+                                                 self._summary_out_ptr, self.stream), "bh_step_host_graph")
         else:
-            nat.check(nat.lib.bh_step_host(self.ref, xb.ctypes.data, int(learning),
-                                           self._summary_out.ctypes.data, self.stream), "bh_step_host")
+            nat.check(nat.lib.bh_step_host(self.ref, xb.__array_interface__["data"][0], int(learning),
+                                           self._summary_out_ptr, self.stream), "bh_step_host")
         self.epoch += 1
         return self._summary_out
 

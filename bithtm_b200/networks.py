@@ -47,15 +47,17 @@ class _RngLink:
         self._live_key = np.ctypeslib.as_array((ctypes.c_uint32 * nat.MT_N).from_address(addr))
         self._live_pos = ctypes.c_int.from_address(addr + 4 * nat.MT_N)
         self._key = np.zeros(nat.MT_N, dtype=np.uint32)  # what the device continues from
+        self._key_bytes = b""
         self._pos = -1
 
     def before(self, eng):
         if self.mode == "lazy" and self._seeded:
             return
         pos = self._live_pos.value
-        if self._seeded and pos == self._pos and np.array_equal(self._live_key, self._key):
+        if self._seeded and pos == self._pos and self._live_key.tobytes() == self._key_bytes:
             return  # nobody drew from np.random since our last write-back
         self._key[:] = self._live_key
+        self._key_bytes = self._key.tobytes()
         self._pos = pos
         eng.set_rng_state(self._key, pos)
         self._seeded = True
@@ -64,6 +66,7 @@ class _RngLink:
         """Continue the device stream from an explicit ``np.random.get_state()`` tuple."""
         key, pos = np.asarray(state[1], dtype=np.uint32), int(state[2])
         self._key[:] = key
+        self._key_bytes = self._key.tobytes()
         self._pos = pos
         eng.set_rng_state(self._key, pos)
         self._seeded = True
@@ -77,16 +80,16 @@ class _RngLink:
             k = eng.k
             tail = summary[4 + 4 * k:4 + 4 * k + nat.MT_N + 1]
             key, pos = tail[:nat.MT_N].view(np.uint32), int(tail[nat.MT_N])
-        self._key[:] = key
-        self._pos = pos
         self._live_key[:] = key
+        self._key_bytes = self._live_key.tobytes()
+        self._pos = pos
         self._live_pos.value = pos
 
     def sync(self, eng):
         key, pos = eng.get_rng_state()
-        self._key[:] = key
-        self._pos = pos
         self._live_key[:] = key
+        self._key_bytes = self._live_key.tobytes()
+        self._pos = pos
         self._live_pos.value = pos
 
 
@@ -236,15 +239,33 @@ class TemporalMemory:
         def __init__(self, engine, projection, summary, have_winner=True, have_jitter=True):
             super().__init__(engine)
             k, c = engine.k, engine.c
-            s = summary
-            self._c, self._C = c, engine.C
-            self._active_column = s[4:4 + k].astype(np.int64)
-            self._row_pred = s[4 + k:4 + 2 * k].view(np.uint32).copy()
-            self._row_act = s[4 + 2 * k:4 + 3 * k].view(np.uint32).copy()
-            self._row_win = s[4 + 3 * k:4 + 4 * k].view(np.uint32).copy()
+            self._c, self._C, self._k = c, engine.C, k
+            self._head = summary[:4 + 4 * k].copy()  # the summary buffer is reused by the next step
             self._have_winner = have_winner
-            self.n_segments = int(s[2])
+            self.n_segments = int(self._head[2])
             self.distal_state = PredictiveProjection.State(engine, projection, have_jitter)
+
+        @property
+        def _active_column(self):  # host data (the copied summary): readable at any time
+            a = self._cache.get("_active_column")
+            if a is None:
+                a = self._cache["_active_column"] = self._head[4:4 + self._k].astype(np.int64)
+            return a
+
+        def _words(self, i):  # row_pred / row_act / row_win of the summary
+            return self._head[4 + i * self._k:4 + (i + 1) * self._k].view(np.uint32)
+
+        @property
+        def _row_pred(self):
+            return self._words(1)
+
+        @property
+        def _row_act(self):
+            return self._words(2)
+
+        @property
+        def _row_win(self):
+            return self._words(3)
 
         def _cells(self, words):
             rows, cells = np.nonzero(_bits(words, self._c))
