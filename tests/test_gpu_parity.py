@@ -565,3 +565,63 @@ def test_batched_overlap_equals_loop_of_process(I, C, B):
         want = np.stack([((perm >= 0.0) & x).sum(axis=1) for x in xs])
     assert got.dtype == np.int64 and np.array_equal(got, want)
     assert np.array_equal(proj.process(xs[5]), want[5])
+
+
+@pytest.mark.gpu
+def test_cfg3_full_size_execution_modes_agree():
+    """BASELINE configs[2] at its full size (65536 columns x 16384 inputs, 32 cells, k = 1311):
+    no oracle run is possible, so the size-independent property is that the
+    execution modes -- the whole step as one cooperative kernel with many-CTA stream
+    production and the two-barrier top-k, and one kernel per stage -- leave bit-identical
+    state on the device (permanence, masks, duty cycles, segments, synapses, RNG stream)."""
+    import torch
+
+    import bithtm_b200 as bithtm
+    from bithtm_b200.projections import DenseProjection
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~24 GiB of device memory")
+    I, C, c, k, steps = 16384, 65536, 32, 1311, 40
+    g = np.random.default_rng(8)
+    base = g.random((10, I)) < 0.2
+    xs = base[np.arange(steps) % 10] ^ (g.random((steps, I)) < 0.05)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    perm = torch.randn(C, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
+
+    def run(fused):
+        np.random.seed(12)
+        sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
+        htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy", fused=fused,
+                                                max_segments=1 << 17, max_synapses_per_segment=128)
+        eng = htm.engine
+        htm.temporal_memory._rng.before(eng)
+        for t in range(steps):
+            htm.process(eng.pack_input(xs[t]), return_state=False)
+        torch.cuda.synchronize()
+        eng.check_status()
+        return htm
+
+    a = run("grid")
+    b = run("off")
+    ea, eb = a.engine, b.engine
+    assert ea.ctx.jump_polys > 0 and ea.ctx.fused_mode == 2 and eb.ctx.fused_mode == 0
+    S = int(ea.scalars()[2])
+    assert S == int(eb.scalars()[2]) and S > 20000
+    for name in ("sp_perm", "sp_mask", "duty", "overlaps", "boosted", "col_pred", "col_act", "col_win", "cell_nseg",
+                 "cell_maxjit", "cell_npred"):
+        assert torch.equal(ea.buf[name], eb.buf[name]), name
+    for name in ("seg_owner", "seg_count", "seg_pot", "seg_conn"):
+        assert torch.equal(ea.buf[name][:S], eb.buf[name][:S]), name
+    E = ea.ctx.syn_capacity
+    live = torch.arange(E, device="cuda")[None, :] < ea.buf["seg_count"][:S, None]
+    for name in ("syn_cell", "syn_perm"):
+        x, y = ea.buf[name][:S * E].view(S, E), eb.buf[name][:S * E].view(S, E)
+        assert torch.equal(torch.where(live, x, torch.zeros_like(x)), torch.where(live, y, torch.zeros_like(y))), name
+    ka, pa = ea.get_rng_state()
+    kb, pb = eb.get_rng_state()
+    ra, rb = np.random.RandomState(), np.random.RandomState()
+    ra.set_state(("MT19937", ka, pa, 0, 0.0))
+    rb.set_state(("MT19937", kb, pb, 0, 0.0))
+    assert np.array_equal(ra.random_sample(1000), rb.random_sample(1000))
