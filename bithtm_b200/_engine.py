@@ -125,6 +125,11 @@ class Engine:
         ring_words = 1 << 20
         while ring_words < need:
             ring_words <<= 1
+        if ring_words > (1 << 31):
+            raise NotImplementedError(
+                f"{k} active columns draw about {typical // 2:,} random numbers per timestep (rand(L, W+1), "
+                "projections.py:120, is quadratic in the number of active columns); the device stream ring is limited "
+                "to 2^31 words. Pass rand_capacity= to bound the draws per step explicitly (see DESIGN.md, cfg5).")
         ctx.rng_ring_words, ctx.rng_step_words, ctx.ring_len = ring_words, step_words, int(ring_len)
         ctx.jump_polys = (step_words + step_words // 2) // _mtjump.CHUNK_WORDS + 3 if parallel_rng else 0
         ctx.rng_lookahead = min(2 * (k * c + 4 * k) + 2 * nat.MT_N, step_words // 2) if parallel_rng else 0
