@@ -118,14 +118,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     ph_post(c, b, nb);
     BH_SYNC();
     BH_STAMP();
-#ifdef BH_ICACHE_EXPERIMENT
-    ph_post(c, b, nb);  // idempotent: second run with warm instruction cache
-    BH_SYNC();
-    BH_STAMP();
-    ph_post(c, b, nb);
-    BH_SYNC();
-    BH_STAMP();
-#endif
     // P7: segment potentials; the drawing CTA is idle for the whole scan: it produces the stream words of
     // the rest of this step and of the next one (the P1 / P3 calls then only top up)
     if (worker) ph_activate_a(c, b, nw);

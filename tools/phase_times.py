@@ -14,9 +14,6 @@ from bench import CFG2, make_inputs
 
 PHASES = ["P0 overlap+draw1", "P1 topk", "P2 sp_learn+duty+select_a", "P3 select_b+learn_select_a",
           "P4 learn_select_b+draw2", "P4b rng chunks", "P5 learn_apply", "P6 post", "P7 activate_a", "P8 draw3", "P9 activate_b"]
-if os.environ.get("BH_ICACHE_EXPERIMENT"):
-    PHASES[8:8] = ["P6' post again (warm I$)", "P6'' post again"]
-
 
 def main():
     fused = sys.argv[1] if len(sys.argv) > 1 else "cluster"
