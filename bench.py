@@ -288,7 +288,11 @@ def ours(args):
                 "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(dominant),
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
                 "kernel_us": {k: round(v * 1e3, 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
-                "algorithmic_bytes_per_launch": ab, "state": stats}
+                "algorithmic_bytes_per_launch": ab, "state": stats,
+                "note": ("cfg2's whole working set is ~3 MB: one step is ~2.6 MB of algorithmic traffic = 0.4 us of HBM "
+                         "time, so the step is bound by its chain of dependent phases (9 barrier-separated phases), not "
+                         "by bandwidth; the HBM-bound sizes of the same kernels are under roofline_hbm_kernels "
+                         "(cfg3: whole step and per kernel)")}
     del htm, eng
 
     # ---------------- end-to-end arm: host inputs through the reference-facing API
