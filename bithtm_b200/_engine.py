@@ -195,7 +195,7 @@ class Engine:
         self.seg_rows = rows
         return {
             "sp_perm": CL * I, "sp_mask": CL * x.mask_stride, "duty": CL, "overlaps": CL, "boosted": CL,
-            "active_cols": 2 * k, "col_active": C_, "col_pred": C_, "col_act": C_, "col_win": C_,
+            "active_cols": 2 * k, "col_active": C_, "col_pred": C_, "col_act": 2 * C_, "col_win": C_,
             "cell_nseg": N, "cell_maxjit": N, "cell_npred": N, "cell_widx": N,
             "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": rows * E, "syn_perm": rows * E,
             "row_pred": k, "row_act": k, "row_win": k, "row_unacc": k, "winners": 2 * k * c, "unacc": k * c,

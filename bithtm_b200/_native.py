@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BITHTM_B200_LIB") or os.path.join(_HERE, "_lib", "libbithtm_b200.so")  # env: A/B builds
 
 MT_N = 624
-ABI_VERSION = 7
+ABI_VERSION = 8
 R_COUNT = 16  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)

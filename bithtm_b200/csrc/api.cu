@@ -70,7 +70,7 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->active_cols, 2 * k);
   cv.take(x->col_active, C);
   cv.take(x->col_pred, C);
-  cv.take(x->col_act, C);
+  cv.take(x->col_act, 2 * C);  // ping-pong by step parity
   cv.take(x->col_win, C);
   cv.take(x->cell_nseg, N);
   cv.take(x->cell_maxjit, N);

@@ -114,12 +114,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (learning) ph_learn_apply(c, s_dyn, b, nb);
     BH_SYNC();
     BH_STAMP();
-    // P6: commit activation bit-words, winner index, segment count
-    ph_post(c, b, nb);
-    BH_SYNC();
+    // (P6, once a phase of its own -- retiring the previous activation words, the winner index, the segment
+    // count -- now runs at the head of P7: the activation words are double-buffered, so nothing it writes is
+    // read by the scan)
     BH_STAMP();
     // P7: segment potentials; the drawing CTA is idle for the whole scan: it produces the stream words of
     // the rest of this step and of the next one (the P1 / P3 calls then only top up)
+    ph_post(c, b, nb);
     if (worker) ph_activate_a(c, b, nw);
     if (rng && nb > 1) ph_rng_speculate(c, 1, true);
     BH_SYNC();

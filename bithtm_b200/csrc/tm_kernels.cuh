@@ -201,7 +201,9 @@ __device__ void ph_select_a(const bh_ctx& c, int b, int nb, bool want = true) {
     if (lane == 0) {
       c.row_pred[r] = pred;
       c.row_win[r] = wbits;
-      c.row_act[r] = burst ? low_mask(cd) : pred;  // networks.py:115
+      const uint32_t abits = burst ? low_mask(cd) : pred;  // networks.py:115
+      c.row_act[r] = abits;
+      c.col_act[(long long)cur * c.column_dim + col] = abits;  // this step's buffer is all-zero here (ph_post)
       c.row_unacc[r] = ubits;
       c.col_win[col] = wbits;
       n_win += __popc(wbits);
@@ -528,6 +530,7 @@ __device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb)
   const int cur = c.sc[BH_SC_STEP] & 1;
   const int Wp = c.sc[BH_SC_W0 + (cur ^ 1)];
   const int* prevw = c.winners + (long long)(cur ^ 1) * c.active_columns * cd;
+  const uint32_t* prev_act = c.col_act + (long long)(cur ^ 1) * c.column_dim;  // cell_activation of the previous step
   const long long off2 = c.rng64[R_OFF2];
   const long long n2 = c.rng64[R_N2];  // doubles draw #2 obtained (capacity-clamped)
   const int sample = c.seg_sampling_synapses;
@@ -556,7 +559,7 @@ __device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb)
         const bool valid = slot < n;
         const int cell = valid ? cells[slot] : 0;
         const float p = valid ? perms[slot] : 0.0f;
-        const bool act = valid && cell_bit(c.col_act, cell);          // previous activation (networks.py:111)
+        const bool act = valid && cell_bit(prev_act, cell);           // previous activation (networks.py:111)
         const double sum = __dadd_rn((double)p, act ? d_on : d_off);  // :102-103
         const bool keep = valid && !(can_delete && sum < 0.0);        // :105-108
         const uint32_t kb = __ballot_sync(BH_FULL, keep);
@@ -608,18 +611,16 @@ __global__ void __launch_bounds__(LA_THREADS) k_tm_learn_apply(const __grid_cons
 __device__ void ph_post(const bh_ctx& c, int b, int nb) {
   const int k = c.active_columns, cd = c.cell_dim;
   const int cur = c.sc[BH_SC_STEP] & 1;
-  const int* act = c.active_cols + cur * k;
   const int* prev = c.active_cols + (cur ^ 1) * k;
   const int Wc = c.sc[BH_SC_W0 + cur], Wp = c.sc[BH_SC_W0 + (cur ^ 1)];
   const int* wl_cur = c.winners + (long long)cur * k * cd;
   const int* wl_prev = c.winners + (long long)(cur ^ 1) * k * cd;
   const int gid = b * blockDim.x + threadIdx.x, gsz = nb * blockDim.x;
+  // the previous step's activation words (the OTHER buffer) have had their last reader (learning): zero
+  // them, so the next step finds its buffer empty and only sets the words of its active columns
+  uint32_t* old_act = c.col_act + (long long)(cur ^ 1) * c.column_dim;
   #pragma unroll 1
-  for (int r = gid; r < k; r += gsz) {
-    c.col_act[act[r]] = c.row_act[r];
-    int pc = prev[r];
-    if (!c.col_active[pc]) c.col_act[pc] = 0u;
-  }
+  for (int r = gid; r < k; r += gsz) old_act[prev[r]] = 0u;
   #pragma unroll 1
   for (int i = gid; i < Wc; i += gsz) c.cell_widx[wl_cur[i]] = i;
   #pragma unroll 1
@@ -641,10 +642,10 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
   __shared__ int s_red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int E = c.syn_capacity;
-  const int S = c.sc[BH_SC_NSEG];
+  const int S = c.sc[BH_SC_NSEG_NEXT];  // == NSEG once ph_post has committed it (it may run alongside)
   const int thr = c.seg_matching_threshold;
   const float pthr = c.tm_perm_threshold;
-  const uint32_t* col_act = c.col_act;
+  const uint32_t* col_act = c.col_act + (long long)(c.sc[BH_SC_STEP] & 1) * c.column_dim;
   const Range rg = block_range(seg_local_count(c, S), b, nb);  // local rows (== segment ids when not sharded)
   int nm = 0, nrec = 0;
 #pragma unroll 1

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 7
+#define BH_ABI_VERSION 8
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 81920
@@ -150,7 +150,8 @@ typedef struct bh_ctx {
   /* ---- temporal memory: per column (bit b = cell b) and per cell.  Cells are    */
   /* addressed on the device as column * 32 + cell; N32 = 32 * C.                  */
   uint32_t* col_pred;      /* [C] cell_prediction        networks.py:122           */
-  uint32_t* col_act;       /* [C] cell_activation        networks.py:118-119       */
+  uint32_t* col_act;       /* [2][C] cell_activation     networks.py:118-119; buffer  */
+                           /* step & 1 = this step's, the other = the previous step's   */
   uint32_t* col_win;       /* [C] winner cells of the current step                 */
   int32_t* cell_nseg;      /* [N32] bundle_segments        projections.py:227        */
   float* cell_maxjit;      /* [N32] max_jittered_potential projections.py:236-237    */
