@@ -776,9 +776,10 @@ extern "C" int bh_batch_graph_create(const bh_ctx* const* ctxs, int n, int steps
     if ((rc = prepare_fused(ctxs[i]->fused_mode))) return rc;
   }
   cudaStream_t st = S_(stream);
-  const int NS = n < 32 ? n : 32;
-  cudaStream_t side[32];
-  cudaEvent_t fork, join[32];
+  // one capture stream per concurrent kernel the device can hold (148 SMs / the smallest useful cluster)
+  const int NS = n < 64 ? n : 64;
+  cudaStream_t side[64];
+  cudaEvent_t fork, join[64];
   for (int i = 0; i < NS; ++i) {
     CU_RET(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
     CU_RET(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
