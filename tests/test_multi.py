@@ -130,21 +130,23 @@ def _nccl_worker(rank, world, port, result, name, steps, fused="off"):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,steps,fused", [("mid", 1000, "off"), ("tiny", 400, "off"), ("mid", 1000, "shard")])
-def test_column_sharded_two_gpus_match_reference_trace(name, steps, fused):
-    """Column-sharded SP + segment-sharded TM on 2 GPUs -- per-stage kernels with NCCL
+@pytest.mark.parametrize("name,steps,fused,world", [("mid", 1000, "off", 2), ("tiny", 400, "off", 2),
+                                                    ("mid", 1000, "shard", 2), ("mid", 1000, "shard", 4),
+                                                    ("mid", 1000, "off", 4), ("mid", 1000, "shard", 8)])
+def test_column_sharded_two_gpus_match_reference_trace(name, steps, fused, world):
+    """Column-sharded SP + segment-sharded TM on 2 / 4 / 8 GPUs -- per-stage kernels with NCCL
     all-gathers ("off"), or one kernel per shard exchanging over NVLink peer memory
     ("shard") -- every rank reproduces the single-network reference trace bit for bit."""
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     result = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, result, name, steps, fused)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, result, name, steps, fused)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
