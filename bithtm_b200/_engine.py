@@ -232,10 +232,9 @@ class Engine:
     # ------------------------------------------------------------------ segment shards
     def held_segment_ids(self, S: int) -> np.ndarray:
         """Ids < S of the segments whose synapse rows this rank stores, ascending (= local row order)."""
-        ids = np.arange(S, dtype=np.int64)
-        if self.seg_world > 1:
-            ids = ids[(ids >> 6) % self.seg_world == self.seg_rank]
-        return ids
+        from ._shard import held_segment_ids
+
+        return held_segment_ids(S, self.seg_rank, self.seg_world)
 
     # fused sharded step (fused="shard"): every rank's exchange region must be visible to its peers
     def exchange_region_ints(self) -> int:

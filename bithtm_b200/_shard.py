@@ -122,3 +122,20 @@ def map_exchange_regions(engine, group=None):
     dist.barrier(group=group)
     engine.set_exchange_regions(ptrs, keepalive=keep)
     return how
+
+
+def held_segment_ids(n_segments, rank, world):
+    """Ids < n_segments of the segments whose synapse rows rank `rank` of `world` stores: ids are
+    dealt in blocks of 64, round-robin (csrc/common.cuh: seg_held / seg_row / seg_gid), ascending --
+    which is also the order of the rank's local rows."""
+    import numpy as np
+
+    ids = np.arange(int(n_segments), dtype=np.int64)
+    if world > 1:
+        ids = ids[(ids >> 6) % world == rank]
+    return ids
+
+
+def local_row(segment_id, world):
+    """Local synapse row of a held segment (csrc/common.cuh: seg_row)."""
+    return segment_id if world <= 1 else ((((segment_id >> 6) // world) << 6) | (segment_id & 63))

@@ -166,3 +166,30 @@ def test_mt19937_jump_polynomials():
         return y ^ (y >> np.uint32(18))
 
     assert np.array_equal(temper(x[624:624 + 1248]), raw)
+
+
+def test_segment_shard_id_mapping_and_merge():
+    """Host mirror of the segment-shard addressing (ids dealt to ranks in blocks of 64; a rank's
+    rows compact and in id order) and the merge of per-rank exports back into id order."""
+    from bithtm_b200._shard import held_segment_ids, local_row, merge_segment_parts
+
+    for world in (1, 2, 3, 4, 8):
+        for S in (0, 1, 63, 64, 65, 500, 64 * world * 3 + 17):
+            parts = [held_segment_ids(S, r, world) for r in range(world)]
+            allids = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+            assert np.array_equal(np.sort(allids), np.arange(S))  # a partition of the ids
+            for r, ids in enumerate(parts):
+                assert np.all(np.diff(ids) > 0)
+                rows = np.array([local_row(int(s), world) for s in ids], dtype=np.int64)
+                assert np.array_equal(rows, np.arange(len(ids)))  # compact, in id order
+    g = np.random.default_rng(0)
+    S, E, world = 300, 8, 3
+    count = g.integers(0, E, size=S)
+    cells = g.integers(0, 1000, size=(S, E))
+    perm = g.random((S, E)).astype(np.float32)
+    parts = []
+    for r in range(world):
+        ids = held_segment_ids(S, r, world)
+        parts.append((ids, count[ids], cells[ids], perm[ids]))
+    c2, cells2, perm2 = merge_segment_parts(parts[::-1])  # any order of the parts
+    assert np.array_equal(c2, count) and np.array_equal(cells2, cells) and np.array_equal(perm2, perm)
