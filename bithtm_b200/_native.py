@@ -115,6 +115,7 @@ _SIGNATURES = {
     "bh_pack_input": (C.c_int, [_CTXP, _P, _P, _P]),
     "bh_sp_overlap": (C.c_int, [_CTXP, _P, _P]),
     "bh_sp_overlap_batched": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
+    "bh_sp_overlap_batched_tc": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
     "bh_boost": (C.c_int, [_CTXP, _P]),
     "bh_inhibit": (C.c_int, [_CTXP, _P]),
     "bh_set_active_columns": (C.c_int, [_CTXP, _P, _P]),

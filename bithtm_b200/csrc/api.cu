@@ -242,6 +242,19 @@ extern "C" int bh_sp_overlap_batched(const bh_ctx* x, const uint32_t* inputs_dev
   return 0;
 }
 
+extern "C" int bh_sp_overlap_batched_tc(const bh_ctx* x, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
+                                        void* stream) {
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (!inputs_dev || !overlaps_out || n_inputs < 0) return BH_E_BADARG;
+  if (n_inputs == 0) return 0;
+  dim3 grid(cdiv(x->col_local, OTC_N), cdiv(n_inputs, OTC_M));
+  if (grid.y > 65535) return BH_E_BADARG;
+  k_sp_overlap_batched_tc<<<grid, OTC_THREADS, 0, S_(stream)>>>(*x, inputs_dev, n_inputs, overlaps_out);
+  LAUNCHED("sp_overlap_batched_tc");
+  return 0;
+}
+
 extern "C" int bh_boost(const bh_ctx* x, void* stream) {
   k_boost<<<cdiv(x->col_local, 256), 256, 0, S_(stream)>>>(*x);
   LAUNCH_CHECK();

@@ -231,6 +231,116 @@ __global__ void __launch_bounds__(1024) k_sp_overlap_batched(const __grid_consta
   if (col0 + tx < c.col_local && in0 + ty < n_inputs) out[(long long)(in0 + ty) * c.col_local + col0 + tx] = acc;
 }
 
+// ---------------------------------------------------------------------------------
+// (a'') the same batched overlap as an int8 TENSOR-CORE contraction:
+//   out[b][j] = sum_i x[b][i] * m[j][i],  x, m in {0,1}  ==  popcount(x[b] & m[j]).
+// A = inputs (row-major, K = input bits), B = connected mask (one mask row per output
+// column, K-contiguous: the "col" operand), both kept bit-packed in HBM and in shared
+// memory and expanded to u8 {0,1} in registers right before the MMA (one nibble -> 4
+// bytes with one multiply: the nibble's bits land 7 positions apart without carries), so
+// operand traffic stays 1 bit per element.  mma.sync.m16n8k32.u8.u8.s32, exact in int32.
+// CTA tile 64 inputs x 128 columns, 4 warps of 32 x 64 (2 x 8 MMA tiles, 64 accumulators),
+// K staged 1024 bits at a time; rows padded to 36 words: the fragment reads
+// (8 rows x 1 word per quad... bank = 4*row + const) are conflict-free.
+// Fragment layout (PTX ISA, m16n8k32 .u8): g = lane / 4, t = lane % 4;
+//   A reg0 = (row g, k 4t..4t+3)  reg1 = (row g+8, same k)  reg2/3 = same rows, k + 16
+//   B reg0 = (k 4t..4t+3, col g)  reg1 = k + 16;  C = (row g, col 2t, 2t+1), (row g+8, ...).
+// Any bit <-> k assignment works as long as A and B use the same one; here k = bit index
+// of the 32-bit word.
+// ---------------------------------------------------------------------------------
+#define OTC_M 64
+#define OTC_N 128
+#define OTC_KW 32
+#define OTC_LD 36
+#define OTC_THREADS 128
+
+__device__ __forceinline__ uint32_t otc_expand(uint32_t w, int shift) {
+  return (((w >> shift) & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+
+__device__ __forceinline__ void otc_mma(int (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(OTC_THREADS) k_sp_overlap_batched_tc(const __grid_constant__ bh_ctx c,
+                                                                       const uint32_t* __restrict__ inputs, int n_inputs,
+                                                                       int32_t* __restrict__ out) {
+  __shared__ __align__(16) uint32_t s_a[OTC_M][OTC_LD], s_b[OTC_N][OTC_LD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 64;
+  const int m0 = blockIdx.y * OTC_M, n0 = blockIdx.x * OTC_N;
+  const int sh_lo = 4 * t, sh_hi = 16 + 4 * t;
+  int acc[2][8][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0;
+
+  for (int w0 = 0; w0 < c.input_words; w0 += OTC_KW) {
+    const int w = w0 + lane;
+    const bool w_ok = w < c.input_words;
+#pragma unroll 4
+    for (int r = warp; r < OTC_M; r += OTC_THREADS / 32) {
+      const int inp = m0 + r;
+      s_a[r][lane] = (w_ok && inp < n_inputs) ? __ldg(inputs + (long long)inp * c.input_words + w) : 0u;
+    }
+#pragma unroll 4
+    for (int r = warp; r < OTC_N; r += OTC_THREADS / 32) {
+      const int col = n0 + r;
+      s_b[r][lane] = (w_ok && col < c.col_local) ? __ldg(c.sp_mask + (long long)col * c.mask_stride + w) : 0u;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int kw = 0; kw < OTC_KW; ++kw) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t w_lo = s_a[wm + i * 16 + g][kw], w_hi = s_a[wm + i * 16 + g + 8][kw];
+        a[i][0] = otc_expand(w_lo, sh_lo);
+        a[i][1] = otc_expand(w_hi, sh_lo);
+        a[i][2] = otc_expand(w_lo, sh_hi);
+        a[i][3] = otc_expand(w_hi, sh_hi);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t wb = s_b[wn + j * 8 + g][kw];
+        uint32_t b[2];
+        b[0] = otc_expand(wb, sh_lo);
+        b[1] = otc_expand(wb, sh_hi);
+        otc_mma(acc[0][j], a[0], b);
+        otc_mma(acc[1][j], a[1], b);
+      }
+    }
+    __syncthreads();
+  }
+
+  const bool pair_ok = (c.col_local & 1) == 0;  // 8-byte stores need even row pitch (col is always even)
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = n0 + wn + j * 8 + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = m0 + wm + i * 16 + g + 8 * h;
+        if (row >= n_inputs || col >= c.col_local) continue;
+        int32_t* o = out + (long long)row * c.col_local + col;
+        if (pair_ok) {
+          *reinterpret_cast<int2*>(o) = make_int2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
+        } else {
+          o[0] = acc[i][j][2 * h];
+          if (col + 1 < c.col_local) o[1] = acc[i][j][2 * h + 1];
+        }
+      }
+    }
+}
+
 __global__ void k_boost(const __grid_constant__ bh_ctx c) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= c.col_local) return;

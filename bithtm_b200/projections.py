@@ -97,10 +97,12 @@ class DenseProjection:
         nat.check(nat.lib.bh_sp_overlap(eng.ref, words.data_ptr(), eng.stream), "bh_sp_overlap")
         return eng.buf["overlaps"].cpu().numpy().astype(np.int64)
 
-    def process_batch(self, input_activations):
+    def process_batch(self, input_activations, tensor_core=True):
         """Extension: ``process`` (projections.py:18-21) for a batch of inputs [B, input_dim] against
         this one projection -> int64 overlaps [B, output_dim] (a CUDA tensor in, a CUDA tensor out
-        when given one).  Column-sharded: this rank's columns."""
+        when given one).  Column-sharded: this rank's columns.  ``tensor_core=True``: the int8
+        tensor-core contraction (``bh_sp_overlap_batched_tc``); ``False``: AND + popcount on the
+        integer pipe (``bh_sp_overlap_batched``).  Both are exact and agree bit for bit."""
         import torch
 
         eng = self._need_engine()
@@ -116,8 +118,8 @@ class DenseProjection:
         packed = (x.view(B, words, 32).to(torch.int64) * weights).sum(dim=2)
         packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32).contiguous()
         out = torch.empty(B, eng.C_local, dtype=torch.int32, device=eng.device)
-        nat.check(nat.lib.bh_sp_overlap_batched(eng.ref, packed.data_ptr(), B, out.data_ptr(), eng.stream),
-                  "bh_sp_overlap_batched")
+        name = "bh_sp_overlap_batched_tc" if tensor_core else "bh_sp_overlap_batched"
+        nat.check(getattr(nat.lib, name)(eng.ref, packed.data_ptr(), B, out.data_ptr(), eng.stream), name)
         out = out.to(torch.int64)
         return out if is_cuda else out.cpu().numpy()
 

@@ -233,10 +233,14 @@ int bh_sp_overlap(const bh_ctx* ctx, const uint32_t* input_words_dev, void* stre
 /* DenseProjection.process for n_inputs input vectors against the ONE connected mask of this
  * network (a loop of projections.py:18-21 over inputs that share the projection, e.g. inference
  * over many streams with SP learning off): inputs_dev [n_inputs][input_words] packed words,
- * overlaps_out [n_inputs][col_local] int32.  Bit-packed AND + popcount; the result write
- * (4 * n_inputs * C bytes) bounds it, which is why no tensor-core contraction is used. */
+ * overlaps_out [n_inputs][col_local] int32.  Bit-packed AND + popcount on the integer pipe. */
 int bh_sp_overlap_batched(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
                           void* stream);
+/* Same contract and same results as bh_sp_overlap_batched, computed as an int8 tensor-core
+ * contraction [n_inputs x I] . [I x C] (mma.sync m16n8k32 u8, int32 accumulate: exact); the
+ * operands stay bit-packed in HBM / shared memory and are widened to {0,1} bytes in registers. */
+int bh_sp_overlap_batched_tc(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
+                             void* stream);
 /* ExponentialBoosting.process (regularizations.py:15-17) -> ctx->boosted */
 int bh_boost(const bh_ctx* ctx, void* stream);
 /* GlobalInhibition.process (regularizations.py:28-29) with the canonical rule

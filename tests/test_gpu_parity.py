@@ -546,7 +546,7 @@ def test_capacity_overflow_raises():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("I,C,B", [(1024, 2048, 300), (200, 300, 33), (4100, 512, 64)])
+@pytest.mark.parametrize("I,C,B", [(1024, 2048, 300), (200, 300, 33), (4100, 512, 64), (97, 131, 1), (1024, 2048, 1024)])
 def test_batched_overlap_equals_loop_of_process(I, C, B):
     """DenseProjection.process_batch == a loop of DenseProjection.process (projections.py:18-21)
     == the dense float64 comparison of the oracle."""
@@ -559,12 +559,14 @@ def test_batched_overlap_equals_loop_of_process(I, C, B):
     sp._ensure_engine()
     g = np.random.default_rng(2)
     xs = g.random((B, I)) < 0.3
-    got = proj.process_batch(xs)
+    got = proj.process_batch(xs)  # int8 tensor-core contraction
+    got_popc = proj.process_batch(xs, tensor_core=False)
     want = ((perm >= 0.0)[None, :, :] & xs[:, None, :]).sum(axis=2) if B * C * I < 3e8 else None
     if want is None:
         want = np.stack([((perm >= 0.0) & x).sum(axis=1) for x in xs])
     assert got.dtype == np.int64 and np.array_equal(got, want)
-    assert np.array_equal(proj.process(xs[5]), want[5])
+    assert got_popc.dtype == np.int64 and np.array_equal(got_popc, want)
+    assert np.array_equal(proj.process(xs[min(5, B - 1)]), want[min(5, B - 1)])
 
 
 @pytest.mark.gpu
