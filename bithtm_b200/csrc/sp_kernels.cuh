@@ -235,45 +235,56 @@ __global__ void __launch_bounds__(1024) k_sp_overlap_batched(const __grid_consta
 // (a'') the same batched overlap as an int8 TENSOR-CORE contraction:
 //   out[b][j] = sum_i x[b][i] * m[j][i],  x, m in {0,1}  ==  popcount(x[b] & m[j]).
 // A = inputs (row-major, K = input bits), B = connected mask (one mask row per output
-// column, K-contiguous: the "col" operand), both kept bit-packed in HBM and in shared
-// memory and expanded to u8 {0,1} in registers right before the MMA (one nibble -> 4
-// bytes with one multiply: the nibble's bits land 7 positions apart without carries), so
-// operand traffic stays 1 bit per element.  mma.sync.m16n8k32.u8.u8.s32, exact in int32.
-// CTA tile 64 inputs x 128 columns, 4 warps of 32 x 64 (2 x 8 MMA tiles, 64 accumulators),
-// K staged 1024 bits at a time; rows padded to 36 words: the fragment reads
-// (8 rows x 1 word per quad... bank = 4*row + const) are conflict-free.
+// column, K-contiguous: the "col" operand).  Both stay bit-packed in HBM and in shared
+// memory and are widened to bytes in registers right before the MMA, so operand traffic is
+// 1 bit per element.  mma.sync.m16n8k32.u8.u8.s32, exact in int32.
+//
 // Fragment layout (PTX ISA, m16n8k32 .u8): g = lane / 4, t = lane % 4;
 //   A reg0 = (row g, k 4t..4t+3)  reg1 = (row g+8, same k)  reg2/3 = same rows, k + 16
 //   B reg0 = (k 4t..4t+3, col g)  reg1 = k + 16;  C = (row g, col 2t, 2t+1), (row g+8, ...).
-// Any bit <-> k assignment works as long as A and B use the same one; here k = bit index
-// of the 32-bit word.
+// A dot product does not care which bit sits at which k as long as A and B agree, so the
+// assignment is chosen for the cheapest widening: byte j of the "low" register of thread t
+// is bit 8j + 2t + 1 of the 32-bit word, byte j of the "high" register is bit 8j + 2t:
+//   A (values 0 / 1):    y = w >> 2t;          hi = y & 0x01010101;  lo = (y >> 1) & 0x01010101
+//   B (values 0 / 128):  y = w * 2^(6 - 2t);   lo = y & 0x80808080;  hi = (y * 2) & 0x80808080
+// (two logic ops + two multiplies per word: half on the ALU pipe, half on the FMA pipe), and
+// the accumulators are divided by 128 at the end (exact; K * 128 < 2^31 for K < 2^24 bits).
+//
+// CTA tile 64 inputs x 128 columns, 4 warps of 32 x 64 (2 x 8 MMA tiles, 64 accumulators),
+// K staged 512 bits at a time through two shared-memory buffers filled by cp.async (the next
+// chunk travels while this one is multiplied); shared rows padded to 20 words so the 128-bit
+// fragment reads (8 rows x 16 B) are conflict-free.
 // ---------------------------------------------------------------------------------
 #define OTC_M 64
 #define OTC_N 128
-#define OTC_KW 32
-#define OTC_LD 36
+#define OTC_KW 16
+#define OTC_LD 20
 #define OTC_THREADS 128
 
-__device__ __forceinline__ uint32_t otc_expand(uint32_t w, int shift) {
-  return (((w >> shift) & 0xFu) * 0x00204081u) & 0x01010101u;
-}
-
-__device__ __forceinline__ void otc_mma(int (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+__device__ __forceinline__ void otc_mma(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(OTC_THREADS) k_sp_overlap_batched_tc(const __grid_constant__ bh_ctx c,
-                                                                       const uint32_t* __restrict__ inputs, int n_inputs,
-                                                                       int32_t* __restrict__ out) {
-  __shared__ __align__(16) uint32_t s_a[OTC_M][OTC_LD], s_b[OTC_N][OTC_LD];
+// 4-byte asynchronous copy global -> shared; !ok copies nothing and writes zero.
+__device__ __forceinline__ void otc_cp4(uint32_t* dst_smem, const uint32_t* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int n = ok ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(OTC_THREADS, 4) k_sp_overlap_batched_tc(const __grid_constant__ bh_ctx c,
+                                                                          const uint32_t* __restrict__ inputs, int n_inputs,
+                                                                          int32_t* __restrict__ out) {
+  __shared__ __align__(16) uint32_t s_a[2][OTC_M][OTC_LD], s_b[2][OTC_N][OTC_LD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 64;
   const int m0 = blockIdx.y * OTC_M, n0 = blockIdx.x * OTC_N;
-  const int sh_lo = 4 * t, sh_hi = 16 + 4 * t;
+  const int a_shift = 2 * t;
+  const uint32_t b_mul = 1u << (6 - 2 * t);
   int acc[2][8][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -282,45 +293,76 @@ __global__ void __launch_bounds__(OTC_THREADS) k_sp_overlap_batched_tc(const __g
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[i][j][r] = 0;
 
-  for (int w0 = 0; w0 < c.input_words; w0 += OTC_KW) {
-    const int w = w0 + lane;
+  // stage one K chunk (OTC_KW words of every row of the tile) into buffer `buf`: a warp covers
+  // two rows per instruction (lanes 0-15 / 16-31), asynchronously, out-of-range -> zero
+  auto stage = [&](int buf, int w0) {
+    const int w = w0 + (lane & 15), half = lane >> 4;
     const bool w_ok = w < c.input_words;
-#pragma unroll 4
-    for (int r = warp; r < OTC_M; r += OTC_THREADS / 32) {
-      const int inp = m0 + r;
-      s_a[r][lane] = (w_ok && inp < n_inputs) ? __ldg(inputs + (long long)inp * c.input_words + w) : 0u;
+#pragma unroll
+    for (int r = 2 * warp + half; r < OTC_M; r += OTC_THREADS / 16) {
+      const bool ok = w_ok && m0 + r < n_inputs;
+      otc_cp4(&s_a[buf][r][lane & 15], ok ? inputs + (long long)(m0 + r) * c.input_words + w : inputs, ok);
     }
-#pragma unroll 4
-    for (int r = warp; r < OTC_N; r += OTC_THREADS / 32) {
-      const int col = n0 + r;
-      s_b[r][lane] = (w_ok && col < c.col_local) ? __ldg(c.sp_mask + (long long)col * c.mask_stride + w) : 0u;
+#pragma unroll
+    for (int r = 2 * warp + half; r < OTC_N; r += OTC_THREADS / 16) {
+      const bool ok = w_ok && n0 + r < c.col_local;
+      otc_cp4(&s_b[buf][r][lane & 15], ok ? c.sp_mask + (long long)(n0 + r) * c.mask_stride + w : c.sp_mask, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int n_chunks = (c.input_words + OTC_KW - 1) / OTC_KW;
+  stage(0, 0);
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < n_chunks) {
+      stage(buf ^ 1, (ch + 1) * OTC_KW);  // buffer buf^1 was released by the barrier ending chunk ch-1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-#pragma unroll 2
-    for (int kw = 0; kw < OTC_KW; ++kw) {
-      uint32_t a[2][4];
+#pragma unroll 1
+    for (int kw = 0; kw < OTC_KW; kw += 4) {
+      uint32_t a[4][2][4];  // [word of the group of 4][m tile][fragment register]
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint32_t w_lo = s_a[wm + i * 16 + g][kw], w_hi = s_a[wm + i * 16 + g + 8][kw];
-        a[i][0] = otc_expand(w_lo, sh_lo);
-        a[i][1] = otc_expand(w_hi, sh_lo);
-        a[i][2] = otc_expand(w_lo, sh_hi);
-        a[i][3] = otc_expand(w_hi, sh_hi);
-      }
+        const uint4 r_lo = *reinterpret_cast<const uint4*>(&s_a[buf][wm + i * 16 + g][kw]);
+        const uint4 r_hi = *reinterpret_cast<const uint4*>(&s_a[buf][wm + i * 16 + g + 8][kw]);
+        const uint32_t lo[4] = {r_lo.x, r_lo.y, r_lo.z, r_lo.w}, hi[4] = {r_hi.x, r_hi.y, r_hi.z, r_hi.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t wb = s_b[wn + j * 8 + g][kw];
-        uint32_t b[2];
-        b[0] = otc_expand(wb, sh_lo);
-        b[1] = otc_expand(wb, sh_hi);
-        otc_mma(acc[0][j], a[0], b);
-        otc_mma(acc[1][j], a[1], b);
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t y0 = lo[q] >> a_shift, y1 = hi[q] >> a_shift;
+          a[q][i][0] = (y0 >> 1) & 0x01010101u;
+          a[q][i][1] = (y1 >> 1) & 0x01010101u;
+          a[q][i][2] = y0 & 0x01010101u;
+          a[q][i][3] = y1 & 0x01010101u;
+        }
+      }
+      // 4 column tiles at a time: 8 independent accumulator tiles between two MMAs on the same one
+#pragma unroll
+      for (int j0 = 0; j0 < 8; j0 += 4) {
+        uint32_t wb[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint4 r_b = *reinterpret_cast<const uint4*>(&s_b[buf][wn + (j0 + jj) * 8 + g][kw]);
+          wb[jj][0] = r_b.x, wb[jj][1] = r_b.y, wb[jj][2] = r_b.z, wb[jj][3] = r_b.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t y = wb[jj][q] * b_mul;
+            const uint32_t b0 = y & 0x80808080u, b1 = (y * 2u) & 0x80808080u;
+            otc_mma(acc[0][j0 + jj], a[q][0], b0, b1);
+            otc_mma(acc[1][j0 + jj], a[q][1], b0, b1);
+          }
       }
     }
     __syncthreads();
   }
 
-  const bool pair_ok = (c.col_local & 1) == 0;  // 8-byte stores need even row pitch (col is always even)
+  const bool pair_ok = (c.col_local & 1) == 0;  // 8-byte stores need an even row pitch (col is always even)
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -331,11 +373,12 @@ __global__ void __launch_bounds__(OTC_THREADS) k_sp_overlap_batched_tc(const __g
         const int row = m0 + wm + i * 16 + g + 8 * h;
         if (row >= n_inputs || col >= c.col_local) continue;
         int32_t* o = out + (long long)row * c.col_local + col;
+        const int v0 = acc[i][j][2 * h] >> 7, v1 = acc[i][j][2 * h + 1] >> 7;
         if (pair_ok) {
-          *reinterpret_cast<int2*>(o) = make_int2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
+          *reinterpret_cast<int2*>(o) = make_int2(v0, v1);
         } else {
-          o[0] = acc[i][j][2 * h];
-          if (col + 1 < c.col_local) o[1] = acc[i][j][2 * h + 1];
+          o[0] = v0;
+          if (col + 1 < c.col_local) o[1] = v1;
         }
       }
     }
