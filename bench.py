@@ -368,6 +368,18 @@ def ours(args):
                                "CUDA graph of 50 steps x 128 launches per GPU; L2-resident; no collective")
         except Exception as e:
             batched = {"error": repr(e)}
+    shared_mask = None
+    if rank == 0 and world == 1 and not args.no_hbm:
+        # many inputs against ONE connected mask (inference over streams that share a spatial pooler): the
+        # overlap as an int8 tensor-core contraction next to the popcount kernel, both exact
+        try:
+            import batched_overlap
+
+            torch.cuda.empty_cache()
+            shared_mask = {"cfg4_shape": batched_overlap.measure(1024, 2048, 1024, 100),
+                           "cfg3_shape": batched_overlap.measure(256, 65536, 16384, 10)}
+        except Exception as e:
+            shared_mask = {"error": repr(e)}
     if rank == 0:
         launches_per_step = launches
         line = {
@@ -385,6 +397,7 @@ def ours(args):
                     "note": "HierarchicalTemporalMemory.process(host bool array), np.random kept in lock-step"},
             "gpu_launches": launches_per_step * K,
             "roofline": roofline, "roofline_hbm_kernels": hbm, "streams_batched": batched, "sharded_cfg3": sharded,
+            "shared_mask_batched_overlap": shared_mask,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -25,11 +25,12 @@ from bithtm_b200.projections import DenseProjection
 REP = 20
 
 
-def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-    C = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
-    I = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
-    iters = int(sys.argv[4]) if len(sys.argv) > 4 else 200
+# int8 operations per second the mma.sync path can sustain on B200 at 1965 MHz, as ncu reports it
+# (sm__ops_path_tensor_op_imma_src_int8_sparsity_off.sum.peak_sustained = 606 208 ops/cycle)
+IMMA_PEAK_TOPS = 606208 * 1.965e9 / 1e12
+
+
+def measure(B=1024, C=2048, I=1024, iters=200):
     torch.manual_seed(0)
     perm = torch.randn(C, I, dtype=torch.float64, device="cuda") * 0.1
     np.random.seed(0)
@@ -70,18 +71,32 @@ def main():
         us = float(np.median(warm))
         res[name] = {"us_l2_flushed_single_launch": round(float(np.median(cold)), 2), "us_back_to_back": round(us, 2),
                      "out_gbs": round(4.0 * B * C / us / 1e3, 1),
-                     "tera_bitops_per_s": round(2.0 * B * C * words * 32 / us / 1e6, 1)}
+                     "int8_tops": round(2.0 * B * C * words * 32 / us / 1e6, 1)}
     same = bool(torch.equal(outs["bh_sp_overlap_batched_tc"], outs["bh_sp_overlap_batched"]))
     # spot check against the definition on a few rows
     mask = (perm >= 0.0)
     bits = ((packed[:4].to(torch.int64)[:, :, None] >> torch.arange(32, device="cuda")) & 1).reshape(4, -1)[:, :I].bool()
     want = (mask[None, :, :] & bits[:, None, :]).sum(dim=2).to(torch.int32)
     ok = bool(torch.equal(outs["bh_sp_overlap_batched_tc"][:4], want))
-    print(json.dumps({"workload": f"{B} inputs x {C} columns x {I} bits, one shared mask", "iters": iters,
-                      "tensor_core": res["bh_sp_overlap_batched_tc"], "popcount": res["bh_sp_overlap_batched"],
-                      "bit_identical": same, "matches_definition": ok,
-                      "algorithmic_bytes": int(4 * B * C + (B + C) * words * 4)}))
-    if not (same and ok):
+    tc = res["bh_sp_overlap_batched_tc"]
+    return {"workload": f"{B} inputs x {C} columns x {I} bits, one shared mask", "iters": iters,
+            "tensor_core": tc, "popcount": res["bh_sp_overlap_batched"],
+            "roofline": {"bound": "tensor", "kernel": "k_sp_overlap_batched_tc", "achieved": tc["int8_tops"],
+                         "peak": round(IMMA_PEAK_TOPS, 1), "unit": "TOP/s (int8, mma.sync path)",
+                         "frac": round(tc["int8_tops"] / IMMA_PEAK_TOPS, 4),
+                         "peak_source": "ncu sm__ops_path_tensor_op_imma_src_int8 peak_sustained x 1965 MHz"},
+            "bit_identical": same, "matches_definition": ok,
+            "algorithmic_bytes": int(4 * B * C + (B + C) * words * 4)}
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    C = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+    I = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    iters = int(sys.argv[4]) if len(sys.argv) > 4 else 200
+    r = measure(B, C, I, iters)
+    print(json.dumps(r))
+    if not (r["bit_identical"] and r["matches_definition"]):
         sys.exit(1)
 
 
