@@ -357,14 +357,14 @@ def ours(args):
             torch.cuda.empty_cache()
             if world > 1:
                 dist.barrier()
-            batched = stream_batch.measure(128, 4, 400, 200, seed0=1000 * rank)
+            batched = stream_batch.measure(128, 4, 400, 200, seed0=1000 * rank, threads=512)
             if world > 1:
                 ms = torch.tensor([batched["ms"]], dtype=torch.float64, device="cuda")
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
                 batched["ms"] = float(ms)
                 batched["streams"] *= world
                 batched["aggregate_steps_per_s"] = batched["streams"] * batched["steps_per_stream"] / (batched["ms"] * 1e-3)
-            batched["note"] = (f"{128 * world} independent cfg2 networks, 128 per GPU, one 4-CTA cluster kernel each, one "
+            batched["note"] = (f"{128 * world} independent cfg2 networks, 128 per GPU, one 4-CTA x 512-thread cluster kernel each (2 CTAs per SM), one "
                                "CUDA graph of 50 steps x 128 launches per GPU; L2-resident; no collective")
         except Exception as e:
             batched = {"error": repr(e)}

@@ -45,7 +45,7 @@ class Engine:
     def __init__(self, input_dim, column_dim, cell_dim, active_columns, *, device=None,
                  max_segments=None, max_synapses_per_segment=128, match_capacity=None,
                  learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
-                 fused="auto", fused_ctas=None, column_shard=None, parallel_rng="auto", segment_shard=None,
+                 fused="auto", fused_ctas=None, fused_threads=None, column_shard=None, parallel_rng="auto", segment_shard=None,
                  exchange_match_capacity=None, exchange_recycle_capacity=None):
         """``column_shard=(rank, world)``: this engine owns columns
         [rank*C/world, (rank+1)*C/world) of the spatial pooler (permanence, mask, duty
@@ -141,6 +141,14 @@ class Engine:
         if fused_ctas is None:
             fused_ctas = 16 if fused == "cluster" else self.sm_count
         ctx.fused_ctas = int(fused_ctas)
+        # threads per CTA of the cluster kernel: 1024 (one CTA per SM) is fastest for ONE network; several
+        # independent networks side by side (StreamBatch) run faster with smaller CTAs sharing the SMs
+        if fused_threads is not None:
+            if fused != "cluster":
+                raise ValueError('fused_threads applies to fused="cluster" only')
+            if not (256 <= int(fused_threads) <= 1024 and int(fused_threads) % 32 == 0):
+                raise ValueError("fused_threads must be a multiple of 32 in [256, 1024]")
+            ctx.fused_threads = int(fused_threads)
         self.ctx = ctx
         self.I, self.C, self.c, self.k, self.N = I, Ccol, c, k, N
 

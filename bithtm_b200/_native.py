@@ -69,7 +69,7 @@ class BhCtx(C.Structure):
         ("tm_perm_initial", C.c_float), ("tm_perm_threshold", C.c_float), ("epsilon", C.c_float),
         ("tm_learn_can_delete", C.c_int32), ("tm_punish_can_delete", C.c_int32),
         ("seg_activation_threshold", C.c_int32), ("seg_matching_threshold", C.c_int32),
-        ("seg_sampling_synapses", C.c_int32), ("fused_ctas", C.c_int32),
+        ("seg_sampling_synapses", C.c_int32), ("fused_ctas", C.c_int32), ("fused_threads", C.c_int32),
         # device pointers
         ("sp_perm", _P), ("sp_mask", _P), ("duty", _P), ("overlaps", _P), ("boosted", _P),
         ("active_cols", _P), ("col_active", _P),

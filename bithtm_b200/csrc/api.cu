@@ -546,6 +546,10 @@ static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_step
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(nb);
   cfg.blockDim = dim3(FUSED_THREADS);
+  if (x->fused_mode == 1 && x->fused_threads) {  // cluster kernel with smaller CTAs (several per SM)
+    if (x->fused_threads < 256 || x->fused_threads > FUSED_THREADS || x->fused_threads % 32) return BH_E_BADARG;
+    cfg.blockDim = dim3(x->fused_threads);
+  }
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

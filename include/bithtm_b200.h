@@ -137,6 +137,9 @@ typedef struct bh_ctx {
   int32_t seg_matching_threshold;
   int32_t seg_sampling_synapses;
   int32_t fused_ctas;      /* CTAs of the fused kernel (cluster size <= 16, or grid)  */
+  int32_t fused_threads;   /* threads per CTA of the cluster kernel (fused_mode 1): a   */
+                           /* multiple of 32 in [256, 1024]; 0 = 1024.  Fewer threads  */
+                           /* let several CTAs share an SM (independent streams)       */
 
   /* ---- spatial pooler (DenseProjection / ExponentialBoosting / inhibition) --- */
   double* sp_perm;         /* [C][I] float64 permanence, row-major                 */

@@ -192,6 +192,17 @@ def test_lockstep_tiny(fused, ctas):
     _lockstep("tiny", fused=fused, fused_ctas=ctas)
 
 
+@pytest.mark.parametrize("ctas,threads", [(4, 512), (8, 256), (16, 768)])
+def test_lockstep_cluster_kernel_with_smaller_ctas(ctas, threads):
+    """The cluster kernel with fewer threads per CTA (the StreamBatch configuration, several
+    CTAs per SM) is the same computation."""
+    _lockstep("tiny", fused="cluster", fused_ctas=ctas, fused_threads=threads)
+
+
+def test_cfg2_cluster_kernel_512_threads_1500_steps():
+    _lockstep("cfg2", steps=1500, check_every=25, fused="cluster", fused_ctas=4, fused_threads=512)
+
+
 @pytest.mark.parametrize("fused", ["cluster", "grid", "off"])
 def test_lockstep_odd_dims(fused):
     _lockstep("odd", fused=fused)
@@ -424,7 +435,7 @@ def test_stream_batch_equals_streams_stepped_alone():
     def build(seed):
         np.random.seed(seed)
         h = bithtm.HierarchicalTemporalMemory(I, C, c, k, rng_sync="lazy", ring_len=steps, max_segments=1 << 12,
-                                              fused="cluster", fused_ctas=4)
+                                              fused="cluster", fused_ctas=4, fused_threads=512)
         return h, np.random.get_state()  # every stream continues from its own state
 
     alone = []
