@@ -248,6 +248,7 @@ extern "C" int bh_sp_overlap_batched_tc(const bh_ctx* x, const uint32_t* inputs_
   if (rc) return rc;
   if (!inputs_dev || !overlaps_out || n_inputs < 0) return BH_E_BADARG;
   if (n_inputs == 0) return 0;
+  if ((long long)x->input_words * 32 >= (1ll << 24)) return BH_E_UNSUPPORTED;  // accumulators hold 128 * overlap
   dim3 grid(cdiv(x->col_local, OTC_N), cdiv(n_inputs, OTC_M));
   if (grid.y > 65535) return BH_E_BADARG;
   k_sp_overlap_batched_tc<<<grid, OTC_THREADS, 0, S_(stream)>>>(*x, inputs_dev, n_inputs, overlaps_out);

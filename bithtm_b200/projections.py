@@ -118,6 +118,9 @@ class DenseProjection:
         packed = (x.view(B, words, 32).to(torch.int64) * weights).sum(dim=2)
         packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32).contiguous()
         out = torch.empty(B, eng.C_local, dtype=torch.int32, device=eng.device)
+        if tensor_core and words * 32 >= 1 << 24:
+            raise ValueError("process_batch(tensor_core=True) supports fewer than 2**24 input bits; "
+                             "pass tensor_core=False")
         name = "bh_sp_overlap_batched_tc" if tensor_core else "bh_sp_overlap_batched"
         nat.check(getattr(nat.lib, name)(eng.ref, packed.data_ptr(), B, out.data_ptr(), eng.stream), name)
         out = out.to(torch.int64)

@@ -241,7 +241,8 @@ int bh_sp_overlap_batched(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_i
                           void* stream);
 /* Same contract and same results as bh_sp_overlap_batched, computed as an int8 tensor-core
  * contraction [n_inputs x I] . [I x C] (mma.sync m16n8k32 u8, int32 accumulate: exact); the
- * operands stay bit-packed in HBM / shared memory and are widened to {0,1} bytes in registers. */
+ * operands stay bit-packed in HBM / shared memory and are widened to bytes in registers.
+ * BH_E_UNSUPPORTED for 2^24 or more input bits (use bh_sp_overlap_batched). */
 int bh_sp_overlap_batched_tc(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
                              void* stream);
 /* ExponentialBoosting.process (regularizations.py:15-17) -> ctx->boosted */
