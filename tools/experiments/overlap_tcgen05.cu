@@ -1,5 +1,12 @@
-// PROTOTYPE -- compile-checked in round 1, NOT yet run on hardware (no GPU minutes were left).
-// Not part of libbithtm_b200.so; nothing in the product path includes this file.
+// PROTOTYPE (stand-alone program; not part of libbithtm_b200.so, nothing in the product path includes it).
+// Run on a B200 at the very end of round 1: results BIT-IDENTICAL to the popcount reference kernel at
+// 1024 x 2048 x 1024 (18.9 us) and at 256 x 65536 x 16384 (638 us = 862 int8 TOP/s; the shipped
+// mma.sync kernel: 12.5 us / 747 us).  Tried with the last GPU seconds, both without effect: 16 instead
+// of 8 producer warps (648 us), three stages of register look-ahead for the global words (657 us) --
+// so neither the widening throughput nor the load latency bounds it; at ~2400 clk per 128x256x128 stage
+// the suspects are the un-swizzled operand reads of the MMA itself and the per-stage
+// fence.proxy.async + mbarrier hand-off.  Next: ncu it; 128-byte-swizzled tiles; a dedicated epilogue
+// warpgroup with a double-buffered accumulator; tile order against the 3.46-wave tail.
 //
 // Shared-mask batched overlap (DenseProjection.process for many inputs against one connected mask,
 // bitHTM projections.py:18-21) as a tcgen05 int8 contraction:
@@ -21,7 +28,7 @@
 // A dot product does not care which bit sits at which k as long as both operands agree: byte j of
 // register s (s = 0..7) of a 32-bit word is bit 8j + s, i.e. (w >> s) & 0x01010101 -- two integer
 // ops per 4 bytes.
-// Every mbarrier wait has an iteration cap that raises an error flag instead of hanging.
+// Every mbarrier wait is bounded (1 s of globaltimer) and raises an error flag instead of hanging.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/_build/overlap_tcgen05 \
 //        tools/experiments/overlap_tcgen05.cu
@@ -44,7 +51,11 @@ constexpr int SBO = 128;                          // bytes between 8-row groups
 constexpr int A_STAGE = CHUNKS * A_LBO;           // 16 KiB
 constexpr int B_STAGE = CHUNKS * B_LBO;           // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
-constexpr int PRODUCER_WARPS = 8;
+#ifndef PRODUCER_WARPS_N
+#define PRODUCER_WARPS_N 8
+#endif
+constexpr int PRODUCER_WARPS = PRODUCER_WARPS_N;  // multiple of 4 (TMEM lane quarters), divides 1536 / 32
+constexpr int COLS_PER_WARP = TILE_N / (PRODUCER_WARPS / 4);
 constexpr int PRODUCERS = PRODUCER_WARPS * 32;
 constexpr int THREADS = PRODUCERS + 32;
 constexpr int ITEMS = (TILE_M + TILE_N) * BLOCK_KW / PRODUCERS;  // (row, word) pairs per producer thread: 6
@@ -62,6 +73,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
 }
 __device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity, int* err) {
   const uint32_t a = smem_u32(b);
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (int it = 0; it < SPIN_CAP; ++it) {
     uint32_t ok;
     asm volatile(
@@ -73,6 +86,11 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity, int* err
         : "memory");
     if (ok) return true;
     if (*(volatile int*)err) return false;
+    if ((it & 255) == 255) {  // wall-clock bound: 1 s
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 1000000000ull) break;
+    }
   }
   atomicExch(err, 1);
   return false;
@@ -168,10 +186,15 @@ __global__ void __launch_bounds__(THREADS, 1)
     int tile_iter = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
       const int m0 = (tile % tiles_m) * TILE_M, n0 = (tile / tiles_m) * TILE_N;
-      uint32_t cur[ITEMS], nxt[ITEMS];
+      // register ring: the words of the next three stages are in flight while this one is widened (a stage
+      // is shorter than one L2 / HBM round trip: with one stage of look-ahead the ring ran at 1.25 us per
+      // stage = the load latency)
+      uint32_t cur[ITEMS], n1[ITEMS], n2[ITEMS], n3[ITEMS];
       fetch(m0, n0, 0, cur);
+      if (k_stages > 1) fetch(m0, n0, BLOCK_KW, n1);
+      if (k_stages > 2) fetch(m0, n0, 2 * BLOCK_KW, n2);
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
-        if (ks + 1 < k_stages) fetch(m0, n0, (ks + 1) * BLOCK_KW, nxt);  // in flight while this stage is widened
+        if (ks + 3 < k_stages) fetch(m0, n0, (ks + 3) * BLOCK_KW, n3);
         const int s = it % STAGES;
         if (!mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1, err)) return;
         uint8_t* a_st = smem + s * STAGE_BYTES;
@@ -192,17 +215,17 @@ __global__ void __launch_bounds__(THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) cur[i] = nxt[i];
+        for (int i = 0; i < ITEMS; ++i) cur[i] = n1[i], n1[i] = n2[i], n2[i] = n3[i];
       }
       // epilogue: accumulator of this tile TMEM -> registers -> global.  Warp w reads TMEM lanes
-      // 32 * (w % 4) .. + 31 (its quarter) and the column half w / 4.
+      // 32 * (w % 4) .. + 31 (its quarter) and the column group w / 4.
       if (!mbar_wait(&acc_full, tile_iter & 1, err)) return;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int q = warp & 3, half = warp >> 2;
       const int row = m0 + 32 * q + lane;
 #pragma unroll 1
-      for (int cblk = 0; cblk < 4; ++cblk) {
-        const int col0 = half * 128 + cblk * 32;
+      for (int cblk = 0; cblk < COLS_PER_WARP / 32; ++cblk) {
+        const int col0 = half * COLS_PER_WARP + cblk * 32;
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
