@@ -3,10 +3,13 @@
 // 1024 x 2048 x 1024 (18.9 us) and at 256 x 65536 x 16384 (638 us = 862 int8 TOP/s; the shipped
 // mma.sync kernel: 12.5 us / 747 us).  Tried with the last GPU seconds, both without effect: 16 instead
 // of 8 producer warps (648 us), three stages of register look-ahead for the global words (657 us) --
-// so neither the widening throughput nor the load latency bounds it; at ~2400 clk per 128x256x128 stage
-// the suspects are the un-swizzled operand reads of the MMA itself and the per-stage
-// fence.proxy.async + mbarrier hand-off.  Next: ncu it; 128-byte-swizzled tiles; a dedicated epilogue
-// warpgroup with a double-buffered accumulator; tile order against the 3.46-wave tail.
+// Reading the SASS afterwards explains both: `fence.proxy.async.shared::cta` is MEMBAR.ALL.CTA +
+// FENCE.VIEW.ASYNC, and the MEMBAR also drains the thread's outstanding global loads, so every stage pays a
+// full L2 / HBM round trip whatever the look-ahead (1.25 us per 128x256x128 stage measured).  Variant 1 below
+// (producer groups that own ring slots, loads issued after the fence) is the fix; it compiles but has NOT
+// been run yet.  Further: loads by dedicated warps or TMA into a raw-word ring; 128-byte-swizzled tiles; a
+// dedicated epilogue warpgroup with a double-buffered accumulator; tile order against the 3.46-wave tail.
+// Shared-memory budget: 48 KB written + 48 KB read per stage against 128 B/clk -> floor ~750 clk per stage.
 //
 // Shared-mask batched overlap (DenseProjection.process for many inputs against one connected mask,
 // bitHTM projections.py:18-21) as a tcgen05 int8 contraction:
@@ -32,7 +35,7 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/_build/overlap_tcgen05 \
 //        tools/experiments/overlap_tcgen05.cu
-//   timeout 60 tools/_build/overlap_tcgen05 [B] [C] [I]
+//   timeout 60 tools/_build/overlap_tcgen05 [B] [C] [I] [variant]
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -85,8 +88,8 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity, int* err
         : "r"(a), "r"(parity)
         : "memory");
     if (ok) return true;
-    if (*(volatile int*)err) return false;
-    if ((it & 255) == 255) {  // wall-clock bound: 1 s
+    if ((it & 255) == 255) {  // every 256 polls: somebody else failed?  wall-clock bound: 1 s
+      if (*(volatile int*)err) return false;
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > 1000000000ull) break;
@@ -279,6 +282,159 @@ __global__ void __launch_bounds__(THREADS, 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
+// ---- variant 1 (NOT YET RUN): producer groups that own ring slots ----------------------------------
+// Finding from the SASS of variant 0: `fence.proxy.async.shared::cta` is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and
+// the MEMBAR drains the thread's outstanding global loads too -- so the register look-ahead of variant 0 is
+// defeated and every stage pays a full L2 / HBM round trip (matches the measured 1.25 us per stage, and
+// explains why neither more producer warps nor deeper look-ahead changed anything).
+// Here 16 producer warps form 4 groups; group g owns ring slot g, i.e. every 4th stage, widens it alone
+// (12 words per thread) and issues the loads of its NEXT stage only AFTER its fence + arrive.  Each group
+// still pays load latency + fence per stage, but four groups do so concurrently.
+constexpr int G_WARPS = 16, G_GROUPS = 4, G_GROUP_THREADS = G_WARPS / G_GROUPS * 32;
+constexpr int G_THREADS = G_WARPS * 32 + 32;
+constexpr int G_ITEMS = (TILE_M + TILE_N) * BLOCK_KW / G_GROUP_THREADS;  // 12
+constexpr int G_COLS_PER_WARP = TILE_N / (G_WARPS / 4);                 // 64
+static_assert(G_GROUPS == STAGES, "a group owns one ring slot");
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+    k_overlap_tcgen05_grouped(const uint32_t* __restrict__ mask, int mask_stride, const uint32_t* __restrict__ inputs,
+                              int words, int B, int C, int32_t* __restrict__ out, int* err) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp < G_WARPS;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], G_WARPS / G_GROUPS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, G_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == G_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int tiles_m = (B + TILE_M - 1) / TILE_M, tiles_n = (C + TILE_N - 1) / TILE_N;
+  const int n_tiles = tiles_m * tiles_n;
+  const int k_stages = (words + BLOCK_KW - 1) / BLOCK_KW;
+
+  if (producer) {
+    const int grp = warp / (G_WARPS / G_GROUPS), gt = tid - grp * G_GROUP_THREADS;  // thread index inside the group
+    // item i of this thread: pair index p = i * G_GROUP_THREADS + gt -> word w = p & 3, row r = p >> 2
+    auto fetch = [&](int m0, int n0, int kw0, uint32_t (&wd)[G_ITEMS]) {
+#pragma unroll
+      for (int i = 0; i < G_ITEMS; ++i) {
+        const int p = i * G_GROUP_THREADS + gt, w = kw0 + (p & 3), r = p >> 2;
+        uint32_t v = 0;
+        if (w < words) {
+          if (r < TILE_M) {
+            if (m0 + r < B) v = __ldg(inputs + (long long)(m0 + r) * words + w);
+          } else if (n0 + r - TILE_M < C) {
+            v = __ldg(mask + (long long)(n0 + r - TILE_M) * mask_stride + w);
+          }
+        }
+        wd[i] = v;
+      }
+    };
+    uint8_t* a_st = smem + grp * STAGE_BYTES;  // this group's ring slot
+    uint8_t* b_st = a_st + A_STAGE;
+    int it_base = 0, tile_iter = 0;  // it_base: stages of all earlier tiles of this CTA
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter, it_base += k_stages) {
+      const int m0 = (tile % tiles_m) * TILE_M, n0 = (tile / tiles_m) * TILE_N;
+      int ks = (grp - it_base) & (G_GROUPS - 1);  // first stage of this tile whose ring position is this group's slot
+      uint32_t cur[G_ITEMS];
+      if (ks < k_stages) fetch(m0, n0, ks * BLOCK_KW, cur);
+      for (; ks < k_stages; ks += G_GROUPS) {
+        const int it = it_base + ks;
+        if (!mbar_wait(&empty_bar[grp], ((it / STAGES) & 1) ^ 1, err)) return;
+#pragma unroll
+        for (int i = 0; i < G_ITEMS; ++i) {
+          const int p = i * G_GROUP_THREADS + gt, w = p & 3, r = p >> 2;
+          const uint32_t x = cur[i];
+          uint4 lo, hi;
+          lo.x = x & 0x01010101u, lo.y = (x >> 1) & 0x01010101u, lo.z = (x >> 2) & 0x01010101u, lo.w = (x >> 3) & 0x01010101u;
+          hi.x = (x >> 4) & 0x01010101u, hi.y = (x >> 5) & 0x01010101u, hi.z = (x >> 6) & 0x01010101u, hi.w = (x >> 7) & 0x01010101u;
+          uint8_t* base = r < TILE_M ? a_st + (2 * w) * A_LBO + r * 16 : b_st + (2 * w) * B_LBO + (r - TILE_M) * 16;
+          const int lbo = r < TILE_M ? A_LBO : B_LBO;
+          *reinterpret_cast<uint4*>(base) = lo;
+          *reinterpret_cast<uint4*>(base + lbo) = hi;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[grp]);
+        // only now the loads of this group's next stage: nothing of them is in flight at the fence above,
+        // and they travel while the group waits for its slot to be consumed
+        if (ks + G_GROUPS < k_stages) fetch(m0, n0, (ks + G_GROUPS) * BLOCK_KW, cur);
+      }
+      if (!mbar_wait(&acc_full, tile_iter & 1, err)) return;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int q = warp & 3, cgrp = warp >> 2;
+      const int row = m0 + 32 * q + lane;
+#pragma unroll 1
+      for (int cblk = 0; cblk < G_COLS_PER_WARP / 32; ++cblk) {
+        const int col0 = cgrp * G_COLS_PER_WARP + cblk * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < B) {
+          int32_t* o = out + (long long)row * C + n0 + col0;
+          if ((C & 3) == 0 && n0 + col0 + 32 <= C) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<int4*>(o)[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + col0 + j < C) o[j] = (int)v[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty);
+    }
+  } else {
+    int it = 0, tile_iter = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+      if (tile_iter > 0) {
+        if (!mbar_wait(&acc_empty, (tile_iter - 1) & 1, err)) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      for (int ks = 0; ks < k_stages; ++ks, ++it) {
+        const int s = it % STAGES;
+        if (!mbar_wait(&full_bar[s], (it / STAGES) & 1, err)) goto done;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = a_addr + A_STAGE;
+#pragma unroll
+          for (int j = 0; j < BLOCK_KW; ++j) {
+            const uint64_t da = umma_desc(a_addr + 2 * j * A_LBO, A_LBO, SBO);
+            const uint64_t db = umma_desc(b_addr + 2 * j * B_LBO, B_LBO, SBO);
+            umma_i8(tmem_base, da, db, (ks | j) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (ks == k_stages - 1) umma_commit(&acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  done:;
+  }
+  __syncthreads();
+  if (warp == G_WARPS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
 // reference: AND + popcount, one thread per output
 __global__ void k_overlap_ref(const uint32_t* mask, int mask_stride, const uint32_t* inputs, int words, int B, int C, int32_t* out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -300,6 +456,7 @@ __global__ void k_overlap_ref(const uint32_t* mask, int mask_stride, const uint3
 
 int main(int argc, char** argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 1024, C = argc > 2 ? atoi(argv[2]) : 2048, I = argc > 3 ? atoi(argv[3]) : 1024;
+  const int variant = argc > 4 ? atoi(argv[4]) : 0;  // 0: validated kernel; 1: producer groups (not yet run)
   const int words = (I + 31) / 32, stride = (words + 3) & ~3;
   std::vector<uint32_t> h_mask((size_t)C * stride, 0), h_in((size_t)B * words, 0);
   uint64_t s = 0x9E3779B97F4A7C15ull;
@@ -332,12 +489,19 @@ int main(int argc, char** argv) {
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const int smem_bytes = STAGES * STAGE_BYTES + 1024;
   CK(cudaFuncSetAttribute(k_overlap_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  CK(cudaFuncSetAttribute(k_overlap_tcgen05_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles = ((B + TILE_M - 1) / TILE_M) * ((C + TILE_N - 1) / TILE_N);
-  const int grid = tiles < sms ? tiles : sms;
+  const int grid_dim = tiles < sms ? tiles : sms;
+  auto launch = [&]() {
+    if (variant == 1)
+      k_overlap_tcgen05_grouped<<<grid_dim, G_THREADS, smem_bytes>>>(d_mask, stride, d_in, words, B, C, d_out, d_err);
+    else
+      k_overlap_tcgen05<<<grid_dim, THREADS, smem_bytes>>>(d_mask, stride, d_in, words, B, C, d_out, d_err);
+  };
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  k_overlap_tcgen05<<<grid, THREADS, smem_bytes>>>(d_mask, stride, d_in, words, B, C, d_out, d_err);
+  launch();
   CK(cudaDeviceSynchronize());
   int h_err = 0;
   CK(cudaMemcpy(&h_err, d_err, 4, cudaMemcpyDeviceToHost));
@@ -360,14 +524,13 @@ int main(int argc, char** argv) {
   }
   const int reps = 20;
   CK(cudaEventRecord(e0));
-  for (int r = 0; r < reps; ++r)
-    k_overlap_tcgen05<<<grid, THREADS, smem_bytes>>>(d_mask, stride, d_in, words, B, C, d_out, d_err);
+  for (int r = 0; r < reps; ++r) launch();
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
   const double us = ms * 1e3 / reps;
-  printf("{\"workload\": \"%d inputs x %d columns x %d bits\", \"bit_identical\": true, \"us\": %.2f, \"int8_tops\": %.1f}\n", B, C,
-         I, us, 2.0 * B * C * (double)words * 32 / us / 1e6);
+  printf("{\"workload\": \"%d inputs x %d columns x %d bits\", \"variant\": %d, \"bit_identical\": true, \"us\": %.2f, \"int8_tops\": %.1f}\n", B, C,
+         I, variant, us, 2.0 * B * C * (double)words * 32 / us / 1e6);
   return 0;
 }
