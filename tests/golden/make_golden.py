@@ -44,7 +44,16 @@ CASES = {
     "cfg2": (1024, 2048, 32, None, 10000, 100, 0.2, 0.05, 0, 1000, 4),
     # every step draws its (learning, return_winner_cell) flags (networks.py:91) from `mode_schedule`
     "mixed": (64, 256, 8, 20, 1200, 12, 0.25, 0.05, 5, 100, 0),
+    # edge cases.  "edge" / "edge24": inputs from `degenerate_inputs` (empty, full and repeated inputs between
+    # ordinary ones; "edge" is the configuration of the GPU test test_degenerate_inputs_match_oracle, whose k = 12
+    # stays below the matching threshold 15, "edge24" lets segments match and learn); "c1": one cell per column;
+    # "k1": a single active column
+    "edge": (96, 320, 16, 12, 400, 0, 0.25, 0.0, 21, 100, 0),
+    "edge24": (96, 320, 16, 24, 800, 0, 0.25, 0.0, 22, 200, 0),
+    "c1": (64, 256, 1, 30, 800, 12, 0.25, 0.05, 4, 200, 0),
+    "k1": (64, 256, 8, 1, 600, 12, 0.25, 0.05, 6, 200, 0),
 }
+DEGENERATE = ("edge", "edge24")
 
 
 def mode_schedule(steps, seed):
@@ -66,6 +75,30 @@ def make_inputs(input_dim, patterns, density, noise, steps, seed):
     flips = g.random((steps, input_dim)) < noise
     idx = np.arange(steps) % patterns
     return base[idx] ^ flips
+
+
+def degenerate_inputs(input_dim, steps, density=0.25, seed=5):
+    """Every 8 steps: ..., empty input (all overlaps 0: the whole top-k is one tie), ..., full input, the
+    input before it once more.  Same recipe as tests/test_gpu_parity.py::test_degenerate_inputs_match_oracle."""
+    g = np.random.default_rng(seed)
+    xs = []
+    for t in range(steps):
+        r = t % 8
+        if r == 3:
+            xs.append(np.zeros(input_dim, dtype=bool))
+        elif r == 6:
+            xs.append(np.ones(input_dim, dtype=bool))
+        elif r == 7:
+            xs.append(xs[-2].copy())
+        else:
+            xs.append(g.random(input_dim) < density)
+    return np.array(xs)
+
+
+def case_inputs(name, input_dim, patterns, density, noise, steps, seed):
+    if name in DEGENERATE:
+        return degenerate_inputs(input_dim, steps, density)
+    return make_inputs(input_dim, patterns, density, noise, steps, seed)
 
 
 def reference_record(htm, sp_state, tm_state):
@@ -104,7 +137,7 @@ def run_case(name):
     import bithtm  # the reference
 
     I, C, c, k, steps, patterns, density, noise, seed, state_every, full_steps = CASES[name]
-    xs = make_inputs(I, patterns, density, noise, steps, seed)
+    xs = case_inputs(name, I, patterns, density, noise, steps, seed)
 
     np.random.seed(seed)
     k_eff = k if k is not None else round(C * 0.02)

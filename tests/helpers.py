@@ -29,7 +29,27 @@ def make_inputs(input_dim, patterns, density, noise, steps, seed):
     return base[idx] ^ flips
 
 
+def degenerate_inputs(input_dim, steps, density=0.25, seed=5):
+    """Same recipe as tests/golden/make_golden.py::degenerate_inputs: every 8 steps an empty input,
+    a full input and a repeated input between ordinary ones."""
+    g = np.random.default_rng(seed)
+    xs = []
+    for t in range(steps):
+        r = t % 8
+        if r == 3:
+            xs.append(np.zeros(input_dim, dtype=bool))
+        elif r == 6:
+            xs.append(np.ones(input_dim, dtype=bool))
+        elif r == 7:
+            xs.append(xs[-2].copy())
+        else:
+            xs.append(g.random(input_dim) < density)
+    return np.array(xs)
+
+
 def golden_inputs(info, steps=None):
+    if info["patterns"] == 0:  # the degenerate-input traces ("edge", "edge24")
+        return degenerate_inputs(info["I"], info["steps"], info["density"])[:steps]
     return make_inputs(info["I"], info["patterns"], info["density"], info["noise"],
                        info["steps"], info["seed"])[:steps]
 

@@ -16,10 +16,12 @@ from oracle.htm_oracle import HTMOracle, OracleConfig, canonical_topk
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name,steps", [("tiny", None), ("odd", None), ("mid", 1500), ("cfg1", 400), ("cfg2", 400)])
+@pytest.mark.parametrize("name,steps", [("tiny", None), ("odd", None), ("mid", 1500), ("cfg1", 400), ("cfg2", 400),
+                                        ("edge", None), ("edge24", None), ("c1", None), ("k1", None)])
 def test_oracle_matches_reference_golden(name, steps):
     """Per-step digests and learned-state digests recorded from cokwa/bitHTM
-    (tests/golden/make_golden.py) are reproduced by the oracle."""
+    (tests/golden/make_golden.py) are reproduced by the oracle.  "edge" / "edge24": empty, full and
+    repeated inputs (whole top-k tied at overlap 0); "c1": one cell per column; "k1": one active column."""
     info = load_golden(name)
     g = info["g"]
     steps = info["steps"] if steps is None else steps
