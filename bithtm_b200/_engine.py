@@ -64,7 +64,7 @@ class Engine:
         I, Ccol, c, k = int(input_dim), int(column_dim), int(cell_dim), int(active_columns)
         N = Ccol * c
         sm, major, minor = C.c_int(0), C.c_int(0), C.c_int(0)
-        nat.check(nat.lib.bh_device_info(self.device.index or 0, C.byref(sm), C.byref(major), C.byref(minor)),
+        nat.check(nat.lib.bh_device_info(self._dev_index, C.byref(sm), C.byref(major), C.byref(minor)),
                   "bh_device_info")
         self.sm_count = sm.value
         if max_segments is None:
@@ -79,6 +79,7 @@ class Engine:
         if tm_blocks is None:
             tm_blocks = self.sm_count if max_segments <= (1 << 20) else min(1024, self.sm_count * 6)
         ctx = nat.BhCtx()
+        ctx.device = self._dev_index  # the library makes it current around every call
         ctx.input_dim, ctx.input_words = I, (I + 31) // 32
         ctx.mask_stride = _round_up(ctx.input_words, 4)
         ctx.column_dim, ctx.cell_dim, ctx.active_columns = Ccol, c, k
@@ -130,13 +131,17 @@ class Engine:
                 f"{k} active columns draw about {typical // 2:,} random numbers per timestep (rand(L, W+1), "
                 "projections.py:120, is quadratic in the number of active columns); the device stream ring is limited "
                 "to 2^31 words. Pass rand_capacity= to bound the draws per step explicitly (see DESIGN.md, cfg5).")
+        # whole step as one kernel: on one thread-block cluster while the step is
+        # latency-bound (mask <= 8 MiB), else on a cooperative grid with one CTA per SM.  The cluster
+        # kernel has no many-CTA stream production phase: a network that draws enough words per step to
+        # want it runs on the grid, and an explicit fused="cluster" produces the stream on one CTA.
+        if fused == "auto":
+            fused = "cluster" if Ccol * ctx.mask_stride * 4 <= (8 << 20) and not parallel_rng else "grid"
+        if fused == "cluster":
+            parallel_rng = False
         ctx.rng_ring_words, ctx.rng_step_words, ctx.ring_len = ring_words, step_words, int(ring_len)
         ctx.jump_polys = (step_words + step_words // 2) // _mtjump.CHUNK_WORDS + 3 if parallel_rng else 0
         ctx.rng_lookahead = min(2 * (k * c + 4 * k) + 2 * nat.MT_N, step_words // 2) if parallel_rng else 0
-        # whole step as one kernel: on one thread-block cluster while the step is
-        # latency-bound (mask <= 8 MiB), else on a cooperative grid with one CTA per SM
-        if fused == "auto":
-            fused = "cluster" if Ccol * ctx.mask_stride * 4 <= (8 << 20) else "grid"
         ctx.fused_mode = {"off": 0, "cluster": 1, "grid": 2, "shard": 3}[fused]
         if fused_ctas is None:
             fused_ctas = 16 if fused == "cluster" else self.sm_count
@@ -188,6 +193,11 @@ class Engine:
             self.xch_send = torch.zeros(n, dtype=torch.int32, device=self.device)
             self.xch_recv = torch.zeros(n * self.seg_world, dtype=torch.int32, device=self.device)
         self.tm_deferred = False  # the last step left a deferred jitter draw / no winner cells (networks.py)
+        # stand-alone PredictiveProjection calls take arbitrary cell lists, so the sparse clean-up the fused
+        # phases do (by active column) cannot be relied on afterwards: countdown of full clears, see
+        # begin_regular_step
+        self.standalone_dirty = 0
+        self._dirty_seen = -1
         self.epoch = 0  # bumped by every completed step; lazily fetched State fields check it
         self._graphs = {}
         self.host_graph = True  # bh_step_host as one CUDA graph launch (constants are frozen at capture)
@@ -327,6 +337,83 @@ class Engine:
         out = torch.empty(max(count, 1), dtype=torch.float64, device=self.device)
         nat.check(nat.lib.bh_rng_fill(self.ref, out.data_ptr(), int(count), self.stream), "bh_rng_fill")
         return out[:count].cpu().numpy()
+
+    def begin_regular_step(self):
+        """Called at the start of every timestep driven through the network classes.  After stand-alone
+        projection calls: step 1 clears the per-column winner words and active flags, step 2 the activation
+        buffer that was filled by the stand-alone call (it is this step's, and must start empty)."""
+        if not self.standalone_dirty or self._dirty_seen == self.epoch:
+            return
+        self._dirty_seen = self.epoch
+        if self.standalone_dirty == 2:
+            self.buf["col_win"].zero_()
+            self.buf["col_active"].zero_()
+        else:
+            half = self.epoch & 1
+            self.buf["col_act"][half * self.C:(half + 1) * self.C].zero_()
+        self.standalone_dirty -= 1
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    _SNAPSHOT = ("sp_perm", "sp_mask", "duty", "overlaps", "boosted", "active_cols", "col_active", "col_pred",
+                 "col_act", "col_win", "cell_nseg", "cell_maxjit", "cell_npred", "cell_widx", "seg_owner",
+                 "seg_count", "seg_pot", "seg_conn", "syn_cell", "syn_perm", "row_pred", "row_act", "row_win",
+                 "row_unacc", "winners", "unacc", "m_seg", "m_conn", "m_jit", "m_flag", "learn_list",
+                 "punish_list", "recyc_list")
+
+    def snapshot(self):
+        """Everything a resumed run needs, as host tensors: the learned state, the previous timestep's
+        context, the scalars and the MT19937 state at the stream cursor."""
+        torch = _torch()
+        torch.cuda.synchronize(self.device)
+        S = int(self.scalars()[nat.SC_NSEG])
+        E = self.ctx.syn_capacity
+        rows = len(self.held_segment_ids(S))
+        out = {"shape": (self.I, self.C, self.c, self.k, self.shard_rank, self.shard_world, self.seg_rank,
+                         self.seg_world), "n_segments": S}
+        for name in self._SNAPSHOT:
+            t = self.buf[name]
+            if name in ("seg_owner", "seg_count", "seg_pot", "seg_conn"):
+                t = t[:S]
+            elif name in ("syn_cell", "syn_perm"):
+                t = t[:rows * E].view(rows, E)
+            out[name] = t.cpu().clone()
+        sc = self.buf["sc"].cpu().clone()
+        sc[nat.SC_BAR_COUNT] = 0
+        out["sc"] = sc
+        out["rng"] = self.get_rng_state()
+        out["epoch"], out["tm_deferred"] = self.epoch, self.tm_deferred
+        return out
+
+    def restore(self, snap):
+        """Inverse of :meth:`snapshot` on an engine of the same shape (capacities may differ)."""
+        torch = _torch()
+        shape = (self.I, self.C, self.c, self.k, self.shard_rank, self.shard_world, self.seg_rank, self.seg_world)
+        if tuple(snap["shape"]) != shape:
+            raise ValueError(f"snapshot of a {tuple(snap['shape'])} network cannot be loaded into {shape}")
+        S, E = int(snap["n_segments"]), self.ctx.syn_capacity
+        if S > self.ctx.seg_capacity or (S > 0 and int(snap["seg_count"].max()) > E):
+            raise nat.NativeError("snapshot holds more segments / synapses per segment than this network's capacity")
+        for name in self._SNAPSHOT:
+            src, dst = snap[name], self.buf[name]
+            if name in ("syn_cell", "syn_perm"):
+                rows, w = src.shape[0], min(src.shape[1], E)
+                dst.zero_()
+                dst[:rows * E].view(rows, E)[:, :w].copy_(src[:, :w].to(self.device))
+            elif name in ("m_seg", "m_conn", "m_jit", "m_flag", "learn_list", "punish_list"):
+                n = min(src.numel(), dst.numel())  # list capacities follow max_segments
+                dst[:n].copy_(src[:n].to(self.device))
+            else:
+                dst.zero_()
+                dst[:src.numel()].copy_(src.reshape(-1).to(self.device))
+        keep = self.buf["sc"].cpu()
+        sc = snap["sc"].clone()
+        for i in (nat.SC_BAR_COUNT, nat.SC_BAR_GEN, nat.SC_INPUT_POS):
+            sc[i] = keep[i]
+        self.buf["sc"].copy_(sc.to(self.device))
+        key, pos = snap["rng"]
+        self.set_rng_state(key, pos)
+        self.epoch, self.tm_deferred = int(snap["epoch"]), bool(snap["tm_deferred"])
+        self._graphs_epoch = None
 
     # ------------------------------------------------------------------ steps
     def step_device(self, words, learning=True):

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BITHTM_B200_LIB") or os.path.join(_HERE, "_lib", "libbithtm_b200.so")  # env: A/B builds
 
 MT_N = 624
-ABI_VERSION = 8
+ABI_VERSION = 9
 R_COUNT = 16  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)
@@ -61,7 +61,7 @@ class BhCtx(C.Structure):
         ("rng_ring_words", C.c_int64), ("rng_step_words", C.c_int64), ("col_lo", C.c_int32), ("col_local", C.c_int32),
         ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
         ("seg_rank", C.c_int32), ("seg_world", C.c_int32), ("xm_cap", C.c_int32), ("xr_cap", C.c_int32),
-        ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32),
+        ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32),
         ("sp_threshold", C.c_double), ("sp_delta_on", C.c_double), ("sp_delta_off", C.c_double),
         ("tm_learn_on", C.c_double), ("tm_learn_off", C.c_double),
         ("tm_punish_on", C.c_double), ("tm_punish_off", C.c_double),
@@ -134,6 +134,10 @@ _SIGNATURES = {
     "bh_tm_activate": (C.c_int, [_CTXP, _P]),
     "bh_tm_step": (C.c_int, [_CTXP, C.c_int, _P]),
     "bh_tm_step_ex": (C.c_int, [_CTXP, C.c_int, C.c_int, C.c_int, _P]),
+    "bh_tm_learn_args": (C.c_int, [_CTXP, _P, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "bh_tm_activate_cells": (C.c_int, [_CTXP, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "bh_tm_fill_jitter": (C.c_int, [_CTXP, _P]),
+    "bh_tm_reset": (C.c_int, [_CTXP, _P]),
     "bh_step": (C.c_int, [_CTXP, _P, C.c_int, _P]),
     "bh_step_ring": (C.c_int, [_CTXP, C.c_int, _P]),
     "bh_step_host": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),

@@ -38,6 +38,26 @@ static thread_local ProfileRec* g_prof = nullptr;
   } while (0)
 #define LAUNCH_CHECK() LAUNCHED("misc")
 
+// Every entry point makes ctx->device current for the duration of the call (kernel launches and
+// function attributes apply to the CURRENT device, whatever stream is passed) and restores the caller's.
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(const bh_ctx* x) {
+    if (x && x->device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != x->device)
+      switched = cudaSetDevice(x->device) == cudaSuccess;
+  }
+  ~DevGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define BH_MAX_DEVICES 64
+static inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= BH_MAX_DEVICES) d = 0;
+  return d;
+}
+
 static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -146,6 +166,8 @@ static int check_ctx(const bh_ctx* x) {
   if (x->jump_polys > 0 && (long long)x->jump_polys * RNG_CHUNK < x->rng_step_words + x->rng_step_words / 2 + RNG_CHUNK)
     return BH_E_BADARG;
   if (x->jump_polys < 0 || x->rng_lookahead < 0) return BH_E_BADARG;
+  // the cluster kernel has no phase for the chunks a many-CTA production plan leaves (fused.cuh)
+  if (x->fused_mode == 1 && x->jump_polys > 0) return BH_E_UNSUPPORTED;
   if (x->seg_world > 1) {
     if (x->seg_rank < 0 || x->seg_rank >= x->seg_world || x->xm_cap < 1 || x->xr_cap < 1) return BH_E_BADARG;
     if (x->fused_mode && x->fused_mode != 3) return BH_E_UNSUPPORTED;  // the exchange sits between kernels
@@ -173,6 +195,7 @@ __global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
 }
 
 extern "C" int bh_init(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   long long N = (long long)x->column_dim * 32;
@@ -199,6 +222,7 @@ static int sp_grid(const bh_ctx* x, int rows_per_block) {
 }
 
 extern "C" int bh_sp_build_mask(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   long long words = (long long)x->col_local * x->mask_stride;
@@ -210,6 +234,7 @@ extern "C" int bh_sp_build_mask(const bh_ctx* x, void* stream) {
 }
 
 extern "C" int bh_pack_input(const bh_ctx* x, const uint8_t* bool_dev, uint32_t* words_dev, void* stream) {
+  DevGuard dev_guard_(x);
   k_pack_input<<<cdiv((long long)x->input_words * 32, 256), 256, 0, S_(stream)>>>(*x, bool_dev, words_dev);
   LAUNCH_CHECK();
   return 0;
@@ -226,11 +251,13 @@ static int launch_overlap(const bh_ctx* x, const uint32_t* in, cudaStream_t st) 
 }
 
 extern "C" int bh_sp_overlap(const bh_ctx* x, const uint32_t* in, void* stream) {
+  DevGuard dev_guard_(x);
   return launch_overlap<false>(x, in, S_(stream));
 }
 
 extern "C" int bh_sp_overlap_batched(const bh_ctx* x, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
                                      void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (!inputs_dev || !overlaps_out || n_inputs < 0) return BH_E_BADARG;
@@ -244,6 +271,7 @@ extern "C" int bh_sp_overlap_batched(const bh_ctx* x, const uint32_t* inputs_dev
 
 extern "C" int bh_sp_overlap_batched_tc(const bh_ctx* x, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
                                         void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (!inputs_dev || !overlaps_out || n_inputs < 0) return BH_E_BADARG;
@@ -257,6 +285,7 @@ extern "C" int bh_sp_overlap_batched_tc(const bh_ctx* x, const uint32_t* inputs_
 }
 
 extern "C" int bh_boost(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   k_boost<<<cdiv(x->col_local, 256), 256, 0, S_(stream)>>>(*x);
   LAUNCH_CHECK();
   return 0;
@@ -282,6 +311,7 @@ static int launch_coop(void (*kern)(const bh_ctx, Args...), const bh_ctx* x, cud
 #define BH_TOPK_MULTI_MIN 16384  // columns from which the grid-wide top-k pays for its barriers
 
 extern "C" int bh_inhibit(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   if (x->column_dim >= BH_TOPK_MULTI_MIN) {
     int rc = launch_coop(k_topk_multi, x, S_(stream));
     if (rc) return rc;
@@ -294,12 +324,14 @@ extern "C" int bh_inhibit(const bh_ctx* x, void* stream) {
 }
 
 extern "C" int bh_set_active_columns(const bh_ctx* x, const int32_t* cols_dev, void* stream) {
+  DevGuard dev_guard_(x);
   k_set_active<<<1, 1024, 0, S_(stream)>>>(*x, cols_dev);
   LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int bh_sp_learn(const bh_ctx* x, const uint32_t* in, void* stream) {
+  DevGuard dev_guard_(x);
   int cap = (x->sm_count > 0 ? x->sm_count : 148) * 8;
   int grid = x->active_columns < cap ? x->active_columns : cap;
   k_sp_learn<<<grid, SP_THREADS, 0, S_(stream)>>>(*x, in);
@@ -308,6 +340,7 @@ extern "C" int bh_sp_learn(const bh_ctx* x, const uint32_t* in, void* stream) {
 }
 
 extern "C" int bh_duty_update(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   k_duty_update<<<cdiv(x->col_local, 256), 256, 0, S_(stream)>>>(*x);
   LAUNCHED("duty_update");
   return 0;
@@ -324,6 +357,7 @@ static int sp_step(const bh_ctx* x, const uint32_t* in, int learning, cudaStream
 // ---- column shard: exchange 1 (top-k candidates) ---------------------------------------
 extern "C" int bh_sp_shard_local(const bh_ctx* x, const uint32_t* in, double* cand_keys, int32_t* cand_cols,
                                  void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (!cand_keys || !cand_cols) return BH_E_BADARG;
@@ -343,6 +377,7 @@ extern "C" int bh_sp_shard_local(const bh_ctx* x, const uint32_t* in, double* ca
 
 extern "C" int bh_sp_shard_finish(const bh_ctx* x, const uint32_t* in, const double* cand_keys,
                                   const int32_t* cand_cols, int n, int learning, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (!cand_keys || !cand_cols || n < x->active_columns) return BH_E_BADARG;
@@ -354,6 +389,7 @@ extern "C" int bh_sp_shard_finish(const bh_ctx* x, const uint32_t* in, const dou
 }
 
 extern "C" int bh_sp_step(const bh_ctx* x, const uint32_t* in, int learning, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   return sp_step(x, in, learning, S_(stream));
@@ -362,6 +398,7 @@ extern "C" int bh_sp_step(const bh_ctx* x, const uint32_t* in, int learning, voi
 __global__ void k_advance_step(const __grid_constant__ bh_ctx c) { c.sc[BH_SC_STEP] = c.sc[BH_SC_STEP] + 1; }
 
 extern "C" int bh_advance_step(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   k_advance_step<<<1, 1, 0, S_(stream)>>>(*x);
   LAUNCH_CHECK();
   return 0;
@@ -386,23 +423,29 @@ static int tm_select(const bh_ctx* x, int want, cudaStream_t st) {
   return 0;
 }
 
-extern "C" int bh_tm_select(const bh_ctx* x, void* stream) { return tm_select(x, 1, S_(stream)); }
+extern "C" int bh_tm_select(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
+  return tm_select(x, 1, S_(stream));
+}
 
 static int learn_apply_smem(const bh_ctx* x) {
   long long bits = (long long)x->active_columns * x->cell_dim;
   return (int)(((bits + 31) / 32) * 4);
 }
 
+// function attributes are per device: remembered per device ordinal of the calling thread's current device
 static int prepare_chunks() {
-  static bool done = false;
-  if (!done) {
+  static bool done[BH_MAX_DEVICES] = {};
+  const int d = current_device_slot();
+  if (!done[d]) {
     CU_RET(cudaFuncSetAttribute(k_rng_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, RNG_CHUNK_SMEM));
-    done = true;
+    done[d] = true;
   }
   return 0;
 }
 
 extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
+  DevGuard dev_guard_(x);
   cudaStream_t st = S_(stream);
   k_tm_learn_select_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, learning);
   LAUNCHED("tm_learn_select_a");
@@ -430,6 +473,7 @@ extern "C" int bh_tm_learn(const bh_ctx* x, int learning, void* stream) {
 }
 
 extern "C" int bh_tm_activate(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   if (x->seg_world > 1) return BH_E_UNSUPPORTED;  // use bh_tm_shard_pre / bh_tm_shard_post
   cudaStream_t st = S_(stream);
   int k = x->active_columns, kc = k * x->cell_dim;
@@ -444,7 +488,79 @@ extern "C" int bh_tm_activate(const bh_ctx* x, void* stream) {
   return 0;
 }
 
+// ---- stand-alone plugin calls with explicit arguments -----------------------------------
+extern "C" int bh_tm_reset(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  k_tm_reset<<<1, 1024, 0, S_(stream)>>>(*x);
+  LAUNCHED("tm_reset");
+  return 0;
+}
+
+extern "C" int bh_tm_fill_jitter(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  k_tm_fill_jitter<<<1, MT_THREADS, 0, S_(stream)>>>(*x);
+  LAUNCHED("tm_fill_jitter");
+  return 0;
+}
+
+extern "C" int bh_tm_learn_args(const bh_ctx* x, const int32_t* winner_cells_dev, int n_winners,
+                                const int32_t* prev_winner_cells_dev, int n_prev_winners,
+                                const uint32_t* prev_activation_words_dev, const uint8_t* column_active_dev,
+                                void* stream) {
+  DevGuard dev_guard_(x);
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  const int kc = x->active_columns * x->cell_dim;
+  if (x->seg_world > 1 || n_winners < 0 || n_winners > kc || n_prev_winners > kc || !prev_activation_words_dev ||
+      !column_active_dev || (n_winners > 0 && !winner_cells_dev) || (n_prev_winners > 0 && !prev_winner_cells_dev))
+    return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  k_tm_fill_jitter<<<1, MT_THREADS, 0, st>>>(*x);  // get_jittered_potential_info(prev_state), projections.py:263
+  LAUNCHED("tm_fill_jitter");
+  const int cap = (x->sm_count > 0 ? x->sm_count : 148) * 8;
+  const int grid = cdiv((long long)x->column_dim * 32, 256);
+  k_tm_adopt_words<<<grid < cap ? grid : cap, 256, 0, st>>>(*x, prev_activation_words_dev, column_active_dev);
+  LAUNCHED("tm_adopt_words");
+  k_tm_adopt_lists<<<1, 1024, 0, st>>>(*x, winner_cells_dev, n_winners, prev_winner_cells_dev, n_prev_winners);
+  LAUNCHED("tm_adopt_lists");
+  return bh_tm_learn(x, 1, stream);
+}
+
+extern "C" int bh_tm_activate_cells(const bh_ctx* x, const int32_t* active_cells_dev, int n_active, int want_jitter,
+                                    int have_winners, void* stream) {
+  DevGuard dev_guard_(x);
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (x->seg_world > 1 || n_active < 0 || (n_active > 0 && !active_cells_dev)) return BH_E_BADARG;
+  cudaStream_t st = S_(stream);
+  const int cap = (x->sm_count > 0 ? x->sm_count : 148) * 8;
+  const int grid = cdiv(2LL * x->column_dim, 256);
+  k_tm_adopt_active_clear<<<grid < cap ? grid : cap, 256, 0, st>>>(*x, have_winners);
+  LAUNCHED("tm_adopt_active_clear");
+  if (n_active > 0) {
+    const int g2 = cdiv(n_active, 256);
+    k_tm_adopt_active_set<<<g2 < cap ? g2 : cap, 256, 0, st>>>(*x, active_cells_dev, n_active);
+    LAUNCHED("tm_adopt_active_set");
+  }
+  k_tm_adopt_widx<<<1, 1024, 0, st>>>(*x);
+  LAUNCHED("tm_adopt_widx");
+  k_tm_activate_a<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  LAUNCHED("tm_activate_a");
+  if (want_jitter) {
+    k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 3, 1);
+    LAUNCHED("tm_draw3");
+  }
+  k_tm_activate_b<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, want_jitter ? 1 : 0);
+  LAUNCHED("tm_activate_b");
+  return 0;
+}
+
 extern "C" int bh_tm_step_ex(const bh_ctx* x, int learning, int want_winner, int want_jitter, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (x->seg_world > 1) return BH_E_UNSUPPORTED;
@@ -472,6 +588,7 @@ static int tm_post_and_scan(const bh_ctx* x, cudaStream_t st) {
 }
 
 extern "C" int bh_tm_shard_pre(const bh_ctx* x, int learning, int32_t* send_dev, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (x->seg_world <= 1 || !send_dev) return BH_E_BADARG;
@@ -485,6 +602,7 @@ extern "C" int bh_tm_shard_pre(const bh_ctx* x, int learning, int32_t* send_dev,
 }
 
 extern "C" int bh_tm_shard_post(const bh_ctx* x, const int32_t* recv_dev, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (x->seg_world <= 1 || !recv_dev) return BH_E_BADARG;
@@ -499,6 +617,7 @@ extern "C" int bh_tm_shard_post(const bh_ctx* x, const int32_t* recv_dev, void* 
 }
 
 extern "C" int bh_tm_step(const bh_ctx* x, int learning, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if ((rc = bh_tm_select(x, stream))) return rc;
@@ -516,10 +635,11 @@ static int fused_smem(const bh_ctx* x) {
   return m;
 }
 
-// One-time function attributes (per process): non-portable cluster sizes, dynamic smem.
+// One-time function attributes (per device): non-portable cluster sizes, dynamic smem.
 static int prepare_fused(int mode) {
-  static bool done[4] = {false, false, false, false};
+  static bool done_all[BH_MAX_DEVICES][4] = {};
   if (mode < 1 || mode > 3) return BH_E_BADARG;
+  bool* done = done_all[current_device_slot()];
   if (done[mode]) return 0;
   if (mode == 1) {
     CU_RET(cudaFuncSetAttribute(k_step_fused<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -580,6 +700,7 @@ static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_step
 }
 
 extern "C" int bh_step(const bh_ctx* x, const uint32_t* in, int learning, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (x->fused_mode) return launch_fused(x, in, 1, learning, 0, S_(stream));
@@ -590,6 +711,7 @@ extern "C" int bh_step(const bh_ctx* x, const uint32_t* in, int learning, void* 
 }
 
 extern "C" int bh_step_launches(const bh_ctx* x, int learning) {
+  DevGuard dev_guard_(x);
   if (x && x->fused_mode) return 1;
   // overlap+boost, topk, [sp_learn], duty | draw1, select a/b | learn-select a/b, draw2, [chunks], [apply] |
   // post, activate a, draw3, activate b
@@ -606,6 +728,7 @@ __global__ void k_ring_fetch(const __grid_constant__ bh_ctx c) {
 }
 
 extern "C" int bh_step_ring(const bh_ctx* x, int learning, void* stream) {
+  DevGuard dev_guard_(x);
   if (!x || x->ring_len <= 0) return BH_E_BADARG;
   if (x->fused_mode) {
     int rc = check_ctx(x);
@@ -646,6 +769,7 @@ static int step_host_enqueue(const bh_ctx* x, int learning, cudaStream_t st) {
 }
 
 extern "C" int bh_host_graph_create(const bh_ctx* x, int learning, void* stream, void** out) {
+  DevGuard dev_guard_(x);
   if (!out) return BH_E_BADARG;
   int rc = check_ctx(x);
   if (rc) return rc;
@@ -678,6 +802,7 @@ extern "C" int bh_host_graph_create(const bh_ctx* x, int learning, void* stream,
 
 extern "C" int bh_step_host_graph(const bh_ctx* x, void* graph_exec, const uint8_t* input_bool_host,
                                   int32_t* summary_host, void* stream) {
+  DevGuard dev_guard_(x);
   if (!x || !graph_exec || !input_bool_host) return BH_E_BADARG;
   cudaStream_t st = S_(stream);
   pack_host(x, input_bool_host);
@@ -700,6 +825,7 @@ extern "C" int bh_step_host_graph(const bh_ctx* x, void* graph_exec, const uint8
 
 extern "C" int bh_step_host(const bh_ctx* x, const uint8_t* input_bool_host, int learning, int32_t* summary_host,
                             void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   if (!input_bool_host || !x->input_pinned || !x->summary_pinned) return BH_E_BADARG;
@@ -712,6 +838,7 @@ extern "C" int bh_step_host(const bh_ctx* x, const uint8_t* input_bool_host, int
 }
 
 extern "C" int bh_summary(const bh_ctx* x, int32_t* summary_host, void* stream) {
+  DevGuard dev_guard_(x);
   if (!x || !x->summary_pinned) return BH_E_BADARG;
   cudaStream_t st = S_(stream);
   int k = x->active_columns;
@@ -728,6 +855,7 @@ extern "C" int bh_summary(const bh_ctx* x, int32_t* summary_host, void* stream) 
 // One step with a CUDA event after every launch; per-launch milliseconds and names.
 extern "C" int bh_profile_step(const bh_ctx* x, const uint32_t* in, int learning, void* stream, float* ms_out,
                                const char** names_out, int max_out) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   ProfileRec rec;
@@ -756,6 +884,7 @@ extern "C" int bh_profile_step(const bh_ctx* x, const uint32_t* in, int learning
 // CUDA graphs over bh_step_ring
 // ------------------------------------------------------------------------------------
 extern "C" int bh_graph_create(const bh_ctx* x, int steps_per_graph, int learning, void* stream, void** out) {
+  DevGuard dev_guard_(x);
   if (!out || steps_per_graph < 1) return BH_E_BADARG;
   int rc = check_ctx(x);
   if (rc) return rc;
@@ -787,7 +916,9 @@ extern "C" int bh_graph_create(const bh_ctx* x, int steps_per_graph, int learnin
 extern "C" int bh_batch_graph_create(const bh_ctx* const* ctxs, int n, int steps_per_graph, int learning,
                                      void* stream, void** out) {
   if (!out || !ctxs || n < 1 || steps_per_graph < 1) return BH_E_BADARG;
+  DevGuard dev_guard_(ctxs[0]);
   for (int i = 0; i < n; ++i) {
+    if (ctxs[i] && ctxs[i]->device != ctxs[0]->device) return BH_E_BADARG;  // one graph, one device
     int rc = check_ctx(ctxs[i]);
     if (rc) return rc;
     if (!ctxs[i]->fused_mode || ctxs[i]->ring_len <= 0) return BH_E_UNSUPPORTED;
@@ -846,6 +977,7 @@ extern "C" int bh_graph_destroy(void* graph_exec) {
 // randomness + test hooks
 // ------------------------------------------------------------------------------------
 extern "C" int bh_rng_import(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   k_rng_import<<<1, 256, 0, S_(stream)>>>(*x);
@@ -854,6 +986,7 @@ extern "C" int bh_rng_import(const bh_ctx* x, void* stream) {
 }
 
 extern "C" int bh_rng_export(const bh_ctx* x, void* stream) {
+  DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
   k_rng_export<<<1, 256, 0, S_(stream)>>>(*x);
@@ -862,6 +995,7 @@ extern "C" int bh_rng_export(const bh_ctx* x, void* stream) {
 }
 
 extern "C" int bh_rng_fill(const bh_ctx* x, double* dst_dev, int64_t count, void* stream) {
+  DevGuard dev_guard_(x);
   if (!x || !dst_dev || count < 0 || 2 * count > x->rng_step_words) return BH_E_BADARG;
   cudaStream_t st = S_(stream);
   k_rng_fill_draw<<<1, MT_THREADS, 0, st>>>(*x, (long long)count);

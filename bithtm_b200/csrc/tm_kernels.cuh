@@ -811,6 +811,156 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_b(const __grid_co
   ph_activate_b(c, blockIdx.x, gridDim.x, false, want_jitter != 0);
 }
 
+// ---------------------------------------------------------------------------------
+// Stand-alone plugin calls (PredictiveProjection.update / .process with explicit
+// arguments, projections.py:245-293) and TemporalMemory.process(prev_state=empty
+// state): adopt the caller's lists into the device buffers the phases read.
+// ---------------------------------------------------------------------------------
+// Forget the previous timestep's context (networks.py:59-65, the empty state): no
+// previous predictions, activation, winner cells or distal state.  Learned state
+// (segments, synapses, segments per cell, SP) is untouched.  One CTA.
+__global__ void __launch_bounds__(1024) k_tm_reset(const __grid_constant__ bh_ctx c) {
+  const int k = c.active_columns, cd = c.cell_dim;
+  const int last = (c.sc[BH_SC_STEP] & 1) ^ 1;  // buffers of the last completed step
+  const int M = c.sc[BH_SC_M];
+#pragma unroll 1
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const int owner = c.seg_owner[c.m_seg[j]];
+    c.cell_maxjit[owner] = 0.0f;
+    c.cell_npred[owner] = 0;
+    c.col_pred[owner >> 5] = 0u;
+  }
+  const int Wl = c.sc[BH_SC_W0 + last];
+  const int* wl = c.winners + (long long)last * k * cd;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < Wl; i += blockDim.x) c.cell_widx[wl[i]] = -1;
+  if (c.sc[BH_SC_HAVE_PREV]) {
+    const int* cols = c.active_cols + last * k;
+    uint32_t* act = c.col_act + (long long)last * c.column_dim;
+#pragma unroll 1
+    for (int r = threadIdx.x; r < k; r += blockDim.x) {
+      act[cols[r]] = 0u;
+      c.col_win[cols[r]] = 0u;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c.sc[BH_SC_HAVE_PREV] = 0;
+    c.sc[BH_SC_M] = 0;
+    c.sc[BH_SC_W0] = 0;
+    c.sc[BH_SC_W1] = 0;
+    c.sc[BH_SC_WNONE0] = 1;
+    c.sc[BH_SC_WNONE1] = 1;
+    c.sc[BH_SC_JIT_PENDING] = 0;
+    c.sc[BH_SC_NU] = 0;
+  }
+}
+
+// PredictiveProjection.update's arguments (projections.py:257): learning_output = ordered winner cells,
+// winner_input = ordered previous winner cells (n_prev < 0: None), input_activation as one bit-word per
+// column, output_punishment as its per-column complement (1 = the column is active, not punished).
+// Grid-stride part (any grid): clear-and-set of the per-column words.  The ordered lists follow in
+// k_tm_adopt_lists (one CTA).
+__global__ void k_tm_adopt_words(const __grid_constant__ bh_ctx c, const uint32_t* prev_act_words,
+                                 const uint8_t* col_active) {
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  uint32_t* prev_act = c.col_act + (long long)(cur ^ 1) * c.column_dim;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+#pragma unroll 1
+  for (long long j = gid; j < c.column_dim; j += gsz) {
+    prev_act[j] = prev_act_words[j];
+    c.col_active[j] = col_active[j];
+    c.col_win[j] = 0u;
+  }
+#pragma unroll 1
+  for (long long j = gid; j < (long long)c.column_dim * 32; j += gsz) c.cell_widx[j] = -1;
+}
+
+__global__ void __launch_bounds__(1024) k_tm_adopt_lists(const __grid_constant__ bh_ctx c, const int* win_cells, int n_win,
+                                                         const int* prev_win, int n_prev) {
+  __shared__ int s_red[32];
+  const int k = c.active_columns, cd = c.cell_dim;
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const bool have_prev = c.sc[BH_SC_HAVE_PREV] != 0;
+  int* wl = c.winners + (long long)cur * k * cd;
+  int* wp = c.winners + (long long)(cur ^ 1) * k * cd;
+  int base = 0;
+#pragma unroll 1
+  for (int tile = 0; tile < n_win; tile += blockDim.x) {
+    const int i = tile + threadIdx.x;
+    const bool ok = i < n_win;
+    const int cell = ok ? win_cells[i] : 0;
+    if (ok) {
+      wl[i] = cell;
+      atomicOr(&c.col_win[cell >> 5], 1u << (cell & 31));
+    }
+    const bool un = ok && have_prev && c.cell_maxjit[cell] < c.epsilon;  // projections.py:271
+    int tot;
+    const int pos = base + block_excl_scan(un ? 1 : 0, s_red, tot);
+    if (un) c.unacc[pos] = cell;
+    base += tot;
+  }
+#pragma unroll 1
+  for (int i = threadIdx.x; i < n_prev; i += blockDim.x) {
+    wp[i] = prev_win[i];
+    c.cell_widx[prev_win[i]] = i;
+  }
+  if (threadIdx.x == 0) {
+    c.sc[BH_SC_W0 + cur] = n_win;
+    c.sc[BH_SC_WNONE0 + cur] = 0;
+    c.sc[BH_SC_W0 + (cur ^ 1)] = n_prev > 0 ? n_prev : 0;
+    c.sc[BH_SC_WNONE0 + (cur ^ 1)] = n_prev < 0 ? 1 : 0;
+    c.sc[BH_SC_NU] = base;
+    c.rng64[R_STEP_BASE] = c.rng64[R_CURSOR];  // a stand-alone call starts its own draw budget
+  }
+}
+
+// PredictiveProjection.process's argument (projections.py:245): the active cells as this step's
+// activation words.  Also what k_tm_post would have done for a stand-alone call: reset the per-cell
+// results of the previous activation (idempotent) and commit the segment count.
+__global__ void k_tm_adopt_active_clear(const __grid_constant__ bh_ctx c, int have_winners) {
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  // both activation buffers: this step's is rebuilt from the argument, the previous step's has had its last
+  // reader (learning) and must be empty for the step after this one
+#pragma unroll 1
+  for (long long j = gid; j < 2LL * c.column_dim; j += gsz) c.col_act[j] = 0u;
+  if (gid == 0 && !have_winners) {  // no update() call preceded: winner_cell is None for this step
+    c.sc[BH_SC_W0 + cur] = 0;
+    c.sc[BH_SC_WNONE0 + cur] = 1;
+    c.rng64[R_STEP_BASE] = c.rng64[R_CURSOR];
+  }
+  const int M = c.sc[BH_SC_M];
+#pragma unroll 1
+  for (long long j = gid; j < M; j += gsz) {
+    const int owner = c.seg_owner[c.m_seg[j]];
+    c.cell_maxjit[owner] = 0.0f;
+    c.cell_npred[owner] = 0;
+    c.col_pred[owner >> 5] = 0u;
+  }
+  if (gid == 0) c.sc[BH_SC_NSEG] = c.sc[BH_SC_NSEG_NEXT];
+}
+// the winner index rotation of ph_post (one CTA): entries of the previous winners out, this step's in
+__global__ void __launch_bounds__(1024) k_tm_adopt_widx(const __grid_constant__ bh_ctx c) {
+  const int k = c.active_columns, cd = c.cell_dim;
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int Wc = c.sc[BH_SC_W0 + cur], Wp = c.sc[BH_SC_W0 + (cur ^ 1)];
+  const int* wl_cur = c.winners + (long long)cur * k * cd;
+  const int* wl_prev = c.winners + (long long)(cur ^ 1) * k * cd;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < Wp; i += blockDim.x) c.cell_widx[wl_prev[i]] = -1;
+  __syncthreads();
+#pragma unroll 1
+  for (int i = threadIdx.x; i < Wc; i += blockDim.x) c.cell_widx[wl_cur[i]] = i;
+}
+__global__ void k_tm_adopt_active_set(const __grid_constant__ bh_ctx c, const int* cells, int n) {
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  uint32_t* act = c.col_act + (long long)cur * c.column_dim;
+#pragma unroll 1
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    atomicOr(&act[cells[i] >> 5], 1u << (cells[i] & 31));
+}
+
 // Step summary for the host (bh_step_host): see include/bithtm_b200.h
 __device__ void ph_summary(const bh_ctx& c, int b, int nb) {
   const int k = c.active_columns;

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _native as nat
 from ._engine import Engine
+from ._rnglink import _RngLink
 from .projections import DenseProjection, PredictiveProjection, _Lazy
 from .regularizations import ExponentialBoosting, GlobalInhibition, eng_set_active
 
@@ -26,71 +27,6 @@ def _bits(words: np.ndarray, c: int) -> np.ndarray:
     """uint32 [n] -> bool [n, c] (bit b = cell b)."""
     w = np.ascontiguousarray(words, dtype=np.uint32).reshape(-1, 1)
     return ((w >> np.arange(c, dtype=np.uint32)) & np.uint32(1)).astype(bool)
-
-
-class _RngLink:
-    """Keeps the device MT19937 state and the global ``np.random`` state in step.
-
-    np.random.get_state()/set_state() cost ~40 us each, so the legacy global
-    RandomState's raw state (624 key words + position, numpy/random/src/mt19937) is
-    read and written in place through the address NumPy publishes for that purpose
-    (``BitGenerator.ctypes.state_address``).  The Gaussian cache of the legacy
-    generator is never touched, exactly as rand() does not touch it."""
-
-    def __init__(self, mode="step"):
-        assert mode in ("step", "lazy")
-        self.mode = mode
-        self._seeded = False
-        import ctypes
-
-        addr = np.random.mtrand._rand._bit_generator.ctypes.state_address
-        self._live_key = np.ctypeslib.as_array((ctypes.c_uint32 * nat.MT_N).from_address(addr))
-        self._live_pos = ctypes.c_int.from_address(addr + 4 * nat.MT_N)
-        self._key = np.zeros(nat.MT_N, dtype=np.uint32)  # what the device continues from
-        self._key_bytes = b""
-        self._pos = -1
-
-    def before(self, eng):
-        if self.mode == "lazy" and self._seeded:
-            return
-        pos = self._live_pos.value
-        if self._seeded and pos == self._pos and self._live_key.tobytes() == self._key_bytes:
-            return  # nobody drew from np.random since our last write-back
-        self._key[:] = self._live_key
-        self._key_bytes = self._key.tobytes()
-        self._pos = pos
-        eng.set_rng_state(self._key, pos)
-        self._seeded = True
-
-    def adopt(self, eng, state):
-        """Continue the device stream from an explicit ``np.random.get_state()`` tuple."""
-        key, pos = np.asarray(state[1], dtype=np.uint32), int(state[2])
-        self._key[:] = key
-        self._key_bytes = self._key.tobytes()
-        self._pos = pos
-        eng.set_rng_state(self._key, pos)
-        self._seeded = True
-
-    def after(self, eng, summary=None):
-        if self.mode == "lazy":
-            return
-        if summary is None:
-            key, pos = eng.get_rng_state()
-        else:
-            k = eng.k
-            tail = summary[4 + 4 * k:4 + 4 * k + nat.MT_N + 1]
-            key, pos = tail[:nat.MT_N].view(np.uint32), int(tail[nat.MT_N])
-        self._live_key[:] = key
-        self._key_bytes = self._live_key.tobytes()
-        self._pos = pos
-        self._live_pos.value = pos
-
-    def sync(self, eng):
-        key, pos = eng.get_rng_state()
-        self._live_key[:] = key
-        self._key_bytes = self._live_key.tobytes()
-        self._pos = pos
-        self._live_pos.value = pos
 
 
 class SpatialPooler:
@@ -192,6 +128,7 @@ class SpatialPooler:
     def process(self, input, learning=True):
         """networks.py:26-35.  Leaves the active columns on the device for the TM."""
         eng = self._ensure_engine()
+        eng.begin_regular_step()
         self.boosting._bind(eng)
         words = eng.pack_input(input)
         if eng.shard_world > 1:
@@ -342,6 +279,7 @@ class TemporalMemory:
     def _attach(self, engine, epsilon=1e-8):
         self._engine = engine
         self.distal_projection._bind(engine, epsilon)
+        self.distal_projection._rng_link = self._rng  # one link per np.random stream
 
     def sync_rng(self):
         """Write the device MT19937 state back into the global np.random."""
@@ -359,9 +297,16 @@ class TemporalMemory:
                 return_state=True):
         """networks.py:91-128.  ``return_state=False`` (extension) enqueues the step without
         reading anything back (no host synchronisation; needs ``rng_sync="lazy"``)."""
+        forget = False
         if prev_state is not None and prev_state is not self.last_state:
-            raise NotImplementedError("bithtm_b200.TemporalMemory keeps the previous state on the device; "
-                                      "an explicit prev_state other than last_state is not supported")
+            # the previous state lives on the device; the one other state that can be named without it is
+            # the empty state (networks.py:59-65): start a new sequence, keeping everything learned
+            if (getattr(prev_state, "distal_state", 0) is None and getattr(prev_state, "winner_cell", 0) is None
+                    and not np.any(prev_state.cell_prediction)):
+                forget = True
+            else:
+                raise NotImplementedError("bithtm_b200.TemporalMemory keeps the previous state on the device; "
+                                          "prev_state may be last_state or an empty state (get_empty_state())")
         want = bool(learning or return_winner_cell)  # networks.py:99
         active_column = None
         tag = getattr(sp_state, "_bh_engine_epoch", None)
@@ -371,7 +316,11 @@ class TemporalMemory:
             active_column = np.asarray(sp_state.active_column)
             self._attach(Engine(1, self.column_dim, self.cell_dim, len(active_column), **self._engine_kwargs), epsilon)
         eng = self._engine
+        eng.begin_regular_step()
         self.distal_projection._bind(eng, epsilon)
+        if forget:
+            nat.check(nat.lib.bh_tm_reset(eng.ref, eng.stream), "bh_tm_reset")
+            self.last_state = self.get_empty_state()
         on_device = tag is not None and tag[0] is eng and tag[1] == eng.epoch
         if not on_device:
             eng_set_active(eng, sp_state.active_column if active_column is None else active_column)
@@ -446,8 +395,13 @@ class HierarchicalTemporalMemory:
         if seg is not None and seg[1] <= 1:
             seg = None
         tm.distal_projection._group = process_group
+        # buffer-sizing keyword arguments given to a user-built SpatialPooler / TemporalMemory are honoured
+        # (explicit arguments of this constructor win)
+        merged = dict(sp._engine_kwargs)
+        merged.update(tm._engine_kwargs)
+        merged.update(engine_kwargs)
         self._engine = Engine(input_dim, column_dim, cell_dim, sp.active_columns, device=device,
-                              column_shard=shard, segment_shard=seg, **engine_kwargs)
+                              column_shard=shard, segment_shard=seg, **merged)
         sp._attach(self._engine)
         tm._attach(self._engine)
         if self._engine.ctx.fused_mode == 3:  # one kernel per shard, exchanges over peer memory
@@ -470,6 +424,30 @@ class HierarchicalTemporalMemory:
     def sync_rng(self):
         self.temporal_memory.sync_rng()
 
+    def reset_sequence(self):
+        """Extension: forget the previous timestep (as ``TemporalMemory.process(prev_state=
+        get_empty_state())`` does, networks.py:59-65, 91-93); everything learned is kept."""
+        eng = self._engine
+        nat.check(nat.lib.bh_tm_reset(eng.ref, eng.stream), "bh_tm_reset")
+        self.temporal_memory.last_state = self.temporal_memory.get_empty_state()
+        eng.tm_deferred = False
+
+    def state_dict(self):
+        """Extension (checkpoint): the learned state, the previous timestep's context and the MT19937
+        stream position of this network (of this rank's shard), as host tensors."""
+        return self._engine.snapshot()
+
+    def load_state_dict(self, state):
+        """Extension (resume): inverse of :meth:`state_dict`; the run continues bit-identically.  With
+        ``rng_sync="step"`` the global ``np.random`` state is set to the checkpoint's as well."""
+        eng, tm = self._engine, self.temporal_memory
+        eng.restore(state)
+        key, pos = state["rng"]
+        if tm._rng.mode == "step":
+            np.random.set_state(("MT19937", np.asarray(key, dtype=np.uint32), int(pos), 0, 0.0))
+        tm._rng.adopt(eng, ("MT19937", key, pos))
+        tm.last_state = None  # lives on the device; the next process() returns the first readable state
+
     def process(self, input, learning=True, return_state=True, return_winner_cell=True):
         """networks.py:146-149 (``return_winner_cell`` -- an extension here -- is passed on to
         ``TemporalMemory.process``; with ``learning=False`` it gives the inference-only step).  Host inputs go through ``bh_step_host`` (one H2D of
@@ -477,6 +455,7 @@ class HierarchicalTemporalMemory:
         ``return_state=False`` (extension; device inputs, ``rng_sync="lazy"``) only enqueues
         the step: nothing is read back and the host does not wait."""
         sp, tm, eng = self.spatial_pooler, self.temporal_memory, self._engine
+        eng.begin_regular_step()
         is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
         staged = not return_winner_cell or eng.tm_deferred  # needs the per-stage kernels (bh_tm_step_ex)
         if eng.ctx.fused_mode == 3:  # the shard's whole step is one kernel (exchanges inside)

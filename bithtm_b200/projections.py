@@ -238,9 +238,16 @@ class PredictiveProjection:
     def __init__(self, output_dim, permanence_initial=0.21, permanence_threshold=0.5, permanence_increment=0.1,
                  permanence_decrement=0.1, permanence_punishment=0.01, segment_activation_threshold=15,
                  segment_matching_threshold=15, segment_sampling_synapses=32,
-                 segment_bundle_growth_exponential=True):
+                 segment_bundle_growth_exponential=True, *, cell_dim=None, active_columns=None, **engine_kwargs):
+        """``cell_dim`` / ``active_columns`` (extensions, keyword-only): let a projection that is NOT owned by
+        a bithtm_b200 TemporalMemory allocate its own device state on first use -- e.g. when it is plugged
+        into the reference's TemporalMemory (networks.py:48-55), which calls ``process`` / ``update`` itself.
+        ``active_columns`` bounds the winner / active cell lists (active_columns * cell_dim cells)."""
         assert segment_activation_threshold >= segment_matching_threshold  # projections.py:211
         self.output_dim = output_dim
+        self._cell_dim, self._active_columns, self._engine_kwargs = cell_dim, active_columns, engine_kwargs
+        self._rng_link = None
+        self._winners_epoch = -1  # engine epoch at which update() supplied the winner cells
         self.permanence_initial = permanence_initial
         self.permanence_threshold = permanence_threshold
         self.permanence_increment = permanence_increment
@@ -346,11 +353,171 @@ class PredictiveProjection:
         (reference_implementations.py:51-70)."""
         return SegmentProjectionView(self)
 
-    def process(self, active_input, return_jittered_potential_info=True):
-        raise NotImplementedError("call through bithtm_b200.TemporalMemory.process (the fused device path)")
+    # ---- the plugin methods themselves (projections.py:229-293), with explicit arguments ----
+    # TemporalMemory.process here runs the whole timestep in fused kernels; these are the same device
+    # phases behind the reference's own method signatures, for callers that orchestrate a timestep
+    # themselves the way networks.py:91-128 does.
+    def _need_engine(self):
+        if self._engine is None:
+            if self._cell_dim is None or self._active_columns is None:
+                raise RuntimeError("PredictiveProjection is not attached to a network: construct a bithtm_b200 "
+                                   "TemporalMemory with it, or pass cell_dim= and active_columns= to use it "
+                                   "stand-alone")
+            from ._engine import Engine
 
-    def update(self, *args, **kwargs):
-        raise NotImplementedError("call through bithtm_b200.TemporalMemory.process (the fused device path)")
+            self._bind(Engine(1, self.output_dim // self._cell_dim, self._cell_dim, self._active_columns,
+                              fused="off", **self._engine_kwargs))
+        if self._engine.seg_world > 1:
+            raise NotImplementedError("stand-alone process / update are not available on segment shards")
+        if self._rng_link is None:
+            from ._rnglink import _RngLink
+
+            self._rng_link = _RngLink("step")
+        return self._engine
+
+    def _device_cells(self, flat):
+        """Reference flat cell ids (column * cell_dim + cell) -> device int32 tensor of column * 32 + cell."""
+        import torch
+
+        eng = self._engine
+        f = np.asarray(flat, dtype=np.int64).reshape(-1)
+        if f.size and (f.min() < 0 or f.max() >= eng.N):
+            raise ValueError("cell index out of range")
+        dev = ((f // eng.c) * 32 + f % eng.c).astype(np.int32)
+        return torch.from_numpy(dev).to(eng.device), int(f.size)
+
+    def fill_jittered_potential_info(self, state, matching_segment_bundle=None):
+        """projections.py:229-239: draws rand(M) for an activation that was asked not to."""
+        eng = self._need_engine()
+        if state._have_jitter:
+            return
+        if state._epoch != eng.epoch:
+            raise RuntimeError("only the latest activation state can still draw its jitter")
+        self._rng_link.before(eng)
+        nat.check(nat.lib.bh_tm_fill_jitter(eng.ref, eng.stream), "bh_tm_fill_jitter")
+        self._rng_link.after(eng)
+        state._have_jitter = True
+
+    def get_jittered_potential_info(self, state, matching_segment_bundle=None):
+        """projections.py:241-243."""
+        self.fill_jittered_potential_info(state, matching_segment_bundle)
+        return state.max_jittered_potential, state.matching_segment_jittered_potential
+
+    def process(self, active_input, return_jittered_potential_info=True):
+        """projections.py:245-255 for an explicit list of active cells (flat ids).  Completes a timestep
+        on the device: an ``update`` call that belongs to the same timestep must come first, as in
+        networks.py:106-121."""
+        eng = self._need_engine()
+        cells, n = self._device_cells(active_input)
+        jit = bool(return_jittered_potential_info)
+        self._rng_link.before(eng)
+        nat.check(nat.lib.bh_tm_activate_cells(eng.ref, cells.data_ptr(), n, int(jit),
+                                               int(self._winners_epoch == eng.epoch), eng.stream),
+                  "bh_tm_activate_cells")
+        eng.epoch += 1
+        eng.tm_deferred = True  # row lists of the fused summary were not formed: next step takes the staged path
+        eng.standalone_dirty = 2
+        if jit:
+            self._rng_link.after(eng)
+        eng.check_status()
+        self._last_state = self.State(eng, self, jit)
+        return self._last_state
+
+    def update(self, prev_state, input_activation, learning_output, output_punishment, winner_input=None,
+               output_learning=None, epsilon=1e-8):
+        """projections.py:257-293.  ``prev_state`` must be the State of the latest activation (the device
+        holds exactly one); ``output_punishment`` must be uniform within a column (it is
+        ``np.repeat(column_punishment, cell_dim)`` at the reference's only call site, networks.py:111)."""
+        if prev_state is None:  # :258-259
+            return
+        eng = self._need_engine()
+        import torch
+
+        if getattr(prev_state, "_engine", None) is not eng or prev_state._epoch != eng.epoch:
+            raise NotImplementedError("prev_state must be the State this projection's latest activation returned "
+                                      "(the previous distal state lives on the device)")
+        if output_learning is not None:
+            raise NotImplementedError("output_learning= is derived from learning_output on the device")
+        C_, c = eng.C, eng.c
+        act = np.asarray(input_activation, dtype=bool).reshape(C_, c)
+        pun = np.asarray(output_punishment, dtype=bool).reshape(C_, c)
+        if not (pun == pun[:, :1]).all():
+            raise NotImplementedError("output_punishment must be the same for all cells of a column")
+        padded = np.zeros((C_, 32), dtype=bool)
+        padded[:, :c] = act
+        words = np.packbits(padded, axis=1, bitorder="little").view(np.uint32).reshape(-1).view(np.int32)
+        col_active = (~pun[:, 0]).astype(np.uint8)
+        win, n_win = self._device_cells(learning_output)
+        if winner_input is None:
+            prev_win, n_prev = win, -1
+        else:
+            prev_win, n_prev = self._device_cells(winner_input)
+        if max(n_win, n_prev) > eng.k * c:
+            raise ValueError("more winner cells than active_columns * cell_dim")
+        self._bind(eng, epsilon)
+        w_dev = torch.from_numpy(words).to(eng.device)
+        a_dev = torch.from_numpy(col_active).to(eng.device)
+        self._rng_link.before(eng)
+        nat.check(nat.lib.bh_tm_learn_args(eng.ref, win.data_ptr(), n_win, prev_win.data_ptr(), n_prev,
+                                           w_dev.data_ptr(), a_dev.data_ptr(), eng.stream), "bh_tm_learn_args")
+        self._rng_link.after(eng)
+        eng.check_status()
+        self._winners_epoch = eng.epoch
+        if not prev_state._have_jitter:  # the update drew it (get_jittered_potential_info, :263)
+            prev_state._have_jitter = True
+
+    # ---- state import: the inverse of export_segments (checkpoint / resume of the learned state) ----
+    def import_segments(self, owner, count, cells, perm):
+        """Load a segment store in the row form ``export_segments`` returns (or what
+        ``reference_implementations.TemporalMemory.copy_custom`` reads, reference_implementations.py:51-70):
+        owner[S] flat cell of each segment, count[S] valid synapses, cells[S, E'] presynaptic flat cells with
+        negative = free slot, perm[S, E'] float32.  Rows are re-compacted; the previous timestep's context is
+        forgotten (``bh_tm_reset``), the learned state is replaced.  Segment shards keep the rows they hold."""
+        import torch
+
+        eng = self._engine
+        if eng is None:
+            raise RuntimeError("attach the projection to a network first")
+        owner = np.asarray(owner, dtype=np.int64).reshape(-1)
+        S = len(owner)
+        cells = np.asarray(cells, dtype=np.int64).reshape(S, -1)
+        perm = np.asarray(perm, dtype=np.float32).reshape(S, -1)
+        E = eng.ctx.syn_capacity
+        valid = cells >= 0
+        n_valid = valid.sum(axis=1)
+        if count is not None and not np.array_equal(n_valid, np.asarray(count).reshape(-1)):
+            raise ValueError("count does not match the number of non-negative cells per row")
+        if S > eng.ctx.seg_capacity or (S and n_valid.max() > E):
+            raise nat.NativeError("import_segments: more segments / synapses per segment than this network's capacity")
+        nat.check(nat.lib.bh_tm_reset(eng.ref, eng.stream), "bh_tm_reset")
+        order = np.argsort(~valid, axis=1, kind="stable")  # valid slots first, original order kept
+        cells_c = np.take_along_axis(cells, order, axis=1)
+        perm_c = np.take_along_axis(perm, order, axis=1)
+        width = cells.shape[1]
+        rows_cell = np.zeros((S, E), dtype=np.int32)
+        rows_perm = np.full((S, E), -1.0, dtype=np.float32)
+        w = min(width, E)
+        dev_cells = (cells_c // eng.c) * 32 + cells_c % eng.c
+        rows_cell[:, :w] = np.where(cells_c[:, :w] >= 0, dev_cells[:, :w], 0)
+        rows_perm[:, :w] = np.where(cells_c[:, :w] >= 0, perm_c[:, :w], -1.0)
+        ids = eng.held_segment_ids(S)
+        n = len(ids)
+        owner_dev = ((owner // eng.c) * 32 + owner % eng.c).astype(np.int32)
+
+        def put(name, arr, length):
+            eng.buf[name][:length].copy_(torch.from_numpy(np.ascontiguousarray(arr).reshape(-1)).to(eng.device))
+
+        for name in ("seg_owner", "seg_count", "seg_pot", "seg_conn"):
+            eng.buf[name].zero_()
+        put("seg_owner", owner_dev, S)
+        put("seg_count", n_valid.astype(np.int32), S)
+        put("syn_cell", rows_cell[ids], n * E)
+        put("syn_perm", rows_perm[ids], n * E)
+        nseg = np.bincount(owner_dev, minlength=eng.C * 32).astype(np.int32)
+        put("cell_nseg", nseg, eng.C * 32)
+        eng.buf["sc"][nat.SC_NSEG] = S
+        eng.buf["sc"][nat.SC_NSEG_NEXT] = S
+        eng.tm_deferred = False
 
 
 class SegmentProjectionView:

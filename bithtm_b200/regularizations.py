@@ -98,8 +98,17 @@ class GlobalInhibition:
         if input_activation is not None and not getattr(input_activation, "_bh_on_device", False):
             import torch
 
-            host = np.asarray(input_activation, dtype=np.float64)
-            eng.buf["boosted"].copy_(torch.from_numpy(host).to(eng.device))
+            host = np.asarray(input_activation, dtype=np.float64) + 0.0  # -0.0 -> +0.0 (they compare equal)
+            if host.shape != (eng.C_local,):
+                raise ValueError(f"expected {eng.C_local} values, got shape {host.shape}")
+            if (host < 0).any():
+                # the device orders keys by their bit patterns as unsigned integers, which is the numeric
+                # order for non-negative doubles only: map arbitrary doubles with the order-preserving
+                # transform (negative: flip all bits, else: flip the sign bit)
+                bits = host.view(np.int64)
+                bits = np.where(bits < 0, ~bits, bits ^ np.int64(-2 ** 63))
+                host = bits.view(np.float64)
+            eng.buf["boosted"].copy_(torch.from_numpy(np.ascontiguousarray(host)).to(eng.device))
         if int(self.active_outputs) != eng.k:
             raise ValueError("active_outputs differs from the network's active_columns")
         nat.check(nat.lib.bh_inhibit(eng.ref, eng.stream), "bh_inhibit")

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 8
+#define BH_ABI_VERSION 9
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 81920
@@ -116,6 +116,10 @@ typedef struct bh_ctx {
   int32_t jump_polys;      /* rows of mt_jump (0 = the stream is produced by one CTA)  */
   int32_t rng_lookahead;   /* stream words draw #2 produces beyond its own need (the   */
                            /* following rand(M) and next step's rand(k, c))            */
+  int32_t device;          /* CUDA device ordinal the buffers live on: every entry point */
+                           /* makes it current for the duration of the call (-1 = keep  */
+                           /* the calling thread's current device)                     */
+  int32_t reserved0;
 
   /* ---- constants, evaluated on the host with the reference's expressions ----- */
   double sp_threshold;     /* projections.py:19  permanence >= threshold           */
@@ -320,6 +324,32 @@ int bh_tm_step(const bh_ctx* ctx, int learning, void* stream);
  * the activation is deferred to the next step that needs it, exactly as the reference's lazy
  * fill_jittered_potential_info does.  Per-stage kernels; not for segment shards. */
 int bh_tm_step_ex(const bh_ctx* ctx, int learning, int want_winner, int want_jitter, void* stream);
+
+/* ---- the distal projection as a stand-alone plugin, with explicit arguments --------------
+ * For callers that drive PredictiveProjection themselves, the way the reference's own
+ * TemporalMemory.process does (networks.py:106-113, 121): lists are device int32 arrays of cells
+ * addressed as column * 32 + cell; not for segment shards.
+ * bh_tm_learn_args    : PredictiveProjection.update (projections.py:257-293).  winner_cells =
+ *                       learning_output (ordered), prev_winner_cells = winner_input (n_prev < 0: None),
+ *                       prev_activation_words [C] = input_activation as one bit-word per column,
+ *                       column_active [C] = 1 where output_punishment is False.  prev_state is the
+ *                       activation this context computed last.  Consumes rand(L, W+1).
+ * bh_tm_activate_cells: PredictiveProjection.process (projections.py:245-255) on an explicit list of
+ *                       active cells; want_jitter = return_jittered_potential_info (consumes rand(M));
+ *                       have_winners = a bh_tm_learn_args call of this timestep supplied the winner
+ *                       cells.  Completes the timestep (sc[BH_SC_STEP] += 1).
+ * bh_tm_fill_jitter   : PredictiveProjection.fill_jittered_potential_info (projections.py:229-239) for
+ *                       an activation that deferred it; no-op otherwise.
+ * bh_tm_reset         : TemporalMemory.process(prev_state = get_empty_state()) (networks.py:59-65,
+ *                       91-93): forget the previous timestep's predictions, activation, winner cells and
+ *                       distal state; the learned state is untouched. */
+int bh_tm_learn_args(const bh_ctx* ctx, const int32_t* winner_cells_dev, int n_winners,
+                     const int32_t* prev_winner_cells_dev, int n_prev_winners,
+                     const uint32_t* prev_activation_words_dev, const uint8_t* column_active_dev, void* stream);
+int bh_tm_activate_cells(const bh_ctx* ctx, const int32_t* active_cells_dev, int n_active, int want_jitter,
+                         int have_winners, void* stream);
+int bh_tm_fill_jitter(const bh_ctx* ctx, void* stream);
+int bh_tm_reset(const bh_ctx* ctx, void* stream);
 
 /* ---- whole timestep: HierarchicalTemporalMemory.process (networks.py:146-149) ------ */
 int bh_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, void* stream);

@@ -10,7 +10,8 @@ import pytest
 
 from helpers import (diff_records, golden_inputs, gpu_record, gpu_state_digest, load_golden, make_inputs,
                      oracle_record, oracle_state_digest, step_digest)
-from oracle.htm_oracle import HTMOracle, OracleConfig
+from oracle.digest import canonical_from_rows, state_digest
+from oracle.htm_oracle import HTMOracle, OracleConfig, canonical_topk
 
 pytestmark = pytest.mark.gpu
 
@@ -210,12 +211,11 @@ def test_lockstep_odd_dims(fused):
     _lockstep("odd", fused=fused)
 
 
-@pytest.mark.skipif(not os.environ.get("BH_RUN_UNVALIDATED"),
-                    reason="traces recorded after round 1's GPU minutes were spent; first run: BH_RUN_UNVALIDATED=1")
 @pytest.mark.parametrize("name", ["edge", "edge24", "c1", "k1"])
-def test_lockstep_edge_case_traces(name):
+@pytest.mark.parametrize("fused", ["auto", "off"])
+def test_lockstep_edge_case_traces(name, fused):
     """Reference traces with empty / full / repeated inputs, one cell per column, one active column."""
-    _lockstep(name)
+    _lockstep(name, fused=fused)
 
 
 def test_lockstep_many_columns_grid_kernel():
@@ -235,6 +235,31 @@ def test_lockstep_many_columns_grid_kernel():
         problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
         assert not problems, f"step {t}: " + "; ".join(problems)
     assert gpu_state_digest(htm) == oracle_state_digest(orc)
+
+
+@pytest.mark.parametrize("fused", ["cluster", "auto"])
+def test_lockstep_many_cells_many_draws(fused):
+    """k = 328 active columns x 32 cells: a step draws enough random numbers for many-CTA stream
+    production.  fused="auto" must pick the cooperative grid (which has the production phase); an explicit
+    fused="cluster" must fall back to one-CTA production instead of leaving planned chunks unproduced."""
+    import bithtm_b200 as bithtm
+
+    I, C, c, k, seed = 256, 16384, 32, 328, 23
+    np.random.seed(seed)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused=fused, max_segments=1 << 16)
+    eng = htm.engine
+    assert (eng.ctx.fused_mode, eng.ctx.jump_polys > 0) == ((1, False) if fused == "cluster" else (2, True))
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed), overlap="packed")
+    g = np.random.default_rng(seed)
+    base = g.random((4, I)) < 0.2
+    for t in range(24):
+        x = base[t % 4] ^ (g.random(I) < 0.05)
+        sp_state, tm_state = htm.process(x)
+        rec = orc.step(x)
+        problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not problems, f"step {t}: " + "; ".join(problems)
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
+    assert np.array_equal(np.random.random_sample(64), orc.rng.random_sample(64))
 
 
 def test_lockstep_mid():
@@ -648,3 +673,263 @@ def test_cfg3_full_size_execution_modes_agree():
     ra.set_state(("MT19937", ka, pa, 0, 0.0))
     rb.set_state(("MT19937", kb, pb, 0, 0.0))
     assert np.array_equal(ra.random_sample(1000), rb.random_sample(1000))
+
+
+def _cfg3_lockstep(fused, steps, patterns=5, **engine_kw):
+    """BASELINE configs[2] at its FULL size (65536 columns x 16384 inputs, 32 cells, k = 1311) lock-step
+    against the ORACLE (networks.py:146-149): the float64 permanence is drawn once on the device, downloaded
+    and handed to both sides; every State field of every step and the learned state are compared.  Few input
+    patterns, so that predictions, learning / punished segments and growth of existing segments (not only
+    the all-bursting start) happen inside the short run."""
+    import torch
+
+    import bithtm_b200 as bithtm
+    from bithtm_b200.projections import DenseProjection
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~24 GiB of device memory")
+    I, C, c, k, seed = 16384, 65536, 32, 1311, 12
+    g = np.random.default_rng(8)
+    base = g.random((patterns, I)) < 0.2
+    xs = base[np.arange(steps) % patterns] ^ (g.random((steps, I)) < 0.05)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    perm = torch.randn(C, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
+    host_perm = perm.cpu().numpy()
+    np.random.seed(seed)
+    sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, fused=fused, max_segments=1 << 17,
+                                            max_synapses_per_segment=128, **engine_kw)
+    del perm
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed), overlap="packed",
+                    permanence=host_perm)
+    predicted = grown = 0
+    for t in range(steps):
+        sp_state, tm_state = htm.process(xs[t])
+        rec = orc.step(xs[t])
+        problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not problems, f"cfg3 {fused} step {t}: " + "; ".join(problems) + f"; sc={htm.engine.scalars()[:18]}"
+        predicted += int((~rec.bursting).sum())
+        grown += len(rec.learning_segment)
+    assert predicted > 0 and grown > steps  # the run left the all-bursting start
+    eng = htm.engine
+    assert eng.check_status() & ~32 == 0
+    # learned state: SP permanence (8 GiB, compared directly), duty cycles, segments, synapses
+    got_perm = eng.buf["sp_perm"].cpu().numpy().reshape(C, I)
+    assert np.array_equal(got_perm.view(np.uint64), orc.permanence.view(np.uint64)), "SP permanence bits"
+    del got_perm
+    tmp = htm.temporal_memory.distal_projection
+    owner, count, cells, perm_rows = tmp.export_segments()
+    assert state_digest(np.zeros(1), htm.spatial_pooler.boosting.duty_cycle, tmp.bundle_segments,
+                        canonical_from_rows(owner, cells, perm_rows)) == \
+        state_digest(np.zeros(1), orc.duty, orc.cell_nseg, orc.canonical_synapses())
+    # the caller's np.random stream ends where the oracle's does
+    assert np.array_equal(np.random.random_sample(64), orc.rng.random_sample(64))
+    return htm
+
+
+@pytest.mark.gpu
+def test_cfg3_lockstep_oracle_fused_grid():
+    """The whole step as one cooperative kernel (long-row overlap, wide SP learning, many-CTA stream
+    production, grid-wide top-k at 148 CTAs) against the oracle at cfg3's full size."""
+    htm = _cfg3_lockstep("grid", 30)
+    assert htm.engine.ctx.fused_mode == 2
+
+
+@pytest.mark.gpu
+def test_cfg3_lockstep_oracle_per_stage():
+    """One kernel per stage (the fine-grained C entry points) against the oracle at cfg3's full size."""
+    htm = _cfg3_lockstep("off", 14)
+    assert htm.engine.ctx.fused_mode == 0
+
+
+# ------------------------------------------------------------------ the plugin surface itself
+def test_predictive_projection_plugin_methods_match_oracle():
+    """PredictiveProjection.update / .process / .get_jittered_potential_info called with explicit arguments,
+    the way the reference's own TemporalMemory.process calls them (networks.py:106-113, 121), against
+    HTMOracle.tm_learn / tm_activate; then the network classes take over again (fused path) and stay
+    bit-exact."""
+    import bithtm_b200 as bithtm
+
+    I, C, c, k, seed = 96, 160, 12, 12, 9
+    np.random.seed(seed)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused="off")
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    pp = htm.temporal_memory.distal_projection
+    g = np.random.default_rng(seed)
+    base = g.random((6, I)) < 0.25
+    prev_state, prev_winners, prev_activation = None, None, np.zeros((C, c), dtype=bool)
+    for t in range(260):
+        x = base[t % 6] ^ (g.random(I) < 0.05)
+        want_jit = t % 7 != 3  # sometimes leave the jitter to the next get_jittered_potential_info
+        sp_state = htm.spatial_pooler.process(x)
+        ac = orc.sp_inhibit(orc.sp_boost(orc.sp_overlap(x)))
+        orc.sp_learn(x, ac)
+        orc.sp_duty_update(ac)
+        assert np.array_equal(sp_state.active_column, ac)
+        # networks.py:99-104 on the host (the oracle's restatement); the caller's own rand(k, c)
+        if prev_state is not None:
+            mj, _ = pp.get_jittered_potential_info(prev_state)  # networks.py:76
+        acp, burst, winners, _ = orc.tm_select(ac)
+        if prev_state is not None:
+            assert np.array_equal(mj.view(np.uint32), orc.max_jit.view(np.uint32))
+        np.random.rand(k, c)  # networks.py:87: keeps the global stream where the reference's would be
+        punish = np.ones(C, dtype=bool)
+        punish[ac] = False
+        learn, _, _, _ = orc.tm_learn(ac, winners)
+        pp.update(prev_state, prev_activation.reshape(-1), winners, np.repeat(punish, c), winner_input=prev_winners)
+        act_rows = acp | burst[:, None]
+        activation = np.zeros((C, c), dtype=bool)
+        activation[ac] = act_rows
+        rows, cells = np.nonzero(act_rows)
+        active_flat = ac[rows] * c + cells
+        orc.tm_activate(activation.reshape(-1), want_jitter=want_jit)
+        st = pp.process(active_flat, return_jittered_potential_info=want_jit)
+        assert np.array_equal(st.segment_potential, orc.seg_potential), t
+        assert np.array_equal(st.matching_segment, orc.m_seg), t
+        assert np.array_equal(st.matching_segment_activation, orc.m_act), t
+        assert np.array_equal(st.prediction, orc.npred.astype(np.float64)), t
+        assert np.array_equal(pp.bundle_segments, orc.cell_nseg), t
+        if want_jit:
+            assert np.array_equal(st.matching_segment_jittered_potential.view(np.uint32), orc.m_jit.view(np.uint32)), t
+            assert np.array_equal(st.max_jittered_potential.view(np.uint32), orc.max_jit.view(np.uint32)), t
+        else:
+            assert st.max_jittered_potential is None
+        assert pp.n_segments == orc.n_seg
+        orc.cell_activation, orc.prev_winners = activation, winners
+        prev_state, prev_winners, prev_activation = st, winners, activation
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
+    assert orc.n_seg > 50 and int((~burst).sum()) > 0
+    # hand over to the network classes: the fused / staged paths continue from the same device state
+    for t in range(260, 330):
+        x = base[t % 6] ^ (g.random(I) < 0.05)
+        sp_state, tm_state = htm.process(x)
+        rec = orc.step(x)
+        problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not problems, f"after hand-over, step {t}: " + "; ".join(problems)
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
+    assert np.array_equal(np.random.random_sample(64), orc.rng.random_sample(64))
+
+
+def test_stand_alone_projection_allocates_its_own_device_state():
+    import bithtm_b200 as bithtm
+
+    pp = bithtm.projections.PredictiveProjection(64 * 4, cell_dim=4, active_columns=6)
+    st = pp.process(np.array([0, 5, 9]))
+    assert len(st.matching_segment) == 0 and st.prediction.shape == (256,) and not st.prediction.any()
+    with pytest.raises(RuntimeError):
+        bithtm.projections.PredictiveProjection(64).process(np.array([1]))
+
+
+@pytest.mark.parametrize("fused", ["cluster", "off"])
+def test_explicit_empty_prev_state_starts_a_new_sequence(fused):
+    """TemporalMemory.process(sp_state, prev_state=get_empty_state()) (networks.py:91-93 with the state of
+    :59-65): predictions, activation, winner cells and the distal state of the previous step are forgotten,
+    the learned state is kept."""
+    import bithtm_b200 as bithtm
+
+    info = load_golden("tiny")
+    I, C, c, k, seed = info["I"], info["C"], info["c"], info["k"], 31
+    np.random.seed(seed)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused=fused)
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    xs = make_inputs(I, 5, 0.25, 0.05, 240, seed)
+    for t in range(240):
+        if t in (90, 91, 170):  # forget the previous step
+            orc.have_prev, orc.prev_winners, orc.jit_pending = False, None, False
+            orc.cell_prediction = np.zeros((C, c), dtype=bool)
+            orc.cell_activation = np.zeros((C, c), dtype=bool)
+            if t == 170:
+                htm.reset_sequence()
+                sp_state, tm_state = htm.process(xs[t])
+            else:
+                sp_state = htm.spatial_pooler.process(xs[t])
+                tm_state = htm.temporal_memory.process(sp_state, prev_state=htm.temporal_memory.get_empty_state())
+        else:
+            sp_state, tm_state = htm.process(xs[t])
+        rec = orc.step(xs[t])
+        problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
+        assert not problems, f"step {t}: " + "; ".join(problems)
+    assert gpu_state_digest(htm) == oracle_state_digest(orc)
+    with pytest.raises(NotImplementedError):
+        htm.temporal_memory.process(sp_state, prev_state=object())
+
+
+@pytest.mark.parametrize("fused", ["cluster", "grid", "off"])
+def test_checkpoint_resume_continues_bit_identically(fused):
+    """state_dict() -> a NEW network -> load_state_dict(): the resumed run equals the uninterrupted one
+    (every State field each step, learned state, np.random position)."""
+    import bithtm_b200 as bithtm
+
+    info = load_golden("tiny")
+    I, C, c, k, seed = info["I"], info["C"], info["c"], info["k"], 17
+    xs = make_inputs(I, 5, 0.25, 0.05, 260, seed)
+    np.random.seed(seed)
+    a = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused=fused)
+    for t in range(150):
+        a.process(xs[t])
+    snap = a.state_dict()
+    digests = []
+    for t in range(150, 260):
+        sp_state, tm_state = a.process(xs[t])
+        digests.append(step_digest(**gpu_record(a, sp_state, tm_state)))
+    final_a, tail_a = gpu_state_digest(a), np.random.random_sample(16)
+    np.random.seed(12345)  # an unrelated stream position: load_state_dict must restore the checkpoint's
+    b = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused=fused, max_segments=4096)
+    b.load_state_dict(snap)
+    for t in range(150, 260):
+        sp_state, tm_state = b.process(xs[t])
+        assert step_digest(**gpu_record(b, sp_state, tm_state)) == digests[t - 150], f"resumed run differs at step {t}"
+    assert gpu_state_digest(b) == final_a
+    assert np.array_equal(np.random.random_sample(16), tail_a)
+
+
+def test_import_segments_is_the_inverse_of_export_segments():
+    """export_segments() of one network -> import_segments() + permanence / duty cycles into a fresh one:
+    both continue identically from an empty previous state."""
+    import torch
+
+    import bithtm_b200 as bithtm
+    from bithtm_b200.projections import DenseProjection
+
+    info = load_golden("tiny")
+    I, C, c, k, seed = info["I"], info["C"], info["c"], info["k"], 41
+    xs = make_inputs(I, 5, 0.25, 0.05, 300, seed)
+    np.random.seed(seed)
+    a = bithtm.HierarchicalTemporalMemory(I, C, c, k)
+    for t in range(200):
+        a.process(xs[t])
+    tmp = a.temporal_memory.distal_projection
+    owner, count, cells, perm = tmp.export_segments()
+    sp_perm, duty = a.spatial_pooler.proximal_projection.permanence, a.spatial_pooler.boosting.duty_cycle
+    sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=sp_perm))
+    b = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp)
+    b.engine.buf["duty"].copy_(torch.from_numpy(duty).to(b.engine.device))
+    shuffled = np.random.default_rng(3).permutation(cells.shape[1])  # slot order is free (SURVEY 8a)
+    b.temporal_memory.distal_projection.import_segments(owner, count, cells[:, shuffled], perm[:, shuffled])
+    assert gpu_state_digest(a) == gpu_state_digest(b)
+    a.reset_sequence()
+    state = np.random.get_state()
+    da = []
+    for t in range(200, 300):
+        sp_state, tm_state = a.process(xs[t])
+        da.append(step_digest(**gpu_record(a, sp_state, tm_state)))
+    np.random.set_state(state)
+    for t in range(200, 300):
+        sp_state, tm_state = b.process(xs[t])
+        assert step_digest(**gpu_record(b, sp_state, tm_state)) == da[t - 200], t
+    assert gpu_state_digest(a) == gpu_state_digest(b)
+
+
+def test_global_inhibition_plugin_orders_negative_values():
+    """GlobalInhibition.process on an arbitrary host array (regularizations.py:28-29 accepts any sign)."""
+    import bithtm_b200 as bithtm
+
+    C, k = 300, 25
+    sp = bithtm.SpatialPooler(200, C, k)
+    sp.process(np.zeros(200, dtype=bool))
+    g = np.random.default_rng(1)
+    for keys in (g.standard_normal(C), -g.random(C), np.where(g.random(C) < 0.5, -0.0, 0.0),
+                 np.concatenate([np.full(150, -1.5), np.full(150, 2.0)])):
+        assert np.array_equal(sp.inhibition.process(keys), canonical_topk(keys + 0.0, k))
