@@ -206,7 +206,7 @@ def test_bench_reference_arm_prints_the_contract_line():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "30",
-                          "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=root)
+                          "--warmup", "3", "--workload", "cfg2"], capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
