@@ -46,7 +46,8 @@ class Engine:
                  max_segments=None, max_synapses_per_segment=128, match_capacity=None,
                  learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
                  fused="auto", fused_ctas=None, fused_threads=None, column_shard=None, parallel_rng="auto", segment_shard=None,
-                 exchange_match_capacity=None, exchange_recycle_capacity=None):
+                 exchange_match_capacity=None, exchange_recycle_capacity=None, lazy_rng="auto", skip_gran=None,
+                 skip_min=None, skip_polys=None):
         """``column_shard=(rank, world)``: this engine owns columns
         [rank*C/world, (rank+1)*C/world) of the spatial pooler (permanence, mask, duty
         cycles).  ``segment_shard=(rank, world)``: it holds the synapse rows of the
@@ -142,6 +143,19 @@ class Engine:
         ctx.rng_ring_words, ctx.rng_step_words, ctx.ring_len = ring_words, step_words, int(ring_len)
         ctx.jump_polys = (step_words + step_words // 2) // _mtjump.CHUNK_WORDS + 3 if parallel_rng else 0
         ctx.rng_lookahead = min(2 * (k * c + 4 * k) + 2 * nat.MT_N, step_words // 2) if parallel_rng else 0
+        # lazy draws (csrc/mt19937.cuh): rand(L, W+1) is only stepped over and the rows that are read are
+        # produced by table jumps -- the cooperative-grid kernels of networks that draw a lot per step
+        if lazy_rng == "auto":
+            lazy_rng = bool(parallel_rng) and fused in ("grid", "shard")
+        if lazy_rng and fused in ("grid", "shard"):
+            gran = int(skip_gran) if skip_gran else 4096
+            while skip_gran is None and (step_words + step_words // 4) // gran > 4096:
+                gran *= 2  # table of at most ~4096 polynomials (2496 B each)
+            ctx.skip_gran = gran
+            ctx.skip_polys = int(skip_polys) if skip_polys else (step_words + step_words // 4) // gran + 8
+            ctx.skip_min = int(skip_min) if skip_min else max(2 * gran, 1 << 16)
+            ctx.job_cap = 64 + step_words // _mtjump.WINDOW_WORDS + 2
+            ctx.lazy_policy = 1 if lazy_rng == "always" else 0
         ctx.fused_mode = {"off": 0, "cluster": 1, "grid": 2, "shard": 3}[fused]
         if fused_ctas is None:
             fused_ctas = 16 if fused == "cluster" else self.sm_count
@@ -187,6 +201,9 @@ class Engine:
         if ctx.jump_polys:
             tab = _mtjump.jump_table(ctx.jump_polys, cache_dir=os.path.dirname(nat.LIB_PATH))
             self.buf["mt_jump"].copy_(torch.from_numpy(tab.view(np.int32).reshape(-1)).to(self.device))
+        if ctx.skip_polys:
+            tab = _mtjump.skip_table(ctx.skip_polys, ctx.skip_gran, cache_dir=os.path.dirname(nat.LIB_PATH))
+            self.buf["mt_skip"].copy_(torch.from_numpy(tab.view(np.int32).reshape(-1)).to(self.device))
         nat.check(nat.lib.bh_init(C.byref(ctx), self.stream), "bh_init")
         if self.seg_world > 1:  # this rank's exchange record / the gathered records of all ranks
             n = int(nat.lib.bh_tm_shard_xch_ints(C.byref(ctx)))
@@ -224,6 +241,8 @@ class Engine:
             "xk_keys": W * min(k, CL) if x.fused_mode == 3 else 0,
             "xk_cols": W * min(k, CL) if x.fused_mode == 3 else 0, "blk": 8 * 1024, "topk_ws": 81920, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
             "rng64": nat.R_COUNT, "sc": nat.SC_COUNT,
+            "mt_skip": x.skip_polys * nat.MT_N, "rng_jump": x.job_cap * 640 if x.skip_polys else 0,
+            "grow_list": x.learn_capacity * 3 if x.skip_polys else 0,
             "input_ring": x.ring_len * x.input_words, "input_dev": x.mask_stride,
             "summary_dev": nat.summary_ints(k),
         }

@@ -114,6 +114,90 @@ def jump_table(n_polys: int, cache_dir: str | None = None) -> np.ndarray:
     return tab
 
 
+# ------------------------------------------------------------------------------ skip table (lazy draws)
+_MASK = (1 << DEGREE) - 1
+
+
+def _reduce_int(x: int) -> int:
+    """x(t) mod phi(t), polynomials over GF(2) as Python integers (bit i = coefficient of t^i)."""
+    while x >> DEGREE:
+        hi = x >> DEGREE
+        x &= _MASK
+        for e in PHI[:-1]:  # t^(19937 + j) = XOR_e t^(e + j)
+            x ^= hi << e
+    return x
+
+
+def _square_int(x: int) -> int:
+    return _reduce_int(int(format(x, "b"), 4))  # bit i -> bit 2i
+
+
+def _mul_int(a: int, b: int) -> int:
+    """a(t) * b(t) mod phi: the carry-less product as an FFT convolution of the coefficient vectors
+    (counts <= 19937 are exact in float64), then the sparse reduction."""
+    n = 1 << 16
+    av = np.frombuffer(a.to_bytes(n // 8, "little"), dtype=np.uint8)
+    bv = np.frombuffer(b.to_bytes(n // 8, "little"), dtype=np.uint8)
+    ab = np.unpackbits(av, bitorder="little").astype(np.float64)
+    bb = np.unpackbits(bv, bitorder="little").astype(np.float64)
+    conv = np.fft.irfft(np.fft.rfft(ab) * np.fft.rfft(bb), n)
+    bits = (np.rint(conv).astype(np.int64) & 1).astype(np.uint8)
+    return _reduce_int(int.from_bytes(np.packbits(bits, bitorder="little").tobytes(), "little"))
+
+
+def _pack_int(g: int) -> np.ndarray:
+    return np.frombuffer(g.to_bytes(MT_N * 4, "little"), dtype=np.uint32).copy()
+
+
+def skip_table(n_polys: int, gran: int, cache_dir: str | None = None) -> np.ndarray:
+    """uint32 [n_polys][624]: row b - 1 = t^(b * gran) mod phi, b = 1..n_polys -- the jumps of the lazy
+    draws (csrc/mt19937.cuh): x[m + a + b * gran + j] = XOR_{i : row[b-1][i]} x[m + a + i + j]."""
+    n_polys, gran = int(n_polys), int(gran)
+    path = None
+    if cache_dir:
+        prefix = f"mtskip_g{gran}_n"
+        path = os.path.join(cache_dir, f"{prefix}{n_polys}.npy")
+        try:
+            cached = sorted((int(f[len(prefix):-4]), f) for f in os.listdir(cache_dir)
+                            if f.startswith(prefix) and f.endswith(".npy") and f[len(prefix):-4].isdigit())
+        except OSError:
+            cached = []
+        for n, f in cached:
+            if n >= n_polys:
+                try:
+                    tab = np.load(os.path.join(cache_dir, f))
+                    if tab.shape == (n, MT_N) and tab.dtype == np.uint32:
+                        return np.ascontiguousarray(tab[:n_polys])
+                except Exception:
+                    pass
+    tab = np.zeros((n_polys, MT_N), dtype=np.uint32)
+    if gran <= 8 * DEGREE:  # multiplying by t^gran is a shift and a short reduction
+        step = None
+    else:
+        step = 2  # t
+        e, base, acc = gran, 2, 1
+        while e:  # t^gran by square and multiply
+            if e & 1:
+                acc = _mul_int(acc, base) if acc != 1 else base
+            e >>= 1
+            if e:
+                base = _square_int(base)
+        step = acc
+    g = 1
+    for p in range(n_polys):
+        g = _reduce_int(g << gran) if step is None else (_mul_int(g, step) if g != 1 else step)
+        tab[p] = _pack_int(g)
+    if path:
+        try:
+            tmp = path + f".{os.getpid()}.tmp"
+            with open(tmp, "wb") as f:
+                np.save(f, tab)
+            os.replace(tmp, path)
+        except OSError:
+            pass
+    return tab
+
+
 # ------------------------------------------------------------------------------ self check
 def raw_stream(key: np.ndarray, n: int) -> np.ndarray:
     """Untempered MT19937 words x[0..n) continuing key = x[0..624) (block-vectorised)."""

@@ -14,13 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BITHTM_B200_LIB") or os.path.join(_HERE, "_lib", "libbithtm_b200.so")  # env: A/B builds
 
 MT_N = 624
-ABI_VERSION = 9
-R_COUNT = 16  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
+ABI_VERSION = 10
+R_COUNT = 32  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)
 (SC_STEP, SC_HAVE_PREV, SC_NSEG, SC_NSEG_NEXT, SC_M, SC_W0, SC_W1, SC_L0, SC_L, SC_P, SC_NU, SC_NR,
  SC_STATUS, SC_MT_POS, SC_X_MATCH, SC_X_RECYC_AVAIL, SC_X_RECYC_TOTAL, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN,
- SC_JIT_PENDING, SC_WNONE0, SC_WNONE1) = range(23)
+ SC_JIT_PENDING, SC_WNONE0, SC_WNONE1, SC_NGROW) = range(24)
 SC_COUNT = 32
 
 ST_SEG_OVERFLOW, ST_SYN_OVERFLOW, ST_MATCH_OVERFLOW, ST_LEARN_OVERFLOW, ST_RAND_OVERFLOW, ST_PRI_TIE = 1, 2, 4, 8, 16, 32
@@ -61,7 +61,9 @@ class BhCtx(C.Structure):
         ("rng_ring_words", C.c_int64), ("rng_step_words", C.c_int64), ("col_lo", C.c_int32), ("col_local", C.c_int32),
         ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
         ("seg_rank", C.c_int32), ("seg_world", C.c_int32), ("xm_cap", C.c_int32), ("xr_cap", C.c_int32),
-        ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32),
+        ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32), ("device", C.c_int32), ("skip_polys", C.c_int32),
+        ("skip_gran", C.c_int32), ("job_cap", C.c_int32), ("lazy_policy", C.c_int32), ("reserved1", C.c_int32),
+        ("skip_min", C.c_int64),
         ("sp_threshold", C.c_double), ("sp_delta_on", C.c_double), ("sp_delta_off", C.c_double),
         ("tm_learn_on", C.c_double), ("tm_learn_off", C.c_double),
         ("tm_punish_on", C.c_double), ("tm_punish_off", C.c_double),
@@ -83,6 +85,7 @@ class BhCtx(C.Structure):
         ("learn_list", _P), ("punish_list", _P), ("recyc_list", _P),
         ("x_send", _P), ("xk_keys", _P), ("xk_cols", _P), ("blk", _P), ("topk_ws", _P),
         ("mt_key", _P), ("rng_ring", _P), ("mt_jump", _P), ("rng64", _P),
+        ("mt_skip", _P), ("rng_jump", _P), ("grow_list", _P),
         ("xpeer", _P * 8),
         ("sc", _P), ("input_ring", _P), ("input_dev", _P), ("input_pinned", _P),
         ("summary_dev", _P), ("summary_pinned", _P),
@@ -100,7 +103,8 @@ DEVICE_BUFFERS = {
     "winners": "int32", "unacc": "int32", "m_seg": "int32", "m_conn": "int32", "m_jit": "float32",
     "m_flag": "uint8", "learn_list": "int32", "punish_list": "int32", "recyc_list": "int32",
     "x_send": "int32", "xk_keys": "float64", "xk_cols": "int32", "blk": "int32", "topk_ws": "int32",
-    "mt_key": "int32", "rng_ring": "int32", "mt_jump": "int32", "rng64": "int64", "sc": "int32", "input_ring": "int32", "input_dev": "int32",
+    "mt_key": "int32", "rng_ring": "int32", "mt_jump": "int32", "rng64": "int64",
+    "mt_skip": "int32", "rng_jump": "int32", "grow_list": "int32", "sc": "int32", "input_ring": "int32", "input_dev": "int32",
     "summary_dev": "int32",
 }
 

@@ -134,6 +134,9 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->rng_ring, (size_t)x->rng_ring_words);
   cv.take(x->mt_jump, (size_t)x->jump_polys * BH_MT_N);
   cv.take(x->rng64, (size_t)R_COUNT);
+  cv.take(x->mt_skip, (size_t)x->skip_polys * BH_MT_N);
+  cv.take(x->rng_jump, x->skip_polys > 0 ? (size_t)x->job_cap * RNG_JOB_STRIDE : 0);
+  cv.take(x->grow_list, x->skip_polys > 0 ? (size_t)x->learn_capacity * 3 : 0);
   cv.take(x->sc, (size_t)BH_SC_COUNT);
   cv.take(x->input_ring, (size_t)x->ring_len * x->input_words);
   cv.take(x->input_dev, (size_t)x->mask_stride);
@@ -166,6 +169,11 @@ static int check_ctx(const bh_ctx* x) {
   if (x->jump_polys > 0 && (long long)x->jump_polys * RNG_CHUNK < x->rng_step_words + x->rng_step_words / 2 + RNG_CHUNK)
     return BH_E_BADARG;
   if (x->jump_polys < 0 || x->rng_lookahead < 0) return BH_E_BADARG;
+  if (x->skip_polys < 0) return BH_E_BADARG;
+  if (x->skip_polys > 0) {  // lazy draws (mt19937.cuh): table granularity, and a job slot for every chunk of the largest step
+    if (x->skip_gran < 32 || (x->skip_gran & (x->skip_gran - 1)) || x->skip_min < 2LL * x->skip_gran) return BH_E_BADARG;
+    if (x->job_cap < RNG_ROW_SLOT0 + x->rng_step_words / RNG_LAZY_CHUNK + 2) return BH_E_BADARG;
+  }
   // the cluster kernel has no phase for the chunks a many-CTA production plan leaves (fused.cuh)
   if (x->fused_mode == 1 && x->jump_polys > 0) return BH_E_UNSUPPORTED;
   if (x->seg_world > 1) {
@@ -632,6 +640,7 @@ static int fused_smem(const bh_ctx* x) {
   int a = x->mask_stride * 4, b = learn_apply_smem(x);
   int m = a > b ? a : b;
   if (x->fused_mode >= 2 && x->jump_polys > 0 && m < RNG_CHUNK_SMEM) m = RNG_CHUNK_SMEM;
+  if (x->fused_mode >= 2 && x->skip_polys > 0 && m < RNG_LAZY_SMEM_WORDS * 4) m = RNG_LAZY_SMEM_WORDS * 4;
   return m;
 }
 

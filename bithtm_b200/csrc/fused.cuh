@@ -104,15 +104,27 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (b >= nl0 && worker) ph_learn_select_b(c, learning, b - nl0, nlrn);
     BH_SYNC();
     BH_STAMP();
+    // A LAZY step (mt19937.cuh; decided by draw #2, published by the barrier) does not materialise
+    // rand(L, W+1): stage 1 of the learning pass finds the rows that grow, jumps produce their words
+    // and the words after the matrix.
+    const bool lazy = MODE == 2 && c.rng64[R_LAZY] != 0;
     // P4b: the stream words draw #2 planned for many CTAs (mt19937.cuh)
-    if (MODE == 2 && c.jump_polys > 0) {
+    if (MODE == 2 && c.jump_polys > 0 && !lazy) {
       ph_rng_chunks(c, s_dyn, b, nb);
       BH_SYNC();
     }
     BH_STAMP();
     // P5: permanence updates, deletion, growth
-    if (learning) ph_learn_apply(c, s_dyn, b, nb);
-    BH_SYNC();
+    if (MODE == 2 && lazy) {
+      if (learning) ph_learn_apply(c, s_dyn, b, nb, 1);
+      ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b, nb);
+      BH_SYNC();
+      ph_rng_lazy_rows(c, s_dyn, b, nb, [&]() { BH_SYNC(); },
+                       [&](bool produce_rows) { ph_learn_grow(c, s_dyn, b, nb, produce_rows); });
+    } else {
+      if (learning) ph_learn_apply(c, s_dyn, b, nb);
+      BH_SYNC();
+    }
     BH_STAMP();
     // (P6, once a phase of its own -- retiring the previous activation words, the winner index, the segment
     // count -- now runs at the head of P7: the activation words are double-buffered, so nothing it writes is
@@ -120,9 +132,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_STAMP();
     // P7: segment potentials; the drawing CTA is idle for the whole scan: it produces the stream words of
     // the rest of this step and of the next one (the P1 / P3 calls then only top up)
+    if (MODE == 2 && lazy) ph_rng_lazy_tail(c, s_dyn, b, nb);
     ph_post(c, b, nb);
     if (worker) ph_activate_a(c, b, nw);
-    if (rng && nb > 1) ph_rng_speculate(c, 1, true);
+    if (rng && nb > 1 && !lazy) ph_rng_speculate(c, 1, true);  // (a lazy step's tail is being generated right now)
     BH_SYNC();
     BH_STAMP();
     // P8: draw #3 (rand(M)) -- a phase of its own only when the words draw #2 left produced do not

@@ -71,8 +71,36 @@ enum {
   R_STEP_BASE,    // cursor at the first draw of the current step
   R_READY3,       // published with draw #2: doubles draw #3 can take from words already produced
   R_EST,          // stream words a step is expected to draw (previous step + margin): speculation target
-  R_COUNT = 16
+  R_REGION_LO,    // words [REGION_LO, PRODUCED) are in the ring without a gap (a lazy step leaves one below)
+  R_DENSE_LO,     // no word at or above DENSE_LO and below PRODUCED was skipped (sparse chunk starts need this)
+  R_LAZY,         // draw #2 of the current step is LAZY: its rand(L, W+1) matrix is not materialised
+  R_JUMP_BASE,    // lazy step: window base of all its jumps (= R_OFF2)
+  R_TAIL,         // lazy step: first word of the region produced after the skipped matrix (= R_OFF3)
+  R_TAIL_CHUNKS,  //            its chunks, produced by jumps
+  R_TAIL_WORDS,   //            words per tail chunk (a multiple of 623)
+  R_GROW_HIST,    // growing rows of the last two steps (low / high 32 bits): lazy <-> dense policy
+  R_COUNT = 32
 };
+
+// Lazy draw #2 (large networks).  rand(L, W+1) (projections.py:120) is quadratic in the number of active
+// columns, and in steady state almost no learning segment grows, i.e. almost none of its rows is ever read
+// (projections.py:114-115: n_add == 0).  A lazy step therefore only ADVANCES the stream cursor over the
+// matrix and produces (a) the rows of the segments that do grow and (b) the words after the matrix (rand(M),
+// the next step's rand(k, c), the next window) by JUMPS: with D = a + b * skip_gran, the 624 words at
+// base + D are  XOR_{i : g_b[i]} x[base + a + i + j],  g_b = t^(b * skip_gran) mod phi from the table
+// ctx.mt_skip, applied to the window of 20560 + skip_gran produced words that follows the cursor.  Every
+// production job (a row, a chunk of the matrix, a chunk of the tail) is one such jump, computed by the whole
+// grid in units of RNG_UNIT_WORDS polynomial words, followed by the serial recurrence on one CTA.
+#define RNG_JOB_STRIDE 640     // words per job slot of ctx.rng_jump
+#define RNG_UNIT_WORDS 24      // polynomial words per work unit: 6 thread groups x 4
+#define RNG_UNITS_PER_POLY (MT_N / RNG_UNIT_WORDS)
+#define RNG_UNIT_WIN (RNG_UNIT_WORDS * 32 + MT_N + 36)  // window words a unit reads
+#define RNG_TAIL_CHUNK 7476    // 12 * 623: smallest tail chunk
+#define RNG_LAZY_CHUNK RNG_WINDOW  // chunk of the matrix when a lazy step must produce all of it (a chunk that starts
+                                   // inside the jump window must also end inside it)
+#define RNG_MAX_TAIL_CHUNKS 64
+#define RNG_ROW_SLOT0 RNG_MAX_TAIL_CHUNKS  // job slots: tail chunks first, then the rows / chunks of the matrix
+#define RNG_LAZY_SMEM_WORDS 2112  // dynamic shared memory of the lazy phases: unit window + partial output, or MT_RING
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v) {
   uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
@@ -168,7 +196,8 @@ __device__ __noinline__ void rng_produce_serial(const bh_ctx& c, uint32_t* x, lo
   __syncthreads();
   const long long G0 = c.rng64[R_PRODUCED];
   if (G0 >= target) return;
-  const long long hist = G0 < 1078 + MT_N ? G0 : 1078 + MT_N;
+  const long long avail = G0 - c.rng64[R_REGION_LO];  // contiguous history (>= 624 words)
+  const long long hist = avail < 1078 + MT_N ? avail : 1078 + MT_N;
   const long long lo = G0 - hist;
 #pragma unroll 1
   for (long long a = lo + t; a < G0; a += NT) x[(unsigned)a & (MT_RING - 1)] = rng_word(c, a);
@@ -200,7 +229,8 @@ __device__ __noinline__ void rng_chunk(const bh_ctx& c, uint32_t* smem, int p) {
   }
 #endif
   const long long plan_end = base + c.rng64[R_PLAN_CHUNKS] * RNG_CHUNK;  // slots below plan_end - ring are reused
-  const long long lowest = plan_end - c.rng_ring_words > 1 ? plan_end - c.rng_ring_words : 1;
+  long long lowest = plan_end - c.rng_ring_words > 1 ? plan_end - c.rng_ring_words : 1;
+  if (c.rng64[R_DENSE_LO] > lowest) lowest = c.rng64[R_DENSE_LO];  // words a lazy step skipped never existed
   const bool sparse = cb - depth >= lowest;
   if (sparse) {
 #pragma unroll 1
@@ -317,9 +347,50 @@ __device__ __forceinline__ long long rng_room(const bh_ctx& c, long long step_ba
 // make sure they -- plus `lookahead` more words -- are produced, serially when the
 // deficit is small, else by planning chunks for ph_rng_chunks (which must run next).
 // `x` = MT_RING words of shared memory.  Returns through shared state only.
+// Thread 0 of the drawing CTA, draw #2 of `count` doubles = rows of row_doubles (= W + 1) at cursor `cur`:
+// decide whether the step is lazy and, if so, lay out its tail.  Returns the number of tail chunks (0: dense).
+__device__ __forceinline__ int rng_plan_lazy(const bh_ctx& c, long long cur, long long count, int row_doubles) {
+  long long* r = c.rng64;
+  const bool was_lazy = r[R_LAZY] != 0;
+  // growing rows of the step before this one (g_prev) and of the one before that (g_before)
+  const long long hist = r[R_GROW_HIST];
+  const long long g_prev = hist < 0 ? 0x7fffffffLL : (long long)c.sc[BH_SC_NGROW];
+  const long long g_before = hist < 0 ? 0x7fffffffLL : (hist & 0xffffffffLL);
+  r[R_GROW_HIST] = (g_before << 32) | g_prev;
+  c.sc[BH_SC_NGROW] = 0;
+  r[R_LAZY] = 0;
+  if (c.skip_polys <= 0 || c.fused_mode < 2) return 0;
+  const long long D = 2 * count;
+  if (D < c.skip_min || cur < 1) return 0;
+  const long long n_chunks = (D + RNG_LAZY_CHUNK - 1) / RNG_LAZY_CHUNK;
+  // a lazy step that finds many growing rows pays a jump per chunk of the matrix; dense production pays 134
+  // loads per chunk start but needs unbroken history: go lazy once two steps in a row grew few rows, return
+  // to dense when two steps in a row grew most of them
+  if (c.lazy_policy == 0 &&
+      (was_lazy ? (g_prev > n_chunks && g_before > n_chunks) : (g_prev > n_chunks / 4 || g_before > n_chunks / 4)))
+    return 0;
+  // tail: rand(M) + the next step's rand(k, c) + the next step's jump window (+ slack for larger M / W)
+  const long long kc2 = 2LL * c.active_columns * c.cell_dim;
+  const long long need = 2 * (2LL * c.sc[BH_SC_M] + 4LL * c.active_columns) + kc2 + c.skip_gran + RNG_WINDOW +
+                         4LL * row_doubles + 4 * MT_N;
+  long long words = RNG_TAIL_CHUNK;
+  long long q = (need + words - 1) / words;
+  if (q > RNG_MAX_TAIL_CHUNKS) {
+    words = ((need + RNG_MAX_TAIL_CHUNKS - 1) / RNG_MAX_TAIL_CHUNKS + (MT_N - 2)) / (MT_N - 1) * (MT_N - 1);
+    q = (need + words - 1) / words;
+  }
+  if ((D + q * words) / c.skip_gran + 1 > c.skip_polys) return 0;  // beyond the jump table
+  r[R_LAZY] = 1;
+  r[R_JUMP_BASE] = cur;
+  r[R_TAIL] = cur + D;
+  r[R_TAIL_CHUNKS] = q;
+  r[R_TAIL_WORDS] = words;
+  return (int)q;
+}
+
 __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long count, int off_slot, int n_slot,
                                       bool first_of_step, long long lookahead, bool may_plan,
-                                      bool publish_next = false) {
+                                      bool publish_next = false, int row_doubles = 0) {
   __shared__ long long s_serial_target;
   if (threadIdx.x == 0) {
     long long* r = c.rng64;
@@ -337,10 +408,13 @@ __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long co
     r[R_CURSOR] = end;
     long long la = lookahead;
     if (la > c.rng_step_words / 2) la = c.rng_step_words / 2;
-    const long long target = end + la + MT_N;  // keep 624 words past the cursor for state export
+    long long target = end + la + MT_N;  // keep 624 words past the cursor for state export
+    const int lazy_chunks = row_doubles > 0 ? rng_plan_lazy(c, cur, count, row_doubles) : 0;
+    if (lazy_chunks > 0)  // only the jump window is needed now; matrix rows and tail come from jumps
+      target = cur + c.skip_gran + RNG_WINDOW + 2LL * row_doubles + MT_N;
     long long produced = r[R_PRODUCED];
     long long serial_target = target;
-    if (may_plan && c.jump_polys > 0 && target - produced > RNG_PAR_MIN) {
+    if (lazy_chunks == 0 && may_plan && c.jump_polys > 0 && target - produced > RNG_PAR_MIN) {
       // the window must consist of generated words (absolute index >= 1)
       const long long need = produced < 1 + RNG_WINDOW ? 1 + RNG_WINDOW : produced;
       long long chunks = (target - need + RNG_CHUNK - 1) / RNG_CHUNK;
@@ -355,7 +429,18 @@ __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long co
   }
   __syncthreads();
   rng_produce_serial(c, x, s_serial_target);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && row_doubles > 0 && c.rng64[R_LAZY]) {
+    // lazy step: from here on the produced region is the tail (generated before anything reads it)
+    long long* r = c.rng64;
+    const long long tail = r[R_TAIL], len = r[R_TAIL_CHUNKS] * r[R_TAIL_WORDS];
+    r[R_PRODUCED] = tail + len;
+    r[R_REGION_LO] = tail;
+    r[R_DENSE_LO] = tail;
+    long long ready = (len - MT_N) / 2;
+    const long long room = rng_room(c, r[R_STEP_BASE], tail);
+    r[R_OFF3] = tail;
+    r[R_READY3] = ready < room ? ready : room;
+  } else if (threadIdx.x == 0) {
     long long* r = c.rng64;
     if (r[R_PLAN_CHUNKS] > 0) r[R_PLAN_BASE] = r[R_PRODUCED];
     if (publish_next) {
@@ -377,7 +462,8 @@ __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long co
 // Thread 0 of the drawing CTA, after the last draw of a step: what the next step is expected to need.
 __device__ __forceinline__ void rng_finish_step(const bh_ctx& c) {
   long long* r = c.rng64;
-  const long long used = r[R_CURSOR] - r[R_STEP_BASE];
+  long long used = r[R_CURSOR] - r[R_STEP_BASE];
+  if (r[R_LAZY]) used -= 2 * r[R_N2];  // a lazy step never produces its matrix
   long long est = used + used / 4 + 2 * (long long)c.active_columns * c.cell_dim + 2 * MT_N;
   if (est > c.rng_step_words / 2) est = c.rng_step_words / 2;
   r[R_EST] = est;
@@ -400,6 +486,156 @@ __device__ __noinline__ void ph_rng_speculate(const bh_ctx& c, int divisor = 1, 
   rng_produce_serial(c, x, c.rng64[ahead ? R_CURSOR : R_STEP_BASE] + c.rng64[R_EST] / divisor);
 }
 
+// ------------------------------------------------------------------------------------
+// lazy steps: production jobs by jumps
+// ------------------------------------------------------------------------------------
+// kind 0: tail chunk i;  1: row of rand(L, W+1) named by grow-list entry i;  2: chunk i of the whole matrix
+__device__ __forceinline__ void rng_job(const bh_ctx& c, int kind, int i, int row_words, long long& dst, long long& n) {
+  const long long* r = c.rng64;
+  if (kind == 0) {
+    dst = r[R_TAIL] + (long long)i * r[R_TAIL_WORDS];
+    n = r[R_TAIL_WORDS];
+  } else if (kind == 1) {
+    dst = r[R_OFF2] + (long long)c.grow_list[3 * i] * row_words;
+    n = row_words;
+  } else {
+    const long long D = 2 * r[R_N2], off = (long long)i * RNG_LAZY_CHUNK;
+    dst = r[R_OFF2] + off;
+    n = D - off < RNG_LAZY_CHUNK ? D - off : RNG_LAZY_CHUNK;
+  }
+}
+
+// All CTAs: the jumps of jobs [0, n_jobs) of one kind, in units of RNG_UNIT_WORDS polynomial words.  Unit
+// (job, w0): out[job][j] ^= XOR_{i in [32 w0, 32 w0 + 768) : g[i]} x[src + i + j].  blockDim.x >= 960.
+// smem: RNG_LAZY_SMEM_WORDS.  A barrier must follow before the slots are read.
+__device__ __noinline__ void ph_rng_jumps(const bh_ctx& c, uint32_t* smem, int kind, int n_jobs, int row_words, int slot0,
+                                          int b, int nb) {
+  uint32_t* s_win = smem;                 // [RNG_UNIT_WIN], 16-byte aligned
+  uint32_t* s_out = smem + 1472;          // [MT_N]
+  const int t = threadIdx.x, NT = blockDim.x;
+  const long long base = c.rng64[R_JUMP_BASE];
+  const long long n_units = (long long)n_jobs * RNG_UNITS_PER_POLY;
+#pragma unroll 1
+  for (long long u = b; u < n_units; u += nb) {
+    const int job = (int)(u / RNG_UNITS_PER_POLY), w0 = (int)(u - (long long)job * RNG_UNITS_PER_POLY) * RNG_UNIT_WORDS;
+    long long dst, n;
+    rng_job(c, kind, job, row_words, dst, n);
+    const long long D = dst - base;
+    const long long poly = D / c.skip_gran - 1;  // row of mt_skip; -1: the job starts inside the produced window
+    if (poly < 0) continue;                      // (uniform over the CTA)
+    const long long src = base + D % c.skip_gran + 32LL * w0;
+    const uint32_t* gp = c.mt_skip + poly * MT_N;
+#pragma unroll 1
+    for (int i = t; i < RNG_UNIT_WIN; i += NT) s_win[i] = rng_word(c, src + i);
+#pragma unroll 1
+    for (int i = t; i < MT_N; i += NT) s_out[i] = 0u;
+    __syncthreads();
+    if (t < 936) {
+      const int grp = t / 156, q = t - grp * 156;
+      uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll 1
+      for (int wl = grp * 4; wl < grp * 4 + 4; ++wl) {
+        const uint32_t gw = __ldg(gp + w0 + wl);
+        if (gw == 0u) continue;
+        const uint4* wp = reinterpret_cast<const uint4*>(s_win + 32 * wl + 4 * q);
+        uint32_t rr[36];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+          const uint4 v = wp[m];
+          rr[4 * m] = v.x;
+          rr[4 * m + 1] = v.y;
+          rr[4 * m + 2] = v.z;
+          rr[4 * m + 3] = v.w;
+        }
+#pragma unroll
+        for (int bb = 0; bb < 32; ++bb) {
+          if (gw & (1u << bb)) {
+            a0 ^= rr[bb];
+            a1 ^= rr[bb + 1];
+            a2 ^= rr[bb + 2];
+            a3 ^= rr[bb + 3];
+          }
+        }
+      }
+      atomicXor(&s_out[4 * q], a0);
+      atomicXor(&s_out[4 * q + 1], a1);
+      atomicXor(&s_out[4 * q + 2], a2);
+      atomicXor(&s_out[4 * q + 3], a3);
+    }
+    __syncthreads();
+    uint32_t* out = c.rng_jump + (long long)(slot0 + job) * RNG_JOB_STRIDE;
+#pragma unroll 1
+    for (int i = t; i < MT_N; i += NT) {
+      const uint32_t v = s_out[i];
+      if (v) atomicXor(&out[i], v);
+    }
+    __syncthreads();
+  }
+}
+
+// One CTA: job slot -> ring (the 624 jumped words), then the serial recurrence up to the job's length; the slot
+// is left zeroed for its next use.  smem: MT_RING words.  Jobs inside the produced window need nothing.
+__device__ __noinline__ void rng_job_generate(const bh_ctx& c, uint32_t* x, int kind, int job, int row_words, int slot0) {
+  const int t = threadIdx.x, NT = blockDim.x;
+  long long dst, n;
+  rng_job(c, kind, job, row_words, dst, n);
+  if ((dst - c.rng64[R_JUMP_BASE]) / c.skip_gran < 1) return;
+  uint32_t* slot = c.rng_jump + (long long)(slot0 + job) * RNG_JOB_STRIDE;
+  const unsigned long long gm = (unsigned long long)(c.rng_ring_words - 1);
+  __syncthreads();
+#pragma unroll 1
+  for (int j = t; j < MT_N; j += NT) {
+    const uint32_t v = __ldcg(slot + j);
+    slot[j] = 0u;
+    x[(unsigned)(dst + j) & (MT_RING - 1)] = v;
+    c.rng_ring[(unsigned long long)(dst + j) & gm] = v;
+  }
+  __syncthreads();
+  if (n > MT_N) mt_generate(c, x, dst, dst + MT_N, dst + n, dst + MT_N, dst + n);
+}
+
+// The lazy part of a step after its stage-1 learning pass (all CTAs of a cooperative kernel; `sync` = its grid
+// barrier).  Round 1 (tail jumps) was done alongside stage 1.  Here: the jumps of the growing rows, their
+// words, and -- through `grow` -- the growth itself.  Leaves a barrier behind only when rows grew.
+template <typename Sync, typename Grow>
+__device__ __forceinline__ void ph_rng_lazy_rows(const bh_ctx& c, uint32_t* smem, int b, int nb, Sync sync, Grow grow) {
+  const int G = c.sc[BH_SC_NGROW];  // uniform: read after the barrier that ended stage 1
+  if (G <= 0) return;
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int row_words = 2 * (c.sc[BH_SC_W0 + (cur ^ 1)] + 1);
+  const long long D = 2 * c.rng64[R_N2];
+  const int n_chunks = (int)((D + RNG_LAZY_CHUNK - 1) / RNG_LAZY_CHUNK);
+  const bool by_rows = G <= n_chunks && G <= c.job_cap - RNG_ROW_SLOT0;
+  if (by_rows) {
+    ph_rng_jumps(c, smem, 1, G, row_words, RNG_ROW_SLOT0, b, nb);
+    sync();
+    grow(true);  // each CTA generates the words of its rows, then grows them
+  } else {
+    // most rows grow: produce the whole matrix in chunks (check_ctx sizes job_cap for the largest step)
+    const int nj = n_chunks < c.job_cap - RNG_ROW_SLOT0 ? n_chunks : c.job_cap - RNG_ROW_SLOT0;
+    ph_rng_jumps(c, smem, 2, nj, row_words, RNG_ROW_SLOT0, b, nb);
+    sync();
+#pragma unroll 1
+    for (int j = b; j < nj; j += nb) {
+      rng_job_generate(c, smem, 2, j, row_words, RNG_ROW_SLOT0);
+      __syncthreads();
+    }
+    sync();
+    grow(false);
+  }
+  sync();
+}
+
+// The tail of a lazy step: chunk q by CTA q (before anything reads the tail; typically next to the scan).
+__device__ __forceinline__ void ph_rng_lazy_tail(const bh_ctx& c, uint32_t* smem, int b, int nb) {
+  const int Q = (int)c.rng64[R_TAIL_CHUNKS];
+#pragma unroll 1
+  for (int q = b; q < Q; q += nb) {
+    rng_job_generate(c, smem, 0, q, 0, 0);
+    __syncthreads();
+  }
+}
+
 // Host state -> ring (single CTA): key = words [0, 624), cursor = pos.
 __device__ __forceinline__ void ph_rng_import(const bh_ctx& c) {
 #pragma unroll 1
@@ -410,6 +646,11 @@ __device__ __forceinline__ void ph_rng_import(const bh_ctx& c) {
     r[R_CURSOR] = c.sc[BH_SC_MT_POS];
     r[R_PLAN_CHUNKS] = 0;
     r[R_STEP_BASE] = c.sc[BH_SC_MT_POS];
+    r[R_REGION_LO] = 0;
+    r[R_DENSE_LO] = 1;
+    r[R_LAZY] = 0;
+    r[R_TAIL_CHUNKS] = 0;
+    r[R_GROW_HIST] = -1;  // unknown: the first steps draw densely
   }
 }
 

@@ -183,16 +183,26 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (worker) ph_learn_select_b(c, learning, b, nw);
     BH_SYNC();
     BH_STAMP();  // 7: learning lists + draw 2
-    if (c.jump_polys > 0) {
+    const bool lazy = c.rng64[R_LAZY] != 0;  // lazy step (fused.cuh): this rank produces only the rows it stores
+    if (c.jump_polys > 0 && !lazy) {
       ph_rng_chunks(c, s_dyn, b, nb);
       BH_SYNC();
     }
     BH_STAMP();  // 8: stream chunks
-    if (learning) ph_learn_apply(c, s_dyn, b, nb);
-    BH_SYNC();
+    if (lazy) {
+      if (learning) ph_learn_apply(c, s_dyn, b, nb, 1);
+      ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b, nb);
+      BH_SYNC();
+      ph_rng_lazy_rows(c, s_dyn, b, nb, [&]() { BH_SYNC(); },
+                       [&](bool produce_rows) { ph_learn_grow(c, s_dyn, b, nb, produce_rows); });
+    } else {
+      if (learning) ph_learn_apply(c, s_dyn, b, nb);
+      BH_SYNC();
+    }
     ph_post(c, b, nb);
     BH_SYNC();
     BH_STAMP();  // 9: learn + post
+    if (lazy) ph_rng_lazy_tail(c, s_dyn, b, nb);
     if (worker) ph_activate_a(c, b, nw);
     BH_SYNC();
     BH_STAMP();  // 10: segment scan

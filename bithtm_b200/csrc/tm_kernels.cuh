@@ -69,6 +69,7 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
   __shared__ uint32_t x[MT_RING];
   __shared__ long long s_count;
   __shared__ int s_red[32];
+  __shared__ int s_row_doubles;
   int m_before = 0, m_total = 0;
   LearnTotals lt;
   lt.L = 0;
@@ -77,6 +78,7 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
   if (threadIdx.x == 0) {
     int* sc = c.sc;
     const int cur = sc[BH_SC_STEP] & 1;
+    s_row_doubles = sc[BH_SC_W0 + (cur ^ 1)] + 1;  // a row of rand(L, W+1)
     long long count = 0;
     if (which == 1) {
       count = (long long)c.active_columns * c.cell_dim;
@@ -97,7 +99,7 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
   }
   __syncthreads();
   if (which == 1) rng_draw(c, x, s_count, R_OFF1, -1, true, 0, false);
-  else if (which == 2) rng_draw(c, x, s_count, R_OFF2, R_N2, false, c.rng_lookahead, true, true);
+  else if (which == 2) rng_draw(c, x, s_count, R_OFF2, R_N2, false, c.rng_lookahead, true, true, s_row_doubles);
   else {
     rng_draw(c, x, s_count, R_OFF3, R_N3, false, 0, false);
     if (threadIdx.x == 0) rng_finish_step(c);
@@ -517,7 +519,9 @@ __device__ void grow_row(const bh_ctx& c, int row, int s, int n, int n_add, int 
   __syncthreads();
 }
 
-__device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb) {
+// mode 0: both stages (the priority rows are in the stream ring).  mode 1 (lazy steps, mt19937.cuh): stage 1
+// only; growing rows are appended to ctx.grow_list as (row, synapses kept, n_add) for ph_learn_grow.
+__device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb, int mode = 0) {
   __shared__ int s_red[32];
   __shared__ int s_hist[256];
   __shared__ int s_rem;
@@ -578,22 +582,56 @@ __device__ void ph_learn_apply(const bh_ctx& c, uint32_t* s_excl, int b, int nb)
         int n_add = sample - n_act;  // projections.py:114-115
         n_add = n_add < 0 ? 0 : (n_add > cap ? cap : n_add);
         if (learn && n_add > 0) {
-          const int g = atomicAdd(&s_ngrow, 1);
-          s_grow_row[g] = row;
-          s_grow_n[g] = kept;
-          s_grow_add[g] = n_add;
+          if (mode == 1) {
+            const int g = atomicAdd(&c.sc[BH_SC_NGROW], 1);  // learn_capacity entries: g < L always
+            c.grow_list[3 * g] = row;
+            c.grow_list[3 * g + 1] = kept;
+            c.grow_list[3 * g + 2] = n_add;
+          } else {
+            const int g = atomicAdd(&s_ngrow, 1);
+            s_grow_row[g] = row;
+            s_grow_n[g] = kept;
+            s_grow_add[g] = n_add;
+          }
         }
       }
     }
     __syncthreads();
     // ---- stage 2: the whole CTA grows the rows its warps flagged ------------------
     const int ng = s_ngrow;
+    if (t == 0 && ng > 0) atomicAdd(&c.sc[BH_SC_NGROW], ng);  // growing rows of the step (lazy / dense policy)
     for (int g = 0; g < ng; ++g) {
       const int grow = s_grow_row[g];
       const bool pr_ok = (long long)(grow + 1) * (Wp + 1) <= n2;
       grow_row(c, grow, c.learn_list[grow], s_grow_n[g], s_grow_add[g], Wp, prevw, off2, pr_ok, s_excl, s_red,
                s_hist, &s_rem, &s_prefix);
     }
+    __syncthreads();
+  }
+}
+
+// Lazy steps, stage 2: grow the rows of ctx.grow_list (their priority rows were produced by jumps).
+// `produce_rows`: each row's words are a production job of its own (kind 1) that the growing CTA generates
+// first; else the whole matrix was produced in chunks.  smem: max(MT_RING, excl words).
+__device__ __noinline__ void ph_learn_grow(const bh_ctx& c, uint32_t* smem, int b, int nb, bool produce_rows) {
+  __shared__ int s_red[32];
+  __shared__ int s_hist[256];
+  __shared__ int s_rem;
+  __shared__ uint32_t s_prefix;
+  const int G = c.sc[BH_SC_NGROW];
+  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int Wp = c.sc[BH_SC_W0 + (cur ^ 1)];
+  const int* prevw = c.winners + (long long)(cur ^ 1) * c.active_columns * c.cell_dim;
+  const long long off2 = c.rng64[R_OFF2], n2 = c.rng64[R_N2];
+#pragma unroll 1
+  for (int i = b; i < G; i += nb) {
+    const int row = c.grow_list[3 * i], n = c.grow_list[3 * i + 1], n_add = c.grow_list[3 * i + 2];
+    if (produce_rows) {
+      rng_job_generate(c, smem, 1, i, 2 * (Wp + 1), RNG_ROW_SLOT0);
+      __syncthreads();
+    }
+    const bool pr_ok = (long long)(row + 1) * (Wp + 1) <= n2;
+    grow_row(c, row, c.learn_list[row], n, n_add, Wp, prevw, off2, pr_ok, smem, s_red, s_hist, &s_rem, &s_prefix);
     __syncthreads();
   }
 }

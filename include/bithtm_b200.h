@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 9
+#define BH_ABI_VERSION 10
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 81920
@@ -67,6 +67,8 @@ enum {
                        /* 229-243 run lazily from networks.py:76)                   */
   BH_SC_WNONE0,        /* winner_cell of buffer 0 / 1 is None (a step with neither  */
   BH_SC_WNONE1,        /* learning nor return_winner_cell): no growth, no rand(L,W+1) */
+  BH_SC_NGROW,         /* learning segments of this step that grow synapses (n_add > 0,  */
+                       /* projections.py:114-115): the rows of rand(L, W+1) that are read */
   BH_SC_COUNT = 32
 };
 
@@ -119,7 +121,16 @@ typedef struct bh_ctx {
   int32_t device;          /* CUDA device ordinal the buffers live on: every entry point */
                            /* makes it current for the duration of the call (-1 = keep  */
                            /* the calling thread's current device)                     */
-  int32_t reserved0;
+  int32_t skip_polys;      /* rows of mt_skip (0 = every draw is materialised): row b - 1 =  */
+                           /* t^(b * skip_gran) mod phi, b = 1..skip_polys             */
+  int32_t skip_gran;       /* stream words per jump-table step (a power of two)        */
+  int32_t job_cap;         /* slots of rng_jump: production jobs of one lazy step       */
+  int32_t lazy_policy;     /* 0: a step is lazy once few rows grew in the last two steps  */
+                           /* (dense production is cheaper while most rows grow); 1: always */
+  int32_t reserved1;
+  int64_t skip_min;        /* a rand(L, W+1) of at least this many stream words may be  */
+                           /* drawn lazily (fused_mode >= 2): only the rows of growing  */
+                           /* segments are produced, by jumps (csrc/mt19937.cuh)        */
 
   /* ---- constants, evaluated on the host with the reference's expressions ----- */
   double sp_threshold;     /* projections.py:19  permanence >= threshold           */
@@ -199,7 +210,10 @@ typedef struct bh_ctx {
   uint32_t* rng_ring;      /* [rng_ring_words] raw stream words by absolute index   */
   uint32_t* mt_jump;       /* [jump_polys][624] jump polynomials (caller-filled,    */
                            /* bithtm_b200/_mtjump.py) for multi-CTA production      */
-  long long* rng64;        /* [16] producer / consumer cursors (csrc/mt19937.cuh)   */
+  long long* rng64;        /* [32] producer / consumer cursors (csrc/mt19937.cuh)   */
+  uint32_t* mt_skip;       /* [skip_polys][624] jump table (caller-filled, _mtjump.skip_table) */
+  uint32_t* rng_jump;      /* [job_cap][640] jump results of a lazy step (zero between uses)   */
+  int32_t* grow_list;      /* [learn_capacity][3] (row, synapses kept, n_add) of growing rows */
 
   /* ---- fused sharded step: exchange regions of all ranks, mapped into this process ---- */
   int32_t* xpeer[BH_MAX_RANKS]; /* xpeer[r] = base of rank r's region of bh_xch_region_ints() */

@@ -195,6 +195,17 @@ def test_lockstep_tiny(fused, ctas):
     _lockstep("tiny", fused=fused, fused_ctas=ctas)
 
 
+@pytest.mark.parametrize("name,ctas,policy", [("tiny", None, "always"), ("tiny", 5, True), ("tiny", 1, "always"),
+                                              ("odd", None, True), ("odd", 7, "always"), ("mid", None, "always")])
+def test_lockstep_lazy_draws(name, ctas, policy):
+    """Lazy rand(L, W+1) (csrc/mt19937.cuh) forced on at small sizes: the matrix is stepped over, the rows of
+    growing segments, whole-matrix chunks and the words after the matrix are produced by table jumps.  Any
+    wrong stream word shows up in the growth, the jitter or the final np.random position."""
+    htm, _ = _lockstep(name, steps=600 if name == "mid" else None, fused="grid", fused_ctas=ctas, lazy_rng=policy,
+                       skip_gran=32, skip_min=64, skip_polys=6000)
+    assert htm.engine.ctx.skip_polys == 6000
+
+
 @pytest.mark.parametrize("ctas,threads", [(4, 512), (8, 256), (16, 768)])
 def test_lockstep_cluster_kernel_with_smaller_ctas(ctas, threads):
     """The cluster kernel with fewer threads per CTA (the StreamBatch configuration, several
@@ -740,6 +751,13 @@ def test_cfg3_lockstep_oracle_fused_grid():
     production, grid-wide top-k at 148 CTAs) against the oracle at cfg3's full size."""
     htm = _cfg3_lockstep("grid", 48, patterns=3)
     assert htm.engine.ctx.fused_mode == 2
+
+
+@pytest.mark.gpu
+def test_cfg3_lockstep_oracle_lazy_draws():
+    """The same with every large rand(L, W+1) drawn lazily (jump table of 4096-word steps): rows, chunks and tail."""
+    htm = _cfg3_lockstep("grid", 24, patterns=3, lazy_rng="always")
+    assert htm.engine.ctx.skip_polys > 0 and htm.engine.ctx.lazy_policy == 1
 
 
 @pytest.mark.gpu
