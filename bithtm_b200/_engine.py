@@ -47,7 +47,7 @@ class Engine:
                  learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
                  fused="auto", fused_ctas=None, fused_threads=None, column_shard=None, parallel_rng="auto", segment_shard=None,
                  exchange_match_capacity=None, exchange_recycle_capacity=None, lazy_rng="auto", skip_gran=None,
-                 skip_min=None, skip_polys=None):
+                 skip_min=None, skip_polys=None, tail_chunks=None):
         """``column_shard=(rank, world)``: this engine owns columns
         [rank*C/world, (rank+1)*C/world) of the spatial pooler (permanence, mask, duty
         cycles).  ``segment_shard=(rank, world)``: it holds the synapse rows of the
@@ -156,6 +156,7 @@ class Engine:
             ctx.skip_min = int(skip_min) if skip_min else max(2 * gran, 1 << 16)
             ctx.job_cap = 64 + step_words // _mtjump.WINDOW_WORDS + 2
             ctx.lazy_policy = 1 if lazy_rng == "always" else 0
+            ctx.tail_chunks = int(tail_chunks or 0)
         ctx.fused_mode = {"off": 0, "cluster": 1, "grid": 2, "shard": 3}[fused]
         if fused_ctas is None:
             fused_ctas = 16 if fused == "cluster" else self.sm_count

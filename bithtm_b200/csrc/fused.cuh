@@ -132,10 +132,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_STAMP();
     // P7: segment potentials; the drawing CTA is idle for the whole scan: it produces the stream words of
     // the rest of this step and of the next one (the P1 / P3 calls then only top up)
+    // (a lazy step: its last CTAs generate the words after the skipped matrix instead of scanning)
+    const int ns = (MODE == 2 && lazy) ? nb - rng_tail_ctas(c, nb) : nw;  // CTAs that scan the segments
+    const bool scanner = b < ns;
     if (MODE == 2 && lazy) ph_rng_lazy_tail(c, s_dyn, b, nb);
     ph_post(c, b, nb);
-    if (worker) ph_activate_a(c, b, nw);
-    if (rng && nb > 1 && !lazy) ph_rng_speculate(c, 1, true);  // (a lazy step's tail is being generated right now)
+    if (scanner) ph_activate_a(c, b, ns);
+    if (rng && nb > 1 && !lazy) ph_rng_speculate(c, 1, true);
     BH_SYNC();
     BH_STAMP();
     // P8: draw #3 (rand(M)) -- a phase of its own only when the words draw #2 left produced do not
@@ -144,18 +147,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     int m_before, m_total;  // this CTA's offset in the matching list and its length (reused by P9)
     {
       __shared__ int s_red3[32];
-      blk_prefix(BLK(c, BLK_MATCH), worker ? b : 0, nw, s_red3, m_before, m_total);
+      blk_prefix(BLK(c, BLK_MATCH), scanner ? b : 0, ns, s_red3, m_before, m_total);
       ready3 = (long long)(m_total < c.match_capacity ? m_total : c.match_capacity) <= c.rng64[R_READY3];
       __syncthreads();
     }
     if (!ready3) {
-      if (rng) ph_draw(c, 3, 1, nw);
+      if (rng) ph_draw(c, 3, 1, ns);
       BH_SYNC();
     }
     BH_STAMP();
     // P9: matching list, jitter, predictions; completes the step
-    if (ready3 && rng) ph_draw3_ready(c, nw, m_total);
-    if (worker) ph_activate_b(c, b, nw, ready3, true, m_before, m_total);
+    if (ready3 && rng) ph_draw3_ready(c, ns, m_total);
+    if (scanner) ph_activate_b(c, b, ns, ready3, true, m_before, m_total);
     BH_SYNC();
     BH_STAMP();
   }

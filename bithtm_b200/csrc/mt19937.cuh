@@ -90,17 +90,18 @@ enum {
 // base + D are  XOR_{i : g_b[i]} x[base + a + i + j],  g_b = t^(b * skip_gran) mod phi from the table
 // ctx.mt_skip, applied to the window of 20560 + skip_gran produced words that follows the cursor.  Every
 // production job (a row, a chunk of the matrix, a chunk of the tail) is one such jump, computed by the whole
-// grid in units of RNG_UNIT_WORDS polynomial words, followed by the serial recurrence on one CTA.
+// grid in units of a few polynomial words, followed by the serial recurrence on one CTA.
 #define RNG_JOB_STRIDE 640     // words per job slot of ctx.rng_jump
-#define RNG_UNIT_WORDS 24      // polynomial words per work unit: 6 thread groups x 4
-#define RNG_UNITS_PER_POLY (MT_N / RNG_UNIT_WORDS)
-#define RNG_UNIT_WIN (RNG_UNIT_WORDS * 32 + MT_N + 36)  // window words a unit reads
+#define RNG_UNIT_MAX 48        // most polynomial words per work unit (6 thread groups x 8)
+#define RNG_UNIT_WIN(uw) ((uw) * 32 + MT_N + 36)  // window words a unit of uw polynomial words reads
 #define RNG_TAIL_CHUNK 7476    // 12 * 623: smallest tail chunk
 #define RNG_LAZY_CHUNK RNG_WINDOW  // chunk of the matrix when a lazy step must produce all of it (a chunk that starts
                                    // inside the jump window must also end inside it)
 #define RNG_MAX_TAIL_CHUNKS 64
 #define RNG_ROW_SLOT0 RNG_MAX_TAIL_CHUNKS  // job slots: tail chunks first, then the rows / chunks of the matrix
-#define RNG_LAZY_SMEM_WORDS 2112  // dynamic shared memory of the lazy phases: unit window + partial output, or MT_RING
+#define RNG_UNIT_WIN_PAD 2208     // RNG_UNIT_WIN(RNG_UNIT_MAX) rounded up to 16 bytes
+#define RNG_LAZY_SMEM_WORDS (RNG_UNIT_WIN_PAD + MT_N + 16)  // dynamic shared memory of the lazy phases: unit window +
+                                                            // partial output, or MT_RING
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v) {
   uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
@@ -373,12 +374,12 @@ __device__ __forceinline__ int rng_plan_lazy(const bh_ctx& c, long long cur, lon
   const long long kc2 = 2LL * c.active_columns * c.cell_dim;
   const long long need = 2 * (2LL * c.sc[BH_SC_M] + 4LL * c.active_columns) + kc2 + c.skip_gran + RNG_WINDOW +
                          4LL * row_doubles + 4 * MT_N;
-  long long words = RNG_TAIL_CHUNK;
-  long long q = (need + words - 1) / words;
-  if (q > RNG_MAX_TAIL_CHUNKS) {
-    words = ((need + RNG_MAX_TAIL_CHUNKS - 1) / RNG_MAX_TAIL_CHUNKS + (MT_N - 2)) / (MT_N - 1) * (MT_N - 1);
-    q = (need + words - 1) / words;
-  }
+  // few chunks: every chunk start costs a jump (~80 us of one SM), its words only the serial recurrence
+  long long q = c.tail_chunks > 0 ? c.tail_chunks : 4;
+  if (q > RNG_MAX_TAIL_CHUNKS) q = RNG_MAX_TAIL_CHUNKS;
+  long long words = ((need + q - 1) / q + (MT_N - 2)) / (MT_N - 1) * (MT_N - 1);
+  if (words < RNG_TAIL_CHUNK) words = RNG_TAIL_CHUNK;
+  q = (need + words - 1) / words;
   if ((D + q * words) / c.skip_gran + 1 > c.skip_polys) return 0;  // beyond the jump table
   r[R_LAZY] = 1;
   r[R_JUMP_BASE] = cur;
@@ -505,19 +506,24 @@ __device__ __forceinline__ void rng_job(const bh_ctx& c, int kind, int i, int ro
   }
 }
 
-// All CTAs: the jumps of jobs [0, n_jobs) of one kind, in units of RNG_UNIT_WORDS polynomial words.  Unit
-// (job, w0): out[job][j] ^= XOR_{i in [32 w0, 32 w0 + 768) : g[i]} x[src + i + j].  blockDim.x >= 960.
+// All CTAs: the jumps of jobs [0, n_jobs) of one kind.  The n_jobs * 624 polynomial words are cut into units of
+// uw words (a multiple of 6, chosen so that every CTA gets one unit when that is possible).  Unit (job, w0):
+// out[job][j] ^= XOR_{i in [32 w0, 32 (w0 + uw)) : g[i]} x[src + i + j].  blockDim.x >= 960.
 // smem: RNG_LAZY_SMEM_WORDS.  A barrier must follow before the slots are read.
 __device__ __noinline__ void ph_rng_jumps(const bh_ctx& c, uint32_t* smem, int kind, int n_jobs, int row_words, int slot0,
                                           int b, int nb) {
-  uint32_t* s_win = smem;                 // [RNG_UNIT_WIN], 16-byte aligned
-  uint32_t* s_out = smem + 1472;          // [MT_N]
+  uint32_t* s_win = smem;                    // [RNG_UNIT_WIN(uw)], 16-byte aligned
+  uint32_t* s_out = smem + RNG_UNIT_WIN_PAD;  // [MT_N]
   const int t = threadIdx.x, NT = blockDim.x;
   const long long base = c.rng64[R_JUMP_BASE];
-  const long long n_units = (long long)n_jobs * RNG_UNITS_PER_POLY;
+  int uw = (int)(((long long)n_jobs * MT_N + nb - 1) / nb);
+  uw = (uw + 5) / 6 * 6;
+  uw = uw < 6 ? 6 : (uw > RNG_UNIT_MAX ? RNG_UNIT_MAX : uw);
+  const int per_poly = (MT_N + uw - 1) / uw, per_group = uw / 6;
+  const long long n_units = (long long)n_jobs * per_poly;
 #pragma unroll 1
   for (long long u = b; u < n_units; u += nb) {
-    const int job = (int)(u / RNG_UNITS_PER_POLY), w0 = (int)(u - (long long)job * RNG_UNITS_PER_POLY) * RNG_UNIT_WORDS;
+    const int job = (int)(u / per_poly), w0 = (int)(u - (long long)job * per_poly) * uw;
     long long dst, n;
     rng_job(c, kind, job, row_words, dst, n);
     const long long D = dst - base;
@@ -525,8 +531,9 @@ __device__ __noinline__ void ph_rng_jumps(const bh_ctx& c, uint32_t* smem, int k
     if (poly < 0) continue;                      // (uniform over the CTA)
     const long long src = base + D % c.skip_gran + 32LL * w0;
     const uint32_t* gp = c.mt_skip + poly * MT_N;
+    const int win = RNG_UNIT_WIN(uw);
 #pragma unroll 1
-    for (int i = t; i < RNG_UNIT_WIN; i += NT) s_win[i] = rng_word(c, src + i);
+    for (int i = t; i < win; i += NT) s_win[i] = rng_word(c, src + i);
 #pragma unroll 1
     for (int i = t; i < MT_N; i += NT) s_out[i] = 0u;
     __syncthreads();
@@ -534,8 +541,8 @@ __device__ __noinline__ void ph_rng_jumps(const bh_ctx& c, uint32_t* smem, int k
       const int grp = t / 156, q = t - grp * 156;
       uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
 #pragma unroll 1
-      for (int wl = grp * 4; wl < grp * 4 + 4; ++wl) {
-        const uint32_t gw = __ldg(gp + w0 + wl);
+      for (int wl = grp * per_group; wl < (grp + 1) * per_group; ++wl) {
+        const uint32_t gw = w0 + wl < MT_N ? __ldg(gp + w0 + wl) : 0u;
         if (gw == 0u) continue;
         const uint4* wp = reinterpret_cast<const uint4*>(s_win + 32 * wl + 4 * q);
         uint32_t rr[36];
@@ -626,11 +633,18 @@ __device__ __forceinline__ void ph_rng_lazy_rows(const bh_ctx& c, uint32_t* smem
   sync();
 }
 
-// The tail of a lazy step: chunk q by CTA q (before anything reads the tail; typically next to the scan).
-__device__ __forceinline__ void ph_rng_lazy_tail(const bh_ctx& c, uint32_t* smem, int b, int nb) {
+// The tail of a lazy step is generated while the other CTAs scan the segments: by the LAST rng_tail_ctas()
+// CTAs of the grid (which then take no part in the scan), chunk q by the q-th of them.
+__device__ __forceinline__ int rng_tail_ctas(const bh_ctx& c, int nb) {
   const int Q = (int)c.rng64[R_TAIL_CHUNKS];
+  return Q < nb - 1 ? Q : (nb - 1 > 0 ? nb - 1 : 0);  // a single CTA generates first and scans afterwards
+}
+__device__ __forceinline__ void ph_rng_lazy_tail(const bh_ctx& c, uint32_t* smem, int b, int nb) {
+  const int Q = (int)c.rng64[R_TAIL_CHUNKS], ngen = rng_tail_ctas(c, nb);
+  const int first = ngen > 0 ? nb - ngen : 0, stride = ngen > 0 ? ngen : 1;
+  if (b < first) return;
 #pragma unroll 1
-  for (int q = b; q < Q; q += nb) {
+  for (int q = b - first; q < Q; q += stride) {
     rng_job_generate(c, smem, 0, q, 0, 0);
     __syncthreads();
   }

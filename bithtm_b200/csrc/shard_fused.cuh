@@ -202,12 +202,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     ph_post(c, b, nb);
     BH_SYNC();
     BH_STAMP();  // 9: learn + post
+    const int ns = lazy ? nb - rng_tail_ctas(c, nb) : nw;  // lazy step: the last CTAs generate the tail instead
     if (lazy) ph_rng_lazy_tail(c, s_dyn, b, nb);
-    if (worker) ph_activate_a(c, b, nw);
+    if (b < ns) ph_activate_a(c, b, ns);
     BH_SYNC();
     BH_STAMP();  // 10: segment scan
     // P8: this rank's record of matching / recyclable segments -> exchange 2 -> merged global lists
-    if (worker) ph_shard_pack(c, c.x_send, b, nw);
+    if (b < ns) ph_shard_pack(c, c.x_send, b, ns);
     BH_SYNC();
     BH_STAMP();  // 11: record
     xch_exchange(c, 1, c.x_send, n4, b, nb, bar);
@@ -219,10 +220,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     const int M = c.sc[BH_SC_X_MATCH] < c.match_capacity ? c.sc[BH_SC_X_MATCH] : c.match_capacity;
     const bool ready3 = (long long)M <= c.rng64[R_READY3];
     if (!ready3) {
-      if (rng) ph_draw(c, 3, 1, nw);
+      if (rng) ph_draw(c, 3, 1, ns);
       BH_SYNC();
     } else if (rng) {
-      ph_draw3_ready(c, nw);
+      ph_draw3_ready(c, ns);
     }
     if (worker) ph_activate_finish(c, b, nw, ready3);
     BH_SYNC();

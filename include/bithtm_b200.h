@@ -127,7 +127,8 @@ typedef struct bh_ctx {
   int32_t job_cap;         /* slots of rng_jump: production jobs of one lazy step       */
   int32_t lazy_policy;     /* 0: a step is lazy once few rows grew in the last two steps  */
                            /* (dense production is cheaper while most rows grow); 1: always */
-  int32_t reserved1;
+  int32_t tail_chunks;     /* chunks the words after a skipped matrix are produced in (one jump */
+                           /* each; 0 = 4)                                                     */
   int64_t skip_min;        /* a rand(L, W+1) of at least this many stream words may be  */
                            /* drawn lazily (fused_mode >= 2): only the rows of growing  */
                            /* segments are produced, by jumps (csrc/mt19937.cuh)        */
