@@ -637,7 +637,7 @@ extern "C" int bh_tm_step(const bh_ctx* x, int learning, void* stream) {
 // whole step
 // ------------------------------------------------------------------------------------
 static int fused_smem(const bh_ctx* x) {
-  int a = x->mask_stride * 4, b = learn_apply_smem(x);
+  int a = x->mask_stride * 4 + (x->fused_mode >= 2 ? TK2_BINS * 4 : 0), b = learn_apply_smem(x);
   int m = a > b ? a : b;
   if (x->fused_mode >= 2 && x->jump_polys > 0 && m < RNG_CHUNK_SMEM) m = RNG_CHUNK_SMEM;
   if (x->fused_mode >= 2 && x->skip_polys > 0 && m < RNG_LAZY_SMEM_WORDS * 4) m = RNG_LAZY_SMEM_WORDS * 4;

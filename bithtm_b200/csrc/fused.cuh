@@ -58,8 +58,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_STAMP();
     // P0: overlap + boost on all CTAs; draw #1 (rand(k, c)) on the rng CTA
     if (rng) ph_draw(c, 1, 1, nw);
-    if (nb == 1) ph_overlap<true>(c, input, s_dyn, 0, 1);
-    else if (!rng) ph_overlap<true>(c, input, s_dyn, b, nb - 1);  // the rng CTA is busy drawing
+    constexpr bool HIST = MODE == 2;  // the grid-wide selection starts from a histogram built here
+    if (nb == 1) ph_overlap<true, HIST>(c, input, s_dyn, 0, 1);
+    else if (!rng) ph_overlap<true, HIST>(c, input, s_dyn, b, nb - 1);  // the rng CTA is busy drawing
     if (zero_copy) {
       if (b == 0)  // s_dyn holds the input words (ph_overlap staged them)
         for (int i = threadIdx.x; i < c.input_words; i += blockDim.x) c.input_dev[i] = s_dyn[i];
@@ -70,15 +71,43 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     // P1: global inhibition (one CTA)
     if (MODE == 2 && c.column_dim >= 16384) {  // grid-wide selection (its own barriers inside)
       if (b == 0) retire_prev_flags(c);
-      topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, c.active_columns,
-                c.active_cols + (c.sc[BH_SC_STEP] & 1) * c.active_columns, nullptr, c.col_active, b, nb, bar);
+      topk_grid_hist(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, c.active_columns,
+                     c.active_cols + (c.sc[BH_SC_STEP] & 1) * c.active_columns, c.col_active, b, nb, bar);
     } else if (b == 0) {
       ph_topk(c);
     }
     if (rng && nb > 1) ph_rng_speculate(c, 2);  // idle here: produce half of the stream words this step will draw
     BH_SYNC();
     BH_STAMP();
-    // P2: SP learning + duty cycles; bursting / winner bits per active column
+    // P2: SP learning + duty cycles; bursting / winner bits per active column.
+    // Large networks (grid mode): the temporal-memory bookkeeping of P2..P4 is a chain of short dependent steps
+    // over a few thousand items, the SP learning a long bandwidth-bound pass.  A TEAM of the last CTAs runs the
+    // whole chain (winner bits on all of them, a team barrier, then the ordered lists, the learning flags, draw
+    // #2 and the learning lists on the drawing CTA alone) while the other CTAs learn: two phases and barriers less.
+    const int team = (MODE == 2 && nb >= 32 && c.sc[BH_SC_M] <= 32768 && c.sc[BH_SC_NSEG] <= (1 << 18)) ? 8 : 0;
+    if (team) {
+      const int t0 = nb - team;
+      if (b >= t0) {
+        if (b == t0 && c.column_dim >= 16384) tk3_rebin_from_selection(c);
+        ph_select_a(c, b - t0, team);
+        grid_barrier(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT), (unsigned)team);
+        if (rng) {
+          ph_select_b(c, 0, 1, true, team);
+          __syncthreads();
+          ph_learn_select_a(c, learning, 0, 1);
+          __syncthreads();
+          ph_draw(c, 2, learning, 1);
+          ph_learn_select_b(c, learning, 0, 1);
+        }
+      } else {
+        if (learning) ph_sp_learn<false>(c, input, b, t0);
+        ph_duty(c, b, t0);
+      }
+      BH_SYNC();
+      BH_STAMP();
+      BH_STAMP();
+      BH_STAMP();
+    } else {
     if (split) {
       if (b < nsel) {
         ph_select_a(c, b, nsel);
@@ -87,6 +116,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
         ph_duty(c, b - nsel, nb - nsel);
       }
     } else {
+      if (MODE == 2 && rng && c.column_dim >= 16384) tk3_rebin_from_selection(c);  // (no-op unless the selection fell back)
       if (learning) ph_sp_learn<MODE == 1>(c, input, b, nb);
       ph_duty(c, b, nb);
       if (worker) ph_select_a(c, b, nw);
@@ -104,6 +134,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (b >= nl0 && worker) ph_learn_select_b(c, learning, b - nl0, nlrn);
     BH_SYNC();
     BH_STAMP();
+    }  // (!team)
     // A LAZY step (mt19937.cuh; decided by draw #2, published by the barrier) does not materialise
     // rand(L, W+1): stage 1 of the learning pass finds the rows that grow, jumps produce their words
     // and the words after the matrix.

@@ -168,21 +168,47 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_SYNC();
     BH_STAMP();  // 4: unpack + global top-k
     // P2..P7 as in fused.cuh; learning and the segment scan touch only what this rank stores
-    if (learning) ph_sp_learn<false>(c, input, b, nb);
-    ph_duty(c, b, nb);
-    if (worker) ph_select_a(c, b, nw);
-    BH_SYNC();
-    BH_STAMP();  // 5: SP learn + duty + winner bits
-    if (worker) {
-      ph_select_b(c, b, nw);
-      ph_learn_select_a(c, learning, b, nw);
+    // a TEAM of the last CTAs runs the replicated temporal-memory bookkeeping chain while the others learn this
+    // shard's spatial-pooler rows (fused.cuh, P2)
+    const int team = (nb >= 64 && c.sc[BH_SC_M] <= 32768) ? 16 : 0;
+    if (team) {
+      const int t0 = nb - team;
+      if (b >= t0) {
+        ph_select_a(c, b - t0, team);
+        grid_barrier(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT), (unsigned)team);
+        if (rng) {
+          ph_select_b(c, 0, 1, true, team);
+          __syncthreads();
+          ph_learn_select_a(c, learning, 0, 1);
+          __syncthreads();
+          ph_draw(c, 2, learning, 1);
+          ph_learn_select_b(c, learning, 0, 1);
+        }
+      } else {
+        if (learning) ph_sp_learn<false>(c, input, b, t0);
+        ph_duty(c, b, t0);
+      }
+      BH_SYNC();
+      BH_STAMP();  // 5: SP learn + duty | winner bits, lists, learning flags, draw 2, learning lists
+      BH_STAMP();
+      BH_STAMP();
+    } else {
+      if (learning) ph_sp_learn<false>(c, input, b, nb);
+      ph_duty(c, b, nb);
+      if (worker) ph_select_a(c, b, nw);
+      BH_SYNC();
+      BH_STAMP();  // 5: SP learn + duty + winner bits
+      if (worker) {
+        ph_select_b(c, b, nw);
+        ph_learn_select_a(c, learning, b, nw);
+      }
+      BH_SYNC();
+      BH_STAMP();  // 6: lists + learning flags
+      if (rng) ph_draw(c, 2, learning, nw);
+      if (worker) ph_learn_select_b(c, learning, b, nw);
+      BH_SYNC();
+      BH_STAMP();  // 7: learning lists + draw 2
     }
-    BH_SYNC();
-    BH_STAMP();  // 6: lists + learning flags
-    if (rng) ph_draw(c, 2, learning, nw);
-    if (worker) ph_learn_select_b(c, learning, b, nw);
-    BH_SYNC();
-    BH_STAMP();  // 7: learning lists + draw 2
     const bool lazy = c.rng64[R_LAZY] != 0;  // lazy step (fused.cuh): this rank produces only the rows it stores
     if (c.jump_polys > 0 && !lazy) {
       ph_rng_chunks(c, s_dyn, b, nb);

@@ -20,6 +20,56 @@
 #define TK2_MAX_CTAS 256
 #define TK2_INTS (TK2_TAB + TK2_MAX_CTAS)
 
+// Predicted histogram (ctx.topk_ws + TK3_BASE): the overlap phase bins the boosted keys while it produces them,
+// with a binning centred on the PREVIOUS step's k-th key, so that the selection that follows starts from a
+// finished global histogram (no pass of its own, one grid barrier less).  Any monotone binning gives an exact
+// selection; a prediction that misses (threshold below the binned range, > 1024 keys in the threshold bin)
+// only costs the general path.
+#define TK3_BASE 24576
+#define TK3_VALID 0        // a binning is set (else: the exponent bits, which always work and rarely resolve)
+#define TK3_SHIFT 1
+#define TK3_BASE64 1       // u64 index: base key bits (ints 2, 3)
+#define TK3_READY 4        // step + 1 of the step whose keys hist[step & 1] holds
+#define TK3_HIST 8         // [2][TK2_BINS]
+#define TK3_CNT (TK3_HIST + 2 * TK2_BINS)         // [2][8]: members of the threshold bin gathered so far
+#define TK3_IDX (TK3_CNT + 16)                    // [2][1024] their positions
+#define TK3_KEY (TK3_IDX + 2 * 1024)              // [2][1024] u64 keys (8-byte aligned)
+#define TK3_TAB (TK3_KEY + 4 * 1024)              // [256] per CTA: keys of its range in bins above the threshold bin
+#define TK3_INTS (TK3_TAB + 256)
+
+struct Tk3Binning {
+  unsigned long long base;
+  int shift;
+};
+__device__ __forceinline__ Tk3Binning tk3_binning(const int* ws3) {
+  Tk3Binning g;
+  if (ws3[TK3_VALID]) {
+    g.base = reinterpret_cast<const unsigned long long*>(ws3)[TK3_BASE64];
+    g.shift = ws3[TK3_SHIFT];
+  } else {
+    g.base = 0ull;
+    g.shift = 52;
+  }
+  return g;
+}
+// bin 0 = below the binned range (not counted), 1..2046 in range, 2047 = everything above
+__device__ __forceinline__ int tk3_bin(const Tk3Binning& g, unsigned long long key) {
+  if (key < g.base) return 0;
+  const unsigned long long d = (key - g.base) >> g.shift;
+  return d >= (unsigned long long)(TK2_BINS - 2) ? TK2_BINS - 1 : (int)d + 1;
+}
+// binning for the next step from this step's k-th and largest selected key: the k-th key lands in the middle
+// bin, the selected keys span at most 256 bins
+__device__ __forceinline__ void tk3_set_binning(int* ws3, unsigned long long kth, unsigned long long mx) {
+  const unsigned long long range = mx > kth ? mx - kth : 1ull;
+  int s = 0;
+  while (s < 62 && (range >> s) > 256ull) ++s;
+  const unsigned long long below = 1023ull << s;
+  reinterpret_cast<unsigned long long*>(ws3)[TK3_BASE64] = kth > below ? kth - below : 0ull;
+  ws3[TK3_SHIFT] = s;
+  ws3[TK3_VALID] = 1;
+}
+
 __device__ __noinline__ unsigned long long block_reduce_u64(unsigned long long v, bool want_max,
                                                                unsigned long long* sm) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -84,9 +134,19 @@ __device__ __forceinline__ int overlap_group(int mask_stride) {
   return g;
 }
 
-template <bool BOOST>
+template <bool BOOST, bool HIST = false>
 __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* input, uint32_t* s_in, int b, int nb) {
   __shared__ unsigned long long s_range[2];  // max key, max ~key of this CTA
+  // HIST: this CTA's keys in the predicted binning (see TK3_*): TK2_BINS ints of dynamic shared memory after
+  // the staged input
+  int* s_khist = reinterpret_cast<int*>(s_in + c.mask_stride);
+  int* ws3 = c.topk_ws + TK3_BASE;
+  Tk3Binning binning;
+  if (HIST) {
+    binning = tk3_binning(ws3);
+#pragma unroll 1
+    for (int i = threadIdx.x; i < TK2_BINS; i += blockDim.x) s_khist[i] = 0;
+  }
   #pragma unroll 1
   for (int i = threadIdx.x; i < c.mask_stride; i += blockDim.x) s_in[i] = i < c.input_words ? input[i] : 0u;
   if (threadIdx.x < 2) s_range[threadIdx.x] = 0ull;
@@ -113,6 +173,10 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
       const unsigned long long key = (unsigned long long)__double_as_longlong(bo);
       key_min = key < key_min ? key : key_min;
       key_max = key > key_max ? key : key_max;
+      if (HIST) {
+        const int bin = tk3_bin(binning, key);
+        if (bin) atomicAdd(&s_khist[bin], 1);
+      }
     }
   };
   auto popc4 = [](const uint4& m, const uint4& x) {
@@ -197,6 +261,16 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
       atomicMax(&w64[0], s_range[0]);
       atomicMax(&w64[1], s_range[1]);
       c.topk_ws[TK2_BASE + TK2_VALID] = 1;
+    }
+    if (HIST) {  // (the barrier above also completed this CTA's shared histogram)
+      const int step = c.sc[BH_SC_STEP];
+      int* ghist = ws3 + TK3_HIST + (step & 1) * TK2_BINS;
+#pragma unroll 1
+      for (int i = threadIdx.x; i < TK2_BINS; i += blockDim.x) {
+        const int h = s_khist[i];
+        if (h) atomicAdd(&ghist[i], h);
+      }
+      if (b == 0 && threadIdx.x == 0) ws3[TK3_READY] = step + 1;
     }
   }
 }
@@ -1179,6 +1253,178 @@ __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long
 #undef TK_STAMP
 }
 
+// ---------------------------------------------------------------------------------
+// (b) grid-wide selection from the histogram the overlap phase left (TK3_*): ONE grid barrier.  Every CTA
+// finds the bin of the k-th key from the finished global histogram, counts its own keys in higher bins and
+// gathers the members of that bin; after the barrier every CTA ranks the members, derives its output offset
+// and writes its part of the ordered list (as topk_grid stage 3).  Falls back to topk_grid when the
+// prediction missed.  keys[j] is column j (unsharded networks).
+// ---------------------------------------------------------------------------------
+__device__ __noinline__ void topk_grid_hist(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
+                               uint8_t* flags, int b, int nb, unsigned int* bar) {
+  TopkScratch& sm = topk_scratch();
+  int* hist = sm.hist;
+  unsigned long long* cand_key = sm.cand_key;
+  int* cand_idx = sm.cand_idx;
+  __shared__ int s_scan[32];
+  __shared__ int s_bin, s_rem, s_ncand, s_kth_idx;
+  __shared__ unsigned long long s_kth_key;
+  int* ws3 = c.topk_ws + TK3_BASE;
+  int* ws = c.topk_ws + TK2_BASE;
+  const int t = threadIdx.x, NT = blockDim.x;
+  const int step = c.sc[BH_SC_STEP], par = step & 1;
+  int* ghist = ws3 + TK3_HIST + par * TK2_BINS;
+  int* gcount = ws3 + TK3_CNT + par * 8;
+  int* gidx = ws3 + TK3_IDX + par * 1024;
+  unsigned long long* gkey = reinterpret_cast<unsigned long long*>(ws3 + TK3_KEY) + par * 1024;
+  int* tab = ws3 + TK3_TAB;
+  const Range rg = block_range(n, b, nb);
+  bool ok = ws3[TK3_READY] == step + 1 && nb <= TK2_MAX_CTAS;
+  if (t == 0) s_ncand = -1;
+  __syncthreads();
+  if (ok) {  // bins in descending order: the bin in which the cumulative count reaches k
+    const int per = (TK2_BINS + NT - 1) / NT;
+    int sum = 0;
+    for (int i = 0; i < per; ++i) {
+      const int bin = TK2_BINS - 1 - (t * per + i);
+      const int h = bin >= 1 ? ghist[bin] : 0;
+      hist[t * per + i] = h;  // (descending order; reused below)
+      sum += h;
+    }
+    int total;
+    const int before = block_excl_scan(sum, s_scan, total);
+    if (before < k && before + sum >= k) {
+      int r = k - before;
+      for (int i = 0; i < per; ++i) {
+        const int h = hist[t * per + i];
+        if (r > 0 && h >= r) {
+          s_bin = TK2_BINS - 1 - (t * per + i);
+          s_rem = r;
+          s_ncand = h;
+          r = -1;
+        } else if (r > 0) {
+          r -= h;
+        }
+      }
+    }
+    __syncthreads();
+    ok = s_ncand >= 0 && s_ncand <= TOPK_THREADS;  // threshold inside the binned range, few keys in its bin
+  }
+  if (!ok) {  // uniform over the grid: the general selection (own histogram pass)
+    if (b == 0 && t == 0) ws3[TK3_READY] = 0;
+    topk_grid(c, keys, n, k, out, nullptr, flags, b, nb, bar);
+    return;
+  }
+  const int bin = s_bin, rem = s_rem;
+  const Tk3Binning binning = tk3_binning(ws3);
+  int above = 0;
+#pragma unroll 1
+  for (int j = rg.begin + t; j < rg.end; j += NT) {
+    const unsigned long long key = keys[j];
+    const int kb = tk3_bin(binning, key);
+    above += kb > bin ? 1 : 0;
+    if (kb == bin) {
+      const int p = atomicAdd(gcount, 1);
+      gkey[p] = key;
+      gidx[p] = j;
+    }
+  }
+  above = block_sum(above, s_scan);
+  if (t == 0) tab[b] = above;
+  grid_barrier(bar, nb);
+  const int nc = *gcount;
+#pragma unroll 1
+  for (int i = t; i < nc; i += NT) {
+    cand_key[i] = gkey[i];
+    cand_idx[i] = gidx[i];
+  }
+  __syncthreads();
+  if (t < nc) {
+    const unsigned long long mk = cand_key[t];
+    const int mi = cand_idx[t];
+    int ahead = 0;
+#pragma unroll 2
+    for (int i = 0; i < nc; ++i) {
+      const unsigned long long okey = cand_key[i];
+      ahead += (okey > mk || (okey == mk && cand_idx[i] < mi)) ? 1 : 0;
+    }
+    if (ahead == rem - 1) {
+      s_kth_key = mk;
+      s_kth_idx = mi;
+    }
+  }
+  __syncthreads();
+  const unsigned long long kth_key = s_kth_key;
+  const int kth_idx = s_kth_idx;
+  int before = 0;
+  if (t < nc) {  // selected members of the bin that precede this CTA's range
+    const unsigned long long mk = cand_key[t];
+    const int mi = cand_idx[t];
+    before = (mi < rg.begin && (mk > kth_key || (mk == kth_key && mi <= kth_idx))) ? 1 : 0;
+  }
+#pragma unroll 1
+  for (int i = t; i < b; i += NT) before += tab[i];
+  int base_sel = block_sum(before, s_scan);
+#pragma unroll 1
+  for (int tile = rg.begin; tile < rg.end; tile += NT) {
+    const int j = tile + t;
+    const unsigned long long key = j < rg.end ? keys[j] : 0ull;
+    const bool take = j < rg.end && (key > kth_key || (key == kth_key && j <= kth_idx));
+    int sel_total;
+    const int pos = base_sel + block_excl_scan(take ? 1 : 0, s_scan, sel_total);
+    if (take && pos < k) {
+      out[pos] = j;
+      if (flags) flags[j] = 1;
+    }
+    base_sel += sel_total;
+  }
+  if (b == nb - 1) {  // (the last CTA: after its own reads) leave the workspaces clean for the next call
+    __syncthreads();
+    int* oh = ws3 + TK3_HIST + (par ^ 1) * TK2_BINS;
+#pragma unroll 1
+    for (int i = t; i < TK2_BINS; i += NT) oh[i] = 0;
+    if (t == 0) {
+      ws3[TK3_CNT + (par ^ 1) * 8] = 0;
+      unsigned long long* w64 = reinterpret_cast<unsigned long long*>(ws);
+      const unsigned long long mx = w64[0];
+      w64[0] = 0ull;
+      w64[1] = 0ull;
+      ws[TK2_VALID] = 0;
+      tk3_set_binning(ws3, kth_key, mx > kth_key ? mx : kth_key);
+    }
+  }
+}
+
+// After a selection that did not set the binning itself (topk_grid fallback): from the selected keys.
+// One CTA, in a later phase (the selection's output must be complete).
+__device__ __forceinline__ void tk3_rebin_from_selection(const bh_ctx& c) {
+  __shared__ unsigned long long s_u64b[32];
+  int* ws3 = c.topk_ws + TK3_BASE;
+  const int step = c.sc[BH_SC_STEP];
+  if (ws3[TK3_READY] == step + 1) return;  // topk_grid_hist succeeded and set it
+  const int k = c.active_columns;
+  const int* act = c.active_cols + (step & 1) * k;
+  const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(c.boosted);
+  unsigned long long mn = ~0ull, mx = 0ull;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const unsigned long long key = keys[act[i]];
+    mn = key < mn ? key : mn;
+    mx = key > mx ? key : mx;
+  }
+  mn = block_reduce_u64(mn, false, s_u64b);
+  mx = block_reduce_u64(mx, true, s_u64b);
+  if (threadIdx.x == 0) tk3_set_binning(ws3, mn, mx);
+  // the histogram of the NEXT step (other parity) must start empty
+  int* oh = ws3 + TK3_HIST + ((step & 1) ^ 1) * TK2_BINS;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < TK2_BINS; i += blockDim.x) oh[i] = 0;
+  int* mine = ws3 + TK3_HIST + (step & 1) * TK2_BINS;  // and this step's was not consumed
+#pragma unroll 1
+  for (int i = threadIdx.x; i < TK2_BINS; i += blockDim.x) mine[i] = 0;
+  if (threadIdx.x < 2) ws3[TK3_CNT + threadIdx.x * 8] = 0;  // (a member count of two steps ago may be left)
+}
+
 // stand-alone cooperative kernels built on topk_multi (grid = one CTA per SM)
 __global__ void __launch_bounds__(TOPK_THREADS, 1) k_topk_multi(const __grid_constant__ bh_ctx c) {
   unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
@@ -1235,14 +1481,19 @@ __device__ __forceinline__ void sp_learn_wide(const bh_ctx& c, const uint32_t* i
   const int cur = c.sc[BH_SC_STEP] & 1;
   const int* act = c.active_cols + cur * k;
   const double d_on = c.sp_delta_on, d_off = c.sp_delta_off, thr = c.sp_threshold;
+  // work unit = a quarter / half of a long row, so that k rows spread evenly over any number of CTAs
+  const int parts = words >= 512 ? 4 : (words >= 256 ? 2 : 1);
+  const int part_words = ((words + parts - 1) / parts + 3) & ~3;
 #pragma unroll 1
-  for (int r = b; r < k; r += nb) {
+  for (int u = b; u < k * parts; u += nb) {
+    const int r = u / parts, part = u - r * parts;
     const int col = act[r] - c.col_lo;  // local row; columns of other shards are skipped
     if (col < 0 || col >= c.col_local) continue;
     double* prow = c.sp_perm + (long long)col * I;
     uint32_t* mrow = c.sp_mask + (long long)col * c.mask_stride;
+    const int w_end = (part + 1) * part_words < words ? (part + 1) * part_words : words;
 #pragma unroll 1
-    for (int w0 = warp * 4; w0 < words; w0 += warps * 4) {  // 4 x 256 B of permanence in flight per warp
+    for (int w0 = part * part_words + warp * 4; w0 < w_end; w0 += warps * 4) {  // 4 x 256 B of permanence in flight per warp
       double p[4];
       uint32_t xin[4];
 #pragma unroll

@@ -227,15 +227,16 @@ __device__ void ph_select_a(const bh_ctx& c, int b, int nb, bool want = true) {
 
 // Phase B: ordered winner / unaccounted lists (row order of active_column, cells
 // ascending: np.where on the [k, c] mask, networks.py:103-104).
-__device__ void ph_select_b(const bh_ctx& c, int b, int nb, bool want = true) {
+// `nb_counts` > 0: ONE CTA (b = 0, nb = 1) forms the whole lists from the counts that nb_counts CTAs left in phase A.
+__device__ void ph_select_b(const bh_ctx& c, int b, int nb, bool want = true, int nb_counts = 0) {
   __shared__ int s_red[32];
   const int k = c.active_columns, cd = c.cell_dim, NT = blockDim.x;
   const int cur = c.sc[BH_SC_STEP] & 1;
   const int* act = c.active_cols + cur * k;
   int* wl = c.winners + (long long)cur * k * cd;
   int w_before, w_total, u_before, u_total;
-  blk_prefix(BLK(c, BLK_WIN), b, nb, s_red, w_before, w_total);
-  blk_prefix(BLK(c, BLK_UNACC), b, nb, s_red, u_before, u_total);
+  blk_prefix(BLK(c, BLK_WIN), b, nb_counts > 0 ? nb_counts : nb, s_red, w_before, w_total);
+  blk_prefix(BLK(c, BLK_UNACC), b, nb_counts > 0 ? nb_counts : nb, s_red, u_before, u_total);
   const Range rg = block_range(k, b, nb);
   int wbase = w_before, ubase = u_before;
   #pragma unroll 1

@@ -69,6 +69,8 @@ enum {
   BH_SC_WNONE1,        /* learning nor return_winner_cell): no growth, no rand(L,W+1) */
   BH_SC_NGROW,         /* learning segments of this step that grow synapses (n_add > 0,  */
                        /* projections.py:114-115): the rows of rand(L, W+1) that are read */
+  BH_SC_BAR2_COUNT,    /* barrier of the CTA team that does the temporal-memory         */
+  BH_SC_BAR2_GEN,      /* bookkeeping while the other CTAs learn the spatial pooler     */
   BH_SC_COUNT = 32
 };
 

@@ -626,34 +626,26 @@ def test_batched_overlap_equals_loop_of_process(I, C, B):
     assert np.array_equal(proj.process(xs[min(5, B - 1)]), want[min(5, B - 1)])
 
 
-@pytest.mark.gpu
-def test_cfg3_full_size_execution_modes_agree():
-    """BASELINE configs[2] at its full size (65536 columns x 16384 inputs, 32 cells, k = 1311):
-    no oracle run is possible, so the size-independent property is that the
-    execution modes -- the whole step as one cooperative kernel with many-CTA stream
-    production and the two-barrier top-k, and one kernel per stage -- leave bit-identical
-    state on the device (permanence, masks, duty cycles, segments, synapses, RNG stream)."""
+def _execution_modes_agree(I, C, c, k, steps, patterns, kw_a, kw_b, min_segments, **common):
+    """Two execution modes of the same network, `steps` device-resident timesteps each: bit-identical state
+    (permanence, masks, duty cycles, segments, synapses, RNG stream).  A size-independent property for sizes
+    and run lengths the oracle cannot follow."""
     import torch
 
     import bithtm_b200 as bithtm
     from bithtm_b200.projections import DenseProjection
 
-    free, _ = torch.cuda.mem_get_info()
-    if free < 40 << 30:
-        pytest.skip("needs ~24 GiB of device memory")
-    I, C, c, k, steps = 16384, 65536, 32, 1311, 40
     g = np.random.default_rng(8)
-    base = g.random((10, I)) < 0.2
-    xs = base[np.arange(steps) % 10] ^ (g.random((steps, I)) < 0.05)
+    base = g.random((patterns, I)) < 0.2
+    xs = base[np.arange(steps) % patterns] ^ (g.random((steps, I)) < 0.05)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(5)
     perm = torch.randn(C, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
 
-    def run(fused):
+    def run(kw):
         np.random.seed(12)
         sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
-        htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy", fused=fused,
-                                                max_segments=1 << 17, max_synapses_per_segment=128)
+        htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy", **common, **kw)
         eng = htm.engine
         htm.temporal_memory._rng.before(eng)
         for t in range(steps):
@@ -662,12 +654,11 @@ def test_cfg3_full_size_execution_modes_agree():
         eng.check_status()
         return htm
 
-    a = run("grid")
-    b = run("off")
+    a = run(kw_a)
+    b = run(kw_b)
     ea, eb = a.engine, b.engine
-    assert ea.ctx.jump_polys > 0 and ea.ctx.fused_mode == 2 and eb.ctx.fused_mode == 0
     S = int(ea.scalars()[2])
-    assert S == int(eb.scalars()[2]) and S > 20000
+    assert S == int(eb.scalars()[2]) and S > min_segments
     for name in ("sp_perm", "sp_mask", "duty", "overlaps", "boosted", "col_pred", "col_act", "col_win", "cell_nseg",
                  "cell_maxjit", "cell_npred"):
         assert torch.equal(ea.buf[name], eb.buf[name]), name
@@ -684,6 +675,32 @@ def test_cfg3_full_size_execution_modes_agree():
     ra.set_state(("MT19937", ka, pa, 0, 0.0))
     rb.set_state(("MT19937", kb, pb, 0, 0.0))
     assert np.array_equal(ra.random_sample(1000), rb.random_sample(1000))
+    return a, b
+
+
+@pytest.mark.gpu
+def test_cfg3_full_size_execution_modes_agree():
+    """BASELINE configs[2] at its full size (65536 columns x 16384 inputs, 32 cells, k = 1311), next to the
+    oracle lock-step tests below: the whole step as one cooperative kernel and one kernel per stage leave
+    bit-identical state on the device after 40 steps."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~24 GiB of device memory")
+    a, b = _execution_modes_agree(16384, 65536, 32, 1311, 40, 10, dict(fused="grid"), dict(fused="off"), 20000,
+                                  max_segments=1 << 17, max_synapses_per_segment=128)
+    assert a.engine.ctx.jump_polys > 0 and a.engine.ctx.fused_mode == 2 and b.engine.ctx.fused_mode == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lazy", ["auto", False])
+def test_grid_kernel_long_run_equals_per_stage(lazy):
+    """700 steps of a 16384-column network (the steady state with its predicted-histogram selection, the
+    bookkeeping team, lazy draws and their occasional fall-backs) against one kernel per stage."""
+    a, b = _execution_modes_agree(1024, 16384, 16, 328, 700, 12, dict(fused="grid", lazy_rng=lazy), dict(fused="off"),
+                                  4000, max_segments=1 << 16)
+    assert a.engine.ctx.fused_mode == 2 and (a.engine.ctx.skip_polys > 0) == (lazy == "auto")
 
 
 def _cfg3_lockstep(fused, steps, patterns=5, **engine_kw):
