@@ -102,6 +102,12 @@ class Engine:
         if self.seg_world > 1 or fused == "shard":
             ctx.xm_cap = int(exchange_match_capacity or min(int(match_capacity), 8 * k + 1024))
             ctx.xr_cap = int(exchange_recycle_capacity or (2 * k + 64))
+        if fused == "shard":
+            # exchanges as {word, sequence} cells (csrc/shard_ll.cuh) while the one-CTA selection / merge fit
+            # in shared memory; very wide networks use the copy + flag protocol
+            ctx.xch_ll = 1 if 4 * (6400 + 2 * k) <= 150 * 1024 else 0
+            if ctx.xch_ll and not exchange_match_capacity:
+                ctx.xm_cap = min(ctx.xm_cap, 4096)  # what one CTA sorts per rank
         ctx.col_local = Ccol // self.shard_world
         ctx.col_lo = self.shard_rank * ctx.col_local
         self.C_local, self.col_lo = ctx.col_local, ctx.col_lo
@@ -238,7 +244,7 @@ class Engine:
             "m_seg": M, "m_conn": M, "m_jit": M, "m_flag": M, "learn_list": x.learn_capacity, "punish_list": M,
             "recyc_list": W * x.xr_cap if W > 1 else 0,
             "x_send": max((3 * min(k, CL) + 3) // 4 * 4, (4 + 3 * x.xm_cap + x.xr_cap + 3) // 4 * 4)
-            if x.fused_mode == 3 else 0,
+            + ((16 + 3 * x.xm_cap + x.xr_cap) if x.xch_ll else 0) if x.fused_mode == 3 else 0,
             "xk_keys": W * min(k, CL) if x.fused_mode == 3 else 0,
             "xk_cols": W * min(k, CL) if x.fused_mode == 3 else 0, "blk": 8 * 1024, "topk_ws": 81920, "mt_key": nat.MT_N, "rng_ring": x.rng_ring_words, "mt_jump": x.jump_polys * nat.MT_N,
             "rng64": nat.R_COUNT, "sc": nat.SC_COUNT,

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BITHTM_B200_LIB") or os.path.join(_HERE, "_lib", "libbithtm_b200.so")  # env: A/B builds
 
 MT_N = 624
-ABI_VERSION = 10
+ABI_VERSION = 11
 R_COUNT = 32  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 
 # device scalar block indices (enum in the header)
@@ -62,7 +62,7 @@ class BhCtx(C.Structure):
         ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
         ("seg_rank", C.c_int32), ("seg_world", C.c_int32), ("xm_cap", C.c_int32), ("xr_cap", C.c_int32),
         ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32), ("device", C.c_int32), ("skip_polys", C.c_int32),
-        ("skip_gran", C.c_int32), ("job_cap", C.c_int32), ("lazy_policy", C.c_int32), ("tail_chunks", C.c_int32),
+        ("skip_gran", C.c_int32), ("job_cap", C.c_int32), ("lazy_policy", C.c_int32), ("tail_chunks", C.c_int32), ("xch_ll", C.c_int32), ("reserved2", C.c_int32),
         ("skip_min", C.c_int64),
         ("sp_threshold", C.c_double), ("sp_delta_on", C.c_double), ("sp_delta_off", C.c_double),
         ("tm_learn_on", C.c_double), ("tm_learn_off", C.c_double),

@@ -119,8 +119,7 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->punish_list, M);
   cv.take(x->recyc_list, W > 1 ? W * (size_t)x->xr_cap : 0);
   if (x->fused_mode == 3) {  // fused sharded step: record staging and the gathered top-k candidates
-    const size_t n1 = (size_t)xch_n1(*x), n4 = (size_t)xch_n4(*x);
-    cv.take(x->x_send, n1 > n4 ? n1 : n4);
+    cv.take(x->x_send, (size_t)xch_send_ints(*x));
     cv.take(x->xk_keys, W * (size_t)xch_k_loc(*x));
     cv.take(x->xk_cols, W * (size_t)xch_k_loc(*x));
   } else {
@@ -641,6 +640,7 @@ static int fused_smem(const bh_ctx* x) {
   int m = a > b ? a : b;
   if (x->fused_mode >= 2 && x->jump_polys > 0 && m < RNG_CHUNK_SMEM) m = RNG_CHUNK_SMEM;
   if (x->fused_mode >= 2 && x->skip_polys > 0 && m < RNG_LAZY_SMEM_WORDS * 4) m = RNG_LAZY_SMEM_WORDS * 4;
+  if (x->fused_mode == 3 && x->xch_ll && m < ll_smem_bytes(*x)) m = (int)(ll_smem_bytes(*x) < (1 << 20) ? ll_smem_bytes(*x) : (1 << 20));
   return m;
 }
 

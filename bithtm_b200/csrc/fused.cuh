@@ -80,31 +80,28 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_SYNC();
     BH_STAMP();
     // P2: SP learning + duty cycles; bursting / winner bits per active column.
-    // Large networks (grid mode): the temporal-memory bookkeeping of P2..P4 is a chain of short dependent steps
-    // over a few thousand items, the SP learning a long bandwidth-bound pass.  A TEAM of the last CTAs runs the
-    // whole chain (winner bits on all of them, a team barrier, then the ordered lists, the learning flags, draw
-    // #2 and the learning lists on the drawing CTA alone) while the other CTAs learn: two phases and barriers less.
-    const int team = (MODE == 2 && nb >= 32 && c.sc[BH_SC_M] <= 32768 && c.sc[BH_SC_NSEG] <= (1 << 18)) ? 8 : 0;
-    if (team) {
-      const int t0 = nb - team;
-      if (b >= t0) {
-        if (b == t0 && c.column_dim >= 16384) tk3_rebin_from_selection(c);
-        ph_select_a(c, b - t0, team);
-        grid_barrier(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT), (unsigned)team);
-        if (rng) {
-          ph_select_b(c, 0, 1, true, team);
-          __syncthreads();
-          ph_learn_select_a(c, learning, 0, 1);
-          __syncthreads();
-          ph_draw(c, 2, learning, 1);
-          ph_learn_select_b(c, learning, 0, 1);
-        }
-      } else {
-        if (learning) ph_sp_learn<false>(c, input, b, t0);
-        ph_duty(c, b, t0);
-      }
+    // Large networks (grid mode): the bookkeeping of P3 / P4 is a chain of short dependent steps over a few
+    // thousand items; ONE CTA (the drawing one) runs it whole -- ordered lists, learning flags, draw #2, learning
+    // lists -- in a single phase: a phase and a barrier less than the many-CTA form.  (Running that chain NEXT TO
+    // the SP learning pass instead was measured slower: 96 us against 64 + 23: its dependent loads queue behind
+    // the bandwidth-bound traffic.)
+    const bool serial_lists = MODE == 2 && nb >= 32 && c.sc[BH_SC_M] <= 32768 && c.sc[BH_SC_NSEG] <= (1 << 18);
+    if (serial_lists) {
+      if (rng && c.column_dim >= 16384) tk3_rebin_from_selection(c);  // (no-op unless the selection fell back)
+      if (learning) ph_sp_learn<false>(c, input, b, nb);
+      ph_duty(c, b, nb);
+      if (worker) ph_select_a(c, b, nw);
       BH_SYNC();
       BH_STAMP();
+      if (rng) {
+        ph_select_b(c, 0, 1, true, nw);
+        __syncthreads();
+        ph_learn_select_a(c, learning, 0, 1);
+        __syncthreads();
+        ph_draw(c, 2, learning, 1);
+        ph_learn_select_b(c, learning, 0, 1);
+      }
+      BH_SYNC();
       BH_STAMP();
       BH_STAMP();
     } else {

@@ -18,6 +18,7 @@
 
 #include "fused.cuh"
 #include "tm_shard.cuh"
+#include "shard_ll.cuh"
 
 #define XCH_FLAG_INTS 16
 // from this many keys the grid-wide selection (two grid barriers) beats one CTA -- much earlier than in the
@@ -31,8 +32,22 @@ __host__ __device__ __forceinline__ int xch_k_loc(const bh_ctx& c) {
 }
 __host__ __device__ __forceinline__ long long xch_n1(const bh_ctx& c) { return (3LL * xch_k_loc(c) + 3) & ~3LL; }
 __host__ __device__ __forceinline__ long long xch_n4(const bh_ctx& c) { return (xch_ints(c) + 3) & ~3LL; }
+// the copy + flag areas, then (xch_ll) the cell areas of shard_ll.cuh
+__host__ __device__ __forceinline__ long long xch_legacy_ints(const bh_ctx& c) {
+  const long long G = c.seg_world > 1 ? c.seg_world : 1;
+  return (XCH_FLAG_INTS + 2LL * G * (xch_n1(c) + xch_n4(c)) + 3) & ~3LL;
+}
 __host__ __device__ __forceinline__ long long xch_region_ints(const bh_ctx& c) {
-  return XCH_FLAG_INTS + 2LL * c.seg_world * (xch_n1(c) + xch_n4(c));
+  return xch_legacy_ints(c) + (c.xch_ll ? ll_area_ints(c) : 0);
+}
+// ctx.x_send: the packed record of an exchange, then (xch_ll) the append lists of the segment scan
+__host__ __device__ __forceinline__ long long xch_send_ints(const bh_ctx& c) {
+  const long long n1 = xch_n1(c), n4 = xch_n4(c);
+  return (n1 > n4 ? n1 : n4) + (c.xch_ll ? 8 + ll_seg_words(c) : 0);
+}
+__device__ __forceinline__ int* xch_append_rec(const bh_ctx& c) {
+  const long long n1 = xch_n1(c), n4 = xch_n4(c);
+  return c.x_send + (n1 > n4 ? n1 : n4);
 }
 // this rank's receive area of exchange `kind` for the current step parity: record of rank s at + s * n
 __device__ __forceinline__ long long xch_recv_off(const bh_ctx& c, int kind, int par) {
@@ -115,11 +130,35 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_STAMP();
     // P0: overlap + boost of the local columns; draw #1 on the rng CTA
     if (rng) ph_draw(c, 1, 1, nw);
-    if (nb == 1) ph_overlap<true>(c, input, s_dyn, 0, 1);
-    else if (!rng) ph_overlap<true>(c, input, s_dyn, b, nb - 1);
+    if (nb == 1) ph_overlap<true, true>(c, input, s_dyn, 0, 1);
+    else if (!rng) ph_overlap<true, true>(c, input, s_dyn, b, nb - 1);
     BH_SYNC();
     BH_STAMP();  // 1: overlap
-    // P1: this shard's best k_loc candidates -> record -> exchange 1 -> global top-k on every rank
+    // P1: global inhibition.  xch_ll: ONE CTA all-gathers the histograms the overlap phase built, derives the
+    // threshold bin, all-gathers the columns above it and the members of it, and writes the active-column list
+    // (shard_ll.cuh): one phase.  Its verdict (did the predicted binning resolve the threshold?) is identical
+    // on every rank; a miss takes the candidate exchange below for this step.
+    bool selected = false;
+    if (c.xch_ll) {
+      int* flag = c.topk_ws + TK3_BASE + TK3_SELECTED;
+      if (b == 0) {
+        int* llp[BH_MAX_RANKS];
+        for (int p = 0; p < (G > 1 ? G : 1); ++p) llp[p] = c.xpeer[p] + xch_legacy_ints(c);
+        const bool ok = ph_shard_select_ll(c, llp, s_dyn);
+        if (threadIdx.x == 0) *flag = ok ? c.sc[BH_SC_STEP] + 1 : 0;
+      }
+      if (rng && nb > 1) ph_rng_speculate(c, 1);
+      BH_SYNC();
+      selected = *flag == c.sc[BH_SC_STEP] + 1;
+      if (selected) {
+        BH_STAMP();  // 2..4: selection
+        BH_STAMP();
+        BH_STAMP();
+        BH_STAMP();
+      }
+    }
+    if (!selected) {
+    // this shard's best k_loc candidates -> record -> exchange 1 -> global top-k on every rank
     int* scratch = reinterpret_cast<int*>(c.row_unacc);  // not in use yet this step
     if (c.col_local >= XCH_TOPK_GRID_MIN) {
       topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
@@ -167,10 +206,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (rng && nb > 1) ph_rng_speculate(c, 1);
     BH_SYNC();
     BH_STAMP();  // 4: unpack + global top-k
+    }  // (!selected)
+    // the binning of the next step's histogram after a candidate exchange: from the gathered candidates
+    const bool rebin = c.xch_ll && !selected;
     // P2..P7 as in fused.cuh; learning and the segment scan touch only what this rank stores
     // a TEAM of the last CTAs runs the replicated temporal-memory bookkeeping chain while the others learn this
     // shard's spatial-pooler rows (fused.cuh, P2)
-    const int team = (nb >= 64 && c.sc[BH_SC_M] <= 32768) ? 16 : 0;
+    const int team = (nb >= 32 && c.sc[BH_SC_M] <= 32768) ? (nb >= 64 ? 16 : 8) : 0;
+    if (rebin && b == (team ? nb - team : 0)) tk3_rebin_sharded(c, G > 1 ? G * k_loc : k_loc);
     if (team) {
       const int t0 = nb - team;
       if (b >= t0) {
@@ -230,10 +273,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_STAMP();  // 9: learn + post
     const int ns = lazy ? nb - rng_tail_ctas(c, nb) : nw;  // lazy step: the last CTAs generate the tail instead
     if (lazy) ph_rng_lazy_tail(c, s_dyn, b, nb);
-    if (b < ns) ph_activate_a(c, b, ns);
+    if (b < ns) ph_activate_a(c, b, ns, c.xch_ll ? xch_append_rec(c) : nullptr);
     BH_SYNC();
     BH_STAMP();  // 10: segment scan
     // P8: this rank's record of matching / recyclable segments -> exchange 2 -> merged global lists
+    if (c.xch_ll) {
+      // the scan appended the record unordered; ONE CTA sorts it, all-gathers and merges (shard_ll.cuh).  A
+      // record too long to sort there, or more recyclable segments than the exchange carries (the LOWEST ids
+      // must be sent), is first rebuilt in order by all CTAs.
+      int* app = xch_append_rec(c);
+      const bool repack = app[0] > LL_LOCAL_MATCH_MAX || app[0] > c.xm_cap || app[1] > c.xr_cap;  // uniform in the rank
+      if (repack) {
+        if (b < ns) ph_shard_pack(c, c.x_send, b, ns);
+        BH_SYNC();
+      }
+      BH_STAMP();  // 11: record
+      if (b == 0) {
+        int* llp[BH_MAX_RANKS];
+        for (int p = 0; p < (G > 1 ? G : 1); ++p) llp[p] = c.xpeer[p] + xch_legacy_ints(c);
+        ph_shard_segs_ll(c, llp, s_dyn, repack ? c.x_send : app, repack);
+        if (repack && threadIdx.x == 0) {
+          app[0] = 0;
+          app[1] = 0;
+        }
+      }
+      BH_SYNC();
+      BH_STAMP();  // 12: exchange 2 + merge
+      BH_STAMP();
+    } else {
     if (b < ns) ph_shard_pack(c, c.x_send, b, ns);
     BH_SYNC();
     BH_STAMP();  // 11: record
@@ -242,6 +309,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     ph_shard_merge(c, region + xch_recv_off(c, 1, par), b, nb, (int)n4);
     BH_SYNC();
     BH_STAMP();  // 13: merge
+    }
     // P9: draw #3 (a phase of its own only when not covered, see fused.cuh), jitter, predictions
     const int M = c.sc[BH_SC_X_MATCH] < c.match_capacity ? c.sc[BH_SC_X_MATCH] : c.match_capacity;
     const bool ready3 = (long long)M <= c.rng64[R_READY3];

@@ -1,0 +1,479 @@
+// Low-latency exchanges of the fused sharded step (shard_fused.cuh) and the two selections built on them.
+//
+// Transport.  A record travels as 8-byte cells {payload word, sequence number} stored straight into every
+// peer's region (st.relaxed.sys.v2: one 8-byte store is one transaction, so a cell is valid as soon as its
+// sequence number reads as this step's) -- no system fence, no grid barrier and no separate flag per
+// exchange, which is what made the copy + fence + barrier + flag protocol cost 12-14 us.  The receiver spins
+// on the cells themselves.  Records are double-buffered by step parity; a rank can be at most one exchange
+// ahead of a peer (finishing an exchange needs every peer's record of it), so a cell is never overwritten
+// before it was read.  Sequence number = step + 1 (regions start zeroed).
+//
+// Exchange 1 (global inhibition, regularizations.py:28-29 over column shards), ONE CTA per rank:
+//   a. all-gather the 2048-bin histograms the overlap phase built with the predicted binning (sp_kernels.cuh
+//      TK3_*): every rank derives the same threshold bin B and how many keys each rank has above / inside it;
+//   b. all-gather, per rank, its columns in bins above B (selected for sure) and its (key, column) pairs inside
+//      B; every rank ranks the pairs identically (larger key first, ties -> lower column) and writes the
+//      global ascending active-column list.
+//   A prediction that misses (threshold outside the binned range, > 1024 keys in B) falls back to the
+//   candidate exchange of shard_fused.cuh for that step.
+// Exchange 2 (matching / recyclable segments, projections.py:247, 80-81 over segment shards), ONE CTA per rank:
+//   the scan appended this rank's matching segments unordered; they are sorted by id, all-gathered, and every
+//   rank merges the sorted lists by counting (binary searches in shared memory).
+#pragma once
+
+#include "sp_kernels.cuh"
+#include "tm_shard.cuh"
+
+#define LL_HIST_WORDS (TK2_BINS + 8)
+#define LL_MEMBERS TOPK_THREADS      // most keys of the threshold bin over all ranks
+#define LL_LOCAL_MATCH_MAX 4096      // most matching segments one rank sorts in shared memory
+#define LL_TOTAL_MATCH_MAX 16384     // most matching segments over all ranks merged in shared memory
+#define LL_TIMEOUT_CYCLES 6000000000LL
+
+__host__ __device__ __forceinline__ int ll_k_loc(const bh_ctx& c) {
+  return c.active_columns < c.col_local ? c.active_columns : c.col_local;
+}
+__host__ __device__ __forceinline__ long long ll_sel_words(const bh_ctx& c) { return ll_k_loc(c) + 3LL * LL_MEMBERS + 8; }
+__host__ __device__ __forceinline__ long long ll_seg_words(const bh_ctx& c) { return 8 + 3LL * c.xm_cap + c.xr_cap; }
+// dynamic shared memory (bytes) the two one-CTA phases below need
+__host__ __device__ __forceinline__ long long ll_smem_bytes(const bh_ctx& c) {
+  const long long sel = 4LL * (TK2_BINS + 2 * LL_MEMBERS + 2 * LL_MEMBERS + 8 + c.active_columns + ll_k_loc(c) + 64);
+  const long long seg = 4LL * (LL_TOTAL_MATCH_MAX + LL_LOCAL_MATCH_MAX);
+  return sel > seg ? sel : seg;
+}
+// ints of the LL area of one region: per kind [2 parity][G sources][words] cells of 2 ints
+__host__ __device__ __forceinline__ long long ll_area_ints(const bh_ctx& c) {
+  const long long G = c.seg_world > 1 ? c.seg_world : 1;
+  return 4 * G * (LL_HIST_WORDS + ll_sel_words(c) + ll_seg_words(c));
+}
+// int offset (inside the LL area) of cell `i` of the record rank `src` sent for exchange `kind` (0 histogram,
+// 1 selection, 2 segments) at step parity `par`
+__device__ __forceinline__ long long ll_cell(const bh_ctx& c, int kind, int par, int src, long long i) {
+  const long long G = c.seg_world > 1 ? c.seg_world : 1;
+  const long long w0 = LL_HIST_WORDS, w1 = ll_sel_words(c), w2 = ll_seg_words(c);
+  const long long base = kind == 0 ? 0 : (kind == 1 ? 2 * G * w0 : 2 * G * (w0 + w1));
+  const long long w = kind == 0 ? w0 : (kind == 1 ? w1 : w2);
+  return 2 * (base + ((long long)par * G + src) * w + i);
+}
+
+__device__ __forceinline__ void ll_store(int* cell, int v, int seq) {
+  asm volatile("st.relaxed.sys.global.v2.s32 [%0], {%1, %2};" ::"l"(cell), "r"(v), "r"(seq) : "memory");
+}
+// spins until the cell carries `seq`; a peer that never answers sets BH_ST_XCH_TIMEOUT instead of hanging
+__device__ __forceinline__ int ll_load(const bh_ctx& c, const int* cell, int seq) {
+  int v, s;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v2.s32 {%0, %1}, [%2];" : "=r"(v), "=r"(s) : "l"(cell) : "memory");
+    if (s == seq) return v;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > LL_TIMEOUT_CYCLES) {
+      atomicOr(&c.sc[BH_SC_STATUS], BH_ST_XCH_TIMEOUT);
+      return 0;
+    }
+  }
+}
+// word i of this rank's record -> every rank (its own region included: one code path)
+__device__ __forceinline__ void ll_put(const bh_ctx& c, int* const* ll, int kind, int par, long long i, int v, int seq) {
+  const int G = c.seg_world > 1 ? c.seg_world : 1;
+  const long long off = ll_cell(c, kind, par, c.seg_rank, i);
+#pragma unroll 1
+  for (int p = 0; p < G; ++p) ll_store(ll[p] + off, v, seq);
+}
+
+// lower bound in a shared-memory ascending int list
+__device__ __forceinline__ int smem_lower(const int* list, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (list[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------
+// Exchange 1.  ONE CTA (blockDim.x = 1024).  `ll[p]` = LL area of rank p's region.  Returns false (on every
+// rank alike) when the step must take the candidate exchange instead; then nothing was written but the flag.
+// smem: 2048 + 64 + 3 * LL_MEMBERS + 2 * LL_MEMBERS (u64 keys) + active_columns + k_loc + 64 ints.
+// ------------------------------------------------------------------------------------
+__device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll, uint32_t* smem) {
+  __shared__ int s_scan[32];
+  __shared__ int s_bin, s_rem, s_ncand, s_cnt[4 * BH_MAX_RANKS];
+  __shared__ unsigned long long s_kth_key, s_gmax;
+  const int t = threadIdx.x, NT = blockDim.x, lane = t & 31, warp = t >> 5;
+  const int G = c.seg_world > 1 ? c.seg_world : 1, me = c.seg_rank;
+  const int k = c.active_columns, k_loc = ll_k_loc(c), n = c.col_local;
+  const int step = c.sc[BH_SC_STEP], par = step & 1, seq = step + 1;
+  int* ws3 = c.topk_ws + TK3_BASE;
+  int* ws = c.topk_ws + TK2_BASE;
+  int* ghist = ws3 + TK3_HIST + par * TK2_BINS;
+  int* s_h = reinterpret_cast<int*>(smem);                       // [2048] summed histogram, descending bin order
+  unsigned long long* s_mkey = reinterpret_cast<unsigned long long*>(s_h + TK2_BINS);  // [LL_MEMBERS]
+  int* s_mcol = reinterpret_cast<int*>(s_mkey + LL_MEMBERS);      // [LL_MEMBERS] global column of a member
+  int* s_msel = s_mcol + LL_MEMBERS;                              // [LL_MEMBERS] selected?  then: exclusive prefix
+  int* s_above = s_msel + LL_MEMBERS + 1;                         // [k] columns above the bin, rank by rank
+  const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(c.boosted);
+  unsigned long long* w64 = reinterpret_cast<unsigned long long*>(ws);
+  const bool have_hist = ws3[TK3_READY] == seq;
+
+  // a. histogram (+ the largest local key) -> everybody
+  const unsigned long long lmax = w64[0];
+#pragma unroll 1
+  for (int i = t; i < TK2_BINS + 3; i += NT) {
+    int v;
+    if (i < TK2_BINS) v = have_hist ? ghist[i] : 0;
+    else v = i == TK2_BINS ? (int)(unsigned)(lmax & 0xffffffffull) : (i == TK2_BINS + 1 ? (int)(unsigned)(lmax >> 32) : (have_hist ? 1 : 0));
+    ll_put(c, ll, 0, par, i, v, seq);
+  }
+  int* mine = ll[me];
+  if (t == 0) {
+    unsigned long long gm = 0ull;
+    int all_hist = 1;
+    for (int g = 0; g < G; ++g) {
+      const unsigned lo = (unsigned)ll_load(c, mine + ll_cell(c, 0, par, g, TK2_BINS), seq);
+      const unsigned hi = (unsigned)ll_load(c, mine + ll_cell(c, 0, par, g, TK2_BINS + 1), seq);
+      all_hist &= ll_load(c, mine + ll_cell(c, 0, par, g, TK2_BINS + 2), seq);
+      const unsigned long long m = ((unsigned long long)hi << 32) | lo;
+      gm = m > gm ? m : gm;
+    }
+    s_gmax = gm;
+    s_ncand = all_hist ? -1 : -2;
+  }
+  {
+    const int per = (TK2_BINS + NT - 1) / NT;  // descending order: slot j holds bin 2047 - j
+    for (int i = 0; i < per; ++i) {
+      const int bin = TK2_BINS - 1 - (t * per + i);
+      int sum = 0;
+      if (bin >= 1)
+        for (int g = 0; g < G; ++g) sum += ll_load(c, mine + ll_cell(c, 0, par, g, bin), seq);
+      s_h[t * per + i] = sum;
+    }
+  }
+  __syncthreads();
+  bool ok = s_ncand == -1;
+  if (ok) {
+    const int per = (TK2_BINS + NT - 1) / NT;
+    int sum = 0;
+    for (int i = 0; i < per; ++i) sum += s_h[t * per + i];
+    int total;
+    const int before = block_excl_scan(sum, s_scan, total);
+    if (before < k && before + sum >= k) {
+      int r = k - before;
+      for (int i = 0; i < per; ++i) {
+        const int h = s_h[t * per + i];
+        if (r > 0 && h >= r) {
+          s_bin = TK2_BINS - 1 - (t * per + i);
+          s_rem = r;
+          s_ncand = h;
+          r = -1;
+        } else if (r > 0) {
+          r -= h;
+        }
+      }
+    }
+    __syncthreads();
+    ok = s_ncand >= 0 && s_ncand <= LL_MEMBERS;
+  }
+  if (!ok) return false;  // identical decision on every rank (same gathered data)
+  const int bin = s_bin, rem = s_rem;
+  // per rank: keys above the bin (a_g) and inside it (m_g); warp g handles rank g
+  if (warp < G) {
+    int a = 0;
+#pragma unroll 1
+    for (int i = bin + 1 + lane; i < TK2_BINS; i += 32) a += ll_load(c, mine + ll_cell(c, 0, par, warp, i), seq);
+    a = warp_sum(a);
+    if (lane == 0) {
+      s_cnt[warp] = a;
+      s_cnt[BH_MAX_RANKS + warp] = ll_load(c, mine + ll_cell(c, 0, par, warp, bin), seq);
+    }
+  }
+  __syncthreads();
+  // b. this rank's columns above the bin and its members of the bin, in ascending column order -> everybody
+  const Tk3Binning binning = tk3_binning(ws3);
+  {
+    int base_a = 0, base_m = 0;
+#pragma unroll 1
+    for (int tile = 0; tile < n; tile += NT) {
+      const int j = tile + t;
+      const unsigned long long key = j < n ? keys[j] : 0ull;
+      const int kb = j < n ? tk3_bin(binning, key) : 0;
+      int tot_a, tot_m;
+      const int pa = base_a + block_excl_scan(kb > bin ? 1 : 0, s_scan, tot_a);
+      const int pm = base_m + block_excl_scan((j < n && kb == bin) ? 1 : 0, s_scan, tot_m);
+      if (kb > bin && pa < k_loc) ll_put(c, ll, 1, par, pa, c.col_lo + j, seq);
+      if (j < n && kb == bin && pm < LL_MEMBERS) {
+        const long long w = k_loc + 3LL * pm;
+        ll_put(c, ll, 1, par, w, (int)(unsigned)(key & 0xffffffffull), seq);
+        ll_put(c, ll, 1, par, w + 1, (int)(unsigned)(key >> 32), seq);
+        ll_put(c, ll, 1, par, w + 2, c.col_lo + j, seq);
+      }
+      base_a += tot_a;
+      base_m += tot_m;
+    }
+  }
+  // gather: offsets of every rank's part
+  if (t == 0) {
+    int oa = 0, om = 0;
+    for (int g = 0; g < G; ++g) {
+      s_cnt[2 * BH_MAX_RANKS + g] = oa;
+      s_cnt[3 * BH_MAX_RANKS + g] = om;
+      oa += s_cnt[g];
+      om += s_cnt[BH_MAX_RANKS + g];
+    }
+  }
+  __syncthreads();
+  int n_above = 0, n_mem = 0;
+  for (int g = 0; g < G; ++g) {
+    n_above += s_cnt[g];
+    n_mem += s_cnt[BH_MAX_RANKS + g];
+  }
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const int a = s_cnt[g], m = s_cnt[BH_MAX_RANKS + g], oa = s_cnt[2 * BH_MAX_RANKS + g], om = s_cnt[3 * BH_MAX_RANKS + g];
+#pragma unroll 1
+    for (int i = t; i < a; i += NT) s_above[oa + i] = ll_load(c, mine + ll_cell(c, 1, par, g, i), seq);
+#pragma unroll 1
+    for (int i = t; i < m; i += NT) {
+      const long long w = k_loc + 3LL * i;
+      const unsigned lo = (unsigned)ll_load(c, mine + ll_cell(c, 1, par, g, w), seq);
+      const unsigned hi = (unsigned)ll_load(c, mine + ll_cell(c, 1, par, g, w + 1), seq);
+      s_mkey[om + i] = ((unsigned long long)hi << 32) | lo;
+      s_mcol[om + i] = ll_load(c, mine + ll_cell(c, 1, par, g, w + 2), seq);
+    }
+  }
+  __syncthreads();
+  // rank the members: larger key first, ties -> lower column; the first `rem` are selected
+  if (t < n_mem) {
+    const unsigned long long mk = s_mkey[t];
+    const int mc = s_mcol[t];
+    int ahead = 0;
+#pragma unroll 2
+    for (int i = 0; i < n_mem; ++i) {
+      const unsigned long long ok2 = s_mkey[i];
+      ahead += (ok2 > mk || (ok2 == mk && s_mcol[i] < mc)) ? 1 : 0;
+    }
+    s_msel[t] = ahead < rem ? 1 : 0;
+    if (ahead == rem - 1) s_kth_key = mk;
+  }
+  __syncthreads();
+  {  // exclusive prefix of the selected flags over the member array (n_mem <= 1024 = one tile)
+    int tot;
+    const int f = t < n_mem ? s_msel[t] : 0;
+    const int pre = block_excl_scan(f, s_scan, tot);
+    __syncthreads();
+    if (t < n_mem) s_msel[t] = pre | (f << 30);
+    if (t == 0) s_msel[n_mem] = tot;
+  }
+  __syncthreads();
+  retire_prev_flags(c);
+  int* out = c.active_cols + par * k;
+  // rank offsets in the final list: everything of the ranks before
+  // (selected members of rank g = prefix at the end of its part - prefix at its start)
+  auto pre_at = [&](int idx) { return idx < n_mem ? (s_msel[idx] & 0x3fffffff) : s_msel[n_mem]; };
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const int a = s_cnt[g], m = s_cnt[BH_MAX_RANKS + g], oa = s_cnt[2 * BH_MAX_RANKS + g], om = s_cnt[3 * BH_MAX_RANKS + g];
+    const int off = oa + pre_at(om);  // columns above the bin + selected members of the ranks before g
+#pragma unroll 1
+    for (int i = t; i < a; i += NT) {  // a column above the bin: after the selected members of g with lower columns
+      const int col = s_above[oa + i];
+      const int lb = smem_lower(s_mcol + om, m, col);
+      const int pos = off + i + (pre_at(om + lb) - pre_at(om));
+      if (pos < k) {
+        out[pos] = col;
+        c.col_active[col] = 1;
+      }
+    }
+#pragma unroll 1
+    for (int i = t; i < m; i += NT) {
+      if (!(s_msel[om + i] >> 30)) continue;
+      const int col = s_mcol[om + i];
+      const int pos = off + smem_lower(s_above + oa, a, col) + (pre_at(om + i) - pre_at(om));
+      if (pos < k) {
+        out[pos] = col;
+        c.col_active[col] = 1;
+      }
+    }
+  }
+  // leave the workspaces clean; binning of the next step from this step's k-th and largest key
+  int* oh = ws3 + TK3_HIST + (par ^ 1) * TK2_BINS;
+#pragma unroll 1
+  for (int i = t; i < TK2_BINS; i += NT) oh[i] = 0;
+  if (t == 0) {
+    w64[0] = 0ull;
+    w64[1] = 0ull;
+    ws[TK2_VALID] = 0;
+    tk3_set_binning(ws3, s_kth_key, s_gmax > s_kth_key ? s_gmax : s_kth_key);
+  }
+  (void)n_above;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------
+// Exchange 2.  ONE CTA.  The scan (ph_activate_a) appended this rank's matching segments as (id, potential,
+// connected) triples at rec[8 + 3 i] with the counter rec[0], and its recyclable segment ids at
+// rec[8 + 3 xm_cap + j] with the counter rec[1] (entries beyond the capacities are not stored) -- unordered.
+// `sorted`: the record was rebuilt in ascending id order (ph_shard_pack; rec = the packed record, header
+// [count, recyclable sent, recyclable true count, status]).
+// smem: LL_TOTAL_MATCH_MAX + LL_LOCAL_MATCH_MAX ints.
+// ------------------------------------------------------------------------------------
+__device__ __noinline__ void ph_shard_segs_ll(const bh_ctx& c, int* const* ll, uint32_t* smem, int* rec, bool sorted) {
+  __shared__ int s_n[4 * BH_MAX_RANKS + 4];
+  const int t = threadIdx.x, NT = blockDim.x;
+  const int G = c.seg_world > 1 ? c.seg_world : 1, me = c.seg_rank;
+  const int step = c.sc[BH_SC_STEP], par = step & 1, seq = step + 1;
+  int* s_all = reinterpret_cast<int*>(smem);            // [LL_TOTAL_MATCH_MAX] ids of all ranks, rank by rank
+  int* s_key = s_all + LL_TOTAL_MATCH_MAX;              // [LL_LOCAL_MATCH_MAX] local ids (unsorted)
+  int status = c.sc[BH_SC_STATUS];
+  int n, nr, nr_total;
+  const int* trip;
+  const int* rids;
+  if (sorted) {
+    n = rec[0];
+    nr = rec[1];
+    nr_total = rec[2];
+    status |= rec[3];
+    trip = nullptr;
+    rids = rec + 4 + 3 * c.xm_cap;
+  } else {
+    n = rec[0];
+    nr_total = rec[1];
+    if (n > c.xm_cap || n > LL_LOCAL_MATCH_MAX) {
+      status |= BH_ST_XCH_OVERFLOW;
+      n = c.xm_cap < LL_LOCAL_MATCH_MAX ? c.xm_cap : LL_LOCAL_MATCH_MAX;
+    }
+    nr = nr_total < c.xr_cap ? nr_total : c.xr_cap;
+    trip = rec + 8;
+    rids = rec + 8 + 3 * c.xm_cap;
+  }
+  // header
+  if (t < 4) ll_put(c, ll, 2, par, t, t == 0 ? n : (t == 1 ? nr : (t == 2 ? nr_total : status)), seq);
+  if (sorted) {  // packed record: ids / potentials / connected counts as three arrays
+#pragma unroll 1
+    for (int i = t; i < n; i += NT) {
+      ll_put(c, ll, 2, par, 8 + 3LL * i, rec[4 + i], seq);
+      ll_put(c, ll, 2, par, 8 + 3LL * i + 1, rec[4 + c.xm_cap + i], seq);
+      ll_put(c, ll, 2, par, 8 + 3LL * i + 2, rec[4 + 2 * c.xm_cap + i], seq);
+    }
+#pragma unroll 1
+    for (int i = t; i < nr; i += NT) ll_put(c, ll, 2, par, 8 + 3LL * c.xm_cap + i, rids[i], seq);
+  } else {
+    // sort by id by counting (ids are distinct): entry i goes to position #{ids < id_i}
+#pragma unroll 1
+    for (int i = t; i < n; i += NT) s_key[i] = trip[3 * i];
+    __syncthreads();
+#pragma unroll 1
+    for (int i = t; i < n; i += NT) {
+      const int id = s_key[i];
+      int pos = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) pos += s_key[j] < id ? 1 : 0;
+      ll_put(c, ll, 2, par, 8 + 3LL * pos, id, seq);
+      ll_put(c, ll, 2, par, 8 + 3LL * pos + 1, trip[3 * i + 1], seq);
+      ll_put(c, ll, 2, par, 8 + 3LL * pos + 2, trip[3 * i + 2], seq);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = t; i < nr; i += NT) s_key[i] = rids[i];
+    __syncthreads();
+#pragma unroll 1
+    for (int i = t; i < nr; i += NT) {
+      const int id = s_key[i];
+      int pos = 0;
+      for (int j = 0; j < nr; ++j) pos += s_key[j] < id ? 1 : 0;
+      ll_put(c, ll, 2, par, 8 + 3LL * c.xm_cap + pos, id, seq);
+    }
+    __syncthreads();
+  }
+  // gather the headers
+  int* mine = ll[me];
+  if (t < G) {
+    s_n[t] = ll_load(c, mine + ll_cell(c, 2, par, t, 0), seq);
+    s_n[BH_MAX_RANKS + t] = ll_load(c, mine + ll_cell(c, 2, par, t, 1), seq);
+    s_n[2 * BH_MAX_RANKS + t] = ll_load(c, mine + ll_cell(c, 2, par, t, 2), seq);
+    s_n[3 * BH_MAX_RANKS + t] = ll_load(c, mine + ll_cell(c, 2, par, t, 3), seq);
+  }
+  __syncthreads();
+  int M = 0, R = 0, RT = 0, st = 0;
+  for (int g = 0; g < G; ++g) {
+    M += s_n[g];
+    R += s_n[BH_MAX_RANKS + g];
+    RT += s_n[2 * BH_MAX_RANKS + g];
+    st |= s_n[3 * BH_MAX_RANKS + g];
+  }
+  if (M > LL_TOTAL_MATCH_MAX) st |= BH_ST_XCH_OVERFLOW;
+  // ids of all ranks into shared memory (rank by rank, each ascending), then merge by counting
+  int off = 0;
+#pragma unroll 1
+  for (int g = 0; g < G && off < LL_TOTAL_MATCH_MAX; ++g) {
+    const int ng = s_n[g] < LL_TOTAL_MATCH_MAX - off ? s_n[g] : LL_TOTAL_MATCH_MAX - off;
+#pragma unroll 1
+    for (int i = t; i < ng; i += NT) s_all[off + i] = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * i), seq);
+    off += ng;
+  }
+  __syncthreads();
+  off = 0;
+#pragma unroll 1
+  for (int g = 0; g < G && off < LL_TOTAL_MATCH_MAX; ++g) {
+    const int ng = s_n[g] < LL_TOTAL_MATCH_MAX - off ? s_n[g] : LL_TOTAL_MATCH_MAX - off;
+#pragma unroll 1
+    for (int i = t; i < ng; i += NT) {
+      const int id = s_all[off + i];
+      int pos = i, o2 = 0;
+      for (int o = 0; o < G; ++o) {
+        const int no = s_n[o];
+        if (o != g && o2 + no <= LL_TOTAL_MATCH_MAX) pos += smem_lower(s_all + o2, no, id);
+        o2 += no;
+      }
+      const int pot = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * i + 1), seq);
+      const int conn = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * i + 2), seq);
+      c.seg_pot[id] = pot;  // every rank knows the potentials of the matching segments
+      c.seg_conn[id] = conn;
+      if (pos < c.match_capacity) {
+        c.m_seg[pos] = id;
+        c.m_conn[pos] = conn;
+      }
+    }
+    off += ng;
+  }
+  __syncthreads();
+  // recyclable ids: the same merge (few; usually none)
+  off = 0;
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const int ng = s_n[BH_MAX_RANKS + g];
+#pragma unroll 1
+    for (int i = t; i < ng && off + i < LL_TOTAL_MATCH_MAX; i += NT)
+      s_all[off + i] = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * c.xm_cap + i), seq);
+    off += ng;
+  }
+  __syncthreads();
+  off = 0;
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const int ng = s_n[BH_MAX_RANKS + g];
+#pragma unroll 1
+    for (int i = t; i < ng && off + i < LL_TOTAL_MATCH_MAX; i += NT) {
+      const int id = s_all[off + i];
+      int pos = i, o2 = 0;
+      for (int o = 0; o < G; ++o) {
+        const int no = s_n[BH_MAX_RANKS + o];
+        if (o != g && o2 + no <= LL_TOTAL_MATCH_MAX) pos += smem_lower(s_all + o2, no, id);
+        o2 += no;
+      }
+      c.recyc_list[pos] = id;
+    }
+    off += ng;
+  }
+  if (t == 0) {
+    c.sc[BH_SC_X_MATCH] = M;
+    c.sc[BH_SC_X_RECYC_AVAIL] = R;
+    c.sc[BH_SC_X_RECYC_TOTAL] = RT;
+    if (st) atomicOr(&c.sc[BH_SC_STATUS], st);
+    if (!sorted) {  // counters of the scan's append lists, for the next step
+      rec[0] = 0;
+      rec[1] = 0;
+    }
+  }
+}

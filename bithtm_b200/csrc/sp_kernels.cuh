@@ -30,6 +30,7 @@
 #define TK3_SHIFT 1
 #define TK3_BASE64 1       // u64 index: base key bits (ints 2, 3)
 #define TK3_READY 4        // step + 1 of the step whose keys hist[step & 1] holds
+#define TK3_SELECTED 5     // sharded step: step + 1 when the histogram exchange selected the active columns
 #define TK3_HIST 8         // [2][TK2_BINS]
 #define TK3_CNT (TK3_HIST + 2 * TK2_BINS)         // [2][8]: members of the threshold bin gathered so far
 #define TK3_IDX (TK3_CNT + 16)                    // [2][1024] their positions
@@ -1423,6 +1424,27 @@ __device__ __forceinline__ void tk3_rebin_from_selection(const bh_ctx& c) {
 #pragma unroll 1
   for (int i = threadIdx.x; i < TK2_BINS; i += blockDim.x) mine[i] = 0;
   if (threadIdx.x < 2) ws3[TK3_CNT + threadIdx.x * 8] = 0;  // (a member count of two steps ago may be left)
+}
+
+// The same for a column shard after a candidate exchange: the gathered candidates (xk_keys / xk_cols, n of
+// them, identical on every rank) contain every selected column.  One CTA.
+__device__ __forceinline__ void tk3_rebin_sharded(const bh_ctx& c, int n) {
+  __shared__ unsigned long long s_u64c[32];
+  int* ws3 = c.topk_ws + TK3_BASE;
+  const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(c.xk_keys);
+  unsigned long long mn = ~0ull, mx = 0ull;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long key = keys[i];
+    mx = key > mx ? key : mx;
+    if (c.col_active[c.xk_cols[i]]) mn = key < mn ? key : mn;
+  }
+  mn = block_reduce_u64(mn, false, s_u64c);
+  mx = block_reduce_u64(mx, true, s_u64c);
+  if (threadIdx.x == 0) tk3_set_binning(ws3, mn, mx > mn ? mx : mn);
+#pragma unroll 1
+  for (int i = threadIdx.x; i < 2 * TK2_BINS; i += blockDim.x) ws3[TK3_HIST + i] = 0;
+  if (threadIdx.x == 0) ws3[TK3_READY] = 0;
 }
 
 // stand-alone cooperative kernels built on topk_multi (grid = one CTA per SM)

@@ -677,7 +677,9 @@ __device__ void ph_post(const bh_ctx& c, int b, int nb) {
 // (:167-173).
 // ---------------------------------------------------------------------------------
 #define ACT_BATCH 5  // segments per warp iteration, 64 slots each: 20 independent loads in flight per lane
-__device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
+// `append` (fused sharded step with cell exchanges): the matching and the recyclable segments are also appended
+// to the lists at append[8..] (counters append[0], append[1]).
+__device__ void ph_activate_a(const bh_ctx& c, int b, int nb, int* append = nullptr) {
   __shared__ int s_red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int E = c.syn_capacity;
@@ -705,7 +707,13 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
         perm[j][h] = v ? c.syn_perm[base + 32 * h] : 0.0f;
       }
     }
-    if (lane < ACT_BATCH && s0 + lane < rg.end && my_n < thr) ++nrec;  // recyclable (projections.py:80)
+    if (lane < ACT_BATCH && s0 + lane < rg.end && my_n < thr) {  // recyclable (projections.py:80)
+      ++nrec;
+      if (append) {
+        const int j = atomicAdd(&append[1], 1);
+        if (j < c.xr_cap) append[8 + 3 * c.xm_cap + j] = seg_gid(c, s0 + lane);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < ACT_BATCH; ++j) n[j] = __shfl_sync(BH_FULL, my_n, j);
     uint32_t word[ACT_BATCH][2];
@@ -740,6 +748,14 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb) {
         c.seg_pot[sid] = pot;
         c.seg_conn[sid] = conn;
         nm += pot >= thr ? 1 : 0;
+        if (append && pot >= thr) {  // this rank's matching segments, unordered (shard_ll.cuh)
+          const int i = atomicAdd(&append[0], 1);
+          if (i < c.xm_cap) {
+            append[8 + 3 * i] = sid;
+            append[8 + 3 * i + 1] = pot;
+            append[8 + 3 * i + 2] = conn;
+          }
+        }
       }
     }
   }

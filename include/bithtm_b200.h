@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 10
+#define BH_ABI_VERSION 11
 #define BH_MT_N 624
 #define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
 #define BH_TOPK_WS_INTS 81920
@@ -131,6 +131,9 @@ typedef struct bh_ctx {
                            /* (dense production is cheaper while most rows grow); 1: always */
   int32_t tail_chunks;     /* chunks the words after a skipped matrix are produced in (one jump */
                            /* each; 0 = 4)                                                     */
+  int32_t xch_ll;          /* fused_mode 3: exchanges as 8-byte {word, sequence} cells stored into */
+                           /* the peers' regions (csrc/shard_ll.cuh); 0 = copy + fence + flag    */
+  int32_t reserved2;
   int64_t skip_min;        /* a rand(L, W+1) of at least this many stream words may be  */
                            /* drawn lazily (fused_mode >= 2): only the rows of growing  */
                            /* segments are produced, by jumps (csrc/mt19937.cuh)        */
