@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
         __syncthreads();
         ph_learn_select_a(c, learning, 0, 1);
         __syncthreads();
-        ph_draw(c, 2, learning, 1);
+        ph_draw(c, 2, learning, 1, true);
         ph_learn_select_b(c, learning, 0, 1);
       }
       BH_SYNC();
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_SYNC();
     BH_STAMP();
     // P4: learning lists, recycled / new segments; draw #2 (rand(L, W+1)) on the rng CTA
-    if (rng) ph_draw(c, 2, learning, nlrn);
+    if (rng) ph_draw(c, 2, learning, nlrn, MODE == 2);
     if (b >= nl0 && worker) ph_learn_select_b(c, learning, b - nl0, nlrn);
     BH_SYNC();
     BH_STAMP();

@@ -350,7 +350,8 @@ __device__ __forceinline__ long long rng_room(const bh_ctx& c, long long step_ba
 // `x` = MT_RING words of shared memory.  Returns through shared state only.
 // Thread 0 of the drawing CTA, draw #2 of `count` doubles = rows of row_doubles (= W + 1) at cursor `cur`:
 // decide whether the step is lazy and, if so, lay out its tail.  Returns the number of tail chunks (0: dense).
-__device__ __forceinline__ int rng_plan_lazy(const bh_ctx& c, long long cur, long long count, int row_doubles) {
+__device__ __forceinline__ int rng_plan_lazy(const bh_ctx& c, long long cur, long long count, int row_doubles,
+                                             bool allow_lazy) {
   long long* r = c.rng64;
   const bool was_lazy = r[R_LAZY] != 0;
   // growing rows of the step before this one (g_prev) and of the one before that (g_before)
@@ -360,7 +361,7 @@ __device__ __forceinline__ int rng_plan_lazy(const bh_ctx& c, long long cur, lon
   r[R_GROW_HIST] = (g_before << 32) | g_prev;
   c.sc[BH_SC_NGROW] = 0;
   r[R_LAZY] = 0;
-  if (c.skip_polys <= 0 || c.fused_mode < 2) return 0;
+  if (c.skip_polys <= 0 || !allow_lazy) return 0;  // (only the cooperative step kernels have the lazy phases)
   const long long D = 2 * count;
   if (D < c.skip_min || cur < 1) return 0;
   const long long n_chunks = (D + RNG_LAZY_CHUNK - 1) / RNG_LAZY_CHUNK;
@@ -391,7 +392,7 @@ __device__ __forceinline__ int rng_plan_lazy(const bh_ctx& c, long long cur, lon
 
 __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long count, int off_slot, int n_slot,
                                       bool first_of_step, long long lookahead, bool may_plan,
-                                      bool publish_next = false, int row_doubles = 0) {
+                                      bool publish_next = false, int row_doubles = 0, bool allow_lazy = false) {
   __shared__ long long s_serial_target;
   if (threadIdx.x == 0) {
     long long* r = c.rng64;
@@ -410,7 +411,7 @@ __device__ __noinline__ void rng_draw(const bh_ctx& c, uint32_t* x, long long co
     long long la = lookahead;
     if (la > c.rng_step_words / 2) la = c.rng_step_words / 2;
     long long target = end + la + MT_N;  // keep 624 words past the cursor for state export
-    const int lazy_chunks = row_doubles > 0 ? rng_plan_lazy(c, cur, count, row_doubles) : 0;
+    const int lazy_chunks = row_doubles > 0 ? rng_plan_lazy(c, cur, count, row_doubles, allow_lazy) : 0;
     if (lazy_chunks > 0)  // only the jump window is needed now; matrix rows and tail come from jumps
       target = cur + c.skip_gran + RNG_WINDOW + 2LL * row_doubles + MT_N;
     long long produced = r[R_PRODUCED];

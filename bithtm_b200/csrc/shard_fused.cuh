@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
           __syncthreads();
           ph_learn_select_a(c, learning, 0, 1);
           __syncthreads();
-          ph_draw(c, 2, learning, 1);
+          ph_draw(c, 2, learning, 1, true);
           ph_learn_select_b(c, learning, 0, 1);
         }
       } else {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       }
       BH_SYNC();
       BH_STAMP();  // 6: lists + learning flags
-      if (rng) ph_draw(c, 2, learning, nw);
+      if (rng) ph_draw(c, 2, learning, nw, true);
       if (worker) ph_learn_select_b(c, learning, b, nw);
       BH_SYNC();
       BH_STAMP();  // 7: learning lists + draw 2

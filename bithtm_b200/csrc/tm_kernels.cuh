@@ -65,7 +65,8 @@ __device__ __forceinline__ LearnTotals learn_totals(const bh_ctx& c, int learnin
 // (for the per-CTA count arrays).  Draw #2 may leave a parallel production plan that
 // ph_rng_chunks (all CTAs) must run before the values are read.
 // ---------------------------------------------------------------------------------
-__device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, int nw) {
+// `allow_lazy`: the caller is a cooperative step kernel that runs the lazy phases after draw #2 (mt19937.cuh).
+__device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, int nw, bool allow_lazy = false) {
   __shared__ uint32_t x[MT_RING];
   __shared__ long long s_count;
   __shared__ int s_red[32];
@@ -99,7 +100,7 @@ __device__ __noinline__ void ph_draw(const bh_ctx& c, int which, int learning, i
   }
   __syncthreads();
   if (which == 1) rng_draw(c, x, s_count, R_OFF1, -1, true, 0, false);
-  else if (which == 2) rng_draw(c, x, s_count, R_OFF2, R_N2, false, c.rng_lookahead, true, true, s_row_doubles);
+  else if (which == 2) rng_draw(c, x, s_count, R_OFF2, R_N2, false, c.rng_lookahead, true, true, s_row_doubles, allow_lazy);
   else {
     rng_draw(c, x, s_count, R_OFF3, R_N3, false, 0, false);
     if (threadIdx.x == 0) rng_finish_step(c);
@@ -301,7 +302,13 @@ __device__ void ph_learn_select_a(const bh_ctx& c, int learning, int b, int nb) 
     const int S = c.sc[BH_SC_NSEG], thr = c.seg_matching_threshold;
     const Range sr = block_range(S, b, nb);
     #pragma unroll 1
-    for (int s = sr.begin + threadIdx.x; s < sr.end; s += NT) nr += c.seg_count[s] < thr ? 1 : 0;
+    for (int s = sr.begin + threadIdx.x; s < sr.end; s += 8 * NT) {  // 8 independent loads in flight per thread
+      int v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = s + u * NT < sr.end ? c.seg_count[s + u * NT] : thr;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) nr += v[u] < thr ? 1 : 0;
+    }
   }
   __shared__ int s_red3[96];
   block_sum3(nl, np, nr, s_red3);

@@ -458,7 +458,9 @@ class HierarchicalTemporalMemory:
         eng.begin_regular_step()
         is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
         staged = not return_winner_cell or eng.tm_deferred  # needs the per-stage kernels (bh_tm_step_ex)
-        if eng.ctx.fused_mode == 3:  # the shard's whole step is one kernel (exchanges inside)
+        fused_device = (eng.ctx.fused_mode in (1, 2) and not is_host and sp._native_inhibition and not staged
+                        and eng.shard_world == 1 and eng.seg_world == 1)
+        if eng.ctx.fused_mode == 3 or fused_device:  # the whole step is one kernel on a device input
             if not sp._native_inhibition:
                 raise NotImplementedError('fused="shard" needs the built-in GlobalInhibition')
             if staged:
