@@ -443,7 +443,8 @@ class Engine:
 
     # ------------------------------------------------------------------ steps
     def step_device(self, words, learning=True):
-        nat.check(nat.lib.bh_step(self.ref, words.data_ptr(), int(bool(learning)), self.stream), "bh_step")
+        """``learning``: bool, or the flag word of ``bh_step`` (1 = learning, 2 = no winner cells)."""
+        nat.check(nat.lib.bh_step(self.ref, words.data_ptr(), int(learning), self.stream), "bh_step")
         self.epoch += 1
 
     def step_host(self, x_bool: np.ndarray, learning=True) -> np.ndarray:
@@ -452,7 +453,7 @@ class Engine:
             xb = np.ascontiguousarray(x_bool, dtype=np.bool_)  # one byte per bit, 0/1: what bh_step_host reads
         if xb.size != self.I:
             raise ValueError(f"input has {xb.size} bits, expected {self.I}")
-        learning = bool(learning)
+        learning = int(learning)  # bool, or the flag word of bh_step
         key = ("host", learning, bytes(self.ctx))  # kernel arguments are frozen in the graph
         handle = self._graphs.get(key)
         if handle is None and self.host_graph:
@@ -490,14 +491,14 @@ class Engine:
         return self._summary_out
 
     def graph(self, steps_per_graph: int, learning=True):
-        key = (steps_per_graph, bool(learning))
+        key = (steps_per_graph, int(learning))
         if key not in self._graphs:
             torch = _torch()
             handle = C.c_void_p()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
-                nat.check(nat.lib.bh_graph_create(self.ref, int(steps_per_graph), int(bool(learning)),
+                nat.check(nat.lib.bh_graph_create(self.ref, int(steps_per_graph), int(learning),
                                                   self.stream, C.byref(handle)), "bh_graph_create")
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graphs[key] = handle

@@ -20,7 +20,7 @@ R_COUNT = 32  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 # device scalar block indices (enum in the header)
 (SC_STEP, SC_HAVE_PREV, SC_NSEG, SC_NSEG_NEXT, SC_M, SC_W0, SC_W1, SC_L0, SC_L, SC_P, SC_NU, SC_NR,
  SC_STATUS, SC_MT_POS, SC_X_MATCH, SC_X_RECYC_AVAIL, SC_X_RECYC_TOTAL, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN,
- SC_JIT_PENDING, SC_WNONE0, SC_WNONE1, SC_NGROW, SC_BAR2_COUNT, SC_BAR2_GEN) = range(26)
+ SC_JIT_PENDING, SC_WNONE0, SC_WNONE1, SC_NGROW, SC_BAR2_COUNT, SC_BAR2_GEN, SC_NPREDCOL, SC_NPREDCOL_PREV) = range(28)
 SC_COUNT = 32
 
 ST_SEG_OVERFLOW, ST_SYN_OVERFLOW, ST_MATCH_OVERFLOW, ST_LEARN_OVERFLOW, ST_RAND_OVERFLOW, ST_PRI_TIE = 1, 2, 4, 8, 16, 32
@@ -43,7 +43,7 @@ ST_FATAL = (ST_SEG_OVERFLOW | ST_SYN_OVERFLOW | ST_MATCH_OVERFLOW | ST_LEARN_OVE
 
 
 def summary_ints(k: int) -> int:
-    return 4 + 4 * k + MT_N + 1
+    return 4 + 4 * k + MT_N + 1 + 4
 
 
 _P = C.c_void_p

@@ -639,6 +639,7 @@ static int fused_smem(const bh_ctx* x) {
   int a = x->mask_stride * 4 + (x->fused_mode >= 2 ? TK2_BINS * 4 : 0), b = learn_apply_smem(x);
   int m = a > b ? a : b;
   if (x->fused_mode >= 2 && x->jump_polys > 0 && m < RNG_CHUNK_SMEM) m = RNG_CHUNK_SMEM;
+  if (m < MT_RING * 4) m = MT_RING * 4;  // the deferred-jitter draw of P0 stages the stream in dynamic shared memory
   if (x->fused_mode >= 2 && x->skip_polys > 0 && m < RNG_LAZY_SMEM_WORDS * 4) m = RNG_LAZY_SMEM_WORDS * 4;
   if (x->fused_mode == 3 && x->xch_ll && m < ll_smem_bytes(*x)) m = (int)(ll_smem_bytes(*x) < (1 << 20) ? ll_smem_bytes(*x) : (1 << 20));
   return m;
@@ -668,6 +669,7 @@ static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_step
                         cudaStream_t st) {
   const int nb = x->fused_ctas;
   if (nb < 1) return BH_E_BADARG;
+  if (learning < 0 || learning > 3 || (x->fused_mode == 3 && learning > 1)) return BH_E_UNSUPPORTED;
   const int smem = fused_smem(x);
   if (smem > 160 * 1024) return BH_E_UNSUPPORTED;
   int prc = prepare_fused(x->fused_mode);
@@ -712,11 +714,11 @@ extern "C" int bh_step(const bh_ctx* x, const uint32_t* in, int learning, void* 
   DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
+  if (learning < 0 || learning > 3 || (x->fused_mode == 3 && learning > 1)) return BH_E_UNSUPPORTED;
   if (x->fused_mode) return launch_fused(x, in, 1, learning, 0, S_(stream));
-  if ((rc = sp_step(x, in, learning, S_(stream)))) return rc;
-  if ((rc = bh_tm_select(x, stream))) return rc;
-  if ((rc = bh_tm_learn(x, learning, stream))) return rc;
-  return bh_tm_activate(x, stream);
+  const int learn = learning & BH_STEP_LEARNING, winners = !(learning & BH_STEP_NO_WINNER_CELLS);
+  if ((rc = sp_step(x, in, learn, S_(stream)))) return rc;
+  return bh_tm_step_ex(x, learn, winners, winners, stream);
 }
 
 extern "C" int bh_step_launches(const bh_ctx* x, int learning) {

@@ -13,8 +13,15 @@
 
 template <int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
-    k_step_fused(const __grid_constant__ bh_ctx c, const uint32_t* input_fixed, int n_steps, int learning, int want_summary) {
+    k_step_fused(const __grid_constant__ bh_ctx c, const uint32_t* input_fixed, int n_steps, int flags, int want_summary) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
+  // flags: BH_STEP_LEARNING | BH_STEP_NO_WINNER_CELLS (TemporalMemory.process's learning / return_winner_cell,
+  // networks.py:91): winner cells are formed (and rand(k, c) drawn) when learning or asked for (:99); the
+  // jitter of the activation is drawn only with return_winner_cell (:121) -- else it stays pending until a
+  // later step needs it.  Neither: the inference-only step, which draws nothing and updates only duty cycles.
+  const int learning = flags & BH_STEP_LEARNING;
+  const bool want_jit = !(flags & BH_STEP_NO_WINNER_CELLS);
+  const bool want = learning || want_jit;
   const int b = blockIdx.x, nb = gridDim.x;
   const int nw = nb > 1 ? nb - 1 : 1;  // CTAs running the ranged TM phases
   const bool worker = b < nw;
@@ -57,7 +64,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     stamp_i = 0;
     BH_STAMP();
     // P0: overlap + boost on all CTAs; draw #1 (rand(k, c)) on the rng CTA
-    if (rng) ph_draw(c, 1, 1, nw);
+    if (rng && want) {
+      ph_fill_jitter(c, s_dyn);  // the previous activation's deferred rand(M) first (no-op otherwise)
+      __syncthreads();
+      ph_draw(c, 1, 1, nw);
+    }
     constexpr bool HIST = MODE == 2;  // the grid-wide selection starts from a histogram built here
     if (nb == 1) ph_overlap<true, HIST>(c, input, s_dyn, 0, 1);
     else if (!rng) ph_overlap<true, HIST>(c, input, s_dyn, b, nb - 1);  // the rng CTA is busy drawing
@@ -80,34 +91,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_SYNC();
     BH_STAMP();
     // P2: SP learning + duty cycles; bursting / winner bits per active column.
-    // Large networks (grid mode): the bookkeeping of P3 / P4 is a chain of short dependent steps over a few
-    // thousand items; ONE CTA (the drawing one) runs it whole -- ordered lists, learning flags, draw #2, learning
-    // lists -- in a single phase: a phase and a barrier less than the many-CTA form.  (Running that chain NEXT TO
-    // the SP learning pass instead was measured slower: 96 us against 64 + 23: its dependent loads queue behind
-    // the bandwidth-bound traffic.)
-    const bool serial_lists = MODE == 2 && nb >= 32 && c.sc[BH_SC_M] <= 32768 && c.sc[BH_SC_NSEG] <= (1 << 18);
-    if (serial_lists) {
-      if (rng && c.column_dim >= 16384) tk3_rebin_from_selection(c);  // (no-op unless the selection fell back)
-      if (learning) ph_sp_learn<false>(c, input, b, nb);
-      ph_duty(c, b, nb);
-      if (worker) ph_select_a(c, b, nw);
-      BH_SYNC();
-      BH_STAMP();
-      if (rng) {
-        ph_select_b(c, 0, 1, true, nw);
-        __syncthreads();
-        ph_learn_select_a(c, learning, 0, 1);
-        __syncthreads();
-        ph_draw(c, 2, learning, 1, true);
-        ph_learn_select_b(c, learning, 0, 1);
-      }
-      BH_SYNC();
-      BH_STAMP();
-      BH_STAMP();
-    } else {
+    // (Measured and rejected at cfg3: the P2..P4 bookkeeping chain on a TEAM of CTAs next to the SP learning pass
+    // -- 96 us against 64 + 23, its dependent loads queue behind the bandwidth-bound traffic; and the P3 + P4
+    // chain on ONE CTA in a single phase -- 40 us against 23.)
     if (split) {
       if (b < nsel) {
-        ph_select_a(c, b, nsel);
+        ph_select_a(c, b, nsel, want);
       } else {
         if (learning) ph_sp_learn<true>(c, input, b - nsel, nb - nsel);
         ph_duty(c, b - nsel, nb - nsel);
@@ -116,12 +105,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       if (MODE == 2 && rng && c.column_dim >= 16384) tk3_rebin_from_selection(c);  // (no-op unless the selection fell back)
       if (learning) ph_sp_learn<MODE == 1>(c, input, b, nb);
       ph_duty(c, b, nb);
-      if (worker) ph_select_a(c, b, nw);
+      if (worker) ph_select_a(c, b, nw, want);
     }
     BH_SYNC();
     BH_STAMP();
     // P3: ordered winner lists; learning / punished flags among previous matching segments
-    if (b < nsel) ph_select_b(c, b, nsel);
+    if (b < nsel) ph_select_b(c, b, nsel, want);
     if (b >= nl0 && worker) ph_learn_select_a(c, learning, b - nl0, nlrn);
     if (rng && nb > 1) ph_rng_speculate(c, 1);  // idle here too: the other half
     BH_SYNC();
@@ -131,7 +120,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (b >= nl0 && worker) ph_learn_select_b(c, learning, b - nl0, nlrn);
     BH_SYNC();
     BH_STAMP();
-    }  // (!team)
     // A LAZY step (mt19937.cuh; decided by draw #2, published by the barrier) does not materialise
     // rand(L, W+1): stage 1 of the learning pass finds the rows that grow, jumps produce their words
     // and the words after the matrix.
@@ -176,7 +164,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     {
       __shared__ int s_red3[32];
       blk_prefix(BLK(c, BLK_MATCH), scanner ? b : 0, ns, s_red3, m_before, m_total);
-      ready3 = (long long)(m_total < c.match_capacity ? m_total : c.match_capacity) <= c.rng64[R_READY3];
+      ready3 = !want_jit || (long long)(m_total < c.match_capacity ? m_total : c.match_capacity) <= c.rng64[R_READY3];
       __syncthreads();
     }
     if (!ready3) {
@@ -185,8 +173,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     }
     BH_STAMP();
     // P9: matching list, jitter, predictions; completes the step
-    if (ready3 && rng) ph_draw3_ready(c, ns, m_total);
-    if (scanner) ph_activate_b(c, b, ns, ready3, true, m_before, m_total);
+    if (want_jit && ready3 && rng) ph_draw3_ready(c, ns, m_total);
+    if (scanner) ph_activate_b(c, b, ns, ready3, want_jit, m_before, m_total);
     BH_SYNC();
     BH_STAMP();
   }

@@ -404,6 +404,8 @@ __device__ void ph_learn_select_b(const bh_ctx& c, int learning, int b, int nb) 
     }
   }
   if (b == 0 && threadIdx.x == 0) {
+    c.sc[BH_SC_NPREDCOL_PREV] = c.sc[BH_SC_NPREDCOL];  // the predictions reset above (example.py:50)
+    c.sc[BH_SC_NPREDCOL] = 0;
     c.sc[BH_SC_L0] = lt.L0;
     c.sc[BH_SC_L] = lt.L;
     c.sc[BH_SC_P] = lt.P;
@@ -815,7 +817,7 @@ __device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false
       }
       if (conn >= c.seg_activation_threshold) {
         atomicAdd(&c.cell_npred[owner], 1);
-        atomicOr(&c.col_pred[owner >> 5], 1u << (owner & 31));
+        if (atomicOr(&c.col_pred[owner >> 5], 1u << (owner & 31)) == 0u) atomicAdd(&c.sc[BH_SC_NPREDCOL], 1);
       }
     }
   }
@@ -833,8 +835,8 @@ __device__ void ph_activate_b(const bh_ctx& c, int b, int nb, bool ready = false
 // The deferred jitter of the previous activation (projections.py:229-239 reached through
 // get_jittered_potential_info, networks.py:76): rand(M) drawn now, before this step's rand(k, c).
 // One CTA; no-op unless BH_SC_JIT_PENDING.
-__device__ void ph_fill_jitter(const bh_ctx& c) {
-  __shared__ uint32_t x[MT_RING];
+// `x`: MT_RING words of shared memory.
+__device__ void ph_fill_jitter(const bh_ctx& c, uint32_t* x) {
   if (!c.sc[BH_SC_JIT_PENDING] || !c.sc[BH_SC_HAVE_PREV]) return;
   const int M = c.sc[BH_SC_M];
   rng_draw(c, x, M, R_OFF3, R_N3, true, 0, false);
@@ -850,7 +852,10 @@ __device__ void ph_fill_jitter(const bh_ctx& c) {
   __syncthreads();
   if (threadIdx.x == 0) c.sc[BH_SC_JIT_PENDING] = 0;
 }
-__global__ void __launch_bounds__(MT_THREADS) k_tm_fill_jitter(const __grid_constant__ bh_ctx c) { ph_fill_jitter(c); }
+__global__ void __launch_bounds__(MT_THREADS) k_tm_fill_jitter(const __grid_constant__ bh_ctx c) {
+  __shared__ uint32_t x[MT_RING];
+  ph_fill_jitter(c, x);
+}
 
 // ---------------------------------------------------------------------------------
 // stand-alone kernels (fine-grained C entry points)
@@ -915,6 +920,7 @@ __global__ void __launch_bounds__(1024) k_tm_reset(const __grid_constant__ bh_ct
     c.sc[BH_SC_WNONE1] = 1;
     c.sc[BH_SC_JIT_PENDING] = 0;
     c.sc[BH_SC_NU] = 0;
+    c.sc[BH_SC_NPREDCOL] = 0;
   }
 }
 
@@ -1000,7 +1006,11 @@ __global__ void k_tm_adopt_active_clear(const __grid_constant__ bh_ctx c, int ha
     c.cell_npred[owner] = 0;
     c.col_pred[owner >> 5] = 0u;
   }
-  if (gid == 0) c.sc[BH_SC_NSEG] = c.sc[BH_SC_NSEG_NEXT];
+  if (gid == 0) {
+    c.sc[BH_SC_NSEG] = c.sc[BH_SC_NSEG_NEXT];
+    c.sc[BH_SC_NPREDCOL_PREV] = c.sc[BH_SC_NPREDCOL];
+    c.sc[BH_SC_NPREDCOL] = 0;
+  }
 }
 // the winner index rotation of ph_post (one CTA): entries of the previous winners out, this step's in
 __global__ void __launch_bounds__(1024) k_tm_adopt_widx(const __grid_constant__ bh_ctx c) {
@@ -1044,6 +1054,13 @@ __device__ void ph_summary(const bh_ctx& c, int b, int nb) {
     out[4 + 3 * k + i] = (int)c.row_win[i];
   }
   rng_export(c, out + 4 + 4 * k, gid, gsz);  // MT19937 state at the stream cursor
+  if (gid == 0) {
+    int* tail = out + 4 + 4 * k + MT_N + 1;
+    tail[0] = c.sc[BH_SC_NPREDCOL_PREV];
+    tail[1] = c.sc[BH_SC_NPREDCOL];
+    tail[2] = 0;
+    tail[3] = 0;
+  }
 }
 
 __global__ void k_summary(const __grid_constant__ bh_ctx c) { ph_summary(c, blockIdx.x, gridDim.x); }

@@ -162,7 +162,7 @@ __device__ void ph_activate_finish(const bh_ctx& c, int b, int nb, bool ready = 
     atomicMax(reinterpret_cast<int*>(c.cell_maxjit + owner), __float_as_int(jit));  // jit > 0
     if (conn >= c.seg_activation_threshold) {
       atomicAdd(&c.cell_npred[owner], 1);
-      atomicOr(&c.col_pred[owner >> 5], 1u << (owner & 31));
+      if (atomicOr(&c.col_pred[owner >> 5], 1u << (owner & 31)) == 0u) atomicAdd(&c.sc[BH_SC_NPREDCOL], 1);
     }
   }
   if (b == 0 && threadIdx.x == 0) {

@@ -178,6 +178,7 @@ class TemporalMemory:
             k, c = engine.k, engine.c
             self._c, self._C, self._k = c, engine.C, k
             self._head = summary[:4 + 4 * k].copy()  # the summary buffer is reused by the next step
+            self._tail = summary[4 + 4 * k + nat.MT_N + 1:4 + 4 * k + nat.MT_N + 5].copy()
             self._have_winner = have_winner
             self.n_segments = int(self._head[2])
             self.distal_state = PredictiveProjection.State(engine, projection, have_jitter)
@@ -225,6 +226,16 @@ class TemporalMemory:
         @property
         def active_column_bursting(self):  # networks.py:97, bool [k, 1]
             return (self._row_pred == 0).reshape(-1, 1)
+
+        @property
+        def column_metrics(self):
+            """Extension: the three counts example.py:55-57 prints, from the step summary alone (no read-back
+            of ``cell_prediction``): bursting active columns, active columns that were predicted, predicted
+            columns that did not become active; plus the columns predicted for the next step."""
+            bursting = int((self._row_pred == 0).sum())
+            correct = self._k - bursting
+            return {"bursting": bursting, "correct": correct, "incorrect": int(self._tail[0]) - correct,
+                    "predicted_columns": int(self._tail[1])}
 
         @property
         def cell_activation(self):  # networks.py:118-119, bool [C, c]
@@ -457,32 +468,17 @@ class HierarchicalTemporalMemory:
         sp, tm, eng = self.spatial_pooler, self.temporal_memory, self._engine
         eng.begin_regular_step()
         is_host = not (hasattr(input, "is_cuda") and input.is_cuda)
-        staged = not return_winner_cell or eng.tm_deferred  # needs the per-stage kernels (bh_tm_step_ex)
-        fused_device = (eng.ctx.fused_mode in (1, 2) and not is_host and sp._native_inhibition and not staged
-                        and eng.shard_world == 1 and eng.seg_world == 1)
-        if eng.ctx.fused_mode == 3 or fused_device:  # the whole step is one kernel on a device input
+        want = bool(learning or return_winner_cell)  # networks.py:99
+        flags = int(bool(learning)) | (0 if return_winner_cell else 2)  # BH_STEP_LEARNING | BH_STEP_NO_WINNER_CELLS
+        mode = eng.ctx.fused_mode
+        if mode == 3:  # the shard's whole step is one kernel (exchanges inside)
             if not sp._native_inhibition:
                 raise NotImplementedError('fused="shard" needs the built-in GlobalInhibition')
-            if staged:
+            if not return_winner_cell:
                 raise NotImplementedError('fused="shard" supports the default return_winner_cell=True only')
-            sp.boosting._bind(eng)
-            words = eng.pack_input(input)
-            tm._rng.before(eng)
-            eng.step_device(words, learning=learning)
-            if not return_state:
-                if tm._rng.mode != "lazy":
-                    raise ValueError('return_state=False needs rng_sync="lazy" (no per-step read-back)')
-                tm.last_state = None
-                return None
-            summary = eng.summary()
-            tm._rng.after(eng, summary)
-            tm_state = tm._finish(summary)
-            sp_state = sp.State(eng, active_column=tm_state._active_column)
-            sp_state._parity ^= 1
-            sp_state._group = sp._group
-            return sp_state, tm_state
-        if (not sp._native_inhibition or not is_host or eng.shard_world > 1 or eng.seg_world > 1 or not return_state
-                or staged):
+        whole_kernel = sp._native_inhibition and (mode == 3 or (eng.shard_world == 1 and eng.seg_world == 1))
+        if not whole_kernel:
+            # an arbitrary host object in the inhibition slot, or NCCL exchanges between the stages of a shard
             sp_state = sp.process(input, learning=learning)
             sp_state._group = sp._group
             tm_state = tm.process(sp_state, learning=learning, return_state=return_state,
@@ -493,9 +489,24 @@ class HierarchicalTemporalMemory:
             return sp_state, tm_state
         sp.boosting._bind(eng)
         tm._rng.before(eng)
-        summary = eng.step_host(np.asarray(input).reshape(-1), learning=learning)
+        if mode == 3 or not is_host or not return_state:
+            # device input (or nothing to read back): enqueue the step; the summary is fetched only when asked for
+            words = eng.pack_input(input)
+            eng.step_device(words, learning=flags)
+            eng.tm_deferred = not return_winner_cell
+            if not return_state:
+                if tm._rng.mode != "lazy":
+                    raise ValueError('return_state=False needs rng_sync="lazy" (no per-step read-back)')
+                tm.last_state = None
+                return None
+            summary = eng.summary()
+        else:
+            # host input: ONE call -- H2D of the packed input, the whole step, D2H of the step summary
+            summary = eng.step_host(np.asarray(input).reshape(-1), learning=flags)
+            eng.tm_deferred = not return_winner_cell
         tm._rng.after(eng, summary)
-        tm_state = tm._finish(summary)
+        tm_state = tm._finish(summary, have_winner=want, have_jitter=bool(return_winner_cell))
         sp_state = sp.State(eng, active_column=tm_state._active_column)
         sp_state._parity ^= 1  # created after the step completed
+        sp_state._group = sp._group
         return sp_state, tm_state

@@ -30,6 +30,8 @@ if __name__ == "__main__":
     parser.add_argument("--cell_dim", type=int, default=32)
     parser.add_argument("--seed", type=int, default=None, help="np.random.seed (the reference is unseeded)")
     parser.add_argument("--quiet", action="store_true", help="print a summary per epoch instead of per step")
+    parser.add_argument("--readback", action="store_true",
+                        help="compute the metrics on the host from cell_prediction, as the reference does")
     args = parser.parse_args()
 
     if args.seed is not None:
@@ -41,16 +43,21 @@ if __name__ == "__main__":
     w_p = len(str(max(args.input_patterns - 1, 1)))
     w_c = len(str(max(args.column_dim - 1, 1)))
     w_a = len(str(max(htm.spatial_pooler.active_columns - 1, 1)))
+    prev_column_prediction = np.zeros(args.column_dim, dtype=bool)  # example.py:50 (only with --readback)
     start_time = time.time()
     for epoch in range(args.epochs):
         totals = np.zeros(3, dtype=np.int64)
         for input_index, curr_input in enumerate(inputs):
-            prev_column_prediction = htm.temporal_memory.last_state.cell_prediction.max(axis=1)  # example.py:50
             noisy_input = curr_input ^ (np.random.rand(args.input_dim) < args.input_noise_probability)  # :52
             sp_state, tm_state = htm.process(noisy_input)
-            burstings = tm_state.active_column_bursting.sum()  # :55
-            corrects = prev_column_prediction[sp_state.active_column].sum()  # :56
-            incorrects = prev_column_prediction.sum() - corrects  # :57
+            if args.readback:  # the reference's own expressions (example.py:50, 55-57): reads cell_prediction back
+                burstings = tm_state.active_column_bursting.sum()
+                corrects = prev_column_prediction[sp_state.active_column].sum()
+                incorrects = prev_column_prediction.sum() - corrects
+                prev_column_prediction = tm_state.cell_prediction.max(axis=1)
+            else:  # the same three counts from the step summary (counted on the device)
+                m = tm_state.column_metrics
+                burstings, corrects, incorrects = m["bursting"], m["correct"], m["incorrect"]
             totals += (burstings, corrects, incorrects)
             if not args.quiet:
                 print(f"epoch {epoch:{w_e}d}, pattern {input_index:{w_p}d}: bursting columns: {burstings:{w_a}d}, "

@@ -31,7 +31,7 @@ extern "C" {
 
 #define BH_ABI_VERSION 11
 #define BH_MT_N 624
-#define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1)
+#define BH_SUMMARY_INTS(k) (4 + 4 * (k) + BH_MT_N + 1 + 4)
 #define BH_TOPK_WS_INTS 81920
 
 /* error codes (negative); CUDA errors are returned as -(1000 + cudaError_t) */
@@ -71,6 +71,8 @@ enum {
                        /* projections.py:114-115): the rows of rand(L, W+1) that are read */
   BH_SC_BAR2_COUNT,    /* barrier of the CTA team that does the temporal-memory         */
   BH_SC_BAR2_GEN,      /* bookkeeping while the other CTAs learn the spatial pooler     */
+  BH_SC_NPREDCOL,      /* columns with a predicted cell after the last activation        */
+  BH_SC_NPREDCOL_PREV, /* ... before this step's learning (example.py:50, the demo's metrics) */
   BH_SC_COUNT = 32
 };
 
@@ -371,7 +373,15 @@ int bh_tm_activate_cells(const bh_ctx* ctx, const int32_t* active_cells_dev, int
 int bh_tm_fill_jitter(const bh_ctx* ctx, void* stream);
 int bh_tm_reset(const bh_ctx* ctx, void* stream);
 
-/* ---- whole timestep: HierarchicalTemporalMemory.process (networks.py:146-149) ------ */
+/* ---- whole timestep: HierarchicalTemporalMemory.process (networks.py:146-149) ------
+ * `learning` of bh_step / bh_step_ring / bh_step_host* / bh_graph_* is a flag word: BH_STEP_LEARNING (1) =
+ * the `learning` argument; BH_STEP_NO_WINNER_CELLS (2) = TemporalMemory.process(return_winner_cell=False)
+ * (networks.py:91, 99, 121).  0 and 1 are the reference's defaults; 2 is the inference-only step (no winner
+ * cells, no random draw, only the duty cycles change; one fused kernel like the learning step); 3 learns
+ * without drawing the jitter of the activation (it is drawn by the next step that needs it).  Segment shards
+ * (fused_mode 3) support 0 and 1. */
+#define BH_STEP_LEARNING 1
+#define BH_STEP_NO_WINNER_CELLS 2
 int bh_step(const bh_ctx* ctx, const uint32_t* input_words_dev, int learning, void* stream);
 /* Same, input taken from input_ring[sc[BH_SC_INPUT_POS]++ % ring_len] (no host
  * involvement; CUDA-graph friendly). */
@@ -381,7 +391,9 @@ int bh_step_ring(const bh_ctx* ctx, int learning, void* stream);
  * summary_host (BH_SUMMARY_INTS(k) int32): [0]=step index, [1]=status, [2]=n_segments,
  * [3]=winner count, then active_column[k], row_pred[k], row_act[k], row_win[k], then
  * the MT19937 state after the step (624 key words + position) so the caller can
- * keep np.random in lock-step. */
+ * keep np.random in lock-step, then [predicted columns before this step, predicted columns
+ * after it, 0, 0]: with row_pred this gives example.py:55-57's bursting / correct / incorrect
+ * column counts without reading cell_prediction back. */
 int bh_step_host(const bh_ctx* ctx, const uint8_t* input_bool_host, int learning,
                  int32_t* summary_host, void* stream);
 

@@ -460,10 +460,46 @@ def test_example_driver_stream_matches_oracle():
         x = inputs[t % 7] ^ (np.random.rand(I) < 0.05)
         xo = inputs_o[t % 7] ^ (rs.rand(I) < 0.05)
         assert np.array_equal(x, xo), f"caller-visible np.random diverged at step {t}"
+        prev_col_pred = orc.cell_prediction.max(axis=1)  # example.py:50
         sp_state, tm_state = htm.process(x)
         rec = orc.step(xo)
         problems = diff_records(gpu_record(htm, sp_state, tm_state), oracle_record(rec))
         assert not problems, f"step {t}: " + "; ".join(problems)
+        # the demo's three counts (example.py:55-57), counted on the device and carried by the step summary
+        corrects = int(prev_col_pred[rec.active_column].sum())
+        assert tm_state.column_metrics == {
+            "bursting": int(rec.bursting.sum()), "correct": corrects, "incorrect": int(prev_col_pred.sum()) - corrects,
+            "predicted_columns": int(orc.cell_prediction.max(axis=1).sum())}, t
+
+
+@pytest.mark.parametrize("extra", [[], ["--readback"]])
+def test_example_script_prints_the_oracle_counts(extra):
+    """example.py (the device-backed copy of the reference's demo, same CLI) run as a script: the per-epoch
+    bursting / correct / incorrect totals equal the oracle's on the same seed, with the metrics taken from the
+    device counters and -- `--readback` -- computed on the host as the reference does."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    args = ["--epochs", "4", "--input_patterns", "25", "--input_dim", "200", "--column_dim", "512", "--cell_dim", "8",
+            "--seed", "5", "--quiet"]
+    out = subprocess.run([sys.executable, os.path.join(root, "example.py"), *args, *extra], capture_output=True,
+                         text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rs = np.random.RandomState(5)
+    inputs = rs.rand(25, 200) < 0.2
+    orc = HTMOracle(OracleConfig(200, 512, 8), rng=rs)
+    want = []
+    for epoch in range(4):
+        tot = np.zeros(3, dtype=np.int64)
+        for x0 in inputs:
+            prev = orc.cell_prediction.max(axis=1)
+            rec = orc.step(x0 ^ (rs.rand(200) < 0.05))
+            corrects = int(prev[rec.active_column].sum())
+            tot += (int(rec.bursting.sum()), corrects, int(prev.sum()) - corrects)
+        want.append(f"epoch {epoch}: bursting {tot[0]}, correct {tot[1]}, incorrect {tot[2]}")
+    got = [ln for ln in out.stdout.splitlines() if ln.startswith("epoch")]
+    assert got == want
 
 
 @pytest.mark.gpu
@@ -505,13 +541,13 @@ def test_stream_batch_equals_streams_stepped_alone():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fused", ["cluster", "off"])
+@pytest.mark.parametrize("fused", ["cluster", "grid", "off"])
 def test_mixed_learning_and_winner_flags_match_reference_trace(fused):
     """Per-step (learning, return_winner_cell) flags of TemporalMemory.process (networks.py:91):
     inference-only steps draw nothing, the jitter draw is deferred until a later step needs
     it, no growth after a step without winner cells -- against the trace recorded from the
-    unmodified reference (tests/golden/mixed.npz), through HierarchicalTemporalMemory.process
-    (which falls back from the fused kernel to the per-stage kernels when it has to)."""
+    unmodified reference (tests/golden/mixed.npz), through HierarchicalTemporalMemory.process:
+    every flag combination is ONE launch of the fused step kernel (or the per-stage kernels with "off")."""
     import bithtm_b200 as bithtm
 
     info = load_golden("mixed")
