@@ -20,7 +20,7 @@ R_COUNT = 32  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 # device scalar block indices (enum in the header)
 (SC_STEP, SC_HAVE_PREV, SC_NSEG, SC_NSEG_NEXT, SC_M, SC_W0, SC_W1, SC_L0, SC_L, SC_P, SC_NU, SC_NR,
  SC_STATUS, SC_MT_POS, SC_X_MATCH, SC_X_RECYC_AVAIL, SC_X_RECYC_TOTAL, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN,
- SC_JIT_PENDING, SC_WNONE0, SC_WNONE1, SC_NGROW, SC_BAR2_COUNT, SC_BAR2_GEN, SC_NPREDCOL, SC_NPREDCOL_PREV) = range(28)
+ SC_JIT_PENDING, SC_WNONE0, SC_WNONE1, SC_NGROW, SC_BAR2_COUNT, SC_BAR2_GEN, SC_NPREDCOL, SC_NPREDCOL_PREV, SC_T5_ERR) = range(29)
 SC_COUNT = 32
 
 ST_SEG_OVERFLOW, ST_SYN_OVERFLOW, ST_MATCH_OVERFLOW, ST_LEARN_OVERFLOW, ST_RAND_OVERFLOW, ST_PRI_TIE = 1, 2, 4, 8, 16, 32
@@ -120,6 +120,8 @@ _SIGNATURES = {
     "bh_sp_overlap": (C.c_int, [_CTXP, _P, _P]),
     "bh_sp_overlap_batched": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
     "bh_sp_overlap_batched_tc": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
+    "bh_sp_overlap_batched_tc5": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
+    "bh_sp_overlap_batched_mma": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
     "bh_boost": (C.c_int, [_CTXP, _P]),
     "bh_inhibit": (C.c_int, [_CTXP, _P]),
     "bh_set_active_columns": (C.c_int, [_CTXP, _P, _P]),

@@ -10,6 +10,7 @@
 #include "fused.cuh"
 #include "tm_shard.cuh"
 #include "shard_fused.cuh"
+#include "overlap_tcgen05.cuh"
 
 #define CU_RET(expr)                                   \
   do {                                                 \
@@ -276,8 +277,83 @@ extern "C" int bh_sp_overlap_batched(const bh_ctx* x, const uint32_t* inputs_dev
   return 0;
 }
 
+extern "C" int bh_sp_overlap_batched_mma(const bh_ctx* x, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
+                                         void* stream);
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda: the library must load
+// without a driver for the build / symbol checks)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+      fn = reinterpret_cast<tmap_encode_fn>(p);
+  }
+  return fn;
+}
+// uint32 [rows][pitch_words] (extent `words` of every row is data), box {t5::KW words, box_rows rows}
+static int tmap_words_2d(CUtensorMap* m, const uint32_t* base, int rows, int words, int pitch_words, int box_rows) {
+  tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return BH_E_UNSUPPORTED;
+  const cuuint64_t dims[2] = {(cuuint64_t)words, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_words * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)t5::KW, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : BH_E_BADARG;
+}
+
+static bool t5_eligible(const bh_ctx* x, const uint32_t* inputs_dev, int n_inputs) {
+  // TMA: 16-byte row pitches and bases; worth it from a few tiles of work on
+  return x->input_words % 4 == 0 && (reinterpret_cast<uintptr_t>(inputs_dev) & 15) == 0 && n_inputs >= 64 &&
+         x->col_local >= 128 && x->input_words >= 16;
+}
+
+extern "C" int bh_sp_overlap_batched_tc5(const bh_ctx* x, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
+                                         void* stream) {
+  DevGuard dev_guard_(x);
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (!inputs_dev || !overlaps_out || n_inputs < 0) return BH_E_BADARG;
+  if (n_inputs == 0) return 0;
+  if (x->input_words % 4 != 0 || (reinterpret_cast<uintptr_t>(inputs_dev) & 15)) return BH_E_UNSUPPORTED;
+  CUtensorMap map_in, map_mask;
+  if ((rc = tmap_words_2d(&map_in, inputs_dev, n_inputs, x->input_words, x->input_words, t5::TILE_M))) return rc;
+  if ((rc = tmap_words_2d(&map_mask, x->sp_mask, x->col_local, x->input_words, x->mask_stride, t5::TILE_N))) return rc;
+  static bool attr_done[BH_MAX_DEVICES] = {};
+  const int d = current_device_slot();
+  if (!attr_done[d]) {
+    CU_RET(cudaFuncSetAttribute(t5::k_sp_overlap_batched_t5, cudaFuncAttributeMaxDynamicSharedMemorySize, t5::SMEM_BYTES));
+    attr_done[d] = true;
+  }
+  const int tiles = cdiv(n_inputs, t5::TILE_M) * cdiv(x->col_local, t5::TILE_N);
+  const int sms = x->sm_count > 0 ? x->sm_count : 148;
+  t5::k_sp_overlap_batched_t5<<<tiles < sms ? tiles : sms, t5::THREADS, t5::SMEM_BYTES, S_(stream)>>>(
+      map_in, map_mask, x->input_words, n_inputs, x->col_local, overlaps_out, x->sc + BH_SC_T5_ERR);
+  LAUNCHED("sp_overlap_batched_tc5");
+  return 0;
+}
+
 extern "C" int bh_sp_overlap_batched_tc(const bh_ctx* x, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
                                         void* stream) {
+  DevGuard dev_guard_(x);
+  int rc = check_ctx(x);
+  if (rc) return rc;
+  if (!inputs_dev || !overlaps_out || n_inputs < 0) return BH_E_BADARG;
+  if (n_inputs == 0) return 0;
+  if (t5_eligible(x, inputs_dev, n_inputs) && tmap_encoder())  // tcgen05 + TMEM + TMA; else the mma.sync kernel
+    return bh_sp_overlap_batched_tc5(x, inputs_dev, n_inputs, overlaps_out, stream);
+  return bh_sp_overlap_batched_mma(x, inputs_dev, n_inputs, overlaps_out, stream);
+}
+
+extern "C" int bh_sp_overlap_batched_mma(const bh_ctx* x, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
+                                         void* stream) {
   DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;

@@ -73,6 +73,7 @@ enum {
   BH_SC_BAR2_GEN,      /* bookkeeping while the other CTAs learn the spatial pooler     */
   BH_SC_NPREDCOL,      /* columns with a predicted cell after the last activation        */
   BH_SC_NPREDCOL_PREV, /* ... before this step's learning (example.py:50, the demo's metrics) */
+  BH_SC_T5_ERR,        /* a barrier wait of the tcgen05 batched overlap timed out          */
   BH_SC_COUNT = 32
 };
 
@@ -266,11 +267,20 @@ int bh_sp_overlap(const bh_ctx* ctx, const uint32_t* input_words_dev, void* stre
 int bh_sp_overlap_batched(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
                           void* stream);
 /* Same contract and same results as bh_sp_overlap_batched, computed as an int8 tensor-core
- * contraction [n_inputs x I] . [I x C] (mma.sync m16n8k32 u8, int32 accumulate: exact); the
- * operands stay bit-packed in HBM / shared memory and are widened to bytes in registers.
- * BH_E_UNSUPPORTED for 2^24 or more input bits (use bh_sp_overlap_batched). */
+ * contraction [n_inputs x I] . [I x C] with int32 accumulation (exact); the operands stay bit-packed
+ * in HBM.  bh_sp_overlap_batched_tc picks the kernel:
+ *  - bh_sp_overlap_batched_tc5: tcgen05.mma kind::i8 (128 x 256 x 32 per instruction), accumulator in TMEM,
+ *    packed words brought in by TMA and widened to bytes in shared memory (csrc/overlap_tcgen05.cuh).
+ *    Needs input_words % 4 == 0 and a 16-byte aligned inputs_dev (TMA pitches), else BH_E_UNSUPPORTED; a
+ *    pipeline fault raises sc[BH_SC_T5_ERR] instead of hanging.
+ *  - bh_sp_overlap_batched_mma: mma.sync m16n8k32 u8, operands widened in registers: small or ragged
+ *    shapes.  BH_E_UNSUPPORTED for 2^24 or more input bits (use bh_sp_overlap_batched). */
 int bh_sp_overlap_batched_tc(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
                              void* stream);
+int bh_sp_overlap_batched_tc5(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
+                              void* stream);
+int bh_sp_overlap_batched_mma(const bh_ctx* ctx, const uint32_t* inputs_dev, int n_inputs, int32_t* overlaps_out,
+                              void* stream);
 /* ExponentialBoosting.process (regularizations.py:15-17) -> ctx->boosted */
 int bh_boost(const bh_ctx* ctx, void* stream);
 /* GlobalInhibition.process (regularizations.py:28-29) with the canonical rule
