@@ -117,6 +117,7 @@ _SIGNATURES = {
     "bh_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bh_sp_build_mask": (C.c_int, [_CTXP, _P]),
     "bh_pack_input": (C.c_int, [_CTXP, _P, _P, _P]),
+    "bh_pack_inputs": (C.c_int, [_CTXP, _P, C.c_int, C.c_int, _P, _P]),
     "bh_sp_overlap": (C.c_int, [_CTXP, _P, _P]),
     "bh_sp_overlap_batched": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),
     "bh_sp_overlap_batched_tc": (C.c_int, [_CTXP, _P, C.c_int, _P, _P]),

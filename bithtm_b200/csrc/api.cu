@@ -248,6 +248,19 @@ extern "C" int bh_pack_input(const bh_ctx* x, const uint8_t* bool_dev, uint32_t*
   return 0;
 }
 
+extern "C" int bh_pack_inputs(const bh_ctx* x, const uint8_t* bool_dev, int n_inputs, int pitch_words, uint32_t* words_dev,
+                              void* stream) {
+  DevGuard dev_guard_(x);
+  if (!x || !bool_dev || !words_dev || n_inputs < 0 || pitch_words < x->input_words) return BH_E_BADARG;
+  if (n_inputs == 0) return 0;
+  const long long warps = (long long)n_inputs * pitch_words;
+  const int cap = (x->sm_count > 0 ? x->sm_count : 148) * 16;
+  const int grid = cdiv(warps * 32, 256);
+  k_pack_inputs<<<grid < cap ? grid : cap, 256, 0, S_(stream)>>>(*x, bool_dev, n_inputs, pitch_words, words_dev);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 template <bool BOOST>
 static int launch_overlap(const bh_ctx* x, const uint32_t* in, cudaStream_t st) {
   int g = overlap_group_host(x);

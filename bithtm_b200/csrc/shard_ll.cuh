@@ -73,6 +73,37 @@ __device__ __forceinline__ int ll_load(const bh_ctx& c, const int* cell, int seq
     }
   }
 }
+// The same cell index in the records of all G source ranks at once (independent loads in flight; spins only on
+// the cells that have not arrived): v[g] for g < G.
+__device__ __forceinline__ void ll_load_ranks(const bh_ctx& c, const int* mine, int kind, int par, long long i, int seq, int G,
+                                              int (&v)[BH_MAX_RANKS]) {
+  unsigned pending = (1u << G) - 1u;
+  long long t0 = 0;
+  while (pending) {
+#pragma unroll
+    for (int g = 0; g < BH_MAX_RANKS; ++g) {
+      if (pending & (1u << g)) {
+        int x, sq;
+        asm volatile("ld.relaxed.sys.global.v2.s32 {%0, %1}, [%2];" : "=r"(x), "=r"(sq) : "l"(mine + ll_cell(c, kind, par, g, i)) : "memory");
+        if (sq == seq) {
+          v[g] = x;
+          pending &= ~(1u << g);
+        }
+      }
+    }
+    if (pending) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > LL_TIMEOUT_CYCLES) {
+        atomicOr(&c.sc[BH_SC_STATUS], BH_ST_XCH_TIMEOUT);
+#pragma unroll
+        for (int g = 0; g < BH_MAX_RANKS; ++g)
+          if (pending & (1u << g)) v[g] = 0;
+        return;
+      }
+    }
+  }
+}
+
 // word i of this rank's record -> every rank (its own region included: one code path)
 __device__ __forceinline__ void ll_put(const bh_ctx& c, int* const* ll, int kind, int par, long long i, int v, int seq) {
   const int G = c.seg_world > 1 ? c.seg_world : 1;
@@ -101,7 +132,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   __shared__ int s_scan[32];
   __shared__ int s_bin, s_rem, s_ncand, s_cnt[4 * BH_MAX_RANKS];
   __shared__ unsigned long long s_kth_key, s_gmax;
-  const int t = threadIdx.x, NT = blockDim.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x, NT = blockDim.x, lane = t & 31;
   const int G = c.seg_world > 1 ? c.seg_world : 1, me = c.seg_rank;
   const int k = c.active_columns, k_loc = ll_k_loc(c), n = c.col_local;
   const int step = c.sc[BH_SC_STEP], par = step & 1, seq = step + 1;
@@ -127,43 +158,49 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     ll_put(c, ll, 0, par, i, v, seq);
   }
   int* mine = ll[me];
+  __shared__ int s_meta[3 * BH_MAX_RANKS];
+  if (t < 3 * G) s_meta[t] = ll_load(c, mine + ll_cell(c, 0, par, t / 3, TK2_BINS + t % 3), seq);
+  // every thread owns two bins (descending order: slot j holds bin 2047 - j) of every rank's histogram and keeps
+  // them in registers: the per-rank counts above / inside the threshold bin need no second read
+  int hv[2][BH_MAX_RANKS];
+  int my_sum = 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int bin = TK2_BINS - 1 - (2 * t + i);
+#pragma unroll
+    for (int g = 0; g < BH_MAX_RANKS; ++g) hv[i][g] = 0;
+    if (bin >= 1) ll_load_ranks(c, mine, 0, par, bin, seq, G, hv[i]);
+    int sum = 0;
+#pragma unroll
+    for (int g = 0; g < BH_MAX_RANKS; ++g) sum += hv[i][g];
+    s_h[2 * t + i] = sum;
+    my_sum += sum;
+  }
+  if (t < 4 * BH_MAX_RANKS) s_cnt[t] = 0;
+  if (t == 0) s_ncand = -1;
+  __syncthreads();
   if (t == 0) {
     unsigned long long gm = 0ull;
     int all_hist = 1;
     for (int g = 0; g < G; ++g) {
-      const unsigned lo = (unsigned)ll_load(c, mine + ll_cell(c, 0, par, g, TK2_BINS), seq);
-      const unsigned hi = (unsigned)ll_load(c, mine + ll_cell(c, 0, par, g, TK2_BINS + 1), seq);
-      all_hist &= ll_load(c, mine + ll_cell(c, 0, par, g, TK2_BINS + 2), seq);
-      const unsigned long long m = ((unsigned long long)hi << 32) | lo;
+      const unsigned long long m = ((unsigned long long)(unsigned)s_meta[3 * g + 1] << 32) | (unsigned)s_meta[3 * g];
+      all_hist &= s_meta[3 * g + 2];
       gm = m > gm ? m : gm;
     }
     s_gmax = gm;
-    s_ncand = all_hist ? -1 : -2;
-  }
-  {
-    const int per = (TK2_BINS + NT - 1) / NT;  // descending order: slot j holds bin 2047 - j
-    for (int i = 0; i < per; ++i) {
-      const int bin = TK2_BINS - 1 - (t * per + i);
-      int sum = 0;
-      if (bin >= 1)
-        for (int g = 0; g < G; ++g) sum += ll_load(c, mine + ll_cell(c, 0, par, g, bin), seq);
-      s_h[t * per + i] = sum;
-    }
+    if (!all_hist) s_ncand = -2;
   }
   __syncthreads();
   bool ok = s_ncand == -1;
   if (ok) {
-    const int per = (TK2_BINS + NT - 1) / NT;
-    int sum = 0;
-    for (int i = 0; i < per; ++i) sum += s_h[t * per + i];
     int total;
-    const int before = block_excl_scan(sum, s_scan, total);
-    if (before < k && before + sum >= k) {
+    const int before = block_excl_scan(my_sum, s_scan, total);
+    if (before < k && before + my_sum >= k) {
       int r = k - before;
-      for (int i = 0; i < per; ++i) {
-        const int h = s_h[t * per + i];
+      for (int i = 0; i < 2; ++i) {
+        const int h = s_h[2 * t + i];
         if (r > 0 && h >= r) {
-          s_bin = TK2_BINS - 1 - (t * per + i);
+          s_bin = TK2_BINS - 1 - (2 * t + i);
           s_rem = r;
           s_ncand = h;
           r = -1;
@@ -177,15 +214,24 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   }
   if (!ok) return false;  // identical decision on every rank (same gathered data)
   const int bin = s_bin, rem = s_rem;
-  // per rank: keys above the bin (a_g) and inside it (m_g); warp g handles rank g
-  if (warp < G) {
-    int a = 0;
-#pragma unroll 1
-    for (int i = bin + 1 + lane; i < TK2_BINS; i += 32) a += ll_load(c, mine + ll_cell(c, 0, par, warp, i), seq);
-    a = warp_sum(a);
-    if (lane == 0) {
-      s_cnt[warp] = a;
-      s_cnt[BH_MAX_RANKS + warp] = ll_load(c, mine + ll_cell(c, 0, par, warp, bin), seq);
+  // per rank: keys above the bin (a_g) and inside it (m_g), from the registers
+  {
+    int a[BH_MAX_RANKS];
+#pragma unroll
+    for (int g = 0; g < BH_MAX_RANKS; ++g) a[g] = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int b2 = TK2_BINS - 1 - (2 * t + i);
+#pragma unroll
+      for (int g = 0; g < BH_MAX_RANKS; ++g) {
+        if (b2 > bin) a[g] += hv[i][g];
+        if (b2 == bin) s_cnt[BH_MAX_RANKS + g] = hv[i][g];
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < BH_MAX_RANKS; ++g) {
+      const int w = warp_sum(a[g]);
+      if (lane == 0 && w) atomicAdd(&s_cnt[g], w);
     }
   }
   __syncthreads();
@@ -388,12 +434,7 @@ __device__ __noinline__ void ph_shard_segs_ll(const bh_ctx& c, int* const* ll, u
   }
   // gather the headers
   int* mine = ll[me];
-  if (t < G) {
-    s_n[t] = ll_load(c, mine + ll_cell(c, 2, par, t, 0), seq);
-    s_n[BH_MAX_RANKS + t] = ll_load(c, mine + ll_cell(c, 2, par, t, 1), seq);
-    s_n[2 * BH_MAX_RANKS + t] = ll_load(c, mine + ll_cell(c, 2, par, t, 2), seq);
-    s_n[3 * BH_MAX_RANKS + t] = ll_load(c, mine + ll_cell(c, 2, par, t, 3), seq);
-  }
+  if (t < 4 * G) s_n[(t & 3) * BH_MAX_RANKS + (t >> 2)] = ll_load(c, mine + ll_cell(c, 2, par, t >> 2, t & 3), seq);
   __syncthreads();
   int M = 0, R = 0, RT = 0, st = 0;
   for (int g = 0; g < G; ++g) {

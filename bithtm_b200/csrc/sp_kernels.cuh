@@ -122,6 +122,22 @@ __global__ void k_pack_input(const __grid_constant__ bh_ctx c, const uint8_t* __
   if (lane == 0) dst[w] = bits;
 }
 
+// n_inputs bool vectors [n_inputs][I] (one byte per bit) -> packed rows of `pitch` words (>= input_words; the
+// padding words are written as zero): the operand layout of the batched overlaps
+__global__ void k_pack_inputs(const __grid_constant__ bh_ctx c, const uint8_t* __restrict__ src, int n_inputs, int pitch,
+                              uint32_t* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const long long n_words = (long long)n_inputs * pitch;
+  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words;
+       w += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int row = (int)(w / pitch), wi = (int)(w - (long long)row * pitch);
+    const int i = wi * 32 + lane;
+    const bool on = i < c.input_dim && src[(long long)row * c.input_dim + i] != 0;
+    const uint32_t bits = __ballot_sync(BH_FULL, on);
+    if (lane == 0) dst[w] = bits;
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // (a) overlap + (c) boost.  G lanes cooperate on one mask row with 128-bit loads
 // (G = largest power of two <= min(32, mask_stride/4)), so a warp covers 32/G rows

@@ -100,29 +100,28 @@ class DenseProjection:
     def process_batch(self, input_activations, tensor_core=True):
         """Extension: ``process`` (projections.py:18-21) for a batch of inputs [B, input_dim] against
         this one projection -> int64 overlaps [B, output_dim] (a CUDA tensor in, a CUDA tensor out
-        when given one).  Column-sharded: this rank's columns.  ``tensor_core=True``: the int8
-        tensor-core contraction (``bh_sp_overlap_batched_tc``); ``False``: AND + popcount on the
-        integer pipe (``bh_sp_overlap_batched``).  Both are exact and agree bit for bit."""
+        when given one).  Column-sharded: this rank's columns.  ``tensor_core``: ``True`` = the int8
+        tensor-core contraction, tcgen05 + TMEM + TMA for all but small or oddly sized problems
+        (``bh_sp_overlap_batched_tc``); ``"tcgen05"`` / ``"mma"`` force one of its two kernels; ``False`` =
+        AND + popcount on the integer pipe (``bh_sp_overlap_batched``).  All are exact and agree bit for bit."""
         import torch
 
         eng = self._need_engine()
         is_cuda = isinstance(input_activations, torch.Tensor) and input_activations.is_cuda
         x = input_activations if is_cuda else torch.from_numpy(np.ascontiguousarray(input_activations)).to(eng.device)
-        x = x.reshape(-1, self.input_dim).to(torch.bool)
+        x = x.reshape(-1, self.input_dim).to(torch.uint8).contiguous()  # one byte per bit
         B, words = x.shape[0], eng.ctx.input_words
-        pad = words * 32 - self.input_dim
-        if pad:
-            x = torch.cat([x, torch.zeros(B, pad, dtype=torch.bool, device=eng.device)], dim=1)
-        # pack 32 bools per word, bit i of word i // 32 (little-endian bit order, as everywhere)
-        weights = (1 << torch.arange(32, device=eng.device, dtype=torch.int64))
-        packed = (x.view(B, words, 32).to(torch.int64) * weights).sum(dim=2)
-        packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32).contiguous()
+        packed = torch.empty(B, words, dtype=torch.int32, device=eng.device)
+        nat.check(nat.lib.bh_pack_inputs(eng.ref, x.data_ptr(), B, words, packed.data_ptr(), eng.stream), "bh_pack_inputs")
         out = torch.empty(B, eng.C_local, dtype=torch.int32, device=eng.device)
         if tensor_core and words * 32 >= 1 << 24:
             raise ValueError("process_batch(tensor_core=True) supports fewer than 2**24 input bits; "
                              "pass tensor_core=False")
-        name = "bh_sp_overlap_batched_tc" if tensor_core else "bh_sp_overlap_batched"
+        name = {True: "bh_sp_overlap_batched_tc", "tcgen05": "bh_sp_overlap_batched_tc5",
+                "mma": "bh_sp_overlap_batched_mma", False: "bh_sp_overlap_batched"}[tensor_core]
         nat.check(getattr(nat.lib, name)(eng.ref, packed.data_ptr(), B, out.data_ptr(), eng.stream), name)
+        if tensor_core in (True, "tcgen05") and int(eng.buf["sc"][nat.SC_T5_ERR].item()):
+            raise nat.NativeError("bithtm_b200: the tcgen05 batched overlap timed out on a pipeline barrier")
         out = out.to(torch.int64)
         return out if is_cuda else out.cpu().numpy()
 

@@ -258,6 +258,10 @@ int bh_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 int bh_sp_build_mask(const bh_ctx* ctx, void* stream);
 /* Pack a device bool[I] (one byte per bit) into input words. */
 int bh_pack_input(const bh_ctx* ctx, const uint8_t* bool_dev, uint32_t* words_dev, void* stream);
+/* Pack n_inputs device bool vectors [n_inputs][I] into rows of pitch_words (>= input_words) words, zero padded:
+ * the input operand of the batched overlaps below. */
+int bh_pack_inputs(const bh_ctx* ctx, const uint8_t* bool_dev, int n_inputs, int pitch_words, uint32_t* words_dev,
+                   void* stream);
 /* DenseProjection.process (projections.py:18-21) -> ctx->overlaps */
 int bh_sp_overlap(const bh_ctx* ctx, const uint32_t* input_words_dev, void* stream);
 /* DenseProjection.process for n_inputs input vectors against the ONE connected mask of this

@@ -639,10 +639,12 @@ def test_capacity_overflow_raises():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("I,C,B", [(1024, 2048, 300), (200, 300, 33), (4100, 512, 64), (97, 131, 1), (1024, 2048, 1024)])
+@pytest.mark.parametrize("I,C,B", [(1024, 2048, 300), (200, 300, 33), (4100, 512, 64), (97, 131, 1), (1024, 2048, 1024),
+                                   (1000, 700, 130), (4096, 515, 129), (2048, 4096, 64), (512, 128, 257)])
 def test_batched_overlap_equals_loop_of_process(I, C, B):
     """DenseProjection.process_batch == a loop of DenseProjection.process (projections.py:18-21)
-    == the dense float64 comparison of the oracle."""
+    == the dense float64 comparison of the oracle: the auto-dispatched tensor-core path (tcgen05 + TMEM + TMA
+    where the shape allows, ragged tiles included), both of its kernels forced, and the popcount kernel."""
     import bithtm_b200 as bithtm
 
     np.random.seed(9)
@@ -659,6 +661,12 @@ def test_batched_overlap_equals_loop_of_process(I, C, B):
         want = np.stack([((perm >= 0.0) & x).sum(axis=1) for x in xs])
     assert got.dtype == np.int64 and np.array_equal(got, want)
     assert got_popc.dtype == np.int64 and np.array_equal(got_popc, want)
+    assert np.array_equal(proj.process_batch(xs, tensor_core="mma"), want)
+    if ((I + 31) // 32) % 4 == 0:  # TMA needs 16-byte row pitches
+        assert np.array_equal(proj.process_batch(xs, tensor_core="tcgen05"), want)
+    else:
+        with pytest.raises(Exception):
+            proj.process_batch(xs, tensor_core="tcgen05")
     assert np.array_equal(proj.process(xs[min(5, B - 1)]), want[min(5, B - 1)])
 
 
