@@ -389,6 +389,11 @@ def ours(args):
         import phase_names
 
         phases = phase_names.read(eng)
+        if world > 1 and eng.ctx.xch_ll:
+            mine = {"phases": phases, "exchange_phases": phase_names.read_ll(eng)}
+            every = [None] * world
+            dist.all_gather_object(every, mine)
+            phases = {f"rank{r}": v for r, v in enumerate(every)}
     except Exception:
         pass
 
@@ -459,7 +464,7 @@ def ours(args):
                     "note": "HierarchicalTemporalMemory.process(host bool array) per step, np.random kept in lock-step; "
                             "every rank feeds the same input"},
             "gpu_launches": launches,
-            "roofline": roofline, "phases_us_rank0_last_step": phases, "state_check": check,
+            "roofline": roofline, "phases_us_last_step": phases, "state_check": check,
             "parity": parity,
             "cpu_baseline": extras.pop("cpu_baseline", None),
             "clocks": clocks,

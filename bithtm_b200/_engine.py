@@ -120,9 +120,19 @@ class Engine:
 
         step_words = max(4 * int(rand_capacity), 1 << 18)  # most words one step may draw (2x margin)
         typical = 2 * (k * (k + 1) + 2 * k * c)
+        huge = step_words > (1 << 29)
+        if huge:
+            # rand(L, W+1) is quadratic in k (BASELINE configs[4]: 4.4e8 doubles per step at k = 20972): such a
+            # network can only step over it (lazy draws, csrc/mt19937.cuh).  The ring must still span one
+            # step's draws (absolute stream index -> slot), with a small margin instead of 2x.
+            step_words = 2 * int(rand_capacity) + int(rand_capacity) // 8
+            if lazy_rng == "auto":
+                lazy_rng = "always"
+            if parallel_rng == "auto":
+                parallel_rng = False  # its jump table would have > 10^5 polynomials
         if parallel_rng == "auto":  # many-CTA stream production once a step draws enough words
             parallel_rng = typical >= 8 * _mtjump.CHUNK_WORDS
-        need = 2 * step_words
+        need = step_words + (1 << 24) if huge else 2 * step_words
         if parallel_rng:
             # history for the sparse chunk start (csrc/mt19937.cuh): 19937 << s words, where 623 << s
             # covers one step's production
@@ -138,6 +148,9 @@ class Engine:
                 f"{k} active columns draw about {typical // 2:,} random numbers per timestep (rand(L, W+1), "
                 "projections.py:120, is quadratic in the number of active columns); the device stream ring is limited "
                 "to 2^31 words. Pass rand_capacity= to bound the draws per step explicitly (see DESIGN.md, cfg5).")
+        if huge and fused not in ("grid", "shard", "auto"):
+            raise NotImplementedError("a network that draws this much per step needs the lazy draws of the cooperative "
+                                      'step kernels: fused="grid" or "shard"')
         # whole step as one kernel: on one thread-block cluster while the step is
         # latency-bound (mask <= 8 MiB), else on a cooperative grid with one CTA per SM.  The cluster
         # kernel has no many-CTA stream production phase: a network that draws enough words per step to
@@ -153,6 +166,8 @@ class Engine:
         # produced by table jumps -- the cooperative-grid kernels of networks that draw a lot per step
         if lazy_rng == "auto":
             lazy_rng = bool(parallel_rng) and fused in ("grid", "shard")
+        if huge and fused == "auto":
+            fused = "grid"
         if lazy_rng and fused in ("grid", "shard"):
             gran = int(skip_gran) if skip_gran else 4096
             while skip_gran is None and (step_words + step_words // 4) // gran > 4096:

@@ -112,6 +112,16 @@ __device__ __forceinline__ void ll_put(const bh_ctx& c, int* const* ll, int kind
   for (int p = 0; p < G; ++p) ll_store(ll[p] + off, v, seq);
 }
 
+// globaltimer stamps of the one-CTA phases (ctx.blk row 7 as u64, from index 40 / 52): tools read them
+#define LL_STAMP(base, i)                                                                    \
+  do {                                                                                       \
+    if (threadIdx.x == 0) {                                                                  \
+      unsigned long long t_;                                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
+      reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE)[(base) + (i)] = t_;   \
+    }                                                                                        \
+  } while (0)
+
 // lower bound in a shared-memory ascending int list
 __device__ __forceinline__ int smem_lower(const int* list, int n, int key) {
   int lo = 0, hi = n;
@@ -148,6 +158,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   unsigned long long* w64 = reinterpret_cast<unsigned long long*>(ws);
   const bool have_hist = ws3[TK3_READY] == seq;
 
+  LL_STAMP(40, 0);
   // a. histogram (+ the largest local key) -> everybody
   const unsigned long long lmax = w64[0];
 #pragma unroll 1
@@ -157,6 +168,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     else v = i == TK2_BINS ? (int)(unsigned)(lmax & 0xffffffffull) : (i == TK2_BINS + 1 ? (int)(unsigned)(lmax >> 32) : (have_hist ? 1 : 0));
     ll_put(c, ll, 0, par, i, v, seq);
   }
+  LL_STAMP(40, 1);
   int* mine = ll[me];
   __shared__ int s_meta[3 * BH_MAX_RANKS];
   if (t < 3 * G) s_meta[t] = ll_load(c, mine + ll_cell(c, 0, par, t / 3, TK2_BINS + t % 3), seq);
@@ -179,6 +191,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   if (t < 4 * BH_MAX_RANKS) s_cnt[t] = 0;
   if (t == 0) s_ncand = -1;
   __syncthreads();
+  LL_STAMP(40, 2);
   if (t == 0) {
     unsigned long long gm = 0ull;
     int all_hist = 1;
@@ -235,29 +248,44 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     }
   }
   __syncthreads();
-  // b. this rank's columns above the bin and its members of the bin, in ascending column order -> everybody
+  LL_STAMP(40, 3);
+  // b. this rank's columns above the bin and its members of the bin, in ascending column order -> everybody.
+  // Thread t owns the contiguous keys [t * per, (t + 1) * per): one block scan per list orders everything.
   const Tk3Binning binning = tk3_binning(ws3);
   {
-    int base_a = 0, base_m = 0;
+    const int per = (n + NT - 1) / NT;
+    const int j0 = t * per, j1 = j0 + per < n ? j0 + per : n;
+    int na = 0, nm = 0;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+      const int kb = tk3_bin(binning, keys[j]);
+      na += kb > bin ? 1 : 0;
+      nm += kb == bin ? 1 : 0;
+    }
+    int tot_a, tot_m;
+    int pa = block_excl_scan(na, s_scan, tot_a);
+    int pm = block_excl_scan(nm, s_scan, tot_m);
+    if (na | nm) {
 #pragma unroll 1
-    for (int tile = 0; tile < n; tile += NT) {
-      const int j = tile + t;
-      const unsigned long long key = j < n ? keys[j] : 0ull;
-      const int kb = j < n ? tk3_bin(binning, key) : 0;
-      int tot_a, tot_m;
-      const int pa = base_a + block_excl_scan(kb > bin ? 1 : 0, s_scan, tot_a);
-      const int pm = base_m + block_excl_scan((j < n && kb == bin) ? 1 : 0, s_scan, tot_m);
-      if (kb > bin && pa < k_loc) ll_put(c, ll, 1, par, pa, c.col_lo + j, seq);
-      if (j < n && kb == bin && pm < LL_MEMBERS) {
-        const long long w = k_loc + 3LL * pm;
-        ll_put(c, ll, 1, par, w, (int)(unsigned)(key & 0xffffffffull), seq);
-        ll_put(c, ll, 1, par, w + 1, (int)(unsigned)(key >> 32), seq);
-        ll_put(c, ll, 1, par, w + 2, c.col_lo + j, seq);
+      for (int j = j0; j < j1; ++j) {
+        const unsigned long long key = keys[j];
+        const int kb = tk3_bin(binning, key);
+        if (kb > bin) {
+          if (pa < k_loc) ll_put(c, ll, 1, par, pa, c.col_lo + j, seq);
+          ++pa;
+        } else if (kb == bin) {
+          if (pm < LL_MEMBERS) {
+            const long long w = k_loc + 3LL * pm;
+            ll_put(c, ll, 1, par, w, (int)(unsigned)(key & 0xffffffffull), seq);
+            ll_put(c, ll, 1, par, w + 1, (int)(unsigned)(key >> 32), seq);
+            ll_put(c, ll, 1, par, w + 2, c.col_lo + j, seq);
+          }
+          ++pm;
+        }
       }
-      base_a += tot_a;
-      base_m += tot_m;
     }
   }
+  LL_STAMP(40, 4);
   // gather: offsets of every rank's part
   if (t == 0) {
     int oa = 0, om = 0;
@@ -289,6 +317,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     }
   }
   __syncthreads();
+  LL_STAMP(40, 5);
   // rank the members: larger key first, ties -> lower column; the first `rem` are selected
   if (t < n_mem) {
     const unsigned long long mk = s_mkey[t];
@@ -353,6 +382,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     tk3_set_binning(ws3, s_kth_key, s_gmax > s_kth_key ? s_gmax : s_kth_key);
   }
   (void)n_above;
+  LL_STAMP(40, 6);
   return true;
 }
 
@@ -393,6 +423,7 @@ __device__ __noinline__ void ph_shard_segs_ll(const bh_ctx& c, int* const* ll, u
     trip = rec + 8;
     rids = rec + 8 + 3 * c.xm_cap;
   }
+  LL_STAMP(52, 0);
   // header
   if (t < 4) ll_put(c, ll, 2, par, t, t == 0 ? n : (t == 1 ? nr : (t == 2 ? nr_total : status)), seq);
   if (sorted) {  // packed record: ids / potentials / connected counts as three arrays
@@ -432,6 +463,7 @@ __device__ __noinline__ void ph_shard_segs_ll(const bh_ctx& c, int* const* ll, u
     }
     __syncthreads();
   }
+  LL_STAMP(52, 1);
   // gather the headers
   int* mine = ll[me];
   if (t < 4 * G) s_n[(t & 3) * BH_MAX_RANKS + (t >> 2)] = ll_load(c, mine + ll_cell(c, 2, par, t >> 2, t & 3), seq);
@@ -443,6 +475,7 @@ __device__ __noinline__ void ph_shard_segs_ll(const bh_ctx& c, int* const* ll, u
     RT += s_n[2 * BH_MAX_RANKS + g];
     st |= s_n[3 * BH_MAX_RANKS + g];
   }
+  LL_STAMP(52, 2);
   if (M > LL_TOTAL_MATCH_MAX) st |= BH_ST_XCH_OVERFLOW;
   // ids of all ranks into shared memory (rank by rank, each ascending), then merge by counting
   int off = 0;
@@ -507,6 +540,7 @@ __device__ __noinline__ void ph_shard_segs_ll(const bh_ctx& c, int* const* ll, u
     }
     off += ng;
   }
+  LL_STAMP(52, 3);
   if (t == 0) {
     c.sc[BH_SC_X_MATCH] = M;
     c.sc[BH_SC_X_RECYC_AVAIL] = R;
