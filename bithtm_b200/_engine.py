@@ -105,7 +105,7 @@ class Engine:
         if fused == "shard":
             # exchanges as {word, sequence} cells (csrc/shard_ll.cuh) while the one-CTA selection / merge fit
             # in shared memory; very wide networks use the copy + flag protocol
-            ctx.xch_ll = 1 if 4 * (6400 + 2 * k) <= 150 * 1024 else 0
+            ctx.xch_ll = 1 if 4 * (6400 + 2 * k) <= 150 * 1024 and Ccol // self.shard_world <= 131072 else 0
             if ctx.xch_ll and not exchange_match_capacity:
                 ctx.xm_cap = min(ctx.xm_cap, 4096)  # what one CTA sorts per rank
         ctx.col_local = Ccol // self.shard_world
@@ -177,7 +177,8 @@ class Engine:
             ctx.skip_min = int(skip_min) if skip_min else max(2 * gran, 1 << 16)
             ctx.job_cap = 64 + step_words // _mtjump.WINDOW_WORDS + 2
             ctx.lazy_policy = 1 if lazy_rng == "always" else 0
-            ctx.tail_chunks = int(tail_chunks or 0)
+            # a shard's phases are short: more, shorter tail chunks (one jump each) keep their generation under the scan
+            ctx.tail_chunks = int(tail_chunks or (8 if fused == "shard" and self.shard_world > 2 else 0))
         ctx.fused_mode = {"off": 0, "cluster": 1, "grid": 2, "shard": 3}[fused]
         if fused_ctas is None:
             fused_ctas = 16 if fused == "cluster" else self.sm_count

@@ -217,16 +217,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     if (team) {
       const int t0 = nb - team;
       if (b >= t0) {
+        // winner bits on the whole team | the drawing CTA forms the ordered winner lists while the others flag the
+        // learning segments | it plans draw #2 while they form the learning lists (team barriers in between)
+        unsigned int* bar2 = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT);
         ph_select_a(c, b - t0, team);
-        grid_barrier(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT), (unsigned)team);
-        if (rng) {
-          ph_select_b(c, 0, 1, true, team);
-          __syncthreads();
-          ph_learn_select_a(c, learning, 0, 1);
-          __syncthreads();
-          ph_draw(c, 2, learning, 1, true);
-          ph_learn_select_b(c, learning, 0, 1);
-        }
+        grid_barrier(bar2, (unsigned)team);
+        if (rng) ph_select_b(c, 0, 1, true, team);
+        else ph_learn_select_a(c, learning, b - t0, team - 1);
+        grid_barrier(bar2, (unsigned)team);
+        if (rng) ph_draw(c, 2, learning, team - 1, true);
+        else ph_learn_select_b(c, learning, b - t0, team - 1);
       } else {
         if (learning) ph_sp_learn<false>(c, input, b, t0);
         ph_duty(c, b, t0);
@@ -268,11 +268,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       if (learning) ph_learn_apply(c, s_dyn, b, nb);
       BH_SYNC();
     }
-    ph_post(c, b, nb);
-    BH_SYNC();
-    BH_STAMP();  // 9: learn + post
+    BH_STAMP();  // 9: learn
+    // (the activation words are double-buffered: what ph_post retires is not read by the scan, so it runs at the
+    // head of the scan phase instead of in a phase of its own)
     const int ns = lazy ? nb - rng_tail_ctas(c, nb) : nw;  // lazy step: the last CTAs generate the tail instead
     if (lazy) ph_rng_lazy_tail(c, s_dyn, b, nb);
+    ph_post(c, b, nb);
     if (b < ns) ph_activate_a(c, b, ns, c.xch_ll ? xch_append_rec(c) : nullptr);
     BH_SYNC();
     BH_STAMP();  // 10: segment scan

@@ -28,6 +28,7 @@
 #define LL_MEMBERS TOPK_THREADS      // most keys of the threshold bin over all ranks
 #define LL_LOCAL_MATCH_MAX 4096      // most matching segments one rank sorts in shared memory
 #define LL_TOTAL_MATCH_MAX 16384     // most matching segments over all ranks merged in shared memory
+#define LL_MASK_WORDS 4               // the selection classifies at most 32 * 4 local keys per thread (131072 columns per rank)
 #define LL_TIMEOUT_CYCLES 6000000000LL
 
 __host__ __device__ __forceinline__ int ll_k_loc(const bh_ctx& c) {
@@ -250,38 +251,56 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   __syncthreads();
   LL_STAMP(40, 3);
   // b. this rank's columns above the bin and its members of the bin, in ascending column order -> everybody.
-  // Thread t owns the contiguous keys [t * per, (t + 1) * per): one block scan per list orders everything.
+  // Thread t owns the contiguous keys [t * per, (t + 1) * per) and remembers their classes as bit masks: one
+  // block scan per list orders everything, and only the members' keys are read a second time.
   const Tk3Binning binning = tk3_binning(ws3);
   {
-    const int per = (n + NT - 1) / NT;
+    const int per = (n + NT - 1) / NT;  // <= 32 * LL_MASK_WORDS (checked by the caller)
     const int j0 = t * per, j1 = j0 + per < n ? j0 + per : n;
+    uint32_t ma[LL_MASK_WORDS], mm[LL_MASK_WORDS];
     int na = 0, nm = 0;
-#pragma unroll 4
-    for (int j = j0; j < j1; ++j) {
-      const int kb = tk3_bin(binning, keys[j]);
-      na += kb > bin ? 1 : 0;
-      nm += kb == bin ? 1 : 0;
+#pragma unroll
+    for (int w = 0; w < LL_MASK_WORDS; ++w) {
+      ma[w] = 0u;
+      mm[w] = 0u;
+      const int jb = j0 + 32 * w;
+      if (jb < j1) {
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          if (jb + i < j1) {
+            const int kb = tk3_bin(binning, keys[jb + i]);
+            ma[w] |= (kb > bin ? 1u : 0u) << i;
+            mm[w] |= (kb == bin ? 1u : 0u) << i;
+          }
+        }
+      }
+      na += __popc(ma[w]);
+      nm += __popc(mm[w]);
     }
     int tot_a, tot_m;
     int pa = block_excl_scan(na, s_scan, tot_a);
     int pm = block_excl_scan(nm, s_scan, tot_m);
-    if (na | nm) {
-#pragma unroll 1
-      for (int j = j0; j < j1; ++j) {
-        const unsigned long long key = keys[j];
-        const int kb = tk3_bin(binning, key);
-        if (kb > bin) {
-          if (pa < k_loc) ll_put(c, ll, 1, par, pa, c.col_lo + j, seq);
-          ++pa;
-        } else if (kb == bin) {
-          if (pm < LL_MEMBERS) {
-            const long long w = k_loc + 3LL * pm;
-            ll_put(c, ll, 1, par, w, (int)(unsigned)(key & 0xffffffffull), seq);
-            ll_put(c, ll, 1, par, w + 1, (int)(unsigned)(key >> 32), seq);
-            ll_put(c, ll, 1, par, w + 2, c.col_lo + j, seq);
-          }
-          ++pm;
+#pragma unroll
+    for (int w = 0; w < LL_MASK_WORDS; ++w) {
+      uint32_t a = ma[w], m = mm[w];
+      while (a) {
+        const int i = __ffs(a) - 1;
+        a &= a - 1;
+        if (pa < k_loc) ll_put(c, ll, 1, par, pa, c.col_lo + j0 + 32 * w + i, seq);
+        ++pa;
+      }
+      while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        const int j = j0 + 32 * w + i;
+        if (pm < LL_MEMBERS) {
+          const unsigned long long key = keys[j];
+          const long long wd = k_loc + 3LL * pm;
+          ll_put(c, ll, 1, par, wd, (int)(unsigned)(key & 0xffffffffull), seq);
+          ll_put(c, ll, 1, par, wd + 1, (int)(unsigned)(key >> 32), seq);
+          ll_put(c, ll, 1, par, wd + 2, c.col_lo + j, seq);
         }
+        ++pm;
       }
     }
   }
