@@ -105,7 +105,7 @@ class Engine:
         if fused == "shard":
             # exchanges as {word, sequence} cells (csrc/shard_ll.cuh) while the one-CTA selection / merge fit
             # in shared memory; very wide networks use the copy + flag protocol
-            ctx.xch_ll = 1 if 4 * (6400 + 2 * k) <= 150 * 1024 and Ccol // self.shard_world <= 131072 else 0
+            ctx.xch_ll = 1 if 4 * (6400 + k + Ccol // self.shard_world // 16) <= 150 * 1024 else 0
             if ctx.xch_ll and not exchange_match_capacity:
                 ctx.xm_cap = min(ctx.xm_cap, 4096)  # what one CTA sorts per rank
         ctx.col_local = Ccol // self.shard_world

@@ -155,7 +155,6 @@ static int check_ctx(const bh_ctx* x) {
   if (x->col_local < 1 || x->col_lo < 0 || x->col_lo + x->col_local > x->column_dim) return BH_E_BADARG;
   if (x->fused_mode < 0 || x->fused_mode > 3) return BH_E_BADARG;
   if (x->col_local != x->column_dim && x->fused_mode && x->fused_mode != 3) return BH_E_UNSUPPORTED;
-  if (x->fused_mode == 3 && x->xch_ll && x->col_local > 32 * LL_MASK_WORDS * FUSED_THREADS) return BH_E_UNSUPPORTED;
   if (x->fused_mode == 3) {  // one kernel per shard, exchanges in-kernel: SP by column and TM by segment, same ranks
     const int W = x->seg_world > 1 ? x->seg_world : 1;
     if (W > BH_MAX_RANKS || x->xm_cap < 1 || x->xr_cap < 1) return BH_E_BADARG;

@@ -28,7 +28,6 @@
 #define LL_MEMBERS TOPK_THREADS      // most keys of the threshold bin over all ranks
 #define LL_LOCAL_MATCH_MAX 4096      // most matching segments one rank sorts in shared memory
 #define LL_TOTAL_MATCH_MAX 16384     // most matching segments over all ranks merged in shared memory
-#define LL_MASK_WORDS 4               // the selection classifies at most 32 * 4 local keys per thread (131072 columns per rank)
 #define LL_TIMEOUT_CYCLES 6000000000LL
 
 __host__ __device__ __forceinline__ int ll_k_loc(const bh_ctx& c) {
@@ -38,7 +37,7 @@ __host__ __device__ __forceinline__ long long ll_sel_words(const bh_ctx& c) { re
 __host__ __device__ __forceinline__ long long ll_seg_words(const bh_ctx& c) { return 8 + 3LL * c.xm_cap + c.xr_cap; }
 // dynamic shared memory (bytes) the two one-CTA phases below need
 __host__ __device__ __forceinline__ long long ll_smem_bytes(const bh_ctx& c) {
-  const long long sel = 4LL * (TK2_BINS + 2 * LL_MEMBERS + 2 * LL_MEMBERS + 8 + c.active_columns + ll_k_loc(c) + 64);
+  const long long sel = 4LL * (TK2_BINS + 2 * LL_MEMBERS + 2 * LL_MEMBERS + 8 + c.active_columns + 2 * ((c.col_local + 31) / 32) + 64);
   const long long seg = 4LL * (LL_TOTAL_MATCH_MAX + LL_LOCAL_MATCH_MAX);
   return sel > seg ? sel : seg;
 }
@@ -160,6 +159,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   const bool have_hist = ws3[TK3_READY] == seq;
 
   LL_STAMP(40, 0);
+  retire_prev_flags(c);  // (independent of the selection; the new flags are set at the end)
   // a. histogram (+ the largest local key) -> everybody
   const unsigned long long lmax = w64[0];
 #pragma unroll 1
@@ -251,48 +251,46 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   __syncthreads();
   LL_STAMP(40, 3);
   // b. this rank's columns above the bin and its members of the bin, in ascending column order -> everybody.
-  // Thread t owns the contiguous keys [t * per, (t + 1) * per) and remembers their classes as bit masks: one
-  // block scan per list orders everything, and only the members' keys are read a second time.
+  // Pass 1 reads the keys coalesced (a warp covers 32 consecutive columns: its ballots ARE the class masks of
+  // that group); pass 2: thread t owns consecutive mask words, one block scan per list orders everything, and
+  // only the members' keys are read a second time.
   const Tk3Binning binning = tk3_binning(ws3);
   {
-    const int per = (n + NT - 1) / NT;  // <= 32 * LL_MASK_WORDS (checked by the caller)
-    const int j0 = t * per, j1 = j0 + per < n ? j0 + per : n;
-    uint32_t ma[LL_MASK_WORDS], mm[LL_MASK_WORDS];
-    int na = 0, nm = 0;
-#pragma unroll
-    for (int w = 0; w < LL_MASK_WORDS; ++w) {
-      ma[w] = 0u;
-      mm[w] = 0u;
-      const int jb = j0 + 32 * w;
-      if (jb < j1) {
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          if (jb + i < j1) {
-            const int kb = tk3_bin(binning, keys[jb + i]);
-            ma[w] |= (kb > bin ? 1u : 0u) << i;
-            mm[w] |= (kb == bin ? 1u : 0u) << i;
-          }
-        }
+    uint32_t* s_ma = reinterpret_cast<uint32_t*>(s_above + k);  // [n / 32] columns above the bin
+    const int n_words = (n + 31) >> 5;
+    uint32_t* s_mm = s_ma + n_words;                             // [n / 32] members of the bin
+#pragma unroll 4
+    for (int j = t; j < ((n + 31) & ~31); j += NT) {
+      const int kb = j < n ? tk3_bin(binning, keys[j]) : 0;
+      const uint32_t a = __ballot_sync(BH_FULL, kb > bin), m = __ballot_sync(BH_FULL, j < n && kb == bin);
+      if (lane == 0) {
+        s_ma[j >> 5] = a;
+        s_mm[j >> 5] = m;
       }
-      na += __popc(ma[w]);
-      nm += __popc(mm[w]);
+    }
+    __syncthreads();
+    const int wpt = (n_words + NT - 1) / NT;
+    const int w0 = t * wpt, w1 = w0 + wpt < n_words ? w0 + wpt : n_words;
+    int na = 0, nm = 0;
+    for (int w = w0; w < w1; ++w) {
+      na += __popc(s_ma[w]);
+      nm += __popc(s_mm[w]);
     }
     int tot_a, tot_m;
     int pa = block_excl_scan(na, s_scan, tot_a);
     int pm = block_excl_scan(nm, s_scan, tot_m);
-#pragma unroll
-    for (int w = 0; w < LL_MASK_WORDS; ++w) {
-      uint32_t a = ma[w], m = mm[w];
+    for (int w = w0; w < w1; ++w) {
+      uint32_t a = s_ma[w], m = s_mm[w];
       while (a) {
         const int i = __ffs(a) - 1;
         a &= a - 1;
-        if (pa < k_loc) ll_put(c, ll, 1, par, pa, c.col_lo + j0 + 32 * w + i, seq);
+        if (pa < k_loc) ll_put(c, ll, 1, par, pa, c.col_lo + 32 * w + i, seq);
         ++pa;
       }
       while (m) {
         const int i = __ffs(m) - 1;
         m &= m - 1;
-        const int j = j0 + 32 * w + i;
+        const int j = 32 * w + i;
         if (pm < LL_MEMBERS) {
           const unsigned long long key = keys[j];
           const long long wd = k_loc + 3LL * pm;
@@ -360,7 +358,6 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     if (t == 0) s_msel[n_mem] = tot;
   }
   __syncthreads();
-  retire_prev_flags(c);
   int* out = c.active_cols + par * k;
   // rank offsets in the final list: everything of the ranks before
   // (selected members of rank g = prefix at the end of its part - prefix at its start)

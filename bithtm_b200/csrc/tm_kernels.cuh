@@ -698,20 +698,28 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb, int* append = null
   const uint32_t* col_act = c.col_act + (long long)(c.sc[BH_SC_STEP] & 1) * c.column_dim;
   const Range rg = block_range(seg_local_count(c, S), b, nb);  // local rows (== segment ids when not sharded)
   int nm = 0, nrec = 0;
+  // The synapse counts of a batch are fetched one iteration AHEAD (software pipeline), so the slot loads can be
+  // predicated on them -- only live slots travel (rows hold ~32 of 64..128 slots) -- without a third dependent
+  // round trip per batch: counts(next) and slots(current) are in flight together.
+  int s_first = rg.begin + warp * ACT_BATCH;
+  int next_n = (lane < ACT_BATCH && s_first + lane < rg.end) ? c.seg_count[seg_gid(c, s_first + lane)] : 0;
 #pragma unroll 1
-  for (int s0 = rg.begin + warp * ACT_BATCH; s0 < rg.end; s0 += warps * ACT_BATCH) {
-    // the counts of the batch and slots [0, 64) of every row are fetched TOGETHER (free slots hold
-    // stale but valid cell ids and are masked afterwards): two dependent round trips per batch
-    // instead of three
-    const int my_n = (lane < ACT_BATCH && s0 + lane < rg.end) ? c.seg_count[seg_gid(c, s0 + lane)] : 0;
+  for (int s0 = s_first; s0 < rg.end; s0 += warps * ACT_BATCH) {
+    const int my_n = next_n;
+    {
+      const int s1 = s0 + warps * ACT_BATCH;
+      next_n = (lane < ACT_BATCH && s1 + lane < rg.end) ? c.seg_count[seg_gid(c, s1 + lane)] : 0;
+    }
     int n[ACT_BATCH], cell[ACT_BATCH][2];
     float perm[ACT_BATCH][2];
+#pragma unroll
+    for (int j = 0; j < ACT_BATCH; ++j) n[j] = __shfl_sync(BH_FULL, my_n, j);
 #pragma unroll
     for (int j = 0; j < ACT_BATCH; ++j) {
       const long long base = (long long)(s0 + j) * E + lane;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const bool v = s0 + j < rg.end && lane + 32 * h < E;
+        const bool v = s0 + j < rg.end && lane + 32 * h < n[j];
         cell[j][h] = v ? c.syn_cell[base + 32 * h] : 0;
         perm[j][h] = v ? c.syn_perm[base + 32 * h] : 0.0f;
       }
@@ -723,8 +731,6 @@ __device__ void ph_activate_a(const bh_ctx& c, int b, int nb, int* append = null
         if (j < c.xr_cap) append[8 + 3 * c.xm_cap + j] = seg_gid(c, s0 + lane);
       }
     }
-#pragma unroll
-    for (int j = 0; j < ACT_BATCH; ++j) n[j] = __shfl_sync(BH_FULL, my_n, j);
     uint32_t word[ACT_BATCH][2];
 #pragma unroll
     for (int j = 0; j < ACT_BATCH; ++j)
