@@ -855,7 +855,17 @@ static void pack_host(const bh_ctx* x, const uint8_t* input_bool_host) {
     int lim = x->input_dim - w * 32;
     if (lim > 32) lim = 32;
     const uint8_t* p = input_bool_host + w * 32;
-    for (int b = 0; b < lim; ++b) bits |= (uint32_t)(p[b] != 0) << b;
+    if (lim == 32) {
+      // 8 bool bytes (0 / 1, np.bool_) -> 8 bits with one multiply: byte i lands on bit 56 + i
+      for (int g = 0; g < 4; ++g) {
+        uint64_t v;
+        memcpy(&v, p + 8 * g, 8);
+        v = (v | (v >> 1) | (v >> 2) | (v >> 3) | (v >> 4) | (v >> 5) | (v >> 6) | (v >> 7)) & 0x0101010101010101ULL;  // != 0
+        bits |= (uint32_t)((v * 0x0102040810204080ULL) >> 56) << (8 * g);
+      }
+    } else {
+      for (int b = 0; b < lim; ++b) bits |= (uint32_t)(p[b] != 0) << b;
+    }
     x->input_pinned[w] = bits;
   }
 }

@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     // P2..P7 as in fused.cuh; learning and the segment scan touch only what this rank stores
     // a TEAM of the last CTAs runs the replicated temporal-memory bookkeeping chain while the others learn this
     // shard's spatial-pooler rows (fused.cuh, P2)
-    const int team = (nb >= 32 && c.sc[BH_SC_M] <= 32768) ? (nb >= 64 ? 16 : 8) : 0;
+    // (the more shards, the shorter the SP learning pass of a rank and the larger the team may be: at 8 shards
+    // the bookkeeping chain, not the learning pass, bounds this phase)
+    const int team = (nb >= 32 && c.sc[BH_SC_M] <= 32768) ? (nb >= 128 ? (G >= 8 ? 64 : (G >= 4 ? 32 : 16)) : (nb >= 64 ? 16 : 8)) : 0;
     if (rebin && b == (team ? nb - team : 0)) tk3_rebin_sharded(c, G > 1 ? G * k_loc : k_loc);
     if (team) {
       const int t0 = nb - team;
@@ -259,8 +261,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     }
     BH_STAMP();  // 8: stream chunks
     if (lazy) {
-      if (learning) ph_learn_apply(c, s_dyn, b, nb, 1);
-      ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b, nb);
+      // stage 1 of the learning pass (a warp per row of this shard: few CTAs' worth) next to the tail jumps
+      const int n1 = nb >= 96 ? 48 : 0;  // CTAs of stage 1 (0: every CTA does both)
+      if (n1) {
+        if (b < n1) {
+          if (learning) ph_learn_apply(c, s_dyn, b, n1, 1);
+        } else {
+          ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b - n1, nb - n1);
+        }
+      } else {
+        if (learning) ph_learn_apply(c, s_dyn, b, nb, 1);
+        ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b, nb);
+      }
       BH_SYNC();
       ph_rng_lazy_rows(c, s_dyn, b, nb, [&]() { BH_SYNC(); },
                        [&](bool produce_rows) { ph_learn_grow(c, s_dyn, b, nb, produce_rows); });

@@ -319,19 +319,22 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     n_above += s_cnt[g];
     n_mem += s_cnt[BH_MAX_RANKS + g];
   }
+  // (flat over all ranks' entries: the loads of different ranks are in flight together)
 #pragma unroll 1
-  for (int g = 0; g < G; ++g) {
-    const int a = s_cnt[g], m = s_cnt[BH_MAX_RANKS + g], oa = s_cnt[2 * BH_MAX_RANKS + g], om = s_cnt[3 * BH_MAX_RANKS + g];
+  for (int e = t; e < n_above; e += NT) {
+    int g = 0;
+    while (g + 1 < G && e >= s_cnt[2 * BH_MAX_RANKS + g + 1]) ++g;
+    s_above[e] = ll_load(c, mine + ll_cell(c, 1, par, g, e - s_cnt[2 * BH_MAX_RANKS + g]), seq);
+  }
 #pragma unroll 1
-    for (int i = t; i < a; i += NT) s_above[oa + i] = ll_load(c, mine + ll_cell(c, 1, par, g, i), seq);
-#pragma unroll 1
-    for (int i = t; i < m; i += NT) {
-      const long long w = k_loc + 3LL * i;
-      const unsigned lo = (unsigned)ll_load(c, mine + ll_cell(c, 1, par, g, w), seq);
-      const unsigned hi = (unsigned)ll_load(c, mine + ll_cell(c, 1, par, g, w + 1), seq);
-      s_mkey[om + i] = ((unsigned long long)hi << 32) | lo;
-      s_mcol[om + i] = ll_load(c, mine + ll_cell(c, 1, par, g, w + 2), seq);
-    }
+  for (int e = t; e < n_mem; e += NT) {
+    int g = 0;
+    while (g + 1 < G && e >= s_cnt[3 * BH_MAX_RANKS + g + 1]) ++g;
+    const long long w = k_loc + 3LL * (e - s_cnt[3 * BH_MAX_RANKS + g]);
+    const unsigned lo = (unsigned)ll_load(c, mine + ll_cell(c, 1, par, g, w), seq);
+    const unsigned hi = (unsigned)ll_load(c, mine + ll_cell(c, 1, par, g, w + 1), seq);
+    s_mkey[e] = ((unsigned long long)hi << 32) | lo;
+    s_mcol[e] = ll_load(c, mine + ll_cell(c, 1, par, g, w + 2), seq);
   }
   __syncthreads();
   LL_STAMP(40, 5);
@@ -493,68 +496,70 @@ __device__ __noinline__ void ph_shard_segs_ll(const bh_ctx& c, int* const* ll, u
   }
   LL_STAMP(52, 2);
   if (M > LL_TOTAL_MATCH_MAX) st |= BH_ST_XCH_OVERFLOW;
-  // ids of all ranks into shared memory (rank by rank, each ascending), then merge by counting
-  int off = 0;
-#pragma unroll 1
-  for (int g = 0; g < G && off < LL_TOTAL_MATCH_MAX; ++g) {
-    const int ng = s_n[g] < LL_TOTAL_MATCH_MAX - off ? s_n[g] : LL_TOTAL_MATCH_MAX - off;
-#pragma unroll 1
-    for (int i = t; i < ng; i += NT) s_all[off + i] = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * i), seq);
-    off += ng;
+  // ids of all ranks into shared memory (rank by rank, each ascending), then merge by counting -- flat over all
+  // entries, so that the loads of different ranks are in flight together
+  __shared__ int s_off[2 * BH_MAX_RANKS + 2];
+  if (t == 0) {
+    int o = 0, o2 = 0;
+    for (int g = 0; g < G; ++g) {
+      s_off[g] = o;
+      s_off[BH_MAX_RANKS + 1 + g] = o2;
+      o += s_n[g];
+      o2 += s_n[BH_MAX_RANKS + g];
+    }
+    s_off[G] = o;
+    s_off[BH_MAX_RANKS + 1 + G] = o2;
   }
   __syncthreads();
-  off = 0;
+  const int Mc = M < LL_TOTAL_MATCH_MAX ? M : LL_TOTAL_MATCH_MAX;
 #pragma unroll 1
-  for (int g = 0; g < G && off < LL_TOTAL_MATCH_MAX; ++g) {
-    const int ng = s_n[g] < LL_TOTAL_MATCH_MAX - off ? s_n[g] : LL_TOTAL_MATCH_MAX - off;
+  for (int e = t; e < Mc; e += NT) {
+    int g = 0;
+    while (g + 1 < G && e >= s_off[g + 1]) ++g;
+    s_all[e] = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * (e - s_off[g])), seq);
+  }
+  __syncthreads();
 #pragma unroll 1
-    for (int i = t; i < ng; i += NT) {
-      const int id = s_all[off + i];
-      int pos = i, o2 = 0;
-      for (int o = 0; o < G; ++o) {
-        const int no = s_n[o];
-        if (o != g && o2 + no <= LL_TOTAL_MATCH_MAX) pos += smem_lower(s_all + o2, no, id);
-        o2 += no;
-      }
-      const int pot = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * i + 1), seq);
-      const int conn = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * i + 2), seq);
-      c.seg_pot[id] = pot;  // every rank knows the potentials of the matching segments
-      c.seg_conn[id] = conn;
-      if (pos < c.match_capacity) {
-        c.m_seg[pos] = id;
-        c.m_conn[pos] = conn;
-      }
+  for (int e = t; e < Mc; e += NT) {
+    int g = 0;
+    while (g + 1 < G && e >= s_off[g + 1]) ++g;
+    const int i = e - s_off[g], id = s_all[e];
+    const int pot = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * i + 1), seq);
+    const int conn = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * i + 2), seq);
+    int pos = i;
+    for (int o = 0; o < G; ++o) {
+      const int lo = s_off[o], hi = s_off[o + 1] < Mc ? s_off[o + 1] : Mc;
+      if (o != g && hi > lo) pos += smem_lower(s_all + lo, hi - lo, id);
     }
-    off += ng;
+    c.seg_pot[id] = pot;  // every rank knows the potentials of the matching segments
+    c.seg_conn[id] = conn;
+    if (pos < c.match_capacity) {
+      c.m_seg[pos] = id;
+      c.m_conn[pos] = conn;
+    }
   }
   __syncthreads();
   // recyclable ids: the same merge (few; usually none)
-  off = 0;
+  const int* r_off = s_off + BH_MAX_RANKS + 1;
+  const int Rc = R < LL_TOTAL_MATCH_MAX ? R : LL_TOTAL_MATCH_MAX;
 #pragma unroll 1
-  for (int g = 0; g < G; ++g) {
-    const int ng = s_n[BH_MAX_RANKS + g];
-#pragma unroll 1
-    for (int i = t; i < ng && off + i < LL_TOTAL_MATCH_MAX; i += NT)
-      s_all[off + i] = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * c.xm_cap + i), seq);
-    off += ng;
+  for (int e = t; e < Rc; e += NT) {
+    int g = 0;
+    while (g + 1 < G && e >= r_off[g + 1]) ++g;
+    s_all[e] = ll_load(c, mine + ll_cell(c, 2, par, g, 8 + 3LL * c.xm_cap + (e - r_off[g])), seq);
   }
   __syncthreads();
-  off = 0;
 #pragma unroll 1
-  for (int g = 0; g < G; ++g) {
-    const int ng = s_n[BH_MAX_RANKS + g];
-#pragma unroll 1
-    for (int i = t; i < ng && off + i < LL_TOTAL_MATCH_MAX; i += NT) {
-      const int id = s_all[off + i];
-      int pos = i, o2 = 0;
-      for (int o = 0; o < G; ++o) {
-        const int no = s_n[BH_MAX_RANKS + o];
-        if (o != g && o2 + no <= LL_TOTAL_MATCH_MAX) pos += smem_lower(s_all + o2, no, id);
-        o2 += no;
-      }
-      c.recyc_list[pos] = id;
+  for (int e = t; e < Rc; e += NT) {
+    int g = 0;
+    while (g + 1 < G && e >= r_off[g + 1]) ++g;
+    const int id = s_all[e];
+    int pos = e - r_off[g];
+    for (int o = 0; o < G; ++o) {
+      const int lo = r_off[o], hi = r_off[o + 1] < Rc ? r_off[o + 1] : Rc;
+      if (o != g && hi > lo) pos += smem_lower(s_all + lo, hi - lo, id);
     }
-    off += ng;
+    c.recyc_list[pos] = id;
   }
   LL_STAMP(52, 3);
   if (t == 0) {
