@@ -309,14 +309,15 @@ class Engine:
             self.ctx.xpeer[r] = int(p)
         self._xch_keepalive = keepalive
 
-    def tm_shard_pre(self, learning=True):
-        nat.check(nat.lib.bh_tm_shard_pre(self.ref, int(bool(learning)), self.xch_send.data_ptr(), self.stream),
+    def tm_shard_pre(self, flags=1):
+        nat.check(nat.lib.bh_tm_shard_pre(self.ref, int(flags), self.xch_send.data_ptr(), self.stream),
                   "bh_tm_shard_pre")
         return self.xch_send
 
-    def tm_shard_post(self, gathered):
+    def tm_shard_post(self, gathered, want_jitter=True):
         assert gathered.numel() == self.xch_recv.numel() and gathered.dtype == self.xch_recv.dtype
-        nat.check(nat.lib.bh_tm_shard_post(self.ref, gathered.data_ptr(), self.stream), "bh_tm_shard_post")
+        nat.check(nat.lib.bh_tm_shard_post_ex(self.ref, gathered.data_ptr(), int(bool(want_jitter)), self.stream),
+                  "bh_tm_shard_post_ex")
         self.epoch += 1
 
     def scalars(self) -> np.ndarray:

@@ -135,6 +135,7 @@ _SIGNATURES = {
     "bh_xch_region_ints": (C.c_size_t, [_CTXP]),
     "bh_tm_shard_pre": (C.c_int, [_CTXP, C.c_int, _P, _P]),
     "bh_tm_shard_post": (C.c_int, [_CTXP, _P, _P]),
+    "bh_tm_shard_post_ex": (C.c_int, [_CTXP, _P, C.c_int, _P]),
     "bh_advance_step": (C.c_int, [_CTXP, _P]),
     "bh_tm_select": (C.c_int, [_CTXP, _P]),
     "bh_tm_learn": (C.c_int, [_CTXP, C.c_int, _P]),

@@ -698,15 +698,17 @@ extern "C" int bh_tm_shard_pre(const bh_ctx* x, int learning, int32_t* send_dev,
   if (rc) return rc;
   if (x->seg_world <= 1 || !send_dev) return BH_E_BADARG;
   cudaStream_t st = S_(stream);
-  if ((rc = bh_tm_select(x, stream))) return rc;
-  if ((rc = bh_tm_learn(x, learning, stream))) return rc;
+  if (learning < 0 || learning > 3) return BH_E_BADARG;
+  const int learn = learning & BH_STEP_LEARNING, winners = !(learning & BH_STEP_NO_WINNER_CELLS);
+  if ((rc = tm_select(x, (learn || winners) ? 1 : 0, st))) return rc;
+  if ((rc = bh_tm_learn(x, learn, stream))) return rc;
   if ((rc = tm_post_and_scan(x, st))) return rc;
   k_tm_shard_pack<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, send_dev);
   LAUNCHED("tm_shard_pack");
   return 0;
 }
 
-extern "C" int bh_tm_shard_post(const bh_ctx* x, const int32_t* recv_dev, void* stream) {
+extern "C" int bh_tm_shard_post_ex(const bh_ctx* x, const int32_t* recv_dev, int want_jitter, void* stream) {
   DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
@@ -714,11 +716,17 @@ extern "C" int bh_tm_shard_post(const bh_ctx* x, const int32_t* recv_dev, void* 
   cudaStream_t st = S_(stream);
   k_tm_shard_merge<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, recv_dev);
   LAUNCHED("tm_shard_merge");
-  k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 3, 1);
-  LAUNCHED("tm_draw3");
-  k_tm_activate_finish<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x);
+  if (want_jitter) {
+    k_tm_draw<<<1, MT_THREADS, 0, st>>>(*x, 3, 1);
+    LAUNCHED("tm_draw3");
+  }
+  k_tm_activate_finish<<<x->tm_blocks, BH_TM_THREADS, 0, st>>>(*x, want_jitter ? 1 : 0);
   LAUNCHED("tm_activate_finish");
   return 0;
+}
+
+extern "C" int bh_tm_shard_post(const bh_ctx* x, const int32_t* recv_dev, void* stream) {
+  return bh_tm_shard_post_ex(x, recv_dev, 1, stream);
 }
 
 extern "C" int bh_tm_step(const bh_ctx* x, int learning, void* stream) {
@@ -767,7 +775,7 @@ static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_step
                         cudaStream_t st) {
   const int nb = x->fused_ctas;
   if (nb < 1) return BH_E_BADARG;
-  if (learning < 0 || learning > 3 || (x->fused_mode == 3 && learning > 1)) return BH_E_UNSUPPORTED;
+  if (learning < 0 || learning > 3) return BH_E_UNSUPPORTED;
   const int smem = fused_smem(x);
   if (smem > 160 * 1024) return BH_E_UNSUPPORTED;
   int prc = prepare_fused(x->fused_mode);
@@ -812,7 +820,7 @@ extern "C" int bh_step(const bh_ctx* x, const uint32_t* in, int learning, void* 
   DevGuard dev_guard_(x);
   int rc = check_ctx(x);
   if (rc) return rc;
-  if (learning < 0 || learning > 3 || (x->fused_mode == 3 && learning > 1)) return BH_E_UNSUPPORTED;
+  if (learning < 0 || learning > 3) return BH_E_UNSUPPORTED;
   if (x->fused_mode) return launch_fused(x, in, 1, learning, 0, S_(stream));
   const int learn = learning & BH_STEP_LEARNING, winners = !(learning & BH_STEP_NO_WINNER_CELLS);
   if ((rc = sp_step(x, in, learn, S_(stream)))) return rc;

@@ -132,19 +132,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     BH_STAMP();
     // P5: permanence updates, deletion, growth
     if (MODE == 2 && lazy) {
-      // stage 1 of the learning pass (a warp per learning / punished row: a few dozen CTAs' worth) next to the
-      // tail jumps on the other CTAs
-      const int n1 = nb >= 96 ? 48 : 0;  // CTAs of stage 1 (0: every CTA does both)
-      if (n1) {
-        if (b < n1) {
-          if (learning) ph_learn_apply(c, s_dyn, b, n1, 1);
-        } else {
-          ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b - n1, nb - n1);
-        }
-      } else {
-        if (learning) ph_learn_apply(c, s_dyn, b, nb, 1);
-        ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b, nb);
-      }
+      // stage 1 of the learning pass and the tail jumps, both spread over every CTA (measured and rejected:
+      // 48 CTAs of stage 1 next to the jumps on the rest -- no gain on one GPU, and the jump units then need more
+      // rounds on a shard: 28 us against 16 at 8 shards)
+      if (learning) ph_learn_apply(c, s_dyn, b, nb, 1);
+      ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b, nb);
       BH_SYNC();
       ph_rng_lazy_rows(c, s_dyn, b, nb, [&]() { BH_SYNC(); },
                        [&](bool produce_rows) { ph_learn_grow(c, s_dyn, b, nb, produce_rows); });

@@ -96,8 +96,12 @@ __device__ void xch_exchange(const bh_ctx& c, int kind, const int* send, long lo
 }
 
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
-    k_step_shard(const __grid_constant__ bh_ctx c, const uint32_t* input_fixed, int n_steps, int learning, int want_summary) {
+    k_step_shard(const __grid_constant__ bh_ctx c, const uint32_t* input_fixed, int n_steps, int flags, int want_summary) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
+  // flags: BH_STEP_LEARNING | BH_STEP_NO_WINNER_CELLS, as in fused.cuh
+  const int learning = flags & BH_STEP_LEARNING;
+  const bool want_jit = !(flags & BH_STEP_NO_WINNER_CELLS);
+  const bool want = learning || want_jit;
   const int b = blockIdx.x, nb = gridDim.x;
   const int nw = nb > 1 ? nb - 1 : 1;
   const bool worker = b < nw;
@@ -129,7 +133,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     stamp_i = 0;
     BH_STAMP();
     // P0: overlap + boost of the local columns; draw #1 on the rng CTA
-    if (rng) ph_draw(c, 1, 1, nw);
+    if (rng && want) {
+      ph_fill_jitter(c, s_dyn);  // the previous activation's deferred rand(M) first (no-op otherwise)
+      __syncthreads();
+      ph_draw(c, 1, 1, nw);
+    }
     if (nb == 1) ph_overlap<true, true>(c, input, s_dyn, 0, 1);
     else if (!rng) ph_overlap<true, true>(c, input, s_dyn, b, nb - 1);
     BH_SYNC();
@@ -212,9 +220,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     // P2..P7 as in fused.cuh; learning and the segment scan touch only what this rank stores
     // a TEAM of the last CTAs runs the replicated temporal-memory bookkeeping chain while the others learn this
     // shard's spatial-pooler rows (fused.cuh, P2)
-    // (the more shards, the shorter the SP learning pass of a rank and the larger the team may be: at 8 shards
-    // the bookkeeping chain, not the learning pass, bounds this phase)
-    const int team = (nb >= 32 && c.sc[BH_SC_M] <= 32768) ? (nb >= 128 ? (G >= 8 ? 64 : (G >= 4 ? 32 : 16)) : (nb >= 64 ? 16 : 8)) : 0;
+    // (a larger team does not shorten the chain: 64 CTAs at 8 shards measured 41 us against 29 with 16 -- its
+    // cost is the dependent round trips and the team barriers, which grow with the team)
+    const int team = (nb >= 32 && c.sc[BH_SC_M] <= 32768) ? (nb >= 64 ? 16 : 8) : 0;
     if (rebin && b == (team ? nb - team : 0)) tk3_rebin_sharded(c, G > 1 ? G * k_loc : k_loc);
     if (team) {
       const int t0 = nb - team;
@@ -222,9 +230,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
         // winner bits on the whole team | the drawing CTA forms the ordered winner lists while the others flag the
         // learning segments | it plans draw #2 while they form the learning lists (team barriers in between)
         unsigned int* bar2 = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT);
-        ph_select_a(c, b - t0, team);
+        ph_select_a(c, b - t0, team, want);
         grid_barrier(bar2, (unsigned)team);
-        if (rng) ph_select_b(c, 0, 1, true, team);
+        if (rng) ph_select_b(c, 0, 1, want, team);
         else ph_learn_select_a(c, learning, b - t0, team - 1);
         grid_barrier(bar2, (unsigned)team);
         if (rng) ph_draw(c, 2, learning, team - 1, true);
@@ -240,11 +248,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     } else {
       if (learning) ph_sp_learn<false>(c, input, b, nb);
       ph_duty(c, b, nb);
-      if (worker) ph_select_a(c, b, nw);
+      if (worker) ph_select_a(c, b, nw, want);
       BH_SYNC();
       BH_STAMP();  // 5: SP learn + duty + winner bits
       if (worker) {
-        ph_select_b(c, b, nw);
+        ph_select_b(c, b, nw, want);
         ph_learn_select_a(c, learning, b, nw);
       }
       BH_SYNC();
@@ -261,18 +269,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     }
     BH_STAMP();  // 8: stream chunks
     if (lazy) {
-      // stage 1 of the learning pass (a warp per row of this shard: few CTAs' worth) next to the tail jumps
-      const int n1 = nb >= 96 ? 48 : 0;  // CTAs of stage 1 (0: every CTA does both)
-      if (n1) {
-        if (b < n1) {
-          if (learning) ph_learn_apply(c, s_dyn, b, n1, 1);
-        } else {
-          ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b - n1, nb - n1);
-        }
-      } else {
-        if (learning) ph_learn_apply(c, s_dyn, b, nb, 1);
-        ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b, nb);
-      }
+      // stage 1 of the learning pass and the tail jumps, both spread over every CTA (measured and rejected:
+      // 48 CTAs of stage 1 next to the jumps on the rest -- no gain on one GPU, and the jump units then need more
+      // rounds on a shard: 28 us against 16 at 8 shards)
+      if (learning) ph_learn_apply(c, s_dyn, b, nb, 1);
+      ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, b, nb);
       BH_SYNC();
       ph_rng_lazy_rows(c, s_dyn, b, nb, [&]() { BH_SYNC(); },
                        [&](bool produce_rows) { ph_learn_grow(c, s_dyn, b, nb, produce_rows); });
@@ -325,14 +326,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     }
     // P9: draw #3 (a phase of its own only when not covered, see fused.cuh), jitter, predictions
     const int M = c.sc[BH_SC_X_MATCH] < c.match_capacity ? c.sc[BH_SC_X_MATCH] : c.match_capacity;
-    const bool ready3 = (long long)M <= c.rng64[R_READY3];
+    const bool ready3 = !want_jit || (long long)M <= c.rng64[R_READY3];
     if (!ready3) {
       if (rng) ph_draw(c, 3, 1, ns);
       BH_SYNC();
-    } else if (rng) {
+    } else if (rng && want_jit) {
       ph_draw3_ready(c, ns);
     }
-    if (worker) ph_activate_finish(c, b, nw, ready3);
+    if (worker) ph_activate_finish(c, b, nw, ready3, want_jit);
     BH_SYNC();
     BH_STAMP();  // 14: draw 3 + jitter + predictions
   }

@@ -147,19 +147,22 @@ __device__ void ph_shard_merge(const bh_ctx& c, const int* recv, int b, int nb, 
 // (projections.py:234-235), per-cell maximum (:236-237), active-segment count (:251).
 // Every rank computes all of it (the per-cell state is replicated).  Completes the step.
 // `ready`: draw #3 was bookkeeping only and may still be running on the drawing CTA.
-__device__ void ph_activate_finish(const bh_ctx& c, int b, int nb, bool ready = false) {
+__device__ void ph_activate_finish(const bh_ctx& c, int b, int nb, bool ready = false, bool want_jitter = true) {
   const int mx = c.sc[BH_SC_X_MATCH] < c.match_capacity ? c.sc[BH_SC_X_MATCH] : c.match_capacity;
-  const int M = ready ? mx : c.sc[BH_SC_M];
+  const int M = (ready || !want_jitter) ? mx : c.sc[BH_SC_M];
   const long long off3 = c.rng64[R_OFF3], n3 = ready ? (long long)mx : c.rng64[R_N3];
 #pragma unroll 1
   for (int j = b * blockDim.x + threadIdx.x; j < M; j += nb * blockDim.x) {
     const int s = c.m_seg[j];
-    const int pot = c.seg_pot[s], conn = c.m_conn[j];
-    const double u = j < n3 ? rng_uniform(c, off3 + 2 * j) : 0.0;
-    const float jit = __double2float_rn(__dadd_rn((double)pot, u));
+    const int conn = c.m_conn[j];
     const int owner = c.seg_owner[s];
-    c.m_jit[j] = jit;
-    atomicMax(reinterpret_cast<int*>(c.cell_maxjit + owner), __float_as_int(jit));  // jit > 0
+    if (want_jitter) {
+      const int pot = c.seg_pot[s];
+      const double u = j < n3 ? rng_uniform(c, off3 + 2 * j) : 0.0;
+      const float jit = __double2float_rn(__dadd_rn((double)pot, u));
+      c.m_jit[j] = jit;
+      atomicMax(reinterpret_cast<int*>(c.cell_maxjit + owner), __float_as_int(jit));  // jit > 0
+    }
     if (conn >= c.seg_activation_threshold) {
       atomicAdd(&c.cell_npred[owner], 1);
       if (atomicOr(&c.col_pred[owner >> 5], 1u << (owner & 31)) == 0u) atomicAdd(&c.sc[BH_SC_NPREDCOL], 1);
@@ -168,6 +171,11 @@ __device__ void ph_activate_finish(const bh_ctx& c, int b, int nb, bool ready = 
   if (b == 0 && threadIdx.x == 0) {
     c.sc[BH_SC_HAVE_PREV] = 1;
     c.sc[BH_SC_STEP] = c.sc[BH_SC_STEP] + 1;
+    c.sc[BH_SC_JIT_PENDING] = want_jitter ? 0 : 1;
+    if (!want_jitter) {  // no draw published M (tm_kernels.cuh, ph_activate_b)
+      if (c.sc[BH_SC_X_MATCH] > c.match_capacity) atomicOr(&c.sc[BH_SC_STATUS], BH_ST_MATCH_OVERFLOW);
+      c.sc[BH_SC_M] = mx;
+    }
   }
 }
 
@@ -177,6 +185,6 @@ __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_shard_pack(const __grid_co
 __global__ void __launch_bounds__(BH_TM_THREADS) k_tm_shard_merge(const __grid_constant__ bh_ctx c, const int* recv) {
   ph_shard_merge(c, recv, blockIdx.x, gridDim.x);
 }
-__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_finish(const __grid_constant__ bh_ctx c) {
-  ph_activate_finish(c, blockIdx.x, gridDim.x);
+__global__ void __launch_bounds__(BH_TM_THREADS) k_tm_activate_finish(const __grid_constant__ bh_ctx c, int want_jitter) {
+  ph_activate_finish(c, blockIdx.x, gridDim.x, false, want_jitter != 0);
 }

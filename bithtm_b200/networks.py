@@ -339,10 +339,9 @@ class TemporalMemory:
         if eng.seg_world > 1:  # segment shards: local scan, ONE all-gather, merge (see _shard.py)
             from ._shard import gather_records
 
-            if not return_winner_cell:
-                raise NotImplementedError("segment shards support the default return_winner_cell=True only")
-            send = eng.tm_shard_pre(learning)
-            eng.tm_shard_post(gather_records(send, eng.xch_recv, self.distal_projection._group))
+            send = eng.tm_shard_pre(int(bool(learning)) | (0 if return_winner_cell else 2))
+            eng.tm_shard_post(gather_records(send, eng.xch_recv, self.distal_projection._group),
+                              want_jitter=bool(return_winner_cell))
         else:
             nat.check(nat.lib.bh_tm_step_ex(eng.ref, int(bool(learning)), int(bool(return_winner_cell)),
                                             int(bool(return_winner_cell)), eng.stream), "bh_tm_step_ex")
@@ -474,8 +473,6 @@ class HierarchicalTemporalMemory:
         if mode == 3:  # the shard's whole step is one kernel (exchanges inside)
             if not sp._native_inhibition:
                 raise NotImplementedError('fused="shard" needs the built-in GlobalInhibition')
-            if not return_winner_cell:
-                raise NotImplementedError('fused="shard" supports the default return_winner_cell=True only')
         whole_kernel = sp._native_inhibition and (mode == 3 or (eng.shard_world == 1 and eng.seg_world == 1))
         if not whole_kernel:
             # an arbitrary host object in the inhibition slot, or NCCL exchanges between the stages of a shard

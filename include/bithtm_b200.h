@@ -330,7 +330,10 @@ int bh_sp_shard_finish(const bh_ctx* ctx, const uint32_t* input_words_dev, const
  * bh_tm_shard_pre : networks.py:95-119 + learning + the local segment scan; fills
  *                   send_dev with this rank's record.
  * bh_tm_shard_post: merges the seg_world gathered records (recv_dev, rank order), draws
- *                   rand(M), computes jitter / predictions; completes the timestep. */
+ *                   rand(M), computes jitter / predictions; completes the timestep.
+ * `learning` of bh_tm_shard_pre carries the BH_STEP_* flags; a step with
+ * BH_STEP_NO_WINNER_CELLS ends with bh_tm_shard_post_ex(..., want_jitter = 0) (the jitter
+ * draw stays pending, networks.py:121). */
 size_t bh_tm_shard_xch_ints(const bh_ctx* ctx);
 /* fused_mode 3: size (int32) of one rank's exchange region.  Every rank allocates one in
  * memory its peers can map (CUDA IPC / symmetric memory), zero-fills it and passes all
@@ -339,6 +342,7 @@ size_t bh_tm_shard_xch_ints(const bh_ctx* ctx);
 size_t bh_xch_region_ints(const bh_ctx* ctx);
 int bh_tm_shard_pre(const bh_ctx* ctx, int learning, int32_t* send_dev, void* stream);
 int bh_tm_shard_post(const bh_ctx* ctx, const int32_t* recv_dev, void* stream);
+int bh_tm_shard_post_ex(const bh_ctx* ctx, const int32_t* recv_dev, int want_jitter, void* stream);
 
 /* Complete a timestep when no temporal memory follows (stand-alone SpatialPooler):
  * sc[BH_SC_STEP] += 1 so the ping-pong buffers rotate. */

@@ -541,7 +541,7 @@ def test_stream_batch_equals_streams_stepped_alone():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fused", ["cluster", "grid", "off"])
+@pytest.mark.parametrize("fused", ["cluster", "grid", "off", "shard"])
 def test_mixed_learning_and_winner_flags_match_reference_trace(fused):
     """Per-step (learning, return_winner_cell) flags of TemporalMemory.process (networks.py:91):
     inference-only steps draw nothing, the jitter draw is deferred until a later step needs
@@ -555,7 +555,7 @@ def test_mixed_learning_and_winner_flags_match_reference_trace(fused):
     I, C, c, k, seed, steps = info["I"], info["C"], info["c"], info["k"], info["seed"], info["steps"]
     xs = golden_inputs(info, steps)
     np.random.seed(seed)
-    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused=fused)
+    htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, fused=fused, **({"fused_ctas": 12} if fused == "shard" else {}))
     orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
     state_at = {int(s): int(d) for s, d in zip(g["state_steps"], g["state_digests"])}
     for t in range(steps):

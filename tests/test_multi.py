@@ -220,7 +220,7 @@ def _emulated_shards(info, world, **kw):
     return shards
 
 
-def _emulated_step(shards, x, learning=True):
+def _emulated_step(shards, x, learning=True, return_winner_cell=True):
     """One timestep of `world` shards living in ONE process: the two all-gathers are
     torch.cat of the per-shard buffers (exactly what NCCL delivers, rank order)."""
     import torch
@@ -243,12 +243,14 @@ def _emulated_step(shards, x, learning=True):
         nat.check(nat.lib.bh_sp_shard_finish(eng.ref, words.data_ptr(), all_keys.data_ptr(), all_cols.data_ptr(),
                                              int(all_keys.numel()), int(learning), eng.stream))
         h.temporal_memory._rng.before(eng)
-    records = torch.cat([h.engine.tm_shard_pre(learning) for h in shards])  # exchange 2
+    flags = int(bool(learning)) | (0 if return_winner_cell else 2)
+    records = torch.cat([h.engine.tm_shard_pre(flags) for h in shards])  # exchange 2
     states = []
     for h in shards:
         eng = h.engine
-        eng.tm_shard_post(records)
-        states.append(h.temporal_memory._finish(eng.summary()))
+        eng.tm_shard_post(records, want_jitter=return_winner_cell)
+        states.append(h.temporal_memory._finish(eng.summary(), have_winner=bool(learning or return_winner_cell),
+                                                have_jitter=bool(return_winner_cell)))
     return states
 
 
@@ -301,6 +303,43 @@ def test_segment_shards_single_process_emulation(name, world, steps):
     assert sum(len(p[0]) for p in parts) == orc.n_seg
     if True:
         assert recycled > 0, "the run never recycled a segment: the cross-shard path was not exercised"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_segment_shards_mixed_flags_match_reference_trace(world):
+    """Per-step (learning, return_winner_cell) flags on segment shards (staged entry points,
+    bh_tm_shard_pre flags + bh_tm_shard_post_ex): inference-only steps, deferred jitter draws,
+    against the trace recorded from the unmodified reference (tests/golden/mixed.npz)."""
+    from helpers import golden_inputs, load_golden
+    from oracle.htm_oracle import HTMOracle, OracleConfig
+
+    info = load_golden("mixed")
+    g = info["g"]
+    I, C, c, k, seed, steps = info["I"], info["C"], info["c"], info["k"], info["seed"], info["steps"]
+    xs = golden_inputs(info, steps)
+    shards = _emulated_shards(info, world)
+    orc = HTMOracle(OracleConfig(I, C, c, k), rng=np.random.RandomState(seed))
+    for t in range(steps):
+        lf, wf = bool(g["learning_flags"][t]), bool(g["winner_flags"][t])
+        rec = orc.step(xs[t], learning=lf, return_winner_cell=wf)
+        states = _emulated_step(shards, xs[t], learning=lf, return_winner_cell=wf)
+        for r, st in enumerate(states):
+            where = f"step {t} shard {r} (learning={lf}, return_winner_cell={wf})"
+            ds = st.distal_state
+            wc = st.winner_cell
+            assert (wc is None) == (not (lf or wf)), where
+            assert np.array_equal(st._active_column, rec.active_column), where
+            if wc is not None:
+                assert np.array_equal(wc[0] * c + wc[1], rec.winner_cell), where
+            assert np.array_equal(st.active_cell[0] * c + st.active_cell[1], rec.active_cell), where
+            assert st.n_segments == rec.n_segments, where
+            assert np.array_equal(ds.matching_segment, rec.matching_segment), where
+            assert np.array_equal(ds.matching_segment_activation, rec.matching_activation), where
+            assert (ds.matching_segment_jittered_potential is None) == (not wf), where
+            if wf:
+                assert np.array_equal(ds.matching_segment_jittered_potential.view(np.uint32),
+                                      np.asarray(rec.matching_jit, dtype=np.float32).view(np.uint32)), where
 
 
 # ----------------------------------------------------------------------------- fused sharded step
