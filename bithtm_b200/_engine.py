@@ -166,8 +166,6 @@ class Engine:
         # produced by table jumps -- the cooperative-grid kernels of networks that draw a lot per step
         if lazy_rng == "auto":
             lazy_rng = bool(parallel_rng) and fused in ("grid", "shard")
-        if huge and fused == "auto":
-            fused = "grid"
         if lazy_rng and fused in ("grid", "shard"):
             gran = int(skip_gran) if skip_gran else 4096
             while skip_gran is None and (step_words + step_words // 4) // gran > 4096:

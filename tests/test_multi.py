@@ -306,7 +306,7 @@ def test_segment_shards_single_process_emulation(name, world, steps):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 4])
 def test_segment_shards_mixed_flags_match_reference_trace(world):
     """Per-step (learning, return_winner_cell) flags on segment shards (staged entry points,
     bh_tm_shard_pre flags + bh_tm_shard_post_ex): inference-only steps, deferred jitter draws,

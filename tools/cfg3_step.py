@@ -35,7 +35,8 @@ def main():
     np.random.seed(0)
     sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
     htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy", ring_len=steps,
-                                            max_segments=1 << 21, max_synapses_per_segment=64, fused="grid")
+                                            max_segments=1 << 21, max_synapses_per_segment=64,
+                                            fused=os.environ.get("BH_FUSED", "grid"))
     del perm
     sp.proximal_projection._host_permanence = None
     torch.cuda.empty_cache()
