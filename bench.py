@@ -405,7 +405,8 @@ def ours(args):
     step_s = dev_s / K
     achieved = ab / step_s / 1e9
     roofline = {"bound": "hbm", "kernel": "k_step_shard" if world > 1 else "k_step_fused<2>", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kernel),
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(kernel) if world == 1 else None,  # (ncu profiles one GPU)
                 "peak_source": peak_src, "algorithmic_bytes_per_launch_step": ab,
                 "algorithmic_bytes_whole_network": ab_total, "state": stats,
                 "note": "per GPU: the step's algorithmic bytes (SURVEY 8d: SP + TM, from the live network state) / "

@@ -47,7 +47,7 @@ class Engine:
                  learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
                  fused="auto", fused_ctas=None, fused_threads=None, column_shard=None, parallel_rng="auto", segment_shard=None,
                  exchange_match_capacity=None, exchange_recycle_capacity=None, lazy_rng="auto", skip_gran=None,
-                 skip_min=None, skip_polys=None, tail_chunks=None):
+                 skip_min=None, skip_polys=None, tail_chunks=None, exchange_cells="auto"):
         """``column_shard=(rank, world)``: this engine owns columns
         [rank*C/world, (rank+1)*C/world) of the spatial pooler (permanence, mask, duty
         cycles).  ``segment_shard=(rank, world)``: it holds the synapse rows of the
@@ -105,7 +105,10 @@ class Engine:
         if fused == "shard":
             # exchanges as {word, sequence} cells (csrc/shard_ll.cuh) while the one-CTA selection / merge fit
             # in shared memory; very wide networks use the copy + flag protocol
-            ctx.xch_ll = 1 if 4 * (6400 + k + Ccol // self.shard_world // 16) <= 150 * 1024 else 0
+            # (and while the matching segments of all ranks -- about one per active column in steady state --
+            # fit the one-CTA merge: 16384 in all, 4096 per rank).  ``exchange_cells=False`` forces the latter.
+            fits = 4 * (6400 + k + Ccol // self.shard_world // 16) <= 150 * 1024 and k <= 4096
+            ctx.xch_ll = 1 if (fits if exchange_cells == "auto" else bool(exchange_cells)) else 0
             if ctx.xch_ll and not exchange_match_capacity:
                 ctx.xm_cap = min(ctx.xm_cap, 4096)  # what one CTA sorts per rank
         ctx.col_local = Ccol // self.shard_world

@@ -370,8 +370,9 @@ def test_fused_shard_kernel_single_shard_matches_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,world,steps", [("tiny", 2, 600), ("mid", 2, 1100), ("odd", 3, 750), ("mid", 4, 950)])
-def test_fused_shard_kernels_concurrent_on_one_gpu(name, world, steps):
+@pytest.mark.parametrize("name,world,steps,cells", [("tiny", 2, 600, True), ("mid", 2, 1100, True), ("odd", 3, 750, True),
+                                                    ("mid", 4, 950, True), ("mid", 2, 1100, False), ("odd", 3, 750, False)])
+def test_fused_shard_kernels_concurrent_on_one_gpu(name, world, steps, cells):
     """`world` shards as `world` cooperative kernels running CONCURRENTLY on one GPU (one
     stream each), exchanging their records through each other's regions exactly as they do
     across GPUs over NVLink.  Every shard must reproduce the oracle."""
@@ -386,7 +387,10 @@ def test_fused_shard_kernels_concurrent_on_one_gpu(name, world, steps):
     info = load_golden(name)
     I, C, c, k, seed = info["I"], info["C"], info["c"], info["k"], info["seed"]
     xs = golden_inputs(info, steps)
-    shards = _emulated_shards(info, world, fused="shard", fused_ctas=8)
+    # cells: the {word, sequence} cell exchange (one-CTA selection / merge); else the copy + fence + flag protocol
+    # with grid-wide selection and merge (what very wide networks such as cfg5 use)
+    shards = _emulated_shards(info, world, fused="shard", fused_ctas=8, exchange_cells=cells)
+    assert all(h.engine.ctx.xch_ll == int(cells) for h in shards)
     regions = [torch.zeros(h.engine.exchange_region_ints(), dtype=torch.int32, device="cuda") for h in shards]
     for h in shards:
         h.engine.set_exchange_regions([r.data_ptr() for r in regions], keepalive=regions)
@@ -423,8 +427,8 @@ def test_fused_shard_kernels_concurrent_on_one_gpu(name, world, steps):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,k,ctas", [(2, 655, 60), (4, 1100, 36)])
-def test_sharded_equals_unsharded_at_scale(world, k, ctas):
+@pytest.mark.parametrize("world,k,ctas,cells", [(2, 655, 60, True), (4, 1100, 36, True), (2, 655, 60, False)])
+def test_sharded_equals_unsharded_at_scale(world, k, ctas, cells):
     """No oracle at this size (validate sharded == unsharded): 32768
     columns x 4096 inputs, many-CTA random-stream production and the grid-wide top-k active.
     One network as a single cooperative kernel vs the same network as two shard kernels
@@ -456,7 +460,7 @@ def test_sharded_equals_unsharded_at_scale(world, k, ctas):
 
     whole = build(fused="grid")
     assert whole.engine.ctx.jump_polys > 0
-    shards = [build(column_shard=(r, world), fused="shard", fused_ctas=ctas) for r in range(world)]
+    shards = [build(column_shard=(r, world), fused="shard", fused_ctas=ctas, exchange_cells=cells) for r in range(world)]
     regions = [torch.zeros(h.engine.exchange_region_ints(), dtype=torch.int32, device="cuda") for h in shards]
     for h in shards + [whole]:
         h.temporal_memory._rng.before(h.engine)

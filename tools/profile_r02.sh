@@ -21,4 +21,11 @@ echo "kernels rc=$?"
 timeout 600 ncu $FULL -k regex:k_sp_overlap_batched_t5 -c 1 -o $O/r02_overlap_t5 python tools/batched_overlap.py 256 65536 16384 5 > $O/r02_ncu_batched_t5.log 2>&1
 timeout 600 ncu $FULL -k regex:k_sp_overlap_batched_tc -c 1 -o $O/r02_overlap_mma python tools/batched_overlap.py 256 65536 16384 5 > $O/r02_ncu_batched_mma.log 2>&1
 echo "batched rc=$?"
-ls -la $O/*.ncu-rep
+# what travels back is capped at 64 MiB: raw pages as CSV for every capture, the reports themselves only for the
+# step kernel and the tcgen05 kernel
+for r in r02_step_fused_grid r02_step_shard r02_cfg3_kernels r02_overlap_t5 r02_overlap_mma; do
+  ncu -i $O/$r.ncu-rep --page raw --csv > $O/$r.raw.csv 2> /dev/null
+done
+ncu -i $O/r02_step_fused_grid.ncu-rep --page source --csv > $O/r02_step_fused_grid.source.csv 2> /dev/null
+rm -f $O/r02_step_shard.ncu-rep $O/r02_cfg3_kernels.ncu-rep $O/r02_overlap_mma.ncu-rep
+ls -la $O/
