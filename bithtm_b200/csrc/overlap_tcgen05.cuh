@@ -14,9 +14,10 @@
 //               256 mask rows x 4 words = 6 KB) into an 8-slot ring; out-of-range rows / words arrive as zeros.
 //               (Round 1's prototype loaded the words with ordinary global loads from the widening warps: the
 //               proxy fence each stage needs then drained those loads, one full memory round trip per stage.)
-//   warps 0-15  widen: raw words -> {0, 1} bytes in the UMMA canonical K-major layout (no swizzle: 8-row x
-//               16-byte core matrices, chunk-major tiles), 3-slot ring of 48 KB stages, full / empty
-//               mbarriers; fence.proxy.async; they are also the epilogue (tcgen05.ld -> global).
+//   warps 0-11  widen, one row of the stage per thread: raw words -> {0, 1} bytes in the UMMA canonical K-major
+//               layout (no swizzle: 8-row x 16-byte core matrices, chunk-major tiles), 3-slot ring of 48 KB
+//               stages, full / empty mbarriers; fence.proxy.async.
+//   warps 0-15  epilogue (tcgen05.ld -> global), a TMEM lane quarter and a column group each.
 //   warp 16     allocates TMEM (256 columns) and issues tcgen05.mma.cta_group::1.kind::i8, M = 128, N = 256,
 //               K = 32 bytes per instruction, accumulator in TMEM; tcgen05.commit frees the stage / publishes
 //               the accumulator.
@@ -49,12 +50,12 @@ constexpr int RAW_BYTES = A_RAW + B_RAW;
 constexpr int WIDEN_WARPS = 16;              // multiple of 4 (TMEM lane quarters)
 constexpr int WIDENERS = WIDEN_WARPS * 32;
 constexpr int THREADS = WIDENERS + 64;       // + MMA warp + TMA warp
-constexpr int ITEMS = (TILE_M + TILE_N) * KW / WIDENERS;  // (row, word) pairs per widening thread: 3
+constexpr int ROW_WARPS = (TILE_M + TILE_N) / 32;         // warps that widen: one row of the stage per thread
 constexpr int COLS_PER_WARP = TILE_N / (WIDEN_WARPS / 4);
 constexpr int TMEM_COLS = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAW_STAGES * RAW_BYTES + 1024;
 constexpr int SPIN_CAP = 1 << 26;
-static_assert((TILE_M + TILE_N) * KW % WIDENERS == 0, "items must divide");
+static_assert(KW == 4 && ROW_WARPS <= WIDEN_WARPS, "a row's words are one 16-byte load");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -147,12 +148,12 @@ __global__ void __launch_bounds__(THREADS, 1)
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], WIDEN_WARPS);
+      mbar_init(&full_bar[s], ROW_WARPS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < RAW_STAGES; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], WIDEN_WARPS);
+      mbar_init(&raw_empty[s], ROW_WARPS);
     }
     mbar_init(&acc_full, 1);
     mbar_init(&acc_empty, WIDEN_WARPS);
@@ -178,26 +179,29 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
       const int m0 = (tile % tiles_m) * TILE_M, n0 = (tile / tiles_m) * TILE_N;
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
+        if (warp >= ROW_WARPS) continue;  // (warps 12-15 only take part in the epilogue)
         const int rs = it % RAW_STAGES, s = it % STAGES;
         if (!mbar_wait(&raw_full[rs], (it / RAW_STAGES) & 1, err)) return;
-        const uint32_t* raw = reinterpret_cast<const uint32_t*>(raw_base + rs * RAW_BYTES);  // [128 + 256 rows][KW]
-        uint32_t wd[ITEMS];
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) wd[i] = raw[i * WIDENERS + tid];  // pair p = i * WIDENERS + tid = row * KW + word
+        // One ROW of the stage per thread (rows 0..127 of the input tile, then 256 mask rows: warps 0-11): its
+        // KW = 4 words arrive as one 16-byte load, and consecutive lanes store to consecutive rows of a core
+        // matrix, i.e. to consecutive 16-byte slots -- every shared-memory access of the stage is conflict-free.
+        // (A (row, word) pair per thread with the word index fastest -- the first version -- put the four words
+        // of a row 2 * LBO apart on the same banks: 16 wavefronts per STS.128 instead of 4, 2400 clk per stage.)
+        const uint4 x4 = reinterpret_cast<const uint4*>(raw_base + rs * RAW_BYTES)[tid];
         if (!mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1, err)) return;
         uint8_t* a_st = smem + s * STAGE_BYTES;
-        uint8_t* b_st = a_st + A_STAGE;
+        const int r = tid;
+        uint8_t* base = r < TILE_M ? a_st + r * 16 : a_st + A_STAGE + (r - TILE_M) * 16;
+        const int lbo = r < TILE_M ? A_LBO : B_LBO;
+        const uint32_t xs[KW] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-          const int p = i * WIDENERS + tid, w = p & (KW - 1), r = p / KW;
-          const uint32_t x = wd[i];
+        for (int w = 0; w < KW; ++w) {
+          const uint32_t x = xs[w];
           uint4 lo, hi;
           lo.x = x & 0x01010101u, lo.y = (x >> 1) & 0x01010101u, lo.z = (x >> 2) & 0x01010101u, lo.w = (x >> 3) & 0x01010101u;
           hi.x = (x >> 4) & 0x01010101u, hi.y = (x >> 5) & 0x01010101u, hi.z = (x >> 6) & 0x01010101u, hi.w = (x >> 7) & 0x01010101u;
-          uint8_t* base = r < TILE_M ? a_st + (2 * w) * A_LBO + r * 16 : b_st + (2 * w) * B_LBO + (r - TILE_M) * 16;
-          const int lbo = r < TILE_M ? A_LBO : B_LBO;
-          *reinterpret_cast<uint4*>(base) = lo;
-          *reinterpret_cast<uint4*>(base + lbo) = hi;
+          *reinterpret_cast<uint4*>(base + (2 * w) * lbo) = lo;
+          *reinterpret_cast<uint4*>(base + (2 * w + 1) * lbo) = hi;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
         __syncwarp();
