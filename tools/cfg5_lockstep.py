@@ -43,7 +43,7 @@ def main():
     sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
     t0 = time.time()
     htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, max_segments=1 << 21,
-                                            max_synapses_per_segment=64)
+                                            max_synapses_per_segment=128)
     del perm
     eng = htm.engine
     print(f"engine: fused_mode {eng.ctx.fused_mode}, skip table {eng.ctx.skip_polys} x {eng.ctx.skip_gran} words, "

@@ -51,7 +51,7 @@ def main():
     sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
     htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy",
                                             column_shard=True if world > 1 else None, max_segments=1 << 22,
-                                            max_synapses_per_segment=64, fused="shard" if world > 1 else "grid",
+                                            max_synapses_per_segment=128, fused="shard" if world > 1 else "grid",
                                             ring_len=steps)
     del perm
     sp.proximal_projection._host_permanence = None
