@@ -40,12 +40,18 @@ def main():
     g = np.random.default_rng(0)
     base = g.random((patterns, I)) < 0.2
     xs = base[np.arange(steps) % patterns] ^ (g.random((steps, I)) < 0.05)
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(77 + rank)
     rows = C // world
     perm = torch.empty(rows, I, dtype=torch.float64, device="cuda")
-    for r0 in range(0, rows, 16384):  # (a single randn of 16 GiB would need a second 16 GiB for the scaling)
-        perm[r0:r0 + 16384] = torch.randn(min(16384, rows - r0), I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
+    # drawn in 64 row blocks with per-block seeds: the same matrix for every world size (a short input lets ONE GPU
+    # hold the whole network, so the 8-GPU run can be compared with the single-GPU one line by line)
+    blk = C // 64
+    for b in range(64):
+        lo = b * blk - rank * rows
+        if lo < 0 or lo >= rows:
+            continue
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(7700 + b)
+        perm[lo:lo + blk] = torch.randn(blk, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
     np.random.seed(0)
     t0 = time.time()
     sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
@@ -89,7 +95,7 @@ def main():
             sigs = [sig]
         agree = all(bool(torch.equal(s, sigs[0])) for s in sigs)
         ok_cols = bool(np.all(np.diff(cols) > 0) and cols[0] >= 0 and cols[-1] < C)
-        entry = dict(step=t, ms=round(float(ms), 3), status=int(sc[12]), segments=int(sc[2]), matching=int(sc[4]),
+        entry = dict(step=t, ms=round(float(ms), 3), status=int(sc[12]), active_columns_crc32=int(sig[0]), segments=int(sc[2]), matching=int(sc[4]),
                      winners=int(sc[5 + cur]), learning_rows=int(sc[8]), growing_rows_local=int(sc[23]),
                      segments_per_cell_sum=int(sig[4]), ranks_agree=agree, active_columns_sorted_distinct=ok_cols)
         log.append(entry)

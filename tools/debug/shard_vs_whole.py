@@ -73,5 +73,6 @@ for t in range(steps):
         print("active columns equal:", np.array_equal(wa, sa))
         break
     if t % 10 == 0 or os.environ.get("VERBOSE"):
-        print(f"step {t}: S={a[2]} M={a[4]} L={a[8]} NU={a[10]} NR={a[11]} | shard0 XM/XRA/XRT {shards[0].engine.scalars()[14:17]}", flush=True)
+        print(f"step {t}: S={a[2]} M={a[4]} L={a[8]} NU={a[10]} NR={a[11]} status={a[12]} | shard0 XM/XRA/XRT "
+              f"{shards[0].engine.scalars()[14:17]} status {[int(h.engine.scalars()[12]) for h in shards]}", flush=True)
 print("done")
