@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       // record too long to sort there, or more recyclable segments than the exchange carries (the LOWEST ids
       // must be sent), is first rebuilt in order by all CTAs.
       int* app = xch_append_rec(c);
-      const bool repack = app[0] > LL_LOCAL_MATCH_MAX || app[0] > c.xm_cap || app[1] > c.xr_cap;  // uniform in the rank
+      const bool repack = app[0] > LL_LOCAL_MATCH_MAX || app[0] > c.xm_cap || app[1] > c.xr_cap ||
+                          app[1] > LL_LOCAL_MATCH_MAX;  // uniform in the rank
       if (repack) {
         if (b < ns) ph_shard_pack(c, c.x_send, b, ns);
         BH_SYNC();

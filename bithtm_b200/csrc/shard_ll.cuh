@@ -259,13 +259,23 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     uint32_t* s_ma = reinterpret_cast<uint32_t*>(s_above + k);  // [n / 32] columns above the bin
     const int n_words = (n + 31) >> 5;
     uint32_t* s_mm = s_ma + n_words;                             // [n / 32] members of the bin
-#pragma unroll 4
-    for (int j = t; j < ((n + 31) & ~31); j += NT) {
-      const int kb = j < n ? tk3_bin(binning, keys[j]) : 0;
-      const uint32_t a = __ballot_sync(BH_FULL, kb > bin), m = __ballot_sync(BH_FULL, j < n && kb == bin);
-      if (lane == 0) {
-        s_ma[j >> 5] = a;
-        s_mm[j >> 5] = m;
+    const int n32 = (n + 31) & ~31;
+#pragma unroll 1
+    for (int j0 = t; j0 < n32; j0 += 8 * NT) {  // 8 independent key loads in flight per thread
+      unsigned long long kv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) kv[u] = j0 + u * NT < n ? keys[j0 + u * NT] : 0ull;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * NT;
+        if (j < n32) {  // (uniform in the warp)
+          const int kb = j < n ? tk3_bin(binning, kv[u]) : 0;
+          const uint32_t a = __ballot_sync(BH_FULL, kb > bin), m = __ballot_sync(BH_FULL, j < n && kb == bin);
+          if (lane == 0) {
+            s_ma[j >> 5] = a;
+            s_mm[j >> 5] = m;
+          }
+        }
       }
     }
     __syncthreads();
@@ -405,6 +415,53 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   return true;
 }
 
+// Ascending positions of n DISTINCT ids (all < S, held in shared memory) without comparing every pair: ids are
+// bucketed by value into blockDim.x buckets (segment ids of a rank are spread evenly over [0, S): a few per
+// bucket), grouped by bucket with shared-memory counters, and ranked inside their bucket.  emit(i, pos) is called
+// once per entry.  s_grp: n ints, s_cnt: 2 * blockDim.x ints, s_scan: 32 ints of scratch.  One CTA, all threads.
+// (Counting smaller ids over the whole list -- the first version -- is n^2 / 32 warp instructions: 5.5 us for
+// the 657 matching segments of a rank at 2 shards, more for its recyclable ids.)
+template <typename F>
+__device__ __forceinline__ void ll_sort_emit(const int* s_id, int n, int S, int* s_grp, int* s_cnt, int* s_scan, F emit) {
+  const int t = threadIdx.x, NT = blockDim.x;
+  int* cnt = s_cnt;
+  int* start = s_cnt + NT;
+  const long long scale = S > 0 ? S : 1;
+  cnt[t] = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int i = t; i < n; i += NT) {
+    const long long b = (long long)s_id[i] * NT / scale;
+    atomicAdd(&cnt[b < NT ? (int)b : NT - 1], 1);
+  }
+  __syncthreads();
+  int tot;
+  const int st = block_excl_scan(cnt[t], s_scan, tot);
+  __syncthreads();
+  start[t] = st;
+  cnt[t] = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int i = t; i < n; i += NT) {
+    const int id = s_id[i];
+    const long long b0 = (long long)id * NT / scale;
+    const int b = b0 < NT ? (int)b0 : NT - 1;
+    s_grp[start[b] + atomicAdd(&cnt[b], 1)] = id;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int i = t; i < n; i += NT) {
+    const int id = s_id[i];
+    const long long b0 = (long long)id * NT / scale;
+    const int b = b0 < NT ? (int)b0 : NT - 1;
+    int pos = start[b];
+    const int e = start[b] + cnt[b];
+    for (int j = start[b]; j < e; ++j) pos += s_grp[j] < id ? 1 : 0;
+    emit(i, pos);
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------
 // Exchange 2.  ONE CTA.  The scan (ph_activate_a) appended this rank's matching segments as (id, potential,
 // connected) triples at rec[8 + 3 i] with the counter rec[0], and its recyclable segment ids at
@@ -455,32 +512,23 @@ __device__ __noinline__ void ph_shard_segs_ll(const bh_ctx& c, int* const* ll, u
 #pragma unroll 1
     for (int i = t; i < nr; i += NT) ll_put(c, ll, 2, par, 8 + 3LL * c.xm_cap + i, rids[i], seq);
   } else {
-    // sort by id by counting (ids are distinct): entry i goes to position #{ids < id_i}
+    // sort by id (ids are distinct): entry i goes to position #{ids < id_i}  (scratch: the area the gathered ids
+    // will occupy afterwards)
+    __shared__ int s_sort_scan[32];
+    const int S_ids = c.sc[BH_SC_NSEG_NEXT];
 #pragma unroll 1
     for (int i = t; i < n; i += NT) s_key[i] = trip[3 * i];
     __syncthreads();
-#pragma unroll 1
-    for (int i = t; i < n; i += NT) {
-      const int id = s_key[i];
-      int pos = 0;
-#pragma unroll 4
-      for (int j = 0; j < n; ++j) pos += s_key[j] < id ? 1 : 0;
-      ll_put(c, ll, 2, par, 8 + 3LL * pos, id, seq);
+    ll_sort_emit(s_key, n, S_ids, s_all, s_all + LL_LOCAL_MATCH_MAX, s_sort_scan, [&](int i, int pos) {
+      ll_put(c, ll, 2, par, 8 + 3LL * pos, s_key[i], seq);
       ll_put(c, ll, 2, par, 8 + 3LL * pos + 1, trip[3 * i + 1], seq);
       ll_put(c, ll, 2, par, 8 + 3LL * pos + 2, trip[3 * i + 2], seq);
-    }
-    __syncthreads();
+    });
 #pragma unroll 1
     for (int i = t; i < nr; i += NT) s_key[i] = rids[i];
     __syncthreads();
-#pragma unroll 1
-    for (int i = t; i < nr; i += NT) {
-      const int id = s_key[i];
-      int pos = 0;
-      for (int j = 0; j < nr; ++j) pos += s_key[j] < id ? 1 : 0;
-      ll_put(c, ll, 2, par, 8 + 3LL * c.xm_cap + pos, id, seq);
-    }
-    __syncthreads();
+    ll_sort_emit(s_key, nr, S_ids, s_all, s_all + LL_LOCAL_MATCH_MAX, s_sort_scan,
+                 [&](int i, int pos) { ll_put(c, ll, 2, par, 8 + 3LL * c.xm_cap + pos, s_key[i], seq); });
   }
   LL_STAMP(52, 1);
   // gather the headers

@@ -36,7 +36,8 @@ def main():
     sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
     htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy", ring_len=steps,
                                             max_segments=1 << 21, max_synapses_per_segment=64,
-                                            fused=os.environ.get("BH_FUSED", "grid"))
+                                            fused=os.environ.get("BH_FUSED", "grid"),
+                                            **({"tail_chunks": int(os.environ["TAIL_CHUNKS"])} if "TAIL_CHUNKS" in os.environ else {}))
     del perm
     sp.proximal_projection._host_permanence = None
     torch.cuda.empty_cache()
