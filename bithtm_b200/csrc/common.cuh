@@ -216,3 +216,39 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n_c
   }
   __syncthreads();
 }
+
+// The same barrier with the generation word cached by the CTA: a kernel opens the barrier once (one load of the
+// generation, before its first arrival -- nobody can complete a barrier this CTA has not arrived at) and every
+// wait then costs ONE round trip (the arrival) + the spin, instead of load + arrival + spin.
+struct GridBar {
+  unsigned int* w;   // [0] arrivals, [1] generation
+  unsigned int gen;  // the generation this CTA is in (thread 0)
+};
+__device__ __forceinline__ GridBar grid_bar_open(unsigned int* words) {
+  GridBar g;
+  g.w = words;
+  g.gen = 0u;
+  if (threadIdx.x == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g.gen) : "l"(words + 1) : "memory");
+  return g;
+}
+__device__ __forceinline__ void grid_barrier(GridBar& g, unsigned int n_ctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(g.w, 1u);
+    if (prev == n_ctas - 1) {
+      g.w[0] = 0u;
+      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(g.w + 1) : "memory");
+    } else {
+      unsigned int now;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(g.w + 1) : "memory");
+      } while (now == g.gen);
+    }
+    g.gen += 1u;
+    __threadfence();
+  }
+  __syncthreads();
+}
+

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
   const int nsel = split ? 4 : nw;
   const int nl0 = split ? nsel : 0;
   const int nlrn = nw - nl0;
-  unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
+  GridBar bar = grid_bar_open(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT));
 #define BH_SYNC()                          \
   do {                                     \
     if (MODE == 1) cluster_barrier();      \

@@ -57,7 +57,7 @@ __device__ __forceinline__ long long xch_recv_off(const bh_ctx& c, int kind, int
 
 // All CTAs of the cooperative grid: deliver send[0..n) (n a multiple of 4, 16-byte aligned,
 // complete and visible grid-wide) to every rank's receive area and wait for all ranks'.
-__device__ void xch_exchange(const bh_ctx& c, int kind, const int* send, long long n, int b, int nb, unsigned int* bar) {
+__device__ void xch_exchange(const bh_ctx& c, int kind, const int* send, long long n, int b, int nb, GridBar& bar) {
   const int G = c.seg_world, me = c.seg_rank;
   const int step = c.sc[BH_SC_STEP];
   const int seq = step + 1;
@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
   const int nw = nb > 1 ? nb - 1 : 1;
   const bool worker = b < nw;
   const bool rng = b == nb - 1;
-  unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
+  GridBar bar = grid_bar_open(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT));
+  GridBar bar2 = grid_bar_open(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT));  // the bookkeeping team's own
 #define BH_SYNC() grid_barrier(bar, (unsigned)nb)
   // phase timestamps of the last step (CTA 0): ctx.blk row 7, as 64-bit globaltimer ns (tools/cfg3_sharded.py)
   unsigned long long* stamps = reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE);
@@ -229,7 +230,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       if (b >= t0) {
         // winner bits on the whole team | the drawing CTA forms the ordered winner lists while the others flag the
         // learning segments | it plans draw #2 while they form the learning lists (team barriers in between)
-        unsigned int* bar2 = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT);
         ph_select_a(c, b - t0, team, want);
         grid_barrier(bar2, (unsigned)team);
         if (rng) ph_select_b(c, 0, 1, want, team);

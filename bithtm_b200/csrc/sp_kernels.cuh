@@ -870,7 +870,7 @@ __global__ void __launch_bounds__(TOPK_THREADS)
 #define BLK_TOPK 6
 
 __device__ __noinline__ void topk_multi(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
-                           const int* map, uint8_t* flags, int b, int nb, unsigned int* bar) {
+                           const int* map, uint8_t* flags, int b, int nb, GridBar& bar) {
   int* hist = topk_scratch().hist;
   __shared__ int s_scan[32];
   __shared__ unsigned long long s_u64[32];
@@ -1068,7 +1068,7 @@ __device__ __noinline__ void topk_multi(const bh_ctx& c, const unsigned long lon
 // Workspace: ctx.topk_ws + TK2_BASE (see the TK2_* layout above).
 // ---------------------------------------------------------------------------------
 __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
-                          const int* map, uint8_t* flags, int b, int nb, unsigned int* bar) {
+                          const int* map, uint8_t* flags, int b, int nb, GridBar& bar) {
   TopkScratch& sm = topk_scratch();
   int* hist = sm.hist;
   unsigned long long* cand_key = sm.cand_key;
@@ -1278,7 +1278,7 @@ __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long
 // prediction missed.  keys[j] is column j (unsharded networks).
 // ---------------------------------------------------------------------------------
 __device__ __noinline__ void topk_grid_hist(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
-                               uint8_t* flags, int b, int nb, unsigned int* bar) {
+                               uint8_t* flags, int b, int nb, GridBar& bar) {
   TopkScratch& sm = topk_scratch();
   int* hist = sm.hist;
   unsigned long long* cand_key = sm.cand_key;
@@ -1465,7 +1465,7 @@ __device__ __forceinline__ void tk3_rebin_sharded(const bh_ctx& c, int n) {
 
 // stand-alone cooperative kernels built on topk_multi (grid = one CTA per SM)
 __global__ void __launch_bounds__(TOPK_THREADS, 1) k_topk_multi(const __grid_constant__ bh_ctx c) {
-  unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
+  GridBar bar = grid_bar_open(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT));
   if (blockIdx.x == 0) retire_prev_flags(c);
   const int k = c.active_columns;
   topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.column_dim, k,
@@ -1474,7 +1474,7 @@ __global__ void __launch_bounds__(TOPK_THREADS, 1) k_topk_multi(const __grid_con
 
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
     k_topk_shard_local_multi(const __grid_constant__ bh_ctx c, int* scratch, double* cand_keys, int32_t* cand_cols) {
-  unsigned int* bar = reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT);
+  GridBar bar = grid_bar_open(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT));
   const int k_loc = c.active_columns < c.col_local ? c.active_columns : c.col_local;
   topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr,
             blockIdx.x, gridDim.x, bar);
