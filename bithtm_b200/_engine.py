@@ -47,7 +47,7 @@ class Engine:
                  learn_capacity=None, rand_capacity=None, ring_len=0, tm_blocks=None,
                  fused="auto", fused_ctas=None, fused_threads=None, column_shard=None, parallel_rng="auto", segment_shard=None,
                  exchange_match_capacity=None, exchange_recycle_capacity=None, lazy_rng="auto", skip_gran=None,
-                 skip_min=None, skip_polys=None, tail_chunks=None, exchange_cells="auto"):
+                 skip_min=None, skip_polys=None, tail_chunks=None, exchange_cells="auto", pipeline=None):
         """``column_shard=(rank, world)``: this engine owns columns
         [rank*C/world, (rank+1)*C/world) of the spatial pooler (permanence, mask, duty
         cycles).  ``segment_shard=(rank, world)``: it holds the synapse rows of the
@@ -184,6 +184,11 @@ class Engine:
         if fused_ctas is None:
             fused_ctas = 16 if fused == "cluster" else self.sm_count
         ctx.fused_ctas = int(fused_ctas)
+        # two-pipeline grid kernel (csrc/fused.cuh, k_step_pipe): the spatial pooler of step s+1 beside the
+        # temporal memory of step s; ``pipeline`` = CTAs of the temporal-memory team (None: BH_PIPE or off)
+        if pipeline is None:
+            pipeline = int(os.environ.get("BH_PIPE", "0"))
+        ctx.pipe_ctas = int(pipeline) if (pipeline and fused == "grid" and Ccol >= 16384) else 0
         # threads per CTA of the cluster kernel: 1024 (one CTA per SM) is fastest for ONE network; several
         # independent networks side by side (StreamBatch) run faster with smaller CTAs sharing the SMs
         if fused_threads is not None:
@@ -254,7 +259,7 @@ class Engine:
         self.seg_rows = rows
         return {
             "sp_perm": CL * I, "sp_mask": CL * x.mask_stride, "duty": CL, "overlaps": CL, "boosted": CL,
-            "active_cols": 2 * k, "col_active": C_, "col_pred": C_, "col_act": 2 * C_, "col_win": C_,
+            "active_cols": 3 * k, "col_active": C_, "col_pred": C_, "col_act": 2 * C_, "col_win": C_,
             "cell_nseg": N, "cell_maxjit": N, "cell_npred": N, "cell_widx": N,
             "seg_owner": S, "seg_count": S, "seg_pot": S, "seg_conn": S, "syn_cell": rows * E, "syn_perm": rows * E,
             "row_pred": k, "row_act": k, "row_win": k, "row_unacc": k, "winners": 2 * k * c, "unacc": k * c,

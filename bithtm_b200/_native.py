@@ -20,7 +20,8 @@ R_COUNT = 32  # int64 slots of ctx.rng64 (csrc/mt19937.cuh)
 # device scalar block indices (enum in the header)
 (SC_STEP, SC_HAVE_PREV, SC_NSEG, SC_NSEG_NEXT, SC_M, SC_W0, SC_W1, SC_L0, SC_L, SC_P, SC_NU, SC_NR,
  SC_STATUS, SC_MT_POS, SC_X_MATCH, SC_X_RECYC_AVAIL, SC_X_RECYC_TOTAL, SC_INPUT_POS, SC_BAR_COUNT, SC_BAR_GEN,
- SC_JIT_PENDING, SC_WNONE0, SC_WNONE1, SC_NGROW, SC_BAR2_COUNT, SC_BAR2_GEN, SC_NPREDCOL, SC_NPREDCOL_PREV, SC_T5_ERR) = range(29)
+ SC_JIT_PENDING, SC_WNONE0, SC_WNONE1, SC_NGROW, SC_BAR2_COUNT, SC_BAR2_GEN, SC_NPREDCOL, SC_NPREDCOL_PREV, SC_T5_ERR,
+ SC_BAR3_COUNT, SC_BAR3_GEN, SC_PIPE_SPLIT) = range(32)
 SC_COUNT = 32
 
 ST_SEG_OVERFLOW, ST_SYN_OVERFLOW, ST_MATCH_OVERFLOW, ST_LEARN_OVERFLOW, ST_RAND_OVERFLOW, ST_PRI_TIE = 1, 2, 4, 8, 16, 32
@@ -62,7 +63,7 @@ class BhCtx(C.Structure):
         ("ring_len", C.c_int32), ("fused_mode", C.c_int32),
         ("seg_rank", C.c_int32), ("seg_world", C.c_int32), ("xm_cap", C.c_int32), ("xr_cap", C.c_int32),
         ("jump_polys", C.c_int32), ("rng_lookahead", C.c_int32), ("device", C.c_int32), ("skip_polys", C.c_int32),
-        ("skip_gran", C.c_int32), ("job_cap", C.c_int32), ("lazy_policy", C.c_int32), ("tail_chunks", C.c_int32), ("xch_ll", C.c_int32), ("reserved2", C.c_int32),
+        ("skip_gran", C.c_int32), ("job_cap", C.c_int32), ("lazy_policy", C.c_int32), ("tail_chunks", C.c_int32), ("xch_ll", C.c_int32), ("pipe_ctas", C.c_int32),
         ("skip_min", C.c_int64),
         ("sp_threshold", C.c_double), ("sp_delta_on", C.c_double), ("sp_delta_off", C.c_double),
         ("tm_learn_on", C.c_double), ("tm_learn_off", C.c_double),

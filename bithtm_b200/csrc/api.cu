@@ -88,7 +88,7 @@ extern "C" size_t bh_layout(bh_ctx* x, void* base) {
   cv.take(x->duty, CL);
   cv.take(x->overlaps, CL);
   cv.take(x->boosted, CL);
-  cv.take(x->active_cols, 2 * k);
+  cv.take(x->active_cols, 3 * k);  // [2] ping-pong by step parity + the staged selection of the step ahead (k_step_pipe)
   cv.take(x->col_active, C);
   cv.take(x->col_pred, C);
   cv.take(x->col_act, 2 * C);  // ping-pong by step parity
@@ -181,6 +181,9 @@ static int check_ctx(const bh_ctx* x) {
   }
   // the cluster kernel has no phase for the chunks a many-CTA production plan leaves (fused.cuh)
   if (x->fused_mode == 1 && x->jump_polys > 0) return BH_E_UNSUPPORTED;
+  if (x->pipe_ctas != 0 && (x->fused_mode != 2 || x->pipe_ctas < 2 || x->pipe_ctas > x->fused_ctas - 1 ||
+                            x->column_dim < 16384 || x->fused_ctas > TK2_MAX_CTAS))
+    return BH_E_UNSUPPORTED;  // two-pipeline kernel: grid mode, both teams non-empty, grid-wide selection
   if (x->seg_world > 1) {
     if (x->seg_rank < 0 || x->seg_rank >= x->seg_world || x->xm_cap < 1 || x->xr_cap < 1) return BH_E_BADARG;
     if (x->fused_mode && x->fused_mode != 3) return BH_E_UNSUPPORTED;  // the exchange sits between kernels
@@ -762,6 +765,7 @@ static int prepare_fused(int mode) {
     CU_RET(cudaFuncSetAttribute(k_step_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   } else if (mode == 2) {
     CU_RET(cudaFuncSetAttribute(k_step_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU_RET(cudaFuncSetAttribute(k_step_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   } else {
     CU_RET(cudaFuncSetAttribute(k_step_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
@@ -803,7 +807,10 @@ static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_step
   } else if (x->fused_mode == 2) {
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
-    CU_RET(cudaLaunchKernelEx(&cfg, k_step_fused<2>, *x, input_fixed, n_steps, learning, want_summary));
+    if (x->pipe_ctas > 0 && n_steps > 1)  // (a single step has nothing to look ahead to)
+      CU_RET(cudaLaunchKernelEx(&cfg, k_step_pipe, *x, input_fixed, n_steps, learning, want_summary));
+    else
+      CU_RET(cudaLaunchKernelEx(&cfg, k_step_fused<2>, *x, input_fixed, n_steps, learning, want_summary));
   } else {
     const int W = x->seg_world > 1 ? x->seg_world : 1;
     for (int r = 0; r < W; ++r)
@@ -812,7 +819,7 @@ static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_step
     attr[0].val.cooperative = 1;
     CU_RET(cudaLaunchKernelEx(&cfg, k_step_shard, *x, input_fixed, n_steps, learning, want_summary));
   }
-  LAUNCHED(x->fused_mode == 1 ? "step_fused_cluster" : (x->fused_mode == 2 ? "step_fused_grid" : "step_shard"));
+  LAUNCHED(x->fused_mode == 1 ? "step_fused_cluster" : (x->fused_mode == 2 ? (x->pipe_ctas > 0 && n_steps > 1 ? "step_pipe" : "step_fused_grid") : "step_shard"));
   return 0;
 }
 

@@ -152,7 +152,8 @@ __device__ __forceinline__ int overlap_group(int mask_stride) {
 }
 
 template <bool BOOST, bool HIST = false>
-__device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* input, uint32_t* s_in, int b, int nb) {
+__device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* input, uint32_t* s_in, int b, int nb,
+                                           int step_ov = -1) {  // step_ov: the step this pass belongs to (pipelined kernel)
   __shared__ unsigned long long s_range[2];  // max key, max ~key of this CTA
   // HIST: this CTA's keys in the predicted binning (see TK3_*): TK2_BINS ints of dynamic shared memory after
   // the staged input
@@ -280,7 +281,7 @@ __device__ __forceinline__ void ph_overlap(const bh_ctx& c, const uint32_t* inpu
       c.topk_ws[TK2_BASE + TK2_VALID] = 1;
     }
     if (HIST) {  // (the barrier above also completed this CTA's shared histogram)
-      const int step = c.sc[BH_SC_STEP];
+      const int step = step_ov >= 0 ? step_ov : c.sc[BH_SC_STEP];
       int* ghist = ws3 + TK3_HIST + (step & 1) * TK2_BINS;
 #pragma unroll 1
       for (int i = threadIdx.x; i < TK2_BINS; i += blockDim.x) {
@@ -1278,7 +1279,7 @@ __device__ __noinline__ void topk_grid(const bh_ctx& c, const unsigned long long
 // prediction missed.  keys[j] is column j (unsharded networks).
 // ---------------------------------------------------------------------------------
 __device__ __noinline__ void topk_grid_hist(const bh_ctx& c, const unsigned long long* keys, const int n, const int k, int* out,
-                               uint8_t* flags, int b, int nb, GridBar& bar) {
+                               uint8_t* flags, int b, int nb, GridBar& bar, int step_ov = -1) {
   TopkScratch& sm = topk_scratch();
   int* hist = sm.hist;
   unsigned long long* cand_key = sm.cand_key;
@@ -1289,7 +1290,7 @@ __device__ __noinline__ void topk_grid_hist(const bh_ctx& c, const unsigned long
   int* ws3 = c.topk_ws + TK3_BASE;
   int* ws = c.topk_ws + TK2_BASE;
   const int t = threadIdx.x, NT = blockDim.x;
-  const int step = c.sc[BH_SC_STEP], par = step & 1;
+  const int step = step_ov >= 0 ? step_ov : c.sc[BH_SC_STEP], par = step & 1;
   int* ghist = ws3 + TK3_HIST + par * TK2_BINS;
   int* gcount = ws3 + TK3_CNT + par * 8;
   int* gidx = ws3 + TK3_IDX + par * 1024;
@@ -1414,13 +1415,13 @@ __device__ __noinline__ void topk_grid_hist(const bh_ctx& c, const unsigned long
 
 // After a selection that did not set the binning itself (topk_grid fallback): from the selected keys.
 // One CTA, in a later phase (the selection's output must be complete).
-__device__ __forceinline__ void tk3_rebin_from_selection(const bh_ctx& c) {
+__device__ __forceinline__ void tk3_rebin_from_selection(const bh_ctx& c, const int* act_ov = nullptr, int step_ov = -1) {
   __shared__ unsigned long long s_u64b[32];
   int* ws3 = c.topk_ws + TK3_BASE;
-  const int step = c.sc[BH_SC_STEP];
+  const int step = step_ov >= 0 ? step_ov : c.sc[BH_SC_STEP];
   if (ws3[TK3_READY] == step + 1) return;  // topk_grid_hist succeeded and set it
   const int k = c.active_columns;
-  const int* act = c.active_cols + (step & 1) * k;
+  const int* act = act_ov ? act_ov : c.active_cols + (step & 1) * k;
   const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(c.boosted);
   unsigned long long mn = ~0ull, mx = 0ull;
 #pragma unroll 1
@@ -1513,10 +1514,10 @@ __global__ void k_set_active(const __grid_constant__ bh_ctx c, const int32_t* __
 // 256-byte permanence segment is coalesced and the ballot is the mask word.
 // projections.py:23-24.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void sp_learn_wide(const bh_ctx& c, const uint32_t* input, int b, int nb) {
+__device__ __forceinline__ void sp_learn_wide(const bh_ctx& c, const uint32_t* input, int b, int nb, int step_ov = -1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int k = c.active_columns, I = c.input_dim, words = c.input_words;
-  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int cur = (step_ov >= 0 ? step_ov : c.sc[BH_SC_STEP]) & 1;
   const int* act = c.active_cols + cur * k;
   const double d_on = c.sp_delta_on, d_off = c.sp_delta_off, thr = c.sp_threshold;
   // work unit = a quarter / half of a long row, so that k rows spread evenly over any number of CTAs
@@ -1560,10 +1561,10 @@ __device__ __forceinline__ void sp_learn_wide(const bh_ctx& c, const uint32_t* i
 
 // Short rows (a warp covers 4 x 32 inputs per iteration, so a row needs only a few warps): the warps of
 // a CTA form teams that work on different rows at the same time.
-__device__ __forceinline__ void sp_learn_grouped(const bh_ctx& c, const uint32_t* input, int b, int nb) {
+__device__ __forceinline__ void sp_learn_grouped(const bh_ctx& c, const uint32_t* input, int b, int nb, int step_ov = -1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int k = c.active_columns, I = c.input_dim, words = c.input_words;
-  const int cur = c.sc[BH_SC_STEP] & 1;
+  const int cur = (step_ov >= 0 ? step_ov : c.sc[BH_SC_STEP]) & 1;
   const int* act = c.active_cols + cur * k;
   const double d_on = c.sp_delta_on, d_off = c.sp_delta_off, thr = c.sp_threshold;
   const int wpr = (words + 3) / 4;  // warps that have work on one row
@@ -1602,9 +1603,9 @@ __device__ __forceinline__ void sp_learn_grouped(const bh_ctx& c, const uint32_t
 // SHORT_ROWS: also compile the team variant (kernels that serve small networks); the HBM-bound grid
 // kernel keeps only the wide loop (the extra code costs it registers and 5 us per step at cfg3).
 template <bool SHORT_ROWS = true>
-__device__ __forceinline__ void ph_sp_learn(const bh_ctx& c, const uint32_t* input, int b, int nb) {
-  if (SHORT_ROWS && (c.input_words + 3) / 4 * 2 <= (int)(blockDim.x >> 5)) sp_learn_grouped(c, input, b, nb);
-  else sp_learn_wide(c, input, b, nb);
+__device__ __forceinline__ void ph_sp_learn(const bh_ctx& c, const uint32_t* input, int b, int nb, int step_ov = -1) {
+  if (SHORT_ROWS && (c.input_words + 3) / 4 * 2 <= (int)(blockDim.x >> 5)) sp_learn_grouped(c, input, b, nb, step_ov);
+  else sp_learn_wide(c, input, b, nb, step_ov);
 }
 
 __global__ void __launch_bounds__(SP_THREADS) k_sp_learn(const __grid_constant__ bh_ctx c, const uint32_t* input) {

@@ -74,6 +74,9 @@ enum {
   BH_SC_NPREDCOL,      /* columns with a predicted cell after the last activation        */
   BH_SC_NPREDCOL_PREV, /* ... before this step's learning (example.py:50, the demo's metrics) */
   BH_SC_T5_ERR,        /* a barrier wait of the tcgen05 batched overlap timed out          */
+  BH_SC_BAR3_COUNT,    /* barrier of the spatial-pooler team of the two-pipeline step kernel */
+  BH_SC_BAR3_GEN,
+  BH_SC_PIPE_SPLIT,    /* CTAs of the temporal-memory team in the current step (two-pipeline kernel)  */
   BH_SC_COUNT = 32
 };
 
@@ -136,7 +139,7 @@ typedef struct bh_ctx {
                            /* each; 0 = 4)                                                     */
   int32_t xch_ll;          /* fused_mode 3: exchanges as 8-byte {word, sequence} cells stored into */
                            /* the peers' regions (csrc/shard_ll.cuh); 0 = copy + fence + flag    */
-  int32_t reserved2;
+  int32_t pipe_ctas;  /* fused_mode 2: > 0 = two-pipeline kernel, CTAs of its temporal-memory team */
   int64_t skip_min;        /* a rand(L, W+1) of at least this many stream words may be  */
                            /* drawn lazily (fused_mode >= 2): only the rows of growing  */
                            /* segments are produced, by jumps (csrc/mt19937.cuh)        */

@@ -687,13 +687,24 @@ def _execution_modes_agree(I, C, c, k, steps, patterns, kw_a, kw_b, min_segments
     perm = torch.randn(C, I, dtype=torch.float64, device="cuda", generator=gen) * 0.1
 
     def run(kw):
+        kw = dict(kw)
+        per_launch = kw.pop("_per_launch", 0)  # > 0: steps from the device input ring, this many per kernel launch
         np.random.seed(12)
         sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
-        htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy", **common, **kw)
+        htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy",
+                                                **({"ring_len": steps} if per_launch else {}), **common, **kw)
         eng = htm.engine
         htm.temporal_memory._rng.before(eng)
-        for t in range(steps):
-            htm.process(eng.pack_input(xs[t]), return_state=False)
+        if per_launch:
+            eng.load_ring(xs)
+            left = steps
+            while left > 0:
+                m = min(left, per_launch)
+                eng.launch_graph(eng.graph(m, learning=True), m)
+                left -= m
+        else:
+            for t in range(steps):
+                htm.process(eng.pack_input(xs[t]), return_state=False)
         torch.cuda.synchronize()
         eng.check_status()
         return htm
@@ -735,6 +746,26 @@ def test_cfg3_full_size_execution_modes_agree():
     a, b = _execution_modes_agree(16384, 65536, 32, 1311, 40, 10, dict(fused="grid"), dict(fused="off"), 20000,
                                   max_segments=1 << 17, max_synapses_per_segment=128)
     assert a.engine.ctx.jump_polys > 0 and a.engine.ctx.fused_mode == 2 and b.engine.ctx.fused_mode == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_launch,team,lazy", [(2, 40, "auto"), (7, 40, "auto"), (50, 64, "auto"), (9, 24, False)])
+def test_pipelined_grid_kernel_equals_grid_kernel(per_launch, team, lazy):
+    """The two-pipeline kernel (spatial pooler of step s+1 beside the temporal memory of step s, csrc/fused.cuh
+    k_step_pipe) against the one-pipeline grid kernel over 700 steps, with 1 / 7 / 50 steps per launch (a
+    launch's first step computes its selection on the whole grid, its last one runs no look-ahead): identical
+    permanence, masks, duty cycles, overlaps, segments, synapses and stream position."""
+    a, b = _execution_modes_agree(1024, 16384, 16, 328, 700, 12,
+                                  dict(fused="grid", lazy_rng=lazy, pipeline=team, _per_launch=per_launch),
+                                  dict(fused="grid", lazy_rng=lazy), 4000, max_segments=1 << 16)
+    assert a.engine.ctx.pipe_ctas == team and b.engine.ctx.pipe_ctas == 0
+    sa, sb = a.engine.scalars(), b.engine.scalars()
+    assert np.array_equal(sa[:13], sb[:13])
+    k = a.engine.k
+    cur = (int(sa[0]) - 1) & 1
+    assert np.array_equal(a.engine.buf["active_cols"][cur * k:(cur + 1) * k].cpu().numpy(),
+                          b.engine.buf["active_cols"][cur * k:(cur + 1) * k].cpu().numpy())
+    assert np.array_equal(a.engine.buf["col_active"].cpu().numpy(), b.engine.buf["col_active"].cpu().numpy())
 
 
 @pytest.mark.gpu
