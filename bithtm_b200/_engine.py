@@ -186,9 +186,16 @@ class Engine:
         ctx.fused_ctas = int(fused_ctas)
         # two-pipeline grid kernel (csrc/fused.cuh, k_step_pipe): the spatial pooler of step s+1 beside the
         # temporal memory of step s; ``pipeline`` = CTAs of the temporal-memory team (None: BH_PIPE or off)
+        # (a launch of a single step -- the end-to-end host call -- always runs the one-pipeline kernel)
         if pipeline is None:
-            pipeline = int(os.environ.get("BH_PIPE", "0"))
-        ctx.pipe_ctas = int(pipeline) if (pipeline and fused == "grid" and Ccol >= 16384) else 0
+            pipeline = os.environ.get("BH_PIPE", "auto")
+            pipeline = pipeline if pipeline == "auto" else int(pipeline)
+        able = (fused == "grid" and Ccol >= 16384) or (fused == "shard" and ctx.xch_ll)
+        if pipeline == "auto":
+            # steady state: the SP passes scale with the CTAs they get, the TM chain is mostly dependent round trips
+            share = 0.33 if fused == "grid" else {1: 0.33, 2: 0.40, 4: 0.5}.get(self.shard_world, 0.6)
+            pipeline = int(round(ctx.fused_ctas * share)) if ctx.fused_ctas >= 64 else 0
+        ctx.pipe_ctas = int(pipeline) if (pipeline and able and 2 <= int(pipeline) < ctx.fused_ctas) else 0
         # threads per CTA of the cluster kernel: 1024 (one CTA per SM) is fastest for ONE network; several
         # independent networks side by side (StreamBatch) run faster with smaller CTAs sharing the SMs
         if fused_threads is not None:

@@ -181,9 +181,11 @@ static int check_ctx(const bh_ctx* x) {
   }
   // the cluster kernel has no phase for the chunks a many-CTA production plan leaves (fused.cuh)
   if (x->fused_mode == 1 && x->jump_polys > 0) return BH_E_UNSUPPORTED;
-  if (x->pipe_ctas != 0 && (x->fused_mode != 2 || x->pipe_ctas < 2 || x->pipe_ctas > x->fused_ctas - 1 ||
-                            x->column_dim < 16384 || x->fused_ctas > TK2_MAX_CTAS))
-    return BH_E_UNSUPPORTED;  // two-pipeline kernel: grid mode, both teams non-empty, grid-wide selection
+  if (x->pipe_ctas != 0) {  // two-pipeline kernels: both teams non-empty; grid mode with its grid-wide selection,
+                            // or the sharded step with cell exchanges
+    if (x->pipe_ctas < 2 || x->pipe_ctas > x->fused_ctas - 1 || x->fused_ctas > TK2_MAX_CTAS) return BH_E_UNSUPPORTED;
+    if (!((x->fused_mode == 2 && x->column_dim >= 16384) || (x->fused_mode == 3 && x->xch_ll))) return BH_E_UNSUPPORTED;
+  }
   if (x->seg_world > 1) {
     if (x->seg_rank < 0 || x->seg_rank >= x->seg_world || x->xm_cap < 1 || x->xr_cap < 1) return BH_E_BADARG;
     if (x->fused_mode && x->fused_mode != 3) return BH_E_UNSUPPORTED;  // the exchange sits between kernels
@@ -768,6 +770,7 @@ static int prepare_fused(int mode) {
     CU_RET(cudaFuncSetAttribute(k_step_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   } else {
     CU_RET(cudaFuncSetAttribute(k_step_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU_RET(cudaFuncSetAttribute(k_step_shard_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
   done[mode] = true;
   return 0;
@@ -817,9 +820,13 @@ static int launch_fused(const bh_ctx* x, const uint32_t* input_fixed, int n_step
       if (!x->xpeer[r]) return BH_E_BADARG;
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
-    CU_RET(cudaLaunchKernelEx(&cfg, k_step_shard, *x, input_fixed, n_steps, learning, want_summary));
+    if (x->pipe_ctas > 0 && n_steps > 1)
+      CU_RET(cudaLaunchKernelEx(&cfg, k_step_shard_pipe, *x, input_fixed, n_steps, learning, want_summary));
+    else
+      CU_RET(cudaLaunchKernelEx(&cfg, k_step_shard, *x, input_fixed, n_steps, learning, want_summary));
   }
-  LAUNCHED(x->fused_mode == 1 ? "step_fused_cluster" : (x->fused_mode == 2 ? (x->pipe_ctas > 0 && n_steps > 1 ? "step_pipe" : "step_fused_grid") : "step_shard"));
+  LAUNCHED(x->fused_mode == 1 ? "step_fused_cluster" : (x->fused_mode == 2 ? (x->pipe_ctas > 0 && n_steps > 1 ? "step_pipe" : "step_fused_grid")
+                                                               : (x->pipe_ctas > 0 && n_steps > 1 ? "step_shard_pipe" : "step_shard")));
   return 0;
 }
 

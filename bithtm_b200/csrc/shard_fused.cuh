@@ -343,3 +343,244 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
 #undef BH_SYNC
 #undef BH_STAMP
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// The shard's step as a TWO-PIPELINE kernel (see k_step_pipe in fused.cuh): the spatial pooler of step s+1 --
+// learn(s) + duty(s) | overlap(s+1) + histogram | one-CTA selection exchange(s+1) into a staging list -- on the
+// first CTAs, the temporal memory of step s -- draw 1 | bookkeeping (a sub-team) | learn | scan | one-CTA
+// segment exchange | jitter + predictions -- on the last ctx.pipe_ctas CTAs.  The two exchanges of a step then
+// overlap each other and the HBM-bound passes instead of adding up.  The teams meet once per step; one CTA
+// commits the staged active columns.  A selection whose predicted binning missed is redone after the join by
+// the whole grid with the candidate exchange (then the step counter already names that step: the code of
+// k_step_shard is used as it is).  Needs the cell exchanges (ctx.xch_ll).
+// ---------------------------------------------------------------------------------------------------------
+// the candidate exchange of k_step_shard (P1, !selected) for the step the step counter names; all CTAs
+__device__ __noinline__ void shard_select_by_candidates(const bh_ctx& c, int b, int nb, GridBar& bar) {
+  const int G = c.seg_world;
+  const int k = c.active_columns, k_loc = xch_k_loc(c);
+  const long long n1 = xch_n1(c);
+  const int par = c.sc[BH_SC_STEP] & 1;
+  const long long gid = (long long)b * blockDim.x + threadIdx.x, gsz = (long long)nb * blockDim.x;
+  int* scratch = reinterpret_cast<int*>(c.row_unacc);  // not in use: the temporal memory is between two steps
+  if (c.col_local >= XCH_TOPK_GRID_MIN) {
+    topk_grid(c, reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr, b, nb, bar);
+  } else if (b == 0) {
+    topk_core(reinterpret_cast<const unsigned long long*>(c.boosted), c.col_local, k_loc, scratch, nullptr, nullptr);
+  }
+  grid_barrier(bar, nb);
+  {
+    double* rk = reinterpret_cast<double*>(c.x_send);
+    int* rc = c.x_send + 2 * k_loc;
+#pragma unroll 1
+    for (long long i = gid; i < k_loc; i += gsz) {
+      const int pos = scratch[i];
+      rk[i] = c.boosted[pos];
+      rc[i] = c.col_lo + pos;
+    }
+  }
+  grid_barrier(bar, nb);
+  xch_exchange(c, 0, c.x_send, n1, b, nb, bar);
+  {
+    const int* recv = c.xpeer[c.seg_rank] + xch_recv_off(c, 0, par);
+#pragma unroll 1
+    for (long long i = gid; i < (long long)G * k_loc; i += gsz) {
+      const int s = (int)(i / k_loc), j = (int)(i - (long long)s * k_loc);
+      const int* rec = recv + s * n1;
+      const int lo = __ldcv(rec + 2 * j), hi = __ldcv(rec + 2 * j + 1);
+      c.xk_keys[i] = __hiloint2double(hi, lo);
+      c.xk_cols[i] = __ldcv(rec + 2 * k_loc + j);
+    }
+  }
+  grid_barrier(bar, nb);
+  if ((long long)G * k_loc >= XCH_TOPK_GRID_MIN) {
+    if (b == 0) retire_prev_flags(c);
+    topk_grid(c, reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k, c.active_cols + par * k, c.xk_cols,
+              c.col_active, b, nb, bar);
+  } else if (b == 0) {
+    retire_prev_flags(c);
+    topk_core(reinterpret_cast<const unsigned long long*>(c.xk_keys), G * k_loc, k, c.active_cols + par * k, c.xk_cols,
+              c.col_active);
+  }
+  grid_barrier(bar, nb);
+  if (b == 0) tk3_rebin_sharded(c, G > 1 ? G * k_loc : k_loc);  // binning of the next histogram from the candidates
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+    k_step_shard_pipe(const __grid_constant__ bh_ctx c, const uint32_t* input_fixed, int n_steps, int flags, int want_summary) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const int learning = flags & BH_STEP_LEARNING;
+  const bool want_jit = !(flags & BH_STEP_NO_WINNER_CELLS);
+  const bool want = learning || want_jit;
+  const int b = blockIdx.x, nb = gridDim.x;
+  const int nt = c.pipe_ctas, ns = nb - nt;   // team sizes
+  const bool sp_team = b < ns;
+  const int tb = b - ns;                       // index inside the TM team
+  const int nw = nt - 1;                       // TM CTAs running the ranged phases
+  const bool worker = !sp_team && tb < nw;
+  const bool rng = b == nb - 1;                // CTA producing the random draws
+  const int team = nt >= 17 ? 16 : (nt >= 9 ? 8 : nt);  // bookkeeping sub-team: the last CTAs of the grid
+  GridBar barA = grid_bar_open(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR_COUNT));
+  GridBar barT = grid_bar_open(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR2_COUNT));
+  GridBar barS = grid_bar_open(reinterpret_cast<unsigned int*>(c.sc + BH_SC_BAR3_COUNT));
+  GridBar barB = grid_bar_open(reinterpret_cast<unsigned int*>(c.blk + 7 * BH_BLK_STRIDE + 600));  // the sub-team's
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(c.blk + 7 * BH_BLK_STRIDE);
+  bool stamp_it = true;
+#define BH_STAMP_AT(i)                                             \
+  do {                                                             \
+    if (threadIdx.x == 0 && (b == 0 || tb == 0) && stamp_it) {     \
+      unsigned long long t_;                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));       \
+      stamps[(b == 0 ? 0 : 64) + (i)] = t_;                        \
+    }                                                              \
+  } while (0)
+  const int G = c.seg_world;
+  const int k = c.active_columns;
+  const int step0 = c.sc[BH_SC_STEP];
+  const int pos0 = c.sc[BH_SC_INPUT_POS];
+  int* stage = c.active_cols + 2 * k;
+  int* sel_flag = c.topk_ws + TK3_BASE + TK3_SELECTED;
+
+  // ---- front of the first step on the whole grid: overlap + histogram, selection exchange
+  {
+    const uint32_t* input = input_fixed ? input_fixed : c.input_ring + (long long)(pos0 % c.ring_len) * c.input_words;
+    BH_STAMP_AT(0);
+    ph_overlap<true, true>(c, input, s_dyn, b, nb, step0);
+    grid_barrier(barA, nb);
+    if (b == 0) {
+      int* llp[BH_MAX_RANKS];
+      for (int p = 0; p < (G > 1 ? G : 1); ++p) llp[p] = c.xpeer[p] + xch_legacy_ints(c);
+      const bool ok = ph_shard_select_ll(c, llp, s_dyn);
+      if (threadIdx.x == 0) *sel_flag = ok ? step0 + 1 : 0;
+    }
+    grid_barrier(barA, nb);
+    if (*sel_flag != step0 + 1) shard_select_by_candidates(c, b, nb, barA);
+    BH_STAMP_AT(1);
+  }
+  for (int step = 0; step < n_steps; ++step) {
+    const int s = step0 + step;
+    const bool more = step + 1 < n_steps;
+    stamp_it = more || n_steps == 1;
+    const uint32_t* input =
+        input_fixed ? input_fixed : c.input_ring + (long long)((pos0 + step) % c.ring_len) * c.input_words;
+    grid_barrier(barA, nb);  // the active columns of step s are committed; step s-1 is complete
+    BH_STAMP_AT(2);
+    if (sp_team) {
+      if (learning) ph_sp_learn<false>(c, input, b, ns, s);
+      ph_duty(c, b, ns);
+      BH_STAMP_AT(3);
+      if (more) {
+        const uint32_t* next = input_fixed ? input_fixed : c.input_ring + (long long)((pos0 + step + 1) % c.ring_len) * c.input_words;
+        grid_barrier(barS, ns);
+        ph_overlap<true, true>(c, next, s_dyn, b, ns, s + 1);
+        grid_barrier(barS, ns);
+        BH_STAMP_AT(4);
+        if (b == 0) {  // the selection exchange of step s+1, into the staging list
+          int* llp[BH_MAX_RANKS];
+          for (int p = 0; p < (G > 1 ? G : 1); ++p) llp[p] = c.xpeer[p] + xch_legacy_ints(c);
+          const bool ok = ph_shard_select_ll(c, llp, s_dyn, s + 1, stage);
+          if (threadIdx.x == 0) *sel_flag = ok ? s + 2 : 0;
+        }
+        BH_STAMP_AT(5);
+      }
+    } else {
+      // ---- temporal memory of step s
+      BH_STAMP_AT(0);
+      if (rng && want) {
+        ph_fill_jitter(c, s_dyn);
+        __syncthreads();
+        ph_draw(c, 1, 1, nw);
+      }
+      grid_barrier(barT, nt);
+      BH_STAMP_AT(1);
+      {  // replicated bookkeeping on the sub-team (as the team of k_step_shard); the other TM CTAs wait
+        const int t0 = nb - team;
+        if (b >= t0) {
+          if (team > 1) {
+            ph_select_a(c, b - t0, team, want);
+            grid_barrier(barB, (unsigned)team);
+            if (rng) ph_select_b(c, 0, 1, want, team);
+            else ph_learn_select_a(c, learning, b - t0, team - 1);
+            grid_barrier(barB, (unsigned)team);
+            if (rng) ph_draw(c, 2, learning, team - 1, true);
+            else ph_learn_select_b(c, learning, b - t0, team - 1);
+          }
+        }
+      }
+      grid_barrier(barT, nt);
+      BH_STAMP_AT(2);
+      const bool lazy = c.rng64[R_LAZY] != 0;
+      if (c.jump_polys > 0 && !lazy) {
+        ph_rng_chunks(c, s_dyn, tb, nt);
+        grid_barrier(barT, nt);
+      }
+      BH_STAMP_AT(3);
+      if (lazy) {
+        if (learning) ph_learn_apply(c, s_dyn, tb, nt, 1);
+        ph_rng_jumps(c, s_dyn, 0, (int)c.rng64[R_TAIL_CHUNKS], 0, 0, tb, nt);
+        grid_barrier(barT, nt);
+        ph_rng_lazy_rows(c, s_dyn, tb, nt, [&]() { grid_barrier(barT, nt); },
+                         [&](bool produce_rows) { ph_learn_grow(c, s_dyn, tb, nt, produce_rows); });
+      } else {
+        if (learning) ph_learn_apply(c, s_dyn, tb, nt);
+        grid_barrier(barT, nt);
+      }
+      BH_STAMP_AT(4);
+      const int nscan = lazy ? nt - rng_tail_ctas(c, nt) : nw;
+      if (lazy) ph_rng_lazy_tail(c, s_dyn, tb, nt);
+      ph_post(c, tb, nt);
+      if (tb < nscan) ph_activate_a(c, tb, nscan, xch_append_rec(c));
+      grid_barrier(barT, nt);
+      BH_STAMP_AT(5);
+      int* app = xch_append_rec(c);
+      const bool repack = app[0] > LL_LOCAL_MATCH_MAX || app[0] > c.xm_cap || app[1] > c.xr_cap ||
+                          app[1] > LL_LOCAL_MATCH_MAX;  // uniform in the rank
+      if (repack) {
+        if (tb < nscan) ph_shard_pack(c, c.x_send, tb, nscan);
+        grid_barrier(barT, nt);
+      }
+      if (tb == 0) {
+        int* llp[BH_MAX_RANKS];
+        for (int p = 0; p < (G > 1 ? G : 1); ++p) llp[p] = c.xpeer[p] + xch_legacy_ints(c);
+        ph_shard_segs_ll(c, llp, s_dyn, repack ? c.x_send : app, repack);
+        if (repack && threadIdx.x == 0) {
+          app[0] = 0;
+          app[1] = 0;
+        }
+      }
+      grid_barrier(barT, nt);
+      BH_STAMP_AT(6);
+      const int M = c.sc[BH_SC_X_MATCH] < c.match_capacity ? c.sc[BH_SC_X_MATCH] : c.match_capacity;
+      const bool ready3 = !want_jit || (long long)M <= c.rng64[R_READY3];
+      if (!ready3) {
+        if (rng) ph_draw(c, 3, 1, nscan);
+        grid_barrier(barT, nt);
+      } else if (rng && want_jit) {
+        ph_draw3_ready(c, nscan);
+      }
+      if (worker) ph_activate_finish(c, tb, nw, ready3, want_jit);
+      BH_STAMP_AT(7);
+    }
+    if (more) {
+      grid_barrier(barA, nb);
+      BH_STAMP_AT(sp_team ? 6 : 8);
+      if (*sel_flag == s + 2) {
+        if (b == 0) {  // commit the staged selection: flags of step s retired, those of step s+1 set, the list copied
+          retire_prev_flags(c);  // (the step counter already says s+1: "previous" is the list of step s)
+          int* out = c.active_cols + ((s + 1) & 1) * k;
+#pragma unroll 1
+          for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            const int col = stage[i];
+            out[i] = col;
+            c.col_active[col] = 1;
+          }
+        }
+      } else {
+        shard_select_by_candidates(c, b, nb, barA);  // (the step counter names step s+1 now)
+      }
+    }
+  }
+  grid_barrier(barA, nb);
+  if (want_summary) ph_summary(c, b, nb);
+  if (!input_fixed && b == 0 && threadIdx.x == 0) c.sc[BH_SC_INPUT_POS] = pos0 + n_steps;
+#undef BH_STAMP_AT
+}

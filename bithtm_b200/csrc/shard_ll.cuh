@@ -138,14 +138,17 @@ __device__ __forceinline__ int smem_lower(const int* list, int n, int key) {
 // rank alike) when the step must take the candidate exchange instead; then nothing was written but the flag.
 // smem: 2048 + 64 + 3 * LL_MEMBERS + 2 * LL_MEMBERS (u64 keys) + active_columns + k_loc + 64 ints.
 // ------------------------------------------------------------------------------------
-__device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll, uint32_t* smem) {
+// `step_ov` / `out_ov` (two-pipeline kernel): the step this selection belongs to when it runs ahead of the step
+// counter, and a staging list instead of active_cols -- then no column flag is touched here.
+__device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll, uint32_t* smem, int step_ov = -1,
+                                                int* out_ov = nullptr) {
   __shared__ int s_scan[32];
   __shared__ int s_bin, s_rem, s_ncand, s_cnt[4 * BH_MAX_RANKS];
   __shared__ unsigned long long s_kth_key, s_gmax;
   const int t = threadIdx.x, NT = blockDim.x, lane = t & 31;
   const int G = c.seg_world > 1 ? c.seg_world : 1, me = c.seg_rank;
   const int k = c.active_columns, k_loc = ll_k_loc(c), n = c.col_local;
-  const int step = c.sc[BH_SC_STEP], par = step & 1, seq = step + 1;
+  const int step = step_ov >= 0 ? step_ov : c.sc[BH_SC_STEP], par = step & 1, seq = step + 1;
   int* ws3 = c.topk_ws + TK3_BASE;
   int* ws = c.topk_ws + TK2_BASE;
   int* ghist = ws3 + TK3_HIST + par * TK2_BINS;
@@ -159,7 +162,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
   const bool have_hist = ws3[TK3_READY] == seq;
 
   LL_STAMP(40, 0);
-  retire_prev_flags(c);  // (independent of the selection; the new flags are set at the end)
+  if (!out_ov) retire_prev_flags(c);  // (independent of the selection; the new flags are set at the end)
   // a. histogram (+ the largest local key) -> everybody
   const unsigned long long lmax = w64[0];
 #pragma unroll 1
@@ -371,7 +374,8 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
     if (t == 0) s_msel[n_mem] = tot;
   }
   __syncthreads();
-  int* out = c.active_cols + par * k;
+  int* out = out_ov ? out_ov : c.active_cols + par * k;
+  const bool set_flags = out_ov == nullptr;
   // rank offsets in the final list: everything of the ranks before
   // (selected members of rank g = prefix at the end of its part - prefix at its start)
   auto pre_at = [&](int idx) { return idx < n_mem ? (s_msel[idx] & 0x3fffffff) : s_msel[n_mem]; };
@@ -386,7 +390,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
       const int pos = off + i + (pre_at(om + lb) - pre_at(om));
       if (pos < k) {
         out[pos] = col;
-        c.col_active[col] = 1;
+        if (set_flags) c.col_active[col] = 1;
       }
     }
 #pragma unroll 1
@@ -396,7 +400,7 @@ __device__ __noinline__ bool ph_shard_select_ll(const bh_ctx& c, int* const* ll,
       const int pos = off + smem_lower(s_above + oa, a, col) + (pre_at(om + i) - pre_at(om));
       if (pos < k) {
         out[pos] = col;
-        c.col_active[col] = 1;
+        if (set_flags) c.col_active[col] = 1;
       }
     }
   }

@@ -757,7 +757,7 @@ def test_pipelined_grid_kernel_equals_grid_kernel(per_launch, team, lazy):
     permanence, masks, duty cycles, overlaps, segments, synapses and stream position."""
     a, b = _execution_modes_agree(1024, 16384, 16, 328, 700, 12,
                                   dict(fused="grid", lazy_rng=lazy, pipeline=team, _per_launch=per_launch),
-                                  dict(fused="grid", lazy_rng=lazy), 4000, max_segments=1 << 16)
+                                  dict(fused="grid", lazy_rng=lazy, pipeline=0), 4000, max_segments=1 << 16)
     assert a.engine.ctx.pipe_ctas == team and b.engine.ctx.pipe_ctas == 0
     sa, sb = a.engine.scalars(), b.engine.scalars()
     assert np.array_equal(sa[:13], sb[:13])

@@ -427,12 +427,17 @@ def test_fused_shard_kernels_concurrent_on_one_gpu(name, world, steps, cells):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,k,ctas,cells", [(2, 655, 60, True), (4, 1100, 36, True), (2, 655, 60, False)])
-def test_sharded_equals_unsharded_at_scale(world, k, ctas, cells):
+@pytest.mark.parametrize("world,k,ctas,cells,per_launch,pipe", [(2, 655, 60, True, 1, 0), (4, 1100, 36, True, 1, 0),
+                                                                 (2, 655, 60, False, 1, 0), (2, 655, 60, True, 8, 24),
+                                                                 (4, 1100, 36, True, 5, 14), (2, 655, 60, True, 20, 0)])
+def test_sharded_equals_unsharded_at_scale(world, k, ctas, cells, per_launch, pipe):
     """No oracle at this size (validate sharded == unsharded): 32768
     columns x 4096 inputs, many-CTA random-stream production and the grid-wide top-k active.
     One network as a single cooperative kernel vs the same network as two shard kernels
-    running concurrently and exchanging through each other's regions."""
+    running concurrently and exchanging through each other's regions.  per_launch > 1: the shards run that
+    many steps per kernel launch from their device input rings -- with pipe > 0 as the two-pipeline shard kernel
+    (csrc/shard_fused.cuh, k_step_shard_pipe: the selection exchange of step s+1 beside the temporal memory of
+    step s, pipe CTAs for the latter)."""
     import torch
 
     import bithtm_b200 as bithtm
@@ -460,8 +465,14 @@ def test_sharded_equals_unsharded_at_scale(world, k, ctas, cells):
 
     whole = build(fused="grid")
     assert whole.engine.ctx.jump_polys > 0
-    shards = [build(column_shard=(r, world), fused="shard", fused_ctas=ctas, exchange_cells=cells) for r in range(world)]
+    ring = dict(ring_len=steps) if per_launch > 1 else {}
+    shards = [build(column_shard=(r, world), fused="shard", fused_ctas=ctas, exchange_cells=cells, pipeline=pipe, **ring)
+              for r in range(world)]
+    assert all(h.engine.ctx.pipe_ctas == pipe for h in shards)
     regions = [torch.zeros(h.engine.exchange_region_ints(), dtype=torch.int32, device="cuda") for h in shards]
+    if per_launch > 1:
+        for h in shards:
+            h.engine.load_ring(xs)
     for h in shards + [whole]:
         h.temporal_memory._rng.before(h.engine)
     for h in shards:
@@ -471,9 +482,16 @@ def test_sharded_equals_unsharded_at_scale(world, k, ctas, cells):
         words = whole.engine.pack_input(xs[t])
         whole.process(words, return_state=False)
         torch.cuda.synchronize()
-        for h, st in zip(shards, streams):
-            with torch.cuda.stream(st):
-                h.process(words, return_state=False)
+        if per_launch > 1:
+            if t % per_launch != per_launch - 1:
+                continue
+            for h, st in zip(shards, streams):  # the last per_launch steps as ONE launch per shard
+                with torch.cuda.stream(st):
+                    h.engine.launch_graph(h.engine.graph(per_launch, learning=True), per_launch)
+        else:
+            for h, st in zip(shards, streams):
+                with torch.cuda.stream(st):
+                    h.process(words, return_state=False)
         torch.cuda.synchronize()
         if t % 20 == 19 or t == steps - 1:
             ref = whole.engine.summary().copy()
