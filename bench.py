@@ -382,6 +382,9 @@ def ours(args):
     exec_mode = (f"whole step = one cooperative kernel per shard ({eng.ctx.fused_ctas} CTAs), both exchanges inside it "
                  f"over NVLink peer memory ({getattr(htm, 'exchange_transport', 'local')})" if world > 1 else
                  f"whole step = one cooperative kernel ({eng.ctx.fused_ctas} CTAs)")
+    if eng.ctx.pipe_ctas > 0:
+        exec_mode += (f"; two-pipeline schedule in multi-step launches: the spatial pooler of step s+1 on "
+                      f"{eng.ctx.fused_ctas - eng.ctx.pipe_ctas} CTAs beside the temporal memory of step s on {eng.ctx.pipe_ctas}")
 
     # phase split of the last step (globaltimer stamps of CTA 0, rank 0)
     phases = None

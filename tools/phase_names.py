@@ -14,13 +14,24 @@ PIPE_TM = ["draw 1", "winner bits", "winner lists + learning flags", "learning l
            "learn", "segment scan", "draw 3", "matching list + jitter + predictions", "waits for the SP team"]
 
 
+PIPE_SHARD_SP = ["SP learn + duty (step s)", "overlap + histogram (step s+1)", "selection exchange (step s+1)",
+                 "waits for the TM team"]
+PIPE_SHARD_TM = ["draw 1", "bookkeeping (sub-team)", "stream production", "learn", "segment scan", "segment exchange + merge",
+                 "draw 3 + jitter + predictions", "waits for the SP team"]
+
+
 def read(eng):
+    if eng.ctx.fused_mode == 3 and eng.ctx.pipe_ctas > 0:
+        raw = eng.buf["blk"][7 * 1024:7 * 1024 + 2 * 80].cpu().numpy().view(np.uint64).astype(np.float64)
+        sp = {n: round(float(v) / 1e3, 2) for n, v in zip(PIPE_SHARD_SP, np.diff(raw[2:7]))}
+        tm = {n: round(float(v) / 1e3, 2) for n, v in zip(PIPE_SHARD_TM, np.diff(raw[64:73]))}
+        return {"SP team": sp, "TM team": tm}
     if eng.ctx.fused_mode == 2 and eng.ctx.pipe_ctas > 0:
         # two-pipeline kernel: the last pipelined iteration of the last launch; both teams start together
         raw = eng.buf["blk"][7 * 1024:7 * 1024 + 2 * 80].cpu().numpy().view(np.uint64).astype(np.float64)
         sp = {n: round(float(v) / 1e3, 2) for n, v in zip(PIPE_SP, np.diff(raw[2:7]))}
         tm = {n: round(float(v) / 1e3, 2) for n, v in zip(PIPE_TM, np.diff(raw[64:75]))}
-        return {"SP team": sp, "TM team": tm, "commit + barrier": round(float(raw[2] - raw[6]) / 1e3, 2) if raw[2] > raw[6] else None}
+        return {"SP team": sp, "TM team": tm}
     names = SHARD if eng.ctx.fused_mode == 3 else FUSED_GRID
     st = eng.buf["blk"][7 * 1024:7 * 1024 + 2 * (len(names) + 1)].cpu().numpy().view(np.uint64).astype(np.float64)
     return {n: round(float(v) / 1e3, 2) for n, v in zip(names, np.diff(st))}
