@@ -90,6 +90,7 @@ def measure(Ccol=65536, I=16384, warm=250, profiled=20):
     fused_us = a.elapsed_time(b) * 1e3 / (2 * per)
     # the same step one kernel per stage (the library is stateless: the mode is a field of the context)
     eng.ctx.fused_mode = 0
+    eng.ctx.pipe_ctas = 0  # (a field of the fused kernels)
     prof, order = {}, []
     for t in range(profiled):
         for name, ms in eng.profile_step(words[t % len(words)], learning=True):
