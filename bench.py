@@ -379,6 +379,7 @@ def ours(args):
     clocks = sampler.stop()
     stats = network_stats(eng)
     check = state_check(htm)
+    eng_pipe = int(eng.ctx.pipe_ctas)
     exec_mode = (f"whole step = one cooperative kernel per shard ({eng.ctx.fused_ctas} CTAs), both exchanges inside it "
                  f"over NVLink peer memory ({getattr(htm, 'exchange_transport', 'local')})" if world > 1 else
                  f"whole step = one cooperative kernel ({eng.ctx.fused_ctas} CTAs)")
@@ -402,12 +403,13 @@ def ours(args):
 
     # ---------------- roofline of the step kernel (this rank's share of the algorithmic bytes)
     peak, peak_src = hbm_peak()
-    kernel = "step_shard" if world > 1 else "step_fused_grid"
+    piped = eng_pipe > 0
+    kernel = ("step_shard_pipe" if piped else "step_shard") if world > 1 else ("step_pipe" if piped else "step_fused_grid")
     ab_total = algorithmic_bytes(cfg, "step_fused_grid", stats)
     ab = ab_total / world
     step_s = dev_s / K
     achieved = ab / step_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_step_shard" if world > 1 else "k_step_fused<2>", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "k_" + kernel if kernel != "step_fused_grid" else "k_step_fused<2>", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(kernel) if world == 1 else None,  # (ncu profiles one GPU)
                 "peak_source": peak_src, "algorithmic_bytes_per_launch_step": ab,

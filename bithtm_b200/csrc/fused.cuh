@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
   const int k = c.active_columns;
   const bool zero_copy = want_summary == 2;
   bool stamp_it = true;  // (the stamps describe the last PIPELINED iteration of a launch)
+  bool drew1 = false;    // draw #1 of the coming step was taken at the end of the previous one
   int* stage = c.active_cols + 2 * k;  // the selection of the step ahead
   const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(c.boosted);
 
@@ -299,12 +300,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       const bool worker = tb < nw;
       // ---- temporal memory of step s (phases as in k_step_fused<2>, on nt CTAs)
       BH_STAMP_AT(0);
-      if (rng && want) {
-        ph_fill_jitter(c, s_dyn);
-        __syncthreads();
-        ph_draw(c, 1, 1, nw);
+      if (!drew1) {  // (else the drawing CTA took draw #1 at the end of the previous step, see below)
+        if (rng && want) {
+          ph_fill_jitter(c, s_dyn);
+          __syncthreads();
+          ph_draw(c, 1, 1, nw);
+        }
+        grid_barrier(barT, nt);
       }
-      grid_barrier(barT, nt);
       BH_STAMP_AT(1);
       if (worker) ph_select_a(c, tb, nw, want);
       if (rng) ph_rng_speculate(c, 2);
@@ -361,8 +364,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
       BH_STAMP_AT(8);
       if (want_jit && ready3 && rng) ph_draw3_ready(c, nscan, m_total);
       if (scanner) ph_activate_b(c, tb, nscan, ready3, want_jit, m_before, m_total);
+      // the next step's rand(k, c) follows this step's rand(M) in the stream: with the jitter drawn every step
+      // (nothing can be pending) the drawing CTA takes it now, and the next step starts with its winner bits
+      if (more && want_jit && rng) ph_draw(c, 1, 1, nw);
       BH_STAMP_AT(9);
     }
+    drew1 = more && want_jit;
     if (more) {
       grid_barrier(barA, nb);
       BH_STAMP_AT(sp_team ? 6 : 10);

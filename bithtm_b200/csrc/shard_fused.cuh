@@ -485,16 +485,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
     } else {
       // ---- temporal memory of step s
       BH_STAMP_AT(0);
-      if (rng && want) {
-        ph_fill_jitter(c, s_dyn);
-        __syncthreads();
-        ph_draw(c, 1, 1, nw);
-      }
-      grid_barrier(barT, nt);
-      BH_STAMP_AT(1);
-      {  // replicated bookkeeping on the sub-team (as the team of k_step_shard); the other TM CTAs wait
+      {  // replicated bookkeeping on the sub-team (as the team of k_step_shard); the other TM CTAs wait.
+         // Draw #1 is the drawing CTA's first act there: only the sub-team waits for it.
         const int t0 = nb - team;
         if (b >= t0) {
+          if (rng && want) {
+            ph_fill_jitter(c, s_dyn);
+            __syncthreads();
+            ph_draw(c, 1, 1, nw);
+          }
+          grid_barrier(barB, (unsigned)team);
+          BH_STAMP_AT(1);
           if (team > 1) {
             ph_select_a(c, b - t0, team, want);
             grid_barrier(barB, (unsigned)team);

@@ -689,6 +689,7 @@ def _execution_modes_agree(I, C, c, k, steps, patterns, kw_a, kw_b, min_segments
     def run(kw):
         kw = dict(kw)
         per_launch = kw.pop("_per_launch", 0)  # > 0: steps from the device input ring, this many per kernel launch
+        flags = kw.pop("_flags", True)          # the `learning` flag word of the launches (BH_STEP_*)
         np.random.seed(12)
         sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
         htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync="lazy",
@@ -700,7 +701,7 @@ def _execution_modes_agree(I, C, c, k, steps, patterns, kw_a, kw_b, min_segments
             left = steps
             while left > 0:
                 m = min(left, per_launch)
-                eng.launch_graph(eng.graph(m, learning=True), m)
+                eng.launch_graph(eng.graph(m, learning=flags), m)
                 left -= m
         else:
             for t in range(steps):
@@ -766,6 +767,15 @@ def test_pipelined_grid_kernel_equals_grid_kernel(per_launch, team, lazy):
     assert np.array_equal(a.engine.buf["active_cols"][cur * k:(cur + 1) * k].cpu().numpy(),
                           b.engine.buf["active_cols"][cur * k:(cur + 1) * k].cpu().numpy())
     assert np.array_equal(a.engine.buf["col_active"].cpu().numpy(), b.engine.buf["col_active"].cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_pipelined_grid_kernel_without_winner_cells():
+    """The same with learning on and return_winner_cell off (flag word 3): the jitter draw of every step stays
+    pending until the next one (no early draw #1 in the two-pipeline kernel), 300 steps, 6 per launch."""
+    _execution_modes_agree(1024, 16384, 16, 328, 300, 12,
+                           dict(fused="grid", pipeline=40, _per_launch=6, _flags=3),
+                           dict(fused="grid", pipeline=0, _per_launch=1, _flags=3), 2000, max_segments=1 << 16)
 
 
 @pytest.mark.gpu
