@@ -24,7 +24,10 @@ def read(eng):
     if eng.ctx.fused_mode == 3 and eng.ctx.pipe_ctas > 0:
         raw = eng.buf["blk"][7 * 1024:7 * 1024 + 2 * 80].cpu().numpy().view(np.uint64).astype(np.float64)
         sp = {n: round(float(v) / 1e3, 2) for n, v in zip(PIPE_SHARD_SP, np.diff(raw[2:7]))}
-        tm = {n: round(float(v) / 1e3, 2) for n, v in zip(PIPE_SHARD_TM, np.diff(raw[64:73]))}
+        # (stamp 1 -- after draw 1 -- is taken inside the bookkeeping sub-team, which the stamping CTA is not part
+        # of when the TM team is larger than the sub-team: draw 1 and the bookkeeping are reported together)
+        tmr = np.concatenate([raw[64:65], raw[66:73]])
+        tm = {n: round(float(v) / 1e3, 2) for n, v in zip(["draw 1 + bookkeeping (sub-team)"] + PIPE_SHARD_TM[2:], np.diff(tmr))}
         return {"SP team": sp, "TM team": tm}
     if eng.ctx.fused_mode == 2 and eng.ctx.pipe_ctas > 0:
         # two-pipeline kernel: the last pipelined iteration of the last launch; both teams start together
