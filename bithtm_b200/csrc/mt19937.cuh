@@ -517,9 +517,22 @@ __device__ __noinline__ void ph_rng_jumps(const bh_ctx& c, uint32_t* smem, int k
   uint32_t* s_out = smem + RNG_UNIT_WIN_PAD;  // [MT_N]
   const int t = threadIdx.x, NT = blockDim.x;
   const long long base = c.rng64[R_JUMP_BASE];
-  int uw = (int)(((long long)n_jobs * MT_N + nb - 1) / nb);
-  uw = (uw + 5) / 6 * 6;
-  uw = uw < 6 ? 6 : (uw > RNG_UNIT_MAX ? RNG_UNIT_MAX : uw);
+  // unit size: the multiple of 6 words that minimises rounds x (words per unit + a fixed cost per unit) -- with
+  // fewer CTAs than units of the largest size, a smaller unit avoids a last round that only a few CTAs work in
+  // (8 jobs on 92 CTAs: 104 units of 48 words = 2 rounds of 48; 168 units of 30 words = 2 rounds of 30)
+  int uw = 6;
+  {
+    long long best = -1;
+#pragma unroll 1
+    for (int cand = 6; cand <= RNG_UNIT_MAX; cand += 6) {
+      const long long units = (long long)n_jobs * ((MT_N + cand - 1) / cand);
+      const long long cost = (units + nb - 1) / nb * (cand + 12);
+      if (best < 0 || cost < best) {
+        best = cost;
+        uw = cand;
+      }
+    }
+  }
   const int per_poly = (MT_N + uw - 1) / uw, per_group = uw / 6;
   const long long n_units = (long long)n_jobs * per_poly;
 #pragma unroll 1
