@@ -3,7 +3,8 @@
 // barriers.  MODE 1: the grid is a single thread-block cluster (hardware
 // barrier.cluster, for networks whose step is latency-bound); MODE 2: a cooperative
 // grid with one CTA per SM and a global-memory barrier (HBM-bound sizes).
-// One launch can run several consecutive steps from the device input ring.
+// One launch can run several consecutive steps from the device input ring; such launches of large networks use
+// k_step_pipe (end of this file): the same phases as two pipelines on two teams of CTAs.
 #pragma once
 
 #include "sp_kernels.cuh"

@@ -14,6 +14,8 @@
 //   segs  [2 parity][G][n4]    n4 = bh_tm_shard_xch_ints rounded up to 4
 // Records are double-buffered by step parity: a rank can be at most one exchange ahead
 // of a peer, because finishing an exchange needs every peer's record of that exchange.
+// After it (xch_ll) the cell areas of shard_ll.cuh.  k_step_shard: one pipeline; k_step_shard_pipe (end of this
+// file): the selection exchange of step s+1 beside the temporal memory of step s, for launches of several steps.
 #pragma once
 
 #include "fused.cuh"
