@@ -382,7 +382,8 @@ def ours(args):
     eng_pipe = int(eng.ctx.pipe_ctas)
     exec_mode = (f"whole step = one cooperative kernel per shard ({eng.ctx.fused_ctas} CTAs), both exchanges inside it "
                  f"over NVLink peer memory ({getattr(htm, 'exchange_transport', 'local')})" if world > 1 else
-                 f"whole step = one cooperative kernel ({eng.ctx.fused_ctas} CTAs)")
+                 f"whole step = one cooperative kernel ({eng.ctx.fused_ctas} CTAs"
+                 f"{', one thread-block cluster' if eng.ctx.fused_mode == 1 else ''})")
     if eng.ctx.pipe_ctas > 0:
         exec_mode += (f"; two-pipeline schedule in multi-step launches: the spatial pooler of step s+1 on "
                       f"{eng.ctx.fused_ctas - eng.ctx.pipe_ctas} CTAs beside the temporal memory of step s on {eng.ctx.pipe_ctas}")
@@ -460,8 +461,10 @@ def ours(args):
             "regime": (f"steady state: the network ran {max(P, W + K)} timesteps of the same input stream before the "
                        f"{W} warm-up steps (setup); `from_scratch` is the same measurement on the first {W}+{K} steps "
                        "of a fresh network"),
-            "l2": "no flush needed: one step streams > 500 MB (connected mask 134 MB + 1311 random 128 KiB permanence "
-                  "rows + the segment store), 4x the 126 MB L2",
+            "l2": ("no flush needed: one step streams > 500 MB (connected mask 134 MB + 1311 random 128 KiB permanence "
+                   "rows + the segment store), 4x the 126 MB L2") if cfg is CFG3 else
+                  ("NOT flushed: this small network's working set (3 MB) stays in L2 between the steps of a launch; "
+                   "the flushed measurement of this size is `latency_cfg2` of the default run"),
             "inputs": "device-resident ring of 100 packed inputs, up to 50 steps per kernel launch",
             "from_scratch": {"value": K / scratch_s, "unit": UNIT, "ms_per_step": scratch_s / K * 1e3,
                              "state": scratch_stats},
