@@ -256,7 +256,7 @@ def build_network(cfg, rank, world, ring_len, rng_sync, fused=None):
     np.random.seed(cfg["seed"])
     sp = bithtm.SpatialPooler(I, C, k, proximal_projection=DenseProjection(I, C, permanence=perm))
     if fused is None:
-        fused = "shard" if world > 1 else "grid"
+        fused = "shard" if world > 1 else ("grid" if cfg is CFG3 else "auto")  # (small networks: the cluster kernel)
     htm = bithtm.HierarchicalTemporalMemory(I, C, c, k, spatial_pooler=sp, rng_sync=rng_sync, ring_len=ring_len,
                                             column_shard=True if world > 1 else None,
                                             max_segments=min(1 << 21, 8 * C * c), max_synapses_per_segment=64,
@@ -379,7 +379,7 @@ def ours(args):
     clocks = sampler.stop()
     stats = network_stats(eng)
     check = state_check(htm)
-    eng_pipe = int(eng.ctx.pipe_ctas)
+    eng_pipe, eng_mode = int(eng.ctx.pipe_ctas), int(eng.ctx.fused_mode)
     exec_mode = (f"whole step = one cooperative kernel per shard ({eng.ctx.fused_ctas} CTAs), both exchanges inside it "
                  f"over NVLink peer memory ({getattr(htm, 'exchange_transport', 'local')})" if world > 1 else
                  f"whole step = one cooperative kernel ({eng.ctx.fused_ctas} CTAs"
@@ -406,11 +406,14 @@ def ours(args):
     peak, peak_src = hbm_peak()
     piped = eng_pipe > 0
     kernel = ("step_shard_pipe" if piped else "step_shard") if world > 1 else ("step_pipe" if piped else "step_fused_grid")
+    if world == 1 and eng_mode == 1:
+        kernel = "step_fused_cluster"
     ab_total = algorithmic_bytes(cfg, "step_fused_grid", stats)
     ab = ab_total / world
     step_s = dev_s / K
     achieved = ab / step_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_" + kernel if kernel != "step_fused_grid" else "k_step_fused<2>", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": {"step_fused_grid": "k_step_fused<2>", "step_fused_cluster": "k_step_fused<1>"}.get(kernel, "k_" + kernel),
+                "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(kernel) if world == 1 else None,  # (ncu profiles one GPU)
                 "peak_source": peak_src, "algorithmic_bytes_per_launch_step": ab,
