@@ -99,7 +99,11 @@ typedef struct bh_ctx {
   int32_t input_words;     /* ceil(I / 32)                                         */
   int32_t mask_stride;     /* uint32 words per connected-mask row, multiple of 4   */
   int32_t column_dim;      /* C                                                    */
-  int32_t cell_dim;        /* c, 1..32                                             */
+  int32_t cell_dim;        /* c, 1..32.  CAP: a column's cells are the bits of ONE 32-bit word in   */
+                           /* col_pred / col_act / col_win, the row words of the step summary and the */
+                           /* warp ballots that form winner cells (lane = cell); the reference accepts  */
+                           /* any cell_dim (networks.py:48-55), its default and every BASELINE config  */
+                           /* use 32.  bh_layout / check_ctx return BH_E_UNSUPPORTED beyond 32.          */
   int32_t active_columns;  /* k                                                    */
   int32_t seg_capacity;    /* S_cap                                                */
   int32_t syn_capacity;    /* E_cap: synapse slots per segment, multiple of 32     */
