@@ -194,7 +194,7 @@ class Engine:
         if pipeline == "auto":
             # steady state: the SP passes scale with the CTAs they get, the TM chain is mostly dependent round trips;
             # the more shards, the less SP work per rank and the larger the TM team should be (measured at cfg3)
-            share = 0.31 if fused == "grid" else {1: 0.31, 2: 0.40, 4: 0.62}.get(self.shard_world, 0.75)
+            share = 0.31 if fused == "grid" else {1: 0.31, 2: 0.35, 4: 0.62}.get(self.shard_world, 0.75)
             pipeline = int(round(ctx.fused_ctas * share)) if ctx.fused_ctas >= 64 else 0
         ctx.pipe_ctas = int(pipeline) if (pipeline and able and 2 <= int(pipeline) < ctx.fused_ctas) else 0
         # threads per CTA of the cluster kernel: 1024 (one CTA per SM) is fastest for ONE network; several
